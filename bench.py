@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — decode tok/s of the quantized-forward hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one decoded token (batch 1) through the whole hot path: embedding row,
+L x [RMSNorm+QKV dequant-GEMV, RoPE+KV write, GQA attention, O GEMV, RMSNorm+gate/up
+GEMV+SwiGLU, down GEMV], final norm + vocab GEMV.  Workload (config.workload): the
+configuration the metric is quoted on — Llama-3-8B architecture, Q4_K_M tensor-type mix,
+random-init GGUF blocks (synthetic), batch 1, 8K context window, 128-token prompt.
+
+  value  : tokens/s with everything resident in HBM (device-side greedy argmax, CUDA-graph
+           replay, no host round trip), timed with CUDA events on the launching stream.
+  e2e    : the same metric through the reference-facing call GpuInference::forward —
+           token id from host memory in, `vocab` f32 logits to host memory out, host argmax
+           (src/main.rs:1811-1822) — wall clock around the K calls.
+  roofline     : the dequant-GEMV kernel (gemv_kernel): weight bytes one token's GEMV launches
+           read / the time of exactly those launches replayed back to back (CUDA events).
+  cpu_baseline : the C++ restatement of the reference's CPU path (oracle/) on this box's cores.
+
+--impl reference times that CPU restatement (the reference is Rust; no rustc in the image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode_tokens_per_sec"
+UNIT = "tok/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.lines, self.proc, self.gpu_index = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_argmax_last(v):
+    """max_by(partial_cmp): the LAST maximal element wins (src/main.rs:1816-1821)."""
+    m = v.max()
+    return int(v.size - 1 - np.argmax(v[::-1] == m))
+
+
+# --------------------------------------------------------------------------- reference arm
+def sampled_preset(preset, n_layers_sample):
+    p = dict(preset)
+    p["n_layers"] = min(preset["n_layers"], n_layers_sample)
+    return p
+
+
+def model_weight_bytes(preset, mix):
+    from llama_gguf_b200.presets import tensor_plan
+    from llama_gguf_b200.randmodel import BLOCK
+
+    total = 0
+    E, k = preset.get("n_experts", 0), preset.get("n_experts_used", 0)
+    for name, t, ne in tensor_plan(preset, mix):
+        be, bb = BLOCK[t]
+        nbytes = int(np.prod(ne)) // be * bb
+        if name == "token_embd.weight":
+            nbytes = (ne[0] // be * bb) + (nbytes if preset.get("tied") else 0)
+        if "_exps." in name:
+            nbytes = nbytes // E * k
+        total += nbytes
+    return total
+
+
+def run_cpu_reference(preset, mix, ctx_len, prompt_len, steps, warmup, n_layers_sample, seed):
+    """Times the oracle's LlamaModel::forward (one decoded token per step) on a layer-bounded sample of the
+    workload and scales by weight bytes to the full model.  Returns (tok/s, info)."""
+    import oracle as O
+    from llama_gguf_b200.randmodel import random_model
+
+    O.build()
+    ps = sampled_preset(preset, n_layers_sample)
+    desc, tensors = random_model(ps, mix, ctx_len, seed=seed)
+    ref = O.OracleModel(desc, tensors)
+    cores = O.num_threads()
+    tok = 1
+    for i in range(min(prompt_len, 4)):  # short prompt: the CPU arm measures decode steps, not prefill
+        ref.forward([(i * 7919 + 1) % desc["vocab"]], want_logits=False)
+    for _ in range(warmup):
+        tok = O.argmax_last(ref.forward([tok]))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tok = O.argmax_last(ref.forward([tok]))
+    dt = time.perf_counter() - t0
+    frac = model_weight_bytes(ps, mix) / model_weight_bytes(preset, mix)
+    ms_sample = dt / steps * 1e3
+    ms_full = ms_sample / frac
+    info = {"cores": cores, "kind": "port",
+            "sample": (f"{steps} greedy decode tokens through {ps['n_layers']} of {preset['n_layers']} layers + full vocab head "
+                       f"({frac * 100:.1f}% of the per-token weight bytes), time scaled by weight bytes to the full model; "
+                       f"C++ restatement of the reference CPU path (scalar quant dots, threads over output rows), "
+                       f"hot-path-only embedding (one row per token)"),
+            "ms_per_step_sample": ms_sample, "avx512": bool(O.lib().orc_has_avx512())}
+    return 1000.0 / ms_full, info, ms_full
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--mix", default="Q4_K_M")
+    ap.add_argument("--ctx", type=int, default=8192)
+    ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--cpu-layers", type=int, default=4, help="layers in the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1236)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from llama_gguf_b200.presets import PRESETS
+
+    preset = PRESETS[args.model]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"{args.model} arch, {args.mix} random-init GGUF blocks, batch-1 greedy decode after a "
+                f"{args.prompt_len}-token prompt, {args.ctx}-token context window (f32 KV)")
+    config = {"workload": workload, "model_arch": args.model, "quant_mix": args.mix, "batch": 1, "context_window": args.ctx,
+              "prompt_len": args.prompt_len, "parallelism": f"tp{args.gpus}" if args.gpus > 1 else "single-gpu",
+              "l2_policy": "inputs larger than L2: each step streams the whole weight set (>= 4.6 GB) through the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, info, ms_full = run_cpu_reference(preset, args.mix, args.ctx, args.prompt_len, args.steps, args.warmup,
+                                             args.cpu_layers, args.seed)
+        info["value"] = v
+        info["unit"] = UNIT
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config, "cpu_baseline": info,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+
+    import llama_gguf_b200 as B
+    from llama_gguf_b200.randmodel import random_model
+
+    if not torch.cuda.is_available() or B.device_count() == 0:
+        log("bench.py: no CUDA device — cuda-b200 has no CPU fallback")
+        return 2
+    if world > 1 or args.gpus > 1:
+        import bench_tp  # tensor-parallel arm lives in its own module
+
+        return bench_tp.main(args, preset, config, rank, world, local_rank)
+
+    torch.cuda.set_device(0)
+    t0 = time.time()
+    from llama_gguf_b200.presets import make_desc
+
+    desc = make_desc(preset, args.ctx)
+    # tensors are streamed straight into the context (host memory stays at one tensor)
+    gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up))
+    log(f"model built and uploaded in {time.time() - t0:.1f} s")
+    st0 = gpu.stats()
+    wbytes, kvpp = st0["weight_bytes_per_token"], st0["kv_bytes_per_pos"]
+
+    # prompt (untimed)
+    for i in range(args.prompt_len):
+        gpu.prefill_token((i * 7919 + 1) % desc["vocab"])
+    tok = host_argmax_last(gpu.forward(1))
+
+    # ---- value: device-resident greedy decode, CUDA events ----
+    toks, _ = gpu.decode_greedy(tok, args.warmup)
+    tok = int(toks[-1])
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    torch.cuda.synchronize()
+    l0 = gpu.stats()["kernel_launches"]
+    kv_len_mid = gpu.position() + args.steps // 2
+    toks, ms = gpu.decode_greedy(tok, args.steps)
+    torch.cuda.synchronize()
+    launches = gpu.stats()["kernel_launches"] - l0
+    tok = int(toks[-1])
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e: GpuInference::forward with host token / host logits ----
+    for _ in range(args.warmup):
+        tok = host_argmax_last(gpu.forward(tok))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        tok = host_argmax_last(gpu.forward(tok))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    clocks = sampler.stop()
+    e2e_val = args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (gemv_kernel) ----
+    peaks, peaks_kind = measured_peaks()
+    gms, glaunches, gbytes = gpu.bench_gemv_pass(20)
+    achieved = gbytes / (gms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemv_dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)",
+                "traffic": traffic, "bytes_per_launch": gbytes / glaunches, "avg_launch_us": gms * 1e3 / glaunches,
+                "launches_per_token": glaunches, "gemv_ms_per_token": gms,
+                "whole_token_frac": (wbytes + kvpp * kv_len_mid) / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- CPU baseline (bounded sample, rank 0) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, info, _ = run_cpu_reference(preset, args.mix, args.ctx, args.prompt_len, args.cpu_steps, 1, args.cpu_layers,
+                                           args.seed)
+            info["value"], info["unit"] = v, UNIT
+            cpu = info
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": desc["vocab"] * 4},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "weight_bytes_per_token": wbytes, "kv_bytes_per_token_at_mid": kvpp * kv_len_mid}
+    print(json.dumps(out))
+    gpu.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

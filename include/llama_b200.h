@@ -1,0 +1,171 @@
+/* llama_b200.h — C ABI of the `cuda-b200` backend for Lexmata/llama-gguf.
+ *
+ * This is the drop-in boundary: a Rust shim binds these symbols
+ * with `extern "C"` and implements the crate's `GpuInference` trait
+ * (src/backend/mod.rs:283-296) and `Backend` trait (src/backend/mod.rs:29-265)
+ * on top of them.  Plain pointers and sizes only; every host pointer is read or
+ * written DURING the call and never retained (the Rust side owns `Vec<u8>`).
+ *
+ * All functions return 0 on success or a negative b200_status; the message is
+ * available from b200_last_error() (thread-local).  No exceptions cross the ABI.
+ */
+#ifndef LLAMA_B200_H
+#define LLAMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 1:1 with BackendError's variants (src/backend/error.rs:3-37). */
+typedef enum b200_status {
+    B200_OK = 0,
+    B200_ERR_NOT_AVAILABLE = -1,         /* BackendError::NotAvailable */
+    B200_ERR_SHAPE_MISMATCH = -2,        /* BackendError::ShapeMismatch */
+    B200_ERR_DTYPE_MISMATCH = -3,        /* BackendError::DTypeMismatch */
+    B200_ERR_UNSUPPORTED_DTYPE = -4,     /* BackendError::UnsupportedDType */
+    B200_ERR_UNSUPPORTED = -5,           /* BackendError::Unsupported */
+    B200_ERR_INVALID_ARGUMENT = -6,      /* BackendError::InvalidArgument */
+    B200_ERR_TENSOR = -7,                /* BackendError::Tensor */
+    B200_ERR_INITIALIZATION_FAILED = -8, /* BackendError::InitializationFailed */
+    B200_ERR_ALLOCATION_FAILED = -9,     /* BackendError::AllocationFailed */
+    B200_ERR_OPERATION_FAILED = -10      /* BackendError::OperationFailed */
+} b200_status;
+
+/* ggml type ids as stored in GGUF (src/gguf/constants.rs:56-89; DType mirrors
+ * them, src/tensor/dtype.rs:175-210). */
+enum {
+    B200_TYPE_F32 = 0, B200_TYPE_F16 = 1, B200_TYPE_Q4_0 = 2, B200_TYPE_Q5_0 = 6, B200_TYPE_Q8_0 = 8,
+    B200_TYPE_Q4_K = 12, B200_TYPE_Q5_K = 13, B200_TYPE_Q6_K = 14
+};
+
+/* What GpuOnlyInference::from_model reads out of ModelConfig
+ * (src/backend/cuda/gpu_only.rs:426-520; src/model/loader.rs:62-300). */
+typedef struct b200_model_desc {
+    int32_t hidden;         /* {arch}.embedding_length */
+    int32_t n_layers;       /* {arch}.block_count */
+    int32_t n_heads;        /* {arch}.attention.head_count */
+    int32_t n_kv_heads;     /* {arch}.attention.head_count_kv */
+    int32_t head_dim;       /* key_length; 0 = hidden / n_heads (loader.rs:116-118) */
+    int32_t ffn;            /* {arch}.feed_forward_length */
+    int32_t vocab;          /* {arch}.vocab_size */
+    int32_t max_seq_len;    /* min({arch}.context_length, EngineConfig::max_context_len) */
+    float norm_eps;         /* attention.layer_norm_rms_epsilon (default 1e-5) */
+    float rope_base;        /* rope.freq_base */
+    float rope_scale;       /* rope.scale_linear; the position is DIVIDED by it (cpu/ops.rs:1300) */
+    int32_t rope_neox;      /* 1 = pairs (i, i+hd/2) [qwen2]; 0 = pairs (2i, 2i+1) [llama] */
+    int32_t n_experts;      /* 0 = dense FFN */
+    int32_t n_experts_used; /* top-k */
+    int32_t expert_ffn;     /* per-expert intermediate size (0 = ffn) */
+    int32_t tied_output;    /* 1 = no output.weight; logits use token_embd (loader.rs:349-355) */
+    int32_t max_batch;      /* number of independent sequence slots (>= 1) */
+} b200_model_desc;
+
+/* Tensor-parallel placement of this context: one context per rank/GPU.
+ * Mirrors ShardingPlan::from_config's divisibility rules
+ * (src/backend/tensor_parallel.rs:69-106). world_size == 1 -> no collectives. */
+typedef struct b200_parallel_desc {
+    int32_t world_size;
+    int32_t rank;
+    int32_t device; /* CUDA ordinal this rank drives */
+} b200_parallel_desc;
+
+typedef struct b200_ctx b200_ctx;
+
+/* ---- library ------------------------------------------------------------ */
+B200_API const char* b200_backend_name(void);       /* Backend::name() -> "cuda-b200" */
+B200_API const char* b200_last_error(void);
+B200_API int b200_device_count(int* out);           /* Backend::is_available() = (count > 0) */
+B200_API int b200_type_block_elems(uint32_t ggml_type);
+B200_API int b200_type_block_bytes(uint32_t ggml_type);
+
+/* ---- GpuOnlyInference surface (src/backend/cuda/gpu_only.rs) ------------ */
+/* from_model (gpu_only.rs:426): create -> upload every tensor -> finalize. */
+B200_API int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_desc* par /* NULL = 1 GPU, device 0 */,
+                    b200_ctx** out);
+/* One call per GGUF tensor, named as the loader names them (loader.rs:592-753,
+ * 1140-1182): token_embd.weight, output_norm.weight, output.weight,
+ * blk.N.{attn_norm,ffn_norm}.weight, blk.N.attn_{q,k,v,output}.weight,
+ * blk.N.attn_{q,k,v}.bias, blk.N.ffn_{gate,up,down}.weight,
+ * blk.N.ffn_gate_inp.weight, blk.N.ffn_{gate,up,down}_exps.weight.
+ * ne[0] = in_features (contiguous), ne[1] = out_features, ne[2] = experts.
+ * The FULL tensor is passed on every rank; the library keeps its own shard. */
+B200_API int b200_ctx_upload_tensor(b200_ctx* ctx, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne, int n_dims,
+                           const void* host, size_t nbytes);
+B200_API int b200_ctx_finalize(b200_ctx* ctx);
+B200_API void b200_ctx_destroy(b200_ctx* ctx);
+
+/* GpuInference::forward (backend/mod.rs:285): one token through every layer;
+ * logits_out receives `vocab` f32 on the host. */
+B200_API int b200_forward(b200_ctx* ctx, int seq, uint32_t token, float* logits_out);
+/* GpuInference::prefill_token (backend/mod.rs:289): KV update, no logits. */
+B200_API int b200_prefill_token(b200_ctx* ctx, int seq, uint32_t token);
+/* GpuOnlyInference::forward_batch (gpu_only.rs:776-790): n tokens of ONE
+ * sequence; logits of the last one (logits_out may be NULL). */
+B200_API int b200_prefill(b200_ctx* ctx, int seq, const uint32_t* tokens, int n, float* logits_out);
+/* One token for each of n DISTINCT sequence slots;
+ * logits_out is n x vocab. */
+B200_API int b200_decode_batch(b200_ctx* ctx, const int* seqs, const uint32_t* tokens, int n, float* logits_out);
+/* GpuInference::reset / position (backend/mod.rs:292-295). */
+B200_API int b200_reset(b200_ctx* ctx, int seq);
+B200_API int b200_position(b200_ctx* ctx, int seq, uint64_t* out);
+
+/* Device-resident greedy decode (sampling on device).
+ * Runs n_steps tokens starting from `first_token`, argmax (last max wins,
+ * src/main.rs:1816-1821) on the GPU, no host round trip between tokens.
+ * tokens_out (n_steps, may be NULL) receives the generated ids; elapsed_ms
+ * (may be NULL) the CUDA-event time of the n_steps on the launching stream. */
+B200_API int b200_decode_greedy(b200_ctx* ctx, int seq, uint32_t first_token, int n_steps, uint32_t* tokens_out,
+                       float* elapsed_ms);
+
+/* Debug/parity taps: hidden state of the last processed token after `layer`
+ * layers (0 = embedding, n_layers = input of the final norm). */
+B200_API int b200_get_hidden(b200_ctx* ctx, int seq, int layer, float* out);
+/* Statistics for bench.py: kernels launched by this library since creation. */
+B200_API int b200_ctx_stats(b200_ctx* ctx, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos);
+/* Roofline probe: replays only the dequant-GEMV launches of one token (same arguments and order
+ * as the decode graph) `iters` times between CUDA events; bytes = weight bytes those launches read. */
+B200_API int b200_bench_gemv_pass(b200_ctx* ctx, int seq, int iters, float* avg_ms_per_pass, uint64_t* launches_per_pass,
+                         uint64_t* bytes_per_pass);
+/* Times `iters` launches of the vec_mat_q kernel over an uploaded weight with
+ * CUDA events on the launching stream (per-kernel GB/s for bench.py). */
+B200_API int b200_bench_weight_gemv(b200_ctx* ctx, const char* gguf_name, int iters, float* avg_ms, uint64_t* bytes);
+
+/* ---- Backend per-op surface (src/backend/mod.rs:29-265) ------------------
+ * Host pointers in, host pointers out: H2D, kernel, D2H, like the existing
+ * CUDA per-op path (src/backend/cuda/mod.rs:229-835).  f32 activations. */
+B200_API int b200_op_add(const float* a, const float* b, float* out, size_t n);
+B200_API int b200_op_mul(const float* a, const float* b, float* out, size_t n);
+B200_API int b200_op_scale(const float* a, float s, float* out, size_t n);
+B200_API int b200_op_silu(const float* x, float* out, size_t n);
+B200_API int b200_op_gelu(const float* x, float* out, size_t n);
+B200_API int b200_op_softmax(const float* x, float* out, size_t n);
+B200_API int b200_op_rms_norm(const float* x, const float* weight, float eps, float* out, size_t n_rows, size_t hidden);
+/* vec_mat: a[k] @ W[k,n] (f32 W, GGUF layout: n rows of k). */
+B200_API int b200_op_vec_mat(const float* a, const float* w, float* out, size_t k, size_t n);
+/* vec_mat_q: W quantised, n rows of k/bs blocks (backend/mod.rs:110). */
+B200_API int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t k, size_t n);
+/* dequantize: bit-exact with the reference's dequantize_* (tensor/quant/dequant.rs). */
+B200_API int b200_op_dequantize(const void* src, uint32_t ggml_type, float* out, size_t n_elems);
+/* rope: q[n_heads,1,hd], k[n_kv,1,hd] in place (cpu/ops.rs:1216-1337). */
+B200_API int b200_op_rope(float* q, float* k, int n_heads, int n_kv_heads, int head_dim, int pos, float freq_base,
+                 float freq_scale, int use_neox);
+/* attention_cached: q[n_heads,1,hd]; k/v cache [n_kv,max_seq,hd] (cpu/ops.rs:1479-1537). */
+B200_API int b200_op_attention_cached(const float* q, const float* k_cache, const float* v_cache, float* out, int n_heads,
+                             int n_kv_heads, int head_dim, int max_seq, float scale, int kv_len);
+/* attention: causal, q[n_heads,seq,hd], k/v[n_kv,seq,hd] (backend/mod.rs attention). */
+B200_API int b200_op_attention(const float* q, const float* k, const float* v, float* out, int n_heads, int n_kv_heads,
+                      int seq_len, int head_dim, float scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAMA_B200_H */

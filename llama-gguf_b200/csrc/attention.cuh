@@ -1,0 +1,279 @@
+// attention.cuh — RoPE + KV-cache write, and GQA split-KV decode attention.
+//
+// Replaces rope_single_pos / update_kv_cache / flash_attention_cached of the existing
+// CUDA backend (src/backend/cuda/kernels.rs:379-441, 800-824, 1395-1460) and follows the
+// CPU semantics of Backend::rope (src/backend/cpu/ops.rs:1216-1337), the cache write
+// (src/model/layers.rs:580-600) and Backend::attention_cached (cpu/ops.rs:1479-1537).
+//
+// KV cache layout per layer (src/model/mod.rs:83-108): [n_kv_heads][max_seq][head_dim] f32.
+//
+// attn_decode: one CTA per (kv head, KV split).  The G = n_heads/n_kv_heads query heads
+// that share a kv head are processed together so every K/V row is read from HBM once
+// per group, not once per query head.  A warp owns a strided subset of the split's
+// positions; each lane holds head_dim/32 contiguous floats of the row (coalesced 128-bit
+// loads), scores are warp-shuffle reductions, softmax is online (running max / sum) in
+// f32.  Warps combine through shared memory, splits through a global scratch; the last
+// CTA to arrive for a kv head (atomic ticket) does the final merge in a fixed order, so
+// results are run-to-run deterministic.
+//
+// Deviation (documented in DESIGN.md): the reference skips value rows whose probability
+// is <= 1e-8 (cpu/ops.rs:1529); this kernel includes them.  The dropped mass is at most
+// kv_len * 1e-8 of the output — far below the 1e-3 parity tolerance.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct RopeKvParams {
+    float* q;              // [n_heads * hd] in place
+    const float* k;        // [n_kv * hd] raw projection (+bias)
+    const float* v;        // [n_kv * hd]
+    float* k_cache;        // [n_kv][max_seq][hd]
+    float* v_cache;
+    const float* freq;     // [hd/2] = 1 / base^(2i/hd), computed on the host with libm powf
+    const int* pos;        // device scalar: position of the current token
+    int n_heads, n_kv, hd, max_seq, neox;
+    float rope_scale;
+};
+
+// Backend::rope + cache write.  One thread per rotated pair, then one per v element.
+__global__ void rope_kv_kernel(const RopeKvParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pos = *p.pos;
+    const int half = p.hd >> 1;
+    const int n_pairs = (p.n_heads + p.n_kv) * half;
+    const int n_v = p.n_kv * p.hd;
+    const float position = (float)pos / p.rope_scale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs + n_v; i += gridDim.x * blockDim.x) {
+        if (i < n_pairs) {
+            const int head = i / half, pi = i - head * half;
+            const float theta = position * p.freq[pi];
+            const float c = cosf(theta), s = sinf(theta);
+            const int i0 = p.neox ? pi : 2 * pi;
+            const int i1 = p.neox ? pi + half : 2 * pi + 1;
+            if (head < p.n_heads) {
+                float* d = p.q + (size_t)head * p.hd;
+                const float x0 = d[i0], x1 = d[i1];
+                d[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+                d[i1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+            } else {
+                const int kh = head - p.n_heads;
+                const float* d = p.k + (size_t)kh * p.hd;
+                float* o = p.k_cache + ((size_t)kh * p.max_seq + pos) * p.hd;
+                const float x0 = d[i0], x1 = d[i1];
+                o[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+                o[i1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+            }
+        } else {
+            const int j = i - n_pairs;
+            const int kh = j / p.hd, d = j - kh * p.hd;
+            p.v_cache[((size_t)kh * p.max_seq + pos) * p.hd + d] = p.v[j];
+        }
+    }
+}
+
+constexpr int kAttnWarps = 8;
+constexpr int kAttnThreads = kAttnWarps * kWarp;
+
+struct AttnParams {
+    const float* q;        // [n_heads][hd], RoPE applied
+    const float* k_cache;  // [n_kv][max_seq][hd]
+    const float* v_cache;
+    float* out;            // [n_heads][hd]
+    float* part;           // scratch [n_kv][n_splits][G][hd + 2]
+    unsigned int* tickets; // [n_kv], zero on entry, left zero on exit
+    const int* pos;        // device scalar (kv_len = *pos + 1) or nullptr
+    int kv_len_fixed;      // used when pos == nullptr
+    int n_kv, G, max_seq, n_splits;
+    float scale;
+};
+
+// merge (m, l, acc) <- (m, l, acc) (+) (m2, l2, acc2)
+__device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca, float& cb, float& mo) {
+    mo = fmaxf(m, m2);
+    ca = (m == -INFINITY) ? 0.0f : expf(m - mo);
+    cb = (m2 == -INFINITY) ? 0.0f : expf(m2 - mo);
+}
+
+template <int HD, int GMAX>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p) {
+    constexpr int VEC = HD / 32;  // floats per lane per row
+    extern __shared__ __align__(16) float sm[];
+    float* s_m = sm;                              // [warps][GMAX]
+    float* s_l = sm + kAttnWarps * GMAX;          // [warps][GMAX]
+    float* s_acc = sm + 2 * kAttnWarps * GMAX;    // [warps][GMAX][HD]
+    __shared__ unsigned int s_ticket;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kh = blockIdx.x, split = blockIdx.y;
+    const int G = p.G;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const int kv_len = p.pos ? (*p.pos + 1) : p.kv_len_fixed;
+    int chunk = (kv_len + p.n_splits - 1) / p.n_splits;
+    chunk = (chunk + kAttnWarps - 1) / kAttnWarps * kAttnWarps;
+    const int start = split * chunk;
+    const int end = min(kv_len, start + chunk);
+
+    float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
+#pragma unroll
+    for (int g = 0; g < GMAX; g++) {
+        m[g] = -INFINITY;
+        l[g] = 0.0f;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            acc[g][v] = 0.0f;
+            q[g][v] = (g < G) ? p.q[((size_t)(kh * G + g)) * HD + lane * VEC + v] : 0.0f;
+        }
+    }
+    const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+    const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+
+    constexpr int UNR = 4;  // positions in flight per warp
+    for (int pos0 = start + warp; pos0 < end; pos0 += kAttnWarps * UNR) {
+        float kr[UNR][VEC], vr[UNR][VEC];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int pp = pos0 + u * kAttnWarps;
+            const int pc = pp < end ? pp : pos0;  // clamp: loads stay in range, result discarded
+            if constexpr (VEC == 4) {
+                float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * HD);
+                float4 b = *reinterpret_cast<const float4*>(vb + (size_t)pc * HD);
+                kr[u][0] = a.x; kr[u][1] = a.y; kr[u][2] = a.z; kr[u][3] = a.w;
+                vr[u][0] = b.x; vr[u][1] = b.y; vr[u][2] = b.z; vr[u][3] = b.w;
+            } else {
+                float2 a = *reinterpret_cast<const float2*>(kb + (size_t)pc * HD);
+                float2 b = *reinterpret_cast<const float2*>(vb + (size_t)pc * HD);
+                kr[u][0] = a.x; kr[u][1] = a.y;
+                vr[u][0] = b.x; vr[u][1] = b.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int pp = pos0 + u * kAttnWarps;
+            if (pp < end) {  // warp-uniform
+#pragma unroll
+                for (int g = 0; g < GMAX; g++) {
+                    if (g < G) {
+                        float d = 0.0f;
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) d = fmaf(q[g][v], kr[u][v], d);
+                        d = warp_sum(d) * p.scale;
+                        const float mn = fmaxf(m[g], d);
+                        const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
+                        const float w = expf(d - mn);
+                        l[g] = l[g] * corr + w;
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) acc[g][v] = fmaf(w, vr[u][v], acc[g][v] * corr);
+                        m[g] = mn;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- combine the warps of this CTA ----
+#pragma unroll
+    for (int g = 0; g < GMAX; g++) {
+        if (g < G) {
+            if (lane == 0) {
+                s_m[warp * GMAX + g] = m[g];
+                s_l[warp * GMAX + g] = l[g];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; v++) s_acc[(warp * GMAX + g) * HD + lane * VEC + v] = acc[g][v];
+        }
+    }
+    __syncthreads();
+    const int part_stride = HD + 2;
+    float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;
+    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {
+        const int g = idx / HD, d = idx - g * HD;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) M = fmaxf(M, s_m[w * GMAX + g]);
+        float L = 0.0f, A = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) {
+            const float mw = s_m[w * GMAX + g];
+            const float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
+            L += s_l[w * GMAX + g] * c;
+            A += s_acc[(w * GMAX + g) * HD + d] * c;
+        }
+        my_part[g * part_stride + d] = A;
+        if (d == 0) {
+            my_part[g * part_stride + HD] = M;
+            my_part[g * part_stride + HD + 1] = L;
+        }
+    }
+
+    // ---- last CTA of this kv head merges the splits ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[kh], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(p.n_splits - 1)) return;
+    __threadfence();
+    const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
+    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {
+        const int g = idx / HD, d = idx - g * HD;
+        float M = -INFINITY;
+        for (int s = 0; s < p.n_splits; s++) M = fmaxf(M, __ldcg(parts + ((size_t)s * G + g) * part_stride + HD));
+        float L = 0.0f, A = 0.0f;
+        for (int s = 0; s < p.n_splits; s++) {
+            const float* ps = parts + ((size_t)s * G + g) * part_stride;
+            const float ms = __ldcg(ps + HD);
+            const float c = (ms == -INFINITY) ? 0.0f : expf(ms - M);
+            L += __ldcg(ps + HD + 1) * c;
+            A += __ldcg(ps + d) * c;
+        }
+        p.out[((size_t)(kh * G + g)) * HD + d] = A / L;
+    }
+    if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
+}
+
+inline size_t attn_smem_bytes(int hd, int gmax) { return (size_t)(2 * kAttnWarps * gmax + kAttnWarps * gmax * hd) * sizeof(float); }
+
+// Backend::attention (cpu/ops.rs:1353-1470): causal, q[n_heads][seq][hd], k/v[n_kv][kv_len][hd].
+// Compatibility surface only (the model path uses attention_cached): one warp per (head, query).
+__global__ void attention_full_kernel(const float* q, const float* k, const float* v, float* out, int n_heads,
+                                      int n_kv, int seq_len, int kv_len, int hd, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_heads * seq_len) return;
+    const int head = wid / seq_len, s = wid - head * seq_len;
+    const int kvh = head / (n_heads / n_kv);
+    const int q_abs = max(kv_len - seq_len, 0) + s;
+    const float* qv = q + ((size_t)head * seq_len + s) * hd;
+    float m = -INFINITY, l = 0.0f;
+    float acc[8];  // hd <= 256
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    for (int pp = 0; pp < kv_len && pp <= q_abs; pp++) {
+        const float* kv = k + ((size_t)kvh * kv_len + pp) * hd;
+        const float* vv = v + ((size_t)kvh * kv_len + pp) * hd;
+        float d = 0.0f;
+        for (int i = lane; i < hd; i += 32) d = fmaf(qv[i], kv[i], d);
+        d = warp_sum(d) * scale;
+        const float mn = fmaxf(m, d);
+        const float corr = (m == -INFINITY) ? 0.0f : expf(m - mn);
+        const float w = expf(d - mn);
+        l = l * corr + w;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int dd = lane + 32 * i;
+            if (dd < hd) acc[i] = fmaf(w, vv[dd], acc[i] * corr);
+        }
+        m = mn;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int dd = lane + 32 * i;
+        if (dd < hd) out[((size_t)head * seq_len + s) * hd + dd] = acc[i] / l;
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,1035 @@
+// engine.cu — context, weight residency, the per-token launch sequence and the C ABI
+// (include/llama_b200.h) of the cuda-b200 backend.
+//
+// Mirrors GpuOnlyInference (src/backend/cuda/gpu_only.rs:24-88, 425-2011): weights are
+// uploaded once and stay resident in their GGUF block layout; a token is one replay of a
+// CUDA graph (embedding row -> L x [norm+QKV GEMV, RoPE+KV write, GQA attention,
+// O GEMV+residual, norm+gate/up GEMV+SwiGLU, down GEMV+residual] -> norm+vocab GEMV).
+// Only two host<->device crossings per token remain: 4 bytes of token id in, `vocab`
+// f32 logits out (none at all in b200_decode_greedy).  Kernel-to-kernel edges are
+// programmatic dependent launches so the next kernel's weight prefetch overlaps the
+// tail of the previous one.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/llama_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc.cuh"
+#include "quant.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(B200_ERR_OPERATION_FAILED, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CU_ALLOC(expr)                                                                                 \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(B200_ERR_ALLOCATION_FAILED, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* b200_backend_name(void) { return "cuda-b200"; }
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_device_count(int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (out) *out = 0;
+        return fail(B200_ERR_NOT_AVAILABLE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    if (out) *out = n;
+    return B200_OK;
+}
+extern "C" int b200_type_block_elems(uint32_t t) { return type_block_elems((int)t); }
+extern "C" int b200_type_block_bytes(uint32_t t) { return type_block_bytes((int)t); }
+
+static bool type_supported(int t) { return type_block_elems(t) != 0; }
+
+// ------------------------------------------------------------------ context
+struct DevTensor {
+    uint8_t* d = nullptr;
+    int type = 0;
+    int n_dims = 0;
+    uint64_t ne[4] = {1, 1, 1, 1};
+    size_t nbytes = 0;
+    long long row_bytes = 0;  // bytes of one output row (ne[0] elements)
+    bool present() const { return d != nullptr; }
+    const float* f32() const { return reinterpret_cast<const float*>(d); }
+};
+
+struct Layer {
+    DevTensor attn_norm, ffn_norm, wq, wk, wv, wo, bq, bk, bv, gate, up, down;
+    DevTensor router, gate_exps, up_exps, down_exps;
+};
+
+enum Mode { MODE_LOGITS = 0, MODE_PREFILL = 1, MODE_GREEDY = 2, MODE_COUNT = 3 };
+
+struct Slot {
+    SeqState* d_state = nullptr;
+    int* d_generated = nullptr;
+    float* kv = nullptr;  // [L][2][n_kv][max_seq][hd]
+    uint64_t host_pos = 0;
+    cudaGraphExec_t graph[MODE_COUNT] = {nullptr, nullptr, nullptr};
+    uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
+};
+
+constexpr int kMaxGenerated = 1 << 16;
+
+struct b200_ctx {
+    b200_model_desc d{};
+    b200_parallel_desc par{1, 0, 0};
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    std::map<std::string, DevTensor> tensors;
+    std::vector<Layer> layers;
+    DevTensor token_embd, output_norm, output;
+    bool finalized = false;
+    // scratch
+    float *xa = nullptr, *xb = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *logits = nullptr;
+    float *attn_part = nullptr, *rope_freq = nullptr, *taps = nullptr, *moe_wt = nullptr;
+    int* moe_sel = nullptr;
+    unsigned int* tickets = nullptr;
+    int n_splits = 1;
+    size_t out_scratch_elems = 0;
+    // pinned host staging
+    float* h_logits = nullptr;
+    int* h_token = nullptr;
+    std::vector<Slot> slots;
+    // options
+    bool use_graph = true, use_pdl = true, use_taps = false;
+    // statistics
+    uint64_t launches = 0;
+    uint64_t weight_bytes_per_token = 0;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    cudaGraphExec_t gemv_graph = nullptr;  // b200_bench_gemv_pass
+    uint64_t gemv_graph_launches = 0;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(b200_ctx* c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = c->use_pdl ? at : nullptr;
+    cfg.numAttrs = c->use_pdl ? 1 : 0;
+    c->launches++;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_desc* par, b200_ctx** out) {
+    if (!desc || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_create: null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(B200_ERR_NOT_AVAILABLE, "cuda-b200: no CUDA device (this backend has no CPU fallback)");
+    }
+    b200_ctx* c = new b200_ctx();
+    c->d = *desc;
+    if (par) c->par = *par;
+    b200_model_desc& d = c->d;
+    if (d.head_dim <= 0) d.head_dim = d.hidden / std::max(d.n_heads, 1);
+    if (d.rope_scale == 0.0f) d.rope_scale = 1.0f;
+    if (d.max_batch <= 0) d.max_batch = 1;
+    if (d.n_experts > 0 && d.expert_ffn <= 0) d.expert_ffn = d.ffn;
+    auto bad = [&](const char* m) {
+        delete c;
+        return fail(B200_ERR_INVALID_ARGUMENT, std::string("b200_ctx_create: ") + m);
+    };
+    if (d.hidden <= 0 || d.n_layers <= 0 || d.n_heads <= 0 || d.n_kv_heads <= 0 || d.vocab <= 0 || d.max_seq_len <= 0)
+        return bad("non-positive model dimension");
+    if (d.n_heads % d.n_kv_heads) return bad("n_heads must be a multiple of n_kv_heads");
+    if (d.head_dim != 64 && d.head_dim != 128) return bad("head_dim must be 64 or 128");
+    if (d.n_heads / d.n_kv_heads > 8) return bad("more than 8 query heads per kv head");
+    if (d.hidden % 32) return bad("hidden must be a multiple of 32");
+    if (d.n_experts > 64 || d.n_experts_used > 8) return bad("at most 64 experts, top-8");
+    if (c->par.world_size < 1 || c->par.rank < 0 || c->par.rank >= c->par.world_size) return bad("bad parallel desc");
+    if (c->par.world_size != 1) return bad("tensor parallelism is configured through b200_ctx_tp_* (not in this build)");
+    if (c->par.device >= n_dev) return bad("device ordinal out of range");
+    CU(cudaSetDevice(c->par.device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, c->par.device));
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->use_graph = env_int("B200_GRAPH", 1) != 0;
+    c->use_pdl = env_int("B200_PDL", 1) != 0;
+    c->use_taps = env_int("B200_TAPS", 0) != 0;
+    c->layers.resize(d.n_layers);
+    *out = c;
+    return B200_OK;
+}
+
+static DevTensor* slot_for_name(b200_ctx* c, const std::string& name) {
+    if (name == "token_embd.weight") return &c->token_embd;
+    if (name == "output_norm.weight") return &c->output_norm;
+    if (name == "output.weight") return &c->output;
+    int li = -1;
+    char rest[96];
+    if (sscanf(name.c_str(), "blk.%d.%95s", &li, rest) == 2 && li >= 0 && li < (int)c->layers.size()) {
+        Layer& L = c->layers[li];
+        std::string r(rest);
+        if (r == "attn_norm.weight") return &L.attn_norm;
+        if (r == "ffn_norm.weight") return &L.ffn_norm;
+        if (r == "attn_q.weight") return &L.wq;
+        if (r == "attn_k.weight") return &L.wk;
+        if (r == "attn_v.weight") return &L.wv;
+        if (r == "attn_output.weight") return &L.wo;
+        if (r == "attn_q.bias") return &L.bq;
+        if (r == "attn_k.bias") return &L.bk;
+        if (r == "attn_v.bias") return &L.bv;
+        if (r == "ffn_gate.weight") return &L.gate;
+        if (r == "ffn_up.weight") return &L.up;
+        if (r == "ffn_down.weight") return &L.down;
+        if (r == "ffn_gate_inp.weight") return &L.router;
+        if (r == "ffn_gate_exps.weight") return &L.gate_exps;
+        if (r == "ffn_up_exps.weight") return &L.up_exps;
+        if (r == "ffn_down_exps.weight") return &L.down_exps;
+    }
+    return nullptr;
+}
+
+extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne,
+                                      int n_dims, const void* host, size_t nbytes) {
+    if (!c || !gguf_name || !ne || !host) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_upload_tensor: null argument");
+    if (c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_upload_tensor: context already finalized");
+    if (n_dims < 1 || n_dims > 3) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": 1..3 dims expected");
+    if (!type_supported((int)ggml_type))
+        return fail(B200_ERR_UNSUPPORTED_DTYPE, std::string(gguf_name) + ": unsupported ggml type " + std::to_string(ggml_type));
+    DevTensor* t = slot_for_name(c, gguf_name);
+    if (!t) return fail(B200_ERR_INVALID_ARGUMENT, std::string("unknown tensor name: ") + gguf_name);
+    const int be = type_block_elems((int)ggml_type), bb = type_block_bytes((int)ggml_type);
+    uint64_t numel = 1;
+    for (int i = 0; i < n_dims; i++) numel *= ne[i];
+    if (ne[0] % be) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": ne[0] not a multiple of the block size");
+    if (numel / be * bb != nbytes) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": byte size does not match shape");
+    CU(cudaSetDevice(c->par.device));
+    if (t->d) cudaFree(t->d);
+    *t = DevTensor();
+    CU_ALLOC(cudaMalloc((void**)&t->d, nbytes + 256));
+    CU(cudaMemcpy(t->d, host, nbytes, cudaMemcpyHostToDevice));
+    CU(cudaMemset(t->d + nbytes, 0, 256));
+    t->type = (int)ggml_type;
+    t->n_dims = n_dims;
+    for (int i = 0; i < n_dims; i++) t->ne[i] = ne[i];
+    t->nbytes = nbytes;
+    t->row_bytes = (long long)(ne[0] / be * bb);
+    c->tensors[gguf_name] = *t;
+    return B200_OK;
+}
+
+static int check_weight(const DevTensor& t, const char* what, uint64_t k, uint64_t n, int layer) {
+    std::string nm = std::string(what) + (layer >= 0 ? " (layer " + std::to_string(layer) + ")" : "");
+    if (!t.present()) return fail(B200_ERR_INVALID_ARGUMENT, "missing tensor " + nm);
+    if (t.ne[0] != k || t.ne[1] != n)
+        return fail(B200_ERR_SHAPE_MISMATCH, nm + ": expected [" + std::to_string(k) + "," + std::to_string(n) + "], got [" +
+                                                 std::to_string(t.ne[0]) + "," + std::to_string(t.ne[1]) + "]");
+    if (k % 32) return fail(B200_ERR_SHAPE_MISMATCH, nm + ": in_features must be a multiple of 32");
+    return B200_OK;
+}
+static int check_f32_vec(const DevTensor& t, const char* what, uint64_t n, int layer, bool required) {
+    std::string nm = std::string(what) + (layer >= 0 ? " (layer " + std::to_string(layer) + ")" : "");
+    if (!t.present()) return required ? fail(B200_ERR_INVALID_ARGUMENT, "missing tensor " + nm) : B200_OK;
+    if (t.type != T_F32) return fail(B200_ERR_DTYPE_MISMATCH, nm + ": must be F32");
+    if (t.ne[0] != n) return fail(B200_ERR_SHAPE_MISMATCH, nm + ": wrong length");
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_finalize(b200_ctx* c) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_finalize: null ctx");
+    if (c->finalized) return B200_OK;
+    const b200_model_desc& d = c->d;
+    CU(cudaSetDevice(c->par.device));
+    const uint64_t H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, I = d.ffn, V = d.vocab;
+    int rc;
+    if ((rc = check_weight(c->token_embd, "token_embd.weight", H, V, -1))) return rc;
+    if ((rc = check_f32_vec(c->output_norm, "output_norm.weight", H, -1, true))) return rc;
+    if (c->output.present()) {
+        if ((rc = check_weight(c->output, "output.weight", H, V, -1))) return rc;
+    } else if (!d.tied_output) {
+        // the loader ties silently when output.weight is absent (loader.rs:349-355)
+    }
+    uint64_t wbytes = c->token_embd.row_bytes;  // one embedding row per token
+    wbytes += (c->output.present() ? c->output.nbytes : c->token_embd.nbytes) + H * 4;
+    for (int l = 0; l < d.n_layers; l++) {
+        Layer& L = c->layers[l];
+        if ((rc = check_f32_vec(L.attn_norm, "attn_norm.weight", H, l, true))) return rc;
+        if ((rc = check_f32_vec(L.ffn_norm, "ffn_norm.weight", H, l, true))) return rc;
+        if ((rc = check_weight(L.wq, "attn_q.weight", H, nh * hd, l))) return rc;
+        if ((rc = check_weight(L.wk, "attn_k.weight", H, nkv * hd, l))) return rc;
+        if ((rc = check_weight(L.wv, "attn_v.weight", H, nkv * hd, l))) return rc;
+        if ((rc = check_weight(L.wo, "attn_output.weight", nh * hd, H, l))) return rc;
+        if ((rc = check_f32_vec(L.bq, "attn_q.bias", nh * hd, l, false))) return rc;
+        if ((rc = check_f32_vec(L.bk, "attn_k.bias", nkv * hd, l, false))) return rc;
+        if ((rc = check_f32_vec(L.bv, "attn_v.bias", nkv * hd, l, false))) return rc;
+        wbytes += L.wq.nbytes + L.wk.nbytes + L.wv.nbytes + L.wo.nbytes + 2 * H * 4;
+        if (d.n_experts > 0) {
+            const uint64_t EI = d.expert_ffn, E = d.n_experts;
+            if (!L.router.present() || L.router.type != T_F32 || L.router.ne[0] != H || L.router.ne[1] != E)
+                return fail(B200_ERR_DTYPE_MISMATCH, "ffn_gate_inp.weight must be F32 [hidden, n_experts] (moe.rs:133)");
+            for (const DevTensor* t : {&L.gate_exps, &L.up_exps}) {
+                if ((rc = check_weight(*t, "ffn_{gate,up}_exps.weight", H, EI, l))) return rc;
+                if (t->ne[2] != E) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
+            }
+            if ((rc = check_weight(L.down_exps, "ffn_down_exps.weight", EI, H, l))) return rc;
+            if (L.down_exps.ne[2] != E) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
+            if (L.gate_exps.type != L.up_exps.type)
+                return fail(B200_ERR_UNSUPPORTED, "gate/up expert tensors must share one quant type");
+            wbytes += L.router.nbytes +
+                      (L.gate_exps.nbytes + L.up_exps.nbytes + L.down_exps.nbytes) / E * d.n_experts_used;
+        } else {
+            if ((rc = check_weight(L.gate, "ffn_gate.weight", H, I, l))) return rc;
+            if ((rc = check_weight(L.up, "ffn_up.weight", H, I, l))) return rc;
+            if ((rc = check_weight(L.down, "ffn_down.weight", I, H, l))) return rc;
+            if (L.gate.type != L.up.type) return fail(B200_ERR_UNSUPPORTED, "ffn_gate/ffn_up must share one quant type");
+            wbytes += L.gate.nbytes + L.up.nbytes + L.down.nbytes;
+        }
+    }
+    c->weight_bytes_per_token = wbytes;
+
+    const uint64_t ffn_w = d.n_experts > 0 ? (uint64_t)d.expert_ffn : I;
+    CU_ALLOC(cudaMalloc((void**)&c->xa, H * 4));
+    CU_ALLOC(cudaMalloc((void**)&c->xb, H * 4));
+    CU_ALLOC(cudaMalloc((void**)&c->qkv, (nh + 2 * nkv) * hd * 4));
+    CU_ALLOC(cudaMalloc((void**)&c->attn, nh * hd * 4));
+    CU_ALLOC(cudaMalloc((void**)&c->hbuf, ffn_w * 4));
+    c->out_scratch_elems = std::max<uint64_t>(std::max<uint64_t>(V, ffn_w), std::max<uint64_t>(H, nh * hd));
+    CU_ALLOC(cudaMalloc((void**)&c->logits, c->out_scratch_elems * 4));
+    c->n_splits = (int)std::min<uint64_t>(64, std::max<uint64_t>(1, (2 * (uint64_t)c->n_sm + nkv - 1) / nkv));
+    CU_ALLOC(cudaMalloc((void**)&c->attn_part, nkv * c->n_splits * (nh / nkv) * (hd + 2) * 4));
+    CU_ALLOC(cudaMalloc((void**)&c->tickets, nkv * sizeof(unsigned int)));
+    CU(cudaMemset(c->tickets, 0, nkv * sizeof(unsigned int)));
+    CU_ALLOC(cudaMalloc((void**)&c->moe_sel, 8 * sizeof(int)));
+    CU_ALLOC(cudaMalloc((void**)&c->moe_wt, 8 * sizeof(float)));
+    CU(cudaMemset(c->moe_sel, 0, 8 * sizeof(int)));
+    CU(cudaMemset(c->moe_wt, 0, 8 * sizeof(float)));
+    CU_ALLOC(cudaMalloc((void**)&c->taps, (uint64_t)(d.n_layers + 1) * H * 4));
+    CU(cudaMemset(c->taps, 0, (uint64_t)(d.n_layers + 1) * H * 4));
+    // RoPE frequencies with the host's libm powf, exactly as the reference computes them
+    // per element (cpu/ops.rs:1305): freq = 1 / base^(2i/hd).
+    {
+        std::vector<float> f(hd / 2);
+        for (uint64_t i = 0; i < hd / 2; i++) f[i] = 1.0f / powf(d.rope_base, (float)(2 * i) / (float)hd);
+        CU_ALLOC(cudaMalloc((void**)&c->rope_freq, f.size() * 4));
+        CU(cudaMemcpy(c->rope_freq, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CU_ALLOC(cudaHostAlloc((void**)&c->h_logits, V * 4, cudaHostAllocDefault));
+    CU_ALLOC(cudaHostAlloc((void**)&c->h_token, sizeof(int), cudaHostAllocDefault));
+    c->slots.resize(d.max_batch);
+    const uint64_t kv_elems = (uint64_t)d.n_layers * 2 * nkv * d.max_seq_len * hd;
+    for (Slot& s : c->slots) {
+        CU_ALLOC(cudaMalloc((void**)&s.d_state, sizeof(SeqState)));
+        CU(cudaMemset(s.d_state, 0, sizeof(SeqState)));
+        CU_ALLOC(cudaMalloc((void**)&s.d_generated, kMaxGenerated * sizeof(int)));
+        CU_ALLOC(cudaMalloc((void**)&s.kv, kv_elems * 4));
+        CU(cudaMemset(s.kv, 0, kv_elems * 4));
+    }
+    // kernels that may need more than 48 KB of dynamic shared memory
+    CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    c->finalized = true;
+    return B200_OK;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->par.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->gemv_graph) cudaGraphExecDestroy(c->gemv_graph);
+    for (auto& kv : c->tensors) cudaFree(kv.second.d);
+    for (Slot& s : c->slots) {
+        for (int m = 0; m < MODE_COUNT; m++)
+            if (s.graph[m]) cudaGraphExecDestroy(s.graph[m]);
+        cudaFree(s.d_state);
+        cudaFree(s.d_generated);
+        cudaFree(s.kv);
+    }
+    for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
+                    (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
+                    (void*)c->rope_freq, c->flush_buf})
+        cudaFree(p);
+    if (c->h_logits) cudaFreeHost(c->h_logits);
+    if (c->h_token) cudaFreeHost(c->h_token);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------ launches
+static void fill_seg(GemvSeg& s, const DevTensor& w, float* out, const DevTensor* bias, int expert_dim) {
+    s.w = w.d;
+    s.out = out;
+    s.bias = (bias && bias->present()) ? bias->f32() : nullptr;
+    s.row_bytes = w.row_bytes;
+    s.expert_stride = expert_dim ? (long long)(w.nbytes / w.ne[2]) : 0;
+    s.type = w.type;
+    s.n_rows = (int)w.ne[1];
+}
+
+static cudaError_t launch_gemv(b200_ctx* c, GemvParams& p) {
+    int n_tasks;
+    if (p.epi == EPI_SWIGLU) {
+        n_tasks = (p.seg[0].n_rows + 1) / 2;
+    } else {
+        n_tasks = 0;
+        for (int s = 0; s < p.n_seg; s++) n_tasks += (p.seg[s].n_rows + kGemvR - 1) / kGemvR;
+    }
+    int grid = (n_tasks + kGemvWarps - 1) / kGemvWarps;
+    grid = std::max(1, std::min(grid, 2 * c->n_sm));
+    size_t smem = (size_t)xpad_floats(p.K) * sizeof(float);
+    return launch_k(c, gemv_kernel, dim3(grid), dim3(kGemvThreads), smem, p);
+}
+
+static cudaError_t launch_attn(b200_ctx* c, const AttnParams& ap, int hd, int G) {
+    dim3 grid(ap.n_kv, ap.n_splits);
+    if (hd == 128) {
+        if (G <= 4) return launch_k(c, attn_decode_kernel<128, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 4), ap);
+        return launch_k(c, attn_decode_kernel<128, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 8), ap);
+    }
+    if (G <= 4) return launch_k(c, attn_decode_kernel<64, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 4), ap);
+    return launch_k(c, attn_decode_kernel<64, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 8), ap);
+}
+
+// Enqueue every kernel of one token for `slot` on c->stream (captured into a graph by the caller).
+static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_gemv = false) {
+    const b200_model_desc& d = c->d;
+    Slot& sl = c->slots[slot_i];
+    const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, G = nh / nkv;
+    cudaError_t e;
+#define CK(x)                      \
+    if ((e = (x)) != cudaSuccess) return e
+    const int* pos_ptr = &sl.d_state->pos_cur;
+    if (!only_gemv)
+        CK(launch_k(c, embed_kernel, dim3(std::max(1, std::min(8, H / 256))), dim3(256), 0, c->token_embd.type,
+                    (const uint8_t*)c->token_embd.d, c->token_embd.row_bytes, H, sl.d_state, c->xa, d.vocab));
+    if (c->use_taps) CK(cudaMemcpyAsync(c->taps, c->xa, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
+    for (int l = 0; l < d.n_layers; l++) {
+        Layer& L = c->layers[l];
+        float* kc = sl.kv + (size_t)l * kv_layer;
+        float* vc = kc + kv_layer / 2;
+        float* q = c->qkv;
+        float* k = c->qkv + (size_t)nh * hd;
+        float* v = k + (size_t)nkv * hd;
+        {   // RMSNorm + QKV (+bias)
+            GemvParams p{};
+            fill_seg(p.seg[0], L.wq, q, &L.bq, 0);
+            fill_seg(p.seg[1], L.wk, k, &L.bk, 0);
+            fill_seg(p.seg[2], L.wv, v, &L.bv, 0);
+            p.n_seg = 3; p.K = H; p.x = c->xa; p.norm_w = L.attn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+            CK(launch_gemv(c, p));
+        }
+        if (!only_gemv) {   // RoPE + KV write
+            RopeKvParams rp{};
+            rp.q = q; rp.k = k; rp.v = v; rp.k_cache = kc; rp.v_cache = vc; rp.freq = c->rope_freq; rp.pos = pos_ptr;
+            rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox;
+            rp.rope_scale = d.rope_scale;
+            int work = (nh + nkv) * hd / 2 + nkv * hd;
+            CK(launch_k(c, rope_kv_kernel, dim3((work + 255) / 256), dim3(256), 0, rp));
+        }
+        if (!only_gemv) {   // GQA decode attention over [0, pos]
+            AttnParams ap{};
+            ap.q = q; ap.k_cache = kc; ap.v_cache = vc; ap.out = c->attn; ap.part = c->attn_part; ap.tickets = c->tickets;
+            ap.pos = pos_ptr; ap.kv_len_fixed = 0; ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len;
+            ap.n_splits = c->n_splits; ap.scale = 1.0f / sqrtf((float)hd);
+            CK(launch_attn(c, ap, hd, G));
+        }
+        {   // O projection + residual: xb = Wo attn + xa
+            GemvParams p{};
+            fill_seg(p.seg[0], L.wo, c->xb, nullptr, 0);
+            p.n_seg = 1; p.K = nh * hd; p.x = c->attn; p.epi = EPI_RESIDUAL; p.residual = c->xa;
+            CK(launch_gemv(c, p));
+        }
+        if (d.n_experts > 0) {
+            RouteParams rt{};
+            rt.x = c->xb; rt.norm_w = L.ffn_norm.f32(); rt.eps = d.norm_eps; rt.w_router = L.router.f32();
+            rt.hidden = H; rt.n_experts = d.n_experts; rt.top_k = d.n_experts_used; rt.sel = c->moe_sel; rt.wt = c->moe_wt;
+            if (!only_gemv) CK(launch_k(c, moe_route_kernel, dim3(1), dim3(256), 0, rt));
+            for (int s = 0; s < d.n_experts_used; s++) {
+                GemvParams p{};
+                fill_seg(p.seg[0], L.gate_exps, c->hbuf, nullptr, 1);
+                fill_seg(p.seg[1], L.up_exps, c->hbuf, nullptr, 1);
+                p.n_seg = 2; p.K = H; p.x = c->xb; p.norm_w = L.ffn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_SWIGLU;
+                p.expert_sel = c->moe_sel; p.expert_wt = c->moe_wt; p.expert_slot = s;
+                CK(launch_gemv(c, p));
+                GemvParams q2{};
+                fill_seg(q2.seg[0], L.down_exps, c->xa, nullptr, 1);
+                q2.n_seg = 1; q2.K = d.expert_ffn; q2.x = c->hbuf; q2.epi = EPI_SCALED_ACC;
+                q2.residual = (s == d.n_experts_used - 1) ? c->xb : nullptr;
+                q2.expert_sel = c->moe_sel; q2.expert_wt = c->moe_wt; q2.expert_slot = s;
+                CK(launch_gemv(c, q2));
+            }
+        } else {
+            GemvParams p{};
+            fill_seg(p.seg[0], L.gate, c->hbuf, nullptr, 0);
+            fill_seg(p.seg[1], L.up, c->hbuf, nullptr, 0);
+            p.n_seg = 2; p.K = H; p.x = c->xb; p.norm_w = L.ffn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_SWIGLU;
+            CK(launch_gemv(c, p));
+            GemvParams q2{};
+            fill_seg(q2.seg[0], L.down, c->xa, nullptr, 0);
+            q2.n_seg = 1; q2.K = d.ffn; q2.x = c->hbuf; q2.epi = EPI_RESIDUAL; q2.residual = c->xb;
+            CK(launch_gemv(c, q2));
+        }
+        if (c->use_taps)
+            CK(cudaMemcpyAsync(c->taps + (size_t)(l + 1) * H, c->xa, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (mode != MODE_PREFILL) {
+        GemvParams p{};
+        fill_seg(p.seg[0], c->output.present() ? c->output : c->token_embd, c->logits, nullptr, 0);
+        p.n_seg = 1; p.K = H; p.x = c->xa; p.norm_w = c->output_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+        CK(launch_gemv(c, p));
+        if (mode == MODE_GREEDY && !only_gemv)
+            CK(launch_k(c, argmax_kernel, dim3(1), dim3(1024), 0, (const float*)c->logits, d.vocab, sl.d_state,
+                        sl.d_generated, kMaxGenerated));
+    }
+#undef CK
+    return cudaSuccess;
+}
+
+// Run one token: graph replay when enabled (captured lazily per slot and mode), else eager.
+static int run_token(b200_ctx* c, int slot_i, Mode mode) {
+    Slot& sl = c->slots[slot_i];
+    const bool graph = c->use_graph && !c->use_taps;
+    if (!graph) {
+        cudaError_t e = enqueue_token(c, slot_i, mode);
+        if (e != cudaSuccess) return fail(B200_ERR_OPERATION_FAILED, std::string("kernel launch: ") + cudaGetErrorString(e));
+        return B200_OK;
+    }
+    if (!sl.graph[mode]) {
+        uint64_t before = c->launches;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = enqueue_token(c, slot_i, mode);
+        cudaGraph_t g = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+        sl.graph_launches[mode] = c->launches - before;
+        c->launches = before;
+        if (e != cudaSuccess || e2 != cudaSuccess || !g) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            if (c->use_pdl) {  // retry once without programmatic edges
+                c->use_pdl = false;
+                return run_token(c, slot_i, mode);
+            }
+            return fail(B200_ERR_OPERATION_FAILED, std::string("graph capture failed: ") +
+                                                       cudaGetErrorString(e != cudaSuccess ? e : e2));
+        }
+        cudaError_t e3 = cudaGraphInstantiate(&sl.graph[mode], g, 0);
+        cudaGraphDestroy(g);
+        if (e3 != cudaSuccess) {
+            sl.graph[mode] = nullptr;
+            cudaGetLastError();
+            if (c->use_pdl) {
+                c->use_pdl = false;
+                return run_token(c, slot_i, mode);
+            }
+            return fail(B200_ERR_OPERATION_FAILED, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e3));
+        }
+    }
+    CU(cudaGraphLaunch(sl.graph[mode], c->stream));
+    c->launches += sl.graph_launches[mode];
+    return B200_OK;
+}
+
+static int check_slot(b200_ctx* c, int seq, const char* fn) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": null ctx");
+    if (!c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": context not finalized");
+    if (seq < 0 || seq >= (int)c->slots.size()) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": bad sequence slot");
+    return B200_OK;
+}
+static int check_token(b200_ctx* c, int seq, uint32_t token, const char* fn) {
+    if (token >= (uint32_t)c->d.vocab)
+        return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": token id " + std::to_string(token) + " exceeds vocab size");
+    if (c->slots[seq].host_pos + 1 > (uint64_t)c->d.max_seq_len)
+        return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": context length exceeded");
+    return B200_OK;
+}
+
+static int set_token(b200_ctx* c, Slot& sl, uint32_t token) {
+    *c->h_token = (int)token;
+    CU(cudaMemcpyAsync(&sl.d_state->token, c->h_token, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_out) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_forward"))) return rc;
+    if (!logits_out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_forward: null logits_out");
+    if ((rc = check_token(c, seq, token, "b200_forward"))) return rc;
+    CU(cudaSetDevice(c->par.device));
+    Slot& sl = c->slots[seq];
+    if ((rc = set_token(c, sl, token))) return rc;
+    if ((rc = run_token(c, seq, MODE_LOGITS))) return rc;
+    CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->d.vocab * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(logits_out, c->h_logits, (size_t)c->d.vocab * 4);
+    sl.host_pos++;
+    return B200_OK;
+}
+
+extern "C" int b200_prefill_token(b200_ctx* c, int seq, uint32_t token) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_prefill_token"))) return rc;
+    if ((rc = check_token(c, seq, token, "b200_prefill_token"))) return rc;
+    CU(cudaSetDevice(c->par.device));
+    Slot& sl = c->slots[seq];
+    if ((rc = set_token(c, sl, token))) return rc;
+    if ((rc = run_token(c, seq, MODE_PREFILL))) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // h_token is reused by the next call
+    sl.host_pos++;
+    return B200_OK;
+}
+
+extern "C" int b200_prefill(b200_ctx* c, int seq, const uint32_t* tokens, int n, float* logits_out) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_prefill"))) return rc;
+    if (!tokens || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: no tokens");
+    for (int i = 0; i < n; i++) {
+        if (i == n - 1 && logits_out) return b200_forward(c, seq, tokens[i], logits_out);
+        if ((rc = b200_prefill_token(c, seq, tokens[i]))) return rc;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_decode_batch(b200_ctx* c, const int* seqs, const uint32_t* tokens, int n, float* logits_out) {
+    if (!c || !seqs || !tokens || !logits_out || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch: bad argument");
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+            if (seqs[i] == seqs[j]) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch: duplicate sequence slot");
+    int rc;
+    for (int i = 0; i < n; i++)
+        if ((rc = b200_forward(c, seqs[i], tokens[i], logits_out + (size_t)i * c->d.vocab))) return rc;
+    return B200_OK;
+}
+
+extern "C" int b200_reset(b200_ctx* c, int seq) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_reset"))) return rc;
+    CU(cudaSetDevice(c->par.device));
+    Slot& sl = c->slots[seq];
+    CU(cudaMemsetAsync(sl.d_state, 0, sizeof(SeqState), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    sl.host_pos = 0;
+    return B200_OK;
+}
+
+extern "C" int b200_position(b200_ctx* c, int seq, uint64_t* out) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_position"))) return rc;
+    if (!out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_position: null out");
+    *out = c->slots[seq].host_pos;
+    return B200_OK;
+}
+
+extern "C" int b200_decode_greedy(b200_ctx* c, int seq, uint32_t first_token, int n_steps, uint32_t* tokens_out,
+                                  float* elapsed_ms) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_decode_greedy"))) return rc;
+    if (n_steps <= 0 || n_steps > kMaxGenerated) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: bad n_steps");
+    if (first_token >= (uint32_t)c->d.vocab) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: token exceeds vocab size");
+    Slot& sl = c->slots[seq];
+    if (sl.host_pos + (uint64_t)n_steps > (uint64_t)c->d.max_seq_len)
+        return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: context length exceeded");
+    CU(cudaSetDevice(c->par.device));
+    if ((rc = set_token(c, sl, first_token))) return rc;
+    CU(cudaMemsetAsync(&sl.d_state->n_generated, 0, sizeof(int), c->stream));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < n_steps; i++)
+        if ((rc = run_token(c, seq, MODE_GREEDY))) return rc;
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    sl.host_pos += (uint64_t)n_steps;
+    if (tokens_out) CU(cudaMemcpy(tokens_out, sl.d_generated, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_get_hidden(b200_ctx* c, int seq, int layer, float* out) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_get_hidden"))) return rc;
+    if (!c->use_taps) return fail(B200_ERR_UNSUPPORTED, "b200_get_hidden: taps are off (set B200_TAPS=1 before b200_ctx_create)");
+    if (layer < 0 || layer > c->d.n_layers || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_get_hidden: bad layer");
+    CU(cudaSetDevice(c->par.device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->taps + (size_t)layer * c->d.hidden, (size_t)c->d.hidden * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_stats: null ctx");
+    if (kernel_launches) *kernel_launches = c->launches;
+    if (weight_bytes) *weight_bytes = c->weight_bytes_per_token;
+    if (kv_bytes_per_pos) *kv_bytes_per_pos = (uint64_t)2 * c->d.n_layers * c->d.n_kv_heads * c->d.head_dim * 4;
+    return B200_OK;
+}
+
+// Roofline probe for bench.py: replays ONLY the gemv_kernel launches of one token (same
+// arguments, order and launch attributes as the decode graph; embedding / RoPE / attention /
+// argmax launches left out) `iters` times between two CUDA events on the launching stream.
+extern "C" int b200_bench_gemv_pass(b200_ctx* c, int seq, int iters, float* avg_ms_per_pass, uint64_t* launches_per_pass,
+                                    uint64_t* bytes_per_pass) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_bench_gemv_pass"))) return rc;
+    if (iters <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_bench_gemv_pass: iters <= 0");
+    CU(cudaSetDevice(c->par.device));
+    if (!c->gemv_graph) {
+        uint64_t before = c->launches;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = enqueue_token(c, seq, MODE_LOGITS, true);
+        cudaGraph_t g = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+        c->gemv_graph_launches = c->launches - before;
+        c->launches = before;
+        if (e != cudaSuccess || e2 != cudaSuccess || !g) {
+            cudaGetLastError();
+            return fail(B200_ERR_OPERATION_FAILED, "b200_bench_gemv_pass: capture failed");
+        }
+        cudaError_t e3 = cudaGraphInstantiate(&c->gemv_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e3 != cudaSuccess) return fail(B200_ERR_OPERATION_FAILED, "b200_bench_gemv_pass: instantiate failed");
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaGraphLaunch(c->gemv_graph, c->stream));  // warm-up
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; i++) CU(cudaGraphLaunch(c->gemv_graph, c->stream));
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->launches += c->gemv_graph_launches * (uint64_t)(iters + 1);
+    if (avg_ms_per_pass) *avg_ms_per_pass = ms / iters;
+    if (launches_per_pass) *launches_per_pass = c->gemv_graph_launches;
+    if (bytes_per_pass) *bytes_per_pass = c->weight_bytes_per_token - c->token_embd.row_bytes;
+    return B200_OK;
+}
+
+// Per-kernel GB/s: times plain vec_mat_q launches over resident weights.  A name with
+// "%d" walks every layer's tensor in order (footprint >> L2, the decode access pattern);
+// a plain name times one tensor and writes a 256 MB buffer between launches to flush L2.
+extern "C" int b200_bench_weight_gemv(b200_ctx* c, const char* gguf_name, int iters, float* avg_ms, uint64_t* bytes) {
+    if (!c || !c->finalized || !gguf_name || iters <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_bench_weight_gemv: bad argument");
+    CU(cudaSetDevice(c->par.device));
+    std::vector<const DevTensor*> ts;
+    if (strstr(gguf_name, "%d")) {
+        for (int l = 0; l < c->d.n_layers; l++) {
+            char nm[128];
+            snprintf(nm, sizeof nm, gguf_name, l);
+            auto it = c->tensors.find(nm);
+            if (it == c->tensors.end()) return fail(B200_ERR_INVALID_ARGUMENT, std::string("no tensor ") + nm);
+            ts.push_back(&it->second);
+        }
+    } else {
+        auto it = c->tensors.find(gguf_name);
+        if (it == c->tensors.end()) return fail(B200_ERR_INVALID_ARGUMENT, std::string("no tensor ") + gguf_name);
+        ts.push_back(&it->second);
+    }
+    uint64_t total = 0;
+    size_t max_k = 0;
+    for (const DevTensor* t : ts) {
+        if (t->n_dims != 2) return fail(B200_ERR_UNSUPPORTED, "b200_bench_weight_gemv: 2-D weights only");
+        if (t->ne[1] > c->out_scratch_elems) return fail(B200_ERR_UNSUPPORTED, "b200_bench_weight_gemv: output too large");
+        total += t->nbytes;
+        max_k = std::max<size_t>(max_k, t->ne[0]);
+    }
+    float* xin = nullptr;
+    CU_ALLOC(cudaMalloc((void**)&xin, max_k * 4));
+    CU(cudaMemset(xin, 0, max_k * 4));
+    const bool flush = ts.size() == 1;
+    if (flush && !c->flush_buf) {
+        c->flush_bytes = 256u << 20;
+        CU_ALLOC(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const bool pdl = c->use_pdl;
+    c->use_pdl = false;
+    double sum_ms = 0.0;
+    for (int it = -1; it < iters; it++) {  // it == -1: warm-up
+        if (flush) CU(cudaMemsetAsync(c->flush_buf, it & 0xff, c->flush_bytes, c->stream));
+        CU(cudaEventRecord(e0, c->stream));
+        for (const DevTensor* t : ts) {
+            GemvParams p{};
+            fill_seg(p.seg[0], *t, c->logits, nullptr, 0);
+            p.n_seg = 1; p.K = (int)t->ne[0]; p.x = xin; p.epi = EPI_STORE;
+            cudaError_t e = launch_gemv(c, p);
+            if (e != cudaSuccess) { c->use_pdl = pdl; return fail(B200_ERR_OPERATION_FAILED, cudaGetErrorString(e)); }
+        }
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 0) sum_ms += ms;
+    }
+    c->use_pdl = pdl;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(xin);
+    if (avg_ms) *avg_ms = (float)(sum_ms / iters);
+    if (bytes) *bytes = total;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ Backend per-op surface
+// Host in / host out, like CudaBackend's per-op path (src/backend/cuda/mod.rs:229-835).
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 4) == cudaSuccess ? 0 : -1; }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+int op_ready() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(B200_ERR_NOT_AVAILABLE, "cuda-b200: no CUDA device (this backend has no CPU fallback)");
+    }
+    return B200_OK;
+}
+int op_finish(const char* what) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200_ERR_OPERATION_FAILED, std::string(what) + ": " + cudaGetErrorString(e));
+    return B200_OK;
+}
+int elementwise(int op, const float* a, const float* b, float s, float* out, size_t n, const char* what) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!a || !out || (op <= EW_MUL && !b)) return fail(B200_ERR_INVALID_ARGUMENT, std::string(what) + ": null pointer");
+    if (n == 0) return B200_OK;
+    DevBuf da, db, dout;
+    if (da.alloc(n * 4) || db.alloc(n * 4) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, what);
+    CU(cudaMemcpy(da.p, a, n * 4, cudaMemcpyHostToDevice));
+    if (b) CU(cudaMemcpy(db.p, b, n * 4, cudaMemcpyHostToDevice));
+    int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    elementwise_kernel<<<grid, 256>>>(op, da.as<float>(), db.as<float>(), s, dout.as<float>(), (long long)n);
+    if ((rc = op_finish(what))) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+}  // namespace
+
+extern "C" int b200_op_add(const float* a, const float* b, float* out, size_t n) { return elementwise(EW_ADD, a, b, 0, out, n, "add"); }
+extern "C" int b200_op_mul(const float* a, const float* b, float* out, size_t n) { return elementwise(EW_MUL, a, b, 0, out, n, "mul"); }
+extern "C" int b200_op_scale(const float* a, float s, float* out, size_t n) { return elementwise(EW_SCALE, a, nullptr, s, out, n, "scale"); }
+extern "C" int b200_op_silu(const float* x, float* out, size_t n) { return elementwise(EW_SILU, x, nullptr, 0, out, n, "silu"); }
+extern "C" int b200_op_gelu(const float* x, float* out, size_t n) { return elementwise(EW_GELU, x, nullptr, 0, out, n, "gelu"); }
+
+extern "C" int b200_op_softmax(const float* x, float* out, size_t n) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!x || !out) return fail(B200_ERR_INVALID_ARGUMENT, "softmax: null pointer");
+    if (n == 0) return B200_OK;
+    DevBuf dx, dout;
+    if (dx.alloc(n * 4) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "softmax");
+    CU(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
+    softmax_rows_kernel<<<1, 256>>>(dx.as<float>(), dout.as<float>(), (int)n);
+    if ((rc = op_finish("softmax"))) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_rms_norm(const float* x, const float* w, float eps, float* out, size_t n_rows, size_t hidden) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!x || !w || !out) return fail(B200_ERR_INVALID_ARGUMENT, "rms_norm: null pointer");
+    if (n_rows == 0 || hidden == 0) return fail(B200_ERR_SHAPE_MISMATCH, "rms_norm: empty shape");
+    size_t n = n_rows * hidden;
+    DevBuf dx, dw, dout;
+    if (dx.alloc(n * 4) || dw.alloc(hidden * 4) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "rms_norm");
+    CU(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw.p, w, hidden * 4, cudaMemcpyHostToDevice));
+    rms_norm_rows_kernel<<<(int)n_rows, 256>>>(dx.as<float>(), dw.as<float>(), eps, dout.as<float>(), (int)hidden);
+    if ((rc = op_finish("rms_norm"))) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_vec_mat(const float* a, const float* w, float* out, size_t k, size_t n) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!a || !w || !out) return fail(B200_ERR_INVALID_ARGUMENT, "vec_mat: null pointer");
+    if (k == 0 || n == 0) return fail(B200_ERR_SHAPE_MISMATCH, "vec_mat: empty shape");
+    DevBuf da, dw, dout;
+    if (da.alloc(k * 4) || dw.alloc(k * n * 4) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat");
+    CU(cudaMemcpy(da.p, a, k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw.p, w, k * n * 4, cudaMemcpyHostToDevice));
+    vec_mat_f32_kernel<<<(int)((n * 32 + 255) / 256), 256>>>(da.as<float>(), dw.as<float>(), dout.as<float>(), (int)k, (int)n);
+    if ((rc = op_finish("vec_mat"))) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t k, size_t n) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!a || !w || !out) return fail(B200_ERR_INVALID_ARGUMENT, "vec_mat_q: null pointer");
+    const int t = (int)ggml_type;
+    if (!type_supported(t)) return fail(B200_ERR_UNSUPPORTED_DTYPE, "vec_mat_q: unsupported ggml type " + std::to_string(ggml_type));
+    const int be = type_block_elems(t), bb = type_block_bytes(t);
+    if (k == 0 || n == 0 || k % be || k % 32) return fail(B200_ERR_SHAPE_MISMATCH, "vec_mat_q: k must be a non-zero multiple of the block size and of 32");
+    const size_t row_bytes = k / be * bb, wbytes = row_bytes * n;
+    DevBuf da, dw, dout;
+    if (da.alloc(k * 4) || dw.alloc(wbytes + 256) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat_q");
+    CU(cudaMemcpy(da.p, a, k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    GemvParams p{};
+    p.seg[0].w = dw.as<uint8_t>(); p.seg[0].out = dout.as<float>(); p.seg[0].row_bytes = (long long)row_bytes;
+    p.seg[0].type = t; p.seg[0].n_rows = (int)n;
+    p.n_seg = 1; p.K = (int)k; p.x = da.as<float>(); p.epi = EPI_STORE;
+    int n_tasks = (int)((n + kGemvR - 1) / kGemvR);
+    int grid = std::max(1, std::min((n_tasks + kGemvWarps - 1) / kGemvWarps, 296));
+    size_t smem = (size_t)xpad_floats((int)k) * sizeof(float);
+    if (smem > 160 * 1024) return fail(B200_ERR_UNSUPPORTED, "vec_mat_q: k too large for the shared-memory x staging");
+    gemv_kernel<<<grid, kGemvThreads, smem>>>(p);
+    if ((rc = op_finish("vec_mat_q"))) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_dequantize(const void* src, uint32_t ggml_type, float* out, size_t n_elems) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!src || !out) return fail(B200_ERR_INVALID_ARGUMENT, "dequantize: null pointer");
+    const int t = (int)ggml_type;
+    if (!type_supported(t)) return fail(B200_ERR_UNSUPPORTED_DTYPE, "dequantize: unsupported ggml type " + std::to_string(ggml_type));
+    const int be = type_block_elems(t), bb = type_block_bytes(t);
+    if (n_elems % be) return fail(B200_ERR_SHAPE_MISMATCH, "dequantize: element count not a multiple of the block size");
+    if (n_elems == 0) return B200_OK;
+    const size_t nbytes = n_elems / be * bb;
+    DevBuf ds, dout;
+    if (ds.alloc(nbytes) || dout.alloc(n_elems * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "dequantize");
+    CU(cudaMemcpy(ds.p, src, nbytes, cudaMemcpyHostToDevice));
+    int grid = (int)std::min<size_t>((n_elems + 255) / 256, 148 * 16);
+    dequantize_kernel<<<grid, 256>>>(t, ds.as<uint8_t>(), (long long)n_elems, dout.as<float>());
+    if ((rc = op_finish("dequantize"))) return rc;
+    CU(cudaMemcpy(out, dout.p, n_elems * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_rope(float* q, float* k, int n_heads, int n_kv_heads, int head_dim, int pos, float freq_base,
+                            float freq_scale, int use_neox) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!q || !k) return fail(B200_ERR_INVALID_ARGUMENT, "rope: null pointer");
+    if (n_heads <= 0 || n_kv_heads <= 0 || head_dim <= 0 || (head_dim & 1) || pos < 0)
+        return fail(B200_ERR_INVALID_ARGUMENT, "RoPE requires 3D tensors [num_heads, seq_len, head_dim] with even head_dim");
+    if (freq_scale == 0.0f) freq_scale = 1.0f;
+    std::vector<float> f(head_dim / 2);
+    for (int i = 0; i < head_dim / 2; i++) f[i] = 1.0f / powf(freq_base, (float)(2 * i) / (float)head_dim);
+    const size_t nq = (size_t)n_heads * head_dim, nk = (size_t)n_kv_heads * head_dim;
+    DevBuf dq, dk, df;
+    if (dq.alloc(nq * 4) || dk.alloc(nk * 4) || df.alloc(f.size() * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "rope");
+    CU(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk.p, k, nk * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(df.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    int work = (n_heads + n_kv_heads) * head_dim / 2;
+    rope_inplace_kernel<<<(work + 255) / 256, 256>>>(dq.as<float>(), dk.as<float>(), df.as<float>(), n_heads, n_kv_heads,
+                                                     head_dim, pos, freq_scale, use_neox);
+    if ((rc = op_finish("rope"))) return rc;
+    CU(cudaMemcpy(q, dq.p, nq * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(k, dk.p, nk * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_attention_cached(const float* q, const float* k_cache, const float* v_cache, float* out,
+                                        int n_heads, int n_kv_heads, int head_dim, int max_seq, float scale, int kv_len) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!q || !k_cache || !v_cache || !out) return fail(B200_ERR_INVALID_ARGUMENT, "attention_cached: null pointer");
+    if (n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || kv_len <= 0 || kv_len > max_seq)
+        return fail(B200_ERR_INVALID_ARGUMENT, "attention_cached: bad head counts or kv_len");
+    const int G = n_heads / n_kv_heads;
+    if ((head_dim != 64 && head_dim != 128) || G > 8)
+        return fail(B200_ERR_UNSUPPORTED, "attention_cached: head_dim must be 64 or 128 and at most 8 query heads per kv head");
+    const size_t nq = (size_t)n_heads * head_dim, nc = (size_t)n_kv_heads * max_seq * head_dim;
+    const int n_splits = std::max(1, std::min(32, (kv_len + 63) / 64));
+    DevBuf dq, dk, dv, dout, dpart, dtick;
+    if (dq.alloc(nq * 4) || dk.alloc(nc * 4) || dv.alloc(nc * 4) || dout.alloc(nq * 4) ||
+        dpart.alloc((size_t)n_kv_heads * n_splits * G * (head_dim + 2) * 4) || dtick.alloc(n_kv_heads * 4))
+        return fail(B200_ERR_ALLOCATION_FAILED, "attention_cached");
+    CU(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk.p, k_cache, nc * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dv.p, v_cache, nc * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dtick.p, 0, n_kv_heads * 4));
+    AttnParams ap{};
+    ap.q = dq.as<float>(); ap.k_cache = dk.as<float>(); ap.v_cache = dv.as<float>(); ap.out = dout.as<float>();
+    ap.part = dpart.as<float>(); ap.tickets = dtick.as<unsigned int>(); ap.pos = nullptr; ap.kv_len_fixed = kv_len;
+    ap.n_kv = n_kv_heads; ap.G = G; ap.max_seq = max_seq; ap.n_splits = n_splits; ap.scale = scale;
+    dim3 grid(n_kv_heads, n_splits);
+    CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    if (head_dim == 128) {
+        if (G <= 4) attn_decode_kernel<128, 4><<<grid, kAttnThreads, attn_smem_bytes(128, 4)>>>(ap);
+        else attn_decode_kernel<128, 8><<<grid, kAttnThreads, attn_smem_bytes(128, 8)>>>(ap);
+    } else {
+        if (G <= 4) attn_decode_kernel<64, 4><<<grid, kAttnThreads, attn_smem_bytes(64, 4)>>>(ap);
+        else attn_decode_kernel<64, 8><<<grid, kAttnThreads, attn_smem_bytes(64, 8)>>>(ap);
+    }
+    if ((rc = op_finish("attention_cached"))) return rc;
+    CU(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_op_attention(const float* q, const float* k, const float* v, float* out, int n_heads, int n_kv_heads,
+                                 int seq_len, int head_dim, float scale) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!q || !k || !v || !out) return fail(B200_ERR_INVALID_ARGUMENT, "attention: null pointer");
+    if (n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || seq_len <= 0 || head_dim <= 0 || head_dim > 256)
+        return fail(B200_ERR_INVALID_ARGUMENT, "Attention requires 3D tensors with head_dim <= 256");
+    const size_t nq = (size_t)n_heads * seq_len * head_dim, nk = (size_t)n_kv_heads * seq_len * head_dim;
+    DevBuf dq, dk, dv, dout;
+    if (dq.alloc(nq * 4) || dk.alloc(nk * 4) || dv.alloc(nk * 4) || dout.alloc(nq * 4))
+        return fail(B200_ERR_ALLOCATION_FAILED, "attention");
+    CU(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk.p, k, nk * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dv.p, v, nk * 4, cudaMemcpyHostToDevice));
+    int warps = n_heads * seq_len;
+    attention_full_kernel<<<(warps * 32 + 255) / 256, 256>>>(dq.as<float>(), dk.as<float>(), dv.as<float>(), dout.as<float>(),
+                                                            n_heads, n_kv_heads, seq_len, seq_len, head_dim, scale);
+    if ((rc = op_finish("attention"))) return rc;
+    CU(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
