@@ -317,22 +317,32 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
         for (int s = 0; s < 3; s++) t0[s + 1] = t0[s] + (s < p.n_seg ? (p.seg[s].n_rows + kGemvR - 1) / kGemvR : 0);
     }
     const int n_tasks = t0[3];
-    const long long eoff = p.expert_sel ? (long long)p.expert_sel[p.expert_slot] : 0;
 
     pdl_launch_dependents();
-    {   // weights do not depend on the predecessor: pull this warp's first rows towards L2 before waiting
+    if (!p.expert_sel) {  // dense weights do not depend on the predecessor: pull this warp's first rows towards L2
         int task = blockIdx.x * kGemvWarps + warp;
-        if (task < n_tasks && p.epi != EPI_SWIGLU) {
-            int s = (task >= t0[2]) ? 2 : (task >= t0[1]) ? 1 : 0;
-            const GemvSeg& sg = p.seg[s];
-            int row0 = (task - t0[s]) * kGemvR;
-            int rows = min(kGemvR, sg.n_rows - row0);
-            const uint8_t* base = sg.w + eoff * sg.expert_stride + (long long)row0 * sg.row_bytes;
-            long long bytes = (long long)rows * sg.row_bytes;
-            for (long long o = (long long)lane * 128; o < bytes; o += 32 * 128) prefetch_l2(base + o);
+        if (task < n_tasks) {
+            if (p.epi == EPI_SWIGLU) {
+                const long long off = (long long)task * 2;
+                const long long bytes = 2 * p.seg[0].row_bytes;
+                for (long long o = (long long)lane * 128; o < bytes; o += 32 * 128) {
+                    prefetch_l2(p.seg[0].w + off * p.seg[0].row_bytes + o);
+                    prefetch_l2(p.seg[1].w + off * p.seg[1].row_bytes + o);
+                }
+            } else {
+                int s = (task >= t0[2]) ? 2 : (task >= t0[1]) ? 1 : 0;
+                const GemvSeg& sg = p.seg[s];
+                int row0 = (task - t0[s]) * kGemvR;
+                int rows = min(kGemvR, sg.n_rows - row0);
+                const uint8_t* base = sg.w + (long long)row0 * sg.row_bytes;
+                long long bytes = (long long)rows * sg.row_bytes;
+                for (long long o = (long long)lane * 128; o < bytes; o += 32 * 128) prefetch_l2(base + o);
+            }
         }
     }
     pdl_wait();
+    // MoE: the selected expert is written by the routing kernel (a predecessor): read it only after the wait
+    const long long eoff = p.expert_sel ? (long long)p.expert_sel[p.expert_slot] : 0;
     stage_x(p, xs, red);
 
     for (int task = blockIdx.x * kGemvWarps + warp; task < n_tasks; task += gridDim.x * kGemvWarps) {
