@@ -21,6 +21,7 @@
 // kv_len * 1e-8 of the output — far below the 1e-3 parity tolerance.
 #pragma once
 #include "common.cuh"
+#include "gemv2.cuh"
 
 namespace b200 {
 
@@ -87,7 +88,14 @@ struct AttnParams {
     int kv_len_fixed;      // used when pos == nullptr
     int n_kv, G, max_seq, n_splits;
     float scale;
+    XPrep y;               // optional: the O-projection's prepared input (y.hi == nullptr: none)
 };
+
+// KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
+constexpr int kAttnMinChunk = 256;
+__device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits) {
+    return max(1, min(n_splits, (kv_len + kAttnMinChunk - 1) / kAttnMinChunk));
+}
 
 // merge (m, l, acc) <- (m, l, acc) (+) (m2, l2, acc2)
 __device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca, float& cb, float& mo) {
@@ -113,7 +121,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     pdl_wait();
 
     const int kv_len = p.pos ? (*p.pos + 1) : p.kv_len_fixed;
-    int chunk = (kv_len + p.n_splits - 1) / p.n_splits;
+    const int ns = attn_eff_splits(kv_len, p.n_splits);
+    if (split >= ns) return;
+    int chunk = (kv_len + ns - 1) / ns;
     chunk = (chunk + kAttnWarps - 1) / kAttnWarps * kAttnWarps;
     const int start = split * chunk;
     const int end = min(kv_len, start + chunk);
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     }
     __syncthreads();
     const int part_stride = HD + 2;
-    float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;
+    float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;  // slots sized for n_splits
     for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {
         const int g = idx / HD, d = idx - g * HD;
         float M = -INFINITY;
@@ -215,27 +225,59 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[kh], 1u);
     __syncthreads();
-    if (s_ticket != (unsigned)(p.n_splits - 1)) return;
+    if (s_ticket != (unsigned)(ns - 1)) return;
     __threadfence();
     const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
-    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {
-        const int g = idx / HD, d = idx - g * HD;
+    // reuse shared memory: coef[ns][GMAX] and 1/L[GMAX]   (ns <= 64, so <= 64*8+8 floats)
+    float* s_coef = sm;
+    float* s_linv = sm + 64 * GMAX;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ns * G; idx += kAttnThreads) {
+        const int s = idx / G, g = idx - s * G;
+        s_coef[s * GMAX + g] = __ldcg(parts + ((size_t)s * G + g) * part_stride + HD);  // m of split s
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
         float M = -INFINITY;
-        for (int s = 0; s < p.n_splits; s++) M = fmaxf(M, __ldcg(parts + ((size_t)s * G + g) * part_stride + HD));
-        float L = 0.0f, A = 0.0f;
-        for (int s = 0; s < p.n_splits; s++) {
-            const float* ps = parts + ((size_t)s * G + g) * part_stride;
-            const float ms = __ldcg(ps + HD);
+        for (int s = 0; s < ns; s++) M = fmaxf(M, s_coef[s * GMAX + g]);
+        float L = 0.0f;
+        for (int s = 0; s < ns; s++) {
+            const float ms = s_coef[s * GMAX + g];
             const float c = (ms == -INFINITY) ? 0.0f : expf(ms - M);
-            L += __ldcg(ps + HD + 1) * c;
-            A += __ldcg(ps + d) * c;
+            s_coef[s * GMAX + g] = c;
+            L += __ldcg(parts + ((size_t)s * G + g) * part_stride + HD + 1) * c;
         }
-        p.out[((size_t)(kh * G + g)) * HD + d] = A / L;
+        s_linv[g] = 1.0f / L;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {  // G*HD is a multiple of 256 or smaller: see below
+        const int g = idx / HD, d = idx - g * HD;
+        float A = 0.0f;
+#pragma unroll 8
+        for (int s = 0; s < ns; s++) A += __ldcg(parts + ((size_t)s * G + g) * part_stride + d) * s_coef[s * GMAX + g];
+        const float o = A * s_linv[g];
+        const int e = (kh * G + g) * HD + d;
+        p.out[e] = o;
+        if (p.y.hi) {  // prepared input of the O projection (gemv2.cuh: fp16 hi/lo in fragment order + 16-element sums)
+            const float yv = fminf(fmaxf(o, -65504.0f), 65504.0f);
+            const __half hh = __float2half_rn(yv);
+            const __half ll = __float2half_rn(yv - __half2float(hh));
+            float xs = __half2float(hh) + __half2float(ll);
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) xs += __shfl_xor_sync(0xffffffffu, xs, off, 16);
+            p.y.hi[xperm(e)] = hh;
+            p.y.lo[xperm(e)] = ll;
+            if ((d & 15) == 0) p.y.xs16[e >> 4] = xs;
+        }
     }
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }
 
-inline size_t attn_smem_bytes(int hd, int gmax) { return (size_t)(2 * kAttnWarps * gmax + kAttnWarps * gmax * hd) * sizeof(float); }
+inline size_t attn_smem_bytes(int hd, int gmax) {
+    size_t a = (size_t)(2 * kAttnWarps * gmax + kAttnWarps * gmax * hd), b = (size_t)(64 * gmax + gmax);
+    return (a > b ? a : b) * sizeof(float);
+}
 
 // Backend::attention (cpu/ops.rs:1353-1470): causal, q[n_heads][seq][hd], k/v[n_kv][kv_len][hd].
 // Compatibility surface only (the model path uses attention_cached): one warp per (head, query).
