@@ -21,7 +21,6 @@
 // kv_len * 1e-8 of the output — far below the 1e-3 parity tolerance.
 #pragma once
 #include "common.cuh"
-#include "gemv2.cuh"
 
 namespace b200 {
 
@@ -88,7 +87,6 @@ struct AttnParams {
     int kv_len_fixed;      // used when pos == nullptr
     int n_kv, G, max_seq, n_splits;
     float scale;
-    XPrep y;               // optional: the O-projection's prepared input (y.hi == nullptr: none)
 };
 
 // KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
@@ -257,19 +255,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
 #pragma unroll 8
         for (int s = 0; s < ns; s++) A += __ldcg(parts + ((size_t)s * G + g) * part_stride + d) * s_coef[s * GMAX + g];
         const float o = A * s_linv[g];
-        const int e = (kh * G + g) * HD + d;
-        p.out[e] = o;
-        if (p.y.hi) {  // prepared input of the O projection (gemv2.cuh: fp16 hi/lo in fragment order + 16-element sums)
-            const float yv = fminf(fmaxf(o, -65504.0f), 65504.0f);
-            const __half hh = __float2half_rn(yv);
-            const __half ll = __float2half_rn(yv - __half2float(hh));
-            float xs = __half2float(hh) + __half2float(ll);
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) xs += __shfl_xor_sync(0xffffffffu, xs, off, 16);
-            p.y.hi[xperm(e)] = hh;
-            p.y.lo[xperm(e)] = ll;
-            if ((d & 15) == 0) p.y.xs16[e >> 4] = xs;
-        }
+        p.out[(kh * G + g) * HD + d] = o;
     }
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }
