@@ -23,6 +23,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemv.cuh"
+#include "gemv_mma.cuh"
 #include "misc.cuh"
 #include "quant.cuh"
 
@@ -110,6 +111,15 @@ struct b200_ctx {
     int* moe_sel = nullptr;
     unsigned int* tickets = nullptr;
     int n_splits = 1;
+    // tensor-pipe GEMV (gemv_mma.cuh): stream-K scratch, watchdog flag, launch knobs
+    float* mma_part = nullptr;
+    unsigned int* mma_tickets = nullptr;
+    int* mma_err = nullptr;
+    int mma_tickets_n = 0;
+    bool use_mma = true;
+    int mma_chunk = 512, mma_warps = 16, mma_stages = 2;
+    size_t smem_optin = 227 * 1024;
+    uint64_t mma_launches = 0, v1_launches = 0;
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
@@ -184,6 +194,11 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_graph = env_int("B200_GRAPH", 1) != 0;
     c->use_pdl = env_int("B200_PDL", 1) != 0;
     c->use_taps = env_int("B200_TAPS", 0) != 0;
+    c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
+    c->mma_chunk = env_int("B200_MMA_CHUNK", 512) == 1024 ? 1024 : 512;
+    c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
+    c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 2)));
+    c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     c->layers.resize(d.n_layers);
     *out = c;
     return B200_OK;
@@ -328,6 +343,12 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     CU_ALLOC(cudaMalloc((void**)&c->attn_part, nkv * c->n_splits * (nh / nkv) * (hd + 2) * 4));
     CU_ALLOC(cudaMalloc((void**)&c->tickets, nkv * sizeof(unsigned int)));
     CU(cudaMemset(c->tickets, 0, nkv * sizeof(unsigned int)));
+    CU_ALLOC(cudaMalloc((void**)&c->mma_part, (size_t)c->n_sm * kMmaMaxWarps * 2 * 32 * sizeof(float)));
+    c->mma_tickets_n = (int)((std::max<uint64_t>(std::max<uint64_t>(V, ffn_w), (nh + 2 * nkv) * hd) + 15) / 16 + 8);
+    CU_ALLOC(cudaMalloc((void**)&c->mma_tickets, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
+    CU(cudaMemset(c->mma_tickets, 0, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
+    CU_ALLOC(cudaMalloc((void**)&c->mma_err, sizeof(int)));
+    CU(cudaMemset(c->mma_err, 0, sizeof(int)));
     CU_ALLOC(cudaMalloc((void**)&c->moe_sel, 8 * sizeof(int)));
     CU_ALLOC(cudaMalloc((void**)&c->moe_wt, 8 * sizeof(float)));
     CU(cudaMemset(c->moe_sel, 0, 8 * sizeof(int)));
@@ -355,6 +376,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     }
     // kernels that may need more than 48 KB of dynamic shared memory
     CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(mma_set_smem_limit((int)c->smem_optin - 1024));
     CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     c->finalized = true;
     return B200_OK;
@@ -375,7 +397,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     }
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
-                    (void*)c->rope_freq, c->flush_buf})
+                    (void*)c->rope_freq, c->flush_buf, (void*)c->mma_part, (void*)c->mma_tickets, (void*)c->mma_err})
         cudaFree(p);
     if (c->h_logits) cudaFreeHost(c->h_logits);
     if (c->h_token) cudaFreeHost(c->h_token);
@@ -394,7 +416,35 @@ static void fill_seg(GemvSeg& s, const DevTensor& w, float* out, const DevTensor
     s.n_rows = (int)w.ne[1];
 }
 
+// Tensor-pipe kernel when the launch is eligible (K-quants / Q8_0, shapes that fit), else the CUDA-core kernel.
+static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& plan) {
+    m = MParams{};
+    for (int s = 0; s < p.n_seg; s++) {
+        MSeg& d = m.seg[s];
+        const GemvSeg& g = p.seg[s];
+        d.w = g.w; d.out = g.out; d.bias = g.bias; d.row_bytes = g.row_bytes; d.expert_stride = g.expert_stride;
+        d.type = g.type; d.n_rows = g.n_rows;
+    }
+    m.n_seg = p.n_seg; m.K = p.K; m.x = p.x; m.norm_w = p.norm_w; m.eps = p.eps; m.residual = p.residual;
+    m.epi = p.epi == EPI_STORE ? ME_STORE : p.epi == EPI_RESIDUAL ? ME_RESIDUAL : p.epi == EPI_SWIGLU ? ME_SWIGLU : ME_SCALED_ACC;
+    m.expert_sel = p.expert_sel; m.expert_wt = p.expert_wt; m.expert_slot = p.expert_slot;
+    m.part = c->mma_part; m.tickets = c->mma_tickets; m.err = c->mma_err;
+    if (!mma_plan(m, c->n_sm, c->mma_chunk, c->mma_warps, c->mma_stages, c->smem_optin - 1024, plan)) return false;
+    int tiles = 0;
+    for (int s = 0; s < m.n_seg; s++) tiles += m.seg[s].n_tiles;
+    return tiles <= c->mma_tickets_n;
+}
+
 static cudaError_t launch_gemv(b200_ctx* c, GemvParams& p) {
+    if (c->use_mma) {
+        MParams m;
+        MPlan plan;
+        if (to_mma_params(c, p, m, plan)) {
+            c->mma_launches++;
+            return launch_k(c, mma_kernel_for(plan.warps), dim3(plan.grid), dim3(plan.warps * 32), plan.smem, m);
+        }
+    }
+    c->v1_launches++;
     int n_tasks;
     if (p.epi == EPI_SWIGLU) {
         n_tasks = (p.seg[0].n_rows + 1) / 2;

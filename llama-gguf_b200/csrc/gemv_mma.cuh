@@ -9,11 +9,13 @@
 //
 // Why this shape (profiles/r01_v1_*: the CUDA-core version spent ~6 issue slots per weight
 // and stalled at 1.2 TB/s):
-//  * weights go HBM -> shared memory with cp.async.bulk (TMA bulk copies, SASS UBLKCP) into
-//    PER-WARP mbarrier rings.  A unit is 16 rows x 512 (or 1024) elements, one bulk copy per
-//    row; a warp produces and consumes its own ring, so there is no cross-warp hand-off and
-//    the first stages are issued BEFORE griddepcontrol.wait (weights never depend on the
-//    previous kernel of the token);
+//  * weights go HBM -> shared memory with 16-byte cp.async (SASS LDGSTS) into PER-WARP rings.
+//    A unit is 16 rows x 512 (or 1024) elements; a lane moves 16-byte pieces of two rows, so an
+//    instruction covers 8 rows x 64 contiguous bytes and costs no address arithmetic.  (Per-row
+//    cp.async.bulk copies measured slower: UBLKCP is issued one lane at a time, ~10 issue slots
+//    per 288-byte copy, profiles/r01_v2_*.)  A warp produces and consumes its own ring, so
+//    there is no cross-warp hand-off and the first stages are issued BEFORE
+//    griddepcontrol.wait (weights never depend on the previous kernel of the token);
 //  * dot products run on the tensor pipe (mma.sync.m16n8k16, SASS HMMA): quants become exact
 //    fp16 integers with one LOP3/PRMT per two elements ((w & 0x000F000F) | 0x6400_6400 =
 //    1024+q), x is split into fp16 hi + lo parts (x = hi + lo to 2^-22) that sit in two
@@ -49,7 +51,10 @@ struct MSeg {
     int n_rows;
     int n_tiles;           // ceil(n_rows / 16)
     int unit0;             // first unit of this segment in the launch
-    int row_stride;        // bytes between row slots of a ring stage
+    int row_stride;        // pitch of the row slots of a ring stage
+    int cb;                // blocks per chunk
+    int chunk_bytes;       // cb * block bytes
+    int nb_row;            // blocks per row (K / block elems)
 };
 
 struct MParams {
@@ -76,6 +81,7 @@ struct MParams {
     float* part;             // [grid*warps][2][32]
     unsigned int* tickets;   // [total logical tiles], zero between launches
     int* err;                // device error flag (watchdog)
+    unsigned long long* dbg; // optional [grid*warps][8] globaltimer stamps (lab only)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -119,7 +125,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -129,34 +135,43 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(mask), "r"(orv));  // (a & mask) | orv
     return r;
 }
+// Shared-memory loads are NOT volatile so that ptxas/nvcc may interleave them with the MMAs of neighbouring
+// blocks.  Ordering against the cp.async pipeline comes from data dependencies: every address is derived from an
+// opaque token produced after the wait (smem_token), and the unit's results are pinned before the stage is refilled.
+__device__ __forceinline__ uint32_t smem_token() {
+    uint32_t t;
+    asm volatile("mov.u32 %0, 0;" : "=r"(t)::"memory");
+    return t;
+}
+__device__ __forceinline__ void pin2(float& a, float& b) { asm volatile("" : "+f"(a), "+f"(b)::"memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
     uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
     unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
     return (uint32_t)v;
 }
 __device__ __forceinline__ int lds_s8(uint32_t a) {
     int v;
-    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+    asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t a) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
 // 16 bytes at a 2-byte-aligned shared address: 5 aligned words + funnel shifts (shift 0 or 16)
@@ -183,47 +198,110 @@ constexpr uint32_t kMagic = 0x64006400u;  // half2(1024, 1024)
 // xs16[i] = sum of float(hi)+float(lo) over elements 16i..16i+15.
 struct XSmem {
     uint32_t xh, xl, xs;  // shared-space byte addresses
+    uint32_t zero;        // 256 bytes of zeros: the B operand of lanes whose column pair is not addressed
 };
 __host__ __device__ __forceinline__ int xperm(int e) { return (e & ~3) | (((e & 1) << 1) | ((e >> 1) & 1)); }
-__host__ __device__ inline size_t x_smem_bytes(int K) { return ((size_t)4 * K + (size_t)(K >> 2) + 127) & ~(size_t)127; }
+// the lo array sits 64 bytes off a multiple of 128 from the hi array: the hi and lo lanes of a B-fragment
+// load hit different banks
+constexpr uint32_t kXlPad = 64;
+// hi[K] + pad + lo[K] halves, xs16[K/16] floats, 256 zero bytes
+__host__ __device__ inline size_t x_smem_bytes(int K) { return (((size_t)4 * K + kXlPad + (size_t)(K >> 2) + 127) & ~(size_t)127) + 256; }
 
-// All threads of the CTA.  K % 16 == 0.  Optional RMSNorm: y = (x * inv) * w (simd.rs:891-892).
-__device__ __forceinline__ void stage_x_split(const float* __restrict__ x, const float* __restrict__ norm_w, float eps, int K,
-                                              uint8_t* smem, float* red /*[kMmaMaxWarps]*/) {
+// x staging, all threads of the CTA, K % 16 == 0.  Optional RMSNorm: y = (x * inv) * w (simd.rs:891-892).
+// The vector is scaled by a power of two (exact) so that its largest element sits near 2^12: the fp16 hi/lo
+// split then keeps ~22 bits relative to the largest element whatever the magnitude of x.
+//   stage_x_load : issues the global loads of x (and the norm weight) and reduces sum(x^2), max|x*w| per
+//                  thread; the first kXRegs float4 of each thread stay in registers for the second pass
+//   stage_x_split: block-reduces, then writes hi / lo / xs16 to shared memory; returns 2^-k for the epilogue
+constexpr int kXRegs = 4;
+struct XStage {
+    float4 v[kXRegs];
+    float ss, am;
+};
+__device__ __forceinline__ void stage_x_load(XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K,
+                                             float* red) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    float ss = 0.0f, am = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kXRegs; i++) {
+        const int e = (tid + i * nthr) * 4;
+        st.v[i] = (e < K) ? *reinterpret_cast<const float4*>(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kXRegs; i++) {
+        const int e = (tid + i * nthr) * 4;
+        const float4 v = st.v[i];
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (norm_w && e < K) w = *reinterpret_cast<const float4*>(norm_w + e);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        am = fmaxf(fmaxf(am, fmaxf(fabsf(v.x * w.x), fabsf(v.y * w.y))), fmaxf(fabsf(v.z * w.z), fabsf(v.w * w.w)));
+    }
+    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (norm_w) w = *reinterpret_cast<const float4*>(norm_w + e);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        am = fmaxf(fmaxf(am, fmaxf(fabsf(v.x * w.x), fabsf(v.y * w.y))), fmaxf(fabsf(v.z * w.z), fabsf(v.w * w.w)));
+    }
+    ss = warp_sum(ss);
+    am = warp_max(am);
+    if ((tid & 31) == 0) { red[tid >> 5] = ss; red[kMmaMaxWarps + (tid >> 5)] = am; }
+    st.ss = ss;
+    st.am = am;
+}
+__device__ __forceinline__ void split_store4(float4 v, int e, const float* __restrict__ norm_w, float inv, float up, __half* xh,
+                                             __half* xl, float* xs, unsigned mask) {
+    if (norm_w) {
+        const float4 w = *reinterpret_cast<const float4*>(norm_w + e);
+        v.x = (v.x * inv) * w.x; v.y = (v.y * inv) * w.y; v.z = (v.z * inv) * w.z; v.w = (v.w * inv) * w.w;
+    }
+    v.x *= up; v.y *= up; v.z *= up; v.w *= up;
+    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+    const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+    uint2 ph, pl;  // stored order [x0, x2, x1, x3]
+    ph.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h2) << 16);
+    ph.y = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h3) << 16);
+    pl.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l2) << 16);
+    pl.y = (uint32_t)__half_as_ushort(l1) | ((uint32_t)__half_as_ushort(l3) << 16);
+    *reinterpret_cast<uint2*>(xh + e) = ph;
+    *reinterpret_cast<uint2*>(xl + e) = pl;
+    float sum = ((__half2float(h0) + __half2float(l0)) + (__half2float(h1) + __half2float(l1))) +
+                ((__half2float(h2) + __half2float(l2)) + (__half2float(h3) + __half2float(l3)));
+    sum += __shfl_xor_sync(mask, sum, 1);
+    sum += __shfl_xor_sync(mask, sum, 2);
+    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum;
+}
+__device__ __forceinline__ float stage_x_split(const XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w,
+                                              float eps, int K, uint8_t* smem, float* red /*[2 * kMmaMaxWarps]*/) {
     const int tid = threadIdx.x, nthr = blockDim.x, nwarp = nthr >> 5;
+    __syncthreads();
+    float tot = 0.0f, amax = 0.0f;
+    for (int w = 0; w < nwarp; w++) { tot += red[w]; amax = fmaxf(amax, red[kMmaMaxWarps + w]); }
     float inv = 1.0f;
     if (norm_w) {
-        float ss = 0.0f;
-        for (int e = tid * 4; e < K; e += nthr * 4) {
-            const float4 v = *reinterpret_cast<const float4*>(x + e);
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-        ss = warp_sum(ss);
-        if ((tid & 31) == 0) red[tid >> 5] = ss;
-        __syncthreads();
-        float tot = 0.0f;
-        for (int w = 0; w < nwarp; w++) tot += red[w];
         inv = 1.0f / sqrtf(tot / (float)K + eps);
+        amax *= inv;
     }
+    int k = 0;
+    if (amax > 0.0f && amax < 3.0e38f) {
+        int ex;
+        frexpf(amax, &ex);            // amax = m * 2^ex, m in [0.5, 1)
+        k = min(max(12 - ex, -100), 100);
+    }
+    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23);
     __half* xh = reinterpret_cast<__half*>(smem);
-    __half* xl = xh + K;
-    float* xs = reinterpret_cast<float*>(smem + (size_t)4 * K);
-    const int l16 = tid & 15;
-    for (int e0 = (tid >> 4) * 16; e0 < K; e0 += (nthr >> 4) * 16) {
-        const int e = e0 + l16;
-        float v = x[e];
-        if (norm_w) v = (v * inv) * norm_w[e];
-        if (v > 65504.0f) v = 65504.0f;
-        if (v < -65504.0f) v = -65504.0f;
-        const __half h = __float2half_rn(v);
-        const __half l = __float2half_rn(v - __half2float(h));
-        xh[xperm(e)] = h;
-        xl[xperm(e)] = l;
-        float s = __half2float(h) + __half2float(l);
+    __half* xl = reinterpret_cast<__half*>(smem + (size_t)2 * K + kXlPad);
+    float* xs = reinterpret_cast<float*>(smem + (size_t)4 * K + kXlPad);
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-        if (l16 == 0) xs[e0 >> 4] = s;
+    for (int i = 0; i < kXRegs; i++) {
+        const int e = (tid + i * nthr) * 4;
+        if (e < K) split_store4(st.v[i], e, norm_w, inv, up, xh, xl, xs, __activemask());
     }
+    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4)
+        split_store4(*reinterpret_cast<const float4*>(x + e), e, norm_w, inv, up, xh, xl, xs, __activemask());
+    if (tid < 64) reinterpret_cast<uint32_t*>(smem + (x_smem_bytes(K) - 256))[tid] = 0u;
+    return down;
 }
 
 // ---------------------------------------------------------------- per-type unit kernels
@@ -262,6 +340,11 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
     const uint32_t arr = (g & 1) ? sm.xl : sm.xh;
     const bool lane_act = (((g >> 1) & 1) == (t >> 1));
     const int c_act = g >> 2;
+    // B-operand base of this lane for each half c: its x elements, or the zero page when its column pair is not addressed
+    const uint32_t xo = 2u * (uint32_t)(e0 + 128 * c_act + 64 * (t >> 1) + 16 * (t & 1));
+    const uint32_t xb0 = (lane_act && c_act == 0) ? arr + xo : sm.zero, xs0 = (lane_act && c_act == 0) ? 512u : 0u;
+    const uint32_t xb1 = (lane_act && c_act == 1) ? arr + xo : sm.zero, xs1 = (lane_act && c_act == 1) ? 512u : 0u;
+#pragma unroll 2
     for (int b = 0; b < nblk; b++) {
         const uint32_t r0 = sp + g * RS + b * BB, r1 = r0 + 8 * RS;
         const uint4 h0 = lds128(r0), h1 = lds128(r1);
@@ -270,22 +353,21 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
             qh0 = lds128(r0 + 16 + 16 * (t & 1));
             qh1 = lds128(r1 + 16 + 16 * (t & 1));
         }
-        float cl[4] = {0.f, 0.f, 0.f, 0.f}, ch[4] = {0.f, 0.f, 0.f, 0.f};
+        // independent accumulator chains per half c (4 MMAs deep instead of 8): cl[c] / ch[c]
+        float cl[2][4], ch[2][4];
+#pragma unroll
+        for (int c = 0; c < 2; c++) cl[c][0] = cl[c][1] = cl[c][2] = cl[c][3] = ch[c][0] = ch[c][1] = ch[c][2] = ch[c][3] = 0.f;
         const int eb = e0 + b * 256;
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const uint4 W0 = lds128(r0 + QS + 64 * c + 16 * t), W1 = lds128(r1 + QS + 64 * c + 16 * t);
             const int gp = 2 * c + (t >> 1);
-            const bool act = lane_act && (c == c_act);
-            const uint32_t xa = arr + 2u * (uint32_t)(eb + 64 * gp + 16 * (t & 1));
+            const uint32_t xa = (c ? xb1 : xb0) + (uint32_t)b * (c ? xs1 : xs0);
             uint4 bl[2], bh[2];
-            bl[0] = bl[1] = bh[0] = bh[1] = make_uint4(0u, 0u, 0u, 0u);
-            if (act) {
-                bl[0] = lds128(xa);
-                bl[1] = lds128(xa + 16);
-                bh[0] = lds128(xa + 64);
-                bh[1] = lds128(xa + 80);
-            }
+            bl[0] = lds128(xa);
+            bl[1] = lds128(xa + 16);
+            bh[0] = lds128(xa + 64);
+            bh[1] = lds128(xa + 80);
             const uint32_t wa4[4] = {W0.x, W0.y, W0.z, W0.w}, wb4[4] = {W1.x, W1.y, W1.z, W1.w};
             const uint32_t ha4[4] = {qh0.x, qh0.y, qh0.z, qh0.w}, hb4[4] = {qh1.x, qh1.y, qh1.z, qh1.w};
 #pragma unroll
@@ -306,21 +388,24 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
                     mh_a8 = lop3_and_or(la >> 1, 0x01000100u, kMagic);
                     mh_b8 = lop3_and_or(lb >> 1, 0x01000100u, kMagic);
                 }
-                const uint32_t wa8 = wa >> 8, wb8 = wb >> 8;
-                mma16816(cl, lop3_and_or(wa, 0x000F000Fu, ml_a), lop3_and_or(wb, 0x000F000Fu, ml_b),
+                const uint32_t wa8 = __umulhi(wa, 0x01000000u), wb8 = __umulhi(wb, 0x01000000u);  // >> 8 on the FMA pipe
+                mma16816(cl[c], lop3_and_or(wa, 0x000F000Fu, ml_a), lop3_and_or(wb, 0x000F000Fu, ml_b),
                          lop3_and_or(wa8, 0x000F000Fu, ml_a8), lop3_and_or(wb8, 0x000F000Fu, ml_b8), blx, bly);
-                mma16816(ch, lop3_and_or(wa, 0x00F000F0u, mh_a), lop3_and_or(wb, 0x00F000F0u, mh_b),
+                mma16816(ch[c], lop3_and_or(wa, 0x00F000F0u, mh_a), lop3_and_or(wb, 0x00F000F0u, mh_b),
                          lop3_and_or(wa8, 0x00F000F0u, mh_a8), lop3_and_or(wb8, 0x00F000F0u, mh_b8), bhx, bhy);
             }
         }
-        // lane t owns sub-blocks 2t (low nibbles) and 2t+1 (high nibbles, carried x16) of this block
+        // lane t owns sub-blocks 2t (low nibbles) and 2t+1 (high nibbles, carried x16) of this block: column pair t,
+        // which was fed by the half c = t>>1
+        const float sl0 = (t & 2) ? cl[1][0] + cl[1][1] : cl[0][0] + cl[0][1], sl1 = (t & 2) ? cl[1][2] + cl[1][3] : cl[0][2] + cl[0][3];
+        const float sh0 = (t & 2) ? ch[1][0] + ch[1][1] : ch[0][0] + ch[0][1], sh1 = (t & 2) ? ch[1][2] + ch[1][3] : ch[0][2] + ch[0][3];
         float dl0, ml0, dh0, mh0, dl1, ml1, dh1, mh1;
         k4_scales(h0, t, dl0, ml0, dh0, mh0);
         k4_scales(h1, t, dl1, ml1, dh1, mh1);
         const uint32_t xsa = sm.xs + 4u * (uint32_t)((eb >> 4) + 4 * t);
         const float xsl = lds_f32(xsa) + lds_f32(xsa + 4), xsh = lds_f32(xsa + 8) + lds_f32(xsa + 12);
-        acc0 += dl0 * (cl[0] + cl[1]) - (1024.0f * dl0 + ml0) * xsl + (dh0 * 0.0625f) * (ch[0] + ch[1]) - (64.0f * dh0 + mh0) * xsh;
-        acc1 += dl1 * (cl[2] + cl[3]) - (1024.0f * dl1 + ml1) * xsl + (dh1 * 0.0625f) * (ch[2] + ch[3]) - (64.0f * dh1 + mh1) * xsh;
+        acc0 += dl0 * sl0 - (1024.0f * dl0 + ml0) * xsl + (dh0 * 0.0625f) * sh0 - (64.0f * dh0 + mh0) * xsh;
+        acc1 += dl1 * sl1 - (1024.0f * dl1 + ml1) * xsl + (dh1 * 0.0625f) * sh1 - (64.0f * dh1 + mh1) * xsh;
     }
 }
 
@@ -348,15 +433,12 @@ __device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, int nblk, int
             lds_piece16(r1 + 64 * n + 16 * t, L1);
             lds_piece16(r0 + 128 + 32 * n + 16 * (t & 1), H0);
             lds_piece16(r1 + 128 + 32 * n + 16 * (t & 1), H1);
-            const uint32_t xa = arr + 2u * (uint32_t)(eb + 128 * n + 16 * t);
+            const uint32_t xa = act ? arr + 2u * (uint32_t)(eb + 128 * n + 16 * t) : sm.zero;
             uint4 bl[2], bh[2];
-            bl[0] = bl[1] = bh[0] = bh[1] = make_uint4(0u, 0u, 0u, 0u);
-            if (act) {
-                bl[0] = lds128(xa);
-                bl[1] = lds128(xa + 16);
-                bh[0] = lds128(xa + 128);
-                bh[1] = lds128(xa + 144);
-            }
+            bl[0] = lds128(xa);
+            bl[1] = lds128(xa + 16);
+            bh[0] = lds128(xa + 128);
+            bh[1] = lds128(xa + 144);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t lo0 = lop3_and_or(L0[i], 0x0F0F0F0Fu, (H0[i] << s_lo) & 0x30303030u);
@@ -402,8 +484,7 @@ __device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int
                 for (int m = 0; m < 2; m++) {
                     const uint32_t w0 = lds32_a2(r0 + 16 * m + 4 * t) ^ 0x80808080u;  // int8 -> biased uint8
                     const uint32_t w1 = lds32_a2(r1 + 16 * m + 4 * t) ^ 0x80808080u;
-                    uint2 bf = make_uint2(0u, 0u);
-                    if (act) bf = lds64(arr + 2u * (uint32_t)(e0 + 32 * b + 16 * m + 4 * t));
+                    const uint2 bf = lds64(act ? arr + 2u * (uint32_t)(e0 + 32 * b + 16 * m + 4 * t) : sm.zero);
                     mma16816(C, __byte_perm(w0, 0x64646464u, 0x4240), __byte_perm(w1, 0x64646464u, 0x4240),
                              __byte_perm(w0, 0x64646464u, 0x4341), __byte_perm(w1, 0x64646464u, 0x4341), bf.x, bf.y);
                 }
@@ -427,26 +508,59 @@ __host__ __device__ inline int mma_chunk_blocks(int type, int chunk_elems) { ret
 // warp that owns unit u when U units are dealt to W warps as [floor(i*U/W), floor((i+1)*U/W))  (W <= U)
 __device__ __forceinline__ int mma_owner(long long u, long long U, long long W) { return (int)(((u + 1) * W - 1) / U); }
 
-__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MParams p) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait(int pending) {  // at most `pending` newest groups still in flight
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+// ticket with release (my partial sums are visible) + acquire (I see the others') semantics: no full fence needed
+__device__ __forceinline__ unsigned int atom_add_acq_rel(unsigned int* p, unsigned int v) {
+    unsigned int r;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_relaxed_gpu(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MMA_STAMP(i)                                                    \
+    do {                                                                \
+        if (p.dbg && lane == 0) p.dbg[(size_t)gw * 8 + (i)] = gtimer(); \
+    } while (0)
+
+// Position of a warp in its run of units: segment s, 16-row tile, logical chunk c (ME_SWIGLU: c >= chunks
+// are the up-projection's chunks).  rowA / rowB point at the first byte of rows tile*16+g and +8 of the
+// matrix the chunk belongs to.  Advanced incrementally: no divisions inside the unit loop.
+struct MCursor {
+    int s, tile, c, mat, chunk;
+    const uint8_t* rowA;
+    const uint8_t* rowB;
+};
+
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ float s_red[kMmaMaxWarps];
-    __shared__ __align__(8) unsigned long long s_bars[kMmaMaxWarps * kMmaMaxStages];
+    __shared__ float s_red[2 * kMmaMaxWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int K = p.K;
     const uint32_t sbase = smem_u32(smem);
-    XSmem sm;
-    sm.xh = sbase;
-    sm.xl = sbase + 2u * K;
-    sm.xs = sbase + 4u * K;
     const uint32_t ring = sbase + (uint32_t)x_smem_bytes(K) + (uint32_t)warp * p.stages * p.stage_bytes;
-    const uint32_t wbar = smem_u32(&s_bars[warp * kMmaMaxStages]);
-
-    if (lane == 0)
-        for (int s = 0; s < p.stages; s++) mbar_init(wbar + 8 * s, 16);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
+    const bool swiglu = p.epi == ME_SWIGLU;
 
     // interleaved warp numbering: consecutive global warps sit on different SMs
     const long long U = p.total_units, W = p.active_warps;
@@ -455,105 +569,149 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
     const int u0 = active ? (int)(gw * U / W) : 0, u1 = active ? (int)((gw + 1) * U / W) : 0;
     const int n_units = u1 - u0;
     long long eoff = 0;  // MoE expert index (valid after pdl_wait)
+    MMA_STAMP(0);
 
-    // unit -> (segment, logical tile, chunk)
-    auto decode = [&](int u, int& s, int& tile, int& chunk) {
-        s = (p.n_seg > 2 && u >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && p.epi != ME_SWIGLU && u >= p.seg[1].unit0) ? 1 : 0;
-        const int local = u - p.seg[s].unit0;
-        tile = local / p.units_per_tile;
-        chunk = local - tile * p.units_per_tile;
+    auto cur_rows = [&](MCursor& q) {
+        q.mat = q.s;
+        q.chunk = q.c;
+        if (swiglu && q.c >= p.chunks) { q.mat = 1; q.chunk = q.c - p.chunks; }
+        const MSeg& sg = p.seg[q.mat];
+        const uint8_t* base = sg.w + eoff * sg.expert_stride;
+        q.rowA = base + (long long)min(q.tile * 16 + g, sg.n_rows - 1) * sg.row_bytes;
+        q.rowB = base + (long long)min(q.tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes;
     };
-    // byte offset (within its row slot) at which the bytes of row `row` of segment sg, chunk `chunk` start
-    auto row_src = [&](const MSeg& sg, int tile, int r, int chunk) -> const uint8_t* {
-        const int row = min(tile * 16 + r, sg.n_rows - 1);
-        const int cb = mma_chunk_blocks(sg.type, p.chunk_elems), bb = type_block_bytes(sg.type);
-        return sg.w + eoff * sg.expert_stride + (long long)row * sg.row_bytes + (long long)chunk * cb * bb;
+    auto cur_init = [&](MCursor& q, int u) {
+        q.s = (p.n_seg > 2 && u >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && !swiglu && u >= p.seg[1].unit0) ? 1 : 0;
+        const int local = u - p.seg[q.s].unit0;
+        q.tile = local / p.units_per_tile;
+        q.c = local - q.tile * p.units_per_tile;
+        cur_rows(q);
     };
-    // issue the bulk copies of unit u into ring stage st (lanes 0..15: one row each)
-    auto issue = [&](int u, int st) {
-        int s, tile, chunk;
-        decode(u, s, tile, chunk);
-        if (p.epi == ME_SWIGLU && chunk >= p.chunks) { s = 1; chunk -= p.chunks; }
-        const MSeg& sg = p.seg[s];
-        if (lane < 16) {
-            const int cb = mma_chunk_blocks(sg.type, p.chunk_elems), bb = type_block_bytes(sg.type), be = type_block_elems(sg.type);
-            const int nblk = min(cb, K / be - chunk * cb);
-            const uint8_t* src = row_src(sg, tile, lane, chunk);
-            const uint32_t doff = (uint32_t)((uintptr_t)src & 15u);
-            const uint32_t bytes = (doff + (uint32_t)(nblk * bb) + 15u) & ~15u;
-            const uint32_t bar = wbar + 8 * st;
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(ring + (uint32_t)st * p.stage_bytes + (uint32_t)lane * sg.row_stride, src - doff, bytes, bar);
+    auto cur_next = [&](MCursor& q) {
+        q.c++;
+        if (q.c == p.units_per_tile) {
+            q.c = 0;
+            q.tile++;
+            if (q.tile == p.seg[q.s].n_tiles && q.s + 1 < p.n_seg && !swiglu) { q.s++; q.tile = 0; }
+            cur_rows(q);
+        } else if (swiglu && q.c == p.chunks) {
+            cur_rows(q);
+        } else {
+            q.chunk++;
+        }
+    };
+    // cp.async the 16 rows of the unit at q into ring stage st: lane (g, t) moves 16-byte pieces t, t+4, ...
+    // of rows g and g+8 (8 rows x 64 contiguous bytes per instruction).  l2_only: just pull the lines into L2.
+    auto issue = [&](const MCursor& q, int st, bool l2_only) {
+        const MSeg& sg = p.seg[q.mat];
+        const int nblk = min(sg.cb, sg.nb_row - q.chunk * sg.cb);
+        const int bytes = nblk * (sg.chunk_bytes / sg.cb);
+        const long long off = (long long)q.chunk * sg.chunk_bytes;
+        const uint8_t* sa = q.rowA + off;
+        const uint8_t* sb = q.rowB + off;
+        const uint32_t da = (uint32_t)((uintptr_t)sa & 15u), db = (uint32_t)((uintptr_t)sb & 15u);
+        if (l2_only) {
+            for (int o = 128 * t; o < bytes + 15; o += 512) {
+                prefetch_l2(sa - da + o);
+                prefetch_l2(sb - db + o);
+            }
+            return;
+        }
+        sa += 16 * t - (int)da;
+        sb += 16 * t - (int)db;
+        const uint32_t dst = ring + (uint32_t)st * p.stage_bytes + (uint32_t)g * sg.row_stride + 16u * t;
+        const uint32_t dstb = dst + 8u * sg.row_stride;
+        const int iters = ((int)max(da, db) + bytes + 63) >> 6;  // whole 64-byte steps; never beyond the row slot
+        for (int i = 0; i < iters; i++) {
+            cp_async16(dst + 64 * i, sa + 64 * i);
+            cp_async16(dstb + 64 * i, sb + 64 * i);
         }
     };
 
+    MCursor cp{}, cc{};
     const int pre = min(p.stages - 1, n_units);
-    if (!p.expert_sel)  // dense weights never depend on a predecessor: start streaming before the PDL wait
-        for (int k = 0; k < pre; k++) issue(u0 + k, k);
+    if (n_units > 0 && !p.expert_sel) {
+        // dense weights never depend on a predecessor: pull the first stages towards L2 before the PDL wait
+        // (fire-and-forget; an early cp.async would make the x loads below queue behind DRAM-latency copies)
+        cur_init(cp, u0);
+        cc = cp;
+        MCursor q = cp;
+        for (int k = 0; k < pre; k++) { issue(q, k, true); cur_next(q); }
+    }
 
     pdl_launch_dependents();
     pdl_wait();
+    MMA_STAMP(1);
 
     if (p.expert_sel) {
         eoff = (long long)p.expert_sel[p.expert_slot];
-        for (int k = 0; k < pre; k++) issue(u0 + k, k);
+        if (n_units > 0) { cur_init(cp, u0); cc = cp; }
     }
-    stage_x_split(p.x, p.norm_w, p.eps, K, smem, s_red);
+    // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
+    XStage xst;
+    stage_x_load(xst, p.x, p.norm_w, K, s_red);
+    for (int k = 0; k < p.stages - 1; k++) {
+        if (k < pre) { issue(cp, k, false); cur_next(cp); }
+        cp_async_commit();
+    }
+    MMA_STAMP(2);
+    const float unscale = stage_x_split(xst, p.x, p.norm_w, p.eps, K, smem, s_red);
     __syncthreads();
+    MMA_STAMP(3);
+    const uint32_t tokx = smem_token();
+    XSmem sm;
+    sm.xh = sbase + tokx;
+    sm.xl = sm.xh + 2u * K + kXlPad;
+    sm.xs = sm.xh + 4u * K + kXlPad;
+    sm.zero = sbase + tokx + (uint32_t)x_smem_bytes(K) - 256u;
 
     float ag0 = 0.f, ag1 = 0.f, au0 = 0.f, au1 = 0.f;
-    bool ok = true;
-    for (int k = 0; k < n_units && ok; k++) {
-        const int u = u0 + k;
+    for (int k = 0; k < n_units; k++) {
         if (k + p.stages - 1 < n_units) {
-            __syncwarp();
-            issue(u + p.stages - 1, (k + p.stages - 1) % p.stages);
+            issue(cp, (k + p.stages - 1) % p.stages, false);
+            cur_next(cp);
         }
-        const int st = k % p.stages;
-        ok = mbar_wait(wbar + 8 * st, (uint32_t)((k / p.stages) & 1), p.err);
-        if (!ok) break;
+        cp_async_commit();
+        cp_async_wait(p.stages - 1);
+        __syncwarp();
+        if (k == 0) MMA_STAMP(4);
 
-        int s, tile, chunk;
-        decode(u, s, tile, chunk);
-        bool is_up = false;
-        int ws = s;
-        if (p.epi == ME_SWIGLU && chunk >= p.chunks) { is_up = true; ws = 1; chunk -= p.chunks; }
-        const MSeg& wsg = p.seg[ws];
+        const MSeg& wsg = p.seg[cc.mat];
         const int type = wsg.type;
-        const int cb = mma_chunk_blocks(type, p.chunk_elems), be = type_block_elems(type);
-        const int nblk = min(cb, K / be - chunk * cb);
-        const int e0 = chunk * p.chunk_elems;
-        const uint32_t sp = ring + (uint32_t)st * p.stage_bytes;
+        const int nblk = min(wsg.cb, wsg.nb_row - cc.chunk * wsg.cb);
+        const int e0 = cc.chunk * p.chunk_elems;
+        const uint32_t sp = ring + (uint32_t)(k % p.stages) * p.stage_bytes + smem_token();
         const uint32_t RS = (uint32_t)wsg.row_stride;
         float a0 = 0.f, a1 = 0.f;
         switch (type) {
             case T_Q4_K: unit_k45<false>(sp, RS, nblk, e0, sm, g, t, a0, a1); break;
             case T_Q5_K: unit_k45<true>(sp, RS, nblk, e0, sm, g, t, a0, a1); break;
-            case T_Q6_K: {
-                const uint32_t d0 = (uint32_t)((uintptr_t)row_src(wsg, tile, g, chunk) & 15u);
-                const uint32_t d1 = (uint32_t)((uintptr_t)row_src(wsg, tile, g + 8, chunk) & 15u);
-                unit_q6k(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
-                break;
-            }
             default: {
-                const uint32_t d0 = (uint32_t)((uintptr_t)row_src(wsg, tile, g, chunk) & 15u);
-                const uint32_t d1 = (uint32_t)((uintptr_t)row_src(wsg, tile, g + 8, chunk) & 15u);
-                unit_q80(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
+                const long long off = (long long)cc.chunk * wsg.chunk_bytes;
+                const uint32_t d0 = (uint32_t)((uintptr_t)(cc.rowA + off) & 15u), d1 = (uint32_t)((uintptr_t)(cc.rowB + off) & 15u);
+                if (type == T_Q6_K) unit_q6k(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
+                else unit_q80(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
                 break;
             }
         }
-        if (is_up) { au0 += a0; au1 += a1; } else { ag0 += a0; ag1 += a1; }
+        pin2(a0, a1);  // the unit's shared-memory reads are complete before the stage can be refilled
+        if (cc.mat != cc.s) { au0 += a0; au1 += a1; } else { ag0 += a0; ag1 += a1; }
+        __syncwarp();  // every lane is done with this stage
+        if (k == n_units - 1) MMA_STAMP(5);
 
         // ---- tile finished (for this warp)? ----
-        int s2 = -1, tile2 = -1, chunk2;
-        if (k + 1 < n_units) decode(u + 1, s2, tile2, chunk2);
-        if (s2 == s && tile2 == tile) continue;
+        const int s = cc.s, tile = cc.tile;
+        const bool tile_done = (cc.c == p.units_per_tile - 1) || (k == n_units - 1);
+        cur_next(cc);
+        if (!tile_done) continue;
 
         // reduce the 4 lanes of a row group, then lane L holds logical row L (0..15 gate/plain, 16..31 up)
         ag0 += __shfl_xor_sync(0xffffffffu, ag0, 1); ag0 += __shfl_xor_sync(0xffffffffu, ag0, 2);
         ag1 += __shfl_xor_sync(0xffffffffu, ag1, 1); ag1 += __shfl_xor_sync(0xffffffffu, ag1, 2);
-        au0 += __shfl_xor_sync(0xffffffffu, au0, 1); au0 += __shfl_xor_sync(0xffffffffu, au0, 2);
-        au1 += __shfl_xor_sync(0xffffffffu, au1, 1); au1 += __shfl_xor_sync(0xffffffffu, au1, 2);
+        if (swiglu) {
+            au0 += __shfl_xor_sync(0xffffffffu, au0, 1); au0 += __shfl_xor_sync(0xffffffffu, au0, 2);
+            au1 += __shfl_xor_sync(0xffffffffu, au1, 1); au1 += __shfl_xor_sync(0xffffffffu, au1, 2);
+        }
         const int src = 4 * (lane & 7);
         const float vg0 = __shfl_sync(0xffffffffu, ag0, src), vg1 = __shfl_sync(0xffffffffu, ag1, src);
         const float vu0 = __shfl_sync(0xffffffffu, au0, src), vu1 = __shfl_sync(0xffffffffu, au1, src);
@@ -563,22 +721,20 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
         // stream-K merge: which warps hold pieces of this tile?
         const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
         const int w_first = mma_owner(tu0, U, W), w_last = mma_owner(tu0 + p.units_per_tile - 1, U, W);
-        const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
         if (w_last != w_first) {
+            const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
             const int slot = ((long long)u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or my last (slot 1)
             p.part[((size_t)gw * 2 + slot) * 32 + lane] = v;
-            __threadfence();
             __syncwarp();
             unsigned int ticket = 0;
-            if (lane == 0) ticket = atomicAdd(&p.tickets[tile_id], 1u);
+            if (lane == 0) ticket = atom_add_acq_rel(&p.tickets[tile_id], 1u);
             ticket = __shfl_sync(0xffffffffu, ticket, 0);
             if (ticket != (unsigned)(w_last - w_first)) continue;  // not the last piece
-            __threadfence();
             v = 0.f;
-            for (int wi = w_first; wi <= w_last; wi++) {
+            for (int wi = w_first; wi <= w_last; wi++) {  // fixed order: deterministic
                 const long long wu0 = (long long)wi * U / W;
                 const int sl = (wu0 >= tu0) ? 0 : 1;
-                v += __ldcg(&p.part[((size_t)wi * 2 + sl) * 32 + lane]);
+                v += ld_relaxed_gpu(&p.part[((size_t)wi * 2 + sl) * 32 + lane]);
             }
             if (lane == 0) p.tickets[tile_id] = 0;
         }
@@ -587,8 +743,9 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
         const MSeg& sg = p.seg[s];
         const int j = tile * 16 + (lane & 15);
         const bool valid = (lane < 16) && (j < sg.n_rows);
+        v *= unscale;
         float val = v;
-        if (p.epi == ME_SWIGLU) {
+        if (swiglu) {
             const float up = __shfl_sync(0xffffffffu, v, (lane & 15) + 16);
             val = mma_silu(v) * up;
         }
@@ -603,17 +760,19 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
             sg.out[j] = val;
         }
     }
+    MMA_STAMP(6);
 }
 
 // ---------------------------------------------------------------- host-side launch planning
 inline bool mma_type_ok(int type) { return type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q8_0; }
 
-// bytes between row slots: room for the chunk (+15 bytes of source misalignment, +4 of funnel over-read),
-// residue mod 128 chosen for conflict-free fragment loads (LDS.128: 64; 32-bit loads: odd multiple of 16)
+// bytes between row slots: room for the chunk plus the whole 64-byte copy iterations that cover up to 15
+// bytes of source misalignment (and the 4-byte funnel over-read), residue mod 128 chosen for conflict-free
+// fragment loads (LDS.128 row pairs: 64; 32-bit loads of 8 rows: odd multiple of 16)
 inline int mma_row_stride(int type, int chunk_elems) {
     const int cb = mma_chunk_blocks(type, chunk_elems), bb = type_block_bytes(type);
     const bool aligned = (type == T_Q4_K || type == T_Q5_K);
-    int rs = aligned ? cb * bb : ((cb * bb + 15 + 4 + 15) & ~15);
+    int rs = aligned ? ((cb * bb + 63) & ~63) : ((15 + cb * bb + 63) & ~63);
     for (;; rs += 16) {
         const int m = rs & 127;
         if (aligned ? (m == 64) : ((m & 15) == 0 && ((m >> 4) & 1))) return rs;
@@ -636,10 +795,13 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
         MSeg& sg = p.seg[s];
         if (!mma_type_ok(sg.type)) return false;
         if (p.K % type_block_elems(sg.type)) return false;
-        if ((sg.type == T_Q4_K || sg.type == T_Q5_K) && ((sg.row_bytes & 15) || (sg.expert_stride & 15))) return false;
+        if ((sg.type == T_Q4_K || sg.type == T_Q5_K) && ((sg.row_bytes & 15) || (sg.expert_stride & 15) || ((uintptr_t)sg.w & 15))) return false;
         if ((sg.row_bytes & 1) || (sg.expert_stride & 1)) return false;
         if (chunk_elems % type_block_elems(sg.type)) return false;
         sg.row_stride = mma_row_stride(sg.type, chunk_elems);
+        sg.cb = mma_chunk_blocks(sg.type, chunk_elems);
+        sg.chunk_bytes = sg.cb * type_block_bytes(sg.type);
+        sg.nb_row = p.K / type_block_elems(sg.type);
         sg.n_tiles = (sg.n_rows + 15) / 16;
         max_rs = std::max(max_rs, sg.row_stride);
     }
@@ -662,7 +824,7 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
     p.stage_bytes = 16 * max_rs;
     const size_t xb = x_smem_bytes(p.K);
     int warps = std::min(want_warps, kMmaMaxWarps), stages = std::min(want_stages, kMmaMaxStages);
-    auto need = [&](int w, int st) { return xb + (size_t)w * st * p.stage_bytes; };
+    auto need = [&](int w, int st) { return xb + (size_t)w * st * p.stage_bytes + 16; };  // +16: funnel loads read one word past a piece
     while (need(warps, stages) > smem_limit) {
         if (stages > 2) stages--;
         else if (warps > 4) warps -= 2;
@@ -678,6 +840,21 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
     p.active_warps = (int)std::min<long long>((long long)plan.grid * warps, p.total_units);
     (void)slots;
     return true;
+}
+
+// The kernel is instantiated for three register budgets (launch bounds): more registers per thread let ptxas
+// overlap two blocks of a unit when fewer warps are resident.
+using MmaKernel = void (*)(const MParams);
+inline MmaKernel mma_kernel_for(int warps) {
+    if (warps <= 8) return gemv_mma_kernel<8>;
+    if (warps <= 12) return gemv_mma_kernel<12>;
+    return gemv_mma_kernel<16>;
+}
+inline cudaError_t mma_set_smem_limit(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 
 }  // namespace b200

@@ -141,6 +141,8 @@ static int g_nsm = 148;
 static float* g_part = nullptr;
 static unsigned int* g_tickets = nullptr;
 static int* g_err = nullptr;
+static unsigned long long* g_dbg = nullptr;
+static bool g_use_dbg = false;
 static size_t g_smem_limit = 227 * 1024;
 
 struct Knobs { int chunk = 512, warps = 16, stages = 2; };
@@ -156,7 +158,8 @@ static void lab_init() {
     CK(cudaMemset(g_tickets, 0, 65536 * 4));
     CK(cudaMalloc(&g_err, 4));
     CK(cudaMemset(g_err, 0, 4));
-    CK(cudaFuncSetAttribute(gemv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
+    CK(cudaMalloc(&g_dbg, (size_t)g_nsm * kMmaMaxWarps * 8 * 8));
+    CK(mma_set_smem_limit((int)prop.sharedMemPerBlockOptin - 1024));
     CK(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 }
 
@@ -165,6 +168,7 @@ static bool launch_mma(cudaStream_t st, MParams p, const Knobs& kn, bool pdl) {
     p.part = g_part;
     p.tickets = g_tickets;
     p.err = g_err;
+    p.dbg = g_use_dbg ? g_dbg : nullptr;
     if (!mma_plan(p, g_nsm, kn.chunk, kn.warps, kn.stages, g_smem_limit, plan)) return false;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
@@ -176,7 +180,7 @@ static bool launch_mma(cudaStream_t st, MParams p, const Knobs& kn, bool pdl) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = pdl ? at : nullptr;
     cfg.numAttrs = pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, gemv_mma_kernel, p));
+    CK(cudaLaunchKernelEx(&cfg, mma_kernel_for(plan.warps), p));
     return true;
 }
 static void launch_v1(cudaStream_t st, GemvParams p, bool pdl) {
@@ -444,6 +448,50 @@ static void time_case(const TimeCase& tc, const std::vector<Knobs>& knobs, bool 
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
 }
 
+
+// in-kernel globaltimer stamps of one launch: where does the time of a kernel go?
+static void timeline_case(const TimeCase& tc, const Knobs& kn) {
+    const int be = type_block_elems(tc.type), bb = type_block_bytes(tc.type);
+    const size_t rb = (size_t)(tc.K / be) * bb;
+    const int nmat = tc.epi == ME_SWIGLU ? 2 : 1;
+    const size_t wbytes = rb * tc.N * nmat;
+    uint8_t* dw; float *dx, *dy, *dr; void* flush;
+    CK(cudaMalloc(&dw, wbytes + 256)); CK(cudaMemset(dw, 0x11, wbytes));
+    CK(cudaMalloc(&dx, tc.K * 4)); CK(cudaMemset(dx, 0, tc.K * 4));
+    CK(cudaMalloc(&dy, (size_t)tc.N * 4)); CK(cudaMalloc(&dr, (size_t)tc.N * 4)); CK(cudaMemset(dr, 0, (size_t)tc.N * 4));
+    CK(cudaMalloc(&flush, 512u << 20));
+    g_use_dbg = true;
+    const size_t nw = (size_t)g_nsm * kMmaMaxWarps;
+    std::vector<unsigned long long> h(nw * 8);
+    const char* names[7] = {"start", "pdl_wait done", "x loaded+copies issued", "x staged", "first unit landed", "last unit computed", "exit"};
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaMemset(flush, rep, 512u << 20));
+        CK(cudaMemset(g_dbg, 0, nw * 64));
+        CK(cudaDeviceSynchronize());
+        MParams p{};
+        p.seg[0] = mseg(dw, dy, nullptr, tc.type, tc.K, tc.N); p.n_seg = 1;
+        if (tc.epi == ME_SWIGLU) { p.seg[1] = mseg(dw + rb * tc.N, dy, nullptr, tc.type, tc.K, tc.N); p.n_seg = 2; }
+        p.K = tc.K; p.x = dx; p.epi = tc.epi; p.residual = dr;
+        launch_mma(0, p, kn, false);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), g_dbg, nw * 64, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (size_t w = 0; w < nw; w++) if (h[w * 8]) t0 = std::min(t0, h[w * 8]);
+        printf("timeline %s ch=%d w=%d st=%d rep %d (ns after the first warp's start; min / avg / max over warps)\n", tc.name, kn.chunk, kn.warps, kn.stages, rep);
+        for (int i = 0; i < 7; i++) {
+            unsigned long long mn = ~0ull, mx = 0; double sum = 0; int n = 0;
+            for (size_t w = 0; w < nw; w++) {
+                if (!h[w * 8] || !h[w * 8 + i]) continue;
+                unsigned long long d = h[w * 8 + i] - t0;
+                mn = std::min(mn, d); mx = std::max(mx, d); sum += d; n++;
+            }
+            if (n) printf("   %-24s %7llu / %9.0f / %7llu   (%d warps)\n", names[i], mn, sum / n, mx, n);
+        }
+    }
+    g_use_dbg = false;
+    cudaFree(dw); cudaFree(dx); cudaFree(dy); cudaFree(dr); cudaFree(flush);
+}
+
 // a Llama-3-8B layer's four GEMVs back to back with PDL, over `layers` distinct weight sets
 static void time_layer_chain(const Knobs& kn, int down_type, bool graph) {
     const int H = 4096, I = 14336, layers = 8;
@@ -523,6 +571,204 @@ static void time_layer_chain(const Knobs& kn, int down_type, bool graph) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
 }
 
+
+// ------------------------------------------------------------------ raw streaming probes
+// How fast can one SM pull bytes with each mechanism, in the ring structure of the GEMV (per-warp rings,
+// `rows` copies of `S` bytes per stage)?  No arithmetic beyond one xor per lane per stage.
+struct StreamParams {
+    const uint8_t* src;
+    long long total;       // bytes
+    int S;                 // bytes per copy (multiple of 16)
+    int rows;              // copies per stage
+    int stages;
+    unsigned int* sink;
+};
+
+__global__ void __launch_bounds__(512, 1) stream_bulk_kernel(const StreamParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long bars[16 * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t stage_bytes = (uint32_t)p.S * p.rows;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * p.stages * stage_bytes;
+    const uint32_t wbar = smem_u32(&bars[warp * 8]);
+    if (lane == 0) for (int s = 0; s < p.stages; s++) mbar_init(wbar + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const long long W = (long long)gridDim.x * nw, gw = (long long)warp * gridDim.x + blockIdx.x;
+    const long long n_stage_total = p.total / stage_bytes;
+    const long long k0 = gw * n_stage_total / W, k1 = (gw + 1) * n_stage_total / W;
+    const int n = (int)(k1 - k0);
+    auto issue = [&](int k, int st) {
+        const uint8_t* base = p.src + (k0 + k) * (long long)stage_bytes;
+        if (lane == 0) mbar_arrive_expect_tx(wbar + 8 * st, stage_bytes);
+        __syncwarp();
+        if (lane < p.rows) bulk_g2s(ring + st * stage_bytes + lane * p.S, base + (long long)lane * p.S, p.S, wbar + 8 * st);
+    };
+    const int pre = min(p.stages - 1, n);
+    for (int k = 0; k < pre; k++) issue(k, k);
+    unsigned int acc = 0;
+    for (int k = 0; k < n; k++) {
+        if (k + p.stages - 1 < n) { __syncwarp(); issue(k + p.stages - 1, (k + p.stages - 1) % p.stages); }
+        const int st = k % p.stages;
+        if (!mbar_wait(wbar + 8 * st, (k / p.stages) & 1, nullptr)) break;
+        acc ^= lds32(ring + st * stage_bytes + lane * 4);
+    }
+    if (acc == 0x12345678u) p.sink[0] = acc;
+}
+
+// cp.async (LDGSTS) 16 B per lane, commit groups per stage
+__global__ void __launch_bounds__(512, 1) stream_cpasync_kernel(const StreamParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t stage_bytes = (uint32_t)p.S * p.rows;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * p.stages * stage_bytes;
+    const long long W = (long long)gridDim.x * nw, gw = (long long)warp * gridDim.x + blockIdx.x;
+    const long long n_stage_total = p.total / stage_bytes;
+    const long long k0 = gw * n_stage_total / W, k1 = (gw + 1) * n_stage_total / W;
+    const int n = (int)(k1 - k0);
+    const int pieces = stage_bytes / 16;
+    auto issue = [&](int k, int st) {
+        const uint8_t* base = p.src + (k0 + k) * (long long)stage_bytes;
+        for (int q = lane; q < pieces; q += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + st * stage_bytes + q * 16), "l"(base + q * 16) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int k = 0; k < p.stages - 1; k++) { if (k < n) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory"); }
+    unsigned int acc = 0;
+    for (int k = 0; k < n; k++) {
+        if (k + p.stages - 1 < n) issue(k + p.stages - 1, (k + p.stages - 1) % p.stages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        if (p.stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (p.stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 3;" ::: "memory");
+        __syncwarp();
+        acc ^= lds32(ring + (k % p.stages) * stage_bytes + lane * 4);
+        __syncwarp();
+    }
+    if (acc == 0x12345678u) p.sink[0] = acc;
+}
+
+// plain LDG.128 into registers, `S/16` loads in flight per lane
+template <int U>
+__global__ void __launch_bounds__(512, 1) stream_ldg_kernel(const StreamParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long W = (long long)gridDim.x * nw, gw = (long long)warp * gridDim.x + blockIdx.x;
+    const long long chunk = 512LL * U;
+    const long long n_total = p.total / chunk;
+    const long long k0 = gw * n_total / W, k1 = (gw + 1) * n_total / W;
+    unsigned int acc = 0;
+    for (long long k = k0; k < k1; k++) {
+        const uint8_t* base = p.src + k * chunk + lane * 16;
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = ldg_stream_u4(base + u * 512);
+#pragma unroll
+        for (int u = 0; u < U; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    if (acc == 0x12345678u) p.sink[0] = acc;
+}
+
+
+// the GEMV's exact access pattern (16 rows at stride row_bytes, S bytes per row per stage, walking along K, then
+// the next 16-row tile), cp.async 16 B pieces, no arithmetic: separates the memory pattern from the compute
+__global__ void __launch_bounds__(512, 1) stream_rows_kernel(const uint8_t* src, int n_rows, int row_bytes, int S, int stages, unsigned int* sink) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+    const int RS = (S + 63) & ~63;
+    const uint32_t stage_bytes = 16u * RS;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * stages * stage_bytes;
+    const int chunks = row_bytes / S, tiles = n_rows / 16;
+    const long long U = (long long)chunks * tiles, W = (long long)gridDim.x * nw, gw = (long long)warp * gridDim.x + blockIdx.x;
+    const long long u0 = gw * U / W, u1 = (gw + 1) * U / W;
+    const int n = (int)(u1 - u0);
+    auto issue = [&](long long u, int st) {
+        const int tile = (int)(u / chunks), chunk = (int)(u - (long long)tile * chunks);
+        const uint8_t* sa = src + (long long)(tile * 16 + g) * row_bytes + (long long)chunk * S + 16 * t;
+        const uint8_t* sb = sa + 8LL * row_bytes;
+        const uint32_t dst = ring + st * stage_bytes + g * RS + 16 * t;
+        for (int i = 0; i < (S + 63) / 64; i++) {
+            cp_async16(dst + 64 * i, sa + 64 * i);
+            cp_async16(dst + 8 * RS + 64 * i, sb + 64 * i);
+        }
+    };
+    for (int k = 0; k < stages - 1; k++) { if (k < n) issue(u0 + k, k); cp_async_commit(); }
+    unsigned int acc = 0;
+    for (int k = 0; k < n; k++) {
+        if (k + stages - 1 < n) issue(u0 + k + stages - 1, (k + stages - 1) % stages);
+        cp_async_commit();
+        cp_async_wait(stages - 1);
+        __syncwarp();
+        acc ^= lds32(ring + (k % stages) * stage_bytes + lane * 4);
+        __syncwarp();
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+static void stream_rows_probe() {
+    const int row_bytes = 2304, n_rows = 14336 * 2 * 8;   // 8 gate/up-sized matrices back to back: 528 MB
+    const long long total = (long long)row_bytes * n_rows;
+    uint8_t* src; unsigned int* sink;
+    CK(cudaMalloc(&src, total + 4096)); CK(cudaMemset(src, 1, total)); CK(cudaMalloc(&sink, 4));
+    CK(cudaFuncSetAttribute(stream_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_limit));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    printf("--- GEMV access pattern, copy only (rows of %d B, 16-row tiles), GB/s\n", row_bytes);
+    struct Cfg { int S, warps, stages; };
+    for (Cfg c : {Cfg{288, 16, 2}, Cfg{288, 12, 3}, Cfg{576, 8, 2}, Cfg{576, 10, 2}, Cfg{1152, 6, 2}, Cfg{2304, 4, 2}, Cfg{2304, 2, 3}}) {
+        const int RS = (c.S + 63) & ~63;
+        size_t sm = (size_t)16 * RS * c.stages * c.warps;
+        if (sm > g_smem_limit) { printf("rows S=%d w=%d st=%d: smem too large\n", c.S, c.warps, c.stages); continue; }
+        stream_rows_kernel<<<g_nsm, c.warps * 32, sm>>>(src, n_rows, row_bytes, c.S, c.stages, sink);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 3; i++) stream_rows_kernel<<<g_nsm, c.warps * 32, sm>>>(src, n_rows, row_bytes, c.S, c.stages, sink);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("rows    S=%-5d w=%-2d st=%d (ring %3zuK/SM): %7.1f\n", c.S, c.warps, c.stages, sm / 1024, total / (ms / 3 * 1e-3) / 1e9);
+    }
+    cudaFree(src); cudaFree(sink);
+}
+
+static void stream_probes() {
+    const long long total = 1LL << 30;
+    uint8_t* src; unsigned int* sink;
+    CK(cudaMalloc(&src, total + 4096)); CK(cudaMemset(src, 1, total)); CK(cudaMalloc(&sink, 4));
+    CK(cudaFuncSetAttribute(stream_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_limit));
+    CK(cudaFuncSetAttribute(stream_cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_limit));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto timeit = [&](auto&& f) {
+        f(); CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 3; i++) f();
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        return total / (ms / 3 * 1e-3) / 1e9;
+    };
+    printf("--- streaming probes over 1 GiB (GB/s); 148 CTAs\n");
+    struct Cfg { int S, rows, warps, stages; };
+    for (Cfg c : {Cfg{288, 16, 16, 2}, Cfg{576, 16, 8, 2}, Cfg{576, 16, 12, 2}, Cfg{1152, 16, 4, 2}, Cfg{1152, 16, 6, 2}, Cfg{2304, 16, 4, 2}, Cfg{4608, 1, 16, 2},
+                  Cfg{4608, 1, 16, 3}, Cfg{9216, 1, 8, 2}, Cfg{9216, 1, 12, 2}, Cfg{18432, 1, 4, 3}, Cfg{2304, 2, 16, 2}, Cfg{1152, 4, 16, 2}, Cfg{576, 8, 16, 2}, Cfg{288, 16, 16, 3},
+                  Cfg{288, 16, 8, 4}, Cfg{288, 16, 8, 2}}) {
+        StreamParams p{src, total, c.S, c.rows, c.stages, sink};
+        size_t sm = (size_t)c.S * c.rows * c.stages * c.warps;
+        if (sm > g_smem_limit) { printf("bulk S=%d rows=%d w=%d st=%d: smem too large\n", c.S, c.rows, c.warps, c.stages); continue; }
+        double gbs = timeit([&]() { stream_bulk_kernel<<<g_nsm, c.warps * 32, sm>>>(p); });
+        printf("bulk    S=%-5d rows=%-2d w=%-2d st=%d (ring %3zuK/SM): %7.1f\n", c.S, c.rows, c.warps, c.stages, sm / 1024, gbs);
+    }
+    for (Cfg c : {Cfg{288, 16, 16, 2}, Cfg{288, 16, 16, 3}, Cfg{576, 16, 8, 2}, Cfg{576, 16, 12, 2}, Cfg{288, 16, 8, 4}, Cfg{288, 16, 8, 2}, Cfg{144, 16, 16, 4}}) {
+        StreamParams p{src, total, c.S, c.rows, c.stages, sink};
+        size_t sm = (size_t)c.S * c.rows * c.stages * c.warps;
+        if (sm > g_smem_limit) continue;
+        double gbs = timeit([&]() { stream_cpasync_kernel<<<g_nsm, c.warps * 32, sm>>>(p); });
+        printf("cpasync S=%-5d rows=%-2d w=%-2d st=%d (ring %3zuK/SM): %7.1f\n", c.S, c.rows, c.warps, c.stages, sm / 1024, gbs);
+    }
+    for (int warps : {8, 16}) {
+        StreamParams p{src, total, 0, 0, 0, sink};
+        printf("ldg128  w=%-2d U=4: %7.1f   U=8: %7.1f   U=16: %7.1f\n", warps, timeit([&]() { stream_ldg_kernel<4><<<g_nsm, warps * 32>>>(p); }),
+               timeit([&]() { stream_ldg_kernel<8><<<g_nsm, warps * 32>>>(p); }), timeit([&]() { stream_ldg_kernel<16><<<g_nsm, warps * 32>>>(p); }));
+        printf("ldg128  w=%-2d 2 CTAs/SM U=8: %7.1f\n", warps, timeit([&]() { stream_ldg_kernel<8><<<2 * g_nsm, warps * 32>>>(p); }));
+    }
+    cudaFree(src); cudaFree(sink);
+}
+
 int main(int argc, char** argv) {
     std::string mode = argc > 1 ? argv[1] : "all";
     lab_init();
@@ -552,8 +798,25 @@ int main(int argc, char** argv) {
         check_qkv(k512);
         printf("CHECK SUMMARY: %s (%d failing groups)\n", g_fail ? "FAIL" : "ALL OK", g_fail);
     }
+    if (mode == "rows") stream_rows_probe();
+    if (mode == "stream" || mode == "all") stream_probes();
+    if (mode == "prof") {   // one case, for ncu: gemv_lab prof <chunk> <warps> <stages>
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 16, argc > 4 ? atoi(argv[4]) : 2};
+        time_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, {kn}, false);
+    }
+    if (mode == "timeline") {
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 1024, argc > 3 ? atoi(argv[3]) : 8, argc > 4 ? atoi(argv[4]) : 2};
+        timeline_case({"O proj 8B", T_Q4_K, 4096, 4096, ME_RESIDUAL}, kn);
+        timeline_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, kn);
+        timeline_case({"down 8B Q4_K", T_Q4_K, 14336, 4096, ME_RESIDUAL}, kn);
+    }
+    if (mode == "chain") {   // gemv_lab chain <chunk> <warps> <stages>: the PDL layer chain alone (for ncu launch lists)
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 1024, argc > 3 ? atoi(argv[3]) : 8, argc > 4 ? atoi(argv[4]) : 2};
+        time_layer_chain(kn, T_Q4_K, false);
+        time_layer_chain(kn, T_Q4_K, true);
+    }
     if (mode == "time" || mode == "all") {
-        std::vector<Knobs> sweep = {{512, 16, 2}, {512, 12, 3}, {512, 8, 4}, {1024, 8, 2}, {1024, 12, 2}, {512, 8, 2}};
+        std::vector<Knobs> sweep = {{512, 16, 2}, {512, 12, 3}, {512, 8, 4}, {1024, 8, 2}, {1024, 10, 2}, {512, 8, 2}, {1024, 6, 3}};
         std::vector<Knobs> one = {{512, 16, 2}, {1024, 8, 2}};
         time_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, sweep, true);
         time_case({"down 8B Q4_K", T_Q4_K, 14336, 4096, ME_RESIDUAL}, sweep, true);
