@@ -14,7 +14,7 @@ random-init GGUF blocks (synthetic), batch 1, 8K context window, 128-token promp
   e2e    : the same metric through the reference-facing call GpuInference::forward —
            token id from host memory in, `vocab` f32 logits to host memory out, host argmax
            (src/main.rs:1811-1822) — wall clock around the K calls.
-  roofline     : the dequant-GEMV kernel (gemv_kernel): weight bytes one token's GEMV launches
+  roofline     : the dequant-GEMV kernel (gemv_mma_kernel): weight bytes one token's GEMV launches
            read / the time of exactly those launches replayed back to back (CUDA events).
   cpu_baseline : the C++ restatement of the reference's CPU path (oracle/) on this box's cores.
 
@@ -265,7 +265,7 @@ def main():
     clocks = sampler.stop()
     e2e_val = args.steps / e2e_s
 
-    # ---- roofline of the dominant kernel (gemv_kernel) ----
+    # ---- roofline of the dominant kernel (gemv_mma_kernel) ----
     peaks, peaks_kind = measured_peaks()
     gms, glaunches, gbytes = gpu.bench_gemv_pass(20)
     achieved = gbytes / (gms * 1e-3) / 1e9
@@ -276,7 +276,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)",
                 "traffic": traffic, "bytes_per_launch": gbytes / glaunches, "avg_launch_us": gms * 1e3 / glaunches,
                 "launches_per_token": glaunches, "gemv_ms_per_token": gms,

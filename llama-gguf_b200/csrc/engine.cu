@@ -117,7 +117,7 @@ struct b200_ctx {
     int* mma_err = nullptr;
     int mma_tickets_n = 0;
     bool use_mma = true;
-    int mma_chunk = 512, mma_warps = 16, mma_stages = 2;
+    int mma_warps = 16, mma_stages = 3;
     size_t smem_optin = 227 * 1024;
     uint64_t mma_launches = 0, v1_launches = 0;
     size_t out_scratch_elems = 0;
@@ -195,9 +195,8 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_pdl = env_int("B200_PDL", 1) != 0;
     c->use_taps = env_int("B200_TAPS", 0) != 0;
     c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
-    c->mma_chunk = env_int("B200_MMA_CHUNK", 512) == 1024 ? 1024 : 512;
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
-    c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 2)));
+    c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     c->layers.resize(d.n_layers);
     *out = c;
@@ -376,7 +375,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     }
     // kernels that may need more than 48 KB of dynamic shared memory
     CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CU(mma_set_smem_limit((int)c->smem_optin - 1024));
+    CU(mma_set_smem_limit((int)c->smem_optin - 6144));
     CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     c->finalized = true;
     return B200_OK;
@@ -429,7 +428,7 @@ static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& p
     m.epi = p.epi == EPI_STORE ? ME_STORE : p.epi == EPI_RESIDUAL ? ME_RESIDUAL : p.epi == EPI_SWIGLU ? ME_SWIGLU : ME_SCALED_ACC;
     m.expert_sel = p.expert_sel; m.expert_wt = p.expert_wt; m.expert_slot = p.expert_slot;
     m.part = c->mma_part; m.tickets = c->mma_tickets; m.err = c->mma_err;
-    if (!mma_plan(m, c->n_sm, c->mma_chunk, c->mma_warps, c->mma_stages, c->smem_optin - 1024, plan)) return false;
+    if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, c->smem_optin - 6144, plan)) return false;
     int tiles = 0;
     for (int s = 0; s < m.n_seg; s++) tiles += m.seg[s].n_tiles;
     return tiles <= c->mma_tickets_n;
@@ -441,7 +440,7 @@ static cudaError_t launch_gemv(b200_ctx* c, GemvParams& p) {
         MPlan plan;
         if (to_mma_params(c, p, m, plan)) {
             c->mma_launches++;
-            return launch_k(c, mma_kernel_for(plan.warps), dim3(plan.grid), dim3(plan.warps * 32), plan.smem, m);
+            return launch_k(c, mma_kernel_for(plan.stages), dim3(plan.grid), dim3(plan.warps * 32), plan.smem, m);
         }
     }
     c->v1_launches++;

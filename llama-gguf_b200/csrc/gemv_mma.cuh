@@ -10,7 +10,7 @@
 // Why this shape (profiles/r01_v1_*: the CUDA-core version spent ~6 issue slots per weight
 // and stalled at 1.2 TB/s):
 //  * weights go HBM -> shared memory with 16-byte cp.async (SASS LDGSTS) into PER-WARP rings.
-//    A unit is 16 rows x 512 (or 1024) elements; a lane moves 16-byte pieces of two rows, so an
+//    A unit is 16 rows x 256 elements (one K-quant super-block per row); a lane moves 16-byte pieces of two rows, so an
 //    instruction covers 8 rows x 64 contiguous bytes and costs no address arithmetic.  (Per-row
 //    cp.async.bulk copies measured slower: UBLKCP is issued one lane at a time, ~10 issue slots
 //    per 288-byte copy, profiles/r01_v2_*.)  A warp produces and consumes its own ring, so
@@ -25,9 +25,10 @@
 //    8 columns of the MMA are used as 4 (hi, lo) pairs: the B operand is zero except in the
 //    pair of the sub-block a lane's k-slots belong to, so each sub-block's sum lands in the
 //    lane that decoded its scale and nothing is shuffled until a tile is finished;
-//  * stream-K: all (tile, chunk) units of a launch are dealt evenly to the warps of a
-//    persistent grid; tiles cut across warps are merged through a small scratch + ticket in
-//    a fixed order (run-to-run deterministic).
+//  * stream-K: all (tile, chunk) units of a launch are dealt evenly, in contiguous runs, to the
+//    warps of a persistent grid (one CTA per SM, up to 16 warps).  Tiles cut across warps are
+//    merged through shared memory inside a CTA and through a small global scratch + ticket
+//    across CTAs, always in a fixed order (run-to-run deterministic).
 //
 // ~1.3 issue slots per weight (Q4_K) instead of ~6; see DESIGN.md for the budget.
 #pragma once
@@ -41,6 +42,8 @@ constexpr int kMmaMaxStages = 4;
 
 enum : int { ME_STORE = 0, ME_RESIDUAL = 1, ME_SWIGLU = 2, ME_SCALED_ACC = 3 };
 
+constexpr int kMmaChunk = 256;   // elements of K per unit (one K-quant super-block, eight Q8_0 blocks)
+
 struct MSeg {
     const uint8_t* w;
     float* out;            // f32 output [n_rows]
@@ -52,8 +55,9 @@ struct MSeg {
     int n_tiles;           // ceil(n_rows / 16)
     int unit0;             // first unit of this segment in the launch
     int row_stride;        // pitch of the row slots of a ring stage
-    int cb;                // blocks per chunk
-    int chunk_bytes;       // cb * block bytes
+    int cb;                // blocks per unit
+    int bb;                // block bytes
+    int chunk_bytes;       // cb * bb
     int nb_row;            // blocks per row (K / block elems)
 };
 
@@ -61,11 +65,10 @@ struct MParams {
     MSeg seg[3];
     int n_seg;
     int K;
-    int chunk_elems;       // 512 or 1024
-    int chunks;            // ceil(K / chunk_elems)
+    int chunks;            // ceil(K / 256)
     int units_per_tile;    // chunks (2*chunks for ME_SWIGLU: gate chunks then up chunks)
     int total_units;
-    int active_warps;      // min(grid*warps, total_units): every active warp owns >= 1 unit
+    int total_warps;       // min(grid*warps, total_units): every one of these warps owns >= 1 unit
     int stages;
     int stage_bytes;       // 16 * max row_stride
     const float* x;        // [K] f32
@@ -77,10 +80,10 @@ struct MParams {
     const int* expert_sel;
     const float* expert_wt;
     int expert_slot;
-    // stream-K merge scratch
-    float* part;             // [grid*warps][2][32]
+    // cross-CTA merge scratch
+    float* part;             // [grid][2][32]
     unsigned int* tickets;   // [total logical tiles], zero between launches
-    int* err;                // device error flag (watchdog)
+    int* err;                // device error flag (unused by the cp.async pipeline; kept for the watchdog ABI)
     unsigned long long* dbg; // optional [grid*warps][8] globaltimer stamps (lab only)
 };
 
@@ -512,15 +515,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait(int pending) {  // at most `pending` newest groups still in flight
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {  // at most N newest groups still in flight
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-// ticket with release (my partial sums are visible) + acquire (I see the others') semantics: no full fence needed
+// ticket with release (my partial sums are visible) + acquire (I see the others') semantics
 __device__ __forceinline__ unsigned int atom_add_acq_rel(unsigned int* p, unsigned int v) {
     unsigned int r;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
@@ -531,7 +530,6 @@ __device__ __forceinline__ float ld_relaxed_gpu(const float* p) {
     asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
-
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -542,101 +540,108 @@ __device__ __forceinline__ unsigned long long gtimer() {
         if (p.dbg && lane == 0) p.dbg[(size_t)gw * 8 + (i)] = gtimer(); \
     } while (0)
 
-// Position of a warp in its run of units: segment s, 16-row tile, logical chunk c (ME_SWIGLU: c >= chunks
-// are the up-projection's chunks).  rowA / rowB point at the first byte of rows tile*16+g and +8 of the
-// matrix the chunk belongs to.  Advanced incrementally: no divisions inside the unit loop.
+// Position of a warp in its run of units: segment s, 16-row tile, matrix (ME_SWIGLU: 0 = gate, 1 = up; else = s),
+// chunk (256 elements) within the row.  a / b are the true addresses of the unit's bytes in rows tile*16+g and +8.
+// Advanced incrementally: the common step is chunk++ and two pointer bumps, no divisions.
 struct MCursor {
-    int s, tile, c, mat, chunk;
-    const uint8_t* rowA;
-    const uint8_t* rowB;
+    int s, tile, mat, chunk;
+    const uint8_t* a;
+    const uint8_t* b;
 };
 
-template <int MAXW>
-__global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p) {
+template <int STAGES>
+__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
+    __shared__ float s_part[kMmaMaxWarps][2][32];   // pieces of tiles shared between warps of this CTA
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nw = blockDim.x >> 5;
     const int K = p.K;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t ring = sbase + (uint32_t)x_smem_bytes(K) + (uint32_t)warp * p.stages * p.stage_bytes;
+    const uint32_t ring = sbase + (uint32_t)x_smem_bytes(K) + (uint32_t)warp * STAGES * p.stage_bytes;
     const bool swiglu = p.epi == ME_SWIGLU;
 
-    // interleaved warp numbering: consecutive global warps sit on different SMs
-    const long long U = p.total_units, W = p.active_warps;
-    const long long gw = (long long)warp * gridDim.x + blockIdx.x;
+    // units are dealt in contiguous runs, warp after warp, CTA after CTA: the pieces of a tile mostly meet inside
+    // one CTA (merged through shared memory), only tiles that straddle CTAs go through global memory
+    const long long U = p.total_units, W = p.total_warps;
+    const long long gw = (long long)blockIdx.x * nw + warp;
     const bool active = gw < W;
     const int u0 = active ? (int)(gw * U / W) : 0, u1 = active ? (int)((gw + 1) * U / W) : 0;
     const int n_units = u1 - u0;
     long long eoff = 0;  // MoE expert index (valid after pdl_wait)
     MMA_STAMP(0);
 
-    auto cur_rows = [&](MCursor& q) {
-        q.mat = q.s;
-        q.chunk = q.c;
-        if (swiglu && q.c >= p.chunks) { q.mat = 1; q.chunk = q.c - p.chunks; }
+    auto cur_ptrs = [&](MCursor& q) {
         const MSeg& sg = p.seg[q.mat];
-        const uint8_t* base = sg.w + eoff * sg.expert_stride;
-        q.rowA = base + (long long)min(q.tile * 16 + g, sg.n_rows - 1) * sg.row_bytes;
-        q.rowB = base + (long long)min(q.tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes;
+        const uint8_t* base = sg.w + eoff * sg.expert_stride + (long long)q.chunk * sg.chunk_bytes;
+        q.a = base + (long long)min(q.tile * 16 + g, sg.n_rows - 1) * sg.row_bytes;
+        q.b = base + (long long)min(q.tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes;
     };
     auto cur_init = [&](MCursor& q, int u) {
         q.s = (p.n_seg > 2 && u >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && !swiglu && u >= p.seg[1].unit0) ? 1 : 0;
         const int local = u - p.seg[q.s].unit0;
         q.tile = local / p.units_per_tile;
-        q.c = local - q.tile * p.units_per_tile;
-        cur_rows(q);
+        q.chunk = local - q.tile * p.units_per_tile;
+        q.mat = q.s;
+        if (swiglu && q.chunk >= p.chunks) { q.mat = 1; q.chunk -= p.chunks; }
+        cur_ptrs(q);
     };
-    auto cur_next = [&](MCursor& q) {
-        q.c++;
-        if (q.c == p.units_per_tile) {
-            q.c = 0;
-            q.tile++;
-            if (q.tile == p.seg[q.s].n_tiles && q.s + 1 < p.n_seg && !swiglu) { q.s++; q.tile = 0; }
-            cur_rows(q);
-        } else if (swiglu && q.c == p.chunks) {
-            cur_rows(q);
-        } else {
-            q.chunk++;
-        }
-    };
-    // cp.async the 16 rows of the unit at q into ring stage st: lane (g, t) moves 16-byte pieces t, t+4, ...
-    // of rows g and g+8 (8 rows x 64 contiguous bytes per instruction).  l2_only: just pull the lines into L2.
-    auto issue = [&](const MCursor& q, int st, bool l2_only) {
-        const MSeg& sg = p.seg[q.mat];
-        const int nblk = min(sg.cb, sg.nb_row - q.chunk * sg.cb);
-        const int bytes = nblk * (sg.chunk_bytes / sg.cb);
-        const long long off = (long long)q.chunk * sg.chunk_bytes;
-        const uint8_t* sa = q.rowA + off;
-        const uint8_t* sb = q.rowB + off;
-        const uint32_t da = (uint32_t)((uintptr_t)sa & 15u), db = (uint32_t)((uintptr_t)sb & 15u);
-        if (l2_only) {
-            for (int o = 128 * t; o < bytes + 15; o += 512) {
-                prefetch_l2(sa - da + o);
-                prefetch_l2(sb - db + o);
-            }
+    auto cur_step = [&](MCursor& q) {
+        q.chunk++;
+        if (q.chunk < p.chunks) {
+            const int cbytes = p.seg[q.mat].chunk_bytes;
+            q.a += cbytes;
+            q.b += cbytes;
             return;
         }
-        sa += 16 * t - (int)da;
-        sb += 16 * t - (int)db;
+        q.chunk = 0;
+        if (swiglu && q.mat == 0) {
+            q.mat = 1;
+        } else {
+            q.tile++;
+            if (swiglu) {
+                q.mat = 0;
+            } else {
+                if (q.tile == p.seg[q.s].n_tiles && q.s + 1 < p.n_seg) { q.s++; q.tile = 0; }
+                q.mat = q.s;
+            }
+        }
+        cur_ptrs(q);
+    };
+    // cp.async the 16 rows of the unit at q into ring stage st: lane (g, t) moves the 16-byte pieces t, t+4, ... of
+    // rows g and g+8 (8 rows x 64 contiguous bytes per instruction); sources are aligned down to 16 bytes (doff).
+    // l2_only: just pull the lines towards L2.
+    auto issue = [&](const MCursor& q, int st, bool l2_only) {
+        const MSeg& sg = p.seg[q.mat];
+        const int bytes = min(sg.cb, sg.nb_row - q.chunk * sg.cb) * sg.bb;
+        const uint32_t da = (uint32_t)((uintptr_t)q.a & 15u), db = (uint32_t)((uintptr_t)q.b & 15u);
+        const uint8_t* sa = q.a - da + 16 * t;
+        const uint8_t* sb = q.b - db + 16 * t;
+        if (l2_only) {
+            if (t * 128 < (int)da + bytes) prefetch_l2(q.a - da + 128 * t);
+            if (t * 128 < (int)db + bytes) prefetch_l2(q.b - db + 128 * t);
+            return;
+        }
         const uint32_t dst = ring + (uint32_t)st * p.stage_bytes + (uint32_t)g * sg.row_stride + 16u * t;
         const uint32_t dstb = dst + 8u * sg.row_stride;
-        const int iters = ((int)max(da, db) + bytes + 63) >> 6;  // whole 64-byte steps; never beyond the row slot
-        for (int i = 0; i < iters; i++) {
-            cp_async16(dst + 64 * i, sa + 64 * i);
-            cp_async16(dstb + 64 * i, sb + 64 * i);
+        const int ea = (int)da + bytes - 16 * t, eb = (int)db + bytes - 16 * t;  // bytes from this lane's first piece to the end
+#pragma unroll
+        for (int i = 0; i < 5; i++) {  // <= 287 bytes per row and unit
+            if (64 * i < ea) cp_async16(dst + 64 * i, sa + 64 * i);
+            if (64 * i < eb) cp_async16(dstb + 64 * i, sb + 64 * i);
         }
     };
 
     MCursor cp{}, cc{};
-    const int pre = min(p.stages - 1, n_units);
+    const int pre = min(STAGES - 1, n_units);
     if (n_units > 0 && !p.expert_sel) {
         // dense weights never depend on a predecessor: pull the first stages towards L2 before the PDL wait
         // (fire-and-forget; an early cp.async would make the x loads below queue behind DRAM-latency copies)
         cur_init(cp, u0);
         cc = cp;
         MCursor q = cp;
-        for (int k = 0; k < pre; k++) { issue(q, k, true); cur_next(q); }
+        for (int k = 0; k < pre; k++) { issue(q, k, true); cur_step(q); }
     }
 
     pdl_launch_dependents();
@@ -650,8 +655,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p)
     // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
     XStage xst;
     stage_x_load(xst, p.x, p.norm_w, K, s_red);
-    for (int k = 0; k < p.stages - 1; k++) {
-        if (k < pre) { issue(cp, k, false); cur_next(cp); }
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; k++) {
+        if (k < pre) { issue(cp, k, false); cur_step(cp); }
         cp_async_commit();
     }
     MMA_STAMP(2);
@@ -665,81 +671,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p)
     sm.xs = sm.xh + 4u * K + kXlPad;
     sm.zero = sbase + tokx + (uint32_t)x_smem_bytes(K) - 256u;
 
-    float ag0 = 0.f, ag1 = 0.f, au0 = 0.f, au1 = 0.f;
-    for (int k = 0; k < n_units; k++) {
-        if (k + p.stages - 1 < n_units) {
-            issue(cp, (k + p.stages - 1) % p.stages, false);
-            cur_next(cp);
-        }
-        cp_async_commit();
-        cp_async_wait(p.stages - 1);
-        __syncwarp();
-        if (k == 0) MMA_STAMP(4);
-
-        const MSeg& wsg = p.seg[cc.mat];
-        const int type = wsg.type;
-        const int nblk = min(wsg.cb, wsg.nb_row - cc.chunk * wsg.cb);
-        const int e0 = cc.chunk * p.chunk_elems;
-        const uint32_t sp = ring + (uint32_t)(k % p.stages) * p.stage_bytes + smem_token();
-        const uint32_t RS = (uint32_t)wsg.row_stride;
-        float a0 = 0.f, a1 = 0.f;
-        switch (type) {
-            case T_Q4_K: unit_k45<false>(sp, RS, nblk, e0, sm, g, t, a0, a1); break;
-            case T_Q5_K: unit_k45<true>(sp, RS, nblk, e0, sm, g, t, a0, a1); break;
-            default: {
-                const long long off = (long long)cc.chunk * wsg.chunk_bytes;
-                const uint32_t d0 = (uint32_t)((uintptr_t)(cc.rowA + off) & 15u), d1 = (uint32_t)((uintptr_t)(cc.rowB + off) & 15u);
-                if (type == T_Q6_K) unit_q6k(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
-                else unit_q80(sp, RS, nblk, e0, d0, d1, sm, g, t, a0, a1);
-                break;
-            }
-        }
-        pin2(a0, a1);  // the unit's shared-memory reads are complete before the stage can be refilled
-        if (cc.mat != cc.s) { au0 += a0; au1 += a1; } else { ag0 += a0; ag1 += a1; }
-        __syncwarp();  // every lane is done with this stage
-        if (k == n_units - 1) MMA_STAMP(5);
-
-        // ---- tile finished (for this warp)? ----
-        const int s = cc.s, tile = cc.tile;
-        const bool tile_done = (cc.c == p.units_per_tile - 1) || (k == n_units - 1);
-        cur_next(cc);
-        if (!tile_done) continue;
-
-        // reduce the 4 lanes of a row group, then lane L holds logical row L (0..15 gate/plain, 16..31 up)
-        ag0 += __shfl_xor_sync(0xffffffffu, ag0, 1); ag0 += __shfl_xor_sync(0xffffffffu, ag0, 2);
-        ag1 += __shfl_xor_sync(0xffffffffu, ag1, 1); ag1 += __shfl_xor_sync(0xffffffffu, ag1, 2);
-        if (swiglu) {
-            au0 += __shfl_xor_sync(0xffffffffu, au0, 1); au0 += __shfl_xor_sync(0xffffffffu, au0, 2);
-            au1 += __shfl_xor_sync(0xffffffffu, au1, 1); au1 += __shfl_xor_sync(0xffffffffu, au1, 2);
-        }
-        const int src = 4 * (lane & 7);
-        const float vg0 = __shfl_sync(0xffffffffu, ag0, src), vg1 = __shfl_sync(0xffffffffu, ag1, src);
-        const float vu0 = __shfl_sync(0xffffffffu, au0, src), vu1 = __shfl_sync(0xffffffffu, au1, src);
-        float v = (lane < 16) ? ((lane & 8) ? vg1 : vg0) : ((lane & 8) ? vu1 : vu0);
-        ag0 = ag1 = au0 = au1 = 0.f;
-
-        // stream-K merge: which warps hold pieces of this tile?
-        const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
-        const int w_first = mma_owner(tu0, U, W), w_last = mma_owner(tu0 + p.units_per_tile - 1, U, W);
-        if (w_last != w_first) {
-            const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
-            const int slot = ((long long)u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or my last (slot 1)
-            p.part[((size_t)gw * 2 + slot) * 32 + lane] = v;
-            __syncwarp();
-            unsigned int ticket = 0;
-            if (lane == 0) ticket = atom_add_acq_rel(&p.tickets[tile_id], 1u);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            if (ticket != (unsigned)(w_last - w_first)) continue;  // not the last piece
-            v = 0.f;
-            for (int wi = w_first; wi <= w_last; wi++) {  // fixed order: deterministic
-                const long long wu0 = (long long)wi * U / W;
-                const int sl = (wu0 >= tu0) ? 0 : 1;
-                v += ld_relaxed_gpu(&p.part[((size_t)wi * 2 + sl) * 32 + lane]);
-            }
-            if (lane == 0) p.tickets[tile_id] = 0;
-        }
-
-        // ---- epilogue: lane L < 16 owns row j of segment s ----
+    // ---- epilogue of a finished tile: lane L < 16 owns row tile*16 + L of segment s (v: lanes 16..31 = up rows) ----
+    auto epilogue = [&](int s, int tile, float v) {
         const MSeg& sg = p.seg[s];
         const int j = tile * 16 + (lane & 15);
         const bool valid = (lane < 16) && (j < sg.n_rows);
@@ -759,6 +692,105 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p)
             }
             sg.out[j] = val;
         }
+    };
+
+    float ag0 = 0.f, ag1 = 0.f, au0 = 0.f, au1 = 0.f;
+    int piece_s[2] = {-1, -1}, piece_tile[2] = {0, 0};  // tiles of which this warp holds only a piece (first / last of its run)
+    int st_c = 0, st_p = (STAGES - 1) % STAGES;
+    for (int k = 0; k < n_units; k++) {
+        if (k + STAGES - 1 < n_units) {
+            issue(cp, st_p, false);
+            cur_step(cp);
+        }
+        st_p = (st_p + 1 == STAGES) ? 0 : st_p + 1;
+        cp_async_commit();
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        if (k == 0) MMA_STAMP(4);
+
+        const MSeg& wsg = p.seg[cc.mat];
+        const int type = wsg.type;
+        const int nblk = min(wsg.cb, wsg.nb_row - cc.chunk * wsg.cb);
+        const int e0 = cc.chunk * kMmaChunk;
+        const uint32_t sp = ring + (uint32_t)st_c * p.stage_bytes + smem_token();
+        const uint32_t RS = (uint32_t)wsg.row_stride;
+        st_c = (st_c + 1 == STAGES) ? 0 : st_c + 1;
+        float a0 = 0.f, a1 = 0.f;
+        switch (type) {
+            case T_Q4_K: unit_k45<false>(sp, RS, 1, e0, sm, g, t, a0, a1); break;
+            case T_Q5_K: unit_k45<true>(sp, RS, 1, e0, sm, g, t, a0, a1); break;
+            case T_Q6_K: unit_q6k(sp, RS, 1, e0, (uint32_t)((uintptr_t)cc.a & 15u), (uint32_t)((uintptr_t)cc.b & 15u), sm, g, t, a0, a1); break;
+            default: unit_q80(sp, RS, nblk, e0, (uint32_t)((uintptr_t)cc.a & 15u), (uint32_t)((uintptr_t)cc.b & 15u), sm, g, t, a0, a1); break;
+        }
+        pin2(a0, a1);  // the unit's shared-memory reads are complete before the stage can be refilled
+        if (swiglu && cc.mat == 1) { au0 += a0; au1 += a1; } else { ag0 += a0; ag1 += a1; }
+        __syncwarp();  // every lane is done with this stage
+
+        // ---- tile finished (for this warp)? ----
+        const int s = cc.s, tile = cc.tile;
+        const bool tile_done = (cc.chunk == p.chunks - 1 && (!swiglu || cc.mat == 1)) || (k == n_units - 1);
+        cur_step(cc);
+        if (!tile_done) continue;
+        if (k == n_units - 1) MMA_STAMP(5);
+
+        // reduce the 4 lanes of a row group, then lane L holds logical row L (0..15 gate/plain, 16..31 up)
+        ag0 += __shfl_xor_sync(0xffffffffu, ag0, 1); ag0 += __shfl_xor_sync(0xffffffffu, ag0, 2);
+        ag1 += __shfl_xor_sync(0xffffffffu, ag1, 1); ag1 += __shfl_xor_sync(0xffffffffu, ag1, 2);
+        if (swiglu) {
+            au0 += __shfl_xor_sync(0xffffffffu, au0, 1); au0 += __shfl_xor_sync(0xffffffffu, au0, 2);
+            au1 += __shfl_xor_sync(0xffffffffu, au1, 1); au1 += __shfl_xor_sync(0xffffffffu, au1, 2);
+        }
+        const int src = 4 * (lane & 7);
+        const float vg0 = __shfl_sync(0xffffffffu, ag0, src), vg1 = __shfl_sync(0xffffffffu, ag1, src);
+        const float vu0 = __shfl_sync(0xffffffffu, au0, src), vu1 = __shfl_sync(0xffffffffu, au1, src);
+        const float v = (lane < 16) ? ((lane & 8) ? vg1 : vg0) : ((lane & 8) ? vu1 : vu0);
+        ag0 = ag1 = au0 = au1 = 0.f;
+
+        const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
+        if ((long long)u0 <= tu0 && tu0 + p.units_per_tile <= (long long)u1) {
+            epilogue(s, tile, v);  // the whole tile is mine
+        } else {
+            const int slot = ((long long)u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or starts inside my run (slot 1)
+            s_part[warp][slot][lane] = v;
+            piece_s[slot] = s;
+            piece_tile[slot] = tile;
+        }
+    }
+
+    // ---- merge the pieces: inside the CTA through shared memory, across CTAs through global memory + ticket ----
+    __syncthreads();
+    const long long cw0 = (long long)blockIdx.x * nw, cw1 = min(cw0 + nw, W) - 1;
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+        if (piece_s[slot] < 0) continue;  // warp-uniform
+        const int s = piece_s[slot], tile = piece_tile[slot];
+        const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
+        const long long w_first = mma_owner(tu0, U, W), w_last = mma_owner(tu0 + p.units_per_tile - 1, U, W);
+        const long long lo = max(w_first, cw0), hi = min(w_last, cw1);
+        if (gw != lo) continue;  // the first warp of the CTA that holds a piece finishes the tile
+        float v = 0.f;
+        for (long long w = lo; w <= hi; w++) {  // fixed order: deterministic
+            const int sl = (w * U / W >= tu0) ? 0 : 1;
+            v += s_part[(int)(w - cw0)][sl][lane];
+        }
+        if (lo != w_first || hi != w_last) {  // the tile straddles CTAs
+            const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
+            const long long c_first = w_first / nw, c_last = w_last / nw;
+            const int cslot = (cw0 * U / W >= tu0) ? 0 : 1;
+            p.part[((size_t)blockIdx.x * 2 + cslot) * 32 + lane] = v;
+            __syncwarp();
+            unsigned int ticket = 0;
+            if (lane == 0) ticket = atom_add_acq_rel(&p.tickets[tile_id], 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket != (unsigned)(c_last - c_first)) continue;  // not the last CTA
+            v = 0.f;
+            for (long long c = c_first; c <= c_last; c++) {
+                const int sl = ((c * nw) * U / W >= tu0) ? 0 : 1;
+                v += ld_relaxed_gpu(&p.part[((size_t)c * 2 + sl) * 32 + lane]);
+            }
+            if (lane == 0) p.tickets[tile_id] = 0;
+        }
+        epilogue(s, tile, v);
     }
     MMA_STAMP(6);
 }
@@ -766,13 +798,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv_mma_kernel(const MParams p)
 // ---------------------------------------------------------------- host-side launch planning
 inline bool mma_type_ok(int type) { return type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q8_0; }
 
-// bytes between row slots: room for the chunk plus the whole 64-byte copy iterations that cover up to 15
-// bytes of source misalignment (and the 4-byte funnel over-read), residue mod 128 chosen for conflict-free
-// fragment loads (LDS.128 row pairs: 64; 32-bit loads of 8 rows: odd multiple of 16)
-inline int mma_row_stride(int type, int chunk_elems) {
-    const int cb = mma_chunk_blocks(type, chunk_elems), bb = type_block_bytes(type);
+// bytes between row slots: the unit's bytes plus up to 15 bytes of source misalignment, residue mod 128 chosen
+// for conflict-free fragment loads (LDS.128 row pairs: 64; 32-bit loads of 8 rows: odd multiple of 16)
+inline int mma_row_stride(int type) {
+    const int cb = kMmaChunk / type_block_elems(type), bb = type_block_bytes(type);
     const bool aligned = (type == T_Q4_K || type == T_Q5_K);
-    int rs = aligned ? ((cb * bb + 63) & ~63) : ((15 + cb * bb + 63) & ~63);
+    int rs = aligned ? ((cb * bb + 15) & ~15) : ((15 + cb * bb + 4 + 15) & ~15);
     for (;; rs += 16) {
         const int m = rs & 127;
         if (aligned ? (m == 64) : ((m & 15) == 0 && ((m >> 4) & 1))) return rs;
@@ -787,7 +818,7 @@ struct MPlan {
 // Fills the derived fields of p (segments' w/out/bias/row_bytes/expert_stride/type/n_rows, n_seg, K, epi
 // must be set) and picks warps/stages so that x + the rings fit in shared memory.  Returns false if the
 // launch is not eligible for this kernel (caller falls back to the CUDA-core kernel).
-inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int want_stages, size_t smem_limit, MPlan& plan) {
+inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size_t smem_limit, MPlan& plan) {
     if (p.K % 32) return false;
     if (p.epi == ME_SWIGLU && (p.n_seg != 2 || p.seg[0].n_rows != p.seg[1].n_rows)) return false;
     int max_rs = 0;
@@ -796,17 +827,16 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
         if (!mma_type_ok(sg.type)) return false;
         if (p.K % type_block_elems(sg.type)) return false;
         if ((sg.type == T_Q4_K || sg.type == T_Q5_K) && ((sg.row_bytes & 15) || (sg.expert_stride & 15) || ((uintptr_t)sg.w & 15))) return false;
-        if ((sg.row_bytes & 1) || (sg.expert_stride & 1)) return false;
-        if (chunk_elems % type_block_elems(sg.type)) return false;
-        sg.row_stride = mma_row_stride(sg.type, chunk_elems);
-        sg.cb = mma_chunk_blocks(sg.type, chunk_elems);
-        sg.chunk_bytes = sg.cb * type_block_bytes(sg.type);
+        if ((sg.row_bytes & 1) || (sg.expert_stride & 1) || ((uintptr_t)sg.w & 1)) return false;
+        sg.row_stride = mma_row_stride(sg.type);
+        sg.cb = kMmaChunk / type_block_elems(sg.type);
+        sg.bb = type_block_bytes(sg.type);
+        sg.chunk_bytes = sg.cb * sg.bb;
         sg.nb_row = p.K / type_block_elems(sg.type);
         sg.n_tiles = (sg.n_rows + 15) / 16;
         max_rs = std::max(max_rs, sg.row_stride);
     }
-    p.chunk_elems = chunk_elems;
-    p.chunks = (p.K + chunk_elems - 1) / chunk_elems;
+    p.chunks = (p.K + kMmaChunk - 1) / kMmaChunk;
     if (p.epi == ME_SWIGLU) {
         p.units_per_tile = 2 * p.chunks;
         p.seg[0].unit0 = 0;
@@ -823,7 +853,7 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
     }
     p.stage_bytes = 16 * max_rs;
     const size_t xb = x_smem_bytes(p.K);
-    int warps = std::min(want_warps, kMmaMaxWarps), stages = std::min(want_stages, kMmaMaxStages);
+    int warps = std::max(4, std::min(want_warps, kMmaMaxWarps)), stages = std::max(2, std::min(want_stages, kMmaMaxStages));
     auto need = [&](int w, int st) { return xb + (size_t)w * st * p.stage_bytes + 16; };  // +16: funnel loads read one word past a piece
     while (need(warps, stages) > smem_limit) {
         if (stages > 2) stages--;
@@ -834,26 +864,22 @@ inline bool mma_plan(MParams& p, int n_sm, int chunk_elems, int want_warps, int 
     plan.warps = warps;
     plan.stages = stages;
     plan.smem = need(warps, stages);
-    const long long slots = (long long)n_sm * warps;
     plan.grid = (int)std::min<long long>(n_sm, (p.total_units + warps - 1) / warps);
     if (plan.grid < 1) plan.grid = 1;
-    p.active_warps = (int)std::min<long long>((long long)plan.grid * warps, p.total_units);
-    (void)slots;
+    p.total_warps = (int)std::min<long long>((long long)plan.grid * warps, p.total_units);
     return true;
 }
 
-// The kernel is instantiated for three register budgets (launch bounds): more registers per thread let ptxas
-// overlap two blocks of a unit when fewer warps are resident.
 using MmaKernel = void (*)(const MParams);
-inline MmaKernel mma_kernel_for(int warps) {
-    if (warps <= 8) return gemv_mma_kernel<8>;
-    if (warps <= 12) return gemv_mma_kernel<12>;
-    return gemv_mma_kernel<16>;
+inline MmaKernel mma_kernel_for(int stages) {
+    if (stages <= 2) return gemv_mma_kernel<2>;
+    if (stages == 3) return gemv_mma_kernel<3>;
+    return gemv_mma_kernel<4>;
 }
 inline cudaError_t mma_set_smem_limit(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 

@@ -145,13 +145,13 @@ static unsigned long long* g_dbg = nullptr;
 static bool g_use_dbg = false;
 static size_t g_smem_limit = 227 * 1024;
 
-struct Knobs { int chunk = 512, warps = 16, stages = 2; };
+struct Knobs { int warps = 16, stages = 3; };
 
 static void lab_init() {
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, 0));
     g_nsm = prop.multiProcessorCount;
-    g_smem_limit = prop.sharedMemPerBlockOptin - 1024;
+    g_smem_limit = prop.sharedMemPerBlockOptin - 6144;  // static shared memory of the kernels
     printf("device: %s, %d SMs, smem optin %zu\n", prop.name, g_nsm, (size_t)prop.sharedMemPerBlockOptin);
     CK(cudaMalloc(&g_part, (size_t)g_nsm * kMmaMaxWarps * 2 * 32 * 4));
     CK(cudaMalloc(&g_tickets, 65536 * 4));
@@ -159,7 +159,7 @@ static void lab_init() {
     CK(cudaMalloc(&g_err, 4));
     CK(cudaMemset(g_err, 0, 4));
     CK(cudaMalloc(&g_dbg, (size_t)g_nsm * kMmaMaxWarps * 8 * 8));
-    CK(mma_set_smem_limit((int)prop.sharedMemPerBlockOptin - 1024));
+    CK(mma_set_smem_limit((int)g_smem_limit));
     CK(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 }
 
@@ -169,7 +169,7 @@ static bool launch_mma(cudaStream_t st, MParams p, const Knobs& kn, bool pdl) {
     p.tickets = g_tickets;
     p.err = g_err;
     p.dbg = g_use_dbg ? g_dbg : nullptr;
-    if (!mma_plan(p, g_nsm, kn.chunk, kn.warps, kn.stages, g_smem_limit, plan)) return false;
+    if (!mma_plan(p, g_nsm, kn.warps, kn.stages, g_smem_limit, plan)) return false;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
     cfg.blockDim = dim3(plan.warps * 32);
@@ -180,7 +180,7 @@ static bool launch_mma(cudaStream_t st, MParams p, const Knobs& kn, bool pdl) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = pdl ? at : nullptr;
     cfg.numAttrs = pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, mma_kernel_for(plan.warps), p));
+    CK(cudaLaunchKernelEx(&cfg, mma_kernel_for(plan.stages), p));
     return true;
 }
 static void launch_v1(cudaStream_t st, GemvParams p, bool pdl) {
@@ -258,7 +258,7 @@ static void check_onehot(int type, int K, const Knobs& kn) {
                 }
             }
         }
-    printf("onehot %-5s K=%-5d chunk=%d: %s (%d / %d mismatches) err=%d\n", tname(type), K, kn.chunk, bad ? "FAIL" : "ok", bad, K * N, read_err());
+    printf("onehot %-5s K=%-5d w=%d st=%d: %s (%d / %d mismatches) err=%d\n", tname(type), K, kn.warps, kn.stages, bad ? "FAIL" : "ok", bad, K * N, read_err());
     if (bad) g_fail++;
     cudaFree(dw); cudaFree(dx); cudaFree(dy);
 }
@@ -332,8 +332,8 @@ static double check_random(int type, int K, int N, const Knobs& kn, int epi, boo
         max_err = std::max(max_err, fabs(got - want[i]) / (rms + 1e-30));
     }
     const bool ok = max_err < 2e-4 && det && nanc == 0 && read_err() == 0;
-    printf("random %-5s K=%-6d N=%-7d epi=%d bias=%d norm=%d xs=%g w=%d st=%d ch=%d: max|err|/rms=%.2e det=%d nan=%d err=%d %s\n", tname(type), K, N, epi,
-           with_bias, with_norm, xscale, kn.warps, kn.stages, kn.chunk, max_err, det, nanc, read_err(), ok ? "ok" : "FAIL");
+    printf("random %-5s K=%-6d N=%-7d epi=%d bias=%d norm=%d xs=%g w=%d st=%d: max|err|/rms=%.2e det=%d nan=%d err=%d %s\n", tname(type), K, N, epi,
+           with_bias, with_norm, xscale, kn.warps, kn.stages, max_err, det, nanc, read_err(), ok ? "ok" : "FAIL");
     if (!ok) g_fail++;
     cudaFree(dw); cudaFree(dx); cudaFree(dn); cudaFree(db); cudaFree(dr); cudaFree(dy);
     return max_err;
@@ -428,8 +428,8 @@ static void time_case(const TimeCase& tc, const std::vector<Knobs>& knobs, bool 
             pp.seg[0] = mseg(dw, dy, nullptr, tc.type, tc.K, tc.N); pp.n_seg = 1;
             if (tc.epi == ME_SWIGLU) { pp.seg[1] = pp.seg[0]; pp.n_seg = 2; }
             pp.K = tc.K; pp.epi = tc.epi;
-            mma_plan(pp, g_nsm, kn.chunk, kn.warps, kn.stages, g_smem_limit, plan);
-            printf("   mma ch=%-4d w=%-2d st=%d (got w=%d st=%d smem=%zuK grid=%d) pdl=%d: %8.2f us  %7.1f GB/s%s err=%d\n", kn.chunk, kn.warps, kn.stages,
+            mma_plan(pp, g_nsm, kn.warps, kn.stages, g_smem_limit, plan);
+            printf("   mma w=%-2d st=%d (got w=%d st=%d smem=%zuK grid=%d) pdl=%d: %8.2f us  %7.1f GB/s%s err=%d\n", kn.warps, kn.stages,
                    plan.warps, plan.stages, plan.smem / 1024, plan.grid, pdl, ms * 1e3, wbytes / (ms * 1e-3) / 1e9, okp ? "" : " PLAN-FAILED", read_err());
         }
     }
@@ -477,7 +477,7 @@ static void timeline_case(const TimeCase& tc, const Knobs& kn) {
         CK(cudaMemcpy(h.data(), g_dbg, nw * 64, cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
         for (size_t w = 0; w < nw; w++) if (h[w * 8]) t0 = std::min(t0, h[w * 8]);
-        printf("timeline %s ch=%d w=%d st=%d rep %d (ns after the first warp's start; min / avg / max over warps)\n", tc.name, kn.chunk, kn.warps, kn.stages, rep);
+        printf("timeline %s w=%d st=%d rep %d (ns after the first warp's start; min / avg / max over warps)\n", tc.name, kn.warps, kn.stages, rep);
         for (int i = 0; i < 7; i++) {
             unsigned long long mn = ~0ull, mx = 0; double sum = 0; int n = 0;
             for (size_t w = 0; w < nw; w++) {
@@ -562,8 +562,8 @@ static void time_layer_chain(const Knobs& kn, int down_type, bool graph) {
     CK(cudaStreamSynchronize(st));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     const double us_layer = ms * 1e3 / iters / layers;
-    printf("layer chain (down/v=%s, %s, ch=%d w=%d st=%d): %.2f us/layer, %.1f MB/layer -> %.1f GB/s  (x32 layers = %.3f ms) err=%d\n", tname(down_type),
-           graph ? "graph+PDL" : "stream+PDL", kn.chunk, kn.warps, kn.stages, us_layer, per_layer / 1e6, per_layer / (us_layer * 1e-6) / 1e9, us_layer * 32e-3, read_err());
+    printf("layer chain (down/v=%s, %s, w=%d st=%d): %.2f us/layer, %.1f MB/layer -> %.1f GB/s  (x32 layers = %.3f ms) err=%d\n", tname(down_type),
+           graph ? "graph+PDL" : "stream+PDL", kn.warps, kn.stages, us_layer, per_layer / 1e6, per_layer / (us_layer * 1e-6) / 1e9, us_layer * 32e-3, read_err());
     if (gx) cudaGraphExecDestroy(gx);
     for (auto& w : ws) { cudaFree(w.q); cudaFree(w.k); cudaFree(w.v); cudaFree(w.o); cudaFree(w.g); cudaFree(w.u); cudaFree(w.d); }
     cudaFree(proto.q); cudaFree(proto.k); cudaFree(proto.v); cudaFree(proto.o); cudaFree(proto.g); cudaFree(proto.u); cudaFree(proto.d);
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(512, 1) stream_rows_kernel(const uint8_t* src,
     for (int k = 0; k < n; k++) {
         if (k + stages - 1 < n) issue(u0 + k + stages - 1, (k + stages - 1) % stages);
         cp_async_commit();
-        cp_async_wait(stages - 1);
+        if (stages == 2) cp_async_wait<1>(); else if (stages == 3) cp_async_wait<2>(); else cp_async_wait<3>();
         __syncwarp();
         acc ^= lds32(ring + (k % stages) * stage_bytes + lane * 4);
         __syncwarp();
@@ -773,13 +773,13 @@ int main(int argc, char** argv) {
     std::string mode = argc > 1 ? argv[1] : "all";
     lab_init();
     if (mode == "check" || mode == "all") {
-        Knobs k512{512, 16, 2}, k1024{1024, 8, 2};
+        Knobs k512{16, 3}, k1024{8, 2};
         for (int type : {T_Q4_K, T_Q5_K, T_Q6_K, T_Q8_0}) {
             check_onehot(type, 512, k512);
             check_onehot(type, 768, k1024);
         }
         check_onehot(T_Q8_0, 96, k512);
-        for (const Knobs& kn : {k512, k1024, Knobs{512, 12, 3}, Knobs{512, 8, 4}}) {
+        for (const Knobs& kn : {k512, k1024, Knobs{12, 4}, Knobs{5, 2}}) {
             for (int type : {T_Q4_K, T_Q5_K, T_Q6_K, T_Q8_0}) {
                 check_random(type, 4096, 4096, kn, ME_STORE, false, false);
                 check_random(type, 2048, 1000, kn, ME_RESIDUAL, true, true);
@@ -800,24 +800,24 @@ int main(int argc, char** argv) {
     }
     if (mode == "rows") stream_rows_probe();
     if (mode == "stream" || mode == "all") stream_probes();
-    if (mode == "prof") {   // one case, for ncu: gemv_lab prof <chunk> <warps> <stages>
-        Knobs kn{argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 16, argc > 4 ? atoi(argv[4]) : 2};
+    if (mode == "prof") {   // one case, for ncu: gemv_lab prof <warps> <stages>
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 16, argc > 3 ? atoi(argv[3]) : 3};
         time_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, {kn}, false);
     }
     if (mode == "timeline") {
-        Knobs kn{argc > 2 ? atoi(argv[2]) : 1024, argc > 3 ? atoi(argv[3]) : 8, argc > 4 ? atoi(argv[4]) : 2};
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 16, argc > 3 ? atoi(argv[3]) : 3};
         timeline_case({"O proj 8B", T_Q4_K, 4096, 4096, ME_RESIDUAL}, kn);
         timeline_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, kn);
         timeline_case({"down 8B Q4_K", T_Q4_K, 14336, 4096, ME_RESIDUAL}, kn);
     }
-    if (mode == "chain") {   // gemv_lab chain <chunk> <warps> <stages>: the PDL layer chain alone (for ncu launch lists)
-        Knobs kn{argc > 2 ? atoi(argv[2]) : 1024, argc > 3 ? atoi(argv[3]) : 8, argc > 4 ? atoi(argv[4]) : 2};
+    if (mode == "chain") {   // gemv_lab chain <warps> <stages>: the PDL layer chain alone (for ncu launch lists)
+        Knobs kn{argc > 2 ? atoi(argv[2]) : 16, argc > 3 ? atoi(argv[3]) : 3};
         time_layer_chain(kn, T_Q4_K, false);
         time_layer_chain(kn, T_Q4_K, true);
     }
     if (mode == "time" || mode == "all") {
-        std::vector<Knobs> sweep = {{512, 16, 2}, {512, 12, 3}, {512, 8, 4}, {1024, 8, 2}, {1024, 10, 2}, {512, 8, 2}, {1024, 6, 3}};
-        std::vector<Knobs> one = {{512, 16, 2}, {1024, 8, 2}};
+        std::vector<Knobs> sweep = {{16, 3}, {16, 2}, {16, 4}, {12, 4}, {12, 3}, {8, 4}};
+        std::vector<Knobs> one = {{16, 3}, {16, 2}, {12, 4}};
         time_case({"gate/up swiglu 8B", T_Q4_K, 4096, 14336, ME_SWIGLU}, sweep, true);
         time_case({"down 8B Q4_K", T_Q4_K, 14336, 4096, ME_RESIDUAL}, sweep, true);
         time_case({"down 8B Q6_K", T_Q6_K, 14336, 4096, ME_RESIDUAL}, sweep, true);
@@ -825,7 +825,7 @@ int main(int argc, char** argv) {
         time_case({"head 8B Q6_K", T_Q6_K, 4096, 128256, ME_STORE}, one, true);
         time_case({"Q5_K 4096x14336", T_Q5_K, 4096, 14336, ME_STORE}, one, true);
         time_case({"Q8_0 2048x5632", T_Q8_0, 2048, 5632, ME_STORE}, one, true);
-        for (const Knobs& kn : {Knobs{512, 16, 2}, Knobs{1024, 8, 2}, Knobs{512, 12, 3}}) {
+        for (const Knobs& kn : {Knobs{16, 3}, Knobs{16, 2}, Knobs{12, 4}}) {
             time_layer_chain(kn, T_Q4_K, false);
             time_layer_chain(kn, T_Q4_K, true);
             time_layer_chain(kn, T_Q6_K, true);
