@@ -963,6 +963,31 @@ extern "C" int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_ty
     if (da.alloc(k * 4) || dw.alloc(wbytes + 256) || dout.alloc(n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat_q");
     CU(cudaMemcpy(da.p, a, k * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
+    // tensor-pipe kernel when the type/shape is eligible (the path the model uses), else the CUDA-core kernel
+    {
+        cudaDeviceProp prop{};
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaGetDeviceProperties(&prop, dev));
+        MParams m{};
+        m.seg[0].w = dw.as<uint8_t>(); m.seg[0].out = dout.as<float>(); m.seg[0].row_bytes = (long long)row_bytes;
+        m.seg[0].type = t; m.seg[0].n_rows = (int)n;
+        m.n_seg = 1; m.K = (int)k; m.x = da.as<float>(); m.epi = ME_STORE;
+        MPlan plan;
+        const size_t lim = (size_t)prop.sharedMemPerBlockOptin - 6144;
+        DevBuf dpart, dtick;
+        if (env_int("B200_GEMV_MMA", 1) && mma_plan(m, prop.multiProcessorCount, 16, 3, lim, plan)) {
+            const size_t tiles = (n + 15) / 16;
+            if (dpart.alloc((size_t)plan.grid * 2 * 32 * 4) || dtick.alloc(tiles * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat_q");
+            CU(cudaMemset(dtick.p, 0, tiles * 4));
+            m.part = dpart.as<float>(); m.tickets = dtick.as<unsigned int>();
+            CU(mma_set_smem_limit((int)lim));
+            mma_kernel_for(plan.stages)<<<plan.grid, plan.warps * 32, plan.smem>>>(m);
+            if ((rc = op_finish("vec_mat_q"))) return rc;
+            CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+            return B200_OK;
+        }
+    }
     CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     GemvParams p{};
     p.seg[0].w = dw.as<uint8_t>(); p.seg[0].out = dout.as<float>(); p.seg[0].row_bytes = (long long)row_bytes;

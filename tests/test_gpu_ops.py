@@ -42,6 +42,13 @@ def test_dequantize_random_weights_bit_exact_vs_oracle(be, oracle, t):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def gemv_err(got, want, k, w_sigma, x):
+    """max |a-b| over the typical magnitude of an output (sigma_w * |x|_2): a single output can cancel to ~0 (n = 1),
+    which would make max|b| a meaningless denominator.  Never smaller than the plain rel_err denominator."""
+    scale = max(float(np.max(np.abs(want))), w_sigma * float(np.linalg.norm(x)))
+    return float(np.max(np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64)))) / scale
+
+
 # (k, n) shapes: ragged row counts (n % 4 != 0), block counts that do not fill a warp step, the 8B shapes scaled down
 GEMV_SHAPES = [(256, 1), (256, 7), (512, 33), (1024, 130), (4096, 64), (5632, 24), (14336, 9), (2048, 1000)]
 
@@ -54,7 +61,7 @@ def test_vec_mat_q_kquants(be, oracle, t, k, n):
     x = rng.standard_normal(k).astype(np.float32)
     want = oracle.vec_mat_q(t, w, x, n)
     got = be.vec_mat_q(x, w, t, k, n)
-    assert rel_err(got, want) < 1e-5
+    assert gemv_err(got, want, k, 0.05, x) < 1e-5
 
 
 @pytest.mark.parametrize("t", [2, 6, 8, 0, 1])
@@ -65,7 +72,7 @@ def test_vec_mat_q_block32_types(be, oracle, t, k, n):
     x = rng.standard_normal(k).astype(np.float32)
     want = oracle.vec_mat_q(t, w, x, n)
     got = be.vec_mat_q(x, w, t, k, n)
-    assert rel_err(got, want) < 1e-5
+    assert gemv_err(got, want, k, 0.05, x) < 1e-5
 
 
 def test_vec_mat_q_random_byte_blocks(be, oracle):
