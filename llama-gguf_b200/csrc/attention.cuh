@@ -87,6 +87,12 @@ struct AttnParams {
     int kv_len_fixed;      // used when pos == nullptr
     int n_kv, G, max_seq, n_splits;
     float scale;
+    // optional fused RoPE + KV-cache write (per-token megakernel): q | k | v raw from the QKV GEMV (+bias), rotated
+    // here exactly as rope_kv_kernel does; the split that owns position `pos` also writes the cache rows
+    const float* qkv_raw;  // nullptr: q is already rotated, the cache already holds position pos
+    const float* freq;     // [hd/2]
+    float rope_scale;
+    int neox, n_heads;
 };
 
 // KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
@@ -102,29 +108,57 @@ __device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca
     cb = (m2 == -INFINITY) ? 0.0f : expf(m2 - mo);
 }
 
-template <int HD, int GMAX>
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p) {
+// One (kv head, KV split) work item, executed by the NW warps of a CTA.  sm: (2*NW*GMAX + NW*GMAX*HD + GMAX*HD)
+// floats (>= 64*GMAX + GMAX); s_ticket: one shared word.
+template <int HD, int GMAX, int NW>
+__device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, int split, int kv_len, float* sm,
+                                                 unsigned int* s_ticket) {
     constexpr int VEC = HD / 32;  // floats per lane per row
-    extern __shared__ __align__(16) float sm[];
-    float* s_m = sm;                              // [warps][GMAX]
-    float* s_l = sm + kAttnWarps * GMAX;          // [warps][GMAX]
-    float* s_acc = sm + 2 * kAttnWarps * GMAX;    // [warps][GMAX][HD]
-    __shared__ unsigned int s_ticket;
+    constexpr int NT = NW * 32;
+    float* s_m = sm;                      // [warps][GMAX]
+    float* s_l = sm + NW * GMAX;          // [warps][GMAX]
+    float* s_acc = sm + 2 * NW * GMAX;    // [warps][GMAX][HD]
+    float* s_q = s_acc + NW * GMAX * HD;  // [GMAX][HD] (fused RoPE only)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kh = blockIdx.x, split = blockIdx.y;
     const int G = p.G;
-
-    pdl_launch_dependents();
-    pdl_wait();
-
-    const int kv_len = p.pos ? (*p.pos + 1) : p.kv_len_fixed;
     const int ns = attn_eff_splits(kv_len, p.n_splits);
     if (split >= ns) return;
     int chunk = (kv_len + ns - 1) / ns;
-    chunk = (chunk + kAttnWarps - 1) / kAttnWarps * kAttnWarps;
+    chunk = (chunk + NW - 1) / NW * NW;
     const int start = split * chunk;
     const int end = min(kv_len, start + chunk);
+
+    if (p.qkv_raw) {  // Backend::rope (cpu/ops.rs:1216-1337) + cache write (layers.rs:580-600)
+        const int pos = kv_len - 1, half = HD / 2;
+        const float position = (float)pos / p.rope_scale;
+        for (int idx = threadIdx.x; idx < G * half; idx += NT) {
+            const int g = idx / half, pi = idx - g * half;
+            const float theta = position * p.freq[pi];
+            const float c = cosf(theta), sn = sinf(theta);
+            const int i0 = p.neox ? pi : 2 * pi, i1 = p.neox ? pi + half : 2 * pi + 1;
+            const float* d = p.qkv_raw + (size_t)(kh * G + g) * HD;
+            const float x0 = d[i0], x1 = d[i1];
+            s_q[g * HD + i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
+            s_q[g * HD + i1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+        }
+        if (pos >= start && pos < end) {
+            const float* kraw = p.qkv_raw + (size_t)p.n_heads * HD + (size_t)kh * HD;
+            const float* vraw = p.qkv_raw + (size_t)(p.n_heads + p.n_kv) * HD + (size_t)kh * HD;
+            float* ko = const_cast<float*>(p.k_cache) + ((size_t)kh * p.max_seq + pos) * HD;
+            float* vo = const_cast<float*>(p.v_cache) + ((size_t)kh * p.max_seq + pos) * HD;
+            for (int pi = threadIdx.x; pi < half; pi += NT) {
+                const float theta = position * p.freq[pi];
+                const float c = cosf(theta), sn = sinf(theta);
+                const int i0 = p.neox ? pi : 2 * pi, i1 = p.neox ? pi + half : 2 * pi + 1;
+                const float x0 = kraw[i0], x1 = kraw[i1];
+                ko[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
+                ko[i1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+            }
+            for (int d = threadIdx.x; d < HD; d += NT) vo[d] = vraw[d];
+        }
+        __syncthreads();
+    }
 
     float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
 #pragma unroll
@@ -134,18 +168,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
             acc[g][v] = 0.0f;
-            q[g][v] = (g < G) ? p.q[((size_t)(kh * G + g)) * HD + lane * VEC + v] : 0.0f;
+            q[g][v] = (g < G) ? (p.qkv_raw ? s_q[g * HD + lane * VEC + v] : p.q[((size_t)(kh * G + g)) * HD + lane * VEC + v]) : 0.0f;
         }
     }
     const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
     const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
 
     constexpr int UNR = 4;  // positions in flight per warp
-    for (int pos0 = start + warp; pos0 < end; pos0 += kAttnWarps * UNR) {
+    for (int pos0 = start + warp; pos0 < end; pos0 += NW * UNR) {
         float kr[UNR][VEC], vr[UNR][VEC];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            const int pp = pos0 + u * kAttnWarps;
+            const int pp = pos0 + u * NW;
             const int pc = pp < end ? pp : pos0;  // clamp: loads stay in range, result discarded
             if constexpr (VEC == 4) {
                 float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * HD);
@@ -161,7 +195,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            const int pp = pos0 + u * kAttnWarps;
+            const int pp = pos0 + u * NW;
             if (pp < end) {  // warp-uniform
 #pragma unroll
                 for (int g = 0; g < GMAX; g++) {
@@ -198,14 +232,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     __syncthreads();
     const int part_stride = HD + 2;
     float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;  // slots sized for n_splits
-    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {
+    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
         const int g = idx / HD, d = idx - g * HD;
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < kAttnWarps; w++) M = fmaxf(M, s_m[w * GMAX + g]);
+        for (int w = 0; w < NW; w++) M = fmaxf(M, s_m[w * GMAX + g]);
         float L = 0.0f, A = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kAttnWarps; w++) {
+        for (int w = 0; w < NW; w++) {
             const float mw = s_m[w * GMAX + g];
             const float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
             L += s_l[w * GMAX + g] * c;
@@ -221,16 +255,16 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     // ---- last CTA of this kv head merges the splits ----
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[kh], 1u);
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(&p.tickets[kh], 1u);
     __syncthreads();
-    if (s_ticket != (unsigned)(ns - 1)) return;
+    if (*s_ticket != (unsigned)(ns - 1)) return;
     __threadfence();
     const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
     // reuse shared memory: coef[ns][GMAX] and 1/L[GMAX]   (ns <= 64, so <= 64*8+8 floats)
     float* s_coef = sm;
     float* s_linv = sm + 64 * GMAX;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < ns * G; idx += kAttnThreads) {
+    for (int idx = threadIdx.x; idx < ns * G; idx += NT) {
         const int s = idx / G, g = idx - s * G;
         s_coef[s * GMAX + g] = __ldcg(parts + ((size_t)s * G + g) * part_stride + HD);  // m of split s
     }
@@ -249,21 +283,32 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
         s_linv[g] = 1.0f / L;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < G * HD; idx += kAttnThreads) {  // G*HD is a multiple of 256 or smaller: see below
+    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
         const int g = idx / HD, d = idx - g * HD;
         float A = 0.0f;
 #pragma unroll 8
         for (int s = 0; s < ns; s++) A += __ldcg(parts + ((size_t)s * G + g) * part_stride + d) * s_coef[s * GMAX + g];
-        const float o = A * s_linv[g];
-        p.out[(kh * G + g) * HD + d] = o;
+        p.out[(kh * G + g) * HD + d] = A * s_linv[g];
     }
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }
 
-inline size_t attn_smem_bytes(int hd, int gmax) {
-    size_t a = (size_t)(2 * kAttnWarps * gmax + kAttnWarps * gmax * hd), b = (size_t)(64 * gmax + gmax);
-    return (a > b ? a : b) * sizeof(float);
+template <int HD, int GMAX>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ unsigned int s_ticket;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int kv_len = p.pos ? (*p.pos + 1) : p.kv_len_fixed;
+    attn_decode_item<HD, GMAX, kAttnWarps>(p, blockIdx.x, blockIdx.y, kv_len, sm, &s_ticket);
 }
+
+// floats of shared memory attn_decode_item needs
+__host__ __device__ inline size_t attn_item_floats(int hd, int gmax, int nw) {
+    size_t a = (size_t)(2 * nw * gmax + nw * gmax * hd + gmax * hd), b = (size_t)(64 * gmax + gmax);
+    return a > b ? a : b;
+}
+inline size_t attn_smem_bytes(int hd, int gmax) { return attn_item_floats(hd, gmax, kAttnWarps) * sizeof(float); }
 
 // Backend::attention (cpu/ops.rs:1353-1470): causal, q[n_heads][seq][hd], k/v[n_kv][kv_len][hd].
 // Compatibility surface only (the model path uses attention_cached): one warp per (head, query).

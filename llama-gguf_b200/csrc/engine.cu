@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "gemv.cuh"
 #include "gemv_mma.cuh"
+#include "mega.cuh"
 #include "misc.cuh"
 #include "quant.cuh"
 
@@ -92,6 +93,7 @@ struct Slot {
     uint64_t host_pos = 0;
     cudaGraphExec_t graph[MODE_COUNT] = {nullptr, nullptr, nullptr};
     uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
+    MegaPhase* d_phases = nullptr;  // per-token megakernel program of this slot (mega.cuh)
 };
 
 constexpr int kMaxGenerated = 1 << 16;
@@ -120,6 +122,16 @@ struct b200_ctx {
     int mma_warps = 16, mma_stages = 3;
     size_t smem_optin = 227 * 1024;
     uint64_t mma_launches = 0, v1_launches = 0;
+    // per-token megakernel (mega.cuh)
+    bool use_mega = true, mega_ok = false;
+    int mega_phases = 0;
+    size_t mega_smem = 0;
+    unsigned int* mega_bar = nullptr;
+    float* mega_cand_val = nullptr;
+    int* mega_cand_idx = nullptr;
+    float* mega_attn_part = nullptr;
+    int mega_splits = 1;
+    uint64_t mega_launches = 0;
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
@@ -195,6 +207,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_pdl = env_int("B200_PDL", 1) != 0;
     c->use_taps = env_int("B200_TAPS", 0) != 0;
     c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
+    c->use_mega = env_int("B200_MEGA", 1) != 0;
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -261,6 +274,7 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     return B200_OK;
 }
 
+static int mega_build(b200_ctx* c);
 static int check_weight(const DevTensor& t, const char* what, uint64_t k, uint64_t n, int layer) {
     std::string nm = std::string(what) + (layer >= 0 ? " (layer " + std::to_string(layer) + ")" : "");
     if (!t.present()) return fail(B200_ERR_INVALID_ARGUMENT, "missing tensor " + nm);
@@ -378,7 +392,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     CU(mma_set_smem_limit((int)c->smem_optin - 6144));
     CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     c->finalized = true;
-    return B200_OK;
+    return mega_build(c);
 }
 
 extern "C" void b200_ctx_destroy(b200_ctx* c) {
@@ -393,7 +407,12 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         cudaFree(s.d_state);
         cudaFree(s.d_generated);
         cudaFree(s.kv);
+        cudaFree(s.d_phases);
     }
+    cudaFree(c->mega_bar);
+    cudaFree(c->mega_cand_val);
+    cudaFree(c->mega_cand_idx);
+    cudaFree(c->mega_attn_part);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
                     (void*)c->rope_freq, c->flush_buf, (void*)c->mma_part, (void*)c->mma_tickets, (void*)c->mma_err})
@@ -563,8 +582,149 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
     return cudaSuccess;
 }
 
+
+// ------------------------------------------------------------------ per-token megakernel (mega.cuh)
+constexpr int kMegaStages = 2;
+
+// Builds the phase program of every slot.  Leaves mega_ok = false (graph path) when a launch is not eligible:
+// MoE, taps, a weight type/shape the tensor-pipe GEMV does not take, or a shape that does not fit shared memory.
+static int mega_build(b200_ctx* c) {
+    const b200_model_desc& d = c->d;
+    c->mega_ok = false;
+    if (!c->use_mega || !c->use_mma || c->use_taps || d.n_experts > 0) return B200_OK;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->par.device);
+    if (!coop) return B200_OK;
+    const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, G = nh / nkv;
+    const size_t lim = c->smem_optin - 6144;
+    c->mega_splits = (int)std::max(1, std::min(64, c->n_sm / nkv));
+    size_t smem = attn_item_floats(hd, G <= 4 ? 4 : 8, kMmaMaxWarps) * sizeof(float);
+    const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
+    const DevTensor& head = c->output.present() ? c->output : c->token_embd;
+
+    auto gemv_phase = [&](MegaPhase& ph, GemvParams& g) -> bool {
+        MParams m;
+        MPlan plan;
+        const int w = c->mma_warps, st = c->mma_stages;
+        c->mma_warps = kMmaMaxWarps;
+        c->mma_stages = kMegaStages;
+        const bool ok = to_mma_params(c, g, m, plan);
+        c->mma_warps = w;
+        c->mma_stages = st;
+        if (!ok || plan.warps != kMmaMaxWarps || plan.stages != kMegaStages) return false;
+        // every phase runs on the full grid: deal the units to all n_sm * 16 warps (or to as many as there are units)
+        m.total_warps = (int)std::min<long long>((long long)c->n_sm * kMmaMaxWarps, m.total_units);
+        ph = MegaPhase{};
+        ph.kind = PH_GEMV;
+        ph.gemv = m;
+        smem = std::max(smem, plan.smem);
+        return true;
+    };
+
+    if (!c->mega_bar) {
+        CU_ALLOC(cudaMalloc((void**)&c->mega_bar, sizeof(unsigned int)));
+        CU_ALLOC(cudaMalloc((void**)&c->mega_cand_val, c->n_sm * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->mega_cand_idx, c->n_sm * sizeof(int)));
+        CU_ALLOC(cudaMalloc((void**)&c->mega_attn_part, (size_t)nkv * c->mega_splits * G * (hd + 2) * sizeof(float)));
+    }
+    for (size_t si = 0; si < c->slots.size(); si++) {
+        Slot& sl = c->slots[si];
+        std::vector<MegaPhase> prog;
+        for (int l = 0; l < d.n_layers; l++) {
+            Layer& L = c->layers[l];
+            float* kc = sl.kv + (size_t)l * kv_layer;
+            float* vc = kc + kv_layer / 2;
+            MegaPhase ph;
+            {   // RMSNorm + QKV (+bias) -> raw q | k | v
+                GemvParams p{};
+                fill_seg(p.seg[0], L.wq, c->qkv, &L.bq, 0);
+                fill_seg(p.seg[1], L.wk, c->qkv + (size_t)nh * hd, &L.bk, 0);
+                fill_seg(p.seg[2], L.wv, c->qkv + (size_t)(nh + nkv) * hd, &L.bv, 0);
+                p.n_seg = 3; p.K = H; p.x = c->xa; p.norm_w = L.attn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+                if (!gemv_phase(ph, p)) return B200_OK;
+                prog.push_back(ph);
+            }
+            {   // RoPE + KV write + GQA decode attention
+                ph = MegaPhase{};
+                ph.kind = PH_ATTN;
+                AttnParams& ap = ph.attn;
+                ap.q = nullptr; ap.k_cache = kc; ap.v_cache = vc; ap.out = c->attn; ap.part = c->mega_attn_part; ap.tickets = c->tickets;
+                ap.pos = &sl.d_state->pos_cur; ap.kv_len_fixed = 0; ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len;
+                ap.n_splits = c->mega_splits; ap.scale = 1.0f / sqrtf((float)hd);
+                ap.qkv_raw = c->qkv; ap.freq = c->rope_freq; ap.rope_scale = d.rope_scale; ap.neox = d.rope_neox; ap.n_heads = nh;
+                prog.push_back(ph);
+            }
+            {   // O projection + residual: xb = Wo attn + xa
+                GemvParams p{};
+                fill_seg(p.seg[0], L.wo, c->xb, nullptr, 0);
+                p.n_seg = 1; p.K = nh * hd; p.x = c->attn; p.epi = EPI_RESIDUAL; p.residual = c->xa;
+                if (!gemv_phase(ph, p)) return B200_OK;
+                prog.push_back(ph);
+            }
+            {   // RMSNorm + gate | up + SwiGLU
+                GemvParams p{};
+                fill_seg(p.seg[0], L.gate, c->hbuf, nullptr, 0);
+                fill_seg(p.seg[1], L.up, c->hbuf, nullptr, 0);
+                p.n_seg = 2; p.K = H; p.x = c->xb; p.norm_w = L.ffn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_SWIGLU;
+                if (!gemv_phase(ph, p)) return B200_OK;
+                prog.push_back(ph);
+            }
+            {   // down + residual: xa = Wd act + xb
+                GemvParams p{};
+                fill_seg(p.seg[0], L.down, c->xa, nullptr, 0);
+                p.n_seg = 1; p.K = d.ffn; p.x = c->hbuf; p.epi = EPI_RESIDUAL; p.residual = c->xb;
+                if (!gemv_phase(ph, p)) return B200_OK;
+                prog.push_back(ph);
+            }
+        }
+        {   // final RMSNorm + vocab head
+            MegaPhase ph;
+            GemvParams p{};
+            fill_seg(p.seg[0], head, c->logits, nullptr, 0);
+            p.n_seg = 1; p.K = H; p.x = c->xa; p.norm_w = c->output_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+            if (!gemv_phase(ph, p)) return B200_OK;
+            prog.push_back(ph);
+        }
+        if (sl.d_phases) cudaFree(sl.d_phases);
+        CU_ALLOC(cudaMalloc((void**)&sl.d_phases, prog.size() * sizeof(MegaPhase)));
+        CU(cudaMemcpy(sl.d_phases, prog.data(), prog.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+        c->mega_phases = (int)prog.size();
+    }
+    if (smem > lim) return B200_OK;
+    c->mega_smem = smem;
+    CU(cudaFuncSetAttribute(mega_decode_kernel<kMegaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<kMegaStages>, kMmaMaxWarps * 32, smem));
+    if (per_sm < 1) return B200_OK;
+    c->mega_ok = true;
+    return B200_OK;
+}
+
+// One cooperative launch: n_tokens tokens of `slot` (MEGA_GREEDY feeds its own argmax back in).
+static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
+    Slot& sl = c->slots[slot_i];
+    const b200_model_desc& d = c->d;
+    MegaParams mp{};
+    mp.phases = sl.d_phases; mp.n_phases = c->mega_phases; mp.mode = mode; mp.n_tokens = n_tokens;
+    mp.bar = c->mega_bar; mp.err = c->mma_err;
+    mp.embd_type = c->token_embd.type; mp.embd = c->token_embd.d; mp.embd_row_bytes = c->token_embd.row_bytes;
+    mp.hidden = d.hidden; mp.vocab = d.vocab; mp.h = c->xa;
+    mp.st = sl.d_state; mp.logits = c->logits; mp.cand_val = c->mega_cand_val; mp.cand_idx = c->mega_cand_idx;
+    mp.generated = sl.d_generated; mp.max_generated = kMaxGenerated;
+    mp.hd = d.head_dim; mp.G = d.n_heads / d.n_kv_heads;
+    CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
+    void* args[] = {&mp};
+    CU(cudaLaunchCooperativeKernel((void*)mega_decode_kernel<kMegaStages>, dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
+                                   c->mega_smem, c->stream));
+    c->launches += 1;
+    c->mega_launches += 1;
+    return B200_OK;
+}
+
 // Run one token: graph replay when enabled (captured lazily per slot and mode), else eager.
 static int run_token(b200_ctx* c, int slot_i, Mode mode) {
+    if (c->mega_ok)
+        return mega_launch(c, slot_i, mode == MODE_LOGITS ? MEGA_LOGITS : mode == MODE_PREFILL ? MEGA_PREFILL : MEGA_GREEDY, 1);
     Slot& sl = c->slots[slot_i];
     const bool graph = c->use_graph && !c->use_taps;
     if (!graph) {
@@ -714,8 +874,12 @@ extern "C" int b200_decode_greedy(b200_ctx* c, int seq, uint32_t first_token, in
     CU(cudaEventCreate(&e1));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < n_steps; i++)
-        if ((rc = run_token(c, seq, MODE_GREEDY))) return rc;
+    if (c->mega_ok) {
+        if ((rc = mega_launch(c, seq, MEGA_GREEDY, n_steps))) return rc;
+    } else {
+        for (int i = 0; i < n_steps; i++)
+            if ((rc = run_token(c, seq, MODE_GREEDY))) return rc;
+    }
     CU(cudaEventRecord(e1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0.0f;

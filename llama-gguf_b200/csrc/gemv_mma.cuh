@@ -313,23 +313,30 @@ __device__ __forceinline__ float stage_x_split(const XStage& st, const float* __
 // t = lane&3.  They add this unit's contribution for rows g and g+8 to acc0 / acc1 (partial over
 // t: summed when the tile is finished).
 
-__device__ __forceinline__ void k4_scales(const uint4& h, int t, float& dl, float& ml, float& dh, float& mh) {
-    // get_scale_min_k4 (dequant.rs:213-225) for sub-blocks 2t (l) and 2t+1 (h)
+// get_scale_min_k4 (dequant.rs:213-225) for sub-blocks 2t (l) and 2t+1 (h) of a block header h = {d|dmin, scales[12]}.
+// One formula for both halves of the table: sub-blocks 0..3 are 6-bit fields of bytes 0..7, sub-blocks 4..7 take
+// their low 4 bits from bytes 8..11 and their top 2 bits from bits 6,7 of bytes 0..7.
+struct K4Lane {
+    uint32_t sh_lo, sh_w, sh_w4, m_lo, m_w;
+};
+__device__ __forceinline__ K4Lane k4_lane(int t) {
+    K4Lane k;
+    const uint32_t sh = 16u * (uint32_t)(t & 1);
+    k.sh_lo = (t < 2) ? sh : sh + 2u;
+    k.m_lo = (t < 2) ? 0x3F3Fu : 0x3030u;
+    k.m_w = (t < 2) ? 0u : 0x0F0Fu;
+    k.sh_w = sh;
+    k.sh_w4 = sh + 4u;
+    return k;
+}
+__device__ __forceinline__ void k4_scales(const uint4& h, const K4Lane& k, float& dl, float& ml, float& dh, float& mh) {
     const float d = half_bits_to_float(h.x), dmin = half_bits_to_float(h.x >> 16);
-    const int sh = 16 * (t & 1);
-    const uint32_t A = (h.y >> sh) & 0xFFFFu, B = (h.z >> sh) & 0xFFFFu, C = (h.w >> sh) & 0xFFFFu;
-    uint32_t scp, mnp;
-    if (t < 2) {
-        scp = A & 0x3F3Fu;
-        mnp = B & 0x3F3Fu;
-    } else {
-        scp = (C & 0x0F0Fu) | ((A >> 2) & 0x3030u);
-        mnp = ((C >> 4) & 0x0F0Fu) | ((B >> 2) & 0x3030u);
-    }
+    const uint32_t scp = lop3_and_or(h.y >> k.sh_lo, k.m_lo, (h.w >> k.sh_w) & k.m_w);
+    const uint32_t mnp = lop3_and_or(h.z >> k.sh_lo, k.m_lo, (h.w >> k.sh_w4) & k.m_w);
     dl = d * (float)(scp & 0xFFu);
-    dh = d * (float)(scp >> 8);
+    dh = d * (float)((scp >> 8) & 0xFFu);
     ml = dmin * (float)(mnp & 0xFFu);
-    mh = dmin * (float)(mnp >> 8);
+    mh = dmin * (float)((mnp >> 8) & 0xFFu);
 }
 
 // Q4_K / Q5_K (blocks.rs:114-141).  Lane t reads 16 qs bytes per 64-byte half c of the block:
@@ -343,6 +350,7 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
     const uint32_t arr = (g & 1) ? sm.xl : sm.xh;
     const bool lane_act = (((g >> 1) & 1) == (t >> 1));
     const int c_act = g >> 2;
+    const K4Lane kl = k4_lane(t);
     // B-operand base of this lane for each half c: its x elements, or the zero page when its column pair is not addressed
     const uint32_t xo = 2u * (uint32_t)(e0 + 128 * c_act + 64 * (t >> 1) + 16 * (t & 1));
     const uint32_t xb0 = (lane_act && c_act == 0) ? arr + xo : sm.zero, xs0 = (lane_act && c_act == 0) ? 512u : 0u;
@@ -403,8 +411,8 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
         const float sl0 = (t & 2) ? cl[1][0] + cl[1][1] : cl[0][0] + cl[0][1], sl1 = (t & 2) ? cl[1][2] + cl[1][3] : cl[0][2] + cl[0][3];
         const float sh0 = (t & 2) ? ch[1][0] + ch[1][1] : ch[0][0] + ch[0][1], sh1 = (t & 2) ? ch[1][2] + ch[1][3] : ch[0][2] + ch[0][3];
         float dl0, ml0, dh0, mh0, dl1, ml1, dh1, mh1;
-        k4_scales(h0, t, dl0, ml0, dh0, mh0);
-        k4_scales(h1, t, dl1, ml1, dh1, mh1);
+        k4_scales(h0, kl, dl0, ml0, dh0, mh0);
+        k4_scales(h1, kl, dl1, ml1, dh1, mh1);
         const uint32_t xsa = sm.xs + 4u * (uint32_t)((eb >> 4) + 4 * t);
         const float xsl = lds_f32(xsa) + lds_f32(xsa + 4), xsh = lds_f32(xsa + 8) + lds_f32(xsa + 12);
         acc0 += dl0 * sl0 - (1024.0f * dl0 + ml0) * xsl + (dh0 * 0.0625f) * sh0 - (64.0f * dh0 + mh0) * xsh;
@@ -542,19 +550,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 // Position of a warp in its run of units: segment s, 16-row tile, matrix (ME_SWIGLU: 0 = gate, 1 = up; else = s),
 // chunk (256 elements) within the row.  a / b are the true addresses of the unit's bytes in rows tile*16+g and +8.
-// Advanced incrementally: the common step is chunk++ and two pointer bumps, no divisions.
 struct MCursor {
     int s, tile, mat, chunk;
     const uint8_t* a;
     const uint8_t* b;
 };
 
+// The whole GEMV of one launch (or of one phase of the per-token megakernel, mega.cuh) for this CTA.
+//   smem   : dynamic shared memory (x staging + rings), 128-byte aligned
+//   s_red  : [2 * kMmaMaxWarps] floats, s_part: [kMmaMaxWarps][2][32] floats (static shared memory of the caller)
+//   pdl    : the launch is part of a programmatic-dependent-launch chain (griddepcontrol at the right place)
+//   warm_l2: pull the first stages towards L2 before anything that depends on the previous kernel
 template <int STAGES>
-__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ float s_red[2 * kMmaMaxWarps];
-    __shared__ float s_part[kMmaMaxWarps][2][32];   // pieces of tiles shared between warps of this CTA
-
+__device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, float* s_red, float (*s_part)[2][32], bool pdl,
+                                             bool warm_l2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nw = blockDim.x >> 5;
     const int K = p.K;
@@ -587,14 +596,8 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
         if (swiglu && q.chunk >= p.chunks) { q.mat = 1; q.chunk -= p.chunks; }
         cur_ptrs(q);
     };
-    auto cur_step = [&](MCursor& q) {
-        q.chunk++;
-        if (q.chunk < p.chunks) {
-            const int cbytes = p.seg[q.mat].chunk_bytes;
-            q.a += cbytes;
-            q.b += cbytes;
-            return;
-        }
+    // the cursor has just moved past the last chunk of its row: next matrix (SwiGLU up rows) / tile / segment
+    auto cur_wrap = [&](MCursor& q) {
         q.chunk = 0;
         if (swiglu && q.mat == 0) {
             q.mat = 1;
@@ -609,55 +612,79 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
         }
         cur_ptrs(q);
     };
-    // cp.async the 16 rows of the unit at q into ring stage st: lane (g, t) moves the 16-byte pieces t, t+4, ... of
-    // rows g and g+8 (8 rows x 64 contiguous bytes per instruction); sources are aligned down to 16 bytes (doff).
-    // l2_only: just pull the lines towards L2.
-    auto issue = [&](const MCursor& q, int st, bool l2_only) {
-        const MSeg& sg = p.seg[q.mat];
-        const int bytes = min(sg.cb, sg.nb_row - q.chunk * sg.cb) * sg.bb;
-        const uint32_t da = (uint32_t)((uintptr_t)q.a & 15u), db = (uint32_t)((uintptr_t)q.b & 15u);
-        const uint8_t* sa = q.a - da + 16 * t;
-        const uint8_t* sb = q.b - db + 16 * t;
+
+    // ---- producer: cp.async the 16 rows of a unit into a ring stage.  Lane (g, t) moves the 16-byte pieces
+    // t, t+4, ... of rows g and g+8 (8 rows x 64 contiguous bytes per instruction); sources are aligned down to
+    // 16 bytes, the residue (doff) is re-derived by the consumer from the same address. ----
+    MCursor cp{};
+    int p_bytes_full = 0, p_bytes_last = 0, p_cbytes = 0;
+    uint32_t p_dst = 0, p_rs8 = 0;   // this lane's first destination in stage 0, 8 row slots further
+    auto prod_run = [&]() {  // per-run constants of the producer's matrix
+        const MSeg& sg = p.seg[cp.mat];
+        p_bytes_full = sg.chunk_bytes;
+        p_bytes_last = (sg.nb_row - (p.chunks - 1) * sg.cb) * sg.bb;
+        p_cbytes = sg.chunk_bytes;
+        p_dst = ring + (uint32_t)g * sg.row_stride + 16u * t;
+        p_rs8 = 8u * sg.row_stride;
+    };
+    auto issue = [&](uint32_t stage_off, bool l2_only) {
+        const int bytes = (cp.chunk == p.chunks - 1) ? p_bytes_last : p_bytes_full;
+        const uint32_t da = (uint32_t)((uintptr_t)cp.a & 15u), db = (uint32_t)((uintptr_t)cp.b & 15u);
         if (l2_only) {
-            if (t * 128 < (int)da + bytes) prefetch_l2(q.a - da + 128 * t);
-            if (t * 128 < (int)db + bytes) prefetch_l2(q.b - db + 128 * t);
-            return;
-        }
-        const uint32_t dst = ring + (uint32_t)st * p.stage_bytes + (uint32_t)g * sg.row_stride + 16u * t;
-        const uint32_t dstb = dst + 8u * sg.row_stride;
-        const int ea = (int)da + bytes - 16 * t, eb = (int)db + bytes - 16 * t;  // bytes from this lane's first piece to the end
+            if (t * 128 < (int)da + bytes) prefetch_l2(cp.a - da + 128 * t);
+            if (t * 128 < (int)db + bytes) prefetch_l2(cp.b - db + 128 * t);
+        } else {
+            const uint8_t* sa = cp.a - da + 16 * t;
+            const uint8_t* sb = cp.b - db + 16 * t;
+            const uint32_t dst = p_dst + stage_off, dstb = dst + p_rs8;
+            const int ea = (int)da + bytes - 16 * t, eb = (int)db + bytes - 16 * t;  // bytes from this lane's first piece to the end
 #pragma unroll
-        for (int i = 0; i < 5; i++) {  // <= 287 bytes per row and unit
-            if (64 * i < ea) cp_async16(dst + 64 * i, sa + 64 * i);
-            if (64 * i < eb) cp_async16(dstb + 64 * i, sb + 64 * i);
+            for (int i = 0; i < 5; i++) {  // <= 287 bytes per row and unit
+                if (64 * i < ea) cp_async16(dst + 64 * i, sa + 64 * i);
+                if (64 * i < eb) cp_async16(dstb + 64 * i, sb + 64 * i);
+            }
+        }
+        cp.chunk++;
+        if (cp.chunk < p.chunks) {
+            cp.a += p_cbytes;
+            cp.b += p_cbytes;
+        } else {
+            cur_wrap(cp);
+            prod_run();
         }
     };
 
-    MCursor cp{}, cc{};
+    MCursor cc{};
     const int pre = min(STAGES - 1, n_units);
     if (n_units > 0 && !p.expert_sel) {
         // dense weights never depend on a predecessor: pull the first stages towards L2 before the PDL wait
         // (fire-and-forget; an early cp.async would make the x loads below queue behind DRAM-latency copies)
         cur_init(cp, u0);
         cc = cp;
-        MCursor q = cp;
-        for (int k = 0; k < pre; k++) { issue(q, k, true); cur_step(q); }
+        prod_run();
+        if (warm_l2) {
+            for (int k = 0; k < pre; k++) issue(0, true);
+            cp = cc;
+            prod_run();
+        }
     }
 
-    pdl_launch_dependents();
-    pdl_wait();
+    if (pdl) {
+        pdl_launch_dependents();
+        pdl_wait();
+    }
     MMA_STAMP(1);
 
     if (p.expert_sel) {
         eoff = (long long)p.expert_sel[p.expert_slot];
-        if (n_units > 0) { cur_init(cp, u0); cc = cp; }
+        if (n_units > 0) { cur_init(cp, u0); cc = cp; prod_run(); }
     }
     // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
     XStage xst;
     stage_x_load(xst, p.x, p.norm_w, K, s_red);
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
-        if (k < pre) { issue(cp, k, false); cur_step(cp); }
+        if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
         cp_async_commit();
     }
     MMA_STAMP(2);
@@ -696,42 +723,58 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
 
     float ag0 = 0.f, ag1 = 0.f, au0 = 0.f, au1 = 0.f;
     int piece_s[2] = {-1, -1}, piece_tile[2] = {0, 0};  // tiles of which this warp holds only a piece (first / last of its run)
-    int st_c = 0, st_p = (STAGES - 1) % STAGES;
-    for (int k = 0; k < n_units; k++) {
-        if (k + STAGES - 1 < n_units) {
-            issue(cp, st_p, false);
-            cur_step(cp);
-        }
-        st_p = (st_p + 1 == STAGES) ? 0 : st_p + 1;
-        cp_async_commit();
-        cp_async_wait<STAGES - 1>();
-        __syncwarp();
-        if (k == 0) MMA_STAMP(4);
-
+    uint32_t off_c = 0, off_p = (uint32_t)((STAGES - 1) % STAGES) * p.stage_bytes;  // consumer / producer stage offsets
+    const uint32_t ring_bytes = (uint32_t)STAGES * p.stage_bytes;
+    int issued = pre, done = 0;
+    bool first = true;
+    while (done < n_units) {
+        // ---- a run: the consecutive units of this warp inside one row-tile of one matrix ----
+        const int len = min(p.chunks - cc.chunk, n_units - done);
         const MSeg& wsg = p.seg[cc.mat];
         const int type = wsg.type;
-        const int nblk = min(wsg.cb, wsg.nb_row - cc.chunk * wsg.cb);
-        const int e0 = cc.chunk * kMmaChunk;
-        const uint32_t sp = ring + (uint32_t)st_c * p.stage_bytes + smem_token();
         const uint32_t RS = (uint32_t)wsg.row_stride;
-        st_c = (st_c + 1 == STAGES) ? 0 : st_c + 1;
-        float a0 = 0.f, a1 = 0.f;
+        const int cbytes = wsg.chunk_bytes;
+        int e0 = cc.chunk * kMmaChunk;
+        uint32_t ca = (uint32_t)(uintptr_t)cc.a, cb = (uint32_t)(uintptr_t)cc.b;  // low address bits: source misalignment
+        float r0 = 0.f, r1 = 0.f;
+        // one unit: keep the ring full, wait for the oldest stage, consume it
+#define MMA_UNIT(CALL)                                                             \
+    for (int i = 0; i < len; i++) {                                                \
+        if (issued < n_units) { issue(off_p, false); issued++; }                   \
+        off_p = (off_p + p.stage_bytes == ring_bytes) ? 0u : off_p + p.stage_bytes; \
+        cp_async_commit();                                                         \
+        cp_async_wait<STAGES - 1>();                                               \
+        __syncwarp();                                                              \
+        if (first) { MMA_STAMP(4); first = false; }                                \
+        const uint32_t sp = ring + off_c + smem_token();                           \
+        off_c = (off_c + p.stage_bytes == ring_bytes) ? 0u : off_c + p.stage_bytes; \
+        float a0 = 0.f, a1 = 0.f;                                                  \
+        CALL;                                                                      \
+        pin2(a0, a1); /* the unit's shared-memory reads are complete before the stage can be refilled */ \
+        r0 += a0;                                                                  \
+        r1 += a1;                                                                  \
+        e0 += kMmaChunk;                                                           \
+        ca += cbytes;                                                              \
+        cb += cbytes;                                                              \
+        __syncwarp(); /* every lane is done with this stage */                     \
+    }
         switch (type) {
-            case T_Q4_K: unit_k45<false>(sp, RS, 1, e0, sm, g, t, a0, a1); break;
-            case T_Q5_K: unit_k45<true>(sp, RS, 1, e0, sm, g, t, a0, a1); break;
-            case T_Q6_K: unit_q6k(sp, RS, 1, e0, (uint32_t)((uintptr_t)cc.a & 15u), (uint32_t)((uintptr_t)cc.b & 15u), sm, g, t, a0, a1); break;
-            default: unit_q80(sp, RS, nblk, e0, (uint32_t)((uintptr_t)cc.a & 15u), (uint32_t)((uintptr_t)cc.b & 15u), sm, g, t, a0, a1); break;
+            case T_Q4_K: MMA_UNIT(unit_k45<false>(sp, RS, 1, e0, sm, g, t, a0, a1)) break;
+            case T_Q5_K: MMA_UNIT(unit_k45<true>(sp, RS, 1, e0, sm, g, t, a0, a1)) break;
+            case T_Q6_K: MMA_UNIT(unit_q6k(sp, RS, 1, e0, ca & 15u, cb & 15u, sm, g, t, a0, a1)) break;
+            default: MMA_UNIT(unit_q80(sp, RS, min(wsg.cb, wsg.nb_row - (e0 >> 5)), e0, ca & 15u, cb & 15u, sm, g, t, a0, a1)) break;
         }
-        pin2(a0, a1);  // the unit's shared-memory reads are complete before the stage can be refilled
-        if (swiglu && cc.mat == 1) { au0 += a0; au1 += a1; } else { ag0 += a0; ag1 += a1; }
-        __syncwarp();  // every lane is done with this stage
+#undef MMA_UNIT
+        done += len;
+        if (swiglu && cc.mat == 1) { au0 += r0; au1 += r1; } else { ag0 += r0; ag1 += r1; }
 
         // ---- tile finished (for this warp)? ----
         const int s = cc.s, tile = cc.tile;
-        const bool tile_done = (cc.chunk == p.chunks - 1 && (!swiglu || cc.mat == 1)) || (k == n_units - 1);
-        cur_step(cc);
+        const bool row_end = (cc.chunk + len == p.chunks);
+        const bool tile_done = (row_end && (!swiglu || cc.mat == 1)) || (done == n_units);
+        if (row_end) cur_wrap(cc);
         if (!tile_done) continue;
-        if (k == n_units - 1) MMA_STAMP(5);
+        if (done == n_units) MMA_STAMP(5);
 
         // reduce the 4 lanes of a row group, then lane L holds logical row L (0..15 gate/plain, 16..31 up)
         ag0 += __shfl_xor_sync(0xffffffffu, ag0, 1); ag0 += __shfl_xor_sync(0xffffffffu, ag0, 2);
@@ -793,6 +836,44 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const MP
         epilogue(s, tile, v);
     }
     MMA_STAMP(6);
+}
+
+// Pull the first ring stages of launch/phase `p` towards L2 (fire-and-forget): called by the megakernel for the
+// NEXT phase before it waits at a grid barrier, so the weight stream does not stop at the phase boundary.
+template <int STAGES>
+__device__ __forceinline__ void mma_warm_l2(const MParams& p, int depth) {
+    if (p.expert_sel) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nw = blockDim.x >> 5;
+    const long long U = p.total_units, W = p.total_warps;
+    const long long gw = (long long)blockIdx.x * nw + warp;
+    if (gw >= W) return;
+    const int u0 = (int)(gw * U / W), u1 = (int)((gw + 1) * U / W);
+    const bool swiglu = p.epi == ME_SWIGLU;
+    int s = (p.n_seg > 2 && u0 >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && !swiglu && u0 >= p.seg[1].unit0) ? 1 : 0;
+    const int local = u0 - p.seg[s].unit0;
+    const int tile = local / p.units_per_tile;
+    int chunk = local - tile * p.units_per_tile, mat = s;
+    if (swiglu && chunk >= p.chunks) { mat = 1; chunk -= p.chunks; }
+    const MSeg& sg = p.seg[mat];
+    // the run of this warp's first units inside its first row: up to `depth` units, contiguous bytes per row
+    const int n = min(min(depth, u1 - u0), p.chunks - chunk);
+    const long long off = (long long)chunk * sg.chunk_bytes;
+    const int bytes = n * sg.chunk_bytes;
+    const uint8_t* a = sg.w + (long long)min(tile * 16 + g, sg.n_rows - 1) * sg.row_bytes + off;
+    const uint8_t* b = sg.w + (long long)min(tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes + off;
+    for (int o = 128 * t; o < bytes + 127; o += 512) {
+        prefetch_l2(a + o);
+        prefetch_l2(b + o);
+    }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const __grid_constant__ MParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float s_red[2 * kMmaMaxWarps];
+    __shared__ float s_part[kMmaMaxWarps][2][32];   // pieces of tiles shared between warps of this CTA
+    mma_gemv_cta<STAGES>(p, smem, s_red, s_part, true, true);
 }
 
 // ---------------------------------------------------------------- host-side launch planning

@@ -1,0 +1,206 @@
+// mega.cuh — one persistent, cooperative kernel per decoded token (or per run of greedy tokens).
+//
+// The graph path launches ~195 kernels per Llama-3-8B token; in-kernel timelines (profiles/r01_v4_gemv_mma.md)
+// show ~5 us of fixed cost per launch (launch, x staging behind cold loads, merge, exit) against 1.5-10 us of
+// streaming.  Here the token is ONE launch of one CTA per SM; the layer sequence of GpuOnlyInference::forward
+// (src/backend/cuda/gpu_only.rs:849-1010; CPU: model/llama.rs:275-362, layers.rs:1082-1245) becomes a list of
+// phases separated by grid barriers:
+//
+//   embed -> L x { QKV GEMV | RoPE + KV write + GQA attention | O GEMV + residual |
+//                  gate/up GEMV + SwiGLU | down GEMV + residual } -> vocab-head GEMV [-> argmax -> next token]
+//
+// GEMV phases are mma_gemv_cta (gemv_mma.cuh) with its arguments read from a per-phase descriptor in global
+// memory; before a CTA waits at a barrier it pulls the first units of the NEXT GEMV towards L2, so the weight
+// stream does not stop at a phase boundary.  RoPE and the KV write are folded into the attention phase
+// (attention.cuh: attn_decode_item with qkv_raw), which removes two launches per layer.
+//
+// Dense models whose every weight launch is eligible for the tensor-pipe GEMV take this path (engine.cu:
+// mega_build); MoE models and the 32-element block types stay on the CUDA-graph path.
+#pragma once
+#include "attention.cuh"
+#include "gemv_mma.cuh"
+#include "misc.cuh"
+
+namespace b200 {
+
+enum : int { PH_GEMV = 0, PH_ATTN = 1 };
+enum : int { MEGA_LOGITS = 0, MEGA_PREFILL = 1, MEGA_GREEDY = 2 };
+
+struct MegaPhase {
+    int kind;
+    int pad[3];
+    MParams gemv;
+    AttnParams attn;
+};
+
+struct MegaParams {
+    const MegaPhase* phases;  // device array: 5 per layer, then the vocab head (last)
+    int n_phases;
+    int mode;
+    int n_tokens;             // tokens processed by this launch (MEGA_GREEDY: argmax feeds the next one)
+    unsigned int* bar;        // grid-barrier counter, zeroed by the host before every launch
+    int* err;                 // watchdog flag (2 = a grid barrier timed out)
+    // embedding row -> residual stream
+    int embd_type;
+    const uint8_t* embd;
+    long long embd_row_bytes;
+    int hidden, vocab;
+    float* h;
+    // sampling state
+    SeqState* st;
+    const float* logits;
+    float* cand_val;          // [grid] per-CTA argmax candidates
+    int* cand_idx;
+    int* generated;
+    int max_generated;
+    int hd, G;
+};
+
+// Arrive + wait on a monotonically increasing counter.  Release/acquire at gpu scope: everything the CTA wrote
+// before the barrier is visible to every CTA after it.  Bounded spin: a lost CTA must never hang the box.
+__device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& target, int* err, int* s_flag) {
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned int v = 0;
+        int ok = 1;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 3000000000LL) {  // ~1.5 s
+                ok = 0;
+                atomicExch(err, 2);
+                break;
+            }
+        }
+        *s_flag = ok;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const __grid_constant__ MegaParams mp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float s_red[2 * kMmaMaxWarps];
+    __shared__ float s_part[kMmaMaxWarps][2][32];
+    __shared__ unsigned int s_ticket;
+    __shared__ int s_flag;
+    __shared__ __align__(16) MegaPhase s_ph;
+    __shared__ float s_av[kMmaMaxWarps];
+    __shared__ int s_ai[kMmaMaxWarps];
+
+    constexpr int NW = kMmaMaxWarps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int target = 0;
+    const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;  // prefill: no vocab head
+
+    for (int tok = 0; tok < mp.n_tokens; tok++) {
+        // ---- embedding (LlamaModel::forward, model/llama.rs:293-306): CTA 0 dequantises row `token`, bit-exactly ----
+        if (blockIdx.x == 0) {
+            int token = mp.st->token;
+            token = min(max(token, 0), mp.vocab - 1);
+            const int be = type_block_elems(mp.embd_type), bb = type_block_bytes(mp.embd_type);
+            const uint8_t* row = mp.embd + (long long)token * mp.embd_row_bytes;
+            for (int i = tid; i < mp.hidden; i += NW * 32) {
+                const int blk = i / be;
+                mp.h[i] = dequant_elem(mp.embd_type, row + (long long)blk * bb, i - blk * be);
+            }
+            if (tid == 0) {
+                const int pn = mp.st->pos_next;
+                mp.st->pos_cur = pn;
+                mp.st->pos_next = pn + 1;
+            }
+        }
+        if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+
+        for (int ph = 0; ph < n_run; ph++) {
+            // phase descriptor -> shared memory
+            {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.phases + ph);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ph);
+                for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += NW * 32) dst[i] = src[i];
+            }
+            __syncthreads();
+            if (s_ph.kind == PH_GEMV) {
+                mma_gemv_cta<STAGES>(s_ph.gemv, smem, s_red, s_part, false, false);
+            } else {
+                const AttnParams& ap = s_ph.attn;
+                const int kv_len = *ap.pos + 1;
+                const int n_items = ap.n_kv * ap.n_splits;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    const int kh = item / ap.n_splits, split = item - kh * ap.n_splits;
+                    float* sm = reinterpret_cast<float*>(smem);
+                    if (mp.hd == 128) {
+                        if (mp.G <= 4) attn_decode_item<128, 4, NW>(ap, kh, split, kv_len, sm, &s_ticket);
+                        else attn_decode_item<128, 8, NW>(ap, kh, split, kv_len, sm, &s_ticket);
+                    } else {
+                        if (mp.G <= 4) attn_decode_item<64, 4, NW>(ap, kh, split, kv_len, sm, &s_ticket);
+                        else attn_decode_item<64, 8, NW>(ap, kh, split, kv_len, sm, &s_ticket);
+                    }
+                    __syncthreads();
+                }
+            }
+            // keep HBM busy across the barrier: the first units of the next GEMV go towards L2 now
+            if (ph + 1 < n_run && mp.phases[ph + 1].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 1].gemv, 4);
+            else if (ph + 2 < n_run && mp.phases[ph + 2].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 2].gemv, 4);
+            if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+        }
+
+        if (mp.mode != MEGA_GREEDY) continue;
+        // ---- greedy pick on the device: raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821) ----
+        {
+            const int per = (mp.vocab + gridDim.x - 1) / gridDim.x;
+            const int lo = blockIdx.x * per, hi = min(mp.vocab, lo + per);
+            float best = -INFINITY;
+            int bi = -1;
+            for (int i = lo + tid; i < hi; i += NW * 32) {
+                const float v = mp.logits[i];
+                if (v >= best || bi < 0) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_av[warp] = best; s_ai[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < NW; w++)
+                    if (s_ai[w] >= 0 && (bi < 0 || s_av[w] > best || (s_av[w] == best && s_ai[w] > bi))) { best = s_av[w]; bi = s_ai[w]; }
+                mp.cand_val[blockIdx.x] = best;
+                mp.cand_idx[blockIdx.x] = bi;
+            }
+        }
+        if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+        if (blockIdx.x == 0) {
+            if (warp == 0) {
+                float best = -INFINITY;
+                int bi = -1;
+                for (int c = lane; c < (int)gridDim.x; c += 32) {
+                    const float v = mp.cand_val[c];
+                    const int i = mp.cand_idx[c];
+                    if (i >= 0 && (bi < 0 || v > best || (v == best && i > bi))) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                }
+                if (lane == 0) {
+                    mp.st->token = bi;
+                    const int gcount = mp.st->n_generated;
+                    if (gcount < mp.max_generated) mp.generated[gcount] = bi;
+                    mp.st->n_generated = gcount + 1;
+                }
+            }
+            __syncthreads();  // CTA 0 embeds the new token at the top of the loop: it must see st->token
+        }
+    }
+}
+
+}  // namespace b200
