@@ -106,6 +106,8 @@ def lib():
     L.b200_decode_greedy.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), fp]
     L.b200_get_hidden.argtypes = [vp, C.c_int, C.c_int, fp]
     L.b200_ctx_stats.argtypes = [vp, u64p, u64p, u64p]
+    L.b200_debug_mega_timeline.argtypes = [vp, u64p, C.c_int]
+    L.b200_debug_mega_phase.argtypes = [vp, C.c_int, u64p, C.c_int]
     L.b200_bench_weight_gemv.argtypes = [vp, C.c_char_p, C.c_int, fp, u64p]
     L.b200_bench_gemv_pass.argtypes = [vp, C.c_int, C.c_int, fp, u64p, u64p]
     L.b200_op_add.argtypes = [fp, fp, fp, C.c_size_t]

@@ -96,7 +96,7 @@ struct AttnParams {
 };
 
 // KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
-constexpr int kAttnMinChunk = 256;
+constexpr int kAttnMinChunk = 64;
 __device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits) {
     return max(1, min(n_splits, (kv_len + kAttnMinChunk - 1) / kAttnMinChunk));
 }

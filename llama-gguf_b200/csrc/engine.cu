@@ -132,6 +132,7 @@ struct b200_ctx {
     float* mega_attn_part = nullptr;
     int mega_splits = 1;
     uint64_t mega_launches = 0;
+    unsigned long long* mega_dbg = nullptr;
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
@@ -712,6 +713,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
     mp.st = sl.d_state; mp.logits = c->logits; mp.cand_val = c->mega_cand_val; mp.cand_idx = c->mega_cand_idx;
     mp.generated = sl.d_generated; mp.max_generated = kMaxGenerated;
     mp.hd = d.head_dim; mp.G = d.n_heads / d.n_kv_heads;
+    mp.dbg = c->mega_dbg;
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
     void* args[] = {&mp};
     CU(cudaLaunchCooperativeKernel((void*)mega_decode_kernel<kMegaStages>, dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
@@ -901,6 +903,47 @@ extern "C" int b200_get_hidden(b200_ctx* c, int seq, int layer, float* out) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy(out, c->taps + (size_t)layer * c->d.hidden, (size_t)c->d.hidden * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
+}
+
+// Debug: globaltimer stamps (ns) of CTA 0 after the embedding barrier and after every phase barrier of the last
+// token run by the megakernel.  First call arms the stamps; returns the number of values written to out.
+extern "C" int b200_debug_mega_timeline(b200_ctx* c, unsigned long long* out, int max_n) {
+    if (!c || !c->mega_ok) return 0;
+    cudaSetDevice(c->par.device);
+    const int n = c->mega_phases + 1;
+    if (!c->mega_dbg) {
+        if (cudaMalloc((void**)&c->mega_dbg, (size_t)(n + 2) * 8) != cudaSuccess) return 0;
+        cudaMemset(c->mega_dbg, 0, (size_t)(n + 2) * 8);
+        return 0;
+    }
+    cudaStreamSynchronize(c->stream);
+    const int m = std::min(n, max_n);
+    if (out) cudaMemcpy(out, c->mega_dbg, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    return m;
+}
+
+// Debug: per-warp globaltimer stamps (gemv_mma.cuh MMA_STAMP) of one GEMV phase of slot 0's megakernel program.
+// phase >= 0 arms (patches the phase descriptor); phase < 0 fetches grid*16*8 values into out.
+extern "C" int b200_debug_mega_phase(b200_ctx* c, int phase, unsigned long long* out, int max_n) {
+    if (!c || !c->mega_ok) return 0;
+    cudaSetDevice(c->par.device);
+    static unsigned long long* buf = nullptr;
+    const size_t n = (size_t)c->n_sm * kMmaMaxWarps * 8;
+    if (!buf && cudaMalloc((void**)&buf, n * 8) != cudaSuccess) return 0;
+    cudaStreamSynchronize(c->stream);
+    if (phase >= 0) {
+        if (phase >= c->mega_phases) return 0;
+        cudaMemset(buf, 0, n * 8);
+        MegaPhase ph;
+        cudaMemcpy(&ph, c->slots[0].d_phases + phase, sizeof ph, cudaMemcpyDeviceToHost);
+        if (ph.kind != PH_GEMV) return 0;
+        ph.gemv.dbg = buf;
+        cudaMemcpy(c->slots[0].d_phases + phase, &ph, sizeof ph, cudaMemcpyHostToDevice);
+        return 1;
+    }
+    const int m = (int)std::min<size_t>(n, (size_t)max_n);
+    if (out) cudaMemcpy(out, buf, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    return m;
 }
 
 extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos) {

@@ -192,7 +192,26 @@ __device__ __forceinline__ uint32_t lds32_a2(uint32_t a) {
     return __funnelshift_r(lds32(base), lds32(base + 4), sh);
 }
 
-constexpr uint32_t kMagic = 0x64006400u;  // half2(1024, 1024)
+// Quants as fp16 operands.  MMA_SUBNORMAL = 1 (default): the integer q sits in the low mantissa bits of an fp16
+// with a zero exponent field, i.e. it IS the subnormal q * 2^-24 -- no offset, so nothing cancels in the f32
+// accumulator; the 2^24 is folded into the final scale and into the staged sums of x.  MMA_SUBNORMAL = 0: the
+// classic magic-number form 1024 + q (0x6400 | q), whose 1024 * sum(x) has to be subtracted again (costs ~7 bits).
+#ifndef MMA_SUBNORMAL
+#define MMA_SUBNORMAL 1
+#endif
+#if MMA_SUBNORMAL
+constexpr uint32_t kMagic = 0u;
+constexpr uint32_t kMagicB = 0u;             // PRMT filler byte
+constexpr float kOff = 0.0f;                 // offset carried by every operand
+constexpr float kXsScale = 5.9604644775390625e-08f;   // 2^-24: staged sums of x are kept in operand units
+constexpr float kUnscale = 16777216.0f;      // 2^24
+#else
+constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
+constexpr uint32_t kMagicB = kMagicB;
+constexpr float kOff = 1024.0f;
+constexpr float kXsScale = 1.0f;
+constexpr float kUnscale = 1.0f;
+#endif
 
 // ---------------------------------------------------------------- x in shared memory
 // fp16 hi and lo parts (x ~= hi + lo), stored so that the 4 elements starting at e (e % 4 == 0)
@@ -273,7 +292,7 @@ __device__ __forceinline__ void split_store4(float4 v, int e, const float* __res
                 ((__half2float(h2) + __half2float(l2)) + (__half2float(h3) + __half2float(l3)));
     sum += __shfl_xor_sync(mask, sum, 1);
     sum += __shfl_xor_sync(mask, sum, 2);
-    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum;
+    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum * kXsScale;
 }
 __device__ __forceinline__ float stage_x_split(const XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w,
                                               float eps, int K, uint8_t* smem, float* red /*[2 * kMmaMaxWarps]*/) {
@@ -292,7 +311,7 @@ __device__ __forceinline__ float stage_x_split(const XStage& st, const float* __
         frexpf(amax, &ex);            // amax = m * 2^ex, m in [0.5, 1)
         k = min(max(12 - ex, -100), 100);
     }
-    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23);
+    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23) * kUnscale;
     __half* xh = reinterpret_cast<__half*>(smem);
     __half* xl = reinterpret_cast<__half*>(smem + (size_t)2 * K + kXlPad);
     float* xs = reinterpret_cast<float*>(smem + (size_t)4 * K + kXlPad);
@@ -415,8 +434,8 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
         k4_scales(h1, kl, dl1, ml1, dh1, mh1);
         const uint32_t xsa = sm.xs + 4u * (uint32_t)((eb >> 4) + 4 * t);
         const float xsl = lds_f32(xsa) + lds_f32(xsa + 4), xsh = lds_f32(xsa + 8) + lds_f32(xsa + 12);
-        acc0 += dl0 * sl0 - (1024.0f * dl0 + ml0) * xsl + (dh0 * 0.0625f) * sh0 - (64.0f * dh0 + mh0) * xsh;
-        acc1 += dl1 * sl1 - (1024.0f * dl1 + ml1) * xsl + (dh1 * 0.0625f) * sh1 - (64.0f * dh1 + mh1) * xsh;
+        acc0 += dl0 * sl0 - (kOff * dl0 + ml0) * xsl + (dh0 * 0.0625f) * sh0 - (kOff * 0.0625f * dh0 + mh0) * xsh;
+        acc1 += dl1 * sl1 - (kOff * dl1 + ml1) * xsl + (dh1 * 0.0625f) * sh1 - (kOff * 0.0625f * dh1 + mh1) * xsh;
     }
 }
 
@@ -458,10 +477,10 @@ __device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, int nblk, int
                 const uint32_t hi1 = lop3_and_or(L1[i] >> 4, 0x0F0F0F0Fu, (H1[i] >> s_hi) & 0x30303030u);
                 const uint32_t blx = (i & 1) ? bl[i >> 1].z : bl[i >> 1].x, bly = (i & 1) ? bl[i >> 1].w : bl[i >> 1].y;
                 const uint32_t bhx = (i & 1) ? bh[i >> 1].z : bh[i >> 1].x, bhy = (i & 1) ? bh[i >> 1].w : bh[i >> 1].y;
-                mma16816(C[2 * n], __byte_perm(lo0, 0x64646464u, 0x4240), __byte_perm(lo1, 0x64646464u, 0x4240),
-                         __byte_perm(lo0, 0x64646464u, 0x4341), __byte_perm(lo1, 0x64646464u, 0x4341), blx, bly);
-                mma16816(C[2 * n + 1], __byte_perm(hi0, 0x64646464u, 0x4240), __byte_perm(hi1, 0x64646464u, 0x4240),
-                         __byte_perm(hi0, 0x64646464u, 0x4341), __byte_perm(hi1, 0x64646464u, 0x4341), bhx, bhy);
+                mma16816(C[2 * n], __byte_perm(lo0, kMagicB, 0x4240), __byte_perm(lo1, kMagicB, 0x4240),
+                         __byte_perm(lo0, kMagicB, 0x4341), __byte_perm(lo1, kMagicB, 0x4341), blx, bly);
+                mma16816(C[2 * n + 1], __byte_perm(hi0, kMagicB, 0x4240), __byte_perm(hi1, kMagicB, 0x4240),
+                         __byte_perm(hi0, kMagicB, 0x4341), __byte_perm(hi1, kMagicB, 0x4341), bhx, bhy);
             }
         }
         const float d0 = half_bits_to_float(lds16(r0 + 208)), d1 = half_bits_to_float(lds16(r1 + 208));
@@ -470,8 +489,8 @@ __device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, int nblk, int
             const int si = 4 * m + t;
             const float xs = lds_f32(sm.xs + 4u * (uint32_t)((eb >> 4) + si));
             const float s0 = (float)lds_s8(r0 + 192 + si), s1 = (float)lds_s8(r1 + 192 + si);
-            acc0 += (d0 * s0) * ((C[m][0] + C[m][1]) - 1056.0f * xs);   // 1024 (fp16 magic) + 32 (Q6_K offset)
-            acc1 += (d1 * s1) * ((C[m][2] + C[m][3]) - 1056.0f * xs);
+            acc0 += (d0 * s0) * ((C[m][0] + C[m][1]) - (kOff + 32.0f) * xs);   // operand offset + Q6_K's 32
+            acc1 += (d1 * s1) * ((C[m][2] + C[m][3]) - (kOff + 32.0f) * xs);
         }
     }
 }
@@ -496,8 +515,8 @@ __device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int
                     const uint32_t w0 = lds32_a2(r0 + 16 * m + 4 * t) ^ 0x80808080u;  // int8 -> biased uint8
                     const uint32_t w1 = lds32_a2(r1 + 16 * m + 4 * t) ^ 0x80808080u;
                     const uint2 bf = lds64(act ? arr + 2u * (uint32_t)(e0 + 32 * b + 16 * m + 4 * t) : sm.zero);
-                    mma16816(C, __byte_perm(w0, 0x64646464u, 0x4240), __byte_perm(w1, 0x64646464u, 0x4240),
-                             __byte_perm(w0, 0x64646464u, 0x4341), __byte_perm(w1, 0x64646464u, 0x4341), bf.x, bf.y);
+                    mma16816(C, __byte_perm(w0, kMagicB, 0x4240), __byte_perm(w1, kMagicB, 0x4240),
+                             __byte_perm(w0, kMagicB, 0x4341), __byte_perm(w1, kMagicB, 0x4341), bf.x, bf.y);
                 }
             }
         }
@@ -505,8 +524,8 @@ __device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int
         if (b < nblk) {
             const uint32_t xa = sm.xs + 4u * (uint32_t)(((e0 + 32 * b) >> 4));
             const float xs = lds_f32(xa) + lds_f32(xa + 4);
-            acc0 += half_bits_to_float(lds16(row0 + b * 34)) * ((C[0] + C[1]) - 1152.0f * xs);  // 1024 + 128
-            acc1 += half_bits_to_float(lds16(row1 + b * 34)) * ((C[2] + C[3]) - 1152.0f * xs);
+            acc0 += half_bits_to_float(lds16(row0 + b * 34)) * ((C[0] + C[1]) - (kOff + 128.0f) * xs);  // operand offset + int8 bias
+            acc1 += half_bits_to_float(lds16(row1 + b * 34)) * ((C[2] + C[3]) - (kOff + 128.0f) * xs);
         }
     }
 }

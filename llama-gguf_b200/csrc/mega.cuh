@@ -54,6 +54,7 @@ struct MegaParams {
     int* generated;
     int max_generated;
     int hd, G;
+    unsigned long long* dbg;  // optional [n_phases + 3] globaltimer stamps of CTA 0 for the LAST token of the launch
 };
 
 // Arrive + wait on a monotonically increasing counter.  Release/acquire at gpu scope: everything the CTA wrote
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
             }
         }
         if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+        if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[0] = gtimer();
 
         for (int ph = 0; ph < n_run; ph++) {
             // phase descriptor -> shared memory
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
             if (ph + 1 < n_run && mp.phases[ph + 1].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 1].gemv, 4);
             else if (ph + 2 < n_run && mp.phases[ph + 2].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 2].gemv, 4);
             if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+            if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[1 + ph] = gtimer();
         }
 
         if (mp.mode != MEGA_GREEDY) continue;
