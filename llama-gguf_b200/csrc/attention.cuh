@@ -245,50 +245,46 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             L += s_l[w * GMAX + g] * c;
             A += s_acc[(w * GMAX + g) * HD + d] * c;
         }
-        my_part[g * part_stride + d] = A;
-        if (d == 0) {
-            my_part[g * part_stride + HD] = M;
-            my_part[g * part_stride + HD + 1] = L;
+        if (ns == 1) {  // a single split: this is the answer (no scratch, no ticket)
+            p.out[(kh * G + g) * HD + d] = A / L;
+        } else {
+            my_part[g * part_stride + d] = A;
+            if (d == 0) {
+                my_part[g * part_stride + HD] = M;
+                my_part[g * part_stride + HD + 1] = L;
+            }
         }
     }
+    if (ns == 1) return;
 
     // ---- last CTA of this kv head merges the splits ----
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) *s_ticket = atomicAdd(&p.tickets[kh], 1u);
+    if (threadIdx.x == 0) {  // release: this CTA's partials are visible; acquire: so are the others'
+        unsigned int t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.tickets + kh) : "memory");
+        *s_ticket = t;
+    }
     __syncthreads();
     if (*s_ticket != (unsigned)(ns - 1)) return;
-    __threadfence();
+    // all partials of this kv head -> shared memory in one round trip, then merge from there
     const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
-    // reuse shared memory: coef[ns][GMAX] and 1/L[GMAX]   (ns <= 64, so <= 64*8+8 floats)
-    float* s_coef = sm;
-    float* s_linv = sm + 64 * GMAX;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < ns * G; idx += NT) {
-        const int s = idx / G, g = idx - s * G;
-        s_coef[s * GMAX + g] = __ldcg(parts + ((size_t)s * G + g) * part_stride + HD);  // m of split s
-    }
-    __syncthreads();
-    if (threadIdx.x < G) {
-        const int g = threadIdx.x;
-        float M = -INFINITY;
-        for (int s = 0; s < ns; s++) M = fmaxf(M, s_coef[s * GMAX + g]);
-        float L = 0.0f;
-        for (int s = 0; s < ns; s++) {
-            const float ms = s_coef[s * GMAX + g];
-            const float c = (ms == -INFINITY) ? 0.0f : expf(ms - M);
-            s_coef[s * GMAX + g] = c;
-            L += __ldcg(parts + ((size_t)s * G + g) * part_stride + HD + 1) * c;
-        }
-        s_linv[g] = 1.0f / L;
-    }
+    const int n_part = ns * G * part_stride;     // contiguous: splits 0..ns-1 of this head
+    float* s_p = sm;                             // [ns][G][HD + 2]   (fits: ns <= NW * GMAX * HD / (G * (HD+2)) is checked by the host)
+    for (int i = threadIdx.x; i < n_part; i += NT) s_p[i] = __ldcg(parts + i);
     __syncthreads();
     for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
         const int g = idx / HD, d = idx - g * HD;
-        float A = 0.0f;
-#pragma unroll 8
-        for (int s = 0; s < ns; s++) A += __ldcg(parts + ((size_t)s * G + g) * part_stride + d) * s_coef[s * GMAX + g];
-        p.out[(kh * G + g) * HD + d] = A * s_linv[g];
+        float M = -INFINITY;
+        for (int s = 0; s < ns; s++) M = fmaxf(M, s_p[(s * G + g) * part_stride + HD]);
+        float L = 0.0f, A = 0.0f;
+        for (int s = 0; s < ns; s++) {
+            const float* ps = s_p + (s * G + g) * part_stride;
+            const float ms = ps[HD];
+            const float c = (ms == -INFINITY) ? 0.0f : expf(ms - M);
+            L += ps[HD + 1] * c;
+            A += ps[d] * c;
+        }
+        p.out[(kh * G + g) * HD + d] = A / L;
     }
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }
@@ -304,11 +300,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
 }
 
 // floats of shared memory attn_decode_item needs
-__host__ __device__ inline size_t attn_item_floats(int hd, int gmax, int nw) {
-    size_t a = (size_t)(2 * nw * gmax + nw * gmax * hd + gmax * hd), b = (size_t)(64 * gmax + gmax);
+__host__ __device__ inline size_t attn_item_floats(int hd, int gmax, int nw, int n_splits, int G) {
+    size_t a = (size_t)(2 * nw * gmax + nw * gmax * hd + gmax * hd), b = (size_t)n_splits * G * (hd + 2);
     return a > b ? a : b;
 }
-inline size_t attn_smem_bytes(int hd, int gmax) { return attn_item_floats(hd, gmax, kAttnWarps) * sizeof(float); }
+inline size_t attn_smem_bytes(int hd, int gmax, int n_splits, int G) { return attn_item_floats(hd, gmax, kAttnWarps, n_splits, G) * sizeof(float); }
 
 // Backend::attention (cpu/ops.rs:1353-1470): causal, q[n_heads][seq][hd], k/v[n_kv][kv_len][hd].
 // Compatibility surface only (the model path uses attention_cached): one warp per (head, query).

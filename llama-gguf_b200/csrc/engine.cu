@@ -390,8 +390,14 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     }
     // kernels that may need more than 48 KB of dynamic shared memory
     CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CU(mma_set_smem_limit((int)c->smem_optin - 6144));
-    CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(mma_set_smem_limit((int)c->smem_optin - 8192));
+    {
+        const int lim_attn = (int)c->smem_optin - 1024;
+        CU(cudaFuncSetAttribute(attn_decode_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+    }
     c->finalized = true;
     return mega_build(c);
 }
@@ -448,7 +454,7 @@ static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& p
     m.epi = p.epi == EPI_STORE ? ME_STORE : p.epi == EPI_RESIDUAL ? ME_RESIDUAL : p.epi == EPI_SWIGLU ? ME_SWIGLU : ME_SCALED_ACC;
     m.expert_sel = p.expert_sel; m.expert_wt = p.expert_wt; m.expert_slot = p.expert_slot;
     m.part = c->mma_part; m.tickets = c->mma_tickets; m.err = c->mma_err;
-    if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, c->smem_optin - 6144, plan)) return false;
+    if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, c->smem_optin - 8192, plan)) return false;
     int tiles = 0;
     for (int s = 0; s < m.n_seg; s++) tiles += m.seg[s].n_tiles;
     return tiles <= c->mma_tickets_n;
@@ -480,11 +486,11 @@ static cudaError_t launch_gemv(b200_ctx* c, GemvParams& p) {
 static cudaError_t launch_attn(b200_ctx* c, const AttnParams& ap, int hd, int G) {
     dim3 grid(ap.n_kv, ap.n_splits);
     if (hd == 128) {
-        if (G <= 4) return launch_k(c, attn_decode_kernel<128, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 4), ap);
-        return launch_k(c, attn_decode_kernel<128, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 8), ap);
+        if (G <= 4) return launch_k(c, attn_decode_kernel<128, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 4, ap.n_splits, ap.G), ap);
+        return launch_k(c, attn_decode_kernel<128, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(128, 8, ap.n_splits, ap.G), ap);
     }
-    if (G <= 4) return launch_k(c, attn_decode_kernel<64, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 4), ap);
-    return launch_k(c, attn_decode_kernel<64, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 8), ap);
+    if (G <= 4) return launch_k(c, attn_decode_kernel<64, 4>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 4, ap.n_splits, ap.G), ap);
+    return launch_k(c, attn_decode_kernel<64, 8>, grid, dim3(kAttnThreads), attn_smem_bytes(64, 8, ap.n_splits, ap.G), ap);
 }
 
 // Enqueue every kernel of one token for `slot` on c->stream (captured into a graph by the caller).
@@ -597,9 +603,9 @@ static int mega_build(b200_ctx* c) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->par.device);
     if (!coop) return B200_OK;
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, G = nh / nkv;
-    const size_t lim = c->smem_optin - 6144;
+    const size_t lim = c->smem_optin - 8192;
     c->mega_splits = (int)std::max(1, std::min(64, c->n_sm / nkv));
-    size_t smem = attn_item_floats(hd, G <= 4 ? 4 : 8, kMmaMaxWarps) * sizeof(float);
+    size_t smem = attn_item_floats(hd, G <= 4 ? 4 : 8, kMmaMaxWarps, c->mega_splits, G) * sizeof(float);
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
     const DevTensor& head = c->output.present() ? c->output : c->token_embd;
 
@@ -613,8 +619,7 @@ static int mega_build(b200_ctx* c) {
         c->mma_warps = w;
         c->mma_stages = st;
         if (!ok || plan.warps != kMmaMaxWarps || plan.stages != kMegaStages) return false;
-        // every phase runs on the full grid: deal the units to all n_sm * 16 warps (or to as many as there are units)
-        m.total_warps = (int)std::min<long long>((long long)c->n_sm * kMmaMaxWarps, m.total_units);
+        mma_deal(m, c->n_sm);  // every phase runs on the full grid of the megakernel
         ph = MegaPhase{};
         ph.kind = PH_GEMV;
         ph.gemv = m;
@@ -1181,7 +1186,7 @@ extern "C" int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_ty
         m.seg[0].type = t; m.seg[0].n_rows = (int)n;
         m.n_seg = 1; m.K = (int)k; m.x = da.as<float>(); m.epi = ME_STORE;
         MPlan plan;
-        const size_t lim = (size_t)prop.sharedMemPerBlockOptin - 6144;
+        const size_t lim = (size_t)prop.sharedMemPerBlockOptin - 8192;
         DevBuf dpart, dtick;
         if (env_int("B200_GEMV_MMA", 1) && mma_plan(m, prop.multiProcessorCount, 16, 3, lim, plan)) {
             const size_t tiles = (n + 15) / 16;
@@ -1280,13 +1285,23 @@ extern "C" int b200_op_attention_cached(const float* q, const float* k_cache, co
     ap.part = dpart.as<float>(); ap.tickets = dtick.as<unsigned int>(); ap.pos = nullptr; ap.kv_len_fixed = kv_len;
     ap.n_kv = n_kv_heads; ap.G = G; ap.max_seq = max_seq; ap.n_splits = n_splits; ap.scale = scale;
     dim3 grid(n_kv_heads, n_splits);
-    CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    {
+        cudaDeviceProp prop{};
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaGetDeviceProperties(&prop, dev));
+        const int lim_attn = (int)prop.sharedMemPerBlockOptin - 1024;
+        CU(cudaFuncSetAttribute(attn_decode_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+        CU(cudaFuncSetAttribute(attn_decode_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
+    }
     if (head_dim == 128) {
-        if (G <= 4) attn_decode_kernel<128, 4><<<grid, kAttnThreads, attn_smem_bytes(128, 4)>>>(ap);
-        else attn_decode_kernel<128, 8><<<grid, kAttnThreads, attn_smem_bytes(128, 8)>>>(ap);
+        if (G <= 4) attn_decode_kernel<128, 4><<<grid, kAttnThreads, attn_smem_bytes(128, 4, ap.n_splits, ap.G)>>>(ap);
+        else attn_decode_kernel<128, 8><<<grid, kAttnThreads, attn_smem_bytes(128, 8, ap.n_splits, ap.G)>>>(ap);
     } else {
-        if (G <= 4) attn_decode_kernel<64, 4><<<grid, kAttnThreads, attn_smem_bytes(64, 4)>>>(ap);
-        else attn_decode_kernel<64, 8><<<grid, kAttnThreads, attn_smem_bytes(64, 8)>>>(ap);
+        if (G <= 4) attn_decode_kernel<64, 4><<<grid, kAttnThreads, attn_smem_bytes(64, 4, ap.n_splits, ap.G)>>>(ap);
+        else attn_decode_kernel<64, 8><<<grid, kAttnThreads, attn_smem_bytes(64, 8, ap.n_splits, ap.G)>>>(ap);
     }
     if ((rc = op_finish("attention_cached"))) return rc;
     CU(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));

@@ -68,7 +68,10 @@ struct MParams {
     int chunks;            // ceil(K / 256)
     int units_per_tile;    // chunks (2*chunks for ME_SWIGLU: gate chunks then up chunks)
     int total_units;
-    int total_warps;       // min(grid*warps, total_units): every one of these warps owns >= 1 unit
+    // dealing: CTA b < n_ctas owns `cbase` (+1 for b < crem) consecutive units (tile_mode 0) or whole 16-row tiles
+    // (tile_mode 1: no tile straddles two CTAs, so nothing is merged through global memory); its warps split the
+    // CTA's units evenly
+    int n_ctas, tile_mode, cbase, crem;
     int stages;
     int stage_bytes;       // 16 * max row_stride
     const float* x;        // [K] f32
@@ -192,26 +195,14 @@ __device__ __forceinline__ uint32_t lds32_a2(uint32_t a) {
     return __funnelshift_r(lds32(base), lds32(base + 4), sh);
 }
 
-// Quants as fp16 operands.  MMA_SUBNORMAL = 1 (default): the integer q sits in the low mantissa bits of an fp16
-// with a zero exponent field, i.e. it IS the subnormal q * 2^-24 -- no offset, so nothing cancels in the f32
-// accumulator; the 2^24 is folded into the final scale and into the staged sums of x.  MMA_SUBNORMAL = 0: the
-// classic magic-number form 1024 + q (0x6400 | q), whose 1024 * sum(x) has to be subtracted again (costs ~7 bits).
-#ifndef MMA_SUBNORMAL
-#define MMA_SUBNORMAL 1
-#endif
-#if MMA_SUBNORMAL
+// Quants as fp16 operands: the integer q sits in the low mantissa bits of an fp16 with a zero exponent field,
+// i.e. it IS the subnormal q * 2^-24 -- no magic-number offset (the classic 0x6400 | q = 1024 + q form makes the
+// f32 accumulator carry 1024 * sum(x) and costs ~7 bits: measured 3e-5 vs 1e-6 relative error).  The 2^24 is
+// folded into the final scale and into the staged sums of x ("operand units").
 constexpr uint32_t kMagic = 0u;
-constexpr uint32_t kMagicB = 0u;             // PRMT filler byte
-constexpr float kOff = 0.0f;                 // offset carried by every operand
-constexpr float kXsScale = 5.9604644775390625e-08f;   // 2^-24: staged sums of x are kept in operand units
-constexpr float kUnscale = 16777216.0f;      // 2^24
-#else
-constexpr uint32_t kMagic = 0x64006400u;     // half2(1024, 1024)
-constexpr uint32_t kMagicB = kMagicB;
-constexpr float kOff = 1024.0f;
-constexpr float kXsScale = 1.0f;
-constexpr float kUnscale = 1.0f;
-#endif
+constexpr uint32_t kMagicB = 0u;                      // PRMT filler byte
+constexpr float kXsScale = 5.9604644775390625e-08f;   // 2^-24
+constexpr float kUnscale = 16777216.0f;               // 2^24
 
 // ---------------------------------------------------------------- x in shared memory
 // fp16 hi and lo parts (x ~= hi + lo), stored so that the 4 elements starting at e (e % 4 == 0)
@@ -219,64 +210,49 @@ constexpr float kUnscale = 1.0f;
 // 32-bit word of quants: order [x0, x2, x1, x3] (bytes 0,2 -> k-slots 2t,2t+1; bytes 1,3 -> 2t+8,2t+9).
 // xs16[i] = sum of float(hi)+float(lo) over elements 16i..16i+15.
 struct XSmem {
-    uint32_t xh, xl, xs;  // shared-space byte addresses
+    uint32_t xh, xl, xs;  // shared-space byte addresses: hi halves, lo halves, per-16 sums
+    uint32_t s32;         // per-32-element scale 2^-k of the staged values
     uint32_t zero;        // 256 bytes of zeros: the B operand of lanes whose column pair is not addressed
 };
 __host__ __device__ __forceinline__ int xperm(int e) { return (e & ~3) | (((e & 1) << 1) | ((e >> 1) & 1)); }
 // the lo array sits 64 bytes off a multiple of 128 from the hi array: the hi and lo lanes of a B-fragment
 // load hit different banks
 constexpr uint32_t kXlPad = 64;
-// hi[K] + pad + lo[K] halves, xs16[K/16] floats, 256 zero bytes
-__host__ __device__ inline size_t x_smem_bytes(int K) { return (((size_t)4 * K + kXlPad + (size_t)(K >> 2) + 127) & ~(size_t)127) + 256; }
+// hi[K] + pad + lo[K] halves, xs16[K/16] floats, s32[K/32] floats, 256 zero bytes
+__host__ __device__ inline size_t x_smem_bytes(int K) {
+    return (((size_t)4 * K + kXlPad + (size_t)(K >> 2) + (size_t)(K >> 3) + 127) & ~(size_t)127) + 256;
+}
 
-// x staging, all threads of the CTA, K % 16 == 0.  Optional RMSNorm: y = (x * inv) * w (simd.rs:891-892).
-// The vector is scaled by a power of two (exact) so that its largest element sits near 2^12: the fp16 hi/lo
-// split then keeps ~22 bits relative to the largest element whatever the magnitude of x.
-//   stage_x_load : issues the global loads of x (and the norm weight) and reduces sum(x^2), max|x*w| per
-//                  thread; the first kXRegs float4 of each thread stay in registers for the second pass
-//   stage_x_split: block-reduces, then writes hi / lo / xs16 to shared memory; returns 2^-k for the epilogue
+// x staging, all threads of the CTA, K % 32 == 0, ONE pass and one __syncthreads (by the caller):
+//   y = x * w (w: optional RMSNorm weight; the scalar 1/rms is applied to the finished dot products instead of
+//   to every element -- (x*inv)*w in the reference, simd.rs:891-892, differs by one rounding);
+//   every 32 elements are scaled by their own power of two 2^k (exact) so that the largest sits near 2^12, then
+//   split into fp16 hi + lo: ~22 significant bits relative to the largest element of the group, whatever |x|;
+//   xs16 = sums of the true values (in operand units, x 2^-24), s32 = 2^-k, red[warp] = partial sum of x^2.
+// stage_x_load issues the global loads (first kXRegs float4 per thread) BEFORE the caller issues weight copies.
 constexpr int kXRegs = 4;
 struct XStage {
-    float4 v[kXRegs];
-    float ss, am;
+    float4 v[kXRegs], w[kXRegs];
 };
-__device__ __forceinline__ void stage_x_load(XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K,
-                                             float* red) {
+__device__ __forceinline__ void stage_x_load(XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    float ss = 0.0f, am = 0.0f;
 #pragma unroll
     for (int i = 0; i < kXRegs; i++) {
         const int e = (tid + i * nthr) * 4;
         st.v[i] = (e < K) ? *reinterpret_cast<const float4*>(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st.w[i] = (norm_w && e < K) ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
-#pragma unroll
-    for (int i = 0; i < kXRegs; i++) {
-        const int e = (tid + i * nthr) * 4;
-        const float4 v = st.v[i];
-        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (norm_w && e < K) w = *reinterpret_cast<const float4*>(norm_w + e);
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        am = fmaxf(fmaxf(am, fmaxf(fabsf(v.x * w.x), fabsf(v.y * w.y))), fmaxf(fabsf(v.z * w.z), fabsf(v.w * w.w)));
-    }
-    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(x + e);
-        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (norm_w) w = *reinterpret_cast<const float4*>(norm_w + e);
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        am = fmaxf(fmaxf(am, fmaxf(fabsf(v.x * w.x), fabsf(v.y * w.y))), fmaxf(fabsf(v.z * w.z), fabsf(v.w * w.w)));
-    }
-    ss = warp_sum(ss);
-    am = warp_max(am);
-    if ((tid & 31) == 0) { red[tid >> 5] = ss; red[kMmaMaxWarps + (tid >> 5)] = am; }
-    st.ss = ss;
-    st.am = am;
 }
-__device__ __forceinline__ void split_store4(float4 v, int e, const float* __restrict__ norm_w, float inv, float up, __half* xh,
-                                             __half* xl, float* xs, unsigned mask) {
-    if (norm_w) {
-        const float4 w = *reinterpret_cast<const float4*>(norm_w + e);
-        v.x = (v.x * inv) * w.x; v.y = (v.y * inv) * w.y; v.z = (v.z * inv) * w.z; v.w = (v.w * inv) * w.w;
-    }
+__device__ __forceinline__ float split_store4(float4 v, float4 w, int e, __half* xh, __half* xl, float* xs, float* s32, unsigned mask) {
+    const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
+    float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    am = fmaxf(am, __shfl_xor_sync(mask, am, 1));
+    am = fmaxf(am, __shfl_xor_sync(mask, am, 2));
+    am = fmaxf(am, __shfl_xor_sync(mask, am, 4));
+    int k = 0;
+    if (am > 0.0f && am < 3.0e38f) k = min(max(138 - (int)((__float_as_uint(am) >> 23) & 0xFFu), -100), 100);  // 12 - (exp - 126)
+    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23);
     v.x *= up; v.y *= up; v.z *= up; v.w *= up;
     const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
     const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
@@ -292,38 +268,42 @@ __device__ __forceinline__ void split_store4(float4 v, int e, const float* __res
                 ((__half2float(h2) + __half2float(l2)) + (__half2float(h3) + __half2float(l3)));
     sum += __shfl_xor_sync(mask, sum, 1);
     sum += __shfl_xor_sync(mask, sum, 2);
-    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum * kXsScale;
+    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum * (down * kXsScale);
+    if ((threadIdx.x & 7) == 0) s32[e >> 5] = down;
+    return ss;
 }
-__device__ __forceinline__ float stage_x_split(const XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w,
-                                              float eps, int K, uint8_t* smem, float* red /*[2 * kMmaMaxWarps]*/) {
-    const int tid = threadIdx.x, nthr = blockDim.x, nwarp = nthr >> 5;
-    __syncthreads();
-    float tot = 0.0f, amax = 0.0f;
-    for (int w = 0; w < nwarp; w++) { tot += red[w]; amax = fmaxf(amax, red[kMmaMaxWarps + w]); }
-    float inv = 1.0f;
-    if (norm_w) {
-        inv = 1.0f / sqrtf(tot / (float)K + eps);
-        amax *= inv;
-    }
-    int k = 0;
-    if (amax > 0.0f && amax < 3.0e38f) {
-        int ex;
-        frexpf(amax, &ex);            // amax = m * 2^ex, m in [0.5, 1)
-        k = min(max(12 - ex, -100), 100);
-    }
-    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23) * kUnscale;
+__device__ __forceinline__ void stage_x_finish(const XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K,
+                                               uint8_t* smem, float* red /*[kMmaMaxWarps]*/) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
     __half* xh = reinterpret_cast<__half*>(smem);
     __half* xl = reinterpret_cast<__half*>(smem + (size_t)2 * K + kXlPad);
     float* xs = reinterpret_cast<float*>(smem + (size_t)4 * K + kXlPad);
+    float* s32 = xs + (K >> 4);
+    float ss = 0.0f;
 #pragma unroll
     for (int i = 0; i < kXRegs; i++) {
         const int e = (tid + i * nthr) * 4;
-        if (e < K) split_store4(st.v[i], e, norm_w, inv, up, xh, xl, xs, __activemask());
+        if (e < K) ss += split_store4(st.v[i], st.w[i], e, xh, xl, xs, s32, __activemask());
     }
-    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4)
-        split_store4(*reinterpret_cast<const float4*>(x + e), e, norm_w, inv, up, xh, xl, xs, __activemask());
+    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        const float4 w = norm_w ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+        ss += split_store4(v, w, e, xh, xl, xs, s32, __activemask());
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
     if (tid < 64) reinterpret_cast<uint32_t*>(smem + (x_smem_bytes(K) - 256))[tid] = 0u;
-    return down;
+}
+// after the caller's __syncthreads: the factor for finished dot products (1/rms when normalising, and 2^24)
+__device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, float eps, int K) {
+    float inv = 1.0f;
+    if (norm) {
+        float tot = 0.0f;
+        const int nwarp = blockDim.x >> 5;
+        for (int w = 0; w < nwarp; w++) tot += red[w];
+        inv = 1.0f / sqrtf(tot / (float)K + eps);
+    }
+    return inv * kUnscale;
 }
 
 // ---------------------------------------------------------------- per-type unit kernels
@@ -434,8 +414,10 @@ __device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int
         k4_scales(h1, kl, dl1, ml1, dh1, mh1);
         const uint32_t xsa = sm.xs + 4u * (uint32_t)((eb >> 4) + 4 * t);
         const float xsl = lds_f32(xsa) + lds_f32(xsa + 4), xsh = lds_f32(xsa + 8) + lds_f32(xsa + 12);
-        acc0 += dl0 * sl0 - (kOff * dl0 + ml0) * xsl + (dh0 * 0.0625f) * sh0 - (kOff * 0.0625f * dh0 + mh0) * xsh;
-        acc1 += dl1 * sl1 - (kOff * dl1 + ml1) * xsl + (dh1 * 0.0625f) * sh1 - (kOff * 0.0625f * dh1 + mh1) * xsh;
+        const uint2 sc = lds64(sm.s32 + 4u * (uint32_t)((eb >> 5) + 2 * t));  // 2^-k of sub-blocks 2t, 2t+1
+        const float kl = __uint_as_float(sc.x), kh = __uint_as_float(sc.y) * 0.0625f;
+        acc0 += (dl0 * kl) * sl0 - ml0 * xsl + (dh0 * kh) * sh0 - mh0 * xsh;
+        acc1 += (dl1 * kl) * sl1 - ml1 * xsl + (dh1 * kh) * sh1 - mh1 * xsh;
     }
 }
 
@@ -488,9 +470,10 @@ __device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, int nblk, int
         for (int m = 0; m < 4; m++) {
             const int si = 4 * m + t;
             const float xs = lds_f32(sm.xs + 4u * (uint32_t)((eb >> 4) + si));
+            const float kk = lds_f32(sm.s32 + 4u * (uint32_t)((eb >> 5) + (si >> 1)));
             const float s0 = (float)lds_s8(r0 + 192 + si), s1 = (float)lds_s8(r1 + 192 + si);
-            acc0 += (d0 * s0) * ((C[m][0] + C[m][1]) - (kOff + 32.0f) * xs);   // operand offset + Q6_K's 32
-            acc1 += (d1 * s1) * ((C[m][2] + C[m][3]) - (kOff + 32.0f) * xs);
+            acc0 += (d0 * s0) * (kk * (C[m][0] + C[m][1]) - 32.0f * xs);   // Q6_K's -32
+            acc1 += (d1 * s1) * (kk * (C[m][2] + C[m][3]) - 32.0f * xs);
         }
     }
 }
@@ -524,8 +507,9 @@ __device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int
         if (b < nblk) {
             const uint32_t xa = sm.xs + 4u * (uint32_t)(((e0 + 32 * b) >> 4));
             const float xs = lds_f32(xa) + lds_f32(xa + 4);
-            acc0 += half_bits_to_float(lds16(row0 + b * 34)) * ((C[0] + C[1]) - (kOff + 128.0f) * xs);  // operand offset + int8 bias
-            acc1 += half_bits_to_float(lds16(row1 + b * 34)) * ((C[2] + C[3]) - (kOff + 128.0f) * xs);
+            const float kk = lds_f32(sm.s32 + 4u * (uint32_t)((e0 >> 5) + b));
+            acc0 += half_bits_to_float(lds16(row0 + b * 34)) * (kk * (C[0] + C[1]) - 128.0f * xs);  // int8 -> biased uint8
+            acc1 += half_bits_to_float(lds16(row1 + b * 34)) * (kk * (C[2] + C[3]) - 128.0f * xs);
         }
     }
 }
@@ -534,9 +518,6 @@ __device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int
 __device__ __forceinline__ float mma_silu(float x) { return x / (1.0f + expf(-x)); }
 
 __host__ __device__ inline int mma_chunk_blocks(int type, int chunk_elems) { return chunk_elems / type_block_elems(type); }
-
-// warp that owns unit u when U units are dealt to W warps as [floor(i*U/W), floor((i+1)*U/W))  (W <= U)
-__device__ __forceinline__ int mma_owner(long long u, long long U, long long W) { return (int)(((u + 1) * W - 1) / U); }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -590,12 +571,19 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     const uint32_t ring = sbase + (uint32_t)x_smem_bytes(K) + (uint32_t)warp * STAGES * p.stage_bytes;
     const bool swiglu = p.epi == ME_SWIGLU;
 
-    // units are dealt in contiguous runs, warp after warp, CTA after CTA: the pieces of a tile mostly meet inside
-    // one CTA (merged through shared memory), only tiles that straddle CTAs go through global memory
-    const long long U = p.total_units, W = p.total_warps;
-    const long long gw = (long long)blockIdx.x * nw + warp;
-    const bool active = gw < W;
-    const int u0 = active ? (int)(gw * U / W) : 0, u1 = active ? (int)((gw + 1) * U / W) : 0;
+    // units are dealt in contiguous runs, CTA after CTA, warp after warp: the pieces of a tile meet inside one CTA
+    // (merged through shared memory); only tiles that straddle CTAs (tile_mode 0) go through global memory
+    const int upt = p.units_per_tile;
+    const int cta = blockIdx.x;
+    const long long gw = (long long)blockIdx.x * nw + warp;  // debug stamps only
+    int cu0 = 0, cu1 = 0;
+    if (cta < p.n_ctas) {
+        const int first = cta * p.cbase + min(cta, p.crem), cnt = p.cbase + (cta < p.crem ? 1 : 0);
+        cu0 = p.tile_mode ? first * upt : first;
+        cu1 = p.tile_mode ? (first + cnt) * upt : first + cnt;
+    }
+    const int cn = cu1 - cu0;
+    const int u0 = cu0 + (warp * cn) / nw, u1 = cu0 + ((warp + 1) * cn) / nw;
     const int n_units = u1 - u0;
     long long eoff = 0;  // MoE expert index (valid after pdl_wait)
     MMA_STAMP(0);
@@ -700,21 +688,23 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     }
     // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
     XStage xst;
-    stage_x_load(xst, p.x, p.norm_w, K, s_red);
+    stage_x_load(xst, p.x, p.norm_w, K);
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
         if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
         cp_async_commit();
     }
     MMA_STAMP(2);
-    const float unscale = stage_x_split(xst, p.x, p.norm_w, p.eps, K, smem, s_red);
+    stage_x_finish(xst, p.x, p.norm_w, K, smem, s_red);
     __syncthreads();
+    const float unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
     MMA_STAMP(3);
     const uint32_t tokx = smem_token();
     XSmem sm;
     sm.xh = sbase + tokx;
     sm.xl = sm.xh + 2u * K + kXlPad;
     sm.xs = sm.xh + 4u * K + kXlPad;
+    sm.s32 = sm.xs + (uint32_t)(K >> 2);
     sm.zero = sbase + tokx + (uint32_t)x_smem_bytes(K) - 256u;
 
     // ---- epilogue of a finished tile: lane L < 16 owns row tile*16 + L of segment s (v: lanes 16..31 = up rows) ----
@@ -808,11 +798,11 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         const float v = (lane < 16) ? ((lane & 8) ? vg1 : vg0) : ((lane & 8) ? vu1 : vu0);
         ag0 = ag1 = au0 = au1 = 0.f;
 
-        const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
-        if ((long long)u0 <= tu0 && tu0 + p.units_per_tile <= (long long)u1) {
+        const int tu0 = p.seg[s].unit0 + tile * upt;
+        if (u0 <= tu0 && tu0 + upt <= u1) {
             epilogue(s, tile, v);  // the whole tile is mine
         } else {
-            const int slot = ((long long)u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or starts inside my run (slot 1)
+            const int slot = (u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or starts inside my run (slot 1)
             s_part[warp][slot][lane] = v;
             piece_s[slot] = s;
             piece_tile[slot] = tile;
@@ -821,35 +811,38 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
 
     // ---- merge the pieces: inside the CTA through shared memory, across CTAs through global memory + ticket ----
     __syncthreads();
-    const long long cw0 = (long long)blockIdx.x * nw, cw1 = min(cw0 + nw, W) - 1;
+    auto warp_of = [&](int u) { return ((u - cu0 + 1) * nw - 1) / cn; };          // local warp that owns unit u of this CTA
+    auto cta_first = [&](int c) { return c * p.cbase + min(c, p.crem); };          // first unit of CTA c (tile_mode 0)
+    auto cta_of = [&](int u) {                                                     // CTA that owns unit u (tile_mode 0)
+        const int big = p.crem * (p.cbase + 1);
+        return u < big ? u / (p.cbase + 1) : p.crem + (u - big) / p.cbase;
+    };
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
         if (piece_s[slot] < 0) continue;  // warp-uniform
         const int s = piece_s[slot], tile = piece_tile[slot];
-        const long long tu0 = (long long)p.seg[s].unit0 + (long long)tile * p.units_per_tile;
-        const long long w_first = mma_owner(tu0, U, W), w_last = mma_owner(tu0 + p.units_per_tile - 1, U, W);
-        const long long lo = max(w_first, cw0), hi = min(w_last, cw1);
-        if (gw != lo) continue;  // the first warp of the CTA that holds a piece finishes the tile
+        const int tu0 = p.seg[s].unit0 + tile * upt;
+        const int lo_u = max(tu0, cu0), hi_u = min(tu0 + upt, cu1) - 1;
+        const int lo = warp_of(lo_u), hi = warp_of(hi_u);
+        if (warp != lo) continue;  // the first warp of the CTA that holds a piece finishes the tile
         float v = 0.f;
-        for (long long w = lo; w <= hi; w++) {  // fixed order: deterministic
-            const int sl = (w * U / W >= tu0) ? 0 : 1;
-            v += s_part[(int)(w - cw0)][sl][lane];
+        for (int w = lo; w <= hi; w++) {  // fixed order: deterministic
+            const int wu0 = cu0 + (w * cn) / nw, wu1 = cu0 + ((w + 1) * cn) / nw;
+            if (wu1 == wu0) continue;     // a warp without units holds no piece
+            v += s_part[w][(wu0 >= tu0) ? 0 : 1][lane];
         }
-        if (lo != w_first || hi != w_last) {  // the tile straddles CTAs
+        if (tu0 < cu0 || tu0 + upt > cu1) {  // the tile straddles CTAs (tile_mode 0 only)
             const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
-            const long long c_first = w_first / nw, c_last = w_last / nw;
-            const int cslot = (cw0 * U / W >= tu0) ? 0 : 1;
-            p.part[((size_t)blockIdx.x * 2 + cslot) * 32 + lane] = v;
+            const int c_first = cta_of(tu0), c_last = cta_of(tu0 + upt - 1);
+            p.part[((size_t)cta * 2 + ((cu0 >= tu0) ? 0 : 1)) * 32 + lane] = v;
             __syncwarp();
             unsigned int ticket = 0;
             if (lane == 0) ticket = atom_add_acq_rel(&p.tickets[tile_id], 1u);
             ticket = __shfl_sync(0xffffffffu, ticket, 0);
             if (ticket != (unsigned)(c_last - c_first)) continue;  // not the last CTA
             v = 0.f;
-            for (long long c = c_first; c <= c_last; c++) {
-                const int sl = ((c * nw) * U / W >= tu0) ? 0 : 1;
-                v += ld_relaxed_gpu(&p.part[((size_t)c * 2 + sl) * 32 + lane]);
-            }
+            for (int c = c_first; c <= c_last; c++)
+                v += ld_relaxed_gpu(&p.part[((size_t)c * 2 + ((cta_first(c) >= tu0) ? 0 : 1)) * 32 + lane]);
             if (lane == 0) p.tickets[tile_id] = 0;
         }
         epilogue(s, tile, v);
@@ -864,10 +857,13 @@ __device__ __forceinline__ void mma_warm_l2(const MParams& p, int depth) {
     if (p.expert_sel) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nw = blockDim.x >> 5;
-    const long long U = p.total_units, W = p.total_warps;
-    const long long gw = (long long)blockIdx.x * nw + warp;
-    if (gw >= W) return;
-    const int u0 = (int)(gw * U / W), u1 = (int)((gw + 1) * U / W);
+    const int cta = blockIdx.x;
+    if (cta >= p.n_ctas) return;
+    const int first = cta * p.cbase + min(cta, p.crem), cnt = p.cbase + (cta < p.crem ? 1 : 0);
+    const int cu0 = p.tile_mode ? first * p.units_per_tile : first;
+    const int cn = p.tile_mode ? cnt * p.units_per_tile : cnt;
+    const int u0 = cu0 + (warp * cn) / nw, u1 = cu0 + ((warp + 1) * cn) / nw;
+    if (u1 == u0) return;
     const bool swiglu = p.epi == ME_SWIGLU;
     int s = (p.n_seg > 2 && u0 >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && !swiglu && u0 >= p.seg[1].unit0) ? 1 : 0;
     const int local = u0 - p.seg[s].unit0;
@@ -908,6 +904,28 @@ inline int mma_row_stride(int type) {
         const int m = rs & 127;
         if (aligned ? (m == 64) : ((m & 15) == 0 && ((m >> 4) & 1))) return rs;
     }
+}
+
+// How the units of a launch are dealt to `grid` CTAs.  Whole tiles per CTA when that costs less than the ~2 us a
+// merge through global memory takes (imbalance of one tile on a short launch); unit-balanced stream-K otherwise.
+inline void mma_deal(MParams& p, int grid) {
+    int tiles = 0;
+    double bytes = 0;
+    const int nseg_tiles = (p.epi == ME_SWIGLU) ? 1 : p.n_seg;
+    for (int s = 0; s < nseg_tiles; s++) tiles += p.seg[s].n_tiles;
+    for (int s = 0; s < p.n_seg; s++) bytes += (double)p.seg[s].n_rows * p.seg[s].nb_row * p.seg[s].bb;
+    p.n_ctas = grid;
+    p.tile_mode = 0;
+    if (tiles >= grid) {
+        const int per = (tiles + grid - 1) / grid;
+        const double imbalance = (double)per * grid / tiles - 1.0;        // extra time of the fullest CTA
+        const double cost_us = imbalance * bytes / 5.0e12 * 1e6;          // at ~5 TB/s
+        if (cost_us < 1.5) p.tile_mode = 1;
+    }
+    const int n = p.tile_mode ? tiles : p.total_units;
+    if (n < grid) p.n_ctas = n;
+    p.cbase = n / p.n_ctas;
+    p.crem = n % p.n_ctas;
 }
 
 struct MPlan {
@@ -966,7 +984,7 @@ inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size
     plan.smem = need(warps, stages);
     plan.grid = (int)std::min<long long>(n_sm, (p.total_units + warps - 1) / warps);
     if (plan.grid < 1) plan.grid = 1;
-    p.total_warps = (int)std::min<long long>((long long)plan.grid * warps, p.total_units);
+    mma_deal(p, plan.grid);
     return true;
 }
 

@@ -57,13 +57,17 @@ struct MegaParams {
     unsigned long long* dbg;  // optional [n_phases + 3] globaltimer stamps of CTA 0 for the LAST token of the launch
 };
 
-// Arrive + wait on a monotonically increasing counter.  Release/acquire at gpu scope: everything the CTA wrote
-// before the barrier is visible to every CTA after it.  Bounded spin: a lost CTA must never hang the box.
-__device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& target, int* err, int* s_flag) {
+// Grid barrier on a monotonically increasing counter, split in two so that work that does not depend on other
+// CTAs (fetching the descriptor of a later phase) runs while thread 0 waits.  Release/acquire at gpu scope:
+// everything the CTA wrote before grid_arrive is visible to every CTA after grid_wait.  Bounded spin: a lost CTA
+// must never hang the box.
+__device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& target) {
     __syncthreads();
     target += gridDim.x;
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+__device__ __forceinline__ bool grid_wait(unsigned int* bar, unsigned int target, int* err, int* s_flag) {
     if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int v = 0;
         int ok = 1;
         const long long t0 = clock64();
@@ -81,6 +85,10 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& ta
     __syncthreads();
     return *s_flag != 0;
 }
+__device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& target, int* err, int* s_flag) {
+    grid_arrive(bar, target);
+    return grid_wait(bar, target, err, s_flag);
+}
 
 template <int STAGES>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const __grid_constant__ MegaParams mp) {
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     __shared__ float s_part[kMmaMaxWarps][2][32];
     __shared__ unsigned int s_ticket;
     __shared__ int s_flag;
-    __shared__ __align__(16) MegaPhase s_ph;
+    __shared__ __align__(16) MegaPhase s_phs[3];   // descriptors of the running phase and the next two (ring)
     __shared__ float s_av[kMmaMaxWarps];
     __shared__ int s_ai[kMmaMaxWarps];
 
@@ -97,6 +105,18 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int target = 0;
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;  // prefill: no vocab head
+
+    // descriptor ring: slot (global phase number % 3).  Threads of warps >= 1 fetch descriptor `ph` (of the token's
+    // program, cyclic) while thread 0 spins in a barrier; it is used two barriers later.
+    auto fetch_desc = [&](long long gph) {
+        if (tid < 32) return;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.phases + (int)(gph % n_run));
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phs[gph % 3]);
+        for (int i = tid - 32; i < (int)(sizeof(MegaPhase) / 4); i += (NW - 1) * 32) dst[i] = src[i];
+    };
+    fetch_desc(0);
+    fetch_desc(1);
+    long long gph = 0;  // phases executed so far in this launch
 
     for (int tok = 0; tok < mp.n_tokens; tok++) {
         // ---- embedding (LlamaModel::forward, model/llama.rs:293-306): CTA 0 dequantises row `token`, bit-exactly ----
@@ -118,18 +138,12 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
         if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
         if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[0] = gtimer();
 
-        for (int ph = 0; ph < n_run; ph++) {
-            // phase descriptor -> shared memory
-            {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.phases + ph);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ph);
-                for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += NW * 32) dst[i] = src[i];
-            }
-            __syncthreads();
-            if (s_ph.kind == PH_GEMV) {
-                mma_gemv_cta<STAGES>(s_ph.gemv, smem, s_red, s_part, false, false);
+        for (int ph = 0; ph < n_run; ph++, gph++) {
+            const MegaPhase& cur = s_phs[gph % 3];
+            if (cur.kind == PH_GEMV) {
+                mma_gemv_cta<STAGES>(cur.gemv, smem, s_red, s_part, false, false);
             } else {
-                const AttnParams& ap = s_ph.attn;
+                const AttnParams& ap = cur.attn;
                 const int kv_len = *ap.pos + 1;
                 const int n_items = ap.n_kv * ap.n_splits;
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -145,10 +159,16 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                     __syncthreads();
                 }
             }
-            // keep HBM busy across the barrier: the first units of the next GEMV go towards L2 now
-            if (ph + 1 < n_run && mp.phases[ph + 1].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 1].gemv, 4);
-            else if (ph + 2 < n_run && mp.phases[ph + 2].kind == PH_GEMV) mma_warm_l2<STAGES>(mp.phases[ph + 2].gemv, 4);
-            if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+            // keep HBM busy across the barrier: the first units of the next GEMV go towards L2 now (its descriptor
+            // is already in the ring)
+            const bool more = (ph + 1 < n_run) || (tok + 1 < mp.n_tokens);
+            if (more) {
+                const MegaPhase& nxt = s_phs[(gph + 1) % 3];
+                if (nxt.kind == PH_GEMV) mma_warm_l2<STAGES>(nxt.gemv, 4);
+            }
+            grid_arrive(mp.bar, target);
+            fetch_desc(gph + 2);
+            if (!grid_wait(mp.bar, target, mp.err, &s_flag)) return;
             if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[1 + ph] = gtimer();
         }
 

@@ -151,7 +151,7 @@ static void lab_init() {
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, 0));
     g_nsm = prop.multiProcessorCount;
-    g_smem_limit = prop.sharedMemPerBlockOptin - 6144;  // static shared memory of the kernels
+    g_smem_limit = prop.sharedMemPerBlockOptin - 8192;  // static shared memory of the kernels
     printf("device: %s, %d SMs, smem optin %zu\n", prop.name, g_nsm, (size_t)prop.sharedMemPerBlockOptin);
     CK(cudaMalloc(&g_part, (size_t)g_nsm * kMmaMaxWarps * 2 * 32 * 4));
     CK(cudaMalloc(&g_tickets, 65536 * 4));
