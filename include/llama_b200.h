@@ -103,6 +103,16 @@ B200_API int b200_ctx_upload_tensor(b200_ctx* ctx, const char* gguf_name, uint32
 B200_API int b200_ctx_finalize(b200_ctx* ctx);
 B200_API void b200_ctx_destroy(b200_ctx* ctx);
 
+/* Tensor parallel (replaces the gRPC all-reduce-via-rank-0 of
+ * src/distributed/tensor_parallel_distributed.rs:135-187): one context per rank/GPU, created with
+ * world_size/rank in b200_parallel_desc.  Between b200_ctx_create and b200_ctx_finalize every rank calls
+ * b200_ctx_tp_handle (a 64-byte CUDA IPC handle of its exchange region), the host passes the handles around
+ * (all-gather), and every rank calls b200_ctx_tp_set_peer for every other rank.  Uploads take the FULL tensor;
+ * the library keeps this rank's column / row shard.  The kernels then exchange partial sums through peer memory
+ * (NVLink).  b200_forward returns this rank's slice of the logits: [rank * vocab/P, (rank+1) * vocab/P). */
+B200_API int b200_ctx_tp_handle(b200_ctx* ctx, void* handle_out64);
+B200_API int b200_ctx_tp_set_peer(b200_ctx* ctx, int peer_rank, const void* handle64);
+
 /* GpuInference::forward (backend/mod.rs:285): one token through every layer;
  * logits_out receives `vocab` f32 on the host. */
 B200_API int b200_forward(b200_ctx* ctx, int seq, uint32_t token, float* logits_out);

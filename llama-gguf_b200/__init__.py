@@ -106,6 +106,8 @@ def lib():
     L.b200_decode_greedy.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), fp]
     L.b200_get_hidden.argtypes = [vp, C.c_int, C.c_int, fp]
     L.b200_ctx_stats.argtypes = [vp, u64p, u64p, u64p]
+    L.b200_ctx_tp_handle.argtypes = [vp, vp]
+    L.b200_ctx_tp_set_peer.argtypes = [vp, C.c_int, vp]
     L.b200_debug_mega_timeline.argtypes = [vp, u64p, C.c_int]
     L.b200_debug_mega_phase.argtypes = [vp, C.c_int, u64p, C.c_int]
     L.b200_bench_weight_gemv.argtypes = [vp, C.c_char_p, C.c_int, fp, u64p]
@@ -324,8 +326,13 @@ class GpuOnlyInference:
     (ggml_type, ne, ndarray) with ne[0] = in_features.
     """
 
-    def __init__(self, desc: dict, tensors: dict, device=0, taps=False, feeder=None):
-        """`feeder(upload)` may stream tensors one by one (upload(name, type, ne, data)) instead of `tensors`."""
+    def __init__(self, desc: dict, tensors: dict, device=0, taps=False, feeder=None, parallel=None, exchange=None):
+        """`feeder(upload)` may stream tensors one by one (upload(name, type, ne, data)) instead of `tensors`.
+
+        Tensor parallel: `parallel=(world_size, rank)` makes this the context of one rank (one process per GPU);
+        `exchange(handle_bytes) -> [handle_bytes of every rank]` is the all-gather the host provides
+        (parallel.all_gather_bytes over torch.distributed).  Every rank uploads the FULL tensors; the library keeps
+        its shard.  forward() then returns this rank's slice of the logits (see parallel.TensorParallelInference)."""
         L = lib()
         if device_count() == 0:
             raise NotAvailable("cuda-b200: no CUDA device (this backend has no CPU fallback)")
@@ -335,7 +342,9 @@ class GpuOnlyInference:
                 raise InvalidArgument(f"unknown model desc field {k}")
             setattr(d, k, v)
         self.desc = {k: getattr(d, k) for k in DESC_KEYS}
-        par = ParallelDesc(1, 0, device)
+        world, rank = parallel if parallel else (1, 0)
+        par = ParallelDesc(world, rank, device)
+        self.world, self.rank = world, rank
         h = C.c_void_p()
         old = os.environ.get("B200_TAPS")
         if taps:
@@ -350,6 +359,15 @@ class GpuOnlyInference:
                     os.environ["B200_TAPS"] = old
         self._h = h
         try:
+            if world > 1:
+                if exchange is None:
+                    raise InvalidArgument("tensor parallel contexts need an `exchange` (all-gather of IPC handles)")
+                mine = C.create_string_buffer(64)
+                _check(L.b200_ctx_tp_handle(self._h, mine))
+                handles = exchange(mine.raw)
+                for r, hb in enumerate(handles):
+                    if r != rank:
+                        _check(L.b200_ctx_tp_set_peer(self._h, r, C.create_string_buffer(hb, 64)))
             for name, (t, ne, data) in (tensors or {}).items():
                 self.upload_tensor(name, t, ne, data)
             if feeder is not None:
@@ -358,7 +376,7 @@ class GpuOnlyInference:
         except Exception:
             self.close()
             raise
-        self.vocab = self.desc["vocab"]
+        self.vocab = self.desc["vocab"] // world  # tensor parallel: this rank's slice of the logits
 
     @classmethod
     def from_model(cls, model, max_seq_len, **kw):

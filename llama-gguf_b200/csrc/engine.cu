@@ -133,6 +133,13 @@ struct b200_ctx {
     int mega_splits = 1;
     uint64_t mega_launches = 0;
     unsigned long long* mega_dbg = nullptr;
+    // tensor parallel (one context per rank/GPU; c->d holds the LOCAL head / ffn counts, dg the global ones)
+    b200_model_desc dg{};
+    int vocab_l = 0;                     // rows of the vocab head owned by this rank
+    uint8_t* tp_region = nullptr;        // [2][P][H] f32 partial sums | flags[16] u32 | cand[P][2] f32   (IPC-exported)
+    uint8_t* tp_peer[kMmaMaxPeers] = {}; // the same region of every rank as mapped in this process (own rank: tp_region)
+    bool tp_peer_set[kMmaMaxPeers] = {};
+    unsigned int tp_epoch = 0;
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
@@ -197,7 +204,19 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     if (d.hidden % 32) return bad("hidden must be a multiple of 32");
     if (d.n_experts > 64 || d.n_experts_used > 8) return bad("at most 64 experts, top-8");
     if (c->par.world_size < 1 || c->par.rank < 0 || c->par.rank >= c->par.world_size) return bad("bad parallel desc");
-    if (c->par.world_size != 1) return bad("tensor parallelism is configured through b200_ctx_tp_* (not in this build)");
+    c->dg = d;
+    if (c->par.world_size != 1) {
+        const int P = c->par.world_size;
+        if (P != 2 && P != 4 && P != 8) return bad("tensor-parallel world size must be 2, 4 or 8");
+        if (d.n_experts > 0) return bad("tensor parallelism for MoE models is not built yet");
+        // ShardingPlan::from_config's divisibility rules (src/backend/tensor_parallel.rs:69-106)
+        if (d.n_heads % P || d.n_kv_heads % P || d.ffn % P || d.vocab % P) return bad("heads, kv heads, ffn and vocab must be divisible by the world size");
+        if ((d.vocab / P) % 16) return bad("vocab / world_size must be a multiple of 16");
+        d.n_heads /= P;
+        d.n_kv_heads /= P;
+        d.ffn /= P;
+    }
+    c->vocab_l = d.vocab / c->par.world_size;
     if (c->par.device >= n_dev) return bad("device ordinal out of range");
     CU(cudaSetDevice(c->par.device));
     cudaDeviceProp prop{};
@@ -246,6 +265,18 @@ static DevTensor* slot_for_name(b200_ctx* c, const std::string& name) {
     return nullptr;
 }
 
+// 0 = replicated, 1 = column-parallel (split output rows), 2 = row-parallel (split K)
+static int tp_shard_kind(const char* name) {
+    const std::string n(name);
+    auto ends = [&](const char* suf) { const std::string s2(suf); return n.size() >= s2.size() && n.compare(n.size() - s2.size(), s2.size(), s2) == 0; };
+    if (n == "output.weight") return 1;
+    if (ends("attn_q.weight") || ends("attn_k.weight") || ends("attn_v.weight") || ends("attn_q.bias") || ends("attn_k.bias") ||
+        ends("attn_v.bias") || ends("ffn_gate.weight") || ends("ffn_up.weight"))
+        return 1;
+    if (ends("attn_output.weight") || ends("ffn_down.weight")) return 2;
+    return 0;
+}
+
 extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne,
                                       int n_dims, const void* host, size_t nbytes) {
     if (!c || !gguf_name || !ne || !host) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_upload_tensor: null argument");
@@ -263,14 +294,43 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     CU(cudaSetDevice(c->par.device));
     if (t->d) cudaFree(t->d);
     *t = DevTensor();
-    CU_ALLOC(cudaMalloc((void**)&t->d, nbytes + 256));
-    CU(cudaMemcpy(t->d, host, nbytes, cudaMemcpyHostToDevice));
-    CU(cudaMemset(t->d + nbytes, 0, 256));
+    // Tensor-parallel shard of this rank (Megatron split; ShardingPlan, src/backend/tensor_parallel.rs:69-106):
+    //   column-parallel = a contiguous range of output rows (attn_q/k/v + biases by head, ffn_gate/up, output),
+    //   row-parallel    = a contiguous range of K blocks of EVERY row (attn_output, ffn_down),
+    //   everything else replicated.  GGUF rows are contiguous blocks, so both are plain (2-D) byte ranges.
+    const int P = c->par.world_size, R = c->par.rank;
+    uint64_t lne[4] = {1, 1, 1, 1};
+    for (int i = 0; i < n_dims; i++) lne[i] = ne[i];
+    const uint64_t row_bytes_full = ne[0] / be * bb;
+    const int kind = (P > 1) ? tp_shard_kind(gguf_name) : 0;
+    if (kind == 1) {
+        const int dim = n_dims == 1 ? 0 : 1;
+        if (ne[dim] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": rows not divisible by the world size");
+        lne[dim] = ne[dim] / P;
+        const size_t lbytes = nbytes / P;
+        CU_ALLOC(cudaMalloc((void**)&t->d, lbytes + 256));
+        CU(cudaMemcpy(t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes, cudaMemcpyHostToDevice));
+        CU(cudaMemset(t->d + lbytes, 0, 256));
+        t->nbytes = lbytes;
+    } else if (kind == 2) {
+        const uint64_t nb = ne[0] / be;
+        if (nb % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": K blocks not divisible by the world size");
+        lne[0] = ne[0] / P;
+        const size_t slice = (size_t)(nb / P) * bb, rows = (size_t)(numel / ne[0]);
+        CU_ALLOC(cudaMalloc((void**)&t->d, slice * rows + 256));
+        CU(cudaMemcpy2D(t->d, slice, (const uint8_t*)host + (size_t)R * slice, row_bytes_full, slice, rows, cudaMemcpyHostToDevice));
+        CU(cudaMemset(t->d + slice * rows, 0, 256));
+        t->nbytes = slice * rows;
+    } else {
+        CU_ALLOC(cudaMalloc((void**)&t->d, nbytes + 256));
+        CU(cudaMemcpy(t->d, host, nbytes, cudaMemcpyHostToDevice));
+        CU(cudaMemset(t->d + nbytes, 0, 256));
+        t->nbytes = nbytes;
+    }
     t->type = (int)ggml_type;
     t->n_dims = n_dims;
-    for (int i = 0; i < n_dims; i++) t->ne[i] = ne[i];
-    t->nbytes = nbytes;
-    t->row_bytes = (long long)(ne[0] / be * bb);
+    for (int i = 0; i < n_dims; i++) t->ne[i] = lne[i];
+    t->row_bytes = (long long)(lne[0] / be * bb);
     c->tensors[gguf_name] = *t;
     return B200_OK;
 }
@@ -303,7 +363,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     if ((rc = check_weight(c->token_embd, "token_embd.weight", H, V, -1))) return rc;
     if ((rc = check_f32_vec(c->output_norm, "output_norm.weight", H, -1, true))) return rc;
     if (c->output.present()) {
-        if ((rc = check_weight(c->output, "output.weight", H, V, -1))) return rc;
+        if ((rc = check_weight(c->output, "output.weight", H, (uint64_t)c->vocab_l, -1))) return rc;
     } else if (!d.tied_output) {
         // the loader ties silently when output.weight is absent (loader.rs:349-355)
     }
@@ -399,7 +459,64 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
         CU(cudaFuncSetAttribute(attn_decode_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim_attn));
     }
     c->finalized = true;
-    return mega_build(c);
+    if (c->par.world_size > 1) {
+        for (int r = 0; r < c->par.world_size; r++)
+            if (!c->tp_peer_set[r]) {
+                c->finalized = false;
+                return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_finalize: tensor-parallel peers not connected (b200_ctx_tp_handle / b200_ctx_tp_set_peer)");
+            }
+    }
+    if ((rc = mega_build(c))) return rc;
+    if (c->par.world_size > 1 && !c->mega_ok) {
+        c->finalized = false;
+        return fail(B200_ERR_UNSUPPORTED, "tensor parallelism needs the megakernel path (dense model, K-quant / Q8_0 weights with 256-aligned shards)");
+    }
+    return B200_OK;
+}
+
+// ---- tensor-parallel plumbing: every rank exports one region (partial sums, flags, argmax candidates) as a CUDA IPC
+// handle; the host side (torch.distributed all_gather in the Python mirror, MPI/gRPC in the Rust shim) passes the
+// handles around; the kernels then read and write peer memory directly over NVLink.
+static size_t tp_region_bytes(const b200_ctx* c) {
+    return (size_t)2 * kMmaMaxPeers * c->d.hidden * sizeof(float) + 64 * sizeof(unsigned int) + kMmaMaxPeers * 2 * sizeof(float) + 256;
+}
+static float* tp_ar(const b200_ctx* c, uint8_t* base, int buf, int rank_slot) {
+    return reinterpret_cast<float*>(base) + ((size_t)buf * kMmaMaxPeers + rank_slot) * c->d.hidden;
+}
+static unsigned int* tp_flags(const b200_ctx* c, uint8_t* base) {
+    return reinterpret_cast<unsigned int*>(base + (size_t)2 * kMmaMaxPeers * c->d.hidden * sizeof(float));
+}
+static float* tp_cand(const b200_ctx* c, uint8_t* base) { return reinterpret_cast<float*>(tp_flags(c, base) + 64); }
+
+extern "C" int b200_ctx_tp_handle(b200_ctx* c, void* handle_out64) {
+    if (!c || !handle_out64) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_tp_handle: null argument");
+    CU(cudaSetDevice(c->par.device));
+    if (!c->tp_region) {
+        CU_ALLOC(cudaMalloc((void**)&c->tp_region, tp_region_bytes(c)));
+        CU(cudaMemset(c->tp_region, 0, tp_region_bytes(c)));
+        CU(cudaDeviceSynchronize());
+        c->tp_peer[c->par.rank] = c->tp_region;
+        c->tp_peer_set[c->par.rank] = true;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->tp_region));
+    memcpy(handle_out64, &h, 64);
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_tp_set_peer(b200_ctx* c, int peer_rank, const void* handle64) {
+    if (!c || !handle64) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_tp_set_peer: null argument");
+    if (peer_rank < 0 || peer_rank >= c->par.world_size) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_tp_set_peer: bad rank");
+    if (peer_rank == c->par.rank) return B200_OK;
+    CU(cudaSetDevice(c->par.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->tp_peer[peer_rank] = (uint8_t*)p;
+    c->tp_peer_set[peer_rank] = true;
+    return B200_OK;
 }
 
 extern "C" void b200_ctx_destroy(b200_ctx* c) {
@@ -416,6 +533,9 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         cudaFree(s.kv);
         cudaFree(s.d_phases);
     }
+    for (int r = 0; r < c->par.world_size && r < kMmaMaxPeers; r++)
+        if (r != c->par.rank && c->tp_peer[r]) cudaIpcCloseMemHandle(c->tp_peer[r]);
+    cudaFree(c->tp_region);
     cudaFree(c->mega_bar);
     cudaFree(c->mega_cand_val);
     cudaFree(c->mega_cand_idx);
@@ -607,7 +727,38 @@ static int mega_build(b200_ctx* c) {
     c->mega_splits = (int)std::max(1, std::min(64, c->n_sm / nkv));
     size_t smem = attn_item_floats(hd, G <= 4 ? 4 : 8, kMmaMaxWarps, c->mega_splits, G) * sizeof(float);
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
-    const DevTensor& head = c->output.present() ? c->output : c->token_embd;
+    DevTensor head = c->output.present() ? c->output : c->token_embd;
+    const int P = c->par.world_size, R = c->par.rank;
+    if (P > 1) {
+        if (!c->output.present()) {  // tied head: this rank's rows of the full embedding table
+            head.d += (size_t)R * c->vocab_l * head.row_bytes;
+            head.nbytes = (size_t)c->vocab_l * head.row_bytes;
+        }
+        head.ne[1] = (uint64_t)c->vocab_l;
+    }
+    // tensor parallel: the two row-parallel GEMVs of a layer leave their partial sums in every rank's region
+    // (buffer 0: attention output projection, buffer 1: FFN down projection); the next GEMV sums them while staging
+    int tp_pending = -1;            // buffer whose sum (+ residual) is the next GEMV's input
+    const float* tp_res = nullptr;  // residual to add to that sum
+    float* tp_full = nullptr;       // where CTA 0 stores the summed vector (residual of a later phase)
+    auto tp_input = [&](MParams& m) {
+        if (P <= 1 || tp_pending < 0) return;
+        m.xsum = tp_ar(c, c->tp_region, tp_pending, 0);
+        m.n_sum = P;
+        m.sum_stride = d.hidden;
+        m.x_res = tp_res;
+        m.x_full_out = tp_full;
+        tp_pending = -1;
+    };
+    auto tp_output = [&](MegaPhase& ph, int buf) {
+        if (P <= 1) return;
+        MParams& m = ph.gemv;
+        m.n_peer = P;
+        for (int r = 0; r < P; r++) m.peer_out[r] = tp_ar(c, c->tp_peer[r], buf, R);
+        m.epi = ME_STORE;       // the residual is added by the consumer, after the sum
+        m.residual = nullptr;
+        ph.tp_sync = 1;
+    };
 
     auto gemv_phase = [&](MegaPhase& ph, GemvParams& g) -> bool {
         MParams m;
@@ -623,6 +774,7 @@ static int mega_build(b200_ctx* c) {
         ph = MegaPhase{};
         ph.kind = PH_GEMV;
         ph.gemv = m;
+        tp_input(ph.gemv);
         smem = std::max(smem, plan.smem);
         return true;
     };
@@ -647,6 +799,7 @@ static int mega_build(b200_ctx* c) {
                 fill_seg(p.seg[1], L.wk, c->qkv + (size_t)nh * hd, &L.bk, 0);
                 fill_seg(p.seg[2], L.wv, c->qkv + (size_t)(nh + nkv) * hd, &L.bv, 0);
                 p.n_seg = 3; p.K = H; p.x = c->xa; p.norm_w = L.attn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+                tp_res = c->xb; tp_full = c->xa;   // TP, layers > 0: xa = sum(down partials) + xb
                 if (!gemv_phase(ph, p)) return B200_OK;
                 prog.push_back(ph);
             }
@@ -665,7 +818,9 @@ static int mega_build(b200_ctx* c) {
                 fill_seg(p.seg[0], L.wo, c->xb, nullptr, 0);
                 p.n_seg = 1; p.K = nh * hd; p.x = c->attn; p.epi = EPI_RESIDUAL; p.residual = c->xa;
                 if (!gemv_phase(ph, p)) return B200_OK;
+                tp_output(ph, 0);
                 prog.push_back(ph);
+                if (P > 1) { tp_pending = 0; tp_res = c->xa; tp_full = c->xb; }   // xb = sum(O partials) + xa
             }
             {   // RMSNorm + gate | up + SwiGLU
                 GemvParams p{};
@@ -680,7 +835,9 @@ static int mega_build(b200_ctx* c) {
                 fill_seg(p.seg[0], L.down, c->xa, nullptr, 0);
                 p.n_seg = 1; p.K = d.ffn; p.x = c->hbuf; p.epi = EPI_RESIDUAL; p.residual = c->xb;
                 if (!gemv_phase(ph, p)) return B200_OK;
+                tp_output(ph, 1);
                 prog.push_back(ph);
+                if (P > 1) { tp_pending = 1; tp_res = c->xb; tp_full = c->xa; }   // xa = sum(down partials) + xb
             }
         }
         {   // final RMSNorm + vocab head
@@ -719,6 +876,18 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
     mp.generated = sl.d_generated; mp.max_generated = kMaxGenerated;
     mp.hd = d.head_dim; mp.G = d.n_heads / d.n_kv_heads;
     mp.dbg = c->mega_dbg;
+    mp.tp_size = c->par.world_size; mp.tp_rank = c->par.rank; mp.vocab_local = c->vocab_l;
+    if (c->par.world_size > 1) {
+        mp.tp_flags = tp_flags(c, c->tp_region);
+        mp.tp_cand = tp_cand(c, c->tp_region);
+        for (int r = 0; r < c->par.world_size; r++) {
+            mp.tp_peer_flags[r] = tp_flags(c, c->tp_peer[r]);
+            mp.tp_peer_cand[r] = tp_cand(c, c->tp_peer[r]);
+        }
+        mp.tp_epoch0 = c->tp_epoch;
+        const int per_token = 2 * d.n_layers + (mode == MEGA_GREEDY ? 1 : 0);
+        c->tp_epoch += (unsigned int)(per_token * n_tokens);
+    }
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
     void* args[] = {&mp};
     CU(cudaLaunchCooperativeKernel((void*)mega_decode_kernel<kMegaStages>, dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
@@ -803,9 +972,10 @@ extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_
     Slot& sl = c->slots[seq];
     if ((rc = set_token(c, sl, token))) return rc;
     if ((rc = run_token(c, seq, MODE_LOGITS))) return rc;
-    CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->d.vocab * 4, cudaMemcpyDeviceToHost, c->stream));
+    // tensor parallel: this rank's slice [rank * vocab/P, (rank+1) * vocab/P) of the logits (the caller gathers)
+    CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    memcpy(logits_out, c->h_logits, (size_t)c->d.vocab * 4);
+    memcpy(logits_out, c->h_logits, (size_t)c->vocab_l * 4);
     sl.host_pos++;
     return B200_OK;
 }

@@ -42,6 +42,7 @@ constexpr int kMmaMaxStages = 4;
 
 enum : int { ME_STORE = 0, ME_RESIDUAL = 1, ME_SWIGLU = 2, ME_SCALED_ACC = 3 };
 
+constexpr int kMmaMaxPeers = 8;
 constexpr int kMmaChunk = 256;   // elements of K per unit (one K-quant super-block, eight Q8_0 blocks)
 
 struct MSeg {
@@ -83,6 +84,16 @@ struct MParams {
     const int* expert_sel;
     const float* expert_wt;
     int expert_slot;
+    // tensor parallel (megakernel only).  Input side: x = sum_r xsum[r * sum_stride + e] (+ x_res[e]) -- the
+    // all-reduce of a row-parallel GEMV is finished by its consumer, in rank order on every rank; CTA 0 also
+    // stores the summed vector to x_full_out (it is the residual of a later phase).  Output side: the finished
+    // rows go to peer_out[r][j] for every rank r (peer memory over NVLink) instead of seg.out.
+    const float* xsum;
+    int n_sum, sum_stride;
+    const float* x_res;
+    float* x_full_out;
+    float* peer_out[kMmaMaxPeers];
+    int n_peer;
     // cross-CTA merge scratch
     float* part;             // [grid][2][32]
     unsigned int* tickets;   // [total logical tiles], zero between launches
@@ -234,12 +245,34 @@ constexpr int kXRegs = 4;
 struct XStage {
     float4 v[kXRegs], w[kXRegs];
 };
-__device__ __forceinline__ void stage_x_load(XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K) {
+// One float4 of the GEMV input: plain x, or (tensor parallel) the rank-ordered sum of the partial vectors + residual
+struct XSource {
+    const float* x;
+    const float* xsum;
+    int n_sum, sum_stride;
+    const float* x_res;
+    float* x_full_out;
+};
+__device__ __forceinline__ float4 x_fetch4(const XSource& xs, int e) {
+    if (xs.n_sum == 0) return *reinterpret_cast<const float4*>(xs.x + e);
+    float4 a = *reinterpret_cast<const float4*>(xs.xsum + e);
+    for (int r = 1; r < xs.n_sum; r++) {
+        const float4 b = *reinterpret_cast<const float4*>(xs.xsum + (size_t)r * xs.sum_stride + e);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (xs.x_res) {
+        const float4 b = *reinterpret_cast<const float4*>(xs.x_res + e);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (xs.x_full_out && blockIdx.x == 0) *reinterpret_cast<float4*>(xs.x_full_out + e) = a;
+    return a;
+}
+__device__ __forceinline__ void stage_x_load(XStage& st, const XSource& xs, const float* __restrict__ norm_w, int K) {
     const int tid = threadIdx.x, nthr = blockDim.x;
 #pragma unroll
     for (int i = 0; i < kXRegs; i++) {
         const int e = (tid + i * nthr) * 4;
-        st.v[i] = (e < K) ? *reinterpret_cast<const float4*>(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st.v[i] = (e < K) ? x_fetch4(xs, e) : make_float4(0.f, 0.f, 0.f, 0.f);
         st.w[i] = (norm_w && e < K) ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
 }
@@ -272,7 +305,7 @@ __device__ __forceinline__ float split_store4(float4 v, float4 w, int e, __half*
     if ((threadIdx.x & 7) == 0) s32[e >> 5] = down;
     return ss;
 }
-__device__ __forceinline__ void stage_x_finish(const XStage& st, const float* __restrict__ x, const float* __restrict__ norm_w, int K,
+__device__ __forceinline__ void stage_x_finish(const XStage& st, const XSource& xsrc, const float* __restrict__ norm_w, int K,
                                                uint8_t* smem, float* red /*[kMmaMaxWarps]*/) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     __half* xh = reinterpret_cast<__half*>(smem);
@@ -286,7 +319,7 @@ __device__ __forceinline__ void stage_x_finish(const XStage& st, const float* __
         if (e < K) ss += split_store4(st.v[i], st.w[i], e, xh, xl, xs, s32, __activemask());
     }
     for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        const float4 v = x_fetch4(xsrc, e);
         const float4 w = norm_w ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
         ss += split_store4(v, w, e, xh, xl, xs, s32, __activemask());
     }
@@ -688,14 +721,15 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     }
     // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
     XStage xst;
-    stage_x_load(xst, p.x, p.norm_w, K);
+    const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
+    stage_x_load(xst, xsrc, p.norm_w, K);
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
         if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
         cp_async_commit();
     }
     MMA_STAMP(2);
-    stage_x_finish(xst, p.x, p.norm_w, K, smem, s_red);
+    stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red);
     __syncthreads();
     const float unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
     MMA_STAMP(3);
@@ -726,7 +760,11 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
                 val = prev + p.expert_wt[p.expert_slot] * val;
                 if (p.residual) val += p.residual[j];
             }
-            sg.out[j] = val;
+            if (p.n_peer > 0) {
+                for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;  // partial of a row-parallel GEMV, to every rank
+            } else {
+                sg.out[j] = val;
+            }
         }
     };
 

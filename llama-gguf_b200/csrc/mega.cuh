@@ -28,7 +28,8 @@ enum : int { MEGA_LOGITS = 0, MEGA_PREFILL = 1, MEGA_GREEDY = 2 };
 
 struct MegaPhase {
     int kind;
-    int pad[3];
+    int tp_sync;   // tensor parallel: the phase wrote partial sums to the peers; exchange flags before the next one
+    int pad[2];
     MParams gemv;
     AttnParams attn;
 };
@@ -55,7 +56,42 @@ struct MegaParams {
     int max_generated;
     int hd, G;
     unsigned long long* dbg;  // optional [n_phases + 3] globaltimer stamps of CTA 0 for the LAST token of the launch
+    // tensor parallel: one megakernel per rank/GPU, partial sums and flags travel through peer memory (NVLink)
+    int tp_size, tp_rank;
+    int vocab_local;                          // rows of the vocab head owned by this rank (argmax offset = rank * vocab_local)
+    unsigned int* tp_flags;                   // local [tp_size]: slot r is written by rank r (monotonic epochs)
+    unsigned int* tp_peer_flags[kMmaMaxPeers];  // the same array on every rank, as mapped here
+    unsigned int tp_epoch0;                   // exchanges of this launch use epochs tp_epoch0 + 1, + 2, ...
+    float* tp_cand;                           // local [tp_size][2]: (best logit, global index as float bits) of every rank
+    float* tp_peer_cand[kMmaMaxPeers];
 };
+
+// Cross-GPU flag exchange after the local grid barrier: CTA 0 tells every peer "my partial sums of exchange `epoch`
+// are in your memory"; every CTA then waits until all ranks have said so.  Bounded spin.
+__device__ __forceinline__ bool tp_exchange(const MegaParams& mp, unsigned int epoch, int* s_flag) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < mp.tp_size)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[tid] + mp.tp_rank), "r"(epoch) : "memory");
+    if (tid == 0) {
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int r = 0; r < mp.tp_size && ok; r++) {
+            for (;;) {
+                unsigned int v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mp.tp_flags + r) : "memory");
+                if ((int)(v - epoch) >= 0) break;
+                if (clock64() - t0 > 3000000000LL) {
+                    ok = 0;
+                    atomicExch(mp.err, 3);
+                    break;
+                }
+            }
+        }
+        *s_flag = ok;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
 
 // Grid barrier on a monotonically increasing counter, split in two so that work that does not depend on other
 // CTAs (fetching the descriptor of a later phase) runs while thread 0 waits.  Release/acquire at gpu scope:
@@ -117,6 +153,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     fetch_desc(0);
     fetch_desc(1);
     long long gph = 0;  // phases executed so far in this launch
+    unsigned int tp_n = 0;  // cross-GPU exchanges so far in this launch
 
     for (int tok = 0; tok < mp.n_tokens; tok++) {
         // ---- embedding (LlamaModel::forward, model/llama.rs:293-306): CTA 0 dequantises row `token`, bit-exactly ----
@@ -166,17 +203,23 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                 const MegaPhase& nxt = s_phs[(gph + 1) % 3];
                 if (nxt.kind == PH_GEMV) mma_warm_l2<STAGES>(nxt.gemv, 4);
             }
+            const bool tp_sync = cur.tp_sync != 0;
+            if (tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
+                __syncthreads();
+                if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            }
             grid_arrive(mp.bar, target);
             fetch_desc(gph + 2);
             if (!grid_wait(mp.bar, target, mp.err, &s_flag)) return;
+            if (tp_sync && !tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag)) return;
             if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[1 + ph] = gtimer();
         }
 
         if (mp.mode != MEGA_GREEDY) continue;
         // ---- greedy pick on the device: raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821) ----
         {
-            const int per = (mp.vocab + gridDim.x - 1) / gridDim.x;
-            const int lo = blockIdx.x * per, hi = min(mp.vocab, lo + per);
+            const int per = (mp.vocab_local + gridDim.x - 1) / gridDim.x;
+            const int lo = blockIdx.x * per, hi = min(mp.vocab_local, lo + per);
             float best = -INFINITY;
             int bi = -1;
             for (int i = lo + tid; i < hi; i += NW * 32) {
@@ -199,6 +242,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
             }
         }
         if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
+        const unsigned int cand_epoch = mp.tp_epoch0 + (mp.tp_size > 1 ? ++tp_n : 0u);  // uniform over the grid
         if (blockIdx.x == 0) {
             if (warp == 0) {
                 float best = -INFINITY;
@@ -213,6 +257,44 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                }
+                if (mp.tp_size > 1) {  // every rank picks the same winner among the per-rank candidates (ties: largest index)
+                    bi += mp.tp_rank * mp.vocab_local;
+                    if (lane < mp.tp_size) {
+                        float* dst = mp.tp_peer_cand[lane] + 2 * mp.tp_rank;
+                        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(best) : "memory");
+                        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + 1), "f"(__int_as_float(bi)) : "memory");
+                    }
+                    __syncwarp();
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                    const unsigned int epoch = cand_epoch;
+                    if (lane < mp.tp_size)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[lane] + mp.tp_rank), "r"(epoch) : "memory");
+                    const long long t0 = clock64();
+                    bool ok = true;
+                    if (lane < mp.tp_size) {
+                        for (;;) {
+                            unsigned int v;
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mp.tp_flags + lane) : "memory");
+                            if ((int)(v - epoch) >= 0) break;
+                            if (clock64() - t0 > 3000000000LL) { ok = false; atomicExch(mp.err, 3); break; }
+                        }
+                    }
+                    __syncwarp();
+                    best = -INFINITY;
+                    bi = -1;
+                    if (ok && lane < mp.tp_size) {
+                        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(best) : "l"(mp.tp_cand + 2 * lane) : "memory");
+                        float fi;
+                        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(fi) : "l"(mp.tp_cand + 2 * lane + 1) : "memory");
+                        bi = __float_as_int(fi);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                    }
                 }
                 if (lane == 0) {
                     mp.st->token = bi;
