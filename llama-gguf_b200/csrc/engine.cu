@@ -418,7 +418,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     CU_ALLOC(cudaMalloc((void**)&c->tickets, nkv * sizeof(unsigned int)));
     CU(cudaMemset(c->tickets, 0, nkv * sizeof(unsigned int)));
     CU_ALLOC(cudaMalloc((void**)&c->mma_part, (size_t)c->n_sm * kMmaMaxWarps * 2 * 32 * sizeof(float)));
-    c->mma_tickets_n = (int)((std::max<uint64_t>(std::max<uint64_t>(V, ffn_w), (nh + 2 * nkv) * hd) + 15) / 16 + 8);
+    c->mma_tickets_n = (int)((std::max<uint64_t>(std::max<uint64_t>(V, 2 * ffn_w), (nh + 2 * nkv) * hd) + 15) / 16 + 8);
     CU_ALLOC(cudaMalloc((void**)&c->mma_tickets, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
     CU(cudaMemset(c->mma_tickets, 0, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
     CU_ALLOC(cudaMalloc((void**)&c->mma_err, sizeof(int)));

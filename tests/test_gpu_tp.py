@@ -33,6 +33,16 @@ def _worker(rank, world, port, mix, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
+        _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np)
+    except Exception as e:  # the parent must not wait for a result that will never come
+        q.put({"rank": rank, "error": repr(e)})
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np):
+    if True:
         arch, desc, tensors = synth.synth_model("llama-tiny", mix, 64)
         tp = TensorParallelInference(desc, tensors, device=rank)
         prompt = synth.prompt_tokens(6, desc["vocab"])
@@ -55,8 +65,6 @@ def _worker(rank, world, port, mix, q):
             single.close()
         tp.close()
         q.put(out)
-    finally:
-        dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("mix", ["Q4_K_M", "Q8_0"])
@@ -75,7 +83,8 @@ def test_tp2_matches_single_gpu_and_oracle(b200, mix):
         p.start()
     outs = {}
     for _ in range(2):
-        o = q.get(timeout=600)
+        o = q.get(timeout=240)
+        assert "error" not in o, o
         outs[o["rank"]] = o
     for p in procs:
         p.join(timeout=120)
