@@ -141,6 +141,7 @@ B200_API int b200_decode_greedy(b200_ctx* ctx, int seq, uint32_t first_token, in
 B200_API int b200_get_hidden(b200_ctx* ctx, int seq, int layer, float* out);
 /* Debug: per-phase globaltimer stamps of the per-token megakernel (first call arms them; see csrc/mega.cuh). */
 B200_API int b200_debug_mega_timeline(b200_ctx* ctx, unsigned long long* out, int max_n);
+B200_API int b200_debug_read(b200_ctx* ctx, int which, float* out, int n);
 B200_API int b200_debug_mega_phase(b200_ctx* ctx, int phase, unsigned long long* out, int max_n);
 /* Statistics for bench.py: kernels launched by this library since creation. */
 B200_API int b200_ctx_stats(b200_ctx* ctx, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos);

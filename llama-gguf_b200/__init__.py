@@ -21,7 +21,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllama_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libllama_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 # ggml type ids (src/gguf/constants.rs:56-89)
@@ -110,6 +110,10 @@ def lib():
     L.b200_ctx_tp_set_peer.argtypes = [vp, C.c_int, vp]
     L.b200_debug_mega_timeline.argtypes = [vp, u64p, C.c_int]
     L.b200_debug_mega_phase.argtypes = [vp, C.c_int, u64p, C.c_int]
+    try:
+        L.b200_debug_read.argtypes = [vp, C.c_int, fp, C.c_int]
+    except AttributeError:  # an older build of the library (B200_LIB override)
+        pass
     L.b200_bench_weight_gemv.argtypes = [vp, C.c_char_p, C.c_int, fp, u64p]
     L.b200_bench_gemv_pass.argtypes = [vp, C.c_int, C.c_int, fp, u64p, u64p]
     L.b200_op_add.argtypes = [fp, fp, fp, C.c_size_t]

@@ -876,6 +876,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
     mp.generated = sl.d_generated; mp.max_generated = kMaxGenerated;
     mp.hd = d.head_dim; mp.G = d.n_heads / d.n_kv_heads;
     mp.dbg = c->mega_dbg;
+    mp.early = env_int("B200_MEGA_EARLY", 1);
     mp.tp_size = c->par.world_size; mp.tp_rank = c->par.rank; mp.vocab_local = c->vocab_l;
     if (c->par.world_size > 1) {
         mp.tp_flags = tp_flags(c, c->tp_region);
@@ -1119,6 +1120,16 @@ extern "C" int b200_debug_mega_phase(b200_ctx* c, int phase, unsigned long long*
     const int m = (int)std::min<size_t>(n, (size_t)max_n);
     if (out) cudaMemcpy(out, buf, (size_t)m * 8, cudaMemcpyDeviceToHost);
     return m;
+}
+
+// Debug: copy one of the activation buffers to the host (0 xa, 1 xb, 2 qkv, 3 attn, 4 hbuf, 5 logits).
+extern "C" int b200_debug_read(b200_ctx* c, int which, float* out, int n) {
+    if (!c || !out) return 0;
+    cudaSetDevice(c->par.device);
+    cudaStreamSynchronize(c->stream);
+    const float* src[6] = {c->xa, c->xb, c->qkv, c->attn, c->hbuf, c->logits};
+    if (which < 0 || which > 5) return 0;
+    return cudaMemcpy(out, src[which], (size_t)n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? n : 0;
 }
 
 extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos) {

@@ -594,9 +594,15 @@ struct MCursor {
 //   s_red  : [2 * kMmaMaxWarps] floats, s_part: [kMmaMaxWarps][2][32] floats (static shared memory of the caller)
 //   pdl    : the launch is part of a programmatic-dependent-launch chain (griddepcontrol at the right place)
 //   warm_l2: pull the first stages towards L2 before anything that depends on the previous kernel
-template <int STAGES>
-__device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, float* s_red, float (*s_part)[2][32], bool pdl,
-                                             bool warm_l2) {
+//   pre()  : runs first (megakernel: __syncthreads + arrive at the grid barrier that ends the previous phase)
+//   post() : runs after the prologue, before anything that depends on other CTAs / the previous kernel
+//            (megakernel: wait at that barrier; stand-alone kernel: griddepcontrol)
+//   early  : issue the first ring stages with cp.async BEFORE post() (weights never depend on a predecessor), so
+//            they land while the barrier is being waited for; otherwise they are issued after the x loads
+template <int STAGES, class Pre, class Post>
+__device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, float* s_red, float (*s_part)[2][32], Pre pre_fn,
+                                             Post post_fn, bool early, bool warm_l2) {
+    pre_fn();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nw = blockDim.x >> 5;
     const int K = p.K;
@@ -702,17 +708,24 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         cur_init(cp, u0);
         cc = cp;
         prod_run();
-        if (warm_l2) {
+        if (early) {
+#pragma unroll
+            for (int k = 0; k < STAGES - 1; k++) {
+                if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
+                cp_async_commit();
+            }
+        } else if (warm_l2) {
             for (int k = 0; k < pre; k++) issue(0, true);
             cp = cc;
             prod_run();
         }
+    } else if (early && !p.expert_sel) {
+#pragma unroll
+        for (int k = 0; k < STAGES - 1; k++) cp_async_commit();
     }
+    const bool issued_early = early && !p.expert_sel;
 
-    if (pdl) {
-        pdl_launch_dependents();
-        pdl_wait();
-    }
+    post_fn();
     MMA_STAMP(1);
 
     if (p.expert_sel) {
@@ -723,10 +736,12 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     XStage xst;
     const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
     stage_x_load(xst, xsrc, p.norm_w, K);
+    if (!issued_early) {
 #pragma unroll
-    for (int k = 0; k < STAGES - 1; k++) {
-        if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
-        cp_async_commit();
+        for (int k = 0; k < STAGES - 1; k++) {
+            if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
+            cp_async_commit();
+        }
     }
     MMA_STAMP(2);
     stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red);
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const __
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
     __shared__ float s_part[kMmaMaxWarps][2][32];   // pieces of tiles shared between warps of this CTA
-    mma_gemv_cta<STAGES>(p, smem, s_red, s_part, true, true);
+    mma_gemv_cta<STAGES>(p, smem, s_red, s_part, [] {}, [] { pdl_launch_dependents(); pdl_wait(); }, false, true);
 }
 
 // ---------------------------------------------------------------- host-side launch planning

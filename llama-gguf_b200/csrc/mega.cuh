@@ -55,6 +55,7 @@ struct MegaParams {
     int* generated;
     int max_generated;
     int hd, G;
+    int early;                // issue a GEMV phase's first weight copies before waiting at the barrier that precedes it
     unsigned long long* dbg;  // optional [n_phases + 3] globaltimer stamps of CTA 0 for the LAST token of the launch
     // tensor parallel: one megakernel per rank/GPU, partial sums and flags travel through peer memory (NVLink)
     int tp_size, tp_rank;
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     };
     fetch_desc(0);
     fetch_desc(1);
+    __syncthreads();  // phase 0 looks at its descriptor before it reaches a barrier
     long long gph = 0;  // phases executed so far in this launch
     unsigned int tp_n = 0;  // cross-GPU exchanges so far in this launch
 
@@ -172,14 +174,36 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                 mp.st->pos_next = pn + 1;
             }
         }
-        if (!grid_barrier(mp.bar, target, mp.err, &s_flag)) return;
-        if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[0] = gtimer();
+        // Every phase BEGINS with the grid barrier that ends its predecessor (the first one: the embedding).  A GEMV
+        // phase arrives, then deals its units and issues its first weight copies, and only then waits: the copies
+        // and the descriptor fetch overlap the barrier latency.
+        bool ok = true;
+        bool prev_tp_sync = false;   // the predecessor left partial sums in peer memory
+        int stamp = 0;
+        auto bar_arrive = [&]() {
+            if (prev_tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
+                __syncthreads();
+                if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            }
+            grid_arrive(mp.bar, target);
+        };
+        auto bar_wait = [&]() {
+            fetch_desc(gph + 2);
+            ok = grid_wait(mp.bar, target, mp.err, &s_flag);
+            if (ok && prev_tp_sync) ok = tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag);
+            if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[stamp] = gtimer();
+            stamp++;
+        };
 
         for (int ph = 0; ph < n_run; ph++, gph++) {
             const MegaPhase& cur = s_phs[gph % 3];
             if (cur.kind == PH_GEMV) {
-                mma_gemv_cta<STAGES>(cur.gemv, smem, s_red, s_part, false, false);
+                mma_gemv_cta<STAGES>(cur.gemv, smem, s_red, s_part, bar_arrive, bar_wait, mp.early != 0, false);
+                if (!ok) return;
             } else {
+                bar_arrive();
+                bar_wait();
+                if (!ok) return;
                 const AttnParams& ap = cur.attn;
                 const int kv_len = *ap.pos + 1;
                 const int n_items = ap.n_kv * ap.n_splits;
@@ -196,24 +220,14 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                     __syncthreads();
                 }
             }
-            // keep HBM busy across the barrier: the first units of the next GEMV go towards L2 now (its descriptor
-            // is already in the ring)
-            const bool more = (ph + 1 < n_run) || (tok + 1 < mp.n_tokens);
-            if (more) {
-                const MegaPhase& nxt = s_phs[(gph + 1) % 3];
-                if (nxt.kind == PH_GEMV) mma_warm_l2<STAGES>(nxt.gemv, 4);
-            }
-            const bool tp_sync = cur.tp_sync != 0;
-            if (tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
-                __syncthreads();
-                if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
-            }
-            grid_arrive(mp.bar, target);
-            fetch_desc(gph + 2);
-            if (!grid_wait(mp.bar, target, mp.err, &s_flag)) return;
-            if (tp_sync && !tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag)) return;
-            if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[1 + ph] = gtimer();
+            prev_tp_sync = cur.tp_sync != 0;
         }
+        // the barrier that ends the last phase of the token
+        gph--;  // fetch_desc(gph + 2) inside bar_wait: keep the ring consistent with the loop above
+        bar_arrive();
+        bar_wait();
+        gph++;
+        if (!ok) return;
 
         if (mp.mode != MEGA_GREEDY) continue;
         // ---- greedy pick on the device: raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821) ----
