@@ -713,6 +713,11 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
 // ------------------------------------------------------------------ per-token megakernel (mega.cuh)
 constexpr int kMegaStages = 2;
 
+static const void* mega_kernel_for(int hd, int G) {
+    if (hd == 128) return G <= 4 ? (const void*)mega_decode_kernel<kMegaStages, 128, 4> : (const void*)mega_decode_kernel<kMegaStages, 128, 8>;
+    return G <= 4 ? (const void*)mega_decode_kernel<kMegaStages, 64, 4> : (const void*)mega_decode_kernel<kMegaStages, 64, 8>;
+}
+
 // Builds the phase program of every slot.  Leaves mega_ok = false (graph path) when a launch is not eligible:
 // MoE, taps, a weight type/shape the tensor-pipe GEMV does not take, or a shape that does not fit shared memory.
 static int mega_build(b200_ctx* c) {
@@ -855,9 +860,10 @@ static int mega_build(b200_ctx* c) {
     }
     if (smem > lim) return B200_OK;
     c->mega_smem = smem;
-    CU(cudaFuncSetAttribute(mega_decode_kernel<kMegaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    const void* kern = mega_kernel_for(hd, G);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<kMegaStages>, kMmaMaxWarps * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMmaMaxWarps * 32, smem));
     if (per_sm < 1) return B200_OK;
     c->mega_ok = true;
     return B200_OK;
@@ -891,7 +897,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
     }
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
     void* args[] = {&mp};
-    CU(cudaLaunchCooperativeKernel((void*)mega_decode_kernel<kMegaStages>, dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
+    CU(cudaLaunchCooperativeKernel(mega_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
                                    c->mega_smem, c->stream));
     c->launches += 1;
     c->mega_launches += 1;

@@ -127,7 +127,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& ta
     return grid_wait(bar, target, err, s_flag);
 }
 
-template <int STAGES>
+// One instantiation per attention shape (head_dim, query heads per kv head rounded up to 4 / 8): a model only ever
+// runs one of them, and the kernel's code footprint matters (every phase starts on a cold instruction path).
+template <int STAGES, int HD, int GMAX>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const __grid_constant__ MegaParams mp) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
@@ -210,13 +212,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                     const int kh = item / ap.n_splits, split = item - kh * ap.n_splits;
                     float* sm = reinterpret_cast<float*>(smem);
-                    if (mp.hd == 128) {
-                        if (mp.G <= 4) attn_decode_item<128, 4, NW>(ap, kh, split, kv_len, sm, &s_ticket);
-                        else attn_decode_item<128, 8, NW>(ap, kh, split, kv_len, sm, &s_ticket);
-                    } else {
-                        if (mp.G <= 4) attn_decode_item<64, 4, NW>(ap, kh, split, kv_len, sm, &s_ticket);
-                        else attn_decode_item<64, 8, NW>(ap, kh, split, kv_len, sm, &s_ticket);
-                    }
+                    attn_decode_item<HD, GMAX, NW>(ap, kh, split, kv_len, sm, &s_ticket);
                     __syncthreads();
                 }
             }
