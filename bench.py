@@ -247,6 +247,7 @@ def main():
     l0 = gpu.stats()["kernel_launches"]
     kv_len_mid = gpu.position() + args.steps // 2
     toks, ms = gpu.decode_greedy(tok, args.steps)
+    toks_head = toks[:8]
     torch.cuda.synchronize()
     launches = gpu.stats()["kernel_launches"] - l0
     tok = int(toks[-1])
@@ -314,7 +315,8 @@ def main():
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": desc["vocab"] * 4},
            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "weight_bytes_per_token": wbytes, "kv_bytes_per_token_at_mid": kvpp * kv_len_mid}
+           "weight_bytes_per_token": wbytes, "kv_bytes_per_token_at_mid": kvpp * kv_len_mid,
+           "greedy_tokens_head": [int(t) for t in toks_head]}
     print(json.dumps(out))
     gpu.close()
     return 0

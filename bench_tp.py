@@ -54,6 +54,7 @@ def main(args, preset, config, rank, world, local_rank):
     l0 = tp.stats()["kernel_launches"]
     kv_len_mid = tp.position() + args.steps // 2
     toks, ms = tp.decode_greedy(tok, args.steps)
+    toks_head = toks[:8]
     torch.cuda.synchronize()
     dist.barrier()
     launches = tp.stats()["kernel_launches"] - l0
@@ -89,7 +90,8 @@ def main(args, preset, config, rank, world, local_rank):
                "e2e": {"value": args.steps / e2e_s, "unit": BM.UNIT, "h2d_bytes_per_step": 4 * world,
                        "d2h_bytes_per_step": desc["vocab"] * 4},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
-               "weight_bytes_per_token_per_rank": wbytes_local, "kv_bytes_per_token_at_mid_per_rank": kvpp_local * kv_len_mid}
+               "weight_bytes_per_token_per_rank": wbytes_local, "kv_bytes_per_token_at_mid_per_rank": kvpp_local * kv_len_mid,
+               "greedy_tokens_head": [int(t) for t in toks_head]}
         print(json.dumps(out))
     tp.close()
     dist.barrier()

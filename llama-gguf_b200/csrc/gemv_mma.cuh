@@ -7,38 +7,38 @@
 // Fused around it: RMSNorm of x (simd.rs:847-899), +bias (layers.rs:68-74), +residual
 // (layers.rs:1202-1241), silu(gate)*up (simd.rs:598-649), out += w_e*y (moe.rs:363-368).
 //
-// Why this shape (profiles/r01_v1_*: the CUDA-core version spent ~6 issue slots per weight
-// and stalled at 1.2 TB/s):
-//  * weights go HBM -> shared memory with 16-byte cp.async (SASS LDGSTS) into PER-WARP rings.
-//    A unit is 16 rows x 256 elements (one K-quant super-block per row); a lane moves 16-byte pieces of two rows, so an
-//    instruction covers 8 rows x 64 contiguous bytes and costs no address arithmetic.  (Per-row
-//    cp.async.bulk copies measured slower: UBLKCP is issued one lane at a time, ~10 issue slots
-//    per 288-byte copy, profiles/r01_v2_*.)  A warp produces and consumes its own ring, so
-//    there is no cross-warp hand-off and the first stages are issued BEFORE
-//    griddepcontrol.wait (weights never depend on the previous kernel of the token);
-//  * dot products run on the tensor pipe (mma.sync.m16n8k16, SASS HMMA): quants become exact
-//    fp16 integers with one LOP3/PRMT per two elements ((w & 0x000F000F) | 0x6400_6400 =
-//    1024+q), x is split into fp16 hi + lo parts (x = hi + lo to 2^-22) that sit in two
-//    columns of the B operand, accumulation is f32.  Block scales / mins are applied in f32
-//    to per-sub-block sums (the reference's separated form, simd.rs:1006-1013); the integer
-//    bias (1024, +32 for Q6_K, +128 for Q8_0) is removed with per-16-element sums of x.  The
-//    8 columns of the MMA are used as 4 (hi, lo) pairs: the B operand is zero except in the
-//    pair of the sub-block a lane's k-slots belong to, so each sub-block's sum lands in the
-//    lane that decoded its scale and nothing is shuffled until a tile is finished;
-//  * stream-K: all (tile, chunk) units of a launch are dealt evenly, in contiguous runs, to the
-//    warps of a persistent grid (one CTA per SM, up to 16 warps).  Tiles cut across warps are
-//    merged through shared memory inside a CTA and through a small global scratch + ticket
-//    across CTAs, always in a fixed order (run-to-run deterministic).
-//
-// ~1.3 issue slots per weight (Q4_K) instead of ~6; see DESIGN.md for the budget.
+// Second generation (profiles/r01_mega_ncu_full.md: the fp16 HMMA version spent 4.1 thread-instructions per
+// weight, half of them outside the dot products, and the token was issue-bound):
+//  * the dot products are INTEGER tensor-pipe MMAs (mma.sync.m16n8k32 u8 x s8 -> s32, SASS IMMA.16832):
+//    a 32-bit word of nibbles becomes four A-operand quants with ONE LOP3 (w & 0x0F0F0F0F; the high nibbles are
+//    w & 0xF0F0F0F0 = 16 q, the 1/16 goes into the scale), i.e. 0.25 instructions per weight for the unpack
+//    instead of 0.5 + the fp16 bias handling;
+//  * x is staged once per launch as three int8 planes: every 32 elements are scaled by their own power of two so
+//    that the largest is in [2^20, 2^21), rounded to an integer and cut into signed bytes hi/mid/lo
+//    (x_int = 65536 hi + 256 mid + lo, 21-22 significant bits relative to the group's largest element, the sums
+//    are exact in s32).  The 8 columns of an MMA carry (hi, mid) pairs of FOUR sub-blocks, a second accumulator
+//    the lo bytes; the B operand is zero except in the columns of the sub-block a lane's k-slots belong to, so
+//    each sub-block's sums land in the lane that decodes its scale and nothing is shuffled until a tile is done;
+//  * block scales / mins are applied in f32 to per-sub-block sums (the reference's separated form
+//    d*sc*sum(q x) - dmin*m*sum(x), simd.rs:1006-1013); 6-bit scales are unpacked for two rows at a time and
+//    converted with PRMT into the mantissa of 2^23 (no I2F);
+//  * a unit is 32 rows x 256 elements: per-unit overhead (producer, B-operand loads, loop) is paid once per
+//    8192 weights, and a finished tile is 32 consecutive outputs in one warp (one x-scale group of the next GEMV);
+//  * weights go HBM -> shared memory with 16-byte cp.async (SASS LDGSTS) into PER-WARP rings of 2-4 stages; a warp
+//    produces and consumes its own ring (no cross-warp hand-off) and the first stages are issued BEFORE the
+//    dependency wait (weights never depend on the previous kernel / phase of the token);
+//  * stream-K: all (tile, chunk) units of a launch are dealt evenly, in contiguous runs, to the warps of a
+//    persistent grid (one CTA per SM, 8 warps).  Tiles cut across warps are merged through shared memory inside a
+//    CTA and through a small global scratch + ticket across CTAs, always in a fixed order (deterministic).
 #pragma once
 #include "common.cuh"
 #include "quant.cuh"
 
 namespace b200 {
 
-constexpr int kMmaMaxWarps = 16;
+constexpr int kMmaMaxWarps = 8;    // warps per CTA (the per-token megakernel uses the same block size)
 constexpr int kMmaMaxStages = 4;
+constexpr int kMmaRows = 32;       // rows per tile / unit (two m16 MMA row blocks)
 
 enum : int { ME_STORE = 0, ME_RESIDUAL = 1, ME_SWIGLU = 2, ME_SCALED_ACC = 3 };
 
@@ -53,7 +53,7 @@ struct MSeg {
     long long expert_stride;
     int type;
     int n_rows;
-    int n_tiles;           // ceil(n_rows / 16)
+    int n_tiles;           // ceil(n_rows / 32)
     int unit0;             // first unit of this segment in the launch
     int row_stride;        // pitch of the row slots of a ring stage
     int cb;                // blocks per unit
@@ -69,12 +69,12 @@ struct MParams {
     int chunks;            // ceil(K / 256)
     int units_per_tile;    // chunks (2*chunks for ME_SWIGLU: gate chunks then up chunks)
     int total_units;
-    // dealing: CTA b < n_ctas owns `cbase` (+1 for b < crem) consecutive units (tile_mode 0) or whole 16-row tiles
+    // dealing: CTA b < n_ctas owns `cbase` (+1 for b < crem) consecutive units (tile_mode 0) or whole 32-row tiles
     // (tile_mode 1: no tile straddles two CTAs, so nothing is merged through global memory); its warps split the
     // CTA's units evenly
     int n_ctas, tile_mode, cbase, crem;
     int stages;
-    int stage_bytes;       // 16 * max row_stride
+    int stage_bytes;       // 32 * max row_stride
     const float* x;        // [K] f32
     const float* norm_w;   // optional fused RMSNorm weight [K]
     float eps;
@@ -95,9 +95,9 @@ struct MParams {
     float* peer_out[kMmaMaxPeers];
     int n_peer;
     // cross-CTA merge scratch
-    float* part;             // [grid][2][32]
+    float* part;             // [grid][2][2][32]
     unsigned int* tickets;   // [total logical tiles], zero between launches
-    int* err;                // device error flag (unused by the cp.async pipeline; kept for the watchdog ABI)
+    int* err;                // device error flag (kept for the watchdog ABI)
     unsigned long long* dbg; // optional [grid*warps][8] globaltimer stamps (lab only)
 };
 
@@ -140,18 +140,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-    asm(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(mask), "r"(orv));  // (a & mask) | orv
-    return r;
-}
 // Shared-memory loads are NOT volatile so that ptxas/nvcc may interleave them with the MMAs of neighbouring
 // blocks.  Ordering against the cp.async pipeline comes from data dependencies: every address is derived from an
 // opaque token produced after the wait (smem_token), and the unit's results are pinned before the stage is refilled.
@@ -160,7 +148,7 @@ __device__ __forceinline__ uint32_t smem_token() {
     asm volatile("mov.u32 %0, 0;" : "=r"(t)::"memory");
     return t;
 }
-__device__ __forceinline__ void pin2(float& a, float& b) { asm volatile("" : "+f"(a), "+f"(b)::"memory"); }
+__device__ __forceinline__ void pin4(float (&a)[4]) { asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3])::"memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -191,60 +179,81 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
-// 16 bytes at a 2-byte-aligned shared address: 5 aligned words + funnel shifts (shift 0 or 16)
-__device__ __forceinline__ void lds_piece16(uint32_t a, uint32_t (&o)[4]) {
+// 8 bytes at a 2-byte-aligned shared address, whatever the residue: 3 aligned words + funnel shifts
+__device__ __forceinline__ void lds_piece8_any(uint32_t a, uint32_t& o0, uint32_t& o1) {
     const uint32_t base = a & ~3u, sh = (a & 3u) << 3;
-    const uint32_t w0 = lds32(base), w1 = lds32(base + 4), w2 = lds32(base + 8), w3 = lds32(base + 12), w4 = lds32(base + 16);
-    o[0] = __funnelshift_r(w0, w1, sh);
-    o[1] = __funnelshift_r(w1, w2, sh);
-    o[2] = __funnelshift_r(w2, w3, sh);
-    o[3] = __funnelshift_r(w3, w4, sh);
+    const uint32_t w0 = lds32(base), w1 = lds32(base + 4), w2 = lds32(base + 8);
+    o0 = __funnelshift_r(w0, w1, sh);
+    o1 = __funnelshift_r(w1, w2, sh);
 }
-// 4 bytes at a 2-byte-aligned shared address
-__device__ __forceinline__ uint32_t lds32_a2(uint32_t a) {
-    const uint32_t base = a & ~3u, sh = (a & 3u) << 3;
-    return __funnelshift_r(lds32(base), lds32(base + 4), sh);
+// 8 bytes at a shared address whose alignment class is known at compile time (AL = 8, 4, or anything even)
+template <int AL>
+__device__ __forceinline__ void lds_piece8(uint32_t a, uint32_t& o0, uint32_t& o1) {
+    if (AL == 8) {
+        const uint2 v = lds64(a);
+        o0 = v.x;
+        o1 = v.y;
+    } else if (AL == 4) {
+        o0 = lds32(a);
+        o1 = lds32(a + 4);
+    } else {
+        lds_piece8_any(a, o0, o1);
+    }
 }
 
-// Quants as fp16 operands: the integer q sits in the low mantissa bits of an fp16 with a zero exponent field,
-// i.e. it IS the subnormal q * 2^-24 -- no magic-number offset (the classic 0x6400 | q = 1024 + q form makes the
-// f32 accumulator carry 1024 * sum(x) and costs ~7 bits: measured 3e-5 vs 1e-6 relative error).  The 2^24 is
-// folded into the final scale and into the staged sums of x ("operand units").
-constexpr uint32_t kMagic = 0u;
-constexpr uint32_t kMagicB = 0u;                      // PRMT filler byte
-constexpr float kXsScale = 5.9604644775390625e-08f;   // 2^-24
-constexpr float kUnscale = 16777216.0f;               // 2^24
+// Integer tensor-pipe MMAs (SASS IMMA.16832): D[16x8] += A[16x32] * B[32x8], s32 accumulators.
+// Fragments (lane = 4n + t): a0 = A[n][4t..4t+3], a1 = A[n+8][4t..], a2 = A[n][16+4t..], a3 = A[n+8][16+4t..];
+// b0 = B[4t..4t+3][n], b1 = B[16+4t..][n]; d0 = D[n][2t], d1 = D[n][2t+1], d2 = D[n+8][2t], d3 = D[n+8][2t+1].
+__device__ __forceinline__ void imma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// first MMA of a chain: C = 0 (no accumulator initialisation instructions)
+__device__ __forceinline__ void imma_u8s8_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+__device__ __forceinline__ void imma_s8s8_z(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+__device__ __forceinline__ void imma_s8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 // ---------------------------------------------------------------- x in shared memory
-// fp16 hi and lo parts (x ~= hi + lo), stored so that the 4 elements starting at e (e % 4 == 0)
-// read as one 8-byte word give the m16n8k16 B fragment of a lane whose four k-slots come from one
-// 32-bit word of quants: order [x0, x2, x1, x3] (bytes 0,2 -> k-slots 2t,2t+1; bytes 1,3 -> 2t+8,2t+9).
-// xs16[i] = sum of float(hi)+float(lo) over elements 16i..16i+15.
-struct XSmem {
-    uint32_t xh, xl, xs;  // shared-space byte addresses: hi halves, lo halves, per-16 sums
-    uint32_t s32;         // per-32-element scale 2^-k of the staged values
-    uint32_t zero;        // 256 bytes of zeros: the B operand of lanes whose column pair is not addressed
+// Three int8 planes p0 (hi), p1 (mid), p2 (lo): x[e] * 2^k(e/32) rounded to an integer = 65536 p0 + 256 p1 + p2, natural
+// element order (4 consecutive elements = one 32-bit word = the four k-slots of an MMA fragment register).
+//   sx[i]  = {2^-k, sum of the 32 elements of group i (true units)}   (float2 per 32 elements)
+//   x16[i] = -32 * sum of elements 16i..16i+15 (true units; Q6_K's offset)
+// The plane bases are 0 / 32 / 64 (mod 128) bytes so that hi / mid / lo loads of one instruction use different banks;
+// 256 zero bytes serve as the B operand of lanes whose columns an MMA does not address.
+struct XLayout {
+    uint32_t p0, p1, p2, sx, x16, zero, total;
 };
-__host__ __device__ __forceinline__ int xperm(int e) { return (e & ~3) | (((e & 1) << 1) | ((e >> 1) & 1)); }
-// the lo array sits 64 bytes off a multiple of 128 from the hi array: the hi and lo lanes of a B-fragment
-// load hit different banks
-constexpr uint32_t kXlPad = 64;
-// hi[K] + pad + lo[K] halves, xs16[K/16] floats, s32[K/32] floats, 256 zero bytes
-__host__ __device__ inline size_t x_smem_bytes(int K) {
-    return (((size_t)4 * K + kXlPad + (size_t)(K >> 2) + (size_t)(K >> 3) + 127) & ~(size_t)127) + 256;
+__host__ __device__ inline XLayout x_layout(int K) {
+    const uint32_t KP = ((uint32_t)K + 127u) & ~127u;
+    XLayout L;
+    L.p0 = 0;
+    L.p1 = KP + 32;
+    L.p2 = 2 * KP + 192;
+    L.sx = 3 * KP + 384;
+    L.x16 = L.sx + (uint32_t)K / 4;                       // K/32 float2
+    L.zero = ((L.x16 + (uint32_t)K / 4 + 127u) & ~127u) + 96;   // K/16 floats
+    L.total = ((L.zero + 256u + 127u) & ~127u);
+    return L;
 }
+__host__ __device__ inline size_t x_smem_bytes(int K) { return x_layout(K).total; }
 
-// x staging, all threads of the CTA, K % 32 == 0, ONE pass and one __syncthreads (by the caller):
-//   y = x * w (w: optional RMSNorm weight; the scalar 1/rms is applied to the finished dot products instead of
-//   to every element -- (x*inv)*w in the reference, simd.rs:891-892, differs by one rounding);
-//   every 32 elements are scaled by their own power of two 2^k (exact) so that the largest sits near 2^12, then
-//   split into fp16 hi + lo: ~22 significant bits relative to the largest element of the group, whatever |x|;
-//   xs16 = sums of the true values (in operand units, x 2^-24), s32 = 2^-k, red[warp] = partial sum of x^2.
-// stage_x_load issues the global loads (first kXRegs float4 per thread) BEFORE the caller issues weight copies.
-constexpr int kXRegs = 4;
-struct XStage {
-    float4 v[kXRegs], w[kXRegs];
+struct XSmem {
+    uint32_t p0, p1, p2, sx, x16, zero;  // shared-space byte addresses
 };
+
 // One float4 of the GEMV input: plain x, or (tensor parallel) the rank-ordered sum of the partial vectors + residual
 struct XSource {
     const float* x;
@@ -267,6 +276,17 @@ __device__ __forceinline__ float4 x_fetch4(const XSource& xs, int e) {
     if (xs.x_full_out && blockIdx.x == 0) *reinterpret_cast<float4*>(xs.x_full_out + e) = a;
     return a;
 }
+
+// x staging from f32, all threads of the CTA, K % 32 == 0, ONE pass and one __syncthreads (by the caller):
+//   y = x * w (w: optional RMSNorm weight; the scalar 1/rms is applied to the finished dot products instead of
+//   to every element -- (x*inv)*w in the reference, simd.rs:891-892, differs by one rounding);
+//   the 8 threads that hold a group of 32 agree on its power of two (largest element -> [2^20, 2^21)), round with
+//   the 1.5*2^23 trick (the integer appears in the mantissa), and cut it into three signed bytes by adding
+//   0x808080 and flipping the three sign bits; red[warp] = partial sum of x^2 (before the weight).
+constexpr int kXRegs = 4;
+struct XStage {
+    float4 v[kXRegs], w[kXRegs];
+};
 __device__ __forceinline__ void stage_x_load(XStage& st, const XSource& xs, const float* __restrict__ norm_w, int K) {
     const int tid = threadIdx.x, nthr = blockDim.x;
 #pragma unroll
@@ -276,58 +296,69 @@ __device__ __forceinline__ void stage_x_load(XStage& st, const XSource& xs, cons
         st.w[i] = (norm_w && e < K) ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
 }
-__device__ __forceinline__ float split_store4(float4 v, float4 w, int e, __half* xh, __half* xl, float* xs, float* s32, unsigned mask) {
+// the scale group's exponent: k such that am * 2^k is in [2^20, 2^21)
+__device__ __forceinline__ int x_group_k(float am) {
+    int k = 0;
+    if (am > 0.0f && am < 3.0e38f) k = min(max(147 - (int)((__float_as_uint(am) >> 23) & 0xFFu), -100), 100);
+    return k;
+}
+__device__ __forceinline__ float split_store4(float4 v, float4 w, int e, uint8_t* xb, const XLayout& L, unsigned mask) {
     const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
     float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
     am = fmaxf(am, __shfl_xor_sync(mask, am, 1));
     am = fmaxf(am, __shfl_xor_sync(mask, am, 2));
     am = fmaxf(am, __shfl_xor_sync(mask, am, 4));
-    int k = 0;
-    if (am > 0.0f && am < 3.0e38f) k = min(max(138 - (int)((__float_as_uint(am) >> 23) & 0xFFu), -100), 100);  // 12 - (exp - 126)
+    const int k = x_group_k(am);
     const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23);
-    v.x *= up; v.y *= up; v.z *= up; v.w *= up;
-    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-    const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
-    const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
-    uint2 ph, pl;  // stored order [x0, x2, x1, x3]
-    ph.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h2) << 16);
-    ph.y = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h3) << 16);
-    pl.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l2) << 16);
-    pl.y = (uint32_t)__half_as_ushort(l1) | ((uint32_t)__half_as_ushort(l3) << 16);
-    *reinterpret_cast<uint2*>(xh + e) = ph;
-    *reinterpret_cast<uint2*>(xl + e) = pl;
-    float sum = ((__half2float(h0) + __half2float(l0)) + (__half2float(h1) + __half2float(l1))) +
-                ((__half2float(h2) + __half2float(l2)) + (__half2float(h3) + __half2float(l3)));
-    sum += __shfl_xor_sync(mask, sum, 1);
-    sum += __shfl_xor_sync(mask, sum, 2);
-    if ((threadIdx.x & 3) == 0) xs[e >> 4] = sum * (down * kXsScale);
-    if ((threadIdx.x & 7) == 0) s32[e >> 5] = down;
+    const int i0 = __float_as_int(fmaf(v.x, up, 12582912.0f)) - 0x4B400000, i1 = __float_as_int(fmaf(v.y, up, 12582912.0f)) - 0x4B400000;
+    const int i2 = __float_as_int(fmaf(v.z, up, 12582912.0f)) - 0x4B400000, i3 = __float_as_int(fmaf(v.w, up, 12582912.0f)) - 0x4B400000;
+    const uint32_t z0 = (uint32_t)(i0 + 0x808080) ^ 0x808080u, z1 = (uint32_t)(i1 + 0x808080) ^ 0x808080u;
+    const uint32_t z2 = (uint32_t)(i2 + 0x808080) ^ 0x808080u, z3 = (uint32_t)(i3 + 0x808080) ^ 0x808080u;
+    // bytes of z: (lo, mid, hi, 0).  4x3 byte transpose -> one word per plane
+    const uint32_t t01 = __byte_perm(z0, z1, 0x5140), t23 = __byte_perm(z2, z3, 0x5140);   // (z0.lo, z1.lo, z0.mid, z1.mid)
+    const uint32_t u01 = __byte_perm(z0, z1, 0x0062), u23 = __byte_perm(z2, z3, 0x0062);   // (z0.hi, z1.hi, -, -)
+    *reinterpret_cast<uint32_t*>(xb + L.p2 + e) = __byte_perm(t01, t23, 0x5410);
+    *reinterpret_cast<uint32_t*>(xb + L.p1 + e) = __byte_perm(t01, t23, 0x7632);
+    *reinterpret_cast<uint32_t*>(xb + L.p0 + e) = __byte_perm(u01, u23, 0x5410);
+    int s16 = (i0 + i1) + (i2 + i3);   // exact
+    s16 += __shfl_xor_sync(mask, s16, 1);
+    s16 += __shfl_xor_sync(mask, s16, 2);
+    const int s32 = s16 + __shfl_xor_sync(mask, s16, 4);
+    if ((threadIdx.x & 3) == 0) *reinterpret_cast<float*>(xb + L.x16 + 4 * (e >> 4)) = -32.0f * ((float)s16 * down);
+    if ((threadIdx.x & 7) == 0) *reinterpret_cast<float2*>(xb + L.sx + 8 * (e >> 5)) = make_float2(down, (float)s32 * down);
     return ss;
 }
 __device__ __forceinline__ void stage_x_finish(const XStage& st, const XSource& xsrc, const float* __restrict__ norm_w, int K,
                                                uint8_t* smem, float* red /*[kMmaMaxWarps]*/) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    __half* xh = reinterpret_cast<__half*>(smem);
-    __half* xl = reinterpret_cast<__half*>(smem + (size_t)2 * K + kXlPad);
-    float* xs = reinterpret_cast<float*>(smem + (size_t)4 * K + kXlPad);
-    float* s32 = xs + (K >> 4);
+    const XLayout L = x_layout(K);
     float ss = 0.0f;
 #pragma unroll
     for (int i = 0; i < kXRegs; i++) {
         const int e = (tid + i * nthr) * 4;
-        if (e < K) ss += split_store4(st.v[i], st.w[i], e, xh, xl, xs, s32, __activemask());
+        if (e < K) ss += split_store4(st.v[i], st.w[i], e, smem, L, __activemask());
     }
-    for (int e = (tid + kXRegs * nthr) * 4; e < K; e += nthr * 4) {
-        const float4 v = x_fetch4(xsrc, e);
-        const float4 w = norm_w ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
-        ss += split_store4(v, w, e, xh, xl, xs, s32, __activemask());
+    // the rest in batches of four independent loads (K = 14336 with 256 threads: 14 float4 per thread)
+    for (int e0 = (tid + kXRegs * nthr) * 4; e0 < K; e0 += 4 * nthr * 4) {
+        float4 v[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + i * nthr * 4;
+            v[i] = (e < K) ? x_fetch4(xsrc, e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[i] = (norm_w && e < K) ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + i * nthr * 4;
+            if (e < K) ss += split_store4(v[i], w[i], e, smem, L, __activemask());
+        }
     }
     ss = warp_sum(ss);
     if ((tid & 31) == 0) red[tid >> 5] = ss;
-    if (tid < 64) reinterpret_cast<uint32_t*>(smem + (x_smem_bytes(K) - 256))[tid] = 0u;
+    if (tid < 64) reinterpret_cast<uint32_t*>(smem + L.zero)[tid] = 0u;
 }
-// after the caller's __syncthreads: the factor for finished dot products (1/rms when normalising, and 2^24)
+// after the caller's __syncthreads: the factor for finished dot products (1/rms when normalising)
 __device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, float eps, int K) {
     float inv = 1.0f;
     if (norm) {
@@ -336,214 +367,279 @@ __device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, fl
         for (int w = 0; w < nwarp; w++) tot += red[w];
         inv = 1.0f / sqrtf(tot / (float)K + eps);
     }
-    return inv * kUnscale;
+    return inv;
 }
 
 // ---------------------------------------------------------------- per-type unit kernels
-// sp = shared address of the stage (row slot r at sp + r*RS; the row's bytes start at +doff),
-// nblk blocks, e0 = element index of the chunk's first element, g = lane>>2 (rows g and g+8),
-// t = lane&3.  They add this unit's contribution for rows g and g+8 to acc0 / acc1 (partial over
-// t: summed when the tile is finished).
-
-// get_scale_min_k4 (dequant.rs:213-225) for sub-blocks 2t (l) and 2t+1 (h) of a block header h = {d|dmin, scales[12]}.
-// One formula for both halves of the table: sub-blocks 0..3 are 6-bit fields of bytes 0..7, sub-blocks 4..7 take
-// their low 4 bits from bytes 8..11 and their top 2 bits from bits 6,7 of bytes 0..7.
-struct K4Lane {
-    uint32_t sh_lo, sh_w, sh_w4, m_lo, m_w;
+// sp = shared address of the stage (row slot r at sp + r*RS; the row's bytes start at +doff), e0 = element index of
+// the unit's first element, lane = 4n + t.  A unit is 32 rows (two MMA row blocks rt = 0, 1) x 256 elements; acc[2rt],
+// acc[2rt+1] collect rows 16rt + n and 16rt + n + 8 (partial over t: summed when the tile is finished).
+//
+// LaneB: where this lane finds its B-operand bytes.  A lane feeds column n with the k-slots of A-lane t, and only the
+// columns of the sub-block those k-slots belong to may be non-zero: addresses are zero_page + m * (d + e0) with
+// m in {0, 1} fixed per lane (one IMAD per address and unit, no selects in the MMA loop).
+struct LaneB {
+    uint32_t d1, d2;   // (hi or mid plane, lo plane) address of this lane's first element at e0 = 0, minus the zero page
+    uint32_t m[6];
+    float hs;          // Q4_K: 1/16 for the sub-blocks this lane owns as D-lane when their quants were carried x16
+    uint32_t sel_yz, sel_w;
 };
-__device__ __forceinline__ K4Lane k4_lane(int t) {
-    K4Lane k;
-    const uint32_t sh = 16u * (uint32_t)(t & 1);
-    k.sh_lo = (t < 2) ? sh : sh + 2u;
-    k.m_lo = (t < 2) ? 0x3F3Fu : 0x3030u;
-    k.m_w = (t < 2) ? 0u : 0x0F0Fu;
-    k.sh_w = sh;
-    k.sh_w4 = sh + 4u;
-    return k;
+
+// Q4_K / Q5_K (blocks.rs:114-141).  A-lane t reads 16 qs bytes per 64-byte half c of the block: bytes 64c+16t.. ->
+// 64-element group gp = 2c + (t>>1) (low nibbles = sub-block 2gp, high = 2gp+1), positions 16(t&1) + 4i + b.
+// Word pair ip (i = 2ip, 2ip+1) is one MMA per nibble kind: k-slots of lanes t<2 / t>=2 belong to two different
+// sub-blocks.  A1[c] carries (hi, mid) of sub-block 4c + j in column pair j = 2(t>>1) + kind, A2[c] its lo bytes in
+// column 2j: D-lane t owns sub-blocks t (c = 0) and 4 + t (c = 1), whose scales it decodes.
+__device__ __forceinline__ LaneB lane_b_k45(const XSmem& sm, int n, int t, bool q5) {
+    LaneB b{};
+    const bool act = (n >> 2) == (t >> 1);
+    const int kind = (n >> 1) & 1;
+    const uint32_t eo = 64u * (uint32_t)(t >> 1) + 16u * (uint32_t)(t & 1) + 32u * (uint32_t)kind;
+    b.d1 = ((n & 1) ? sm.p1 : sm.p0) + eo - sm.zero;
+    b.d2 = sm.p2 + eo - sm.zero;
+    b.m[0] = (act && kind == 0) ? 1u : 0u;
+    b.m[1] = (act && kind == 1) ? 1u : 0u;
+    b.m[2] = (b.m[0] && !(n & 1)) ? 1u : 0u;
+    b.m[3] = (b.m[1] && !(n & 1)) ? 1u : 0u;
+    b.hs = (!q5 && (t & 1)) ? 0.0625f : 1.0f;
+    b.sel_yz = (uint32_t)t | ((uint32_t)(4 + t) << 4);
+    b.sel_w = b.sel_yz | (b.sel_yz << 8);
+    return b;
 }
-__device__ __forceinline__ void k4_scales(const uint4& h, const K4Lane& k, float& dl, float& ml, float& dh, float& mh) {
-    const float d = half_bits_to_float(h.x), dmin = half_bits_to_float(h.x >> 16);
-    const uint32_t scp = lop3_and_or(h.y >> k.sh_lo, k.m_lo, (h.w >> k.sh_w) & k.m_w);
-    const uint32_t mnp = lop3_and_or(h.z >> k.sh_lo, k.m_lo, (h.w >> k.sh_w4) & k.m_w);
-    dl = d * (float)(scp & 0xFFu);
-    dh = d * (float)((scp >> 8) & 0xFFu);
-    ml = dmin * (float)(mnp & 0xFFu);
-    mh = dmin * (float)((mnp >> 8) & 0xFFu);
+// byte k of v -> float(2^23 + byte): the byte lands in the mantissa of 0x4B000000
+__device__ __forceinline__ float byte_magic(uint32_t v, uint32_t sel) { return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)); }
+
+// get_scale_min_k4 (dequant.rs:213-225) for sub-blocks t and 4+t of two rows at once (block headers h0, h1 =
+// {d|dmin, scales[12]}): d*sc and dmin*m as the reference computes them (one rounding each).
+__device__ __forceinline__ void k4_scales2(const uint4& h0, const uint4& h1, const LaneB& lb, float (&dsc)[2][2], float (&dm)[2][2]) {
+    const uint32_t Y = __byte_perm(h0.y, h1.y, lb.sel_yz), Z = __byte_perm(h0.z, h1.z, lb.sel_yz);
+    const uint32_t YZ = __byte_perm(Y, Z, 0x5410);              // (y r0, y r1, z r0, z r1): bytes t of scales[0..3], [4..7]
+    const uint32_t W = __byte_perm(h0.w, h1.w, lb.sel_w);       // (w r0, w r1, w r0, w r1): byte t of scales[8..11]
+    const uint32_t R = YZ & 0x3F3F3F3Fu;                         // (sc_t r0, sc_t r1, m_t r0, m_t r1)
+    const uint32_t W2 = (W & 0x00000F0Fu) | ((W >> 4) & 0x0F0F0000u);
+    const uint32_t R2 = W2 | ((YZ >> 2) & 0x30303030u);          // (sc_{4+t} r0, r1, m_{4+t} r0, r1)
+    const float d0 = half_bits_to_float(h0.x), n0 = half_bits_to_float(h0.x >> 16);
+    const float d1 = half_bits_to_float(h1.x), n1 = half_bits_to_float(h1.x >> 16);
+    const float d0b = d0 * -8388608.0f, n0b = n0 * -8388608.0f, d1b = d1 * -8388608.0f, n1b = n1 * -8388608.0f;
+    dsc[0][0] = fmaf(d0, byte_magic(R, 0x7440), d0b);
+    dsc[0][1] = fmaf(d1, byte_magic(R, 0x7441), d1b);
+    dm[0][0] = fmaf(n0, byte_magic(R, 0x7442), n0b);
+    dm[0][1] = fmaf(n1, byte_magic(R, 0x7443), n1b);
+    dsc[1][0] = fmaf(d0, byte_magic(R2, 0x7440), d0b);
+    dsc[1][1] = fmaf(d1, byte_magic(R2, 0x7441), d1b);
+    dm[1][0] = fmaf(n0, byte_magic(R2, 0x7442), n0b);
+    dm[1][1] = fmaf(n1, byte_magic(R2, 0x7443), n1b);
 }
 
-// Q4_K / Q5_K (blocks.rs:114-141).  Lane t reads 16 qs bytes per 64-byte half c of the block:
-// bytes 64c+16t.. -> group gp = 2c + (t>>1) (64 elements: low nibbles = sub-block 2gp, high = 2gp+1),
-// positions l = 16(t&1) + 4i + j.  Group gp is routed to column pair gp, so lane t' of the D
-// fragment ends up with sub-blocks 2t' (cl) and 2t'+1 (ch), whose scales it decodes.
 template <bool Q5>
-__device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, int nblk, int e0, const XSmem& sm, int g, int t, float& acc0,
-                                         float& acc1) {
-    constexpr int BB = Q5 ? 176 : 144, QS = Q5 ? 48 : 16;
-    const uint32_t arr = (g & 1) ? sm.xl : sm.xh;
-    const bool lane_act = (((g >> 1) & 1) == (t >> 1));
-    const int c_act = g >> 2;
-    const K4Lane kl = k4_lane(t);
-    // B-operand base of this lane for each half c: its x elements, or the zero page when its column pair is not addressed
-    const uint32_t xo = 2u * (uint32_t)(e0 + 128 * c_act + 64 * (t >> 1) + 16 * (t & 1));
-    const uint32_t xb0 = (lane_act && c_act == 0) ? arr + xo : sm.zero, xs0 = (lane_act && c_act == 0) ? 512u : 0u;
-    const uint32_t xb1 = (lane_act && c_act == 1) ? arr + xo : sm.zero, xs1 = (lane_act && c_act == 1) ? 512u : 0u;
-#pragma unroll 2
-    for (int b = 0; b < nblk; b++) {
-        const uint32_t r0 = sp + g * RS + b * BB, r1 = r0 + 8 * RS;
-        const uint4 h0 = lds128(r0), h1 = lds128(r1);
-        uint4 qh0 = make_uint4(0u, 0u, 0u, 0u), qh1 = qh0;
-        if (Q5) {
-            qh0 = lds128(r0 + 16 + 16 * (t & 1));
-            qh1 = lds128(r1 + 16 + 16 * (t & 1));
-        }
-        // independent accumulator chains per half c (4 MMAs deep instead of 8): cl[c] / ch[c]
-        float cl[2][4], ch[2][4];
+__device__ __forceinline__ void unit_k45(uint32_t sp, uint32_t RS, uint32_t e0, const XSmem& sm, const LaneB& lb, int g, int t,
+                                         float (&acc)[4]) {
+    constexpr uint32_t QS = Q5 ? 48u : 16u;
+    const uint32_t t1 = lb.d1 + e0, t2 = lb.d2 + e0;
+    const uint32_t a1l = sm.zero + lb.m[0] * t1, a1h = sm.zero + lb.m[1] * t1;
+    const uint32_t a2l = sm.zero + lb.m[2] * t2, a2h = sm.zero + lb.m[3] * t2;
+    uint4 bl[2], bh[2], cl[2], ch[2];
 #pragma unroll
-        for (int c = 0; c < 2; c++) cl[c][0] = cl[c][1] = cl[c][2] = cl[c][3] = ch[c][0] = ch[c][1] = ch[c][2] = ch[c][3] = 0.f;
-        const int eb = e0 + b * 256;
+    for (int c = 0; c < 2; c++) {
+        bl[c] = lds128(a1l + 128u * c);
+        bh[c] = lds128(a1h + 128u * c);
+        cl[c] = lds128(a2l + 128u * c);
+        ch[c] = lds128(a2h + 128u * c);
+    }
+    const uint2 kx0 = lds64(sm.sx + 8u * ((e0 >> 5) + (uint32_t)t)), kx1 = lds64(sm.sx + 8u * ((e0 >> 5) + (uint32_t)t + 4u));
+    const float kf[2] = {__uint_as_float(kx0.x) * lb.hs, __uint_as_float(kx1.x) * lb.hs};
+    const float XS[2] = {__uint_as_float(kx0.y), __uint_as_float(kx1.y)};
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++) {
+        const uint32_t r0 = sp + (uint32_t)(16 * rt + g) * RS, r1 = r0 + 8u * RS;
+        const uint4 h0 = lds128(r0), h1 = lds128(r1);
+        uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;
+        if (Q5) {
+            qa = lds128(r0 + 16u + 16u * (uint32_t)(t & 1));
+            qb = lds128(r1 + 16u + 16u * (uint32_t)(t & 1));
+        }
+        int A1[2][4], A2[2][4];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            const uint4 W0 = lds128(r0 + QS + 64 * c + 16 * t), W1 = lds128(r1 + QS + 64 * c + 16 * t);
-            const int gp = 2 * c + (t >> 1);
-            const uint32_t xa = (c ? xb1 : xb0) + (uint32_t)b * (c ? xs1 : xs0);
-            uint4 bl[2], bh[2];
-            bl[0] = lds128(xa);
-            bl[1] = lds128(xa + 16);
-            bh[0] = lds128(xa + 64);
-            bh[1] = lds128(xa + 80);
-            const uint32_t wa4[4] = {W0.x, W0.y, W0.z, W0.w}, wb4[4] = {W1.x, W1.y, W1.z, W1.w};
-            const uint32_t ha4[4] = {qh0.x, qh0.y, qh0.z, qh0.w}, hb4[4] = {qh1.x, qh1.y, qh1.z, qh1.w};
+            const uint4 W0 = lds128(r0 + QS + 64u * c + 16u * (uint32_t)t), W1 = lds128(r1 + QS + 64u * c + 16u * (uint32_t)t);
+            const uint32_t w0[4] = {W0.x, W0.y, W0.z, W0.w}, w1[4] = {W1.x, W1.y, W1.z, W1.w};
+            const uint32_t ha[4] = {qa.x, qa.y, qa.z, qa.w}, hb[4] = {qb.x, qb.y, qb.z, qb.w};
+            const uint32_t bls[4] = {bl[c].x, bl[c].y, bl[c].z, bl[c].w}, bhs[4] = {bh[c].x, bh[c].y, bh[c].z, bh[c].w};
+            const uint32_t cls[4] = {cl[c].x, cl[c].y, cl[c].z, cl[c].w}, chs[4] = {ch[c].x, ch[c].y, ch[c].z, ch[c].w};
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t wa = wa4[i], wb = wb4[i];
-                const uint32_t blx = (i & 1) ? bl[i >> 1].z : bl[i >> 1].x, bly = (i & 1) ? bl[i >> 1].w : bl[i >> 1].y;
-                const uint32_t bhx = (i & 1) ? bh[i >> 1].z : bh[i >> 1].x, bhy = (i & 1) ? bh[i >> 1].w : bh[i >> 1].y;
-                uint32_t ml_a = kMagic, ml_b = kMagic, ml_a8 = kMagic, ml_b8 = kMagic;  // low-group or-values
-                uint32_t mh_a = kMagic, mh_b = kMagic, mh_a8 = kMagic, mh_b8 = kMagic;  // high-group or-values
-                if (Q5) {  // 5th bit (dequant.rs:262-315): +16 for the low sub-block (bit 4), +256 (= 16*16) for the x16-carried high one
-                    const uint32_t la = ha4[i] >> (2 * gp), lb = hb4[i] >> (2 * gp);  // bit0 of each byte: sub-block 2gp, bit1: 2gp+1
-                    ml_a = lop3_and_or(la << 4, 0x00100010u, kMagic);
-                    ml_b = lop3_and_or(lb << 4, 0x00100010u, kMagic);
-                    ml_a8 = lop3_and_or(la >> 4, 0x00100010u, kMagic);
-                    ml_b8 = lop3_and_or(lb >> 4, 0x00100010u, kMagic);
-                    mh_a = lop3_and_or(la << 7, 0x01000100u, kMagic);
-                    mh_b = lop3_and_or(lb << 7, 0x01000100u, kMagic);
-                    mh_a8 = lop3_and_or(la >> 1, 0x01000100u, kMagic);
-                    mh_b8 = lop3_and_or(lb >> 1, 0x01000100u, kMagic);
+            for (int ip = 0; ip < 2; ip++) {
+                uint32_t lo[4], hi[4];
+                const uint32_t src[4] = {w0[2 * ip], w1[2 * ip], w0[2 * ip + 1], w1[2 * ip + 1]};   // fragment order a0..a3
+                if (!Q5) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        lo[r] = src[r] & 0x0F0F0F0Fu;
+                        hi[r] = src[r] & 0xF0F0F0F0u;   // 16 q: the 1/16 is in lb.hs
+                    }
+                } else {   // 5th bit (dequant.rs:262-315): bit 2gp of qh byte -> low sub-block, bit 2gp+1 -> high sub-block
+                    const uint32_t sh = 2u * (2u * c + (uint32_t)(t >> 1));
+                    const uint32_t hq[4] = {ha[2 * ip] >> sh, hb[2 * ip] >> sh, ha[2 * ip + 1] >> sh, hb[2 * ip + 1] >> sh};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        lo[r] = (src[r] & 0x0F0F0F0Fu) | ((hq[r] << 4) & 0x10101010u);
+                        hi[r] = ((src[r] >> 4) & 0x0F0F0F0Fu) | ((hq[r] << 3) & 0x10101010u);
+                    }
                 }
-                const uint32_t wa8 = __umulhi(wa, 0x01000000u), wb8 = __umulhi(wb, 0x01000000u);  // >> 8 on the FMA pipe
-                mma16816(cl[c], lop3_and_or(wa, 0x000F000Fu, ml_a), lop3_and_or(wb, 0x000F000Fu, ml_b),
-                         lop3_and_or(wa8, 0x000F000Fu, ml_a8), lop3_and_or(wb8, 0x000F000Fu, ml_b8), blx, bly);
-                mma16816(ch[c], lop3_and_or(wa, 0x00F000F0u, mh_a), lop3_and_or(wb, 0x00F000F0u, mh_b),
-                         lop3_and_or(wa8, 0x00F000F0u, mh_a8), lop3_and_or(wb8, 0x00F000F0u, mh_b8), bhx, bhy);
+                if (ip == 0) {
+                    imma_u8s8_z(A1[c], lo[0], lo[1], lo[2], lo[3], bls[0], bls[1]);
+                    imma_u8s8_z(A2[c], lo[0], lo[1], lo[2], lo[3], cls[0], cls[1]);
+                } else {
+                    imma_u8s8(A1[c], lo[0], lo[1], lo[2], lo[3], bls[2], bls[3]);
+                    imma_u8s8(A2[c], lo[0], lo[1], lo[2], lo[3], cls[2], cls[3]);
+                }
+                imma_u8s8(A1[c], hi[0], hi[1], hi[2], hi[3], bhs[2 * ip], bhs[2 * ip + 1]);
+                imma_u8s8(A2[c], hi[0], hi[1], hi[2], hi[3], chs[2 * ip], chs[2 * ip + 1]);
             }
         }
-        // lane t owns sub-blocks 2t (low nibbles) and 2t+1 (high nibbles, carried x16) of this block: column pair t,
-        // which was fed by the half c = t>>1
-        const float sl0 = (t & 2) ? cl[1][0] + cl[1][1] : cl[0][0] + cl[0][1], sl1 = (t & 2) ? cl[1][2] + cl[1][3] : cl[0][2] + cl[0][3];
-        const float sh0 = (t & 2) ? ch[1][0] + ch[1][1] : ch[0][0] + ch[0][1], sh1 = (t & 2) ? ch[1][2] + ch[1][3] : ch[0][2] + ch[0][3];
-        float dl0, ml0, dh0, mh0, dl1, ml1, dh1, mh1;
-        k4_scales(h0, kl, dl0, ml0, dh0, mh0);
-        k4_scales(h1, kl, dl1, ml1, dh1, mh1);
-        const uint32_t xsa = sm.xs + 4u * (uint32_t)((eb >> 4) + 4 * t);
-        const float xsl = lds_f32(xsa) + lds_f32(xsa + 4), xsh = lds_f32(xsa + 8) + lds_f32(xsa + 12);
-        const uint2 sc = lds64(sm.s32 + 4u * (uint32_t)((eb >> 5) + 2 * t));  // 2^-k of sub-blocks 2t, 2t+1
-        const float kl = __uint_as_float(sc.x), kh = __uint_as_float(sc.y) * 0.0625f;
-        acc0 += (dl0 * kl) * sl0 - ml0 * xsl + (dh0 * kh) * sh0 - mh0 * xsh;
-        acc1 += (dl1 * kl) * sl1 - ml1 * xsl + (dh1 * kh) * sh1 - mh1 * xsh;
-    }
-}
-
-// Q6_K (blocks.rs:143-155, dequant.rs:321-356): ql[128] qh[64] scales[16] d.  16 scale groups of 16.
-// Per 128-half n, lane t reads ql bytes 64n+16t.. : t<2 -> "A" bytes (low nibble: quarter c=0, high: c=2),
-// t>=2 -> "B" bytes (c=1 / c=3); positions l = 16(t&1)+4i+j, so lane t's low-nibble values are elements
-// 128n + 16t + 4i + j and its high-nibble values are +64.  Lane t's group (scale 8n + 2c + (t&1) = 4m + t,
-// m = 2n + lowhigh) is routed to column pair t: four accumulator sets C[m], D-lane t' owns scale 4m + t'.
-__device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, int nblk, int e0, uint32_t doff0, uint32_t doff1,
-                                         const XSmem& sm, int g, int t, float& acc0, float& acc1) {
-    const uint32_t arr = (g & 1) ? sm.xl : sm.xh;
-    const bool act = (g >> 1) == t;
-    const uint32_t s_lo = 4u - 2u * (uint32_t)(t >> 1);  // (qh >> 2c) << 4 for c = t>>1
-    const uint32_t s_hi = 2u * (uint32_t)(t >> 1);       // (qh >> 2c) << 4 for c = 2 + (t>>1): qh >> (2*(t>>1)), bits 4,5
-    for (int b = 0; b < nblk; b++) {
-        const uint32_t r0 = sp + g * RS + doff0 + b * 210, r1 = sp + (g + 8) * RS + doff1 + b * 210;
-        float C[4][4];
+        float dsc[2][2], dm[2][2];
+        k4_scales2(h0, h1, lb, dsc, dm);
 #pragma unroll
-        for (int m = 0; m < 4; m++) C[m][0] = C[m][1] = C[m][2] = C[m][3] = 0.f;
-        const int eb = e0 + b * 256;
-#pragma unroll
-        for (int n = 0; n < 2; n++) {
-            uint32_t L0[4], L1[4], H0[4], H1[4];
-            lds_piece16(r0 + 64 * n + 16 * t, L0);
-            lds_piece16(r1 + 64 * n + 16 * t, L1);
-            lds_piece16(r0 + 128 + 32 * n + 16 * (t & 1), H0);
-            lds_piece16(r1 + 128 + 32 * n + 16 * (t & 1), H1);
-            const uint32_t xa = act ? arr + 2u * (uint32_t)(eb + 128 * n + 16 * t) : sm.zero;
-            uint4 bl[2], bh[2];
-            bl[0] = lds128(xa);
-            bl[1] = lds128(xa + 16);
-            bh[0] = lds128(xa + 128);
-            bh[1] = lds128(xa + 144);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t lo0 = lop3_and_or(L0[i], 0x0F0F0F0Fu, (H0[i] << s_lo) & 0x30303030u);
-                const uint32_t lo1 = lop3_and_or(L1[i], 0x0F0F0F0Fu, (H1[i] << s_lo) & 0x30303030u);
-                const uint32_t hi0 = lop3_and_or(L0[i] >> 4, 0x0F0F0F0Fu, (H0[i] >> s_hi) & 0x30303030u);
-                const uint32_t hi1 = lop3_and_or(L1[i] >> 4, 0x0F0F0F0Fu, (H1[i] >> s_hi) & 0x30303030u);
-                const uint32_t blx = (i & 1) ? bl[i >> 1].z : bl[i >> 1].x, bly = (i & 1) ? bl[i >> 1].w : bl[i >> 1].y;
-                const uint32_t bhx = (i & 1) ? bh[i >> 1].z : bh[i >> 1].x, bhy = (i & 1) ? bh[i >> 1].w : bh[i >> 1].y;
-                mma16816(C[2 * n], __byte_perm(lo0, kMagicB, 0x4240), __byte_perm(lo1, kMagicB, 0x4240),
-                         __byte_perm(lo0, kMagicB, 0x4341), __byte_perm(lo1, kMagicB, 0x4341), blx, bly);
-                mma16816(C[2 * n + 1], __byte_perm(hi0, kMagicB, 0x4240), __byte_perm(hi1, kMagicB, 0x4240),
-                         __byte_perm(hi0, kMagicB, 0x4341), __byte_perm(hi1, kMagicB, 0x4341), bhx, bhy);
-            }
-        }
-        const float d0 = half_bits_to_float(lds16(r0 + 208)), d1 = half_bits_to_float(lds16(r1 + 208));
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const int si = 4 * m + t;
-            const float xs = lds_f32(sm.xs + 4u * (uint32_t)((eb >> 4) + si));
-            const float kk = lds_f32(sm.s32 + 4u * (uint32_t)((eb >> 5) + (si >> 1)));
-            const float s0 = (float)lds_s8(r0 + 192 + si), s1 = (float)lds_s8(r1 + 192 + si);
-            acc0 += (d0 * s0) * (kk * (C[m][0] + C[m][1]) - 32.0f * xs);   // Q6_K's -32
-            acc1 += (d1 * s1) * (kk * (C[m][2] + C[m][3]) - 32.0f * xs);
+        for (int c = 0; c < 2; c++) {
+            const float s0 = fmaf((float)(A1[c][0] * 256 + A1[c][1]), 256.0f, (float)A2[c][0]);
+            const float s1 = fmaf((float)(A1[c][2] * 256 + A1[c][3]), 256.0f, (float)A2[c][2]);
+            acc[2 * rt] = fmaf(dsc[c][0] * kf[c], s0, fmaf(-dm[c][0], XS[c], acc[2 * rt]));
+            acc[2 * rt + 1] = fmaf(dsc[c][1] * kf[c], s1, fmaf(-dm[c][1], XS[c], acc[2 * rt + 1]));
         }
     }
 }
 
-// Q8_0 (blocks.rs:60-70): 34-byte blocks of 32.  Lane t reads bytes 16m+4t.. of a block (two MMAs per block);
-// blocks 4i..4i+3 share one accumulator set through the column pairs (block bi -> pair bi), D-lane t' owns
-// block 4i + t'.
-__device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, int nblk, int e0, uint32_t doff0, uint32_t doff1,
-                                         const XSmem& sm, int g, int t, float& acc0, float& acc1) {
-    const uint32_t arr = (g & 1) ? sm.xl : sm.xh;
-    const uint32_t row0 = sp + g * RS + doff0, row1 = sp + (g + 8) * RS + doff1;
-    for (int b4 = 0; b4 < nblk; b4 += 4) {
-        float C[4] = {0.f, 0.f, 0.f, 0.f};
+// Q6_K (blocks.rs:143-155, dequant.rs:321-356): ql[128] qh[64] scales[16] d; 16 scale groups of 16 elements.
+// Per 128-element half hf, A-lane t reads 8-byte pieces ql[64hf + 8t..], ql[64hf + 32 + 8t..], qh[32hf + 8t..]:
+// positions l = 8t..8t+7 of the four quarters q (element 128hf + 32q + l, scale group 8hf + 2q + (l>>4)).  One MMA
+// per quarter; its k-slots belong to two scale groups (t<2 / t>=2).  A1[hf][q>>1] carries (hi, mid) of group
+// 8hf + 4(q>>1) + j in column pair j = 2(q&1) + (t>>1); A2[hf] the lo bytes of group 8hf + s in column
+// 2(s&3) + (s>>2): D-lane t owns groups 8hf + t and 8hf + 4 + t.
+__device__ __forceinline__ LaneB lane_b_q6k(const XSmem& sm, int n, int t) {
+    LaneB b{};
+    const bool act = ((n >> 1) & 1) == (t >> 1);
+    b.d1 = ((n & 1) ? sm.p1 : sm.p0) + 8u * (uint32_t)t - sm.zero;
+    b.d2 = sm.p2 + 8u * (uint32_t)t - sm.zero;
+    b.m[0] = (act && (n >> 2) == 0) ? 1u : 0u;   // even quarters
+    b.m[1] = (act && (n >> 2) == 1) ? 1u : 0u;   // odd quarters
+    const int q2 = (n >> 2) + 2 * (n & 1);
 #pragma unroll
-        for (int bi = 0; bi < 4; bi++) {
-            const int b = b4 + bi;
-            if (b < nblk) {  // warp-uniform
-                const uint32_t r0 = row0 + b * 34 + 2, r1 = row1 + b * 34 + 2;
-                const bool act = (g >> 1) == bi;
+    for (int q = 0; q < 4; q++) b.m[2 + q] = (act && q == q2) ? 1u : 0u;
+    b.hs = 1.0f;
+    return b;
+}
+template <int AL>
+__device__ __forceinline__ void unit_q6k(uint32_t sp, uint32_t RS, uint32_t e0, uint32_t doff, const XSmem& sm, const LaneB& lb,
+                                         int g, int t, float (&acc)[4]) {
+    const uint32_t t1 = lb.d1 + e0, t2 = lb.d2 + e0;
+    const uint32_t a1[2] = {sm.zero + lb.m[0] * t1, sm.zero + lb.m[1] * t1};
+    uint2 B1[2][4], B2[2][4];
 #pragma unroll
-                for (int m = 0; m < 2; m++) {
-                    const uint32_t w0 = lds32_a2(r0 + 16 * m + 4 * t) ^ 0x80808080u;  // int8 -> biased uint8
-                    const uint32_t w1 = lds32_a2(r1 + 16 * m + 4 * t) ^ 0x80808080u;
-                    const uint2 bf = lds64(act ? arr + 2u * (uint32_t)(e0 + 32 * b + 16 * m + 4 * t) : sm.zero);
-                    mma16816(C, __byte_perm(w0, kMagicB, 0x4240), __byte_perm(w1, kMagicB, 0x4240),
-                             __byte_perm(w0, kMagicB, 0x4341), __byte_perm(w1, kMagicB, 0x4341), bf.x, bf.y);
-                }
+    for (int q = 0; q < 4; q++) {
+        const uint32_t a2 = sm.zero + lb.m[2 + q] * t2;
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            B1[hf][q] = lds64(a1[q & 1] + 128u * hf + 32u * q);
+            B2[hf][q] = lds64(a2 + 128u * hf + 32u * q);
+        }
+    }
+#pragma unroll 1
+    for (int rt = 0; rt < 2; rt++) {
+        const uint32_t blk0 = sp + (uint32_t)(16 * rt + g) * RS + doff, blk1 = blk0 + 8u * RS;
+        int A1[2][2][4], A2[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            uint32_t QA[4], QB[4], QH[4];   // fragment order: (row n word 0, row n+8 word 0, row n word 1, row n+8 word 1)
+            lds_piece8<AL>(blk0 + 64u * hf + 8u * (uint32_t)t, QA[0], QA[2]);
+            lds_piece8<AL>(blk1 + 64u * hf + 8u * (uint32_t)t, QA[1], QA[3]);
+            lds_piece8<AL>(blk0 + 64u * hf + 32u + 8u * (uint32_t)t, QB[0], QB[2]);
+            lds_piece8<AL>(blk1 + 64u * hf + 32u + 8u * (uint32_t)t, QB[1], QB[3]);
+            lds_piece8<AL>(blk0 + 128u + 32u * hf + 8u * (uint32_t)t, QH[0], QH[2]);
+            lds_piece8<AL>(blk1 + 128u + 32u * hf + 8u * (uint32_t)t, QH[1], QH[3]);
+            uint32_t a[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                a[0][r] = (QA[r] & 0x0F0F0F0Fu) | ((QH[r] << 4) & 0x30303030u);
+                a[1][r] = (QB[r] & 0x0F0F0F0Fu) | ((QH[r] << 2) & 0x30303030u);
+                a[2][r] = ((QA[r] >> 4) & 0x0F0F0F0Fu) | (QH[r] & 0x30303030u);
+                a[3][r] = ((QB[r] >> 4) & 0x0F0F0F0Fu) | ((QH[r] >> 2) & 0x30303030u);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if ((q & 1) == 0) imma_u8s8_z(A1[hf][q >> 1], a[q][0], a[q][1], a[q][2], a[q][3], B1[hf][q].x, B1[hf][q].y);
+                else imma_u8s8(A1[hf][q >> 1], a[q][0], a[q][1], a[q][2], a[q][3], B1[hf][q].x, B1[hf][q].y);
+                if (q == 0) imma_u8s8_z(A2[hf], a[q][0], a[q][1], a[q][2], a[q][3], B2[hf][q].x, B2[hf][q].y);
+                else imma_u8s8(A2[hf], a[q][0], a[q][1], a[q][2], a[q][3], B2[hf][q].x, B2[hf][q].y);
             }
         }
-        const int b = b4 + t;  // lane t owns block b4 + t
-        if (b < nblk) {
-            const uint32_t xa = sm.xs + 4u * (uint32_t)(((e0 + 32 * b) >> 4));
-            const float xs = lds_f32(xa) + lds_f32(xa + 4);
-            const float kk = lds_f32(sm.s32 + 4u * (uint32_t)((e0 >> 5) + b));
-            acc0 += half_bits_to_float(lds16(row0 + b * 34)) * (kk * (C[0] + C[1]) - 128.0f * xs);  // int8 -> biased uint8
-            acc1 += half_bits_to_float(lds16(row1 + b * 34)) * (kk * (C[2] + C[3]) - 128.0f * xs);
+        const float d0 = half_bits_to_float(lds16(blk0 + 208u)), d1 = half_bits_to_float(lds16(blk1 + 208u));
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+            for (int qq = 0; qq < 2; qq++) {
+                const uint32_t sg = 8u * hf + 4u * qq + (uint32_t)t;
+                const float s0 = fmaf((float)(A1[hf][qq][0] * 256 + A1[hf][qq][1]), 256.0f, (float)A2[hf][qq]);
+                const float s1 = fmaf((float)(A1[hf][qq][2] * 256 + A1[hf][qq][3]), 256.0f, (float)A2[hf][2 + qq]);
+                const float kf = lds_f32(sm.sx + 8u * ((e0 >> 5) + (sg >> 1)));
+                const float xn = lds_f32(sm.x16 + 4u * ((e0 >> 4) + sg));   // -32 * sum(x) of the group
+                const float sc0 = (float)lds_s8(blk0 + 192u + sg), sc1 = (float)lds_s8(blk1 + 192u + sg);
+                r0 = fmaf(d0 * sc0, fmaf(kf, s0, xn), r0);
+                r1 = fmaf(d1 * sc1, fmaf(kf, s1, xn), r1);
+            }
+        if (rt == 0) { acc[0] += r0; acc[1] += r1; } else { acc[2] += r0; acc[3] += r1; }
+    }
+}
+
+// Q8_0 (blocks.rs:60-70): 34-byte blocks of 32, signed quants (s8 x s8 MMA, no offset).  A-lane t reads bytes
+// 8t..8t+7 of a block: one MMA per block.  A1[b>>2] carries (hi, mid) of block b in column pair b&3, A2 the lo bytes
+// of block b in column 2(b&3) + (b>>2): D-lane t owns blocks t and 4 + t.
+__device__ __forceinline__ LaneB lane_b_q80(const XSmem& sm, int n, int t) {
+    LaneB b{};
+    b.d1 = ((n & 1) ? sm.p1 : sm.p0) + 8u * (uint32_t)t - sm.zero;
+    b.d2 = sm.p2 + 8u * (uint32_t)t - sm.zero;
+    b.m[0] = (uint32_t)(n >> 1);                 // block (mod 4) this lane feeds in A1
+    b.m[1] = (uint32_t)((n >> 1) + 4 * (n & 1)); // block this lane feeds in A2
+    b.hs = 1.0f;
+    return b;
+}
+__device__ __forceinline__ void unit_q80(uint32_t sp, uint32_t RS, uint32_t e0, uint32_t doff, int nblk, const XSmem& sm,
+                                         const LaneB& lb, int g, int t, float (&acc)[4]) {
+    const uint32_t t1 = sm.zero + lb.d1 + e0, t2 = sm.zero + lb.d2 + e0;
+    uint2 B1[8], B2[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        B1[b] = lds64(((uint32_t)(b & 3) == lb.m[0]) ? t1 + 32u * b : sm.zero);
+        B2[b] = lds64(((uint32_t)b == lb.m[1]) ? t2 + 32u * b : sm.zero);
+    }
+#pragma unroll 1
+    for (int rt = 0; rt < 2; rt++) {
+        const uint32_t row0 = sp + (uint32_t)(16 * rt + g) * RS + doff, row1 = row0 + 8u * RS;
+        int A1[2][4], A2[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) A1[0][i] = A1[1][i] = A2[i] = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (b < nblk) {   // warp-uniform (ragged last chunk)
+                uint32_t a0, a1, a2, a3;
+                lds_piece8_any(row0 + 34u * b + 2u + 8u * (uint32_t)t, a0, a2);
+                lds_piece8_any(row1 + 34u * b + 2u + 8u * (uint32_t)t, a1, a3);
+                imma_s8s8(A1[b >> 2], a0, a1, a2, a3, B1[b].x, B1[b].y);
+                imma_s8s8(A2, a0, a1, a2, a3, B2[b].x, B2[b].y);
+            }
         }
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int b = t + 4 * j;
+            if (b < nblk) {
+                const float s0 = fmaf((float)(A1[j][0] * 256 + A1[j][1]), 256.0f, (float)A2[j]);
+                const float s1 = fmaf((float)(A1[j][2] * 256 + A1[j][3]), 256.0f, (float)A2[2 + j]);
+                const float kf = lds_f32(sm.sx + 8u * ((e0 >> 5) + (uint32_t)b));
+                r0 = fmaf(half_bits_to_float(lds16(row0 + 34u * b)) * kf, s0, r0);
+                r1 = fmaf(half_bits_to_float(lds16(row1 + 34u * b)) * kf, s1, r1);
+            }
+        }
+        if (rt == 0) { acc[0] += r0; acc[1] += r1; } else { acc[2] += r0; acc[3] += r1; }
     }
 }
 
@@ -559,6 +655,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {  // at most N newest groups still in flight
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // warp-uniform n in 0..3
+    if (n <= 0) cp_async_wait<0>();
+    else if (n == 1) cp_async_wait<1>();
+    else if (n == 2) cp_async_wait<2>();
+    else cp_async_wait<3>();
 }
 // ticket with release (my partial sums are visible) + acquire (I see the others') semantics
 __device__ __forceinline__ unsigned int atom_add_acq_rel(unsigned int* p, unsigned int v) {
@@ -581,31 +683,29 @@ __device__ __forceinline__ unsigned long long gtimer() {
         if (p.dbg && lane == 0) p.dbg[(size_t)gw * 8 + (i)] = gtimer(); \
     } while (0)
 
-// Position of a warp in its run of units: segment s, 16-row tile, matrix (ME_SWIGLU: 0 = gate, 1 = up; else = s),
-// chunk (256 elements) within the row.  a / b are the true addresses of the unit's bytes in rows tile*16+g and +8.
+// Position of a warp in its run of units: segment s, 32-row tile, matrix (ME_SWIGLU: 0 = gate, 1 = up; else = s),
+// chunk (256 elements) within the row.
 struct MCursor {
     int s, tile, mat, chunk;
-    const uint8_t* a;
-    const uint8_t* b;
 };
 
 // The whole GEMV of one launch (or of one phase of the per-token megakernel, mega.cuh) for this CTA.
 //   smem   : dynamic shared memory (x staging + rings), 128-byte aligned
-//   s_red  : [2 * kMmaMaxWarps] floats, s_part: [kMmaMaxWarps][2][32] floats (static shared memory of the caller)
-//   pdl    : the launch is part of a programmatic-dependent-launch chain (griddepcontrol at the right place)
-//   warm_l2: pull the first stages towards L2 before anything that depends on the previous kernel
+//   s_red  : [2 * kMmaMaxWarps] floats, s_part: [kMmaMaxWarps][2][2][32] floats (static shared memory of the caller)
 //   pre()  : runs first (megakernel: __syncthreads + arrive at the grid barrier that ends the previous phase)
 //   post() : runs after the prologue, before anything that depends on other CTAs / the previous kernel
 //            (megakernel: wait at that barrier; stand-alone kernel: griddepcontrol)
 //   early  : issue the first ring stages with cp.async BEFORE post() (weights never depend on a predecessor), so
 //            they land while the barrier is being waited for; otherwise they are issued after the x loads
-template <int STAGES, class Pre, class Post>
-__device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, float* s_red, float (*s_part)[2][32], Pre pre_fn,
+//   warm_l2: (not early) pull the first stages towards L2 before post()
+template <class Pre, class Post>
+__device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, float* s_red, float (*s_part)[2][2][32], Pre pre_fn,
                                              Post post_fn, bool early, bool warm_l2) {
     pre_fn();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nw = blockDim.x >> 5;
     const int K = p.K;
+    const int STAGES = p.stages;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t ring = sbase + (uint32_t)x_smem_bytes(K) + (uint32_t)warp * STAGES * p.stage_bytes;
     const bool swiglu = p.epi == ME_SWIGLU;
@@ -624,15 +724,9 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     const int cn = cu1 - cu0;
     const int u0 = cu0 + (warp * cn) / nw, u1 = cu0 + ((warp + 1) * cn) / nw;
     const int n_units = u1 - u0;
-    long long eoff = 0;  // MoE expert index (valid after pdl_wait)
+    long long eoff = 0;  // MoE expert index (valid after post_fn)
     MMA_STAMP(0);
 
-    auto cur_ptrs = [&](MCursor& q) {
-        const MSeg& sg = p.seg[q.mat];
-        const uint8_t* base = sg.w + eoff * sg.expert_stride + (long long)q.chunk * sg.chunk_bytes;
-        q.a = base + (long long)min(q.tile * 16 + g, sg.n_rows - 1) * sg.row_bytes;
-        q.b = base + (long long)min(q.tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes;
-    };
     auto cur_init = [&](MCursor& q, int u) {
         q.s = (p.n_seg > 2 && u >= p.seg[2].unit0) ? 2 : (p.n_seg > 1 && !swiglu && u >= p.seg[1].unit0) ? 1 : 0;
         const int local = u - p.seg[q.s].unit0;
@@ -640,7 +734,6 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         q.chunk = local - q.tile * p.units_per_tile;
         q.mat = q.s;
         if (swiglu && q.chunk >= p.chunks) { q.mat = 1; q.chunk -= p.chunks; }
-        cur_ptrs(q);
     };
     // the cursor has just moved past the last chunk of its row: next matrix (SwiGLU up rows) / tile / segment
     auto cur_wrap = [&](MCursor& q) {
@@ -656,60 +749,70 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
                 q.mat = q.s;
             }
         }
-        cur_ptrs(q);
     };
 
-    // ---- producer: cp.async the 16 rows of a unit into a ring stage.  Lane (g, t) moves the 16-byte pieces
-    // t, t+4, ... of rows g and g+8 (8 rows x 64 contiguous bytes per instruction); sources are aligned down to
-    // 16 bytes, the residue (doff) is re-derived by the consumer from the same address. ----
+    // ---- producer: cp.async the 32 rows of a unit into a ring stage.  Lane (g, t) moves the 16-byte pieces
+    // t, t+4, ... of rows g, g+8, g+16, g+24 (8 rows x 64 contiguous bytes per instruction); sources are aligned down
+    // to 16 bytes, the residue (doff) is re-derived by the consumer from the same address. ----
     MCursor cp{};
-    int p_bytes_full = 0, p_bytes_last = 0, p_cbytes = 0;
+    const uint8_t* psrc[4] = {nullptr, nullptr, nullptr, nullptr};   // this lane's first 16-byte piece of each of its rows
+    int p_da = 0, p_short = 0, p_cbytes = 0;   // p_da: residue mod 16 of the unit's first byte in this lane's rows
     uint32_t p_dst = 0, p_rs8 = 0;   // this lane's first destination in stage 0, 8 row slots further
-    auto prod_run = [&]() {  // per-run constants of the producer's matrix
+    auto prod_run = [&]() {  // per-run constants of the producer's matrix and tile
         const MSeg& sg = p.seg[cp.mat];
-        p_bytes_full = sg.chunk_bytes;
-        p_bytes_last = (sg.nb_row - (p.chunks - 1) * sg.cb) * sg.bb;
         p_cbytes = sg.chunk_bytes;
+        p_short = sg.chunk_bytes - (sg.nb_row - (p.chunks - 1) * sg.cb) * sg.bb;   // bytes the last chunk of a row is short of
         p_dst = ring + (uint32_t)g * sg.row_stride + 16u * t;
         p_rs8 = 8u * sg.row_stride;
+        const uint8_t* base = sg.w + eoff * sg.expert_stride + (long long)cp.chunk * sg.chunk_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint8_t* row = base + (long long)min(cp.tile * kMmaRows + g + 8 * j, sg.n_rows - 1) * sg.row_bytes;
+            const uint32_t da = (uint32_t)((uintptr_t)row & 15u);
+            psrc[j] = row - da + 16 * t;
+            // bytes from this lane's first piece to the end of the row's unit.  The four rows of a lane have the same
+            // residue (8 * row_bytes is a multiple of 16); rows clamped at the ragged end of a matrix may differ by a
+            // few bytes -- their results are discarded and every tensor has 256 bytes of slack
+            if (j == 0) p_da = (int)da;
+        }
     };
     auto issue = [&](uint32_t stage_off, bool l2_only) {
-        const int bytes = (cp.chunk == p.chunks - 1) ? p_bytes_last : p_bytes_full;
-        const uint32_t da = (uint32_t)((uintptr_t)cp.a & 15u), db = (uint32_t)((uintptr_t)cp.b & 15u);
+        const int ea = p_da + p_cbytes - 16 * t - ((cp.chunk == p.chunks - 1) ? p_short : 0);
+        const uint32_t dst = p_dst + stage_off;
         if (l2_only) {
-            if (t * 128 < (int)da + bytes) prefetch_l2(cp.a - da + 128 * t);
-            if (t * 128 < (int)db + bytes) prefetch_l2(cp.b - db + 128 * t);
-        } else {
-            const uint8_t* sa = cp.a - da + 16 * t;
-            const uint8_t* sb = cp.b - db + 16 * t;
-            const uint32_t dst = p_dst + stage_off, dstb = dst + p_rs8;
-            const int ea = (int)da + bytes - 16 * t, eb = (int)db + bytes - 16 * t;  // bytes from this lane's first piece to the end
 #pragma unroll
-            for (int i = 0; i < 5; i++) {  // <= 287 bytes per row and unit
-                if (64 * i < ea) cp_async16(dst + 64 * i, sa + 64 * i);
-                if (64 * i < eb) cp_async16(dstb + 64 * i, sb + 64 * i);
+            for (int j = 0; j < 4; j++)
+                if (112 * t < ea) prefetch_l2(psrc[j] + 112 * t);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; i++) {   // <= 287 bytes per row and unit
+                if (64 * i < ea) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) cp_async16(dst + (uint32_t)j * p_rs8 + 64u * i, psrc[j] + 64 * i);
+                }
             }
         }
         cp.chunk++;
-        if (cp.chunk < p.chunks) {
-            cp.a += p_cbytes;
-            cp.b += p_cbytes;
-        } else {
+        if (cp.chunk == p.chunks) {
             cur_wrap(cp);
             prod_run();
+        } else {   // the sources stay 16-byte aligned: advance by whole pieces, carry the residue
+            const int nd = p_da + p_cbytes, adv = nd & ~15;
+            p_da = nd & 15;
+#pragma unroll
+            for (int j = 0; j < 4; j++) psrc[j] += adv;
         }
     };
 
     MCursor cc{};
     const int pre = min(STAGES - 1, n_units);
     if (n_units > 0 && !p.expert_sel) {
-        // dense weights never depend on a predecessor: pull the first stages towards L2 before the PDL wait
-        // (fire-and-forget; an early cp.async would make the x loads below queue behind DRAM-latency copies)
+        // dense weights never depend on a predecessor: start (or at least pull towards L2) the first stages before
+        // the dependency wait
         cur_init(cp, u0);
         cc = cp;
         prod_run();
         if (early) {
-#pragma unroll
             for (int k = 0; k < STAGES - 1; k++) {
                 if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
                 cp_async_commit();
@@ -720,7 +823,6 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
             prod_run();
         }
     } else if (early && !p.expert_sel) {
-#pragma unroll
         for (int k = 0; k < STAGES - 1; k++) cp_async_commit();
     }
     const bool issued_early = early && !p.expert_sel;
@@ -732,12 +834,11 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         eoff = (long long)p.expert_sel[p.expert_slot];
         if (n_units > 0) { cur_init(cp, u0); cc = cp; prod_run(); }
     }
-    // x: first pass (loads + sum of squares / max) is issued BEFORE the weight copies, the split after them
+    // x: the loads are issued BEFORE the weight copies, the split after them
     XStage xst;
     const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
     stage_x_load(xst, xsrc, p.norm_w, K);
     if (!issued_early) {
-#pragma unroll
         for (int k = 0; k < STAGES - 1; k++) {
             if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
             cp_async_commit();
@@ -749,24 +850,23 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     const float unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
     MMA_STAMP(3);
     const uint32_t tokx = smem_token();
+    const XLayout XL = x_layout(K);
     XSmem sm;
-    sm.xh = sbase + tokx;
-    sm.xl = sm.xh + 2u * K + kXlPad;
-    sm.xs = sm.xh + 4u * K + kXlPad;
-    sm.s32 = sm.xs + (uint32_t)(K >> 2);
-    sm.zero = sbase + tokx + (uint32_t)x_smem_bytes(K) - 256u;
+    sm.p0 = sbase + tokx + XL.p0;
+    sm.p1 = sbase + tokx + XL.p1;
+    sm.p2 = sbase + tokx + XL.p2;
+    sm.sx = sbase + tokx + XL.sx;
+    sm.x16 = sbase + tokx + XL.x16;
+    sm.zero = sbase + tokx + XL.zero;
 
-    // ---- epilogue of a finished tile: lane L < 16 owns row tile*16 + L of segment s (v: lanes 16..31 = up rows) ----
-    auto epilogue = [&](int s, int tile, float v) {
+    // ---- epilogue of a finished tile: lane L owns row tile*32 + L of segment s (vu: the up row for SwiGLU) ----
+    auto epilogue = [&](int s, int tile, float v, float vu) {
         const MSeg& sg = p.seg[s];
-        const int j = tile * 16 + (lane & 15);
-        const bool valid = (lane < 16) && (j < sg.n_rows);
+        const int j = tile * kMmaRows + lane;
+        const bool valid = j < sg.n_rows;
         v *= unscale;
         float val = v;
-        if (swiglu) {
-            const float up = __shfl_sync(0xffffffffu, v, (lane & 15) + 16);
-            val = mma_silu(v) * up;
-        }
+        if (swiglu) val = mma_silu(v) * (vu * unscale);
         if (valid) {
             if (sg.bias) val += sg.bias[j];
             if (p.epi == ME_RESIDUAL) val += p.residual[j];
@@ -783,9 +883,9 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         }
     };
 
-    float ag0 = 0.f, ag1 = 0.f, au0 = 0.f, au1 = 0.f;
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
     int piece_s[2] = {-1, -1}, piece_tile[2] = {0, 0};  // tiles of which this warp holds only a piece (first / last of its run)
-    uint32_t off_c = 0, off_p = (uint32_t)((STAGES - 1) % STAGES) * p.stage_bytes;  // consumer / producer stage offsets
+    uint32_t off_c = 0, off_p = (uint32_t)(STAGES - 1) * p.stage_bytes;  // consumer / producer stage offsets
     const uint32_t ring_bytes = (uint32_t)STAGES * p.stage_bytes;
     int issued = pre, done = 0;
     bool first = true;
@@ -795,68 +895,99 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         const MSeg& wsg = p.seg[cc.mat];
         const int type = wsg.type;
         const uint32_t RS = (uint32_t)wsg.row_stride;
-        const int cbytes = wsg.chunk_bytes;
-        int e0 = cc.chunk * kMmaChunk;
-        uint32_t ca = (uint32_t)(uintptr_t)cc.a, cb = (uint32_t)(uintptr_t)cc.b;  // low address bits: source misalignment
-        float r0 = 0.f, r1 = 0.f;
+        const uint32_t cbytes = (uint32_t)wsg.chunk_bytes;
+        uint32_t e0 = (uint32_t)cc.chunk * kMmaChunk;
+        // low address bits of this lane's first row of the unit: the source misalignment (identical for its four rows,
+        // 8 * row_bytes being a multiple of 16)
+        uint32_t ca = (uint32_t)(uintptr_t)wsg.w + (uint32_t)eoff * (uint32_t)wsg.expert_stride + (uint32_t)cc.chunk * cbytes +
+                      (uint32_t)min(cc.tile * kMmaRows + g, wsg.n_rows - 1) * (uint32_t)wsg.row_bytes;
+        const LaneB lb = (type == T_Q6_K) ? lane_b_q6k(sm, g, t) : (type == T_Q8_0) ? lane_b_q80(sm, g, t) : lane_b_k45(sm, g, t, type == T_Q5_K);
+        // Q6_K: alignment class of the block starts of this run (warp-uniform: rows and tiles differ by multiples of row_bytes)
+        const uint32_t rbm = (uint32_t)wsg.row_bytes | (uint32_t)wsg.expert_stride | (uint32_t)(uintptr_t)wsg.w;
+        float racc[4] = {0.f, 0.f, 0.f, 0.f};
         // one unit: keep the ring full, wait for the oldest stage, consume it
 #define MMA_UNIT(CALL)                                                             \
     for (int i = 0; i < len; i++) {                                                \
         if (issued < n_units) { issue(off_p, false); issued++; }                   \
         off_p = (off_p + p.stage_bytes == ring_bytes) ? 0u : off_p + p.stage_bytes; \
         cp_async_commit();                                                         \
-        cp_async_wait<STAGES - 1>();                                               \
+        cp_async_wait_dyn(STAGES - 1);                                             \
         __syncwarp();                                                              \
         if (first) { MMA_STAMP(4); first = false; }                                \
         const uint32_t sp = ring + off_c + smem_token();                           \
         off_c = (off_c + p.stage_bytes == ring_bytes) ? 0u : off_c + p.stage_bytes; \
-        float a0 = 0.f, a1 = 0.f;                                                  \
+        float ua[4] = {0.f, 0.f, 0.f, 0.f};                                        \
         CALL;                                                                      \
-        pin2(a0, a1); /* the unit's shared-memory reads are complete before the stage can be refilled */ \
-        r0 += a0;                                                                  \
-        r1 += a1;                                                                  \
+        pin4(ua); /* the unit's shared-memory reads are complete before the stage can be refilled */ \
+        racc[0] += ua[0]; racc[1] += ua[1]; racc[2] += ua[2]; racc[3] += ua[3];    \
         e0 += kMmaChunk;                                                           \
         ca += cbytes;                                                              \
-        cb += cbytes;                                                              \
         __syncwarp(); /* every lane is done with this stage */                     \
     }
         switch (type) {
-            case T_Q4_K: MMA_UNIT(unit_k45<false>(sp, RS, 1, e0, sm, g, t, a0, a1)) break;
-            case T_Q5_K: MMA_UNIT(unit_k45<true>(sp, RS, 1, e0, sm, g, t, a0, a1)) break;
-            case T_Q6_K: MMA_UNIT(unit_q6k(sp, RS, 1, e0, ca & 15u, cb & 15u, sm, g, t, a0, a1)) break;
-            default: MMA_UNIT(unit_q80(sp, RS, min(wsg.cb, wsg.nb_row - (e0 >> 5)), e0, ca & 15u, cb & 15u, sm, g, t, a0, a1)) break;
+            case T_Q4_K: MMA_UNIT(unit_k45<false>(sp, RS, e0, sm, lb, g, t, ua)) break;
+            case T_Q5_K: MMA_UNIT(unit_k45<true>(sp, RS, e0, sm, lb, g, t, ua)) break;
+            case T_Q6_K:
+                if ((rbm & 7u) == 0u) {
+                    // block b of a row starts at 210 b: 8-byte aligned for b % 4 == 0, 4-byte for b % 4 == 2, else 2-byte
+                    MMA_UNIT({
+                        const uint32_t dof = ca & 15u;
+                        if ((dof & 7u) == 0u) unit_q6k<8>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                        else if ((dof & 3u) == 0u) unit_q6k<4>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                        else unit_q6k<2>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                    })
+                } else {
+                    MMA_UNIT(unit_q6k<2>(sp, RS, e0, ca & 15u, sm, lb, g, t, ua))
+                }
+                break;
+            default: MMA_UNIT(unit_q80(sp, RS, e0, ca & 15u, min(wsg.cb, wsg.nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua)) break;
         }
 #undef MMA_UNIT
         done += len;
-        if (swiglu && cc.mat == 1) { au0 += r0; au1 += r1; } else { ag0 += r0; ag1 += r1; }
+        if (swiglu && cc.mat == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) au[j] += racc[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ag[j] += racc[j];
+        }
 
         // ---- tile finished (for this warp)? ----
         const int s = cc.s, tile = cc.tile;
         const bool row_end = (cc.chunk + len == p.chunks);
         const bool tile_done = (row_end && (!swiglu || cc.mat == 1)) || (done == n_units);
-        if (row_end) cur_wrap(cc);
+        if (row_end) cur_wrap(cc); else cc.chunk += len;
         if (!tile_done) continue;
         if (done == n_units) MMA_STAMP(5);
 
-        // reduce the 4 lanes of a row group, then lane L holds logical row L (0..15 gate/plain, 16..31 up)
-        ag0 += __shfl_xor_sync(0xffffffffu, ag0, 1); ag0 += __shfl_xor_sync(0xffffffffu, ag0, 2);
-        ag1 += __shfl_xor_sync(0xffffffffu, ag1, 1); ag1 += __shfl_xor_sync(0xffffffffu, ag1, 2);
-        if (swiglu) {
-            au0 += __shfl_xor_sync(0xffffffffu, au0, 1); au0 += __shfl_xor_sync(0xffffffffu, au0, 2);
-            au1 += __shfl_xor_sync(0xffffffffu, au1, 1); au1 += __shfl_xor_sync(0xffffffffu, au1, 2);
+        // reduce the 4 lanes of a row group, then lane L holds logical row L = 8j + n (register j of lanes 4n..4n+3)
+        float vg = 0.f, vu = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], 1);
+            ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], 2);
+            const float x = __shfl_sync(0xffffffffu, ag[j], 4 * (lane & 7));
+            if ((lane >> 3) == j) vg = x;
+            ag[j] = 0.f;
         }
-        const int src = 4 * (lane & 7);
-        const float vg0 = __shfl_sync(0xffffffffu, ag0, src), vg1 = __shfl_sync(0xffffffffu, ag1, src);
-        const float vu0 = __shfl_sync(0xffffffffu, au0, src), vu1 = __shfl_sync(0xffffffffu, au1, src);
-        const float v = (lane < 16) ? ((lane & 8) ? vg1 : vg0) : ((lane & 8) ? vu1 : vu0);
-        ag0 = ag1 = au0 = au1 = 0.f;
+        if (swiglu) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                au[j] += __shfl_xor_sync(0xffffffffu, au[j], 1);
+                au[j] += __shfl_xor_sync(0xffffffffu, au[j], 2);
+                const float x = __shfl_sync(0xffffffffu, au[j], 4 * (lane & 7));
+                if ((lane >> 3) == j) vu = x;
+                au[j] = 0.f;
+            }
+        }
 
         const int tu0 = p.seg[s].unit0 + tile * upt;
         if (u0 <= tu0 && tu0 + upt <= u1) {
-            epilogue(s, tile, v);  // the whole tile is mine
+            epilogue(s, tile, vg, vu);  // the whole tile is mine
         } else {
             const int slot = (u0 >= tu0) ? 0 : 1;  // tile is my first (slot 0) or starts inside my run (slot 1)
-            s_part[warp][slot][lane] = v;
+            s_part[warp][slot][0][lane] = vg;
+            s_part[warp][slot][1][lane] = vu;
             piece_s[slot] = s;
             piece_tile[slot] = tile;
         }
@@ -878,34 +1009,41 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         const int lo_u = max(tu0, cu0), hi_u = min(tu0 + upt, cu1) - 1;
         const int lo = warp_of(lo_u), hi = warp_of(hi_u);
         if (warp != lo) continue;  // the first warp of the CTA that holds a piece finishes the tile
-        float v = 0.f;
+        float v = 0.f, vu = 0.f;
         for (int w = lo; w <= hi; w++) {  // fixed order: deterministic
             const int wu0 = cu0 + (w * cn) / nw, wu1 = cu0 + ((w + 1) * cn) / nw;
             if (wu1 == wu0) continue;     // a warp without units holds no piece
-            v += s_part[w][(wu0 >= tu0) ? 0 : 1][lane];
+            const int ws = (wu0 >= tu0) ? 0 : 1;
+            v += s_part[w][ws][0][lane];
+            vu += s_part[w][ws][1][lane];
         }
         if (tu0 < cu0 || tu0 + upt > cu1) {  // the tile straddles CTAs (tile_mode 0 only)
             const int tile_id = (s == 0 ? 0 : (s == 1 ? p.seg[0].n_tiles : p.seg[0].n_tiles + p.seg[1].n_tiles)) + tile;
             const int c_first = cta_of(tu0), c_last = cta_of(tu0 + upt - 1);
-            p.part[((size_t)cta * 2 + ((cu0 >= tu0) ? 0 : 1)) * 32 + lane] = v;
+            float* mine = p.part + ((size_t)cta * 2 + ((cu0 >= tu0) ? 0 : 1)) * 64;
+            mine[lane] = v;
+            mine[32 + lane] = vu;
             __syncwarp();
             unsigned int ticket = 0;
             if (lane == 0) ticket = atom_add_acq_rel(&p.tickets[tile_id], 1u);
             ticket = __shfl_sync(0xffffffffu, ticket, 0);
             if (ticket != (unsigned)(c_last - c_first)) continue;  // not the last CTA
             v = 0.f;
-            for (int c = c_first; c <= c_last; c++)
-                v += ld_relaxed_gpu(&p.part[((size_t)c * 2 + ((cta_first(c) >= tu0) ? 0 : 1)) * 32 + lane]);
+            vu = 0.f;
+            for (int c = c_first; c <= c_last; c++) {
+                const float* theirs = p.part + ((size_t)c * 2 + ((cta_first(c) >= tu0) ? 0 : 1)) * 64;
+                v += ld_relaxed_gpu(theirs + lane);
+                vu += ld_relaxed_gpu(theirs + 32 + lane);
+            }
             if (lane == 0) p.tickets[tile_id] = 0;
         }
-        epilogue(s, tile, v);
+        epilogue(s, tile, v, vu);
     }
     MMA_STAMP(6);
 }
 
 // Pull the first ring stages of launch/phase `p` towards L2 (fire-and-forget): called by the megakernel for the
 // NEXT phase before it waits at a grid barrier, so the weight stream does not stop at the phase boundary.
-template <int STAGES>
 __device__ __forceinline__ void mma_warm_l2(const MParams& p, int depth) {
     if (p.expert_sel) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -928,20 +1066,17 @@ __device__ __forceinline__ void mma_warm_l2(const MParams& p, int depth) {
     const int n = min(min(depth, u1 - u0), p.chunks - chunk);
     const long long off = (long long)chunk * sg.chunk_bytes;
     const int bytes = n * sg.chunk_bytes;
-    const uint8_t* a = sg.w + (long long)min(tile * 16 + g, sg.n_rows - 1) * sg.row_bytes + off;
-    const uint8_t* b = sg.w + (long long)min(tile * 16 + g + 8, sg.n_rows - 1) * sg.row_bytes + off;
-    for (int o = 128 * t; o < bytes + 127; o += 512) {
-        prefetch_l2(a + o);
-        prefetch_l2(b + o);
+    for (int j = 0; j < 4; j++) {
+        const uint8_t* a = sg.w + (long long)min(tile * kMmaRows + g + 8 * j, sg.n_rows - 1) * sg.row_bytes + off;
+        for (int o = 128 * t; o < bytes + 127; o += 512) prefetch_l2(a + o);
     }
 }
 
-template <int STAGES>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const __grid_constant__ MParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
-    __shared__ float s_part[kMmaMaxWarps][2][32];   // pieces of tiles shared between warps of this CTA
-    mma_gemv_cta<STAGES>(p, smem, s_red, s_part, [] {}, [] { pdl_launch_dependents(); pdl_wait(); }, false, true);
+    __shared__ float s_part[kMmaMaxWarps][2][2][32];   // pieces of tiles shared between warps of this CTA
+    mma_gemv_cta(p, smem, s_red, s_part, [] {}, [] { pdl_launch_dependents(); pdl_wait(); }, false, true);
 }
 
 // ---------------------------------------------------------------- host-side launch planning
@@ -987,9 +1122,10 @@ struct MPlan {
 };
 
 // Fills the derived fields of p (segments' w/out/bias/row_bytes/expert_stride/type/n_rows, n_seg, K, epi
-// must be set) and picks warps/stages so that x + the rings fit in shared memory.  Returns false if the
+// must be set) and picks the ring depth so that x + the rings fit in shared memory.  Returns false if the
 // launch is not eligible for this kernel (caller falls back to the CUDA-core kernel).
 inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size_t smem_limit, MPlan& plan) {
+    (void)want_warps;   // the block is always kMmaMaxWarps warps (the megakernel's block size)
     if (p.K % 32) return false;
     if (p.epi == ME_SWIGLU && (p.n_seg != 2 || p.seg[0].n_rows != p.seg[1].n_rows)) return false;
     int max_rs = 0;
@@ -1004,7 +1140,7 @@ inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size
         sg.bb = type_block_bytes(sg.type);
         sg.chunk_bytes = sg.cb * sg.bb;
         sg.nb_row = p.K / type_block_elems(sg.type);
-        sg.n_tiles = (sg.n_rows + 15) / 16;
+        sg.n_tiles = (sg.n_rows + kMmaRows - 1) / kMmaRows;
         max_rs = std::max(max_rs, sg.row_stride);
     }
     p.chunks = (p.K + kMmaChunk - 1) / kMmaChunk;
@@ -1022,13 +1158,13 @@ inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size
         }
         p.total_units = u;
     }
-    p.stage_bytes = 16 * max_rs;
+    p.stage_bytes = kMmaRows * max_rs;
     const size_t xb = x_smem_bytes(p.K);
-    int warps = std::max(4, std::min(want_warps, kMmaMaxWarps)), stages = std::max(2, std::min(want_stages, kMmaMaxStages));
+    const int warps = kMmaMaxWarps;
+    int stages = std::max(2, std::min(want_stages, kMmaMaxStages));
     auto need = [&](int w, int st) { return xb + (size_t)w * st * p.stage_bytes + 16; };  // +16: funnel loads read one word past a piece
     while (need(warps, stages) > smem_limit) {
         if (stages > 2) stages--;
-        else if (warps > 4) warps -= 2;
         else return false;
     }
     p.stages = stages;
@@ -1042,16 +1178,9 @@ inline bool mma_plan(MParams& p, int n_sm, int want_warps, int want_stages, size
 }
 
 using MmaKernel = void (*)(const MParams);
-inline MmaKernel mma_kernel_for(int stages) {
-    if (stages <= 2) return gemv_mma_kernel<2>;
-    if (stages == 3) return gemv_mma_kernel<3>;
-    return gemv_mma_kernel<4>;
-}
+inline MmaKernel mma_kernel_for(int) { return gemv_mma_kernel; }
 inline cudaError_t mma_set_smem_limit(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    return e;
+    return cudaFuncSetAttribute(gemv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 }  // namespace b200

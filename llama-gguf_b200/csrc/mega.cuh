@@ -129,11 +129,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& ta
 
 // One instantiation per attention shape (head_dim, query heads per kv head rounded up to 4 / 8): a model only ever
 // runs one of them, and the kernel's code footprint matters (every phase starts on a cold instruction path).
-template <int STAGES, int HD, int GMAX>
+template <int HD, int GMAX>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const __grid_constant__ MegaParams mp) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
-    __shared__ float s_part[kMmaMaxWarps][2][32];
+    __shared__ float s_part[kMmaMaxWarps][2][2][32];
     __shared__ unsigned int s_ticket;
     __shared__ int s_flag;
     __shared__ __align__(16) MegaPhase s_phs[3];   // descriptors of the running phase and the next two (ring)
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
         for (int ph = 0; ph < n_run; ph++, gph++) {
             const MegaPhase& cur = s_phs[gph % 3];
             if (cur.kind == PH_GEMV) {
-                mma_gemv_cta<STAGES>(cur.gemv, smem, s_red, s_part, bar_arrive, bar_wait, mp.early != 0, false);
+                mma_gemv_cta(cur.gemv, smem, s_red, s_part, bar_arrive, bar_wait, mp.early != 0, false);
                 if (!ok) return;
             } else {
                 bar_arrive();
