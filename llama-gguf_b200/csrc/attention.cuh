@@ -93,6 +93,10 @@ struct AttnParams {
     const float* freq;     // [hd/2]
     float rope_scale;
     int neox, n_heads;
+    // optional: also write the staged (int8 planes) form of the output vector for the GEMV that consumes it
+    // (gemv_mma.cuh: stage_out32); stage_K = n_heads * hd
+    uint8_t* stage_out;
+    int stage_K;
 };
 
 // KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
@@ -100,6 +104,9 @@ constexpr int kAttnMinChunk = 64;
 __device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits) {
     return max(1, min(n_splits, (kv_len + kAttnMinChunk - 1) / kAttnMinChunk));
 }
+
+// defined in gemv_mma.cuh (stage_out32 without a weight); a warp holds 32 consecutive elements of the output vector
+__device__ __forceinline__ void attn_stage_out(float val, int j, int K, uint8_t* xg);
 
 // merge (m, l, acc) <- (m, l, acc) (+) (m2, l2, acc2)
 __device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca, float& cb, float& mo) {
@@ -246,7 +253,9 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             A += s_acc[(w * GMAX + g) * HD + d] * c;
         }
         if (ns == 1) {  // a single split: this is the answer (no scratch, no ticket)
-            p.out[(kh * G + g) * HD + d] = A / L;
+            const float o = A / L;
+            p.out[(kh * G + g) * HD + d] = o;
+            if (p.stage_out) attn_stage_out(o, (kh * G + g) * HD + d, p.stage_K, p.stage_out);
         } else {
             my_part[g * part_stride + d] = A;
             if (d == 0) {
@@ -284,7 +293,9 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             L += ps[HD + 1] * c;
             A += ps[d] * c;
         }
-        p.out[(kh * G + g) * HD + d] = A / L;
+        const float o = A / L;
+        p.out[(kh * G + g) * HD + d] = o;
+        if (p.stage_out) attn_stage_out(o, (kh * G + g) * HD + d, p.stage_K, p.stage_out);
     }
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }

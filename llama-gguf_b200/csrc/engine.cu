@@ -130,6 +130,7 @@ struct b200_ctx {
     float* mega_cand_val = nullptr;
     int* mega_cand_idx = nullptr;
     float* mega_attn_part = nullptr;
+    uint8_t* mega_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // staged (int8 planes) forms of xa, xb, attn, hbuf
     int mega_splits = 1;
     uint64_t mega_launches = 0;
     unsigned long long* mega_dbg = nullptr;
@@ -540,6 +541,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->mega_cand_val);
     cudaFree(c->mega_cand_idx);
     cudaFree(c->mega_attn_part);
+    for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
                     (void*)c->rope_freq, c->flush_buf, (void*)c->mma_part, (void*)c->mma_tickets, (void*)c->mma_err})
@@ -778,6 +780,7 @@ static int mega_build(b200_ctx* c) {
         mma_deal(m, c->n_sm);  // every phase runs on the full grid of the megakernel
         ph = MegaPhase{};
         ph.kind = PH_GEMV;
+        m.pf_units = env_int("B200_PF_UNITS", 8);
         ph.gemv = m;
         tp_input(ph.gemv);
         smem = std::max(smem, plan.smem);
@@ -790,6 +793,20 @@ static int mega_build(b200_ctx* c) {
         CU_ALLOC(cudaMalloc((void**)&c->mega_cand_idx, c->n_sm * sizeof(int)));
         CU_ALLOC(cudaMalloc((void**)&c->mega_attn_part, (size_t)nkv * c->mega_splits * G * (hd + 2) * sizeof(float)));
     }
+    // single GPU: every activation vector that feeds a GEMV is also kept in its staged form, written by the phase
+    // that produces it (gemv_mma.cuh: stage_out32), so the consuming GEMV copies it instead of converting it per CTA
+    const bool staged = P == 1 && env_int("B200_STAGED_X", 1) && H % 32 == 0 && (nh * hd) % 32 == 0 && d.ffn % 32 == 0;
+    if (staged && !c->mega_stage[0]) {
+        const int ks[4] = {H, H, nh * hd, (int)d.ffn};
+        for (int i = 0; i < 4; i++) {
+            CU_ALLOC(cudaMalloc((void**)&c->mega_stage[i], x_staged_bytes(ks[i]) + 256));
+            CU(cudaMemset(c->mega_stage[i], 0, x_staged_bytes(ks[i]) + 256));
+        }
+    }
+    uint8_t* const st_xa = staged ? c->mega_stage[0] : nullptr;
+    uint8_t* const st_xb = staged ? c->mega_stage[1] : nullptr;
+    uint8_t* const st_attn = staged ? c->mega_stage[2] : nullptr;
+    uint8_t* const st_hbuf = staged ? c->mega_stage[3] : nullptr;
     for (size_t si = 0; si < c->slots.size(); si++) {
         Slot& sl = c->slots[si];
         std::vector<MegaPhase> prog;
@@ -806,6 +823,7 @@ static int mega_build(b200_ctx* c) {
                 p.n_seg = 3; p.K = H; p.x = c->xa; p.norm_w = L.attn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
                 tp_res = c->xb; tp_full = c->xa;   // TP, layers > 0: xa = sum(down partials) + xb
                 if (!gemv_phase(ph, p)) return B200_OK;
+                if (l > 0) ph.gemv.x_staged = st_xa;   // layer 0 reads the embedding row (f32)
                 prog.push_back(ph);
             }
             {   // RoPE + KV write + GQA decode attention
@@ -816,6 +834,7 @@ static int mega_build(b200_ctx* c) {
                 ap.pos = &sl.d_state->pos_cur; ap.kv_len_fixed = 0; ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len;
                 ap.n_splits = c->mega_splits; ap.scale = 1.0f / sqrtf((float)hd);
                 ap.qkv_raw = c->qkv; ap.freq = c->rope_freq; ap.rope_scale = d.rope_scale; ap.neox = d.rope_neox; ap.n_heads = nh;
+                ap.stage_out = st_attn; ap.stage_K = nh * hd;
                 prog.push_back(ph);
             }
             {   // O projection + residual: xb = Wo attn + xa
@@ -824,6 +843,8 @@ static int mega_build(b200_ctx* c) {
                 p.n_seg = 1; p.K = nh * hd; p.x = c->attn; p.epi = EPI_RESIDUAL; p.residual = c->xa;
                 if (!gemv_phase(ph, p)) return B200_OK;
                 tp_output(ph, 0);
+                ph.gemv.x_staged = st_attn;
+                ph.gemv.stage_out = st_xb; ph.gemv.stage_w = L.ffn_norm.f32(); ph.gemv.stage_K = H;
                 prog.push_back(ph);
                 if (P > 1) { tp_pending = 0; tp_res = c->xa; tp_full = c->xb; }   // xb = sum(O partials) + xa
             }
@@ -833,6 +854,8 @@ static int mega_build(b200_ctx* c) {
                 fill_seg(p.seg[1], L.up, c->hbuf, nullptr, 0);
                 p.n_seg = 2; p.K = H; p.x = c->xb; p.norm_w = L.ffn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_SWIGLU;
                 if (!gemv_phase(ph, p)) return B200_OK;
+                ph.gemv.x_staged = st_xb;
+                ph.gemv.stage_out = st_hbuf; ph.gemv.stage_w = nullptr; ph.gemv.stage_K = (int)d.ffn;
                 prog.push_back(ph);
             }
             {   // down + residual: xa = Wd act + xb
@@ -841,6 +864,9 @@ static int mega_build(b200_ctx* c) {
                 p.n_seg = 1; p.K = d.ffn; p.x = c->hbuf; p.epi = EPI_RESIDUAL; p.residual = c->xb;
                 if (!gemv_phase(ph, p)) return B200_OK;
                 tp_output(ph, 1);
+                ph.gemv.x_staged = st_hbuf;
+                ph.gemv.stage_out = st_xa; ph.gemv.stage_K = H;
+                ph.gemv.stage_w = (l + 1 < d.n_layers) ? c->layers[l + 1].attn_norm.f32() : c->output_norm.f32();
                 prog.push_back(ph);
                 if (P > 1) { tp_pending = 1; tp_res = c->xb; tp_full = c->xa; }   // xa = sum(down partials) + xb
             }
@@ -851,6 +877,7 @@ static int mega_build(b200_ctx* c) {
             fill_seg(p.seg[0], head, c->logits, nullptr, 0);
             p.n_seg = 1; p.K = H; p.x = c->xa; p.norm_w = c->output_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
             if (!gemv_phase(ph, p)) return B200_OK;
+            ph.gemv.x_staged = st_xa;
             prog.push_back(ph);
         }
         if (sl.d_phases) cudaFree(sl.d_phases);
@@ -1377,7 +1404,7 @@ extern "C" int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_ty
         DevBuf dpart, dtick;
         if (env_int("B200_GEMV_MMA", 1) && mma_plan(m, prop.multiProcessorCount, 16, 3, lim, plan)) {
             const size_t tiles = (n + 15) / 16;
-            if (dpart.alloc((size_t)plan.grid * 2 * 32 * 4) || dtick.alloc(tiles * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat_q");
+            if (dpart.alloc((size_t)plan.grid * 2 * 64 * 4) || dtick.alloc(tiles * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "vec_mat_q");
             CU(cudaMemset(dtick.p, 0, tiles * 4));
             m.part = dpart.as<float>(); m.tickets = dtick.as<unsigned int>();
             CU(mma_set_smem_limit((int)lim));

@@ -74,8 +74,17 @@ struct MParams {
     // CTA's units evenly
     int n_ctas, tile_mode, cbase, crem;
     int stages;
+    int pf_units;          // megakernel: units per warp (beyond the ring) pulled towards L2 before the barrier wait
     int stage_bytes;       // 32 * max row_stride
     const float* x;        // [K] f32
+    // Producer-staged input (per-token megakernel, single GPU): the phase that produced x also wrote its int8 planes,
+    // group scales / sums and per-group sums of squares (stage_out32); this launch copies them instead of converting
+    // x in every CTA.  The RMSNorm weight is already applied; norm_w != nullptr only says "scale by 1/rms".
+    const uint8_t* x_staged;
+    // Producer side: also write the staged form of the output vector (stage_K rows in total, times stage_w[j])
+    uint8_t* stage_out;
+    const float* stage_w;
+    int stage_K;
     const float* norm_w;   // optional fused RMSNorm weight [K]
     float eps;
     int epi;
@@ -234,7 +243,7 @@ __device__ __forceinline__ void imma_s8s8(int (&c)[4], uint32_t a0, uint32_t a1,
 // The plane bases are 0 / 32 / 64 (mod 128) bytes so that hi / mid / lo loads of one instruction use different banks;
 // 256 zero bytes serve as the B operand of lanes whose columns an MMA does not address.
 struct XLayout {
-    uint32_t p0, p1, p2, sx, x16, zero, total;
+    uint32_t p0, p1, p2, sx, x16, ssq, zero, total;
 };
 __host__ __device__ inline XLayout x_layout(int K) {
     const uint32_t KP = ((uint32_t)K + 127u) & ~127u;
@@ -244,11 +253,14 @@ __host__ __device__ inline XLayout x_layout(int K) {
     L.p2 = 2 * KP + 192;
     L.sx = 3 * KP + 384;
     L.x16 = L.sx + (uint32_t)K / 4;                       // K/32 float2
-    L.zero = ((L.x16 + (uint32_t)K / 4 + 127u) & ~127u) + 96;   // K/16 floats
+    L.ssq = L.x16 + (uint32_t)K / 4;                      // K/16 floats; then K/32 floats: sum of x^2 per group (staged form only)
+    L.zero = ((L.ssq + (uint32_t)K / 8 + 127u) & ~127u) + 96;
     L.total = ((L.zero + 256u + 127u) & ~127u);
     return L;
 }
 __host__ __device__ inline size_t x_smem_bytes(int K) { return x_layout(K).total; }
+// bytes of the staged form of a K-vector in GLOBAL memory (what a producer writes and a consumer copies: no zero page)
+__host__ __device__ inline size_t x_staged_bytes(int K) { return (x_layout(K).zero + 15u) & ~15u; }
 
 struct XSmem {
     uint32_t p0, p1, p2, sx, x16, zero;  // shared-space byte addresses
@@ -369,6 +381,40 @@ __device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, fl
     }
     return inv;
 }
+
+// The staged form of 32 consecutive elements j0..j0+31 (j0 % 32 == 0) of a vector, written to GLOBAL memory by the warp
+// that produced them (lane L holds element j0 + L): the same bytes stage_x_finish would write to shared memory for
+// x * w (w = 1 without a norm weight), plus the group's sum of x^2 (before the weight).  All 32 lanes must call it.
+__device__ __forceinline__ void stage_out32(float val, float w, int j, int K, uint8_t* xg) {
+    const XLayout L = x_layout(K);
+    const bool valid = j < K;
+    const int lane = threadIdx.x & 31;
+    const float x = valid ? val : 0.0f;
+    const float v = x * w;
+    const float am = warp_max(fabsf(v));
+    const int k = x_group_k(am);
+    const float up = __int_as_float((127 + k) << 23), down = __int_as_float((127 - k) << 23);
+    const int i = __float_as_int(fmaf(v, up, 12582912.0f)) - 0x4B400000;
+    const uint32_t z = (uint32_t)(i + 0x808080) ^ 0x808080u;
+    int s16 = i;
+    s16 += __shfl_xor_sync(0xffffffffu, s16, 1);
+    s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
+    s16 += __shfl_xor_sync(0xffffffffu, s16, 4);
+    s16 += __shfl_xor_sync(0xffffffffu, s16, 8);
+    const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 16);
+    const float ssq = warp_sum(x * x);
+    if (!valid) return;   // K % 32 == 0: a group is valid as a whole
+    xg[L.p2 + j] = (uint8_t)(z & 0xFFu);
+    xg[L.p1 + j] = (uint8_t)((z >> 8) & 0xFFu);
+    xg[L.p0 + j] = (uint8_t)((z >> 16) & 0xFFu);
+    if ((lane & 15) == 0) *reinterpret_cast<float*>(xg + L.x16 + 4 * (j >> 4)) = -32.0f * ((float)s16 * down);
+    if (lane == 0) {
+        *reinterpret_cast<float2*>(xg + L.sx + 8 * (j >> 5)) = make_float2(down, (float)s32 * down);
+        *reinterpret_cast<float*>(xg + L.ssq + 4 * (j >> 5)) = ssq;
+    }
+}
+
+__device__ __forceinline__ void attn_stage_out(float val, int j, int K, uint8_t* xg) { stage_out32(val, 1.0f, j, K, xg); }
 
 // ---------------------------------------------------------------- per-type unit kernels
 // sp = shared address of the stage (row slot r at sp + r*RS; the row's bytes start at +doff), e0 = element index of
@@ -827,30 +873,80 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     }
     const bool issued_early = early && !p.expert_sel;
 
-    post_fn();
+    // While the CTA waits for its predecessors (grid barrier of the megakernel), its warps pull the units after the
+    // ring stages towards L2, one instruction (lane = row: 32 lines of 128 bytes) per call, nearest first; the caller
+    // stops calling as soon as the barrier opens, so a late CTA never delays itself (HBM keeps streaming this phase's
+    // weights during the barrier instead of idling).
+    MCursor pfq = cp;
+    int pf_left = (issued_early && n_units > 0) ? min(p.pf_units, n_units - pre) : 0, pf_off = 0, pf_bytes = -1;
+    const uint8_t* pf_a = nullptr;
+    auto prefetch_step = [&]() -> bool {
+        if (pf_left <= 0) return false;
+        if (pf_bytes < 0) {   // next run of the cursor
+            const int len = min(p.chunks - pfq.chunk, pf_left);
+            const MSeg& sg = p.seg[pfq.mat];
+            const uint8_t* a = sg.w + (long long)min(pfq.tile * kMmaRows + lane, sg.n_rows - 1) * sg.row_bytes + (long long)pfq.chunk * sg.chunk_bytes;
+            pf_bytes = len * sg.chunk_bytes + (int)((uintptr_t)a & 127u);
+            pf_a = a - ((uintptr_t)a & 127u);
+            pf_off = 0;
+            pf_left -= len;
+            if (pfq.chunk + len == p.chunks) cur_wrap(pfq); else pfq.chunk += len;
+        }
+        prefetch_l2(pf_a + pf_off);
+        pf_off += 128;
+        if (pf_off >= pf_bytes) pf_bytes = -1;
+        return true;
+    };
+
+    post_fn(prefetch_step);
     MMA_STAMP(1);
 
     if (p.expert_sel) {
         eoff = (long long)p.expert_sel[p.expert_slot];
         if (n_units > 0) { cur_init(cp, u0); cc = cp; prod_run(); }
     }
-    // x: the loads are issued BEFORE the weight copies, the split after them
-    XStage xst;
-    const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
-    stage_x_load(xst, xsrc, p.norm_w, K);
-    if (!issued_early) {
-        for (int k = 0; k < STAGES - 1; k++) {
-            if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
-            cp_async_commit();
+    const XLayout XL = x_layout(K);
+    float unscale = 1.0f;
+    if (p.x_staged) {
+        // the producer of x left its staged form in global memory: a flat copy, no arithmetic
+        if (!issued_early) {
+            for (int k = 0; k < STAGES - 1; k++) {
+                if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
+                cp_async_commit();
+            }
         }
+        const uint32_t n16 = (XL.zero + 15u) >> 4;
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(sbase + 16u * i, p.x_staged + 16u * i);
+        cp_async_commit();
+        MMA_STAMP(2);
+        cp_async_wait<0>();
+        if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(smem + XL.zero)[threadIdx.x] = 0u;
+        __syncthreads();
+        if (p.norm_w) {   // sum of x^2 from the per-group partial sums, in the same order in every warp and CTA
+            const float* ssq = reinterpret_cast<const float*>(smem + XL.ssq);
+            float tot = 0.0f;
+            for (int i = lane; i < (K >> 5); i += 32) tot += ssq[i];
+            tot = warp_sum(tot);
+            unscale = 1.0f / sqrtf(tot / (float)K + p.eps);
+        }
+    } else {
+        // x: the loads are issued BEFORE the weight copies, the split after them
+        XStage xst;
+        const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
+        stage_x_load(xst, xsrc, p.norm_w, K);
+        if (!issued_early) {
+            for (int k = 0; k < STAGES - 1; k++) {
+                if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
+                cp_async_commit();
+            }
+        }
+        MMA_STAMP(2);
+        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red);
+        __syncthreads();
+        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
     }
-    MMA_STAMP(2);
-    stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red);
-    __syncthreads();
-    const float unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
     MMA_STAMP(3);
     const uint32_t tokx = smem_token();
-    const XLayout XL = x_layout(K);
     XSmem sm;
     sm.p0 = sbase + tokx + XL.p0;
     sm.p1 = sbase + tokx + XL.p1;
@@ -864,12 +960,16 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         const MSeg& sg = p.seg[s];
         const int j = tile * kMmaRows + lane;
         const bool valid = j < sg.n_rows;
+        // one round trip for everything the row needs from global memory
+        const float e_bias = (valid && sg.bias) ? sg.bias[j] : 0.0f;
+        const float e_res = (valid && p.epi == ME_RESIDUAL) ? p.residual[j] : 0.0f;
+        const float e_w = (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
         v *= unscale;
         float val = v;
         if (swiglu) val = mma_silu(v) * (vu * unscale);
         if (valid) {
-            if (sg.bias) val += sg.bias[j];
-            if (p.epi == ME_RESIDUAL) val += p.residual[j];
+            val += e_bias;
+            val += e_res;
             if (p.epi == ME_SCALED_ACC) {  // moe.rs:363-368
                 const float prev = p.expert_slot == 0 ? 0.0f : sg.out[j];
                 val = prev + p.expert_wt[p.expert_slot] * val;
@@ -881,6 +981,7 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
                 sg.out[j] = val;
             }
         }
+        if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);   // the next GEMV's input, ready to copy
     };
 
     float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
@@ -928,17 +1029,15 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
             case T_Q4_K: MMA_UNIT(unit_k45<false>(sp, RS, e0, sm, lb, g, t, ua)) break;
             case T_Q5_K: MMA_UNIT(unit_k45<true>(sp, RS, e0, sm, lb, g, t, ua)) break;
             case T_Q6_K:
-                if ((rbm & 7u) == 0u) {
-                    // block b of a row starts at 210 b: 8-byte aligned for b % 4 == 0, 4-byte for b % 4 == 2, else 2-byte
-                    MMA_UNIT({
-                        const uint32_t dof = ca & 15u;
-                        if ((dof & 7u) == 0u) unit_q6k<8>(sp, RS, e0, dof, sm, lb, g, t, ua);
-                        else if ((dof & 3u) == 0u) unit_q6k<4>(sp, RS, e0, dof, sm, lb, g, t, ua);
-                        else unit_q6k<2>(sp, RS, e0, dof, sm, lb, g, t, ua);
-                    })
-                } else {
-                    MMA_UNIT(unit_q6k<2>(sp, RS, e0, ca & 15u, sm, lb, g, t, ua))
-                }
+                // block b of a row starts at 210 b: 8-byte aligned for b % 4 == 0, 4-byte for b % 4 == 2, else 2-byte (when
+                // the rows themselves are 8-byte aligned; the generic variant takes any even residue)
+                MMA_UNIT({
+                    const uint32_t dof = ca & 15u;
+                    const uint32_t cls = (rbm & 7u) ? 1u : (dof & 7u);
+                    if (cls == 0u) unit_q6k<8>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                    else if (cls == 4u) unit_q6k<4>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                    else unit_q6k<2>(sp, RS, e0, dof, sm, lb, g, t, ua);
+                })
                 break;
             default: MMA_UNIT(unit_q80(sp, RS, e0, ca & 15u, min(wsg.cb, wsg.nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua)) break;
         }
@@ -1076,7 +1175,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) gemv_mma_kernel(const __
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_red[2 * kMmaMaxWarps];
     __shared__ float s_part[kMmaMaxWarps][2][2][32];   // pieces of tiles shared between warps of this CTA
-    mma_gemv_cta(p, smem, s_red, s_part, [] {}, [] { pdl_launch_dependents(); pdl_wait(); }, false, true);
+    mma_gemv_cta(p, smem, s_red, s_part, [] {}, [](auto&&) { pdl_launch_dependents(); pdl_wait(); }, false, true);
 }
 
 // ---------------------------------------------------------------- host-side launch planning

@@ -103,6 +103,32 @@ __device__ __forceinline__ void grid_arrive(unsigned int* bar, unsigned int& tar
     target += gridDim.x;
     if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
 }
+// grid_wait_busy: the warps that do not poll call busy() (one small piece of independent work per call, e.g. an L2
+// prefetch of the next weights) until it returns false or thread 0 has seen the barrier open (s_open == target).
+template <class Busy>
+__device__ __forceinline__ bool grid_wait_busy(unsigned int* bar, unsigned int target, int* err, int* s_flag, volatile unsigned int* s_open,
+                                               Busy&& busy) {
+    if (threadIdx.x == 0) {
+        unsigned int v = 0;
+        int ok = 1;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 3000000000LL) {  // ~1.5 s
+                ok = 0;
+                atomicExch(err, 2);
+                break;
+            }
+        }
+        *s_flag = ok;
+        *s_open = target;
+    } else if (threadIdx.x >= 32) {
+        while (*s_open != target && busy()) {}
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
 __device__ __forceinline__ bool grid_wait(unsigned int* bar, unsigned int target, int* err, int* s_flag) {
     if (threadIdx.x == 0) {
         unsigned int v = 0;
@@ -136,6 +162,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     __shared__ float s_part[kMmaMaxWarps][2][2][32];
     __shared__ unsigned int s_ticket;
     __shared__ int s_flag;
+    __shared__ unsigned int s_open;
     __shared__ __align__(16) MegaPhase s_phs[3];   // descriptors of the running phase and the next two (ring)
     __shared__ float s_av[kMmaMaxWarps];
     __shared__ int s_ai[kMmaMaxWarps];
@@ -155,6 +182,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     };
     fetch_desc(0);
     fetch_desc(1);
+    if (tid == 0) s_open = 0u;
     __syncthreads();  // phase 0 looks at its descriptor before it reaches a barrier
     long long gph = 0;  // phases executed so far in this launch
     unsigned int tp_n = 0;  // cross-GPU exchanges so far in this launch
@@ -189,9 +217,9 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
             }
             grid_arrive(mp.bar, target);
         };
-        auto bar_wait = [&]() {
+        auto bar_wait = [&](auto&& busy) {
             fetch_desc(gph + 2);
-            ok = grid_wait(mp.bar, target, mp.err, &s_flag);
+            ok = grid_wait_busy(mp.bar, target, mp.err, &s_flag, &s_open, busy);
             if (ok && prev_tp_sync) ok = tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag);
             if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[stamp] = gtimer();
             stamp++;
@@ -204,7 +232,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
                 if (!ok) return;
             } else {
                 bar_arrive();
-                bar_wait();
+                bar_wait([] { return false; });
                 if (!ok) return;
                 const AttnParams& ap = cur.attn;
                 const int kv_len = *ap.pos + 1;
@@ -221,7 +249,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
         // the barrier that ends the last phase of the token
         gph--;  // fetch_desc(gph + 2) inside bar_wait: keep the ring consistent with the loop above
         bar_arrive();
-        bar_wait();
+        bar_wait([] { return false; });
         gph++;
         if (!ok) return;
 
