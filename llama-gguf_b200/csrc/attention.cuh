@@ -34,7 +34,14 @@ struct RopeKvParams {
     const int* pos;        // device scalar: position of the current token
     int n_heads, n_kv, hd, max_seq, neox;
     float rope_scale;
+    long long kv_head_stride, kv_pos_stride;   // floats; 0 = the reference layout [n_kv][max_seq][hd]
 };
+// offset (floats) of row (kv head, position) in a K or V cache
+template <class P>
+__device__ __forceinline__ size_t kv_row(const P& p, int kh, int pos, int hd) {
+    return p.kv_pos_stride ? (size_t)kh * (size_t)p.kv_head_stride + (size_t)pos * (size_t)p.kv_pos_stride
+                           : ((size_t)kh * p.max_seq + pos) * hd;
+}
 
 // Backend::rope + cache write.  One thread per rotated pair, then one per v element.
 __global__ void rope_kv_kernel(const RopeKvParams p) {
@@ -60,7 +67,7 @@ __global__ void rope_kv_kernel(const RopeKvParams p) {
             } else {
                 const int kh = head - p.n_heads;
                 const float* d = p.k + (size_t)kh * p.hd;
-                float* o = p.k_cache + ((size_t)kh * p.max_seq + pos) * p.hd;
+                float* o = p.k_cache + kv_row(p, kh, pos, p.hd);
                 const float x0 = d[i0], x1 = d[i1];
                 o[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
                 o[i1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
@@ -68,7 +75,7 @@ __global__ void rope_kv_kernel(const RopeKvParams p) {
         } else {
             const int j = i - n_pairs;
             const int kh = j / p.hd, d = j - kh * p.hd;
-            p.v_cache[((size_t)kh * p.max_seq + pos) * p.hd + d] = p.v[j];
+            p.v_cache[kv_row(p, kh, pos, p.hd) + d] = p.v[j];
         }
     }
 }
@@ -97,10 +104,24 @@ struct AttnParams {
     // (gemv_mma.cuh: stage_out32); stage_K = n_heads * hd
     uint8_t* stage_out;
     int stage_K;
+    // optional strides (floats) of a position-major cache ([pos][k|v][n_kv][hd]); 0 = the reference layout
+    // [n_kv][max_seq][hd] (model/mod.rs:83-108), which is what the engine uses (position-major measured no faster)
+    long long kv_head_stride, kv_pos_stride;
+    unsigned long long* dbg;   // optional [grid][8] globaltimer stamps of thread 0 (debug timelines)
 };
+__device__ __forceinline__ void attn_stamp(const AttnParams& p, int i) {
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.dbg[(size_t)blockIdx.x * 8 + i] = t;
+    }
+}
 
 // KV positions per split: short contexts use few CTAs (the grid is sized for max_seq; surplus CTAs exit at once)
-constexpr int kAttnMinChunk = 64;
+#ifndef B200_ATTN_MIN_CHUNK
+#define B200_ATTN_MIN_CHUNK 32
+#endif
+constexpr int kAttnMinChunk = B200_ATTN_MIN_CHUNK;
 __device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits) {
     return max(1, min(n_splits, (kv_len + kAttnMinChunk - 1) / kAttnMinChunk));
 }
@@ -119,7 +140,7 @@ __device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca
 // floats (>= 64*GMAX + GMAX); s_ticket: one shared word.
 template <int HD, int GMAX, int NW>
 __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, int split, int kv_len, float* sm,
-                                                 unsigned int* s_ticket) {
+                                                 unsigned int* s_ticket, const float* s_rope = nullptr) {
     constexpr int VEC = HD / 32;  // floats per lane per row
     constexpr int NT = NW * 32;
     float* s_m = sm;                      // [warps][GMAX]
@@ -137,35 +158,40 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
     const int end = min(kv_len, start + chunk);
 
     if (p.qkv_raw) {  // Backend::rope (cpu/ops.rs:1216-1337) + cache write (layers.rs:580-600)
+        // s_rope (per-token table of the megakernel: cos[pi], sin[pi] at [pi], [HD/2 + pi]) holds exactly the values
+        // computed below; every global load of this block is issued before the first use (one round trip)
         const int pos = kv_len - 1, half = HD / 2;
         const float position = (float)pos / p.rope_scale;
+        const bool own = pos >= start && pos < end;   // this split writes the cache rows of the new position
+        const float* kraw = p.qkv_raw + (size_t)p.n_heads * HD + (size_t)kh * HD;
+        const float* vraw = p.qkv_raw + (size_t)(p.n_heads + p.n_kv) * HD + (size_t)kh * HD;
         for (int idx = threadIdx.x; idx < G * half; idx += NT) {
             const int g = idx / half, pi = idx - g * half;
-            const float theta = position * p.freq[pi];
-            const float c = cosf(theta), sn = sinf(theta);
             const int i0 = p.neox ? pi : 2 * pi, i1 = p.neox ? pi + half : 2 * pi + 1;
             const float* d = p.qkv_raw + (size_t)(kh * G + g) * HD;
             const float x0 = d[i0], x1 = d[i1];
+            const bool kk = own && idx < half;        // the first `half` threads also rotate the k row
+            const float k0 = kk ? kraw[i0] : 0.f, k1 = kk ? kraw[i1] : 0.f;
+            const bool vv = own && idx < HD;
+            const float v0 = vv ? vraw[idx] : 0.f;
+            float c, sn;
+            if (s_rope) { c = s_rope[pi]; sn = s_rope[half + pi]; }
+            else { const float theta = position * p.freq[pi]; c = cosf(theta); sn = sinf(theta); }
             s_q[g * HD + i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
             s_q[g * HD + i1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
-        }
-        if (pos >= start && pos < end) {
-            const float* kraw = p.qkv_raw + (size_t)p.n_heads * HD + (size_t)kh * HD;
-            const float* vraw = p.qkv_raw + (size_t)(p.n_heads + p.n_kv) * HD + (size_t)kh * HD;
-            float* ko = const_cast<float*>(p.k_cache) + ((size_t)kh * p.max_seq + pos) * HD;
-            float* vo = const_cast<float*>(p.v_cache) + ((size_t)kh * p.max_seq + pos) * HD;
-            for (int pi = threadIdx.x; pi < half; pi += NT) {
-                const float theta = position * p.freq[pi];
-                const float c = cosf(theta), sn = sinf(theta);
-                const int i0 = p.neox ? pi : 2 * pi, i1 = p.neox ? pi + half : 2 * pi + 1;
-                const float x0 = kraw[i0], x1 = kraw[i1];
-                ko[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
-                ko[i1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+            if (kk) {
+                float* ko = const_cast<float*>(p.k_cache) + kv_row(p, kh, pos, HD);
+                ko[i0] = __fsub_rn(__fmul_rn(k0, c), __fmul_rn(k1, sn));
+                ko[i1] = __fadd_rn(__fmul_rn(k0, sn), __fmul_rn(k1, c));
             }
-            for (int d = threadIdx.x; d < HD; d += NT) vo[d] = vraw[d];
+            if (vv) const_cast<float*>(p.v_cache)[kv_row(p, kh, pos, HD) + idx] = v0;
+        }
+        if (own && G * half < HD) {   // fewer rotated q pairs than v elements (G == 1): the rest of the v row
+            for (int d = G * half + threadIdx.x; d < HD; d += NT) const_cast<float*>(p.v_cache)[kv_row(p, kh, pos, HD) + d] = vraw[d];
         }
         __syncthreads();
     }
+    attn_stamp(p, 2);
 
     float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
 #pragma unroll
@@ -178,53 +204,110 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             q[g][v] = (g < G) ? (p.qkv_raw ? s_q[g * HD + lane * VEC + v] : p.q[((size_t)(kh * G + g)) * HD + lane * VEC + v]) : 0.0f;
         }
     }
-    const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
-    const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+    const float* kb = p.k_cache + kv_row(p, kh, 0, HD) + lane * VEC;
+    const float* vb = p.v_cache + kv_row(p, kh, 0, HD) + lane * VEC;
+    const size_t pstride = p.kv_pos_stride ? (size_t)p.kv_pos_stride : (size_t)HD;
 
-    constexpr int UNR = 4;  // positions in flight per warp
-    for (int pos0 = start + warp; pos0 < end; pos0 += NW * UNR) {
-        float kr[UNR][VEC], vr[UNR][VEC];
+    // A warp owns positions start + warp + i * NW.  Batches of UB positions: all dot products and their warp reductions
+    // of a batch are independent, one running-max update per batch (block-wise online softmax), and the K/V rows of
+    // the next batch are in flight while this one is computed (two register buffers).
+    constexpr int UB = 4;
+    constexpr int STEP = NW * UB;
+    auto load = [&](int pos0, float (&kr)[UB][VEC], float (&vr)[UB][VEC]) {
 #pragma unroll
-        for (int u = 0; u < UNR; u++) {
+        for (int u = 0; u < UB; u++) {
             const int pp = pos0 + u * NW;
             const int pc = pp < end ? pp : pos0;  // clamp: loads stay in range, result discarded
             if constexpr (VEC == 4) {
-                float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * HD);
-                float4 b = *reinterpret_cast<const float4*>(vb + (size_t)pc * HD);
+                const float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * pstride);
+                const float4 b = *reinterpret_cast<const float4*>(vb + (size_t)pc * pstride);
                 kr[u][0] = a.x; kr[u][1] = a.y; kr[u][2] = a.z; kr[u][3] = a.w;
                 vr[u][0] = b.x; vr[u][1] = b.y; vr[u][2] = b.z; vr[u][3] = b.w;
             } else {
-                float2 a = *reinterpret_cast<const float2*>(kb + (size_t)pc * HD);
-                float2 b = *reinterpret_cast<const float2*>(vb + (size_t)pc * HD);
+                const float2 a = *reinterpret_cast<const float2*>(kb + (size_t)pc * pstride);
+                const float2 b = *reinterpret_cast<const float2*>(vb + (size_t)pc * pstride);
                 kr[u][0] = a.x; kr[u][1] = a.y;
                 vr[u][0] = b.x; vr[u][1] = b.y;
             }
         }
+    };
+#ifdef B200_ATTN_PROBE
+    long long pr_t0 = clock64();
+    int pr_n = 0;
+#define ATTN_PROBE(i) do { if (p.dbg && threadIdx.x == 0 && pr_n == 1) p.dbg[(size_t)blockIdx.x * 8 + (i)] = (unsigned long long)(clock64() - pr_t0); } while (0)
+#else
+#define ATTN_PROBE(i) do {} while (0)
+#endif
+    auto compute = [&](int pos0, const float (&kr)[UB][VEC], const float (&vr)[UB][VEC]) {
+#ifdef B200_ATTN_PROBE
+        pr_n++;
+        if (pr_n == 1) pr_t0 = clock64();
+#endif
+        float s[UB][GMAX];
 #pragma unroll
-        for (int u = 0; u < UNR; u++) {
-            const int pp = pos0 + u * NW;
-            if (pp < end) {  // warp-uniform
+        for (int u = 0; u < UB; u++)
 #pragma unroll
-                for (int g = 0; g < GMAX; g++) {
-                    if (g < G) {
-                        float d = 0.0f;
+            for (int g = 0; g < GMAX; g++) {
+                float d = 0.0f;
 #pragma unroll
-                        for (int v = 0; v < VEC; v++) d = fmaf(q[g][v], kr[u][v], d);
-                        d = warp_sum(d) * p.scale;
-                        const float mn = fmaxf(m[g], d);
-                        const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
-                        const float w = expf(d - mn);
-                        l[g] = l[g] * corr + w;
-#pragma unroll
-                        for (int v = 0; v < VEC; v++) acc[g][v] = fmaf(w, vr[u][v], acc[g][v] * corr);
-                        m[g] = mn;
-                    }
-                }
+                for (int v = 0; v < VEC; v++) d = fmaf(q[g][v], kr[u][v], d);
+                s[u][g] = d;
             }
+        ATTN_PROBE(4);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+#pragma unroll
+                for (int g = 0; g < GMAX; g++) s[u][g] += __shfl_xor_sync(0xffffffffu, s[u][g], o);
+        ATTN_PROBE(5);
+#pragma unroll
+        for (int g = 0; g < GMAX; g++) {
+            if (g < G) {
+                float mb = -INFINITY;
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    s[u][g] = (pos0 + u * NW < end) ? s[u][g] * p.scale : -INFINITY;   // warp-uniform
+                    mb = fmaxf(mb, s[u][g]);
+                }
+                const float mn = fmaxf(m[g], mb);   // finite: the first position of a batch is always valid
+                const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
+                float w[UB], ws = 0.0f;
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    w[u] = (s[u][g] == -INFINITY) ? 0.0f : expf(s[u][g] - mn);
+                    ws += w[u];
+                }
+                l[g] = l[g] * corr + ws;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    float a = acc[g][v] * corr;
+#pragma unroll
+                    for (int u = 0; u < UB; u++) a = fmaf(w[u], vr[u][v], a);
+                    acc[g][v] = a;
+                }
+                m[g] = mn;
+            }
+        }
+        ATTN_PROBE(6);
+    };
+    {
+        float kA[UB][VEC], vA[UB][VEC], kB[UB][VEC], vB[UB][VEC];
+        int pos0 = start + warp;
+        if (pos0 < end) load(pos0, kA, vA);
+        while (pos0 < end) {
+            if (pos0 + STEP < end) load(pos0 + STEP, kB, vB);
+            compute(pos0, kA, vA);
+            pos0 += STEP;
+            if (pos0 >= end) break;
+            if (pos0 + STEP < end) load(pos0 + STEP, kA, vA);
+            compute(pos0, kB, vB);
+            pos0 += STEP;
         }
     }
 
     // ---- combine the warps of this CTA ----
+    attn_stamp(p, 3);
 #pragma unroll
     for (int g = 0; g < GMAX; g++) {
         if (g < G) {
@@ -267,6 +350,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
     if (ns == 1) return;
 
     // ---- last CTA of this kv head merges the splits ----
+    attn_stamp(p, 4);
     __syncthreads();
     if (threadIdx.x == 0) {  // release: this CTA's partials are visible; acquire: so are the others'
         unsigned int t;
@@ -274,6 +358,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
         *s_ticket = t;
     }
     __syncthreads();
+    attn_stamp(p, 5);
     if (*s_ticket != (unsigned)(ns - 1)) return;
     // all partials of this kv head -> shared memory in one round trip, then merge from there
     const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
@@ -297,6 +382,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
         p.out[(kh * G + g) * HD + d] = o;
         if (p.stage_out) attn_stage_out(o, (kh * G + g) * HD + d, p.stage_K, p.stage_out);
     }
+    attn_stamp(p, 6);
     if (threadIdx.x == 0) p.tickets[kh] = 0;  // ready for the next launch / graph replay
 }
 

@@ -1145,8 +1145,8 @@ extern "C" int b200_debug_mega_phase(b200_ctx* c, int phase, unsigned long long*
         cudaMemset(buf, 0, n * 8);
         MegaPhase ph;
         cudaMemcpy(&ph, c->slots[0].d_phases + phase, sizeof ph, cudaMemcpyDeviceToHost);
-        if (ph.kind != PH_GEMV) return 0;
-        ph.gemv.dbg = buf;
+        if (ph.kind == PH_GEMV) ph.gemv.dbg = buf;
+        else ph.attn.dbg = buf;
         cudaMemcpy(c->slots[0].d_phases + phase, &ph, sizeof ph, cudaMemcpyHostToDevice);
         return 1;
     }

@@ -1027,7 +1027,9 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
     }
         switch (type) {
             case T_Q4_K: MMA_UNIT(unit_k45<false>(sp, RS, e0, sm, lb, g, t, ua)) break;
+#ifndef B200_LEAN_TEST
             case T_Q5_K: MMA_UNIT(unit_k45<true>(sp, RS, e0, sm, lb, g, t, ua)) break;
+#endif
             case T_Q6_K:
                 // block b of a row starts at 210 b: 8-byte aligned for b % 4 == 0, 4-byte for b % 4 == 2, else 2-byte (when
                 // the rows themselves are 8-byte aligned; the generic variant takes any even residue)
@@ -1039,7 +1041,11 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
                     else unit_q6k<2>(sp, RS, e0, dof, sm, lb, g, t, ua);
                 })
                 break;
+#ifndef B200_LEAN_TEST
             default: MMA_UNIT(unit_q80(sp, RS, e0, ca & 15u, min(wsg.cb, wsg.nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua)) break;
+#else
+            default: break;
+#endif
         }
 #undef MMA_UNIT
         done += len;

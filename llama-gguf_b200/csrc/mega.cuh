@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
     __shared__ int s_flag;
     __shared__ unsigned int s_open;
     __shared__ __align__(16) MegaPhase s_phs[3];   // descriptors of the running phase and the next two (ring)
+    __shared__ float s_rope[HD];   // per-token RoPE table: cos(theta_i) at [i], sin(theta_i) at [HD/2 + i]
     __shared__ float s_av[kMmaMaxWarps];
     __shared__ int s_ai[kMmaMaxWarps];
 
@@ -228,20 +229,60 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) mega_decode_kernel(const
         for (int ph = 0; ph < n_run; ph++, gph++) {
             const MegaPhase& cur = s_phs[gph % 3];
             if (cur.kind == PH_GEMV) {
-                mma_gemv_cta(cur.gemv, smem, s_red, s_part, bar_arrive, bar_wait, mp.early != 0, false);
+                // The GEMV that feeds an attention phase (QKV): while its barrier is closed, the waiting warps first pull
+                // the K/V rows that attention will read (positions 0..pos of this layer, cold in HBM: the weight stream
+                // has flushed L2 since the previous token) towards L2, then the GEMV's own next weights.
+                const MegaPhase& nxt = s_phs[(gph + 1) % 3];
+                #ifndef B200_KV_PF
+#define B200_KV_PF 0
+#endif
+                const bool kv_pf = B200_KV_PF && (ph + 1 < n_run) && nxt.kind == PH_ATTN && tid >= 32;
+                // (real loads, results discarded: a prefetch instruction is dropped on a TLB miss, and the page walk is most
+                // of the latency of the first K/V access of a layer).  Position-major caches: rows 0..pos are contiguous.
+                long long kv_li = (long long)blockIdx.x * ((NW - 1) * 32) + (tid - 32);
+                const long long kv_lines = (kv_pf && nxt.attn.kv_pos_stride) ? ((long long)(*nxt.attn.pos + 1) * nxt.attn.kv_pos_stride) / 32 : 0;
+                auto wait_kv = [&](auto&& busy) {
+                    bar_wait([&]() -> bool {
+                        if (kv_li < kv_lines) {
+                            unsigned int sink;
+                            asm volatile("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(sink) : "l"(nxt.attn.k_cache + 32 * kv_li));
+                            kv_li += (long long)gridDim.x * ((NW - 1) * 32);
+                            return true;
+                        }
+                        return busy();
+                    });
+                };
+                mma_gemv_cta(cur.gemv, smem, s_red, s_part, bar_arrive, wait_kv, mp.early != 0, false);
                 if (!ok) return;
             } else {
+                attn_stamp(cur.attn, 0);
                 bar_arrive();
                 bar_wait([] { return false; });
                 if (!ok) return;
                 const AttnParams& ap = cur.attn;
+                attn_stamp(ap, 1);
                 const int kv_len = *ap.pos + 1;
+                if (ph == 1) {   // first attention phase of the token: the rotation angles (Backend::rope, cpu/ops.rs:1216-1337)
+                    const float position = (float)(kv_len - 1) / ap.rope_scale;
+                    for (int pi = tid; pi < HD / 2; pi += NW * 32) {
+                        const float theta = position * ap.freq[pi];
+                        s_rope[pi] = cosf(theta);
+                        s_rope[HD / 2 + pi] = sinf(theta);
+                    }
+                    __syncthreads();
+                }
                 const int n_items = ap.n_kv * ap.n_splits;
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                     const int kh = item / ap.n_splits, split = item - kh * ap.n_splits;
                     float* sm = reinterpret_cast<float*>(smem);
-                    attn_decode_item<HD, GMAX, NW>(ap, kh, split, kv_len, sm, &s_ticket);
+                    attn_decode_item<HD, GMAX, NW>(ap, kh, split, kv_len, sm, &s_ticket, s_rope);
                     __syncthreads();
+#ifdef B200_ATTN_TWICE   // experiment: the same item again with a warm instruction cache (single-split configs only)
+                    attn_stamp(ap, 4);
+                    attn_decode_item<HD, GMAX, NW>(ap, kh, split, kv_len, sm, &s_ticket, s_rope);
+                    __syncthreads();
+                    attn_stamp(ap, 5);
+#endif
                 }
             }
             prev_tp_sync = cur.tp_sync != 0;
