@@ -143,6 +143,9 @@ B200_API int b200_get_hidden(b200_ctx* ctx, int seq, int layer, float* out);
 B200_API int b200_debug_mega_timeline(b200_ctx* ctx, unsigned long long* out, int max_n);
 B200_API int b200_debug_read(b200_ctx* ctx, int which, float* out, int n);
 B200_API int b200_debug_mega_phase(b200_ctx* ctx, int phase, unsigned long long* out, int max_n);
+/* Watchdog words of the tensor-pipe / megakernel paths: out8[0] = 0 when no bounded wait ever gave up, else
+ * (code, which wait, CTA, sequence number); clears them. */
+B200_API int b200_debug_err(b200_ctx* ctx, int* out8);
 /* Statistics for bench.py: kernels launched by this library since creation. */
 B200_API int b200_ctx_stats(b200_ctx* ctx, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos);
 /* Roofline probe: replays only the dequant-GEMV launches of one token (same arguments and order

@@ -136,6 +136,11 @@ __device__ __forceinline__ void softmax_merge_scale(float m, float m2, float& ca
     cb = (m2 == -INFINITY) ? 0.0f : expf(m2 - mo);
 }
 
+// Barrier of the NT threads that execute an item: named barrier 1, so that the streamed megakernel (stream.cuh) can
+// run an extra producer warp that never joins (in the stand-alone kernels NT is the whole CTA).
+template <int NT>
+__device__ __forceinline__ void attn_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
 // One (kv head, KV split) work item, executed by the NW warps of a CTA.  sm: (2*NW*GMAX + NW*GMAX*HD + GMAX*HD)
 // floats (>= 64*GMAX + GMAX); s_ticket: one shared word.
 template <int HD, int GMAX, int NW>
@@ -189,7 +194,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
         if (own && G * half < HD) {   // fewer rotated q pairs than v elements (G == 1): the rest of the v row
             for (int d = G * half + threadIdx.x; d < HD; d += NT) const_cast<float*>(p.v_cache)[kv_row(p, kh, pos, HD) + d] = vraw[d];
         }
-        __syncthreads();
+        attn_sync<NT>();
     }
     attn_stamp(p, 2);
 
@@ -319,7 +324,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             for (int v = 0; v < VEC; v++) s_acc[(warp * GMAX + g) * HD + lane * VEC + v] = acc[g][v];
         }
     }
-    __syncthreads();
+    attn_sync<NT>();
     const int part_stride = HD + 2;
     float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;  // slots sized for n_splits
     for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
@@ -351,13 +356,13 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
 
     // ---- last CTA of this kv head merges the splits ----
     attn_stamp(p, 4);
-    __syncthreads();
+    attn_sync<NT>();
     if (threadIdx.x == 0) {  // release: this CTA's partials are visible; acquire: so are the others'
         unsigned int t;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.tickets + kh) : "memory");
         *s_ticket = t;
     }
-    __syncthreads();
+    attn_sync<NT>();
     attn_stamp(p, 5);
     if (*s_ticket != (unsigned)(ns - 1)) return;
     // all partials of this kv head -> shared memory in one round trip, then merge from there
@@ -365,7 +370,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
     const int n_part = ns * G * part_stride;     // contiguous: splits 0..ns-1 of this head
     float* s_p = sm;                             // [ns][G][HD + 2]   (fits: ns <= NW * GMAX * HD / (G * (HD+2)) is checked by the host)
     for (int i = threadIdx.x; i < n_part; i += NT) s_p[i] = __ldcg(parts + i);
-    __syncthreads();
+    attn_sync<NT>();
     for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
         const int g = idx / HD, d = idx - g * HD;
         float M = -INFINITY;

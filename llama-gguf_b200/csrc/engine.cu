@@ -9,6 +9,7 @@
 // f32 logits out (none at all in b200_decode_greedy).  Kernel-to-kernel edges are
 // programmatic dependent launches so the next kernel's weight prefetch overlaps the
 // tail of the previous one.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -27,6 +28,7 @@
 #include "mega.cuh"
 #include "misc.cuh"
 #include "quant.cuh"
+#include "stream.cuh"
 
 using namespace b200;
 
@@ -134,6 +136,11 @@ struct b200_ctx {
     int mega_splits = 1;
     uint64_t mega_launches = 0;
     unsigned long long* mega_dbg = nullptr;
+    // streamed megakernel (stream.cuh): TMA tensor maps of the weight matrices, ring geometry
+    bool use_stream = true, stream_ok = false;
+    void* d_tmaps = nullptr;
+    size_t stream_smem = 0;
+    int stream_ring_off = 0, stream_slots = 0;
     // tensor parallel (one context per rank/GPU; c->d holds the LOCAL head / ffn counts, dg the global ones)
     b200_model_desc dg{};
     int vocab_l = 0;                     // rows of the vocab head owned by this rank
@@ -229,6 +236,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_taps = env_int("B200_TAPS", 0) != 0;
     c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
     c->use_mega = env_int("B200_MEGA", 1) != 0;
+    c->use_stream = env_int("B200_STREAM", 1) != 0;
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -422,8 +430,8 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     c->mma_tickets_n = (int)((std::max<uint64_t>(std::max<uint64_t>(V, 2 * ffn_w), (nh + 2 * nkv) * hd) + 15) / 16 + 8);
     CU_ALLOC(cudaMalloc((void**)&c->mma_tickets, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
     CU(cudaMemset(c->mma_tickets, 0, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
-    CU_ALLOC(cudaMalloc((void**)&c->mma_err, sizeof(int)));
-    CU(cudaMemset(c->mma_err, 0, sizeof(int)));
+    CU_ALLOC(cudaMalloc((void**)&c->mma_err, 8 * sizeof(int)));
+    CU(cudaMemset(c->mma_err, 0, 8 * sizeof(int)));
     CU_ALLOC(cudaMalloc((void**)&c->moe_sel, 8 * sizeof(int)));
     CU_ALLOC(cudaMalloc((void**)&c->moe_wt, 8 * sizeof(float)));
     CU(cudaMemset(c->moe_sel, 0, 8 * sizeof(int)));
@@ -541,6 +549,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->mega_cand_val);
     cudaFree(c->mega_cand_idx);
     cudaFree(c->mega_attn_part);
+    cudaFree(c->d_tmaps);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
@@ -720,6 +729,8 @@ static const void* mega_kernel_for(int hd, int G) {
     return G <= 4 ? (const void*)mega_decode_kernel<64, 4> : (const void*)mega_decode_kernel<64, 8>;
 }
 
+static int stream_build(b200_ctx* c);
+
 // Builds the phase program of every slot.  Leaves mega_ok = false (graph path) when a launch is not eligible:
 // MoE, taps, a weight type/shape the tensor-pipe GEMV does not take, or a shape that does not fit shared memory.
 static int mega_build(b200_ctx* c) {
@@ -893,6 +904,116 @@ static int mega_build(b200_ctx* c) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMmaMaxWarps * 32, smem));
     if (per_sm < 1) return B200_OK;
     c->mega_ok = true;
+    return stream_build(c);
+}
+
+
+// ------------------------------------------------------------------ streamed megakernel (stream.cuh)
+static const void* stream_kernel_for(int hd, int G) {
+    if (hd == 128) return G <= 4 ? (const void*)stream_decode_kernel<128, 4> : (const void*)stream_decode_kernel<128, 8>;
+    return G <= 4 ? (const void*)stream_decode_kernel<64, 4> : (const void*)stream_decode_kernel<64, 8>;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Upgrades the phase programs built by mega_build to the streamed kernel when every weight matrix can be described
+// by a TMA tensor map (rows that are 16-byte multiples, 16-byte aligned base) and every phase uses one entry shape.
+// Leaves stream_ok = false (first megakernel) otherwise.
+static int stream_build(b200_ctx* c) {
+    const b200_model_desc& d = c->d;
+    c->stream_ok = false;
+    if (!c->use_stream || c->par.world_size > 1) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 1, line %d)\n", __LINE__); return B200_OK; }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: no cuTensorMapEncodeTiled entry point\n");
+        return B200_OK;
+    }
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
+    const int hd = d.head_dim, G = d.n_heads / d.n_kv_heads;
+    std::vector<CUtensorMap> maps;
+    std::map<const void*, int> map_of;   // weight base -> index in maps
+    std::vector<std::vector<MegaPhase>> progs(c->slots.size());
+    int max_K = d.hidden;
+    for (size_t si = 0; si < c->slots.size(); si++) {
+        std::vector<MegaPhase>& prog = progs[si];
+        prog.resize(c->mega_phases);
+        CU(cudaMemcpy(prog.data(), c->slots[si].d_phases, prog.size() * sizeof(MegaPhase), cudaMemcpyDeviceToHost));
+        for (size_t pi = 0; pi < prog.size(); pi++) {
+            if (prog[pi].kind != PH_GEMV) continue;
+            MParams& m = prog[pi].gemv;
+            if (m.expert_sel || m.n_peer || m.n_sum || m.K % kMmaChunk) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 2, line %d)\n", __LINE__); return B200_OK; }
+            const int C = stream_chunks_per_entry(m.seg[0].type);
+            for (int s = 0; s < m.n_seg; s++) {
+                MSeg& sg = m.seg[s];
+                if (!mma_type_ok(sg.type) || stream_chunks_per_entry(sg.type) != C) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 3, line %d)\n", __LINE__); return B200_OK; }
+                if ((sg.row_bytes & 15) || ((uintptr_t)sg.w & 15)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 4, line %d)\n", __LINE__); return B200_OK; }
+                sg.s_pitch = stream_pitch(sg.type);
+                sg.s_elem = stream_elem_bytes(sg.type);
+                if (sg.s_pitch * kMmaRows > kStreamSlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 5, line %d)\n", __LINE__); return B200_OK; }
+                auto it = map_of.find(sg.w);
+                if (it == map_of.end()) {
+                    CUtensorMap tm;
+                    const cuuint64_t dims[2] = {(cuuint64_t)(sg.row_bytes / sg.s_elem), (cuuint64_t)sg.n_rows};
+                    const cuuint64_t strides[1] = {(cuuint64_t)sg.row_bytes};
+                    const cuuint32_t box[2] = {(cuuint32_t)(sg.s_pitch / sg.s_elem), (cuuint32_t)kMmaRows};
+                    const cuuint32_t estr[2] = {1, 1};
+                    const CUresult r = encode(&tm, sg.s_elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                                              (void*)sg.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: cuTensorMapEncodeTiled failed (%d) for type %d rows %d row_bytes %lld\n", (int)r, sg.type, sg.n_rows, sg.row_bytes); return B200_OK; }
+                    it = map_of.emplace(sg.w, (int)maps.size()).first;
+                    maps.push_back(tm);
+                }
+                sg.tmap = (const void*)(uintptr_t)(it->second + 1);   // index + 1 for now; device address below
+            }
+            m.s_C = C;
+            m.s_ept = (m.chunks + C - 1) / C;
+            m.s_parts = m.epi == ME_SWIGLU ? 2 : 1;
+            int tiles = 0;
+            for (int s = 0; s < (m.epi == ME_SWIGLU ? 1 : m.n_seg); s++) tiles += m.seg[s].n_tiles;
+            m.s_tiles = tiles;
+            m.s_ncta = std::min(c->n_sm, tiles);
+            m.s_cbase = tiles / m.s_ncta;
+            m.s_crem = tiles % m.s_ncta;
+            m.s_rot = env_int("B200_STREAM_ROT", 1) ? (int)((pi * 37) % (size_t)c->n_sm) : 0;
+            max_K = std::max(max_K, m.K);
+        }
+    }
+    const void* kern = stream_kernel_for(hd, G);
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kern));
+    size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn_item_floats(hd, G <= 4 ? 4 : 8, kSW, c->mega_splits, G) * sizeof(float));
+    x_region = (x_region + 127) & ~(size_t)127;
+    const size_t avail = c->smem_optin - fa.sharedSizeBytes;
+    if (avail < x_region + 3 * (size_t)kStreamSlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 7, line %d)\n", __LINE__); return B200_OK; }
+    int slots = (int)std::min<size_t>(kStreamMaxSlots, (avail - x_region) / kStreamSlotBytes);
+    slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kStreamMaxSlots)));
+    const size_t smem = x_region + (size_t)slots * kStreamSlotBytes;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
+    if (per_sm < 1) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 8, line %d)\n", __LINE__); return B200_OK; }
+    if (c->d_tmaps) cudaFree(c->d_tmaps);
+    c->d_tmaps = nullptr;
+    CU_ALLOC(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+    CU(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (size_t si = 0; si < c->slots.size(); si++) {
+        for (MegaPhase& ph : progs[si]) {
+            if (ph.kind != PH_GEMV) continue;
+            for (int s = 0; s < ph.gemv.n_seg; s++)
+                ph.gemv.seg[s].tmap = (const CUtensorMap*)c->d_tmaps + ((int)(uintptr_t)ph.gemv.seg[s].tmap - 1);
+        }
+        CU(cudaMemcpy(c->slots[si].d_phases, progs[si].data(), progs[si].size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    }
+    c->stream_smem = smem;
+    c->stream_ring_off = (int)x_region;
+    c->stream_slots = slots;
+    c->stream_ok = true;
+    if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: ok, %d slots, ring_off %d, smem %zu, %zu tensor maps\n", slots, (int)x_region, smem, maps.size());
     return B200_OK;
 }
 
@@ -923,9 +1044,19 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         c->tp_epoch += (unsigned int)(per_token * n_tokens);
     }
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
-    void* args[] = {&mp};
-    CU(cudaLaunchCooperativeKernel(mega_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
-                                   c->mega_smem, c->stream));
+    if (c->stream_ok) {
+        StreamParams sp{};
+        sp.mp = mp;
+        sp.ring_off = c->stream_ring_off;
+        sp.n_slots = c->stream_slots;
+        void* sargs[] = {&sp};
+        CU(cudaLaunchCooperativeKernel(stream_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kStreamThreads), sargs,
+                                       c->stream_smem, c->stream));
+    } else {
+        void* args[] = {&mp};
+        CU(cudaLaunchCooperativeKernel(mega_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kMmaMaxWarps * 32), args,
+                                       c->mega_smem, c->stream));
+    }
     c->launches += 1;
     c->mega_launches += 1;
     return B200_OK;
@@ -1170,6 +1301,16 @@ extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* 
     if (kernel_launches) *kernel_launches = c->launches;
     if (weight_bytes) *weight_bytes = c->weight_bytes_per_token;
     if (kv_bytes_per_pos) *kv_bytes_per_pos = (uint64_t)2 * c->d.n_layers * c->d.n_kv_heads * c->d.head_dim * 4;
+    return B200_OK;
+}
+
+// Debug: the watchdog words of the tensor-pipe / megakernel paths (0 = no wait ever gave up); clears them.
+extern "C" int b200_debug_err(b200_ctx* c, int* out8) {
+    if (!c || !out8) return fail(B200_ERR_INVALID_ARGUMENT, "b200_debug_err: null argument");
+    CU(cudaSetDevice(c->par.device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out8, c->mma_err, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->mma_err, 0, 8 * sizeof(int)));
     return B200_OK;
 }
 

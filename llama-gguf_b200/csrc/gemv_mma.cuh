@@ -60,6 +60,11 @@ struct MSeg {
     int bb;                // block bytes
     int chunk_bytes;       // cb * bb
     int nb_row;            // blocks per row (K / block elems)
+    // streamed megakernel (stream.cuh): TMA tensor map of this matrix ([n_rows][row_bytes / elem] tiled in boxes of
+    // 32 rows x s_pitch bytes), nullptr when the matrix is not eligible
+    const void* tmap;
+    int s_pitch;           // bytes between the rows of a ring entry (= inner box bytes)
+    int s_elem;            // bytes per tensor-map element (inner coordinates are in these units)
 };
 
 struct MParams {
@@ -76,6 +81,9 @@ struct MParams {
     int stages;
     int pf_units;          // megakernel: units per warp (beyond the ring) pulled towards L2 before the barrier wait
     int stage_bytes;       // 32 * max row_stride
+    // streamed megakernel: a ring entry is 32 rows x s_C chunks; a tile (x matrix part) is s_ept entries; whole tiles
+    // are dealt to CTAs: CTA b (rotated by s_rot) owns s_cbase (+1 for the first s_crem) tiles of the s_tiles logical ones
+    int s_C, s_ept, s_parts, s_tiles, s_ncta, s_cbase, s_crem, s_rot;
     const float* x;        // [K] f32
     // Producer-staged input (per-token megakernel, single GPU): the phase that produced x also wrote its int8 planes,
     // group scales / sums and per-group sums of squares (stage_out32); this launch copies them instead of converting
@@ -299,8 +307,8 @@ constexpr int kXRegs = 4;
 struct XStage {
     float4 v[kXRegs], w[kXRegs];
 };
-__device__ __forceinline__ void stage_x_load(XStage& st, const XSource& xs, const float* __restrict__ norm_w, int K) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ __forceinline__ void stage_x_load(XStage& st, const XSource& xs, const float* __restrict__ norm_w, int K, int nthr) {
+    const int tid = threadIdx.x;
 #pragma unroll
     for (int i = 0; i < kXRegs; i++) {
         const int e = (tid + i * nthr) * 4;
@@ -342,8 +350,8 @@ __device__ __forceinline__ float split_store4(float4 v, float4 w, int e, uint8_t
     return ss;
 }
 __device__ __forceinline__ void stage_x_finish(const XStage& st, const XSource& xsrc, const float* __restrict__ norm_w, int K,
-                                               uint8_t* smem, float* red /*[kMmaMaxWarps]*/) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+                                               uint8_t* smem, float* red /*[kMmaMaxWarps]*/, int nthr) {
+    const int tid = threadIdx.x;
     const XLayout L = x_layout(K);
     float ss = 0.0f;
 #pragma unroll
@@ -371,11 +379,10 @@ __device__ __forceinline__ void stage_x_finish(const XStage& st, const XSource& 
     if (tid < 64) reinterpret_cast<uint32_t*>(smem + L.zero)[tid] = 0u;
 }
 // after the caller's __syncthreads: the factor for finished dot products (1/rms when normalising)
-__device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, float eps, int K) {
+__device__ __forceinline__ float stage_x_unscale(const float* red, bool norm, float eps, int K, int nwarp) {
     float inv = 1.0f;
     if (norm) {
         float tot = 0.0f;
-        const int nwarp = blockDim.x >> 5;
         for (int w = 0; w < nwarp; w++) tot += red[w];
         inv = 1.0f / sqrtf(tot / (float)K + eps);
     }
@@ -933,7 +940,7 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
         // x: the loads are issued BEFORE the weight copies, the split after them
         XStage xst;
         const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};
-        stage_x_load(xst, xsrc, p.norm_w, K);
+        stage_x_load(xst, xsrc, p.norm_w, K, (int)blockDim.x);
         if (!issued_early) {
             for (int k = 0; k < STAGES - 1; k++) {
                 if (k < pre) issue((uint32_t)k * p.stage_bytes, false);
@@ -941,9 +948,9 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
             }
         }
         MMA_STAMP(2);
-        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red);
+        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, (int)blockDim.x);
         __syncthreads();
-        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K);
+        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K, (int)(blockDim.x >> 5));
     }
     MMA_STAMP(3);
     const uint32_t tokx = smem_token();

@@ -1,0 +1,590 @@
+// stream.cuh — the streamed per-token megakernel: one persistent CTA per SM whose PRODUCER warp never stops pulling
+// weights from HBM while the consumer warps walk the phases of the token.
+//
+// Why (profiles/r01_mega_ncu_full.md, per-phase timeline): in the first megakernel (mega.cuh) every GEMV phase
+// pays ~5 us of fixed cost (grid barrier, x staging, ring ramp-up, stragglers) against 1.5-10 us of streaming, and
+// HBM idles during all of it: 29 % of the copy roofline for a whole token.  Weights never depend on the token, so
+// here they are fetched by a warp that is not part of any phase:
+//
+//   * producer = one elected lane of warp 8.  It walks the same phase program as the consumers, but only the GEMV
+//     phases, and issues ONE `cp.async.bulk.tensor.2d` (TMA, SASS UTMALDG) per ring entry: a box of 32 weight rows x
+//     4 super-blocks (Q4_K: 32 x 576 B) straight from the untouched GGUF row layout, described by a tensor map per
+//     weight matrix ([n_rows][row_bytes], encoded once at model load).  Rows / columns past the end of a matrix are
+//     zero-filled by the TMA unit (a zero block has d = 0: it contributes nothing), so ragged shapes need no code.
+//     The only thing the producer ever waits for is a free slot of the ring (mbarrier `empty`), never a grid barrier:
+//     while the consumers sit in a barrier, stage x or run attention, the next GEMV's weights keep arriving
+//     (6 slots x 148 SMs = up to 24 MB in flight / buffered).
+//   * consumers = 8 warps.  A phase's 32-row tiles are dealt whole to CTAs (no tile is shared between CTAs: nothing
+//     is merged through global memory, no tickets), the entries of a CTA's tiles are dealt in contiguous runs to its
+//     warps; entry n of the CTA's sequence goes to warp n % 8 so the ring is consumed in issue order.  A warp waits
+//     for its entry (mbarrier `full`, completed by the TMA transaction bytes), runs the integer tensor-pipe unit
+//     kernels of gemv_mma.cuh on it (the box pitch is the ring row stride: 576 = 64 mod 128 keeps the fragment loads
+//     conflict-free), and hands the slot back.  Tiles cut across warps are merged in shared memory in warp order
+//     (deterministic), epilogues (bias, residual, SwiGLU, staged int8 form of the output for the next GEMV) as before.
+//   * attention / RoPE / KV-write phases are attn_decode_item (attention.cuh) on the consumer warps; all CTA-wide
+//     synchronisation of the consumers uses named barrier 1 (the producer never joins a barrier).
+//
+// Replaces the same reference code as mega.cuh: GpuOnlyInference::forward (src/backend/cuda/gpu_only.rs:849-1010),
+// CPU LlamaModel::forward (src/model/llama.rs:275-362) with the fused dots of src/backend/cpu/simd.rs:931-1146.
+// Dense single-GPU models whose weight rows are 16-byte multiples take this path; the rest stay on mega.cuh.
+#pragma once
+#include "mega.cuh"
+
+namespace b200 {
+
+constexpr int kSW = kMmaMaxWarps;               // consumer warps
+constexpr int kSNT = kSW * 32;                  // consumer threads
+constexpr int kStreamThreads = kSNT + 32;       // + the producer warp
+constexpr int kStreamSlotBytes = 27136;         // 32 rows x 848 bytes (Q6_K: 4 blocks + 8), a multiple of 128
+constexpr int kStreamMaxSlots = 8;
+
+struct StreamParams {
+    MegaParams mp;
+    int ring_off;   // bytes of dynamic shared memory before the ring (x staging / attention scratch), multiple of 128
+    int n_slots;
+};
+
+// ---------------------------------------------------------------- host-side geometry
+// chunks (256 elements) per ring entry and the inner box of the tensor map, per block type
+inline int stream_chunks_per_entry(int type) { return type == T_Q8_0 ? 3 : 4; }
+inline int stream_elem_bytes(int type) { return type == T_Q8_0 ? 8 : 4; }
+// (Q6_K: 840 bytes of blocks + up to 8 bytes in front when the entry starts at an odd multiple of 840)
+inline int stream_pitch(int type) {
+    const int cb = kMmaChunk / type_block_elems(type), bb = type_block_bytes(type);
+    const int raw = stream_chunks_per_entry(type) * cb * bb;   // Q4_K 576, Q5_K 704, Q6_K 840, Q8_0 816
+    return (raw + 15) & ~15;                                   // Q6_K: 848 (8 bytes of the next block ride along)
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSNT) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+// Bounded wait.  A CTA that gives up raises s_dead so that every other wait of the CTA returns at once: all threads
+// keep walking the program (barrier counts stay consistent, nothing hangs), the results are garbage and *err says so.
+// err[0] = 4, err[1..3] = (which wait, CTA, ring sequence number) of the first wait that gave up (b200_debug_err).
+__device__ __forceinline__ bool s_wait(uint32_t bar, uint32_t parity, volatile int* s_dead, int* err, int code, uint32_t seq) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if (*s_dead) return false;
+        if (clock64() - t0 > 2000000000LL) {  // ~1 s
+            *s_dead = 1;
+            if (atomicExch(err, 4) == 0) { err[1] = code; err[2] = (int)blockIdx.x; err[3] = (int)seq; }
+            return false;
+        }
+    }
+}
+// A CTA that gave up may still have TMA loads in flight: let them land before the CTA (and its shared memory) goes away
+__device__ __forceinline__ void s_drain(volatile int* s_dead) {
+    if (*s_dead) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < 400000LL) {}
+    }
+}
+
+// The tiles of a phase this CTA owns, and the entries they make
+struct SDeal {
+    int T0, cnt, E;
+};
+__device__ __forceinline__ SDeal s_deal(int s_rot, int s_ncta, int s_cbase, int s_crem, int per_tile) {
+    int b = (int)blockIdx.x + s_rot;
+    if (b >= (int)gridDim.x) b -= (int)gridDim.x;
+    SDeal d{0, 0, 0};
+    if (b < s_ncta) {
+        d.T0 = b * s_cbase + min(b, s_crem);
+        d.cnt = s_cbase + (b < s_crem ? 1 : 0);
+    }
+    d.E = d.cnt * per_tile;
+    return d;
+}
+
+struct SRing {
+    uint32_t base, full, empty;   // shared-space addresses: slots, full[n_slots], empty[n_slots] (8 bytes each)
+    int n_slots;
+    // Number of entries the producer has issued so far.  A consumer may only wait on `full` for entry q once q has been
+    // issued: mbarrier waits are by phase PARITY, so a warp that waits for round r + 1 of a slot while round r is still
+    // being filled (its entry belongs to another warp) would see "the other parity" and run ahead on stale bytes.
+    volatile uint32_t* issued;
+};
+
+// ---------------------------------------------------------------- producer
+__device__ __forceinline__ void stream_producer(const StreamParams& sp, const SRing& rg, volatile int* s_dead) {
+    const MegaParams& mp = sp.mp;
+    const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
+    uint32_t slot = 0, round = 0;
+    for (int tok = 0; tok < mp.n_tokens; tok++) {
+        for (int ph = 0; ph < n_run; ph++) {
+            const MegaPhase* P = mp.phases + ph;
+            if (P->kind != PH_GEMV) continue;
+            const MParams* g = &P->gemv;
+            const int n_seg = g->n_seg, ept = g->s_ept, parts = g->s_parts;
+            const bool swiglu = g->epi == ME_SWIGLU;
+            const void* tm[3];
+            int nt[3], cstep[3], bytes[3], esz[3];
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const MSeg* sg = &g->seg[s < n_seg ? s : 0];
+                tm[s] = sg->tmap;
+                nt[s] = sg->n_tiles;
+                cstep[s] = g->s_C * sg->chunk_bytes;   // bytes between the entries of a row
+                esz[s] = sg->s_elem;
+                bytes[s] = sg->s_pitch * kMmaRows;
+            }
+            const int per_tile = parts * ept;
+            const SDeal d = s_deal(g->s_rot, g->s_ncta, g->s_cbase, g->s_crem, per_tile);
+            const int base = d.E / kSW, rem = d.E - base * kSW;
+            if (tok == 0 && d.E > 0) {
+                // tensor maps live in global memory (written by the host before the launch): the TMA unit reads them
+                // through the tensormap proxy, which needs an acquire fence in every CTA before the first use
+#pragma unroll
+                for (int s = 0; s < 3; s++)
+                    if (s < n_seg) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm[s]) : "memory");
+            }
+            for (int i = 0; i <= base; i++) {
+                const int nw = (i < base) ? kSW : rem;
+                for (int w = 0; w < nw; w++) {
+                    const int j = w * base + min(w, rem) + i;
+                    const int tl = j / per_tile, r = j - tl * per_tile;
+                    const int part = r / ept, ce = r - part * ept;
+                    int s = 0, tile = d.T0 + tl;
+                    if (swiglu) {
+                        s = part;
+                    } else {
+                        while (s + 1 < n_seg && tile >= nt[s]) { tile -= nt[s]; s++; }
+                    }
+                    const void* tmap = s == 0 ? tm[0] : s == 1 ? tm[1] : tm[2];
+                    const int cs = s == 0 ? cstep[0] : s == 1 ? cstep[1] : cstep[2];
+                    const int nb = s == 0 ? bytes[0] : s == 1 ? bytes[1] : bytes[2];
+                    const int es = s == 0 ? esz[0] : s == 1 ? esz[1] : esz[2];
+                    // the box must start on a 16-byte boundary of the row (tools/tma_lab.cu: an unaligned start is an
+                    // illegal instruction): Q6_K entries start at 840 ce, odd ones are fetched from 8 bytes earlier
+                    const int c0 = ((ce * cs) & ~15) / es;
+                    if (!s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, mp.err, 1000 + ph, round * (uint32_t)rg.n_slots + slot)) return;
+                    mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nb);
+                    tma_load_2d(rg.base + slot * (uint32_t)kStreamSlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
+                    __threadfence_block();   // the barrier is armed before anybody learns that the entry was issued
+                    *rg.issued = round * (uint32_t)rg.n_slots + slot + 1u;
+                    if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumer side of one GEMV phase
+// seq0: number of ring entries this CTA has consumed before this phase (every consumer thread keeps the same count).
+template <class Pre, class Post>
+__device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem, const SRing& rg, uint32_t& seq0, float* s_red,
+                                                float (*s_part)[2][2][32], volatile int* s_dead, Pre pre_fn, Post post_fn) {
+    pre_fn();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int K = p.K;
+    const uint32_t sbase = smem_u32(smem);
+    const bool swiglu = p.epi == ME_SWIGLU;
+    const int ept = p.s_ept, per_tile = p.s_parts * ept;
+    const SDeal d = s_deal(p.s_rot, p.s_ncta, p.s_cbase, p.s_crem, per_tile);
+    const int base = d.E / kSW, rem = d.E - base * kSW;
+    const int j0 = warp * base + min(warp, rem), n_ent = base + (warp < rem ? 1 : 0), j1 = j0 + n_ent;
+    const long long gw = (long long)blockIdx.x * kSW + warp;  // debug stamps only
+    MMA_STAMP(0);
+
+    post_fn();
+    MMA_STAMP(1);
+
+    // ---- x: the staged form left by its producer (flat copy) or f32 -> three int8 planes here ----
+    const XLayout XL = x_layout(K);
+    float unscale = 1.0f;
+    if (p.x_staged) {
+        const uint32_t n16 = (XL.zero + 15u) >> 4;
+        for (uint32_t i = tid; i < n16; i += kSNT) cp_async16(sbase + 16u * i, p.x_staged + 16u * i);
+        cp_async_commit();
+        MMA_STAMP(2);
+        cp_async_wait<0>();
+        if (tid < 64) reinterpret_cast<uint32_t*>(smem + XL.zero)[tid] = 0u;
+        cons_sync();
+        if (p.norm_w) {
+            const float* ssq = reinterpret_cast<const float*>(smem + XL.ssq);
+            float tot = 0.0f;
+            for (int i = lane; i < (K >> 5); i += 32) tot += ssq[i];
+            tot = warp_sum(tot);
+            unscale = 1.0f / sqrtf(tot / (float)K + p.eps);
+        }
+    } else {
+        XStage xst;
+        const XSource xsrc{p.x, nullptr, 0, 0, nullptr, nullptr};
+        stage_x_load(xst, xsrc, p.norm_w, K, kSNT);
+        MMA_STAMP(2);
+        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, kSNT);
+        cons_sync();
+        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K, kSW);
+    }
+    MMA_STAMP(3);
+    const uint32_t tokx = smem_token();
+    XSmem sm;
+    sm.p0 = sbase + tokx + XL.p0;
+    sm.p1 = sbase + tokx + XL.p1;
+    sm.p2 = sbase + tokx + XL.p2;
+    sm.sx = sbase + tokx + XL.sx;
+    sm.x16 = sbase + tokx + XL.x16;
+    sm.zero = sbase + tokx + XL.zero;
+
+    // ---- epilogue of a finished tile: lane L owns row tile*32 + L of segment s (vu: the up row for SwiGLU) ----
+    auto epilogue = [&](int s, int tile, float v, float vu) {
+        const MSeg& sg = p.seg[s];
+        const int j = tile * kMmaRows + lane;
+        const bool valid = j < sg.n_rows;
+        const float e_bias = (valid && sg.bias) ? sg.bias[j] : 0.0f;
+        const float e_res = (valid && p.epi == ME_RESIDUAL) ? p.residual[j] : 0.0f;
+        const float e_w = (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
+        v *= unscale;
+        float val = v;
+        if (swiglu) val = mma_silu(v) * (vu * unscale);
+        if (valid) {
+            val += e_bias;
+            val += e_res;
+            sg.out[j] = val;
+        }
+        if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
+    };
+    // logical tile T of the phase -> (segment, tile within the segment)
+    auto seg_of = [&](int T, int& s, int& tile) {
+        s = 0;
+        tile = T;
+        if (!swiglu)
+            while (s + 1 < p.n_seg && tile >= p.seg[s].n_tiles) { tile -= p.seg[s].n_tiles; s++; }
+    };
+
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
+    int piece_tl[2] = {-1, -1};   // CTA-local tiles of which this warp holds only a piece (first / last of its run)
+    bool first = true;
+    for (int i = 0; i < n_ent; i++) {
+        const int j = j0 + i;
+        const int tl = j / per_tile, r = j - tl * per_tile;
+        const int part = r / ept, ce = r - part * ept;
+        int s, tile;
+        seg_of(d.T0 + tl, s, tile);
+        const int mat = swiglu ? part : s;
+        const MSeg& wsg = p.seg[mat];
+        const int type = wsg.type;
+        const uint32_t RS = (uint32_t)wsg.s_pitch, cbytes = (uint32_t)wsg.chunk_bytes;
+        const int c0 = ce * p.s_C, nc = min(p.s_C, p.chunks - c0);
+        const uint32_t e00 = (uint32_t)c0 * kMmaChunk;
+        const uint32_t doff = ((uint32_t)ce * (uint32_t)p.s_C * cbytes) & 15u;   // the box starts 16-byte aligned: Q6_K, odd entries: 8
+        const LaneB lb = (type == T_Q6_K) ? lane_b_q6k(sm, g, t) : (type == T_Q8_0) ? lane_b_q80(sm, g, t) : lane_b_k45(sm, g, t, type == T_Q5_K);
+
+        const uint32_t q = seq0 + (uint32_t)(i * kSW + warp);
+        const uint32_t slot = q % (uint32_t)rg.n_slots, par = (q / (uint32_t)rg.n_slots) & 1u;
+        if ((int)(*rg.issued - q) <= 0) {   // not issued yet (bounded spin, like s_wait)
+            const long long t0 = clock64();
+            while ((int)(*rg.issued - q) <= 0 && !*s_dead) {
+                if (clock64() - t0 > 2000000000LL) {
+                    *s_dead = 1;
+                    if (atomicExch(p.err, 4) == 0) { p.err[1] = 4000 + warp; p.err[2] = (int)blockIdx.x; p.err[3] = (int)q; }
+                }
+            }
+        }
+        s_wait(rg.full + 8u * slot, par, s_dead, p.err, 2000 + warp, q);
+        if (first) { MMA_STAMP(4); first = false; }
+        const uint32_t spb = rg.base + slot * (uint32_t)kStreamSlotBytes + doff + smem_token();
+        float ua[4] = {0.f, 0.f, 0.f, 0.f};
+        switch (type) {
+            case T_Q4_K:
+                for (int c = 0; c < nc; c++) unit_k45<false>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
+                break;
+            case T_Q5_K:
+                for (int c = 0; c < nc; c++) unit_k45<true>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
+                break;
+            case T_Q6_K:
+                // block c of the entry starts at doff + 210 c (doff = 0 or 8): 8-byte aligned for c = 0, 4-byte for c = 2, else 2-byte
+                for (int c = 0; c < nc; c++) {
+                    const uint32_t a = spb + (uint32_t)c * cbytes, e0 = e00 + (uint32_t)c * kMmaChunk;
+                    if (c == 0) unit_q6k<8>(a, RS, e0, 0u, sm, lb, g, t, ua);
+                    else if (c == 2) unit_q6k<4>(a, RS, e0, 0u, sm, lb, g, t, ua);
+                    else unit_q6k<2>(a, RS, e0, 0u, sm, lb, g, t, ua);
+                }
+                break;
+            default:
+                for (int c = 0; c < nc; c++) {
+                    const uint32_t e0 = e00 + (uint32_t)c * kMmaChunk;
+                    unit_q80(spb + (uint32_t)c * cbytes, RS, e0, 0u, min(wsg.cb, wsg.nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua);
+                }
+                break;
+        }
+        pin4(ua);   // every shared-memory read of the entry has completed before the slot is handed back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.empty + 8u * slot);
+        if (swiglu && part == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) au[k] += ua[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) ag[k] += ua[k];
+        }
+
+        // ---- tile finished (for this warp)? ----
+        const bool row_end = ce == ept - 1;
+        const bool tile_done = (row_end && (!swiglu || part == 1)) || (i == n_ent - 1);
+        if (!tile_done) continue;
+        if (i == n_ent - 1) MMA_STAMP(5);
+        // reduce the 4 lanes of a row group, then lane L holds logical row L = 8k + n (register k of lanes 4n..4n+3)
+        float vg = 0.f, vu = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ag[k] += __shfl_xor_sync(0xffffffffu, ag[k], 1);
+            ag[k] += __shfl_xor_sync(0xffffffffu, ag[k], 2);
+            const float x = __shfl_sync(0xffffffffu, ag[k], 4 * (lane & 7));
+            if ((lane >> 3) == k) vg = x;
+            ag[k] = 0.f;
+        }
+        if (swiglu) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                au[k] += __shfl_xor_sync(0xffffffffu, au[k], 1);
+                au[k] += __shfl_xor_sync(0xffffffffu, au[k], 2);
+                const float x = __shfl_sync(0xffffffffu, au[k], 4 * (lane & 7));
+                if ((lane >> 3) == k) vu = x;
+                au[k] = 0.f;
+            }
+        }
+        const int te0 = tl * per_tile;
+        if (j0 <= te0 && te0 + per_tile <= j1) {
+            epilogue(s, tile, vg, vu);   // the whole tile is mine
+        } else {
+            const int ps = (j0 >= te0) ? 0 : 1;   // the tile is my first (0) or starts inside my run (1)
+            s_part[warp][ps][0][lane] = vg;
+            s_part[warp][ps][1][lane] = vu;
+            piece_tl[ps] = tl;
+        }
+    }
+    seq0 += (uint32_t)d.E;
+
+    // ---- merge the pieces of tiles shared between warps, in warp order ----
+    cons_sync();
+    auto start_of = [&](int w) { return w * base + min(w, rem); };
+    auto warp_of = [&](int e) { return e < rem * (base + 1) ? e / (base + 1) : rem + (e - rem * (base + 1)) / max(base, 1); };
+#pragma unroll
+    for (int ps = 0; ps < 2; ps++) {
+        if (piece_tl[ps] < 0) continue;  // warp-uniform
+        const int tl = piece_tl[ps], te0 = tl * per_tile;
+        const int lo = warp_of(te0), hi = warp_of(te0 + per_tile - 1);
+        if (warp != lo) continue;        // the first warp that holds a piece finishes the tile
+        float v = 0.f, vu = 0.f;
+        for (int w = lo; w <= hi; w++) {
+            const int ws = (start_of(w) >= te0) ? 0 : 1;
+            v += s_part[w][ws][0][lane];
+            vu += s_part[w][ws][1][lane];
+        }
+        int s, tile;
+        seg_of(d.T0 + tl, s, tile);
+        epilogue(s, tile, v, vu);
+    }
+    MMA_STAMP(6);
+}
+
+// ---------------------------------------------------------------- grid barrier of the consumer warps
+__device__ __forceinline__ void s_grid_arrive(unsigned int* bar, unsigned int& target) {
+    cons_sync();
+    target += gridDim.x;
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+__device__ __forceinline__ bool s_grid_wait(unsigned int* bar, unsigned int target, int* err, int* s_flag, volatile int* s_dead) {
+    if (threadIdx.x == 0) {
+        unsigned int v = 0;
+        int ok = 1;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (*s_dead || clock64() - t0 > 3000000000LL) {  // ~1.5 s
+                ok = 0;
+                *s_dead = 1;
+                if (atomicExch(err, 2) == 0) { err[1] = 3000; err[2] = (int)blockIdx.x; err[3] = (int)target; }
+                break;
+            }
+        }
+        *s_flag = ok;
+    }
+    cons_sync();
+    return *s_flag != 0;
+}
+
+template <int HD, int GMAX>
+__global__ void __maxnreg__(168) stream_decode_kernel(const __grid_constant__ StreamParams sp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long s_bars[2 * kStreamMaxSlots];
+    __shared__ float s_red[2 * kSW];
+    __shared__ float s_part[kSW][2][2][32];
+    __shared__ unsigned int s_ticket;
+    __shared__ int s_flag;
+    __shared__ int s_dead;
+    __shared__ unsigned int s_issued;
+    __shared__ __align__(16) MegaPhase s_phs[3];
+    __shared__ float s_rope[HD];
+    __shared__ float s_av[kSW];
+    __shared__ int s_ai[kSW];
+
+    const MegaParams& mp = sp.mp;
+    constexpr int NW = kSW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SRing rg;
+    rg.base = smem_u32(smem) + (uint32_t)sp.ring_off;
+    rg.full = smem_u32(s_bars);
+    rg.empty = rg.full + 8u * (uint32_t)sp.n_slots;
+    rg.n_slots = sp.n_slots;
+    rg.issued = &s_issued;
+    if (tid == 0) {
+        for (int i = 0; i < sp.n_slots; i++) {
+            mbar_init(rg.full + 8u * i, 1);
+            mbar_init(rg.empty + 8u * i, 1);
+        }
+        s_dead = 0;
+        s_issued = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();   // the only CTA-wide barrier that includes the producer warp
+
+    if (warp == NW) {
+        if (lane == 0) stream_producer(sp, rg, &s_dead);
+        s_drain(&s_dead);
+        return;
+    }
+
+    unsigned int target = 0;
+    uint32_t seq0 = 0;
+    const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
+    auto fetch_desc = [&](long long gph) {
+        if (tid < 32) return;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.phases + (int)(gph % n_run));
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phs[gph % 3]);
+        for (int i = tid - 32; i < (int)(sizeof(MegaPhase) / 4); i += (NW - 1) * 32) dst[i] = src[i];
+    };
+    fetch_desc(0);
+    fetch_desc(1);
+    cons_sync();
+    long long gph = 0;
+
+    for (int tok = 0; tok < mp.n_tokens; tok++) {
+        // ---- embedding (LlamaModel::forward, model/llama.rs:293-306): CTA 0 dequantises row `token`, bit-exactly ----
+        if (blockIdx.x == 0) {
+            int token = mp.st->token;
+            token = min(max(token, 0), mp.vocab - 1);
+            const int be = type_block_elems(mp.embd_type), bb = type_block_bytes(mp.embd_type);
+            const uint8_t* row = mp.embd + (long long)token * mp.embd_row_bytes;
+            for (int i = tid; i < mp.hidden; i += kSNT) {
+                const int blk = i / be;
+                mp.h[i] = dequant_elem(mp.embd_type, row + (long long)blk * bb, i - blk * be);
+            }
+            if (tid == 0) {
+                const int pn = mp.st->pos_next;
+                mp.st->pos_cur = pn;
+                mp.st->pos_next = pn + 1;
+            }
+        }
+        bool ok = true;
+        int stamp = 0;
+        auto bar_arrive = [&]() { s_grid_arrive(mp.bar, target); };
+        auto bar_wait = [&]() {
+            fetch_desc(gph + 2);
+            ok = s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
+            if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[stamp] = gtimer();
+            stamp++;
+        };
+
+        for (int ph = 0; ph < n_run; ph++, gph++) {
+            const MegaPhase& cur = s_phs[gph % 3];
+            if (cur.kind == PH_GEMV) {
+                stream_gemv_cta(cur.gemv, smem, rg, seq0, s_red, s_part, &s_dead, bar_arrive, bar_wait);
+            } else {
+                attn_stamp(cur.attn, 0);
+                bar_arrive();
+                bar_wait();
+                const AttnParams& ap = cur.attn;
+                attn_stamp(ap, 1);
+                const int kv_len = *ap.pos + 1;
+                if (ph == 1) {   // first attention phase of the token: the rotation angles (Backend::rope, cpu/ops.rs:1216-1337)
+                    const float position = (float)(kv_len - 1) / ap.rope_scale;
+                    for (int pi = tid; pi < HD / 2; pi += kSNT) {
+                        const float theta = position * ap.freq[pi];
+                        s_rope[pi] = cosf(theta);
+                        s_rope[HD / 2 + pi] = sinf(theta);
+                    }
+                    cons_sync();
+                }
+                const int n_items = ap.n_kv * ap.n_splits;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    const int kh = item / ap.n_splits, split = item - kh * ap.n_splits;
+                    attn_decode_item<HD, GMAX, NW>(ap, kh, split, kv_len, reinterpret_cast<float*>(smem), &s_ticket, s_rope);
+                    cons_sync();
+                }
+            }
+        }
+        // the barrier that ends the last phase of the token
+        gph--;
+        bar_arrive();
+        bar_wait();
+        gph++;
+        (void)ok;
+
+        if (mp.mode != MEGA_GREEDY) continue;
+        // ---- greedy pick on the device: raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821) ----
+        {
+            const int per = (mp.vocab_local + gridDim.x - 1) / gridDim.x;
+            const int lo = blockIdx.x * per, hi = min(mp.vocab_local, lo + per);
+            float best = -INFINITY;
+            int bi = -1;
+            for (int i = lo + tid; i < hi; i += kSNT) {
+                const float v = mp.logits[i];
+                if (v >= best || bi < 0) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_av[warp] = best; s_ai[warp] = bi; }
+            cons_sync();
+            if (tid == 0) {
+                for (int w = 1; w < NW; w++)
+                    if (s_ai[w] >= 0 && (bi < 0 || s_av[w] > best || (s_av[w] == best && s_ai[w] > bi))) { best = s_av[w]; bi = s_ai[w]; }
+                mp.cand_val[blockIdx.x] = best;
+                mp.cand_idx[blockIdx.x] = bi;
+            }
+        }
+        s_grid_arrive(mp.bar, target);
+        s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
+        if (blockIdx.x == 0) {
+            if (warp == 0) {
+                float best = -INFINITY;
+                int bi = -1;
+                for (int c = lane; c < (int)gridDim.x; c += 32) {
+                    const float v = mp.cand_val[c];
+                    const int i = mp.cand_idx[c];
+                    if (i >= 0 && (bi < 0 || v > best || (v == best && i > bi))) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                }
+                if (lane == 0) {
+                    mp.st->token = bi;
+                    const int gcount = mp.st->n_generated;
+                    if (gcount < mp.max_generated) mp.generated[gcount] = bi;
+                    mp.st->n_generated = gcount + 1;
+                }
+            }
+            cons_sync();  // CTA 0 embeds the new token at the top of the loop: it must see st->token
+        }
+    }
+    s_drain(&s_dead);
+}
+
+}  // namespace b200
