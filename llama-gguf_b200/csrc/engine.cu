@@ -946,24 +946,27 @@ static int stream_build(b200_ctx* c) {
             if (prog[pi].kind != PH_GEMV) continue;
             MParams& m = prog[pi].gemv;
             if (m.expert_sel || m.n_peer || m.n_sum || m.K % kMmaChunk) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 2, line %d)\n", __LINE__); return B200_OK; }
-            const int C = stream_chunks_per_entry(m.seg[0].type);
+            int C = 1 << 30;
+            for (int s = 0; s < m.n_seg; s++) {
+                if (!mma_type_ok(m.seg[s].type)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (type %d)\n", m.seg[s].type); return B200_OK; }
+                C = std::min(C, stream_pref_chunks(m.seg[s].type));
+            }
             for (int s = 0; s < m.n_seg; s++) {
                 MSeg& sg = m.seg[s];
-                if (!mma_type_ok(sg.type) || stream_chunks_per_entry(sg.type) != C) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 3, line %d)\n", __LINE__); return B200_OK; }
-                if ((sg.row_bytes & 15) || ((uintptr_t)sg.w & 15)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 4, line %d)\n", __LINE__); return B200_OK; }
-                sg.s_pitch = stream_pitch(sg.type);
-                sg.s_elem = stream_elem_bytes(sg.type);
-                if (sg.s_pitch * kMmaRows > kStreamSlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 5, line %d)\n", __LINE__); return B200_OK; }
+                if ((sg.row_bytes & 15) || ((uintptr_t)sg.w & 15)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (row bytes %lld)\n", sg.row_bytes); return B200_OK; }
+                sg.s_pitch = stream_pitch(sg.type, C);
+                sg.s_elem = 4;
+                if (sg.s_pitch * kMmaRows > kStreamSlotBytes || sg.s_pitch / 4 > 256) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (pitch %d)\n", sg.s_pitch); return B200_OK; }
                 auto it = map_of.find(sg.w);
                 if (it == map_of.end()) {
                     CUtensorMap tm;
-                    const cuuint64_t dims[2] = {(cuuint64_t)(sg.row_bytes / sg.s_elem), (cuuint64_t)sg.n_rows};
+                    const cuuint64_t dims[2] = {(cuuint64_t)(sg.row_bytes / 4), (cuuint64_t)sg.n_rows};
                     const cuuint64_t strides[1] = {(cuuint64_t)sg.row_bytes};
-                    const cuuint32_t box[2] = {(cuuint32_t)(sg.s_pitch / sg.s_elem), (cuuint32_t)kMmaRows};
+                    const cuuint32_t box[2] = {(cuuint32_t)(sg.s_pitch / 4), (cuuint32_t)kMmaRows};
                     const cuuint32_t estr[2] = {1, 1};
-                    const CUresult r = encode(&tm, sg.s_elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
-                                              (void*)sg.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)sg.w, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                     if (r != CUDA_SUCCESS) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: cuTensorMapEncodeTiled failed (%d) for type %d rows %d row_bytes %lld\n", (int)r, sg.type, sg.n_rows, sg.row_bytes); return B200_OK; }
                     it = map_of.emplace(sg.w, (int)maps.size()).first;
                     maps.push_back(tm);
@@ -1049,6 +1052,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         sp.mp = mp;
         sp.ring_off = c->stream_ring_off;
         sp.n_slots = c->stream_slots;
+        sp.no_load = env_int("B200_STREAM_NOLOAD", 0);
         void* sargs[] = {&sp};
         CU(cudaLaunchCooperativeKernel(stream_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kStreamThreads), sargs,
                                        c->stream_smem, c->stream));

@@ -32,27 +32,36 @@
 
 namespace b200 {
 
-constexpr int kSW = kMmaMaxWarps;               // consumer warps
+constexpr int kSW = 7;                           // consumer warps (7 + the producer warp = 256 threads: 255 registers each, no spills)
 constexpr int kSNT = kSW * 32;                  // consumer threads
 constexpr int kStreamThreads = kSNT + 32;       // + the producer warp
-constexpr int kStreamSlotBytes = 27136;         // 32 rows x 848 bytes (Q6_K: 4 blocks + 8), a multiple of 128
-constexpr int kStreamMaxSlots = 8;
+constexpr int kStreamSlotBytes = 9216;          // 32 rows x 288 bytes (Q4_K, 2 super-blocks): small entries, many slots
+constexpr int kStreamMaxSlots = 24;
 
 struct StreamParams {
     MegaParams mp;
     int ring_off;   // bytes of dynamic shared memory before the ring (x staging / attention scratch), multiple of 128
     int n_slots;
+    int no_load;    // experiment: the producer arms the barriers but moves no bytes (consumer speed without HBM)
 };
 
 // ---------------------------------------------------------------- host-side geometry
-// chunks (256 elements) per ring entry and the inner box of the tensor map, per block type
-inline int stream_chunks_per_entry(int type) { return type == T_Q8_0 ? 3 : 4; }
-inline int stream_elem_bytes(int type) { return type == T_Q8_0 ? 8 : 4; }
-// (Q6_K: 840 bytes of blocks + up to 8 bytes in front when the entry starts at an odd multiple of 840)
-inline int stream_pitch(int type) {
+// Why small entries: a slot is busy from the moment its TMA load is issued until the consuming warp has finished the
+// entry (~1.5-2 us of flight + the warp's compute time), so the ring needs (bytes in flight: ~44 GB/s per SM x 2 us)
+// + (warps x entry) bytes.  With 32 x 576-byte entries (first version) 6 slots fed 8 warps at 3.3 TB/s; halving the
+// entry halves both the compute hold time and the bytes pinned by computing warps.
+// Chunks (256 elements) per ring entry a type would like; a phase uses the minimum over its matrices.
+inline int stream_pref_chunks(int type) { return type == T_Q4_K ? 2 : 1; }
+// Inner box of the tensor map = row pitch of a ring entry.  The box must start on a 16-byte boundary of the row
+// (tools/tma_lab.cu: an unaligned start is an illegal instruction), so an entry that starts at byte b of its row is
+// fetched from b & ~15 and the consumer skips b & 15 bytes: the pitch covers the largest such residue.
+// Q4_K 288 (C = 2) / 144, Q5_K 176, Q6_K 210 + 14 = 224, Q8_0 272.
+inline int stream_pitch(int type, int C) {
     const int cb = kMmaChunk / type_block_elems(type), bb = type_block_bytes(type);
-    const int raw = stream_chunks_per_entry(type) * cb * bb;   // Q4_K 576, Q5_K 704, Q6_K 840, Q8_0 816
-    return (raw + 15) & ~15;                                   // Q6_K: 848 (8 bytes of the next block ride along)
+    const int raw = C * cb * bb;
+    int maxres = 0;
+    for (int ce = 0; ce < 16; ce++) maxres = std::max(maxres, (ce * raw) & 15);
+    return (raw + maxres + 15) & ~15;
 }
 
 // ---------------------------------------------------------------- device helpers
@@ -125,17 +134,17 @@ __device__ __forceinline__ void stream_producer(const StreamParams& sp, const SR
             const int n_seg = g->n_seg, ept = g->s_ept, parts = g->s_parts;
             const bool swiglu = g->epi == ME_SWIGLU;
             const void* tm[3];
-            int nt[3], cstep[3], bytes[3], esz[3];
+            int nt[3], cstep[3], bytes[3];
 #pragma unroll
             for (int s = 0; s < 3; s++) {
                 const MSeg* sg = &g->seg[s < n_seg ? s : 0];
                 tm[s] = sg->tmap;
                 nt[s] = sg->n_tiles;
                 cstep[s] = g->s_C * sg->chunk_bytes;   // bytes between the entries of a row
-                esz[s] = sg->s_elem;
                 bytes[s] = sg->s_pitch * kMmaRows;
             }
             const int per_tile = parts * ept;
+            const float inv_pt = 1.0f / (float)per_tile, inv_ept = 1.0f / (float)ept;   // exact small-integer division
             const SDeal d = s_deal(g->s_rot, g->s_ncta, g->s_cbase, g->s_crem, per_tile);
             const int base = d.E / kSW, rem = d.E - base * kSW;
             if (tok == 0 && d.E > 0) {
@@ -149,24 +158,26 @@ __device__ __forceinline__ void stream_producer(const StreamParams& sp, const SR
                 const int nw = (i < base) ? kSW : rem;
                 for (int w = 0; w < nw; w++) {
                     const int j = w * base + min(w, rem) + i;
-                    const int tl = j / per_tile, r = j - tl * per_tile;
-                    const int part = r / ept, ce = r - part * ept;
+                    const int tl = __float2int_rd(((float)j + 0.5f) * inv_pt), r = j - tl * per_tile;
+                    const int part = __float2int_rd(((float)r + 0.5f) * inv_ept), ce = r - part * ept;
                     int s = 0, tile = d.T0 + tl;
                     if (swiglu) {
                         s = part;
                     } else {
-                        while (s + 1 < n_seg && tile >= nt[s]) { tile -= nt[s]; s++; }
+                        if (n_seg > 1 && tile >= nt[0]) { tile -= nt[0]; s = 1; }
+                        if (s == 1 && n_seg > 2 && tile >= nt[1]) { tile -= nt[1]; s = 2; }
                     }
                     const void* tmap = s == 0 ? tm[0] : s == 1 ? tm[1] : tm[2];
                     const int cs = s == 0 ? cstep[0] : s == 1 ? cstep[1] : cstep[2];
                     const int nb = s == 0 ? bytes[0] : s == 1 ? bytes[1] : bytes[2];
-                    const int es = s == 0 ? esz[0] : s == 1 ? esz[1] : esz[2];
-                    // the box must start on a 16-byte boundary of the row (tools/tma_lab.cu: an unaligned start is an
-                    // illegal instruction): Q6_K entries start at 840 ce, odd ones are fetched from 8 bytes earlier
-                    const int c0 = ((ce * cs) & ~15) / es;
+                    const int c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
                     if (!s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, mp.err, 1000 + ph, round * (uint32_t)rg.n_slots + slot)) return;
-                    mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nb);
-                    tma_load_2d(rg.base + slot * (uint32_t)kStreamSlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
+                    if (sp.no_load) {
+                        mbar_arrive(rg.full + 8u * slot);
+                    } else {
+                        mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nb);
+                        tma_load_2d(rg.base + slot * (uint32_t)kStreamSlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
+                    }
                     __threadfence_block();   // the barrier is armed before anybody learns that the entry was issued
                     *rg.issued = round * (uint32_t)rg.n_slots + slot + 1u;
                     if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
@@ -262,23 +273,39 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
     float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
     int piece_tl[2] = {-1, -1};   // CTA-local tiles of which this warp holds only a piece (first / last of its run)
     bool first = true;
-    for (int i = 0; i < n_ent; i++) {
-        const int j = j0 + i;
-        const int tl = j / per_tile, r = j - tl * per_tile;
-        const int part = r / ept, ce = r - part * ept;
-        int s, tile;
+    // cursor of this warp's run: CTA-local tile, matrix part (SwiGLU: 0 = gate, 1 = up), entry within the row
+    int tl = 0, part = 0, ce = 0, s = 0, tile = 0;
+    if (n_ent > 0) {
+        tl = j0 / per_tile;
+        const int r = j0 - tl * per_tile;
+        part = r / ept;
+        ce = r - part * ept;
         seg_of(d.T0 + tl, s, tile);
-        const int mat = swiglu ? part : s;
-        const MSeg& wsg = p.seg[mat];
-        const int type = wsg.type;
-        const uint32_t RS = (uint32_t)wsg.s_pitch, cbytes = (uint32_t)wsg.chunk_bytes;
-        const int c0 = ce * p.s_C, nc = min(p.s_C, p.chunks - c0);
+    }
+    // ring position of the warp's entries: q = seq0 + i * kSW + warp
+    uint32_t q = seq0 + (uint32_t)warp;
+    uint32_t slot = q % (uint32_t)rg.n_slots, round = q / (uint32_t)rg.n_slots;
+    // per-matrix constants of the cursor's position (refreshed when the cursor moves to another matrix)
+    int type = -1, nb_row = 0, cb = 0;
+    uint32_t RS = 0, cbytes = 0;
+    LaneB lb{};
+    auto load_mat = [&]() {
+        const MSeg& wsg = p.seg[swiglu ? part : s];
+        RS = (uint32_t)wsg.s_pitch;
+        cbytes = (uint32_t)wsg.chunk_bytes;
+        nb_row = wsg.nb_row;
+        cb = wsg.cb;
+        if (wsg.type != type) {
+            type = wsg.type;
+            lb = (type == T_Q6_K) ? lane_b_q6k(sm, g, t) : (type == T_Q8_0) ? lane_b_q80(sm, g, t) : lane_b_k45(sm, g, t, type == T_Q5_K);
+        }
+    };
+    if (n_ent > 0) load_mat();
+    const int sC = p.s_C, n_chunks = p.chunks, n_parts = p.s_parts;
+    for (int i = 0; i < n_ent; i++) {
+        const int c0 = ce * sC, nc = min(sC, n_chunks - c0);
         const uint32_t e00 = (uint32_t)c0 * kMmaChunk;
-        const uint32_t doff = ((uint32_t)ce * (uint32_t)p.s_C * cbytes) & 15u;   // the box starts 16-byte aligned: Q6_K, odd entries: 8
-        const LaneB lb = (type == T_Q6_K) ? lane_b_q6k(sm, g, t) : (type == T_Q8_0) ? lane_b_q80(sm, g, t) : lane_b_k45(sm, g, t, type == T_Q5_K);
-
-        const uint32_t q = seq0 + (uint32_t)(i * kSW + warp);
-        const uint32_t slot = q % (uint32_t)rg.n_slots, par = (q / (uint32_t)rg.n_slots) & 1u;
+        const uint32_t doff = ((uint32_t)c0 * cbytes) & 15u;   // the box starts 16-byte aligned (Q6_K: any even residue)
         if ((int)(*rg.issued - q) <= 0) {   // not issued yet (bounded spin, like s_wait)
             const long long t0 = clock64();
             while ((int)(*rg.issued - q) <= 0 && !*s_dead) {
@@ -288,7 +315,7 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
                 }
             }
         }
-        s_wait(rg.full + 8u * slot, par, s_dead, p.err, 2000 + warp, q);
+        s_wait(rg.full + 8u * slot, round & 1u, s_dead, p.err, 2000 + warp, q);
         if (first) { MMA_STAMP(4); first = false; }
         const uint32_t spb = rg.base + slot * (uint32_t)kStreamSlotBytes + doff + smem_token();
         float ua[4] = {0.f, 0.f, 0.f, 0.f};
@@ -300,24 +327,29 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
                 for (int c = 0; c < nc; c++) unit_k45<true>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
                 break;
             case T_Q6_K:
-                // block c of the entry starts at doff + 210 c (doff = 0 or 8): 8-byte aligned for c = 0, 4-byte for c = 2, else 2-byte
+                // block c of the entry starts at doff + 210 c: pick the widest loads its alignment allows (the row pitch is
+                // a multiple of 16)
                 for (int c = 0; c < nc; c++) {
                     const uint32_t a = spb + (uint32_t)c * cbytes, e0 = e00 + (uint32_t)c * kMmaChunk;
-                    if (c == 0) unit_q6k<8>(a, RS, e0, 0u, sm, lb, g, t, ua);
-                    else if (c == 2) unit_q6k<4>(a, RS, e0, 0u, sm, lb, g, t, ua);
+                    const uint32_t al = (doff + (uint32_t)c * cbytes) & 7u;
+                    if (al == 0u) unit_q6k<8>(a, RS, e0, 0u, sm, lb, g, t, ua);
+                    else if (al == 4u) unit_q6k<4>(a, RS, e0, 0u, sm, lb, g, t, ua);
                     else unit_q6k<2>(a, RS, e0, 0u, sm, lb, g, t, ua);
                 }
                 break;
             default:
                 for (int c = 0; c < nc; c++) {
                     const uint32_t e0 = e00 + (uint32_t)c * kMmaChunk;
-                    unit_q80(spb + (uint32_t)c * cbytes, RS, e0, 0u, min(wsg.cb, wsg.nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua);
+                    unit_q80(spb + (uint32_t)c * cbytes, RS, e0, 0u, min(cb, nb_row - (int)(e0 >> 5)), sm, lb, g, t, ua);
                 }
                 break;
         }
         pin4(ua);   // every shared-memory read of the entry has completed before the slot is handed back
         __syncwarp();
         if (lane == 0) mbar_arrive(rg.empty + 8u * slot);
+        q += (uint32_t)kSW;
+        slot += (uint32_t)kSW;
+        while (slot >= (uint32_t)rg.n_slots) { slot -= (uint32_t)rg.n_slots; round++; }
         if (swiglu && part == 1) {
 #pragma unroll
             for (int k = 0; k < 4; k++) au[k] += ua[k];
@@ -326,9 +358,22 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
             for (int k = 0; k < 4; k++) ag[k] += ua[k];
         }
 
-        // ---- tile finished (for this warp)? ----
+        // ---- advance the cursor; tile finished (for this warp)? ----
         const bool row_end = ce == ept - 1;
-        const bool tile_done = (row_end && (!swiglu || part == 1)) || (i == n_ent - 1);
+        const bool tile_end = row_end && part == n_parts - 1;
+        const bool tile_done = tile_end || (i == n_ent - 1);
+        const int cur_tl = tl, cur_s = s, cur_tile = tile;
+        ce++;
+        if (row_end) {
+            ce = 0;
+            part++;
+            if (tile_end) {
+                part = 0;
+                tl++;
+                if (i + 1 < n_ent) seg_of(d.T0 + tl, s, tile);
+            }
+            if (i + 1 < n_ent) load_mat();
+        }
         if (!tile_done) continue;
         if (i == n_ent - 1) MMA_STAMP(5);
         // reduce the 4 lanes of a row group, then lane L holds logical row L = 8k + n (register k of lanes 4n..4n+3)
@@ -351,14 +396,14 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
                 au[k] = 0.f;
             }
         }
-        const int te0 = tl * per_tile;
+        const int te0 = cur_tl * per_tile;
         if (j0 <= te0 && te0 + per_tile <= j1) {
-            epilogue(s, tile, vg, vu);   // the whole tile is mine
+            epilogue(cur_s, cur_tile, vg, vu);   // the whole tile is mine
         } else {
             const int ps = (j0 >= te0) ? 0 : 1;   // the tile is my first (0) or starts inside my run (1)
             s_part[warp][ps][0][lane] = vg;
             s_part[warp][ps][1][lane] = vu;
-            piece_tl[ps] = tl;
+            piece_tl[ps] = cur_tl;
         }
     }
     seq0 += (uint32_t)d.E;
@@ -414,7 +459,7 @@ __device__ __forceinline__ bool s_grid_wait(unsigned int* bar, unsigned int targ
 }
 
 template <int HD, int GMAX>
-__global__ void __maxnreg__(168) stream_decode_kernel(const __grid_constant__ StreamParams sp) {
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const __grid_constant__ StreamParams sp) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long s_bars[2 * kStreamMaxSlots];
     __shared__ float s_red[2 * kSW];
