@@ -995,6 +995,7 @@ static int stream_build(b200_ctx* c) {
     if (avail < x_region + 3 * (size_t)kStreamSlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 7, line %d)\n", __LINE__); return B200_OK; }
     int slots = (int)std::min<size_t>(kStreamMaxSlots, (avail - x_region) / kStreamSlotBytes);
     slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kStreamMaxSlots)));
+    if (slots <= kSW) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (%d ring slots)\n", slots); return B200_OK; }   // the parity protocol needs more slots than consumer warps
     const size_t smem = x_region + (size_t)slots * kStreamSlotBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

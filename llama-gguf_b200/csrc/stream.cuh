@@ -115,75 +115,104 @@ __device__ __forceinline__ SDeal s_deal(int s_rot, int s_ncta, int s_cbase, int 
 struct SRing {
     uint32_t base, full, empty;   // shared-space addresses: slots, full[n_slots], empty[n_slots] (8 bytes each)
     int n_slots;
-    // Number of entries the producer has issued so far.  A consumer may only wait on `full` for entry q once q has been
-    // issued: mbarrier waits are by phase PARITY, so a warp that waits for round r + 1 of a slot while round r is still
-    // being filled (its entry belongs to another warp) would see "the other parity" and run ahead on stale bytes.
-    volatile uint32_t* issued;
 };
 
 // ---------------------------------------------------------------- producer
+// What the producer needs to know about a GEMV phase, loaded from the phase program in global memory one phase AHEAD
+// (the loads of phase n + 1 are in flight while the entries of phase n are issued: a descriptor fetch is two dependent
+// L2 round trips, ~1.5 us, and would otherwise sit in front of the first copy of every phase).
+struct PDesc {
+    int gemv;          // 0: not a GEMV phase
+    int n_seg, ept, parts, swiglu;
+    int rot, ncta, cbase, crem;
+    const void* tm[3];
+    int nt[3], cstep[3], bytes[3];
+};
+__device__ __forceinline__ void pdesc_load(PDesc& d, const MegaPhase* P) {
+    d.gemv = P->kind == PH_GEMV;
+    const MParams* g = &P->gemv;
+    d.n_seg = g->n_seg; d.ept = g->s_ept; d.parts = g->s_parts; d.swiglu = g->epi == ME_SWIGLU;
+    d.rot = g->s_rot; d.ncta = g->s_ncta; d.cbase = g->s_cbase; d.crem = g->s_crem;
+    const int sC = g->s_C;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        const MSeg* sg = &g->seg[s];
+        d.tm[s] = sg->tmap;
+        d.nt[s] = sg->n_tiles;
+        d.cstep[s] = sC * sg->chunk_bytes;   // bytes between the entries of a row
+        d.bytes[s] = sg->s_pitch * kMmaRows;
+    }
+}
+
 __device__ __forceinline__ void stream_producer(const StreamParams& sp, const SRing& rg, volatile int* s_dead) {
     const MegaParams& mp = sp.mp;
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
+    const long long total = (long long)mp.n_tokens * n_run;
     uint32_t slot = 0, round = 0;
-    for (int tok = 0; tok < mp.n_tokens; tok++) {
-        for (int ph = 0; ph < n_run; ph++) {
-            const MegaPhase* P = mp.phases + ph;
-            if (P->kind != PH_GEMV) continue;
-            const MParams* g = &P->gemv;
-            const int n_seg = g->n_seg, ept = g->s_ept, parts = g->s_parts;
-            const bool swiglu = g->epi == ME_SWIGLU;
-            const void* tm[3];
-            int nt[3], cstep[3], bytes[3];
-#pragma unroll
-            for (int s = 0; s < 3; s++) {
-                const MSeg* sg = &g->seg[s < n_seg ? s : 0];
-                tm[s] = sg->tmap;
-                nt[s] = sg->n_tiles;
-                cstep[s] = g->s_C * sg->chunk_bytes;   // bytes between the entries of a row
-                bytes[s] = sg->s_pitch * kMmaRows;
-            }
-            const int per_tile = parts * ept;
-            const float inv_pt = 1.0f / (float)per_tile, inv_ept = 1.0f / (float)ept;   // exact small-integer division
-            const SDeal d = s_deal(g->s_rot, g->s_ncta, g->s_cbase, g->s_crem, per_tile);
+    PDesc cur, nxt;
+    pdesc_load(cur, mp.phases);
+    int ph_next = 1 % n_run;
+    for (long long it = 0; it < total; it++) {
+        pdesc_load(nxt, mp.phases + ph_next);   // issued now, first used after this phase's entries
+        if (++ph_next == n_run) ph_next = 0;
+        if (cur.gemv) {
+            const int ept = cur.ept, per_tile = cur.parts * ept;
+            const SDeal d = s_deal(cur.rot, cur.ncta, cur.cbase, cur.crem, per_tile);
             const int base = d.E / kSW, rem = d.E - base * kSW;
-            if (tok == 0 && d.E > 0) {
+            if (it < n_run && d.E > 0) {
                 // tensor maps live in global memory (written by the host before the launch): the TMA unit reads them
                 // through the tensormap proxy, which needs an acquire fence in every CTA before the first use
 #pragma unroll
                 for (int s = 0; s < 3; s++)
-                    if (s < n_seg) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm[s]) : "memory");
+                    if (s < cur.n_seg) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(cur.tm[s]) : "memory");
+            }
+            // one cursor per consumer warp (its run of entries is contiguous): tile within the phase, part, entry in the row
+            int c_tile[kSW], c_part[kSW], c_ce[kSW];
+#pragma unroll
+            for (int w = 0; w < kSW; w++) {
+                const int j = w * base + min(w, rem);
+                const int tl = j / per_tile, r = j - tl * per_tile;
+                c_tile[w] = d.T0 + tl;
+                c_part[w] = r / ept;
+                c_ce[w] = r - c_part[w] * ept;
             }
             for (int i = 0; i <= base; i++) {
                 const int nw = (i < base) ? kSW : rem;
-                for (int w = 0; w < nw; w++) {
-                    const int j = w * base + min(w, rem) + i;
-                    const int tl = __float2int_rd(((float)j + 0.5f) * inv_pt), r = j - tl * per_tile;
-                    const int part = __float2int_rd(((float)r + 0.5f) * inv_ept), ce = r - part * ept;
-                    int s = 0, tile = d.T0 + tl;
-                    if (swiglu) {
-                        s = part;
-                    } else {
-                        if (n_seg > 1 && tile >= nt[0]) { tile -= nt[0]; s = 1; }
-                        if (s == 1 && n_seg > 2 && tile >= nt[1]) { tile -= nt[1]; s = 2; }
+#pragma unroll
+                for (int w = 0; w < kSW; w++) {
+                    if (w < nw) {
+                        const int part = c_part[w], ce = c_ce[w];
+                        int s = 0, tile = c_tile[w];
+                        if (cur.swiglu) {
+                            s = part;
+                        } else {
+                            if (cur.n_seg > 1 && tile >= cur.nt[0]) { tile -= cur.nt[0]; s = 1; }
+                            if (s == 1 && cur.n_seg > 2 && tile >= cur.nt[1]) { tile -= cur.nt[1]; s = 2; }
+                        }
+                        const void* tmap = s == 0 ? cur.tm[0] : s == 1 ? cur.tm[1] : cur.tm[2];
+                        const int cs = s == 0 ? cur.cstep[0] : s == 1 ? cur.cstep[1] : cur.cstep[2];
+                        const int nb = s == 0 ? cur.bytes[0] : s == 1 ? cur.bytes[1] : cur.bytes[2];
+                        const int c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
+                        // advance the cursor of warp w
+                        if (ce + 1 == ept) {
+                            c_ce[w] = 0;
+                            if (part + 1 == cur.parts) { c_part[w] = 0; c_tile[w]++; } else { c_part[w] = part + 1; }
+                        } else {
+                            c_ce[w] = ce + 1;
+                        }
+                        if (!s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, mp.err, 1000, round * (uint32_t)rg.n_slots + slot)) return;
+                        if (sp.no_load) {
+                            mbar_arrive(rg.full + 8u * slot);
+                        } else {
+                            mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nb);
+                            tma_load_2d(rg.base + slot * (uint32_t)kStreamSlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
+                        }
+                        if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
                     }
-                    const void* tmap = s == 0 ? tm[0] : s == 1 ? tm[1] : tm[2];
-                    const int cs = s == 0 ? cstep[0] : s == 1 ? cstep[1] : cstep[2];
-                    const int nb = s == 0 ? bytes[0] : s == 1 ? bytes[1] : bytes[2];
-                    const int c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
-                    if (!s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, mp.err, 1000 + ph, round * (uint32_t)rg.n_slots + slot)) return;
-                    if (sp.no_load) {
-                        mbar_arrive(rg.full + 8u * slot);
-                    } else {
-                        mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nb);
-                        tma_load_2d(rg.base + slot * (uint32_t)kStreamSlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
-                    }
-                    __threadfence_block();   // the barrier is armed before anybody learns that the entry was issued
-                    *rg.issued = round * (uint32_t)rg.n_slots + slot + 1u;
-                    if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
                 }
             }
         }
+        cur = nxt;
     }
 }
 
@@ -306,15 +335,11 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
         const int c0 = ce * sC, nc = min(sC, n_chunks - c0);
         const uint32_t e00 = (uint32_t)c0 * kMmaChunk;
         const uint32_t doff = ((uint32_t)c0 * cbytes) & 15u;   // the box starts 16-byte aligned (Q6_K: any even residue)
-        if ((int)(*rg.issued - q) <= 0) {   // not issued yet (bounded spin, like s_wait)
-            const long long t0 = clock64();
-            while ((int)(*rg.issued - q) <= 0 && !*s_dead) {
-                if (clock64() - t0 > 2000000000LL) {
-                    *s_dead = 1;
-                    if (atomicExch(p.err, 4) == 0) { p.err[1] = 4000 + warp; p.err[2] = (int)blockIdx.x; p.err[3] = (int)q; }
-                }
-            }
-        }
+        // mbarrier waits are by phase PARITY: before waiting for round r of `full` this warp makes sure the slot's round
+        // r - 1 (an entry of ANOTHER warp) has been released, i.e. `full` is in phase r and not still in phase r - 1, where
+        // "parity r" would read as already complete.  Unambiguous because no warp is ever more than n_slots entries ahead
+        // of the slowest one (n_slots > kSW); round 0 passes at once (fresh barrier, parity 1).
+        s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, p.err, 4000 + warp, q);
         s_wait(rg.full + 8u * slot, round & 1u, s_dead, p.err, 2000 + warp, q);
         if (first) { MMA_STAMP(4); first = false; }
         const uint32_t spb = rg.base + slot * (uint32_t)kStreamSlotBytes + doff + smem_token();
@@ -467,7 +492,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
     __shared__ unsigned int s_ticket;
     __shared__ int s_flag;
     __shared__ int s_dead;
-    __shared__ unsigned int s_issued;
     __shared__ __align__(16) MegaPhase s_phs[3];
     __shared__ float s_rope[HD];
     __shared__ float s_av[kSW];
@@ -481,14 +505,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
     rg.full = smem_u32(s_bars);
     rg.empty = rg.full + 8u * (uint32_t)sp.n_slots;
     rg.n_slots = sp.n_slots;
-    rg.issued = &s_issued;
     if (tid == 0) {
         for (int i = 0; i < sp.n_slots; i++) {
             mbar_init(rg.full + 8u * i, 1);
             mbar_init(rg.empty + 8u * i, 1);
         }
         s_dead = 0;
-        s_issued = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
