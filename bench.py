@@ -282,11 +282,13 @@ def main():
         # the dominant (only) kernel is mega_decode_kernel: algorithmic bytes per token = weights + KV rows read,
         # duration = CUDA-event time per token of the timed region above
         achieved = token_bytes / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "mega_decode_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        kname = "stream_decode_kernel" if gpu.path() == "stream" else "mega_decode_kernel"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)",
                     "traffic": traffic, "bytes_per_launch": token_bytes, "avg_launch_us": ms_per_step * 1e3,
                     "launches_per_token": 1, "frac_of_nominal_8TBs": achieved / 8000.0,
-                    "note": "one persistent kernel per token (161 phases for Llama-3-8B); per launch = per token",
+                    "note": "one persistent kernel per token (161 phases for Llama-3-8B; stream = TMA producer warp + mbarrier ring "
+                            "across phase boundaries); per launch = per token",
                     "gemv_standalone": {"kernel": "gemv_mma_kernel", "GBps": gbytes / (gms * 1e-3) / 1e9,
                                         "launches_per_token": glaunches, "ms_per_token": gms,
                                         "what": "the same GEMVs as 129 separate PDL-chained launches"}}

@@ -146,6 +146,9 @@ B200_API int b200_debug_mega_phase(b200_ctx* ctx, int phase, unsigned long long*
 /* Watchdog words of the tensor-pipe / megakernel paths: out8[0] = 0 when no bounded wait ever gave up, else
  * (code, which wait, CTA, sequence number); clears them. */
 B200_API int b200_debug_err(b200_ctx* ctx, int* out8);
+/* Decode path chosen by b200_ctx_finalize: 0 = CUDA graph of per-op kernels, 1 = per-token megakernel,
+ * 2 = streamed megakernel (TMA producer warp + mbarrier ring, csrc/stream.cuh). */
+B200_API int b200_ctx_path(b200_ctx* ctx, int* out);
 /* Statistics for bench.py: kernels launched by this library since creation. */
 B200_API int b200_ctx_stats(b200_ctx* ctx, uint64_t* kernel_launches, uint64_t* weight_bytes, uint64_t* kv_bytes_per_pos);
 /* Roofline probe: replays only the dequant-GEMV launches of one token (same arguments and order

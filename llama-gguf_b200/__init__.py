@@ -109,6 +109,8 @@ def lib():
     L.b200_ctx_tp_handle.argtypes = [vp, vp]
     L.b200_ctx_tp_set_peer.argtypes = [vp, C.c_int, vp]
     L.b200_debug_mega_timeline.argtypes = [vp, u64p, C.c_int]
+    L.b200_debug_err.argtypes = [vp, C.POINTER(C.c_int)]
+    L.b200_ctx_path.argtypes = [vp, C.POINTER(C.c_int)]
     L.b200_debug_mega_phase.argtypes = [vp, C.c_int, u64p, C.c_int]
     try:
         L.b200_debug_read.argtypes = [vp, C.c_int, fp, C.c_int]
@@ -405,6 +407,18 @@ class GpuOnlyInference:
             self.close()
         except Exception:
             pass
+
+    def path(self):
+        """Decode path chosen at finalize: "graph" | "mega" | "stream"."""
+        v = C.c_int(0)
+        _check(lib().b200_ctx_path(self._h, C.byref(v)))
+        return ("graph", "mega", "stream")[v.value]
+
+    def watchdog(self):
+        """The eight watchdog words of the megakernel paths (all zero = no bounded wait ever gave up); clears them."""
+        e = (C.c_int * 8)()
+        _check(lib().b200_debug_err(self._h, e))
+        return list(e)
 
     # -- GpuInference ------------------------------------------------------
     def forward(self, token_id, seq=0):

@@ -951,6 +951,14 @@ static int stream_build(b200_ctx* c) {
                 if (!mma_type_ok(m.seg[s].type)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (type %d)\n", m.seg[s].type); return B200_OK; }
                 C = std::min(C, stream_pref_chunks(m.seg[s].type));
             }
+            {   // short phases: a CTA that owns only a handful of entries cannot spread them over its warps (O projection:
+                // one tile = 8 two-chunk entries for 7 warps, one warp does twice the work of the others) -> one-chunk entries
+                int tiles_all = 0;
+                for (int s = 0; s < (m.epi == ME_SWIGLU ? 1 : m.n_seg); s++) tiles_all += m.seg[s].n_tiles;
+                const int per_cta = (tiles_all + c->n_sm - 1) / c->n_sm;
+                const int entries = per_cta * (m.epi == ME_SWIGLU ? 2 : 1) * ((m.chunks + C - 1) / C);
+                if (C > 1 && entries < env_int("B200_STREAM_MIN_ENTRIES", 0)) C = 1;
+            }
             for (int s = 0; s < m.n_seg; s++) {
                 MSeg& sg = m.seg[s];
                 if ((sg.row_bytes & 15) || ((uintptr_t)sg.w & 15)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (row bytes %lld)\n", sg.row_bytes); return B200_OK; }
@@ -1306,6 +1314,14 @@ extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* 
     if (kernel_launches) *kernel_launches = c->launches;
     if (weight_bytes) *weight_bytes = c->weight_bytes_per_token;
     if (kv_bytes_per_pos) *kv_bytes_per_pos = (uint64_t)2 * c->d.n_layers * c->d.n_kv_heads * c->d.head_dim * 4;
+    return B200_OK;
+}
+
+// Which decode path finalize selected: 0 = CUDA graph of per-op kernels, 1 = per-token megakernel (mega.cuh),
+// 2 = streamed megakernel (stream.cuh).
+extern "C" int b200_ctx_path(b200_ctx* c, int* out) {
+    if (!c || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_path: null argument");
+    *out = c->mega_ok ? (c->stream_ok ? 2 : 1) : 0;
     return B200_OK;
 }
 

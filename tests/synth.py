@@ -22,6 +22,12 @@ TINY = {
     # tinyllama-like: hd=64, G=8
     "tinyllama-tiny": dict(arch="llama", hidden=512, n_layers=2, n_heads=8, n_kv_heads=1, head_dim=64, ffn=1536,
                            vocab=512, norm_eps=1e-5, rope_base=1e4, rope_neox=0, bias=False, tied=False),
+    # shapes the streamed megakernel takes (csrc/stream.cuh): every weight row a 16-byte multiple, i.e. K % 2048 == 0 for
+    # the Q6_K tensors of a *_K_M mix; vocab not a multiple of 32 (ragged last tile, zero-filled by the TMA unit)
+    "llama-stream-tiny": dict(arch="llama", hidden=2048, n_layers=2, n_heads=16, n_kv_heads=4, head_dim=128, ffn=4096,
+                              vocab=1000, norm_eps=1e-5, rope_base=5e5, rope_neox=0, bias=False, tied=False),
+    "tinyllama-stream-tiny": dict(arch="llama", hidden=2048, n_layers=2, n_heads=32, n_kv_heads=4, head_dim=64, ffn=2048,
+                                  vocab=520, norm_eps=1e-5, rope_base=1e4, rope_neox=0, bias=False, tied=False),
     # mixtral-like: 4 experts top-2
     "mixtral-tiny": dict(arch="llama", hidden=512, n_layers=2, n_heads=8, n_kv_heads=2, head_dim=64, ffn=512,
                          vocab=512, norm_eps=1e-5, rope_base=1e6, rope_neox=0, bias=False, tied=False,
