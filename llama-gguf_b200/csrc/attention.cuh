@@ -93,6 +93,7 @@ struct AttnParams {
     const int* pos;        // device scalar (kv_len = *pos + 1) or nullptr
     int kv_len_fixed;      // used when pos == nullptr
     int n_kv, G, max_seq, n_splits;
+    int min_chunk;         // KV positions per split below which a context is not split further (0: kAttnMinChunk)
     float scale;
     // optional fused RoPE + KV-cache write (per-token megakernel): q | k | v raw from the QKV GEMV (+bias), rotated
     // here exactly as rope_kv_kernel does; the split that owns position `pos` also writes the cache rows
@@ -122,8 +123,9 @@ __device__ __forceinline__ void attn_stamp(const AttnParams& p, int i) {
 #define B200_ATTN_MIN_CHUNK 32
 #endif
 constexpr int kAttnMinChunk = B200_ATTN_MIN_CHUNK;
-__device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits) {
-    return max(1, min(n_splits, (kv_len + kAttnMinChunk - 1) / kAttnMinChunk));
+__device__ __forceinline__ int attn_eff_splits(int kv_len, int n_splits, int min_chunk) {
+    const int mc = min_chunk > 0 ? min_chunk : kAttnMinChunk;
+    return max(1, min(n_splits, (kv_len + mc - 1) / mc));
 }
 
 // defined in gemv_mma.cuh (stage_out32 without a weight); a warp holds 32 consecutive elements of the output vector
@@ -155,7 +157,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = p.G;
-    const int ns = attn_eff_splits(kv_len, p.n_splits);
+    const int ns = attn_eff_splits(kv_len, p.n_splits, p.min_chunk);
     if (split >= ns) return;
     int chunk = (kv_len + ns - 1) / ns;
     chunk = (chunk + NW - 1) / NW * NW;
@@ -369,7 +371,15 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
     const float* parts = p.part + (size_t)kh * p.n_splits * G * part_stride;
     const int n_part = ns * G * part_stride;     // contiguous: splits 0..ns-1 of this head
     float* s_p = sm;                             // [ns][G][HD + 2]   (fits: ns <= NW * GMAX * HD / (G * (HD+2)) is checked by the host)
-    for (int i = threadIdx.x; i < n_part; i += NT) s_p[i] = __ldcg(parts + i);
+    // batches of 8 independent loads per thread (a plain copy loop keeps one load in flight per iteration: ~0.7 us each)
+    for (int i0 = threadIdx.x; i0 < n_part; i0 += NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (i0 + k * NT < n_part) ? __ldcg(parts + i0 + k * NT) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (i0 + k * NT < n_part) s_p[i0 + k * NT] = v[k];
+    }
     attn_sync<NT>();
     for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
         const int g = idx / HD, d = idx - g * HD;

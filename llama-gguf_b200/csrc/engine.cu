@@ -844,6 +844,7 @@ static int mega_build(b200_ctx* c) {
                 ap.q = nullptr; ap.k_cache = kc; ap.v_cache = vc; ap.out = c->attn; ap.part = c->mega_attn_part; ap.tickets = c->tickets;
                 ap.pos = &sl.d_state->pos_cur; ap.kv_len_fixed = 0; ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len;
                 ap.n_splits = c->mega_splits; ap.scale = 1.0f / sqrtf((float)hd);
+                ap.min_chunk = env_int("B200_ATTN_MIN_CHUNK", 0);
                 ap.qkv_raw = c->qkv; ap.freq = c->rope_freq; ap.rope_scale = d.rope_scale; ap.neox = d.rope_neox; ap.n_heads = nh;
                 ap.stage_out = st_attn; ap.stage_K = nh * hd;
                 prog.push_back(ph);
