@@ -14,8 +14,9 @@ random-init GGUF blocks (synthetic), batch 1, 8K context window, 128-token promp
   e2e    : the same metric through the reference-facing call GpuInference::forward —
            token id from host memory in, `vocab` f32 logits to host memory out, host argmax
            (src/main.rs:1811-1822) — wall clock around the K calls.
-  roofline     : the dequant-GEMV kernel (gemv_mma_kernel): weight bytes one token's GEMV launches
-           read / the time of exactly those launches replayed back to back (CUDA events).
+  roofline     : the per-token kernel (stream_decode_kernel, or mega_decode_kernel for shapes it does not take): weight
+           bytes + KV rows one token reads / the CUDA-event time per token of the timed region (the kernel IS the step);
+           `gemv_standalone` = the same GEMVs as 129 separate launches, for comparison.
   cpu_baseline : the C++ restatement of the reference's CPU path (oracle/) on this box's cores.
 
 --impl reference times that CPU restatement (the reference is Rust; no rustc in the image).
