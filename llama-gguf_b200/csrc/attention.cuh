@@ -329,19 +329,31 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
     attn_sync<NT>();
     const int part_stride = HD + 2;
     float* my_part = p.part + ((size_t)(kh * p.n_splits + split) * G) * part_stride;  // slots sized for n_splits
-    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
-        const int g = idx / HD, d = idx - g * HD;
+    // merge coefficients once per (warp, head): thread g turns s_m[w][g] into exp(m_w - M) and leaves (M, L) in
+    // s_l[0][g], s_l[1][g] (an expf per element and warp in the loop below was ~2 us of dependent math per item)
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
         float M = -INFINITY;
 #pragma unroll
         for (int w = 0; w < NW; w++) M = fmaxf(M, s_m[w * GMAX + g]);
-        float L = 0.0f, A = 0.0f;
+        float L = 0.0f;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
             const float mw = s_m[w * GMAX + g];
             const float c = (mw == -INFINITY) ? 0.0f : expf(mw - M);
             L += s_l[w * GMAX + g] * c;
-            A += s_acc[(w * GMAX + g) * HD + d] * c;
+            s_m[w * GMAX + g] = c;
         }
+        s_l[0 * GMAX + g] = M;
+        s_l[1 * GMAX + g] = L;
+    }
+    attn_sync<NT>();
+    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
+        const int g = idx / HD, d = idx - g * HD;
+        const float M = s_l[0 * GMAX + g], L = s_l[1 * GMAX + g];
+        float A = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) A += s_acc[(w * GMAX + g) * HD + d] * s_m[w * GMAX + g];
         if (ns == 1) {  // a single split: this is the answer (no scratch, no ticket)
             const float o = A / L;
             p.out[(kh * G + g) * HD + d] = o;
@@ -381,17 +393,29 @@ __device__ __forceinline__ void attn_decode_item(const AttnParams& p, int kh, in
             if (i0 + k * NT < n_part) s_p[i0 + k * NT] = v[k];
     }
     attn_sync<NT>();
-    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
-        const int g = idx / HD, d = idx - g * HD;
+    // coefficients once per (split, head): thread g turns the split maxima into exp(m_s - M), leaves L in split 0's slot
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
         float M = -INFINITY;
         for (int s = 0; s < ns; s++) M = fmaxf(M, s_p[(s * G + g) * part_stride + HD]);
-        float L = 0.0f, A = 0.0f;
+        float L = 0.0f;
         for (int s = 0; s < ns; s++) {
-            const float* ps = s_p + (s * G + g) * part_stride;
+            float* ps = s_p + (s * G + g) * part_stride;
             const float ms = ps[HD];
             const float c = (ms == -INFINITY) ? 0.0f : expf(ms - M);
             L += ps[HD + 1] * c;
-            A += ps[d] * c;
+            ps[HD] = c;
+        }
+        s_p[(0 * G + g) * part_stride + HD + 1] = L;
+    }
+    attn_sync<NT>();
+    for (int idx = threadIdx.x; idx < G * HD; idx += NT) {
+        const int g = idx / HD, d = idx - g * HD;
+        const float L = s_p[(0 * G + g) * part_stride + HD + 1];
+        float A = 0.0f;
+        for (int s = 0; s < ns; s++) {
+            const float* ps = s_p + (s * G + g) * part_stride;
+            A += ps[d] * ps[HD];
         }
         const float o = A / L;
         p.out[(kh * G + g) * HD + d] = o;
