@@ -151,6 +151,7 @@ struct b200_ctx {
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
+    int* h_err = nullptr;   // pinned copy of the first watchdog word, fetched with every synchronising call
     int* h_token = nullptr;
     std::vector<Slot> slots;
     // options
@@ -447,6 +448,8 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
         CU(cudaMemcpy(c->rope_freq, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
     }
     CU_ALLOC(cudaHostAlloc((void**)&c->h_logits, V * 4, cudaHostAllocDefault));
+    CU_ALLOC(cudaHostAlloc((void**)&c->h_err, 8 * sizeof(int), cudaHostAllocDefault));
+    memset(c->h_err, 0, 8 * sizeof(int));
     CU_ALLOC(cudaHostAlloc((void**)&c->h_token, sizeof(int), cudaHostAllocDefault));
     c->slots.resize(d.max_batch);
     const uint64_t kv_elems = (uint64_t)d.n_layers * 2 * nkv * d.max_seq_len * hd;
@@ -556,6 +559,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
                     (void*)c->rope_freq, c->flush_buf, (void*)c->mma_part, (void*)c->mma_tickets, (void*)c->mma_err})
         cudaFree(p);
     if (c->h_logits) cudaFreeHost(c->h_logits);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_token) cudaFreeHost(c->h_token);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1142,6 +1146,17 @@ static int set_token(b200_ctx* c, Slot& sl, uint32_t token) {
     return B200_OK;
 }
 
+// The megakernels never hang: a wait that gives up (~1 s) raises the watchdog words and the launch finishes with garbage.
+// Every synchronising entry point fetches the words with its results and turns them into an error (fail loudly).
+#define WATCHDOG_FETCH(c) CU(cudaMemcpyAsync((c)->h_err, (c)->mma_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, (c)->stream))
+static int watchdog_check(b200_ctx* c, const char* who) {
+    if (!c->h_err[0]) return B200_OK;
+    char msg[200];
+    snprintf(msg, sizeof msg, "%s: device watchdog tripped (code %d, wait %d, CTA %d, sequence %d): results discarded", who, c->h_err[0],
+             c->h_err[1], c->h_err[2], c->h_err[3]);
+    return fail(B200_ERR_OPERATION_FAILED, msg);
+}
+
 extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_out) {
     int rc;
     if ((rc = check_slot(c, seq, "b200_forward"))) return rc;
@@ -1153,7 +1168,9 @@ extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_
     if ((rc = run_token(c, seq, MODE_LOGITS))) return rc;
     // tensor parallel: this rank's slice [rank * vocab/P, (rank+1) * vocab/P) of the logits (the caller gathers)
     CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
+    WATCHDOG_FETCH(c);
     CU(cudaStreamSynchronize(c->stream));
+    if ((rc = watchdog_check(c, "b200_forward"))) return rc;
     memcpy(logits_out, c->h_logits, (size_t)c->vocab_l * 4);
     sl.host_pos++;
     return B200_OK;
@@ -1167,7 +1184,9 @@ extern "C" int b200_prefill_token(b200_ctx* c, int seq, uint32_t token) {
     Slot& sl = c->slots[seq];
     if ((rc = set_token(c, sl, token))) return rc;
     if ((rc = run_token(c, seq, MODE_PREFILL))) return rc;
+    WATCHDOG_FETCH(c);
     CU(cudaStreamSynchronize(c->stream));  // h_token is reused by the next call
+    if ((rc = watchdog_check(c, "b200_prefill_token"))) return rc;
     sl.host_pos++;
     return B200_OK;
 }
@@ -1237,7 +1256,9 @@ extern "C" int b200_decode_greedy(b200_ctx* c, int seq, uint32_t first_token, in
             if ((rc = run_token(c, seq, MODE_GREEDY))) return rc;
     }
     CU(cudaEventRecord(e1, c->stream));
+    WATCHDOG_FETCH(c);
     CU(cudaStreamSynchronize(c->stream));
+    if ((rc = watchdog_check(c, "b200_decode_greedy"))) return rc;
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
@@ -1333,6 +1354,7 @@ extern "C" int b200_debug_err(b200_ctx* c, int* out8) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy(out8, c->mma_err, 8 * sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemset(c->mma_err, 0, 8 * sizeof(int)));
+    memset(c->h_err, 0, 8 * sizeof(int));
     return B200_OK;
 }
 

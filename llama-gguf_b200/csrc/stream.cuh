@@ -233,54 +233,29 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
     const long long gw = (long long)blockIdx.x * kSW + warp;  // debug stamps only
     MMA_STAMP(0);
 
-    post_fn();
-    MMA_STAMP(1);
-
-    // ---- x: the staged form left by its producer (flat copy) or f32 -> three int8 planes here ----
+    // ---- everything that does not depend on other CTAs happens BEFORE the barrier wait (it used to cost ~0.7 us after it:
+    // integer divisions of the cursor, matrix constants, B-operand lane tables) ----
     const XLayout XL = x_layout(K);
     float unscale = 1.0f;
-    if (p.x_staged) {
-        const uint32_t n16 = (XL.zero + 15u) >> 4;
-        for (uint32_t i = tid; i < n16; i += kSNT) cp_async16(sbase + 16u * i, p.x_staged + 16u * i);
-        cp_async_commit();
-        MMA_STAMP(2);
-        cp_async_wait<0>();
-        if (tid < 64) reinterpret_cast<uint32_t*>(smem + XL.zero)[tid] = 0u;
-        cons_sync();
-        if (p.norm_w) {
-            const float* ssq = reinterpret_cast<const float*>(smem + XL.ssq);
-            float tot = 0.0f;
-            for (int i = lane; i < (K >> 5); i += 32) tot += ssq[i];
-            tot = warp_sum(tot);
-            unscale = 1.0f / sqrtf(tot / (float)K + p.eps);
-        }
-    } else {
-        XStage xst;
-        const XSource xsrc{p.x, nullptr, 0, 0, nullptr, nullptr};
-        stage_x_load(xst, xsrc, p.norm_w, K, kSNT);
-        MMA_STAMP(2);
-        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, kSNT);
-        cons_sync();
-        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K, kSW);
-    }
-    MMA_STAMP(3);
-    const uint32_t tokx = smem_token();
-    XSmem sm;
-    sm.p0 = sbase + tokx + XL.p0;
-    sm.p1 = sbase + tokx + XL.p1;
-    sm.p2 = sbase + tokx + XL.p2;
-    sm.sx = sbase + tokx + XL.sx;
-    sm.x16 = sbase + tokx + XL.x16;
-    sm.zero = sbase + tokx + XL.zero;
+    int pf_s = -1, pf_tile = -1;                          // first tile this warp will finish, and its epilogue operands
+    float pf_bias = 0.0f, pf_res = 0.0f, pf_w = 1.0f;
+    XSmem sm;   // final after the x staging below (an opaque token is added so that no load of x is hoisted above it)
+    sm.p0 = sbase + XL.p0;
+    sm.p1 = sbase + XL.p1;
+    sm.p2 = sbase + XL.p2;
+    sm.sx = sbase + XL.sx;
+    sm.x16 = sbase + XL.x16;
+    sm.zero = sbase + XL.zero;
 
     // ---- epilogue of a finished tile: lane L owns row tile*32 + L of segment s (vu: the up row for SwiGLU) ----
     auto epilogue = [&](int s, int tile, float v, float vu) {
         const MSeg& sg = p.seg[s];
         const int j = tile * kMmaRows + lane;
         const bool valid = j < sg.n_rows;
-        const float e_bias = (valid && sg.bias) ? sg.bias[j] : 0.0f;
-        const float e_res = (valid && p.epi == ME_RESIDUAL) ? p.residual[j] : 0.0f;
-        const float e_w = (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
+        const bool pf = s == pf_s && tile == pf_tile;   // warp-uniform
+        const float e_bias = pf ? pf_bias : (valid && sg.bias) ? sg.bias[j] : 0.0f;
+        const float e_res = pf ? pf_res : (valid && p.epi == ME_RESIDUAL) ? p.residual[j] : 0.0f;
+        const float e_w = pf ? pf_w : (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
         v *= unscale;
         float val = v;
         if (swiglu) val = mma_silu(v) * (vu * unscale);
@@ -299,9 +274,6 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
             while (s + 1 < p.n_seg && tile >= p.seg[s].n_tiles) { tile -= p.seg[s].n_tiles; s++; }
     };
 
-    float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
-    int piece_tl[2] = {-1, -1};   // CTA-local tiles of which this warp holds only a piece (first / last of its run)
-    bool first = true;
     // cursor of this warp's run: CTA-local tile, matrix part (SwiGLU: 0 = gate, 1 = up), entry within the row
     int tl = 0, part = 0, ce = 0, s = 0, tile = 0;
     if (n_ent > 0) {
@@ -331,6 +303,59 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
     };
     if (n_ent > 0) load_mat();
     const int sC = p.s_C, n_chunks = p.chunks, n_parts = p.s_parts;
+    // the first tile this warp will finish (its start lies in the warp's run): its bias / residual / norm-weight values
+    // are fetched right after the barrier, in the shadow of the x staging, instead of in front of the epilogue's stores
+    if (n_ent > 0) {
+        const int ptl = (j0 + per_tile - 1) / per_tile;
+        if (ptl * per_tile < j1) seg_of(d.T0 + ptl, pf_s, pf_tile);
+    }
+
+    post_fn();
+    MMA_STAMP(1);
+    if (pf_s >= 0) {
+        const MSeg& sg = p.seg[pf_s];
+        const int j = pf_tile * kMmaRows + lane;
+        const bool valid = j < sg.n_rows;
+        pf_bias = (valid && sg.bias) ? sg.bias[j] : 0.0f;
+        pf_res = (valid && p.epi == ME_RESIDUAL) ? p.residual[j] : 0.0f;
+        pf_w = (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
+    }
+
+    // ---- x: the staged form left by its producer (flat copy) or f32 -> three int8 planes here ----
+    if (p.x_staged) {
+        const uint32_t n16 = (XL.zero + 15u) >> 4;
+        for (uint32_t i = tid; i < n16; i += kSNT) cp_async16(sbase + 16u * i, p.x_staged + 16u * i);
+        cp_async_commit();
+        MMA_STAMP(2);
+        cp_async_wait<0>();
+        if (tid < 64) reinterpret_cast<uint32_t*>(smem + XL.zero)[tid] = 0u;
+        cons_sync();
+        if (p.norm_w) {
+            const float* ssq = reinterpret_cast<const float*>(smem + XL.ssq);
+            float tot = 0.0f;
+            for (int i = lane; i < (K >> 5); i += 32) tot += ssq[i];
+            tot = warp_sum(tot);
+            unscale = 1.0f / sqrtf(tot / (float)K + p.eps);
+        }
+    } else {
+        XStage xst;
+        const XSource xsrc{p.x, nullptr, 0, 0, nullptr, nullptr};
+        stage_x_load(xst, xsrc, p.norm_w, K, kSNT);
+        MMA_STAMP(2);
+        stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, kSNT);
+        cons_sync();
+        unscale = stage_x_unscale(s_red, p.norm_w != nullptr, p.eps, K, kSW);
+    }
+    MMA_STAMP(3);
+    {   // lane tables (lb) hold differences of these addresses, so they stay valid
+        const uint32_t tokx = smem_token();
+        sm.sx += tokx;
+        sm.x16 += tokx;
+        sm.zero += tokx;
+    }
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
+    int piece_tl[2] = {-1, -1};   // CTA-local tiles of which this warp holds only a piece (first / last of its run)
+    bool first = true;
     for (int i = 0; i < n_ent; i++) {
         const int c0 = ce * sC, nc = min(sC, n_chunks - c0);
         const uint32_t e00 = (uint32_t)c0 * kMmaChunk;
