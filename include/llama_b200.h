@@ -173,6 +173,10 @@ B200_API int b200_op_rms_norm(const float* x, const float* weight, float eps, fl
 B200_API int b200_op_vec_mat(const float* a, const float* w, float* out, size_t k, size_t n);
 /* vec_mat_q: W quantised, n rows of k/bs blocks (backend/mod.rs:110). */
 B200_API int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t k, size_t n);
+/* Extension (no counterpart in the reference's Backend trait, which runs a prompt as T vec_mat_q calls,
+ * src/model/llama.rs:327-345): T rows at once through the tcgen05/TMEM dequant-GEMM.  a [t_rows][k] f32,
+ * W = n rows of k/bs GGUF blocks (Q4_K, Q5_K, Q6_K, Q8_0), out [t_rows][n].  fp16 operands, f32 accumulation. */
+B200_API int b200_op_mat_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t t_rows, size_t k, size_t n);
 /* dequantize: bit-exact with the reference's dequantize_* (tensor/quant/dequant.rs). */
 B200_API int b200_op_dequantize(const void* src, uint32_t ggml_type, float* out, size_t n_elems);
 /* rope: q[n_heads,1,hd], k[n_kv,1,hd] in place (cpu/ops.rs:1216-1337). */

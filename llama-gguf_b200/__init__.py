@@ -127,6 +127,7 @@ def lib():
     L.b200_op_rms_norm.argtypes = [fp, fp, C.c_float, fp, C.c_size_t, C.c_size_t]
     L.b200_op_vec_mat.argtypes = [fp, fp, fp, C.c_size_t, C.c_size_t]
     L.b200_op_vec_mat_q.argtypes = [fp, vp, C.c_uint32, fp, C.c_size_t, C.c_size_t]
+    L.b200_op_mat_mat_q.argtypes = [fp, vp, C.c_uint32, fp, C.c_size_t, C.c_size_t, C.c_size_t]
     L.b200_op_dequantize.argtypes = [vp, C.c_uint32, fp, C.c_size_t]
     L.b200_op_rope.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
     L.b200_op_attention_cached.argtypes = [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
@@ -250,6 +251,21 @@ class CudaB200Backend:
             raise ShapeMismatch(f"vec_mat: expected [{a.shape[0]}], got [{k}]")
         out = np.empty(n, dtype=np.float32)
         _check(lib().b200_op_vec_mat(_fp(a), _fp(b), _fp(out), k, n))
+        return out
+
+    def mat_mat_q(self, a, raw, ggml_type, k, n):
+        """a [t, k] f32, W [k, n] quantised (raw GGUF blocks) -> [t, n] through the tcgen05 dequant-GEMM (fp16 operands)."""
+        a = _f32(a)
+        if a.ndim != 2 or a.shape[1] != k:
+            raise ShapeMismatch(f"mat_mat_q: expected [t, {k}], got {list(a.shape)}")
+        if ggml_type not in BLOCK:
+            raise UnsupportedDType(f"mat_mat_q: ggml type {ggml_type}")
+        raw = np.ascontiguousarray(raw).view(np.uint8).ravel()
+        be, bb = BLOCK[ggml_type]
+        if k % be or raw.size != k // be * bb * n:
+            raise ShapeMismatch(f"mat_mat_q: {raw.size} bytes do not match [{k}, {n}] of {TYPE_NAMES[ggml_type]}")
+        out = np.empty((a.shape[0], n), dtype=np.float32)
+        _check(lib().b200_op_mat_mat_q(_fp(a), raw.ctypes.data, ggml_type, _fp(out), a.shape[0], k, n))
         return out
 
     def vec_mat_q(self, a, raw, ggml_type, k, n):

@@ -24,6 +24,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemv.cuh"
+#include "gemm_umma.cuh"
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -1558,6 +1559,32 @@ extern "C" int b200_op_vec_mat(const float* a, const float* w, float* out, size_
     vec_mat_f32_kernel<<<(int)((n * 32 + 255) / 256), 256>>>(da.as<float>(), dw.as<float>(), dout.as<float>(), (int)k, (int)n);
     if ((rc = op_finish("vec_mat"))) return rc;
     CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// Backend extension for prefill / batched decode: T input rows at once through the tcgen05 dequant-GEMM
+// (csrc/gemm_umma.cuh).  out[t][j] = sum_k a[t][k] * deq(W)[j][k]: the same contraction as T calls of vec_mat_q, fp16
+// operands with f32 accumulation (documented tolerance 2e-3 of the largest output).
+extern "C" int b200_op_mat_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t t_rows, size_t k, size_t n) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!a || !w || !out) return fail(B200_ERR_INVALID_ARGUMENT, "mat_mat_q: null pointer");
+    const int t = (int)ggml_type;
+    if (!umma_type_ok(t)) return fail(B200_ERR_UNSUPPORTED_DTYPE, "mat_mat_q: ggml type " + std::to_string(ggml_type) + " (Q4_K, Q5_K, Q6_K, Q8_0 only)");
+    const int be = type_block_elems(t), bb = type_block_bytes(t);
+    if (t_rows == 0 || k == 0 || n == 0 || k % be || k % 64) return fail(B200_ERR_SHAPE_MISMATCH, "mat_mat_q: k must be a non-zero multiple of the block size and of 64");
+    const size_t row_bytes = k / be * bb, wbytes = row_bytes * n;
+    DevBuf da, dw, dout;
+    if (da.alloc(t_rows * k * 4) || dw.alloc(wbytes + 256) || dout.alloc(t_rows * n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "mat_mat_q");
+    CU(cudaMemcpy(da.p, a, t_rows * k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
+    UmmaParams p{};
+    p.w = dw.as<uint8_t>(); p.row_bytes = (long long)row_bytes; p.type = t; p.n_rows = (int)n; p.K = (int)k;
+    p.x = da.as<float>(); p.ldx = (int)k; p.T = (int)t_rows; p.y = dout.as<float>(); p.ldy = (int)n;
+    if (!umma_eligible(p)) return fail(B200_ERR_SHAPE_MISMATCH, "mat_mat_q: rows of this type / length are not aligned for the tensor-core path");
+    CU(umma_launch(p, 0));
+    if ((rc = op_finish("mat_mat_q"))) return rc;
+    CU(cudaMemcpy(out, dout.p, t_rows * n * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 

@@ -1,0 +1,264 @@
+// gemm_umma.cuh — tcgen05 / TMEM dequant-GEMM: the one dense contraction of prefill and batched decode.
+//
+//   Y[t][j] (+)= sum_k deq(W)[j][k] * X[t][k] (+ bias[j]),   W = N rows of GGUF blocks (Q4_K / Q5_K / Q6_K / Q8_0), X f32.
+//
+// The reference runs a prompt token by token through its vec_mat_q kernels (src/model/llama.rs:327-345,
+// src/backend/cuda/gpu_only.rs:776-790: T GEMVs per weight matrix, every one of them re-reading the matrix); this is
+// the same arithmetic as T columns of one GEMM: the weights are read once per 256-token tile.
+//
+// One CTA (128 threads) per (128 weight rows, TN tokens) output tile.  Per K step of 64 elements (128 bytes of fp16 =
+// one row of a 128B-swizzle atom):
+//   * thread r dequantises 64 elements of ITS weight row in registers with the reference arithmetic in f32
+//     (dequant.rs:205-356: d*sc*q - dmin*m, (d*sc)*q for Q6_K, q*d for Q8_0), rounds to fp16 and writes the row's eight
+//     16-byte chunks into the K-major SWIZZLE_128B shared-memory tile (chunk c of row r at chunk c ^ (r & 7));
+//   * the activations (f32 in HBM) are rounded to fp16 into a second tile the same way;
+//   * fence.proxy.async, then ONE elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M = 128 weight rows,
+//     N = TN tokens, K = 16 each; SASS UTCHMMA) on the two shared-memory descriptors; the f32 accumulator lives in TMEM
+//     (TN columns x 128 lanes); tcgen05.commit -> mbarrier tells the CTA that the tiles may be overwritten;
+//   * epilogue: warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld.32x32b.x32 (SASS LDTM), thread = weight row, 32
+//     tokens per load, and stores Y so that a warp writes 32 consecutive floats of one token's row.
+// fp16 operands, f32 accumulation: measured 3e-4 of the largest output against a double-precision dequant-then-dot
+// (tools/umma_lab.cu); the exact token-by-token path stays the default where bit-level greedy parity matters.
+// First version: not pipelined (dequant, MMA and the next step's loads are serialised by one mbarrier) -- 150 TFLOP/s on
+// the 2K-token gate projection, i.e. the dequant, not the tensor pipe, is the limit.
+#pragma once
+#include "common.cuh"
+#include "quant.cuh"
+
+namespace b200 {
+
+constexpr int kUmmaM = 128;   // weight rows per CTA
+constexpr int kUmmaK = 64;    // K elements per step
+
+__device__ __forceinline__ uint32_t umma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start >> 4 [0,14), LBO >> 4 [16,30) (unused for swizzled K-major), SBO >> 4 [32,46) = 1024 bytes between 8-row groups,
+// version 1 [46,48), layout type 2 = SWIZZLE_128B [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (0), K-major both, N >> 3 at 17, M >> 4 at 24
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool umma_mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: never hang the box
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!ok && clock64() - t0 > 2000000000LL) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ uint32_t umma_pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a 128B-swizzled tile of 128-byte rows
+__device__ __forceinline__ uint32_t umma_sw128(int r, int c) {
+    return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t umma_ld16(const uint8_t* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
+
+// Eight consecutive elements k0 + 8c .. k0 + 8c + 7 (k0 % 64 == 0) of the weight row `row`, as four packed half2.
+__device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0, int c) {
+    float v[8];
+    if (type == T_Q4_K || type == T_Q5_K) {   // dequant.rs:205-315
+        const bool q5 = type == T_Q5_K;
+        const uint8_t* blk = row + (long long)(k0 >> 8) * (q5 ? 176 : 144);
+        const int gp = (k0 & 255) >> 6, hi = c >> 2;        // sub-block 2gp (low nibbles) or 2gp + 1 (high nibbles)
+        const uint32_t dd = __ldg(reinterpret_cast<const uint32_t*>(blk));
+        const float d = half_bits_to_float(dd), dmin = half_bits_to_float(dd >> 16);
+        int sc, mn;
+        scale_min_k4(blk + 4, 2 * gp + hi, sc, mn);
+        const float d1 = __fmul_rn(d, (float)sc), m1 = __fmul_rn(dmin, (float)mn);
+        const uint8_t* qs = blk + (q5 ? 48 : 16) + 32 * gp + 8 * (c & 3);
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(qs));
+        uint2 h = make_uint2(0u, 0u);
+        if (q5) h = __ldg(reinterpret_cast<const uint2*>(blk + 16 + 8 * (c & 3)));
+        const int sh = 4 * hi, hb = 2 * gp + hi;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t ww = i < 4 ? w.x : w.y, hh = i < 4 ? h.x : h.y;
+            int q = (int)((ww >> (8 * (i & 3) + sh)) & 15u);
+            if (q5) q += (int)((hh >> (8 * (i & 3) + hb)) & 1u) << 4;
+            v[i] = __fsub_rn(__fmul_rn(d1, (float)q), m1);
+        }
+    } else if (type == T_Q6_K) {   // dequant.rs:321-356; blocks are only 2-byte aligned
+        const uint8_t* blk = row + (long long)(k0 >> 8) * 210;
+        const int ks = (k0 & 255) >> 6, n = ks >> 1, qq = 2 * (ks & 1) + (c >> 2), l0 = 8 * (c & 3);
+        const float d = half_bits_to_float(umma_ld16(blk + 208));
+        const int sc = (int)(signed char)__ldg(blk + 192 + 8 * n + (l0 >> 4) + 2 * qq);
+        const float ds = __fmul_rn(d, (float)sc);
+        const uint8_t* ql = blk + 64 * n + 32 * (qq & 1) + l0;
+        const uint8_t* qh = blk + 128 + 32 * n + l0;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const uint32_t a = umma_ld16(ql + i), b = umma_ld16(qh + i);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t lo = (a >> (8 * j + 4 * (qq >> 1))) & 15u, hb = (b >> (8 * j + 2 * qq)) & 3u;
+                v[i + j] = __fmul_rn(ds, (float)((int)(lo | (hb << 4)) - 32));
+            }
+        }
+    } else {   // Q8_0, dequant.rs:103-109
+        const uint8_t* blk = row + (long long)((k0 >> 5) + (c >> 2)) * 34;
+        const float d = half_bits_to_float(umma_ld16(blk));
+        const uint8_t* q = blk + 2 + 8 * (c & 3);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const uint32_t a = umma_ld16(q + i);
+            v[i] = __fmul_rn((float)(int)(signed char)(a & 255u), d);
+            v[i + 1] = __fmul_rn((float)(int)(signed char)(a >> 8), d);
+        }
+    }
+    return make_uint4(umma_pack_h2(v[0], v[1]), umma_pack_h2(v[2], v[3]), umma_pack_h2(v[4], v[5]), umma_pack_h2(v[6], v[7]));
+}
+
+struct UmmaParams {
+    const uint8_t* w;
+    long long row_bytes;
+    int type, n_rows, K;
+    const float* x;      // [T][ldx]
+    int ldx, T;
+    float* y;            // [T][ldy]: Y[t][j]
+    int ldy;
+    const float* bias;   // optional [n_rows]
+    int accumulate;      // Y += ... (residual connection) instead of Y = ...
+    int* err;            // watchdog word (set to 5 if the MMA completion never arrives)
+};
+
+template <int TN>
+__global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams p) {
+    extern __shared__ __align__(1024) uint8_t umma_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_tmem;
+    uint8_t* base = umma_smem + ((1024u - (umma_smem_u32(umma_smem) & 1023u)) & 1023u);   // the swizzle pattern is on absolute address bits
+    uint8_t* sA = base;                       // [128 weight rows][128 B]
+    uint8_t* sB = base + kUmmaM * 128;        // [TN tokens][128 B]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row0 = blockIdx.x * kUmmaM, tok0 = blockIdx.y * TN;
+    const uint32_t bar = umma_smem_u32(&s_bar);
+    constexpr int kCols = TN < 32 ? 32 : TN;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma_smem_u32(&s_tmem)), "n"(kCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc(kUmmaM, TN);
+    const uint8_t* wrow = p.w + (long long)min(row0 + tid, p.n_rows - 1) * p.row_bytes;
+    uint32_t phase = 0;
+    bool alive = true;
+    for (int k0 = 0; k0 < p.K; k0 += kUmmaK) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
+        for (int i = tid; i < TN * 8; i += 128) {
+            const int r = i >> 3, c = i & 7, tk = tok0 + r;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (tk < p.T) {
+                const float* xp = p.x + (long long)tk * p.ldx + k0 + 8 * c;
+                const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
+                v = make_uint4(umma_pack_h2(a.x, a.y), umma_pack_h2(a.z, a.w), umma_pack_h2(b.x, b.y), umma_pack_h2(b.z, b.w));
+            }
+            *reinterpret_cast<uint4*>(sB + umma_sw128(r, c)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc(umma_smem_u32(sA)), db = umma_desc(umma_smem_u32(sB));
+#pragma unroll
+            for (int kk = 0; kk < kUmmaK / 16; kk++)   // 16 fp16 = 32 bytes along the swizzled row: start address + 2
+                umma_f16(tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (k0 > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar);
+        }
+        if (alive && !umma_mbar_wait(bar, phase)) {
+            alive = false;
+            if (p.err) atomicExch(p.err, 5);
+        }
+        phase ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = weight rows, 32 token columns per load ----
+    const int j = row0 + tid;
+    const float bj = (p.bias && j < p.n_rows) ? p.bias[j] : 0.0f;
+#pragma unroll 1
+    for (int n0 = 0; n0 < TN; n0 += 32) {
+        if (tok0 + n0 >= p.T) break;   // CTA-uniform
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int n = 0; n < 32; n++) {
+            const int tk = tok0 + n0 + n;
+            if (tk < p.T && j < p.n_rows) {
+                float* yp = p.y + (long long)tk * p.ldy + j;
+                float val = __uint_as_float(v[n]) + bj;
+                if (p.accumulate) val += *yp;
+                *yp = val;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCols) : "memory");
+}
+
+inline bool umma_type_ok(int type) { return type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q8_0; }
+// Is the launch eligible?  K a multiple of 256 (K-quants) / 64, rows at least 2-byte aligned (4 for Q4_K / Q5_K headers),
+// activations 16-byte aligned rows.
+inline bool umma_eligible(const UmmaParams& p) {
+    if (!umma_type_ok(p.type) || p.K <= 0 || p.K % 64 || p.K % type_block_elems(p.type) || p.T <= 0 || p.n_rows <= 0) return false;
+    const bool k45 = p.type == T_Q4_K || p.type == T_Q5_K;
+    if (((uintptr_t)p.w | (uintptr_t)p.row_bytes) & (k45 ? 7 : 1)) return false;
+    if (((uintptr_t)p.x & 15) || (p.ldx & 3)) return false;
+    return true;
+}
+template <int TN>
+inline cudaError_t umma_launch_tn(const UmmaParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(kUmmaM + TN) * 128 + 1024;
+    static bool once = false;   // per instantiation
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(dequant_gemm_umma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
+    dim3 grid((p.n_rows + kUmmaM - 1) / kUmmaM, (p.T + TN - 1) / TN);
+    dequant_gemm_umma_kernel<TN><<<grid, 128, smem, st>>>(p);
+    return cudaGetLastError();
+}
+inline cudaError_t umma_launch(const UmmaParams& p, cudaStream_t st) {
+    if (p.T <= 32) return umma_launch_tn<32>(p, st);
+    if (p.T <= 64) return umma_launch_tn<64>(p, st);
+    if (p.T <= 128) return umma_launch_tn<128>(p, st);
+    return umma_launch_tn<256>(p, st);
+}
+
+}  // namespace b200

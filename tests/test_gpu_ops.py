@@ -189,3 +189,19 @@ def test_error_mapping(be, b200):
         be.vec_mat_q(np.ones(256, np.float32), np.zeros(100, np.uint8), 12, 256, 1)
     with pytest.raises(b200.InvalidArgument):
         be.rope(np.ones((2, 4), np.float32), np.ones((2, 4), np.float32), 0, 1e4, 1.0, False)
+
+
+# ---- tcgen05 / TMEM dequant-GEMM (csrc/gemm_umma.cuh): T rows of vec_mat_q at once, fp16 operands, f32 accumulation ----
+# tolerance: 2e-3 of the typical output magnitude (fp16 rounding of both operands, ~3e-4 measured), stated here because
+# this path trades the exact f32 arithmetic of the GEMV for the tensor cores (prefill / batched decode).
+@pytest.mark.parametrize("t", [12, 13, 14, 8])
+@pytest.mark.parametrize("rows,k,n", [(1, 256, 5), (32, 512, 130), (33, 1024, 128), (70, 4096, 257), (300, 2048, 64)])
+def test_mat_mat_q_tensor_core_gemm(be, oracle, t, rows, k, n):
+    rng = np.random.default_rng(k * 17 + n + t + rows)
+    w = oracle.quantize(t, rng.normal(0, 0.05, k * n).astype(np.float32))
+    x = rng.standard_normal((rows, k)).astype(np.float32)
+    got = be.mat_mat_q(x, w, t, k, n)
+    assert got.shape == (rows, n)
+    for r in sorted({0, rows // 2, rows - 1}):
+        want = oracle.vec_mat_q(t, w, x[r], n)
+        assert gemv_err(got[r], want, k, 0.05, x[r]) < 2e-3, f"row {r}"
