@@ -446,10 +446,14 @@ class GpuOnlyInference:
         _check(lib().b200_prefill_token(self._h, seq, int(token_id)))
 
     def forward_batch(self, token_ids, seq=0):
+        """GpuOnlyInference::forward_batch (src/backend/cuda/gpu_only.rs:776-790): the whole prompt, logits of its last
+        token.  Prompts of >= 32 tokens of an eligible dense model run through the tcgen05 dequant-GEMM (fp16 operands)."""
         toks = np.ascontiguousarray(token_ids, dtype=np.uint32)
         logits = np.empty(self.vocab, dtype=np.float32)
         _check(lib().b200_prefill(self._h, seq, toks.ctypes.data_as(C.POINTER(C.c_uint32)), toks.size, _fp(logits)))
         return logits
+
+    prefill = forward_batch
 
     def reset(self, seq=0):
         _check(lib().b200_reset(self._h, seq))

@@ -28,6 +28,7 @@
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
+#include "prefill.cuh"
 #include "quant.cuh"
 #include "stream.cuh"
 
@@ -152,6 +153,12 @@ struct b200_ctx {
     size_t out_scratch_elems = 0;
     // pinned host staging
     float* h_logits = nullptr;
+    // GEMM prefill (gemm_umma.cuh + prefill.cuh): activation rows of one chunk of prompt tokens
+    bool use_prefill_gemm = true;
+    int prefill_gemm_min = 32;
+    float* pf_buf = nullptr;
+    int* pf_tok = nullptr;
+    uint64_t prefill_gemm_tokens = 0;
     int* h_err = nullptr;   // pinned copy of the first watchdog word, fetched with every synchronising call
     int* h_token = nullptr;
     std::vector<Slot> slots;
@@ -239,6 +246,8 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
     c->use_mega = env_int("B200_MEGA", 1) != 0;
     c->use_stream = env_int("B200_STREAM", 1) != 0;
+    c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
+    c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -554,6 +563,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->mega_cand_idx);
     cudaFree(c->mega_attn_part);
     cudaFree(c->d_tmaps);
+    cudaFree(c->pf_buf);
+    cudaFree(c->pf_tok);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
@@ -1081,6 +1092,107 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
     return B200_OK;
 }
 
+
+// ------------------------------------------------------------------ GEMM prefill
+// A prompt of n >= prefill_gemm_min tokens is processed kPrefillChunk tokens at a time: every weight matrix is one
+// tcgen05 dequant-GEMM per chunk (gemm_umma.cuh) instead of one GEMV per token (what the reference does:
+// src/model/llama.rs:327-345), RoPE / KV write / causal attention / SwiGLU run on T rows (prefill.cuh).  fp16 tensor-core
+// operands: logits agree with the exact path to ~1e-3 relative, so the token-by-token entry points stay exact and this
+// path is taken only by the batch entry point b200_prefill (B200_PREFILL_GEMM=0 turns it off).
+constexpr int kPrefillChunk = 256;
+
+static bool prefill_gemm_ok(const b200_ctx* c) {
+    const b200_model_desc& d = c->d;
+    if (!c->use_prefill_gemm || c->par.world_size > 1 || d.n_experts > 0 || c->use_taps) return false;
+    if (d.head_dim != 64 && d.head_dim != 128) return false;
+    auto ok = [&](const DevTensor& w, int K) {
+        UmmaParams p{};
+        p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K; p.T = 1;
+        p.x = c->xa; p.ldx = K;   // buffers of the pipeline are 256-byte aligned, leading dimensions multiples of 4
+        return w.present() && (int)w.ne[0] == K && umma_eligible(p);
+    };
+    const int H = d.hidden, A = d.n_heads * d.head_dim, I = (int)d.ffn;
+    if (H % 4 || A % 4 || I % 4) return false;
+    for (const Layer& L : c->layers)
+        if (!ok(L.wq, H) || !ok(L.wk, H) || !ok(L.wv, H) || !ok(L.wo, A) || !ok(L.gate, H) || !ok(L.up, H) || !ok(L.down, I)) return false;
+    return true;
+}
+
+static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, bool want_logits) {
+    const b200_model_desc& d = c->d;
+    Slot& sl = c->slots[seq];
+    const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, A = nh * hd, I = (int)d.ffn;
+    const int QKV = (nh + 2 * nkv) * hd;
+    const size_t per_tok = (size_t)2 * H + QKV + A + 2 * (size_t)I;
+    if (!c->pf_buf) {
+        CU_ALLOC(cudaMalloc((void**)&c->pf_buf, per_tok * kPrefillChunk * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->pf_tok, kPrefillChunk * sizeof(int)));
+    }
+    float* X = c->pf_buf;                               // [T][H] residual stream
+    float* XN = X + (size_t)kPrefillChunk * H;          // [T][H] normed
+    float* Q = XN + (size_t)kPrefillChunk * H;          // [T][QKV]
+    float* AT = Q + (size_t)kPrefillChunk * QKV;        // [T][A]
+    float* G = AT + (size_t)kPrefillChunk * A;          // [T][I] gate, then silu(gate) * up
+    float* U = G + (size_t)kPrefillChunk * I;           // [T][I]
+    const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
+    cudaStream_t st = c->stream;
+    auto gemm = [&](const DevTensor& w, int K, const float* x, int ldx, int T, float* y, int ldy, const DevTensor* bias, int acc) -> cudaError_t {
+        UmmaParams p{};
+        p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K;
+        p.x = x; p.ldx = ldx; p.T = T; p.y = y; p.ldy = ldy;
+        p.bias = (bias && bias->present()) ? bias->f32() : nullptr;
+        p.accumulate = acc; p.err = c->mma_err;
+        c->launches++;
+        return umma_launch(p, st);
+    };
+    int last_T = 0;
+    for (int done = 0; done < n; done += kPrefillChunk) {
+        const int T = std::min(kPrefillChunk, n - done);
+        const int pos0 = (int)sl.host_pos + done;
+        last_T = T;
+        CU(cudaMemcpyAsync(c->pf_tok, tokens + done, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
+        prefill_embed_kernel<<<T, 256, 0, st>>>(c->token_embd.type, c->token_embd.d, c->token_embd.row_bytes, H, c->pf_tok, d.vocab, X);
+        for (int l = 0; l < d.n_layers; l++) {
+            Layer& L = c->layers[l];
+            float* kc = sl.kv + (size_t)l * kv_layer;
+            float* vc = kc + kv_layer / 2;
+            rms_norm_rows_kernel<<<T, 256, 0, st>>>(X, L.attn_norm.f32(), d.norm_eps, XN, H);
+            CU(gemm(L.wq, H, XN, H, T, Q, QKV, &L.bq, 0));
+            CU(gemm(L.wk, H, XN, H, T, Q + A, QKV, &L.bk, 0));
+            CU(gemm(L.wv, H, XN, H, T, Q + A + nkv * hd, QKV, &L.bv, 0));
+            PrefillRopeParams rp{};
+            rp.qkv = Q; rp.ld = QKV; rp.k_cache = kc; rp.v_cache = vc; rp.freq = c->rope_freq; rp.pos0 = pos0;
+            rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox; rp.rope_scale = d.rope_scale;
+            prefill_rope_kv_kernel<<<T, 256, 0, st>>>(rp);
+            PrefillAttnParams ap{};
+            ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = AT; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
+            ap.n_heads = nh; ap.n_kv = nkv; ap.max_seq = d.max_seq_len; ap.scale = 1.0f / sqrtf((float)hd);
+            const int ablocks = (int)(((long long)T * nh * 32 + 255) / 256);
+            if (hd == 128) prefill_attn_kernel<128><<<ablocks, 256, 0, st>>>(ap);
+            else prefill_attn_kernel<64><<<ablocks, 256, 0, st>>>(ap);
+            CU(gemm(L.wo, A, AT, A, T, X, H, nullptr, 1));                       // X += Wo attn
+            rms_norm_rows_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XN, H);
+            CU(gemm(L.gate, H, XN, H, T, G, I, nullptr, 0));
+            CU(gemm(L.up, H, XN, H, T, U, I, nullptr, 0));
+            prefill_swiglu_kernel<<<std::min(148 * 8, (int)(((long long)T * I + 255) / 256)), 256, 0, st>>>(G, U, (long long)T * I);
+            CU(gemm(L.down, I, G, I, T, X, H, nullptr, 1));                      // X += Wd act
+            c->launches += 5;
+        }
+        c->launches += 1;
+        CU(cudaGetLastError());
+    }
+    prefill_advance_kernel<<<1, 32, 0, st>>>(sl.d_state, n);
+    if (want_logits) {   // final RMSNorm + vocab head of the last token, through the exact GEMV path
+        CU(cudaMemcpyAsync(c->xa, X + (size_t)(last_T - 1) * H, (size_t)H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        GemvParams p{};
+        fill_seg(p.seg[0], c->output.present() ? c->output : c->token_embd, c->logits, nullptr, 0);
+        p.n_seg = 1; p.K = H; p.x = c->xa; p.norm_w = c->output_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
+        CU(launch_gemv(c, p));
+    }
+    c->prefill_gemm_tokens += (uint64_t)n;
+    return B200_OK;
+}
+
 // Run one token: graph replay when enabled (captured lazily per slot and mode), else eager.
 static int run_token(b200_ctx* c, int slot_i, Mode mode) {
     if (c->mega_ok)
@@ -1196,6 +1308,21 @@ extern "C" int b200_prefill(b200_ctx* c, int seq, const uint32_t* tokens, int n,
     int rc;
     if ((rc = check_slot(c, seq, "b200_prefill"))) return rc;
     if (!tokens || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: no tokens");
+    if (n >= c->prefill_gemm_min && prefill_gemm_ok(c)) {
+        for (int i = 0; i < n; i++)
+            if (tokens[i] >= (uint32_t)c->d.vocab) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: token id exceeds vocab size");
+        Slot& sl = c->slots[seq];
+        if (sl.host_pos + (uint64_t)n > (uint64_t)c->d.max_seq_len) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: context length exceeded");
+        CU(cudaSetDevice(c->par.device));
+        if ((rc = prefill_gemm(c, seq, tokens, n, logits_out != nullptr))) return rc;
+        if (logits_out) CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
+        WATCHDOG_FETCH(c);
+        CU(cudaStreamSynchronize(c->stream));
+        if ((rc = watchdog_check(c, "b200_prefill"))) return rc;
+        if (logits_out) memcpy(logits_out, c->h_logits, (size_t)c->vocab_l * 4);
+        sl.host_pos += (uint64_t)n;
+        return B200_OK;
+    }
     for (int i = 0; i < n; i++) {
         if (i == n - 1 && logits_out) return b200_forward(c, seq, tokens[i], logits_out);
         if ((rc = b200_prefill_token(c, seq, tokens[i]))) return rc;

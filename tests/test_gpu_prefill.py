@@ -1,0 +1,63 @@
+"""GEMM prefill (csrc/gemm_umma.cuh tcgen05/TMEM dequant-GEMM + csrc/prefill.cuh) through the batch entry point
+b200_prefill, against the oracle's token-by-token LlamaModel::forward (src/model/llama.rs:275-362).
+
+Tolerance: this path rounds both GEMM operands to fp16 (f32 accumulation in TMEM), so it is held to 3e-3 relative
+(max|a-b| / max|b|) on the logits -- looser than the 1e-3 of the exact paths, which the token-by-token entry points
+(prefill_token / forward) keep.  The KV cache it leaves must let the exact decode path continue within the same bound."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from synth import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-3
+
+synth.TINY["qwen-kq-tiny"] = dict(arch="qwen2", hidden=512, n_layers=2, n_heads=8, n_kv_heads=2, head_dim=64, ffn=1024,
+                                  vocab=600, norm_eps=1e-6, rope_base=1e6, rope_neox=1, bias=True, tied=True)
+
+
+@pytest.mark.parametrize("preset,mix,n", [("llama-tiny", "Q4_K_M", 48), ("llama-tiny", "Q6_K", 33), ("llama-stream-tiny", "Q4_K_M", 300),
+                                          ("tinyllama-tiny", "Q8_0", 64), ("qwen-kq-tiny", "Q5_K_M", 40)])
+def test_gemm_prefill_logits_and_kv_cache(b200, oracle, preset, mix, n):
+    arch, desc, tensors = synth.synth_model(preset, mix, 384)
+    gpu = b200.GpuOnlyInference(desc, tensors)
+    ref = oracle.OracleModel(desc, tensors)
+    prompt = synth.prompt_tokens(n, desc["vocab"])
+    l0 = gpu.stats()["kernel_launches"]
+    got = gpu.prefill(prompt)
+    launches = gpu.stats()["kernel_launches"] - l0
+    want = ref.forward(prompt)
+    chunks = (n + 255) // 256
+    assert launches <= chunks * (13 * desc["n_layers"] + 1) + 2, "one launch sequence per 256-token chunk, not per token"
+    assert gpu.position() == n == ref.position()
+    assert rel_err(got, want) < TOL
+    # the exact decode path continues on the cache the GEMM prefill wrote
+    tok = oracle.argmax_last(want)
+    for _ in range(4):
+        want = ref.forward([tok])
+        got = gpu.forward(tok)
+        assert rel_err(got, want) < TOL
+        tok = oracle.argmax_last(want)
+    gpu.close()
+
+
+def test_short_prompts_and_disabled_gemm_stay_exact(b200, oracle):
+    arch, desc, tensors = synth.synth_model("llama-tiny", "Q4_K_M", 96)
+    ref = oracle.OracleModel(desc, tensors)
+    prompt = synth.prompt_tokens(40, desc["vocab"])
+    want = ref.forward(prompt)
+    os.environ["B200_PREFILL_GEMM"] = "0"
+    try:
+        gpu = b200.GpuOnlyInference(desc, tensors)
+    finally:
+        os.environ.pop("B200_PREFILL_GEMM", None)
+    assert rel_err(gpu.prefill(prompt), want) < 1e-4      # token by token, exact arithmetic
+    gpu.close()
+    gpu = b200.GpuOnlyInference(desc, tensors)
+    ref2 = oracle.OracleModel(desc, tensors)
+    short = prompt[:8]                                    # below the GEMM threshold (32 tokens)
+    assert rel_err(gpu.prefill(short), ref2.forward(short)) < 1e-4
+    gpu.close()
