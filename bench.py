@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=4, help="layers in the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefill-len", type=int, default=2048, help="tokens of the GEMM-prefill measurement (0 = skip)")
     ap.add_argument("--seed", type=int, default=1236)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -302,6 +303,32 @@ def main():
                     "whole_token_frac": token_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    # ---- prefill: the whole prompt through the batch entry point (tcgen05 dequant-GEMM, csrc/gemm_umma.cuh) ----
+    prefill = None
+    if args.prefill_len > 0 and args.prefill_len <= args.ctx:
+        try:
+            ptoks = [(i * 7919 + 1) % desc["vocab"] for i in range(args.prefill_len)]
+            gpu.reset()
+            gpu.prefill(ptoks[:64])                      # warm-up (module load, attributes)
+            gpu.reset()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            gpu.prefill(ptoks)
+            torch.cuda.synchronize()
+            pf_s = time.perf_counter() - t2
+            from llama_gguf_b200.presets import tensor_plan
+            macs = sum(int(np.prod(ne)) for name, tt, ne in tensor_plan(preset, args.mix)
+                       if name.startswith("blk.") and name.endswith(".weight") and "norm" not in name)
+            tfl = 2.0 * macs * args.prefill_len / pf_s / 1e12
+            prefill = {"tokens": args.prefill_len, "seconds": pf_s, "tok_per_s": args.prefill_len / pf_s,
+                       "gemm_tflops": tfl, "tensor_peak_tflops": peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")),
+                       "tensor_frac": tfl / peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")),
+                       "path": "b200_prefill: 256-token chunks, tcgen05.mma kind::f16 dequant-GEMM + batched RoPE/attention/SwiGLU, "
+                               "host tokens in, logits of the last token out (wall clock)",
+                       "token_by_token_tok_per_s": 1000.0 / ms_per_step}
+        except Exception as e:
+            prefill = {"tokens": args.prefill_len, "error": str(e)}
+
     # ---- CPU baseline (bounded sample, rank 0) ----
     cpu = None
     if not args.no_cpu_baseline:
@@ -317,7 +344,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": desc["vocab"] * 4},
-           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "prefill": prefill,
            "weight_bytes_per_token": wbytes, "kv_bytes_per_token_at_mid": kvpp * kv_len_mid,
            "greedy_tokens_head": [int(t) for t in toks_head]}
     print(json.dumps(out))

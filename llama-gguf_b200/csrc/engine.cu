@@ -1094,17 +1094,19 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
 
 
 // ------------------------------------------------------------------ GEMM prefill
-// A prompt of n >= prefill_gemm_min tokens is processed kPrefillChunk tokens at a time: every weight matrix is one
+// A prompt of n >= prefill_gemm_min tokens is processed prefill_chunk() tokens at a time: every weight matrix is one
 // tcgen05 dequant-GEMM per chunk (gemm_umma.cuh) instead of one GEMV per token (what the reference does:
 // src/model/llama.rs:327-345), RoPE / KV write / causal attention / SwiGLU run on T rows (prefill.cuh).  fp16 tensor-core
 // operands: logits agree with the exact path to ~1e-3 relative, so the token-by-token entry points stay exact and this
 // path is taken only by the batch entry point b200_prefill (B200_PREFILL_GEMM=0 turns it off).
-constexpr int kPrefillChunk = 256;
+// tokens per pass: large enough that the GEMM grids ((rows / 128) x (T / 256) CTAs) fill the 148 SMs even for the
+// 1024-row k / v projections; 47 K floats of activations per token (Llama-3-8B) = 386 MB at 2048
+static int prefill_chunk() { static int v = std::max(32, std::min(4096, env_int("B200_PREFILL_CHUNK", 2048))); return v; }
 
 static bool prefill_gemm_ok(const b200_ctx* c) {
     const b200_model_desc& d = c->d;
     if (!c->use_prefill_gemm || c->par.world_size > 1 || d.n_experts > 0 || c->use_taps) return false;
-    if (d.head_dim != 64 && d.head_dim != 128) return false;
+    if ((d.head_dim != 64 && d.head_dim != 128) || d.n_heads % d.n_kv_heads || d.n_heads / d.n_kv_heads > 8) return false;
     auto ok = [&](const DevTensor& w, int K) {
         UmmaParams p{};
         p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K; p.T = 1;
@@ -1124,16 +1126,17 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, A = nh * hd, I = (int)d.ffn;
     const int QKV = (nh + 2 * nkv) * hd;
     const size_t per_tok = (size_t)2 * H + QKV + A + 2 * (size_t)I;
+    const int cap = std::min(prefill_chunk(), d.max_seq_len);
     if (!c->pf_buf) {
-        CU_ALLOC(cudaMalloc((void**)&c->pf_buf, per_tok * kPrefillChunk * sizeof(float)));
-        CU_ALLOC(cudaMalloc((void**)&c->pf_tok, kPrefillChunk * sizeof(int)));
+        CU_ALLOC(cudaMalloc((void**)&c->pf_buf, per_tok * cap * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->pf_tok, cap * sizeof(int)));
     }
     float* X = c->pf_buf;                               // [T][H] residual stream
-    float* XN = X + (size_t)kPrefillChunk * H;          // [T][H] normed
-    float* Q = XN + (size_t)kPrefillChunk * H;          // [T][QKV]
-    float* AT = Q + (size_t)kPrefillChunk * QKV;        // [T][A]
-    float* G = AT + (size_t)kPrefillChunk * A;          // [T][I] gate, then silu(gate) * up
-    float* U = G + (size_t)kPrefillChunk * I;           // [T][I]
+    float* XN = X + (size_t)cap * H;          // [T][H] normed
+    float* Q = XN + (size_t)cap * H;          // [T][QKV]
+    float* AT = Q + (size_t)cap * QKV;        // [T][A]
+    float* G = AT + (size_t)cap * A;          // [T][I] gate, then silu(gate) * up
+    float* U = G + (size_t)cap * I;           // [T][I]
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
     cudaStream_t st = c->stream;
     auto gemm = [&](const DevTensor& w, int K, const float* x, int ldx, int T, float* y, int ldy, const DevTensor* bias, int acc) -> cudaError_t {
@@ -1146,8 +1149,8 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         return umma_launch(p, st);
     };
     int last_T = 0;
-    for (int done = 0; done < n; done += kPrefillChunk) {
-        const int T = std::min(kPrefillChunk, n - done);
+    for (int done = 0; done < n; done += cap) {
+        const int T = std::min(cap, n - done);
         const int pos0 = (int)sl.host_pos + done;
         last_T = T;
         CU(cudaMemcpyAsync(c->pf_tok, tokens + done, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1167,9 +1170,15 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             PrefillAttnParams ap{};
             ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = AT; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
             ap.n_heads = nh; ap.n_kv = nkv; ap.max_seq = d.max_seq_len; ap.scale = 1.0f / sqrtf((float)hd);
-            const int ablocks = (int)(((long long)T * nh * 32 + 255) / 256);
-            if (hd == 128) prefill_attn_kernel<128><<<ablocks, 256, 0, st>>>(ap);
-            else prefill_attn_kernel<64><<<ablocks, 256, 0, st>>>(ap);
+            const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
+            const int Gq = nh / nkv;
+            if (hd == 128) {
+                if (Gq <= 4) prefill_attn_kernel<128, 4><<<ablocks, 128, 0, st>>>(ap);
+                else prefill_attn_kernel<128, 8><<<ablocks, 128, 0, st>>>(ap);
+            } else {
+                if (Gq <= 4) prefill_attn_kernel<64, 4><<<ablocks, 128, 0, st>>>(ap);
+                else prefill_attn_kernel<64, 8><<<ablocks, 128, 0, st>>>(ap);
+            }
             CU(gemm(L.wo, A, AT, A, T, X, H, nullptr, 1));                       // X += Wo attn
             rms_norm_rows_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XN, H);
             CU(gemm(L.gate, H, XN, H, T, G, I, nullptr, 0));

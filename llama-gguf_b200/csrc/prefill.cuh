@@ -78,55 +78,99 @@ struct PrefillAttnParams {
     int pos0, T, n_heads, n_kv, max_seq;
     float scale;
 };
-// one warp per (token, query head): online softmax over cache positions 0 .. pos0 + t (causal), two positions per step
-template <int HD>
-__global__ void __launch_bounds__(256) prefill_attn_kernel(const PrefillAttnParams p) {
-    constexpr int VEC = HD / 32;
+// One warp per (token, kv head): the G query heads of the group share every K / V row read (GQA), four cache positions per
+// step (16 independent dot products and reductions in flight), block-wise online softmax as in attn_decode_item.
+// Causal: token t attends cache positions 0 .. pos0 + t.
+template <int HD, int GMAX>
+__global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnParams p) {
+    constexpr int VEC = HD / 32, UB = 4;
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= (long long)p.T * p.n_heads) return;
-    const int t = (int)(wid / p.n_heads), h = (int)(wid - (long long)t * p.n_heads);
-    const int kh = h / (p.n_heads / p.n_kv);
+    if (wid >= (long long)p.T * p.n_kv) return;
+    const int t = (int)(wid / p.n_kv), kh = (int)(wid - (long long)t * p.n_kv);
+    const int G = p.n_heads / p.n_kv;
     const int kv_len = p.pos0 + t + 1;
-    float q[VEC], acc[VEC];
-    const float* qp = p.qkv + (size_t)t * p.ld + (size_t)h * HD + lane * VEC;
+    float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) { q[v] = qp[v]; acc[v] = 0.0f; }
-    const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
-    const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
-    float m = -INFINITY, l = 0.0f;
-    for (int pos = 0; pos < kv_len; pos += 2) {
-        const bool two = pos + 1 < kv_len;
-        float k0[VEC], k1[VEC], v0[VEC], v1[VEC];
+    for (int g = 0; g < GMAX; g++) {
+        m[g] = -INFINITY;
+        l[g] = 0.0f;
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
-            k0[v] = kb[(size_t)pos * HD + v];
-            v0[v] = vb[(size_t)pos * HD + v];
-            k1[v] = two ? kb[(size_t)(pos + 1) * HD + v] : 0.0f;
-            v1[v] = two ? vb[(size_t)(pos + 1) * HD + v] : 0.0f;
+            acc[g][v] = 0.0f;
+            q[g][v] = g < G ? p.qkv[(size_t)t * p.ld + (size_t)(kh * G + g) * HD + lane * VEC + v] : 0.0f;
         }
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-        for (int v = 0; v < VEC; v++) { s0 = fmaf(q[v], k0[v], s0); s1 = fmaf(q[v], k1[v], s1); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        s0 *= p.scale;
-        s1 = two ? s1 * p.scale : -INFINITY;
-        const float mn = fmaxf(m, fmaxf(s0, s1));
-        const float corr = (m == -INFINITY) ? 0.0f : expf(m - mn);
-        const float w0 = expf(s0 - mn), w1 = two ? expf(s1 - mn) : 0.0f;
-        l = l * corr + w0 + w1;
-#pragma unroll
-        for (int v = 0; v < VEC; v++) acc[v] = fmaf(w1, v1[v], fmaf(w0, v0[v], acc[v] * corr));
-        m = mn;
     }
-    float* op = p.out + (size_t)t * p.ldo + (size_t)h * HD + lane * VEC;
-    const float inv = 1.0f / l;
+    const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+    const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+    for (int pos = 0; pos < kv_len; pos += UB) {
+        float kr[UB][VEC], vr[UB][VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) op[v] = acc[v] * inv;
+        for (int u = 0; u < UB; u++) {
+            const int pc = min(pos + u, kv_len - 1);   // clamped: stays in range, masked below
+            if constexpr (VEC == 4) {
+                const float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const float4*>(vb + (size_t)pc * HD);
+                kr[u][0] = a.x; kr[u][1] = a.y; kr[u][2] = a.z; kr[u][3] = a.w;
+                vr[u][0] = b.x; vr[u][1] = b.y; vr[u][2] = b.z; vr[u][3] = b.w;
+            } else {
+                const float2 a = *reinterpret_cast<const float2*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const float2*>(vb + (size_t)pc * HD);
+                kr[u][0] = a.x; kr[u][1] = a.y;
+                vr[u][0] = b.x; vr[u][1] = b.y;
+            }
+        }
+        float s[UB][GMAX];
+#pragma unroll
+        for (int u = 0; u < UB; u++)
+#pragma unroll
+            for (int g = 0; g < GMAX; g++) {
+                float d = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) d = fmaf(q[g][v], kr[u][v], d);
+                s[u][g] = d;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+#pragma unroll
+                for (int g = 0; g < GMAX; g++) s[u][g] += __shfl_xor_sync(0xffffffffu, s[u][g], o);
+#pragma unroll
+        for (int g = 0; g < GMAX; g++) {
+            if (g < G) {
+                float mb = -INFINITY;
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    s[u][g] = (pos + u < kv_len) ? s[u][g] * p.scale : -INFINITY;
+                    mb = fmaxf(mb, s[u][g]);
+                }
+                const float mn = fmaxf(m[g], mb);
+                const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
+                float w[UB], ws = 0.0f;
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    w[u] = (s[u][g] == -INFINITY) ? 0.0f : expf(s[u][g] - mn);
+                    ws += w[u];
+                }
+                l[g] = l[g] * corr + ws;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    float a = acc[g][v] * corr;
+#pragma unroll
+                    for (int u = 0; u < UB; u++) a = fmaf(w[u], vr[u][v], a);
+                    acc[g][v] = a;
+                }
+                m[g] = mn;
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < GMAX; g++) {
+        if (g < G) {
+            const float inv = 1.0f / l[g];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) p.out[(size_t)t * p.ldo + (size_t)(kh * G + g) * HD + lane * VEC + v] = acc[g][v] * inv;
+        }
+    }
 }
 
 // g[i] = silu(g[i]) * u[i]  (silu rounded to f32 first, then the product: simd.rs:598-649)

@@ -10,6 +10,6 @@ python - <<'PY'
 import json
 try:
     d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1])
-    print("value %.1f tok/s  %.3f ms  e2e %.1f  frac %.3f  tokens %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d.get("greedy_tokens_head")))
+    print("prefill", d.get("prefill")); print("value %.1f tok/s  %.3f ms  e2e %.1f  frac %.3f  tokens %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d.get("greedy_tokens_head")))
 except Exception as e: print("no bench json", e)
 PY

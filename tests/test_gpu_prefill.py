@@ -19,10 +19,10 @@ synth.TINY["qwen-kq-tiny"] = dict(arch="qwen2", hidden=512, n_layers=2, n_heads=
                                   vocab=600, norm_eps=1e-6, rope_base=1e6, rope_neox=1, bias=True, tied=True)
 
 
-@pytest.mark.parametrize("preset,mix,n", [("llama-tiny", "Q4_K_M", 48), ("llama-tiny", "Q6_K", 33), ("llama-stream-tiny", "Q4_K_M", 300),
+@pytest.mark.parametrize("preset,mix,n", [("llama-tiny", "Q4_K_M", 48), ("llama-tiny", "Q6_K", 33), ("llama-stream-tiny", "Q4_K_M", 300), ("llama-tiny", "Q4_K_M", 2100),
                                           ("tinyllama-tiny", "Q8_0", 64), ("qwen-kq-tiny", "Q5_K_M", 40)])
 def test_gemm_prefill_logits_and_kv_cache(b200, oracle, preset, mix, n):
-    arch, desc, tensors = synth.synth_model(preset, mix, 384)
+    arch, desc, tensors = synth.synth_model(preset, mix, max(384, n + 8))
     gpu = b200.GpuOnlyInference(desc, tensors)
     ref = oracle.OracleModel(desc, tensors)
     prompt = synth.prompt_tokens(n, desc["vocab"])
@@ -30,8 +30,8 @@ def test_gemm_prefill_logits_and_kv_cache(b200, oracle, preset, mix, n):
     got = gpu.prefill(prompt)
     launches = gpu.stats()["kernel_launches"] - l0
     want = ref.forward(prompt)
-    chunks = (n + 255) // 256
-    assert launches <= chunks * (13 * desc["n_layers"] + 1) + 2, "one launch sequence per 256-token chunk, not per token"
+    chunks = (n + 2047) // 2048
+    assert launches <= chunks * (13 * desc["n_layers"] + 1) + 2, "one launch sequence per chunk of the prompt, not per token"
     assert gpu.position() == n == ref.position()
     assert rel_err(got, want) < TOL
     # the exact decode path continues on the cache the GEMM prefill wrote
