@@ -1110,11 +1110,11 @@ static bool prefill_gemm_ok(const b200_ctx* c) {
     auto ok = [&](const DevTensor& w, int K) {
         UmmaParams p{};
         p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K; p.T = 1;
-        p.x = c->xa; p.ldx = K;   // buffers of the pipeline are 256-byte aligned, leading dimensions multiples of 4
+        p.x = reinterpret_cast<const __half*>(c->xa); p.ldx = K;   // pipeline buffers are 256-byte aligned
         return w.present() && (int)w.ne[0] == K && umma_eligible(p);
     };
     const int H = d.hidden, A = d.n_heads * d.head_dim, I = (int)d.ffn;
-    if (H % 4 || A % 4 || I % 4) return false;
+    if (H % 8 || A % 8 || I % 8) return false;
     for (const Layer& L : c->layers)
         if (!ok(L.wq, H) || !ok(L.wk, H) || !ok(L.wv, H) || !ok(L.wo, A) || !ok(L.gate, H) || !ok(L.up, H) || !ok(L.down, I)) return false;
     return true;
@@ -1125,21 +1125,22 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     Slot& sl = c->slots[seq];
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, A = nh * hd, I = (int)d.ffn;
     const int QKV = (nh + 2 * nkv) * hd;
-    const size_t per_tok = (size_t)2 * H + QKV + A + 2 * (size_t)I;
+    const size_t per_tok = (size_t)H + QKV + 2 * (size_t)I + ((size_t)H + A + I + 1) / 2;   // floats (the fp16 rows count half)
     const int cap = std::min(prefill_chunk(), d.max_seq_len);
     if (!c->pf_buf) {
         CU_ALLOC(cudaMalloc((void**)&c->pf_buf, per_tok * cap * sizeof(float)));
         CU_ALLOC(cudaMalloc((void**)&c->pf_tok, cap * sizeof(int)));
     }
-    float* X = c->pf_buf;                               // [T][H] residual stream
-    float* XN = X + (size_t)cap * H;          // [T][H] normed
-    float* Q = XN + (size_t)cap * H;          // [T][QKV]
-    float* AT = Q + (size_t)cap * QKV;        // [T][A]
-    float* G = AT + (size_t)cap * A;          // [T][I] gate, then silu(gate) * up
-    float* U = G + (size_t)cap * I;           // [T][I]
+    float* X = c->pf_buf;                               // [T][H] residual stream (f32)
+    float* Q = X + (size_t)cap * H;                     // [T][QKV] f32
+    float* G = Q + (size_t)cap * QKV;                   // [T][I] gate
+    float* U = G + (size_t)cap * I;                     // [T][I] up
+    __half* XNh = reinterpret_cast<__half*>(U + (size_t)cap * I);   // [T][H] normed rows, fp16 (GEMM input)
+    __half* ATh = XNh + (size_t)cap * H;                // [T][A] attention output, fp16
+    __half* Hh = ATh + (size_t)cap * A;                 // [T][I] silu(gate) * up, fp16
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
     cudaStream_t st = c->stream;
-    auto gemm = [&](const DevTensor& w, int K, const float* x, int ldx, int T, float* y, int ldy, const DevTensor* bias, int acc) -> cudaError_t {
+    auto gemm = [&](const DevTensor& w, int K, const __half* x, int ldx, int T, float* y, int ldy, const DevTensor* bias, int acc) -> cudaError_t {
         UmmaParams p{};
         p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K;
         p.x = x; p.ldx = ldx; p.T = T; p.y = y; p.ldy = ldy;
@@ -1159,16 +1160,16 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             Layer& L = c->layers[l];
             float* kc = sl.kv + (size_t)l * kv_layer;
             float* vc = kc + kv_layer / 2;
-            rms_norm_rows_kernel<<<T, 256, 0, st>>>(X, L.attn_norm.f32(), d.norm_eps, XN, H);
-            CU(gemm(L.wq, H, XN, H, T, Q, QKV, &L.bq, 0));
-            CU(gemm(L.wk, H, XN, H, T, Q + A, QKV, &L.bk, 0));
-            CU(gemm(L.wv, H, XN, H, T, Q + A + nkv * hd, QKV, &L.bv, 0));
+            prefill_rms_norm_kernel<<<T, 256, 0, st>>>(X, L.attn_norm.f32(), d.norm_eps, XNh, H);
+            CU(gemm(L.wq, H, XNh, H, T, Q, QKV, &L.bq, 0));
+            CU(gemm(L.wk, H, XNh, H, T, Q + A, QKV, &L.bk, 0));
+            CU(gemm(L.wv, H, XNh, H, T, Q + A + nkv * hd, QKV, &L.bv, 0));
             PrefillRopeParams rp{};
             rp.qkv = Q; rp.ld = QKV; rp.k_cache = kc; rp.v_cache = vc; rp.freq = c->rope_freq; rp.pos0 = pos0;
             rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox; rp.rope_scale = d.rope_scale;
             prefill_rope_kv_kernel<<<T, 256, 0, st>>>(rp);
             PrefillAttnParams ap{};
-            ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = AT; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
+            ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = ATh; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
             ap.n_heads = nh; ap.n_kv = nkv; ap.max_seq = d.max_seq_len; ap.scale = 1.0f / sqrtf((float)hd);
             const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
             const int Gq = nh / nkv;
@@ -1179,12 +1180,12 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
                 if (Gq <= 4) prefill_attn_kernel<64, 4><<<ablocks, 128, 0, st>>>(ap);
                 else prefill_attn_kernel<64, 8><<<ablocks, 128, 0, st>>>(ap);
             }
-            CU(gemm(L.wo, A, AT, A, T, X, H, nullptr, 1));                       // X += Wo attn
-            rms_norm_rows_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XN, H);
-            CU(gemm(L.gate, H, XN, H, T, G, I, nullptr, 0));
-            CU(gemm(L.up, H, XN, H, T, U, I, nullptr, 0));
-            prefill_swiglu_kernel<<<std::min(148 * 8, (int)(((long long)T * I + 255) / 256)), 256, 0, st>>>(G, U, (long long)T * I);
-            CU(gemm(L.down, I, G, I, T, X, H, nullptr, 1));                      // X += Wd act
+            CU(gemm(L.wo, A, ATh, A, T, X, H, nullptr, 1));                       // X += Wo attn
+            prefill_rms_norm_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XNh, H);
+            CU(gemm(L.gate, H, XNh, H, T, G, I, nullptr, 0));
+            CU(gemm(L.up, H, XNh, H, T, U, I, nullptr, 0));
+            prefill_swiglu_kernel<<<std::min(148 * 8, (int)(((long long)T * I + 255) / 256)), 256, 0, st>>>(G, U, Hh, (long long)T * I);
+            CU(gemm(L.down, I, Hh, I, T, X, H, nullptr, 1));                      // X += Wd act
             c->launches += 5;
         }
         c->launches += 1;
@@ -1710,13 +1711,14 @@ extern "C" int b200_op_mat_mat_q(const float* a, const void* w, uint32_t ggml_ty
     const int be = type_block_elems(t), bb = type_block_bytes(t);
     if (t_rows == 0 || k == 0 || n == 0 || k % be || k % 64) return fail(B200_ERR_SHAPE_MISMATCH, "mat_mat_q: k must be a non-zero multiple of the block size and of 64");
     const size_t row_bytes = k / be * bb, wbytes = row_bytes * n;
-    DevBuf da, dw, dout;
-    if (da.alloc(t_rows * k * 4) || dw.alloc(wbytes + 256) || dout.alloc(t_rows * n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "mat_mat_q");
+    DevBuf da, dh, dw, dout;
+    if (da.alloc(t_rows * k * 4) || dh.alloc(t_rows * k * 2) || dw.alloc(wbytes + 256) || dout.alloc(t_rows * n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "mat_mat_q");
     CU(cudaMemcpy(da.p, a, t_rows * k * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
+    umma_to_half_kernel<<<(int)std::min<size_t>((t_rows * k + 255) / 256, 148 * 8), 256>>>(da.as<float>(), dh.as<__half>(), (long long)(t_rows * k));
     UmmaParams p{};
     p.w = dw.as<uint8_t>(); p.row_bytes = (long long)row_bytes; p.type = t; p.n_rows = (int)n; p.K = (int)k;
-    p.x = da.as<float>(); p.ldx = (int)k; p.T = (int)t_rows; p.y = dout.as<float>(); p.ldy = (int)n;
+    p.x = dh.as<__half>(); p.ldx = (int)k; p.T = (int)t_rows; p.y = dout.as<float>(); p.ldy = (int)n;
     if (!umma_eligible(p)) return fail(B200_ERR_SHAPE_MISMATCH, "mat_mat_q: rows of this type / length are not aligned for the tensor-core path");
     CU(umma_launch(p, 0));
     if ((rc = op_finish("mat_mat_q"))) return rc;

@@ -11,7 +11,7 @@
 //   * thread r dequantises 64 elements of ITS weight row in registers with the reference arithmetic in f32
 //     (dequant.rs:205-356: d*sc*q - dmin*m, (d*sc)*q for Q6_K, q*d for Q8_0), rounds to fp16 and writes the row's eight
 //     16-byte chunks into the K-major SWIZZLE_128B shared-memory tile (chunk c of row r at chunk c ^ (r & 7));
-//   * the activations (f32 in HBM) are rounded to fp16 into a second tile the same way;
+//   * the activations (fp16 in HBM, rounded once by their producer) are copied into a second tile the same way;
 //   * fence.proxy.async, then ONE elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M = 128 weight rows,
 //     N = TN tokens, K = 16 each; SASS UTCHMMA) on the two shared-memory descriptors; the f32 accumulator lives in TMEM
 //     (TN columns x 128 lanes); tcgen05.commit -> mbarrier tells the CTA that the tiles may be overwritten;
@@ -127,11 +127,49 @@ __device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0,
     return make_uint4(umma_pack_h2(v[0], v[1]), umma_pack_h2(v[2], v[3]), umma_pack_h2(v[4], v[5]), umma_pack_h2(v[6], v[7]));
 }
 
+// Q4_K, 16-byte aligned rows: the 64 elements k0 .. k0 + 63 of a row are the low and high nibbles of 32 consecutive qs
+// bytes (one scale / min pair each): header and scales decoded once, two 16-byte loads, written as the row's 8 chunks.
+__device__ __forceinline__ void umma_deq64_q4k(const uint8_t* row, int k0, uint8_t* sA, int r) {
+    const uint8_t* blk = row + (long long)(k0 >> 8) * 144;
+    const int gp = (k0 & 255) >> 6;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(blk));   // d | dmin, scales[12]
+    const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
+    const uint8_t sc[12] = {(uint8_t)hdr.y, (uint8_t)(hdr.y >> 8), (uint8_t)(hdr.y >> 16), (uint8_t)(hdr.y >> 24),
+                            (uint8_t)hdr.z, (uint8_t)(hdr.z >> 8), (uint8_t)(hdr.z >> 16), (uint8_t)(hdr.z >> 24),
+                            (uint8_t)hdr.w, (uint8_t)(hdr.w >> 8), (uint8_t)(hdr.w >> 16), (uint8_t)(hdr.w >> 24)};
+    int s1, m1, s2, m2;
+    scale_min_k4(sc, 2 * gp, s1, m1);
+    scale_min_k4(sc, 2 * gp + 1, s2, m2);
+    const float d1 = __fmul_rn(d, (float)s1), mm1 = __fmul_rn(dmin, (float)m1), d2 = __fmul_rn(d, (float)s2), mm2 = __fmul_rn(dmin, (float)m2);
+    const uint4* q4 = reinterpret_cast<const uint4*>(blk + 16 + 32 * gp);
+    const uint4 qa = __ldg(q4), qb = __ldg(q4 + 1);
+    const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {   // chunk c: elements 8c..8c+7 (low nibbles), chunk 4 + c: elements 32 + 8c.. (high nibbles)
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t w = qw[2 * c + h];
+            lo[2 * h] = umma_pack_h2(__fsub_rn(__fmul_rn(d1, (float)(w & 15)), mm1), __fsub_rn(__fmul_rn(d1, (float)((w >> 8) & 15)), mm1));
+            lo[2 * h + 1] = umma_pack_h2(__fsub_rn(__fmul_rn(d1, (float)((w >> 16) & 15)), mm1), __fsub_rn(__fmul_rn(d1, (float)((w >> 24) & 15)), mm1));
+            hi[2 * h] = umma_pack_h2(__fsub_rn(__fmul_rn(d2, (float)((w >> 4) & 15)), mm2), __fsub_rn(__fmul_rn(d2, (float)((w >> 12) & 15)), mm2));
+            hi[2 * h + 1] = umma_pack_h2(__fsub_rn(__fmul_rn(d2, (float)((w >> 20) & 15)), mm2), __fsub_rn(__fmul_rn(d2, (float)((w >> 28) & 15)), mm2));
+        }
+        *reinterpret_cast<uint4*>(sA + umma_sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(sA + umma_sw128(r, 4 + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+}
+
+// f32 -> fp16 of a GEMM input (per-op entry point; the prefill kernels write fp16 themselves)
+__global__ void umma_to_half_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
+}
+
 struct UmmaParams {
     const uint8_t* w;
     long long row_bytes;
     int type, n_rows, K;
-    const float* x;      // [T][ldx]
+    const __half* x;     // [T][ldx] fp16 (rounded once by the kernel that produced the vector, not by every CTA)
     int ldx, T;
     float* y;            // [T][ldy]: Y[t][j]
     int ldy;
@@ -168,17 +206,18 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
     const uint8_t* wrow = p.w + (long long)min(row0 + tid, p.n_rows - 1) * p.row_bytes;
     uint32_t phase = 0;
     bool alive = true;
+    const bool q4_fast = p.type == T_Q4_K && !(((uintptr_t)p.w | (uintptr_t)p.row_bytes) & 15);
     for (int k0 = 0; k0 < p.K; k0 += kUmmaK) {
+        if (q4_fast) {
+            umma_deq64_q4k(wrow, k0, sA, tid);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
+        }
         for (int i = tid; i < TN * 8; i += 128) {
             const int r = i >> 3, c = i & 7, tk = tok0 + r;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (tk < p.T) {
-                const float* xp = p.x + (long long)tk * p.ldx + k0 + 8 * c;
-                const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
-                v = make_uint4(umma_pack_h2(a.x, a.y), umma_pack_h2(a.z, a.w), umma_pack_h2(b.x, b.y), umma_pack_h2(b.z, b.w));
-            }
+            if (tk < p.T) v = *reinterpret_cast<const uint4*>(p.x + (long long)tk * p.ldx + k0 + 8 * c);
             *reinterpret_cast<uint4*>(sB + umma_sw128(r, c)) = v;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
@@ -233,12 +272,12 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
 
 inline bool umma_type_ok(int type) { return type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q8_0; }
 // Is the launch eligible?  K a multiple of 256 (K-quants) / 64, rows at least 2-byte aligned (4 for Q4_K / Q5_K headers),
-// activations 16-byte aligned rows.
+// fp16 activation rows 16-byte aligned.
 inline bool umma_eligible(const UmmaParams& p) {
     if (!umma_type_ok(p.type) || p.K <= 0 || p.K % 64 || p.K % type_block_elems(p.type) || p.T <= 0 || p.n_rows <= 0) return false;
     const bool k45 = p.type == T_Q4_K || p.type == T_Q5_K;
     if (((uintptr_t)p.w | (uintptr_t)p.row_bytes) & (k45 ? 7 : 1)) return false;
-    if (((uintptr_t)p.x & 15) || (p.ldx & 3)) return false;
+    if (((uintptr_t)p.x & 15) || (p.ldx & 7)) return false;
     return true;
 }
 template <int TN>

@@ -73,7 +73,7 @@ struct PrefillAttnParams {
     int ld;
     const float* k_cache;  // [n_kv][max_seq][hd], positions 0 .. pos0 + T - 1 valid
     const float* v_cache;
-    float* out;            // [T][ldo]: [n_heads][hd] per token
+    __half* out;           // [T][ldo]: [n_heads][hd] per token, fp16 (input of the O-projection GEMM)
     int ldo;
     int pos0, T, n_heads, n_kv, max_seq;
     float scale;
@@ -168,16 +168,34 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
         if (g < G) {
             const float inv = 1.0f / l[g];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) p.out[(size_t)t * p.ldo + (size_t)(kh * G + g) * HD + lane * VEC + v] = acc[g][v] * inv;
+            for (int v = 0; v < VEC; v++) p.out[(size_t)t * p.ldo + (size_t)(kh * G + g) * HD + lane * VEC + v] = __float2half_rn(acc[g][v] * inv);
         }
     }
 }
 
+// RMSNorm of T rows, output rounded to fp16 for the tensor-core GEMM that consumes it (same f32 arithmetic as
+// rms_norm_rows_kernel: ss = sum x^2, inv = 1/sqrt(ss/n + eps), (x*inv)*w; simd.rs:847-899)
+__global__ void __launch_bounds__(256) prefill_rms_norm_kernel(const float* x, const float* w, float eps, __half* out, int n) {
+    __shared__ float red[8];
+    const float* xr = x + (size_t)blockIdx.x * n;
+    __half* orow = out + (size_t)blockIdx.x * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int k = 0; k < 8; k++) tot += red[k];
+    const float inv = 1.0f / sqrtf(tot / (float)n + eps);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) orow[i] = __float2half_rn(__fmul_rn(__fmul_rn(xr[i], inv), w[i]));
+}
+
 // g[i] = silu(g[i]) * u[i]  (silu rounded to f32 first, then the product: simd.rs:598-649)
-__global__ void prefill_swiglu_kernel(float* __restrict__ g, const float* __restrict__ u, long long n) {
+__global__ void prefill_swiglu_kernel(const float* __restrict__ g, const float* __restrict__ u, __half* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x = g[i];
-        g[i] = (x / (1.0f + expf(-x))) * u[i];
+        out[i] = __float2half_rn((x / (1.0f + expf(-x))) * u[i]);
     }
 }
 
