@@ -19,8 +19,8 @@
 //     tokens per load, and stores Y so that a warp writes 32 consecutive floats of one token's row.
 // fp16 operands, f32 accumulation: measured 3e-4 of the largest output against a double-precision dequant-then-dot
 // (tools/umma_lab.cu); the exact token-by-token path stays the default where bit-level greedy parity matters.
-// First version: not pipelined (dequant, MMA and the next step's loads are serialised by one mbarrier) -- 150 TFLOP/s on
-// the 2K-token gate projection, i.e. the dequant, not the tensor pipe, is the limit.
+// Two stages: the MMAs of step k overlap the dequant of step k + 1; the dequant (CUDA cores), not the tensor pipe, is the
+// limit.
 #pragma once
 #include "common.cuh"
 #include "quant.cuh"
@@ -181,17 +181,19 @@ struct UmmaParams {
 template <int TN>
 __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams p) {
     extern __shared__ __align__(1024) uint8_t umma_smem[];
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_tmem;
+    constexpr int kStageBytes = (kUmmaM + TN) * 128;
     uint8_t* base = umma_smem + ((1024u - (umma_smem_u32(umma_smem) & 1023u)) & 1023u);   // the swizzle pattern is on absolute address bits
-    uint8_t* sA = base;                       // [128 weight rows][128 B]
-    uint8_t* sB = base + kUmmaM * 128;        // [TN tokens][128 B]
+    uint8_t* sA = base;                       // stage s: [128 weight rows][128 B] at sA + s * kStageBytes
+    uint8_t* sB = base + kUmmaM * 128;        //          [TN tokens][128 B]      at sB + s * kStageBytes
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row0 = blockIdx.x * kUmmaM, tok0 = blockIdx.y * TN;
-    const uint32_t bar = umma_smem_u32(&s_bar);
+    const uint32_t bar = umma_smem_u32(&s_bar[0]);
     constexpr int kCols = TN < 32 ? 32 : TN;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -204,37 +206,58 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = umma_idesc(kUmmaM, TN);
     const uint8_t* wrow = p.w + (long long)min(row0 + tid, p.n_rows - 1) * p.row_bytes;
-    uint32_t phase = 0;
+    // Two stages of (A, B) tiles: the MMAs of step k run while the threads dequantise step k + 1; a stage is rewritten
+    // only after the commit of the step that last read it (two steps back) has arrived on the stage's mbarrier.
+    uint32_t ph0 = 0, ph1 = 0;
     bool alive = true;
     const bool q4_fast = p.type == T_Q4_K && !(((uintptr_t)p.w | (uintptr_t)p.row_bytes) & 15);
-    for (int k0 = 0; k0 < p.K; k0 += kUmmaK) {
+    int it = 0;
+    for (int k0 = 0; k0 < p.K; k0 += kUmmaK, it++) {
+        const int sidx = it & 1;
+        uint8_t* tA = sA + sidx * kStageBytes;
+        uint8_t* tB = sB + sidx * kStageBytes;
+        if (it >= 2 && alive) {
+            if (!umma_mbar_wait(bar + 8u * sidx, sidx ? ph1 : ph0)) {
+                alive = false;
+                if (p.err) atomicExch(p.err, 5);
+            }
+            if (sidx) ph1 ^= 1u; else ph0 ^= 1u;
+        }
         if (q4_fast) {
-            umma_deq64_q4k(wrow, k0, sA, tid);
+            umma_deq64_q4k(wrow, k0, tA, tid);
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
         }
-        for (int i = tid; i < TN * 8; i += 128) {
-            const int r = i >> 3, c = i & 7, tk = tok0 + r;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (tk < p.T) v = *reinterpret_cast<const uint4*>(p.x + (long long)tk * p.ldx + k0 + 8 * c);
-            *reinterpret_cast<uint4*>(sB + umma_sw128(r, c)) = v;
+        {
+            constexpr int NB = TN * 8 / 128;   // 16-byte chunks of the activation tile per thread
+            uint4 v[NB];
+#pragma unroll
+            for (int u = 0; u < NB; u++) {     // all loads first (independent), then the stores
+                const int i = tid + u * 128, r = i >> 3, c = i & 7, tk = tok0 + r;
+                v[u] = tk < p.T ? __ldg(reinterpret_cast<const uint4*>(p.x + (long long)tk * p.ldx + k0 + 8 * c)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int i = tid + u * 128, r = i >> 3, c = i & 7;
+                *reinterpret_cast<uint4*>(tB + umma_sw128(r, c)) = v[u];
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t da = umma_desc(umma_smem_u32(sA)), db = umma_desc(umma_smem_u32(sB));
+            const uint64_t da = umma_desc(umma_smem_u32(tA)), db = umma_desc(umma_smem_u32(tB));
 #pragma unroll
             for (int kk = 0; kk < kUmmaK / 16; kk++)   // 16 fp16 = 32 bytes along the swizzled row: start address + 2
                 umma_f16(tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (k0 > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bar);
+            umma_commit(bar + 8u * sidx);
         }
-        if (alive && !umma_mbar_wait(bar, phase)) {
-            alive = false;
-            if (p.err) atomicExch(p.err, 5);
-        }
-        phase ^= 1u;
+    }
+    // the accumulator is complete when the last commit has arrived (commits arrive in issue order)
+    if (it > 0 && alive) {
+        const int sidx = (it - 1) & 1;
+        if (!umma_mbar_wait(bar + 8u * sidx, sidx ? ph1 : ph0) && p.err) atomicExch(p.err, 5);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = weight rows, 32 token columns per load ----
@@ -282,7 +305,7 @@ inline bool umma_eligible(const UmmaParams& p) {
 }
 template <int TN>
 inline cudaError_t umma_launch_tn(const UmmaParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(kUmmaM + TN) * 128 + 1024;
+    const size_t smem = (size_t)2 * (kUmmaM + TN) * 128 + 1024;   // two stages
     static bool once = false;   // per instantiation
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(dequant_gemm_umma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
