@@ -103,21 +103,31 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
     }
     const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
     const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
-    for (int pos = 0; pos < kv_len; pos += UB) {
-        float kr[UB][VEC], vr[UB][VEC];
+    // the K / V rows of the next four positions are in flight while these four are processed (two register buffers)
+    auto load = [&](int pos, float (&kk)[UB][VEC], float (&vv)[UB][VEC]) {
 #pragma unroll
         for (int u = 0; u < UB; u++) {
             const int pc = min(pos + u, kv_len - 1);   // clamped: stays in range, masked below
             if constexpr (VEC == 4) {
                 const float4 a = *reinterpret_cast<const float4*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const float4*>(vb + (size_t)pc * HD);
-                kr[u][0] = a.x; kr[u][1] = a.y; kr[u][2] = a.z; kr[u][3] = a.w;
-                vr[u][0] = b.x; vr[u][1] = b.y; vr[u][2] = b.z; vr[u][3] = b.w;
+                kk[u][0] = a.x; kk[u][1] = a.y; kk[u][2] = a.z; kk[u][3] = a.w;
+                vv[u][0] = b.x; vv[u][1] = b.y; vv[u][2] = b.z; vv[u][3] = b.w;
             } else {
                 const float2 a = *reinterpret_cast<const float2*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const float2*>(vb + (size_t)pc * HD);
-                kr[u][0] = a.x; kr[u][1] = a.y;
-                vr[u][0] = b.x; vr[u][1] = b.y;
+                kk[u][0] = a.x; kk[u][1] = a.y;
+                vv[u][0] = b.x; vv[u][1] = b.y;
             }
         }
+    };
+    float kn[UB][VEC], vn[UB][VEC];
+    load(0, kn, vn);
+    for (int pos = 0; pos < kv_len; pos += UB) {
+        float kr[UB][VEC], vr[UB][VEC];
+#pragma unroll
+        for (int u = 0; u < UB; u++)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) { kr[u][v] = kn[u][v]; vr[u][v] = vn[u][v]; }
+        if (pos + UB < kv_len) load(pos + UB, kn, vn);
         float s[UB][GMAX];
 #pragma unroll
         for (int u = 0; u < UB; u++)
