@@ -323,7 +323,7 @@ def main():
             prefill = {"tokens": args.prefill_len, "seconds": pf_s, "tok_per_s": args.prefill_len / pf_s,
                        "gemm_tflops": tfl, "tensor_peak_tflops": peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")),
                        "tensor_frac": tfl / peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")),
-                       "path": "b200_prefill: 256-token chunks, tcgen05.mma kind::f16 dequant-GEMM + batched RoPE/attention/SwiGLU, "
+                       "path": "b200_prefill: 2048-token chunks, tcgen05.mma kind::f16 dequant-GEMM + batched RoPE/attention/SwiGLU, "
                                "host tokens in, logits of the last token out (wall clock)",
                        "token_by_token_tok_per_s": 1000.0 / ms_per_step}
         except Exception as e:

@@ -158,6 +158,12 @@ struct b200_ctx {
     int prefill_gemm_min = 32;
     float* pf_buf = nullptr;
     int* pf_tok = nullptr;
+    uint8_t* pf_rows = nullptr;      // batched decode: per-row position | KV base pointer | SeqState pointer
+    float* pf_logits = nullptr;      // batched decode: [rows][vocab]
+    float* pf_split = nullptr;       // split-K partial tiles of the small-T GEMMs
+    size_t pf_split_floats = 0;
+    int pf_logits_rows = 0;
+    int batch_gemm_min = 12;   // measured crossover on Llama-3-8B: the GEMM pass costs ~18 ms whatever the row count, a sequence alone 2 ms
     uint64_t prefill_gemm_tokens = 0;
     int* h_err = nullptr;   // pinned copy of the first watchdog word, fetched with every synchronising call
     int* h_token = nullptr;
@@ -248,6 +254,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_stream = env_int("B200_STREAM", 1) != 0;
     c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
+    c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 12));
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -565,6 +572,9 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->d_tmaps);
     cudaFree(c->pf_buf);
     cudaFree(c->pf_tok);
+    cudaFree(c->pf_rows);
+    cudaFree(c->pf_logits);
+    cudaFree(c->pf_split);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
@@ -1120,7 +1130,9 @@ static bool prefill_gemm_ok(const b200_ctx* c) {
     return true;
 }
 
-static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, bool want_logits) {
+// seqs == nullptr: the n tokens are consecutive positions of slot `seq` (prefill).  seqs != nullptr: batched decode, token i
+// is the next token of slot seqs[i] (distinct slots); the logits of all n rows are left in c->pf_logits ([n][vocab]).
+static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, bool want_logits, const int* seqs = nullptr) {
     const b200_model_desc& d = c->d;
     Slot& sl = c->slots[seq];
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, A = nh * hd, I = (int)d.ffn;
@@ -1130,6 +1142,36 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     if (!c->pf_buf) {
         CU_ALLOC(cudaMalloc((void**)&c->pf_buf, per_tok * cap * sizeof(float)));
         CU_ALLOC(cudaMalloc((void**)&c->pf_tok, cap * sizeof(int)));
+        CU_ALLOC(cudaMalloc((void**)&c->pf_rows, (size_t)cap * 24));
+    }
+    if (!c->pf_split) {   // split-K scratch for passes of <= 64 rows: 8 partial tiles of the widest projection
+        c->pf_split_floats = (size_t)8 * 64 * std::max(std::max(I, QKV), H);
+        CU_ALLOC(cudaMalloc((void**)&c->pf_split, c->pf_split_floats * sizeof(float)));
+    }
+    // batched decode: per-row (position, KV base of the slot, SeqState of the slot)
+    const bool rows = seqs != nullptr;
+    int* d_pos = reinterpret_cast<int*>(c->pf_rows);
+    float** d_kv = reinterpret_cast<float**>(c->pf_rows + (size_t)cap * 8);
+    SeqState** d_st = reinterpret_cast<SeqState**>(c->pf_rows + (size_t)cap * 16);
+    if (rows) {
+        if (n > cap) return fail(B200_ERR_INVALID_ARGUMENT, "batched decode: more rows than the activation buffers hold");
+        std::vector<int> hp(n);
+        std::vector<float*> hk(n);
+        std::vector<SeqState*> hs(n);
+        for (int i = 0; i < n; i++) {
+            Slot& s = c->slots[seqs[i]];
+            hp[i] = (int)s.host_pos; hk[i] = s.kv; hs[i] = s.d_state;
+        }
+        CU(cudaMemcpyAsync(d_pos, hp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_kv, hk.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_st, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
+        if (c->pf_logits_rows < n) {
+            cudaFree(c->pf_logits);
+            c->pf_logits = nullptr;
+            CU_ALLOC(cudaMalloc((void**)&c->pf_logits, (size_t)n * d.vocab * sizeof(float)));
+            c->pf_logits_rows = n;
+        }
     }
     float* X = c->pf_buf;                               // [T][H] residual stream (f32)
     float* Q = X + (size_t)cap * H;                     // [T][QKV] f32
@@ -1146,7 +1188,8 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         p.x = x; p.ldx = ldx; p.T = T; p.y = y; p.ldy = ldy;
         p.bias = (bias && bias->present()) ? bias->f32() : nullptr;
         p.accumulate = acc; p.err = c->mma_err;
-        c->launches++;
+        umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
+        c->launches += p.k_split ? 2 : 1;
         return umma_launch(p, st);
     };
     int last_T = 0;
@@ -1167,10 +1210,12 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             PrefillRopeParams rp{};
             rp.qkv = Q; rp.ld = QKV; rp.k_cache = kc; rp.v_cache = vc; rp.freq = c->rope_freq; rp.pos0 = pos0;
             rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox; rp.rope_scale = d.rope_scale;
+            if (rows) { rp.row_pos = d_pos; rp.row_kv = d_kv; rp.k_off = (long long)((size_t)l * kv_layer); rp.v_off = rp.k_off + (long long)(kv_layer / 2); }
             prefill_rope_kv_kernel<<<T, 256, 0, st>>>(rp);
             PrefillAttnParams ap{};
             ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = ATh; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
             ap.n_heads = nh; ap.n_kv = nkv; ap.max_seq = d.max_seq_len; ap.scale = 1.0f / sqrtf((float)hd);
+            if (rows) { ap.row_pos = d_pos; ap.row_kv = d_kv; ap.k_off = rp.k_off; ap.v_off = rp.v_off; }
             const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
             const int Gq = nh / nkv;
             if (hd == 128) {
@@ -1190,6 +1235,17 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         }
         c->launches += 1;
         CU(cudaGetLastError());
+    }
+    if (rows) {   // every row's slot advances by one; final RMSNorm + vocab head of ALL rows through the GEMM
+        prefill_advance_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_st, n);
+        const DevTensor& head = c->output.present() ? c->output : c->token_embd;
+        prefill_rms_norm_kernel<<<n, 256, 0, st>>>(X, c->output_norm.f32(), d.norm_eps, XNh, H);
+        UmmaParams hp{};
+        hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = d.vocab; hp.K = H;
+        hp.x = XNh; hp.ldx = H; hp.T = n; hp.y = c->pf_logits; hp.ldy = d.vocab; hp.err = c->mma_err;
+        CU(umma_launch(hp, st));
+        c->launches += 3;
+        return B200_OK;
     }
     prefill_advance_kernel<<<1, 32, 0, st>>>(sl.d_state, n);
     if (want_logits) {   // final RMSNorm + vocab head of the last token, through the exact GEMV path
@@ -1346,6 +1402,28 @@ extern "C" int b200_decode_batch(b200_ctx* c, const int* seqs, const uint32_t* t
         for (int j = 0; j < i; j++)
             if (seqs[i] == seqs[j]) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch: duplicate sequence slot");
     int rc;
+    // n >= batch_gemm_min rows of an eligible dense model: ONE pass of the tcgen05 dequant-GEMMs for all the sequences (the
+    // weights are read once per step instead of once per sequence); fp16 tensor-core operands, see gemm_umma.cuh
+    if (n >= c->batch_gemm_min && prefill_gemm_ok(c)) {
+        const DevTensor& head = c->output.present() ? c->output : c->token_embd;
+        UmmaParams hp{};
+        hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = c->d.vocab; hp.K = c->d.hidden; hp.T = 1;
+        hp.x = reinterpret_cast<const __half*>(c->xa); hp.ldx = c->d.hidden;
+        if (umma_eligible(hp) && n <= std::min(prefill_chunk(), c->d.max_seq_len)) {
+            for (int i = 0; i < n; i++) {
+                if ((rc = check_slot(c, seqs[i], "b200_decode_batch"))) return rc;
+                if ((rc = check_token(c, seqs[i], tokens[i], "b200_decode_batch"))) return rc;
+            }
+            CU(cudaSetDevice(c->par.device));
+            if ((rc = prefill_gemm(c, seqs[0], tokens, n, false, seqs))) return rc;
+            WATCHDOG_FETCH(c);
+            CU(cudaStreamSynchronize(c->stream));
+            if ((rc = watchdog_check(c, "b200_decode_batch"))) return rc;
+            CU(cudaMemcpy(logits_out, c->pf_logits, (size_t)n * c->d.vocab * sizeof(float), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; i++) c->slots[seqs[i]].host_pos++;
+            return B200_OK;
+        }
+    }
     for (int i = 0; i < n; i++)
         if ((rc = b200_forward(c, seqs[i], tokens[i], logits_out + (size_t)i * c->d.vocab))) return rc;
     return B200_OK;

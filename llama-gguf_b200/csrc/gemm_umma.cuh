@@ -175,6 +175,11 @@ struct UmmaParams {
     int ldy;
     const float* bias;   // optional [n_rows]
     int accumulate;      // Y += ... (residual connection) instead of Y = ...
+    // split-K (small T: too few (rows / 128) x (T / TN) tiles to fill the GPU): blockIdx.z handles K range
+    // [z * k_split, (z + 1) * k_split) and stores its partial tile to part[z][t][j] (ld = n_rows); umma_reduce_kernel adds
+    // the partials in z order (deterministic) and applies bias / accumulate
+    int k_split;         // 0 = no split
+    float* part;
     int* err;            // watchdog word (set to 5 if the MMA completion never arrives)
 };
 
@@ -212,7 +217,8 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
     bool alive = true;
     const bool q4_fast = p.type == T_Q4_K && !(((uintptr_t)p.w | (uintptr_t)p.row_bytes) & 15);
     int it = 0;
-    for (int k0 = 0; k0 < p.K; k0 += kUmmaK, it++) {
+    const int kb = p.k_split ? (int)blockIdx.z * p.k_split : 0, ke = p.k_split ? min(p.K, kb + p.k_split) : p.K;
+    for (int k0 = kb; k0 < ke; k0 += kUmmaK, it++) {
         const int sidx = it & 1;
         uint8_t* tA = sA + sidx * kStageBytes;
         uint8_t* tB = sB + sidx * kStageBytes;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
             const uint64_t da = umma_desc(umma_smem_u32(tA)), db = umma_desc(umma_smem_u32(tB));
 #pragma unroll
             for (int kk = 0; kk < kUmmaK / 16; kk++)   // 16 fp16 = 32 bytes along the swizzled row: start address + 2
-                umma_f16(tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (k0 > 0 || kk > 0) ? 1u : 0u);
+                umma_f16(tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (k0 > kb || kk > 0) ? 1u : 0u);
             umma_commit(bar + 8u * sidx);
         }
     }
@@ -281,16 +287,33 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
         for (int n = 0; n < 32; n++) {
             const int tk = tok0 + n0 + n;
             if (tk < p.T && j < p.n_rows) {
-                float* yp = p.y + (long long)tk * p.ldy + j;
-                float val = __uint_as_float(v[n]) + bj;
-                if (p.accumulate) val += *yp;
-                *yp = val;
+                if (p.k_split) {
+                    p.part[((long long)blockIdx.z * p.T + tk) * p.n_rows + j] = __uint_as_float(v[n]);
+                } else {
+                    float* yp = p.y + (long long)tk * p.ldy + j;
+                    float val = __uint_as_float(v[n]) + bj;
+                    if (p.accumulate) val += *yp;
+                    *yp = val;
+                }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCols) : "memory");
+}
+
+// Y[t][j] (+)= sum_z part[z][t][j] + bias[j]   (split-K epilogue, z in fixed order)
+__global__ void umma_reduce_kernel(const UmmaParams p, int splits) {
+    const long long n = (long long)p.T * p.n_rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / p.n_rows), j = (int)(i - (long long)t * p.n_rows);
+        float acc = 0.0f;
+        for (int z = 0; z < splits; z++) acc += p.part[(long long)z * n + i];
+        if (p.bias) acc += p.bias[j];
+        float* yp = p.y + (long long)t * p.ldy + j;
+        *yp = p.accumulate ? *yp + acc : acc;
+    }
 }
 
 inline bool umma_type_ok(int type) { return type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q8_0; }
@@ -312,9 +335,30 @@ inline cudaError_t umma_launch_tn(const UmmaParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         once = true;
     }
-    dim3 grid((p.n_rows + kUmmaM - 1) / kUmmaM, (p.T + TN - 1) / TN);
+    const int splits = p.k_split ? (p.K + p.k_split - 1) / p.k_split : 1;
+    dim3 grid((p.n_rows + kUmmaM - 1) / kUmmaM, (p.T + TN - 1) / TN, splits);
     dequant_gemm_umma_kernel<TN><<<grid, 128, smem, st>>>(p);
+    if (splits > 1) {
+        const long long n = (long long)p.T * p.n_rows;
+        umma_reduce_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>(p, splits);
+    }
     return cudaGetLastError();
+}
+// Split-K plan for a launch with few tiles: K ranges of at least 512 elements (multiples of 256), at most 8, enough to put
+// ~2 CTAs on every SM.  `scratch_floats` = capacity of `part`; returns with p.k_split / p.part set (0 = no split).
+inline void umma_plan_split(UmmaParams& p, float* scratch, size_t scratch_floats, int n_sm) {
+    p.k_split = 0;
+    p.part = nullptr;
+    if (!scratch || p.T > 64) return;
+    const int tn = p.T <= 32 ? 32 : 64;
+    const int tiles = ((p.n_rows + kUmmaM - 1) / kUmmaM) * ((p.T + tn - 1) / tn);
+    int splits = std::min(8, std::min(p.K / 512, (2 * n_sm + tiles - 1) / tiles));
+    while (splits > 1 && (size_t)splits * p.T * p.n_rows > scratch_floats) splits--;
+    if (splits <= 1) return;
+    int ks = ((p.K + splits - 1) / splits + 255) & ~255;
+    if (ks >= p.K) return;
+    p.k_split = ks;
+    p.part = scratch;
 }
 inline cudaError_t umma_launch(const UmmaParams& p, cudaStream_t st) {
     if (p.T <= 32) return umma_launch_tn<32>(p, st);

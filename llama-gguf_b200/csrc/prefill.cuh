@@ -31,10 +31,17 @@ struct PrefillRopeParams {
     const float* freq;     // [hd/2]
     int pos0, n_heads, n_kv, hd, max_seq, neox;
     float rope_scale;
+    // batched decode: row t is the next token of ITS OWN sequence slot -- position row_pos[t], caches at
+    // row_kv[t] + k_off / v_off (floats); nullptr = rows are consecutive positions of one sequence (prefill)
+    const int* row_pos;
+    float* const* row_kv;
+    long long k_off, v_off;
 };
 // one CTA per token: Backend::rope for the token's position pos0 + t, k rows -> cache, v rows -> cache
 __global__ void prefill_rope_kv_kernel(const PrefillRopeParams p) {
-    const int t = blockIdx.x, pos = p.pos0 + t;
+    const int t = blockIdx.x, pos = p.row_pos ? p.row_pos[t] : p.pos0 + t;
+    float* const k_cache = p.row_pos ? p.row_kv[t] + p.k_off : p.k_cache;
+    float* const v_cache = p.row_pos ? p.row_kv[t] + p.v_off : p.v_cache;
     const int half = p.hd >> 1;
     const int n_pairs = (p.n_heads + p.n_kv) * half, n_v = p.n_kv * p.hd;
     const float position = (float)pos / p.rope_scale;
@@ -55,7 +62,7 @@ __global__ void prefill_rope_kv_kernel(const PrefillRopeParams p) {
             } else {
                 const int kh = head - p.n_heads;
                 const float* d = kraw + (size_t)kh * p.hd;
-                float* o = p.k_cache + ((size_t)kh * p.max_seq + pos) * p.hd;
+                float* o = k_cache + ((size_t)kh * p.max_seq + pos) * p.hd;
                 const float x0 = d[i0], x1 = d[i1];
                 o[i0] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
                 o[i1] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
@@ -63,7 +70,7 @@ __global__ void prefill_rope_kv_kernel(const PrefillRopeParams p) {
         } else {
             const int j = i - n_pairs;
             const int kh = j / p.hd, d = j - kh * p.hd;
-            p.v_cache[((size_t)kh * p.max_seq + pos) * p.hd + d] = vraw[j];
+            v_cache[((size_t)kh * p.max_seq + pos) * p.hd + d] = vraw[j];
         }
     }
 }
@@ -77,6 +84,9 @@ struct PrefillAttnParams {
     int ldo;
     int pos0, T, n_heads, n_kv, max_seq;
     float scale;
+    const int* row_pos;        // batched decode: see PrefillRopeParams
+    float* const* row_kv;
+    long long k_off, v_off;
 };
 // One warp per (token, kv head): the G query heads of the group share every K / V row read (GQA), four cache positions per
 // step (16 independent dot products and reductions in flight), block-wise online softmax as in attn_decode_item.
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
     if (wid >= (long long)p.T * p.n_kv) return;
     const int t = (int)(wid / p.n_kv), kh = (int)(wid - (long long)t * p.n_kv);
     const int G = p.n_heads / p.n_kv;
-    const int kv_len = p.pos0 + t + 1;
+    const int kv_len = (p.row_pos ? p.row_pos[t] : p.pos0 + t) + 1;
     float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
 #pragma unroll
     for (int g = 0; g < GMAX; g++) {
@@ -101,8 +111,8 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
             q[g][v] = g < G ? p.qkv[(size_t)t * p.ld + (size_t)(kh * G + g) * HD + lane * VEC + v] : 0.0f;
         }
     }
-    const float* kb = p.k_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
-    const float* vb = p.v_cache + (size_t)kh * p.max_seq * HD + lane * VEC;
+    const float* kb = (p.row_pos ? p.row_kv[t] + p.k_off : p.k_cache) + (size_t)kh * p.max_seq * HD + lane * VEC;
+    const float* vb = (p.row_pos ? p.row_kv[t] + p.v_off : p.v_cache) + (size_t)kh * p.max_seq * HD + lane * VEC;
     // the K / V rows of the next four positions are in flight while these four are processed (two register buffers)
     auto load = [&](int pos, float (&kk)[UB][VEC], float (&vv)[UB][VEC]) {
 #pragma unroll
@@ -214,6 +224,16 @@ __global__ void prefill_advance_kernel(SeqState* st, int T) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         st->pos_cur = st->pos_next + T - 1;
         st->pos_next = st->pos_next + T;
+    }
+}
+
+// batched decode: every row's slot advances by one token
+__global__ void prefill_advance_rows_kernel(SeqState* const* st, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        SeqState* s = st[i];
+        s->pos_cur = s->pos_next;
+        s->pos_next = s->pos_next + 1;
     }
 }
 

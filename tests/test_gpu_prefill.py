@@ -31,7 +31,7 @@ def test_gemm_prefill_logits_and_kv_cache(b200, oracle, preset, mix, n):
     launches = gpu.stats()["kernel_launches"] - l0
     want = ref.forward(prompt)
     chunks = (n + 2047) // 2048
-    assert launches <= chunks * (13 * desc["n_layers"] + 1) + 2, "one launch sequence per chunk of the prompt, not per token"
+    assert launches <= chunks * (20 * desc["n_layers"] + 1) + 2, "one launch sequence per chunk of the prompt (7 GEMMs + split-K reduces + 5 small kernels per layer), not per token"
     assert gpu.position() == n == ref.position()
     assert rel_err(got, want) < TOL
     # the exact decode path continues on the cache the GEMM prefill wrote
@@ -60,4 +60,36 @@ def test_short_prompts_and_disabled_gemm_stay_exact(b200, oracle):
     ref2 = oracle.OracleModel(desc, tensors)
     short = prompt[:8]                                    # below the GEMM threshold (32 tokens)
     assert rel_err(gpu.prefill(short), ref2.forward(short)) < 1e-4
+    gpu.close()
+
+
+@pytest.mark.parametrize("preset,mix", [("llama-tiny", "Q4_K_M"), ("qwen-kq-tiny", "Q5_K_M")])
+def test_batched_decode_through_the_gemm(b200, oracle, preset, mix):
+    """b200_decode_batch with >= 12 sequences: one pass of the dequant-GEMMs for all rows, each row at ITS slot's position
+    and on ITS slot's KV cache.  Same fp16 tolerance as the GEMM prefill."""
+    nseq = 12
+    arch, desc, tensors = synth.synth_model(preset, mix, 64, max_batch=nseq)
+    gpu = b200.GpuOnlyInference(desc, tensors)
+    refs = [oracle.OracleModel(desc, tensors) for _ in range(nseq)]
+    rng = np.random.default_rng(7)
+    for s in range(nseq):   # different history lengths per slot (exact token-by-token path)
+        for t in rng.integers(0, desc["vocab"], size=1 + (s * 5) % 17):
+            gpu.prefill_token(int(t), s)
+            refs[s].forward([int(t)])
+    slots = list(range(nseq))
+    for step in range(3):
+        toks = [int(t) for t in rng.integers(0, desc["vocab"], size=nseq)]
+        l0 = gpu.stats()["kernel_launches"]
+        got = gpu.decode_batch(slots, toks)
+        assert gpu.stats()["kernel_launches"] - l0 <= 20 * desc["n_layers"] + 6, "one pass for all rows, not one per sequence"
+        for s in range(nseq):
+            want = refs[s].forward([toks[s]])
+            assert rel_err(got[s], want) < TOL, f"step {step} slot {s}"
+            assert gpu.position(s) == refs[s].position()
+    # a small batch takes the per-sequence path (one launch sequence per row) on the caches the GEMM steps wrote
+    l0 = gpu.stats()["kernel_launches"]
+    got = gpu.decode_batch([0, 1, 2], [3, 4, 5])
+    assert gpu.stats()["kernel_launches"] - l0 >= 3
+    for s in range(3):
+        assert rel_err(got[s], refs[s].forward([3 + s])) < TOL
     gpu.close()
