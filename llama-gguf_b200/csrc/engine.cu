@@ -330,6 +330,7 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     for (int i = 0; i < n_dims; i++) lne[i] = ne[i];
     const uint64_t row_bytes_full = ne[0] / be * bb;
     const int kind = (P > 1) ? tp_shard_kind(gguf_name) : 0;
+    long long tp_pitch = 0;
     if (kind == 1) {
         const int dim = n_dims == 1 ? 0 : 1;
         if (ne[dim] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": rows not divisible by the world size");
@@ -343,11 +344,15 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
         const uint64_t nb = ne[0] / be;
         if (nb % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": K blocks not divisible by the world size");
         lne[0] = ne[0] / P;
+        // rows keep their bytes, but start 16 bytes apart at least: a row pitch that is a 16-byte multiple is what the TMA
+        // tensor map of the streamed kernel needs (Llama-3-8B TP=2: 28 Q6_K blocks = 5880 bytes -> pitch 5888)
         const size_t slice = (size_t)(nb / P) * bb, rows = (size_t)(numel / ne[0]);
-        CU_ALLOC(cudaMalloc((void**)&t->d, slice * rows + 256));
-        CU(cudaMemcpy2D(t->d, slice, (const uint8_t*)host + (size_t)R * slice, row_bytes_full, slice, rows, cudaMemcpyHostToDevice));
-        CU(cudaMemset(t->d + slice * rows, 0, 256));
-        t->nbytes = slice * rows;
+        const size_t pitch = (slice + 15) & ~(size_t)15;
+        CU_ALLOC(cudaMalloc((void**)&t->d, pitch * rows + 256));
+        CU(cudaMemset(t->d, 0, pitch * rows + 256));
+        CU(cudaMemcpy2D(t->d, pitch, (const uint8_t*)host + (size_t)R * slice, row_bytes_full, slice, rows, cudaMemcpyHostToDevice));
+        t->nbytes = pitch * rows;
+        tp_pitch = (long long)pitch;
     } else {
         CU_ALLOC(cudaMalloc((void**)&t->d, nbytes + 256));
         CU(cudaMemcpy(t->d, host, nbytes, cudaMemcpyHostToDevice));
@@ -357,7 +362,7 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     t->type = (int)ggml_type;
     t->n_dims = n_dims;
     for (int i = 0; i < n_dims; i++) t->ne[i] = lne[i];
-    t->row_bytes = (long long)(lne[0] / be * bb);
+    t->row_bytes = tp_pitch ? tp_pitch : (long long)(lne[0] / be * bb);
     c->tensors[gguf_name] = *t;
     return B200_OK;
 }
@@ -951,7 +956,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static int stream_build(b200_ctx* c) {
     const b200_model_desc& d = c->d;
     c->stream_ok = false;
-    if (!c->use_stream || c->par.world_size > 1) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 1, line %d)\n", __LINE__); return B200_OK; }
+    if (!c->use_stream || (c->par.world_size > 1 && !env_int("B200_STREAM_TP", 1))) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 1, line %d)\n", __LINE__); return B200_OK; }
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
@@ -972,7 +977,7 @@ static int stream_build(b200_ctx* c) {
         for (size_t pi = 0; pi < prog.size(); pi++) {
             if (prog[pi].kind != PH_GEMV) continue;
             MParams& m = prog[pi].gemv;
-            if (m.expert_sel || m.n_peer || m.n_sum || m.K % kMmaChunk) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 2, line %d)\n", __LINE__); return B200_OK; }
+            if (m.expert_sel || m.K % kMmaChunk) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 2, line %d)\n", __LINE__); return B200_OK; }
             int C = 1 << 30;
             for (int s = 0; s < m.n_seg; s++) {
                 if (!mma_type_ok(m.seg[s].type)) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (type %d)\n", m.seg[s].type); return B200_OK; }

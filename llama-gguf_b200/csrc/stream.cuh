@@ -262,7 +262,11 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
         if (valid) {
             val += e_bias;
             val += e_res;
-            sg.out[j] = val;
+            if (p.n_peer > 0) {
+                for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;   // partial of a row-parallel GEMV, to every rank (NVLink peer memory)
+            } else {
+                sg.out[j] = val;
+            }
         }
         if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
     };
@@ -339,7 +343,7 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
         }
     } else {
         XStage xst;
-        const XSource xsrc{p.x, nullptr, 0, 0, nullptr, nullptr};
+        const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};   // tensor parallel: x = sum of the ranks' partial vectors (+ residual)
         stage_x_load(xst, xsrc, p.norm_w, K, kSNT);
         MMA_STAMP(2);
         stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, kSNT);
@@ -508,6 +512,33 @@ __device__ __forceinline__ bool s_grid_wait(unsigned int* bar, unsigned int targ
     return *s_flag != 0;
 }
 
+// Cross-GPU flag exchange after the local grid barrier (consumer warps only; see tp_exchange in mega.cuh)
+__device__ __forceinline__ bool s_tp_exchange(const MegaParams& mp, unsigned int epoch, int* s_flag, volatile int* s_dead) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < mp.tp_size)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[tid] + mp.tp_rank), "r"(epoch) : "memory");
+    if (tid == 0) {
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int r = 0; r < mp.tp_size && ok; r++) {
+            for (;;) {
+                unsigned int v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mp.tp_flags + r) : "memory");
+                if ((int)(v - epoch) >= 0) break;
+                if (*s_dead || clock64() - t0 > 3000000000LL) {
+                    ok = 0;
+                    *s_dead = 1;
+                    if (atomicExch(mp.err, 3) == 0) { mp.err[1] = 5000 + r; mp.err[2] = (int)blockIdx.x; mp.err[3] = (int)epoch; }
+                    break;
+                }
+            }
+        }
+        *s_flag = ok;
+    }
+    cons_sync();
+    return *s_flag != 0;
+}
+
 template <int HD, int GMAX>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const __grid_constant__ StreamParams sp) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -560,6 +591,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
     fetch_desc(1);
     cons_sync();
     long long gph = 0;
+    unsigned int tp_n = 0;   // cross-GPU exchanges so far in this launch
 
     for (int tok = 0; tok < mp.n_tokens; tok++) {
         // ---- embedding (LlamaModel::forward, model/llama.rs:293-306): CTA 0 dequantises row `token`, bit-exactly ----
@@ -579,11 +611,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
             }
         }
         bool ok = true;
+        bool prev_tp_sync = false;   // the predecessor left partial sums in peer memory
         int stamp = 0;
-        auto bar_arrive = [&]() { s_grid_arrive(mp.bar, target); };
+        auto bar_arrive = [&]() {
+            if (prev_tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
+                cons_sync();
+                if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            }
+            s_grid_arrive(mp.bar, target);
+        };
         auto bar_wait = [&]() {
             fetch_desc(gph + 2);
             ok = s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
+            if (prev_tp_sync) ok = s_tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag, &s_dead) && ok;
             if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[stamp] = gtimer();
             stamp++;
         };
@@ -615,6 +655,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
                     cons_sync();
                 }
             }
+            prev_tp_sync = cur.tp_sync != 0;
         }
         // the barrier that ends the last phase of the token
         gph--;
@@ -651,6 +692,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
         }
         s_grid_arrive(mp.bar, target);
         s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
+        const unsigned int cand_epoch = mp.tp_epoch0 + (mp.tp_size > 1 ? ++tp_n : 0u);  // uniform over the grid
         if (blockIdx.x == 0) {
             if (warp == 0) {
                 float best = -INFINITY;
@@ -665,6 +707,43 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
                     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                }
+                if (mp.tp_size > 1) {  // every rank picks the same winner among the per-rank candidates (ties: largest index)
+                    bi += mp.tp_rank * mp.vocab_local;
+                    if (lane < mp.tp_size) {
+                        float* dst = mp.tp_peer_cand[lane] + 2 * mp.tp_rank;
+                        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(best) : "memory");
+                        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + 1), "f"(__int_as_float(bi)) : "memory");
+                    }
+                    __syncwarp();
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                    if (lane < mp.tp_size)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[lane] + mp.tp_rank), "r"(cand_epoch) : "memory");
+                    const long long t0 = clock64();
+                    bool okc = true;
+                    if (lane < mp.tp_size) {
+                        for (;;) {
+                            unsigned int v;
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mp.tp_flags + lane) : "memory");
+                            if ((int)(v - cand_epoch) >= 0) break;
+                            if (clock64() - t0 > 3000000000LL) { okc = false; atomicExch(mp.err, 3); break; }
+                        }
+                    }
+                    __syncwarp();
+                    best = -INFINITY;
+                    bi = -1;
+                    if (okc && lane < mp.tp_size) {
+                        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(best) : "l"(mp.tp_cand + 2 * lane) : "memory");
+                        float fi;
+                        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(fi) : "l"(mp.tp_cand + 2 * lane + 1) : "memory");
+                        bi = __float_as_int(fi);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+                    }
                 }
                 if (lane == 0) {
                     mp.st->token = bi;

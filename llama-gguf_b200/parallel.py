@@ -134,5 +134,8 @@ class TensorParallelInference:
     def stats(self):
         return self.gpu.stats()
 
+    def path(self):
+        return self.gpu.path()
+
     def close(self):
         self.gpu.close()

@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mix, q):
+def _worker(rank, world, port, mix, q, preset="llama-tiny"):
     import sys
 
     here = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +33,7 @@ def _worker(rank, world, port, mix, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np)
+        _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np, preset)
     except Exception as e:  # the parent must not wait for a result that will never come
         q.put({"rank": rank, "error": repr(e)})
         raise
@@ -41,16 +41,16 @@ def _worker(rank, world, port, mix, q):
         dist.destroy_process_group()
 
 
-def _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np):
+def _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np, preset):
     if True:
-        arch, desc, tensors = synth.synth_model("llama-tiny", mix, 64)
+        arch, desc, tensors = synth.synth_model(preset, mix, 64, vocab=1024 if preset == "llama-stream-tiny" else None)
         tp = TensorParallelInference(desc, tensors, device=rank)
         prompt = synth.prompt_tokens(6, desc["vocab"])
         for t in prompt[:-1]:
             tp.prefill_token(t)
         logits = tp.forward(prompt[-1])
         toks, _ = tp.decode_greedy(int(np.argmax(logits)), 8)
-        out = {"rank": rank, "logits": logits, "tokens": toks.tolist()}
+        out = {"rank": rank, "logits": logits, "tokens": toks.tolist(), "path": tp.path()}
         if rank == 0:
             import oracle as O
 
@@ -67,8 +67,8 @@ def _run(rank, world, mix, q, torch, dist, B, synth, TensorParallelInference, np
         q.put(out)
 
 
-@pytest.mark.parametrize("mix", ["Q4_K_M", "Q8_0"])
-def test_tp2_matches_single_gpu_and_oracle(b200, mix):
+@pytest.mark.parametrize("mix,preset", [("Q4_K_M", "llama-tiny"), ("Q8_0", "llama-tiny"), ("Q4_K_M", "llama-stream-tiny")])
+def test_tp2_matches_single_gpu_and_oracle(b200, mix, preset):
     if b200.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -78,7 +78,7 @@ def test_tp2_matches_single_gpu_and_oracle(b200, mix):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mix, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mix, q, preset)) for r in range(2)]
     for p in procs:
         p.start()
     outs = {}
@@ -90,6 +90,8 @@ def test_tp2_matches_single_gpu_and_oracle(b200, mix):
         p.join(timeout=120)
         assert p.exitcode == 0
     r0, r1 = outs[0], outs[1]
+    # shards whose rows are 16-byte multiples run the streamed megakernel under TP too, the rest the first megakernel
+    assert r0["path"] == r1["path"] == ("stream" if preset == "llama-stream-tiny" or mix == "Q8_0" else "mega")
     assert np.array_equal(r0["logits"], r1["logits"])                      # every rank sees the same gathered logits
     assert synth.rel_err(r0["logits"], r0["want"]) < 1e-3                   # north_star tolerance vs the CPU reference path
     assert synth.rel_err(r0["logits"], r0["single_logits"]) < 1e-4          # summation order differs, nothing else
