@@ -941,9 +941,13 @@ static int mega_build(b200_ctx* c) {
 
 
 // ------------------------------------------------------------------ streamed megakernel (stream.cuh)
-static const void* stream_kernel_for(int hd, int G) {
-    if (hd == 128) return G <= 4 ? (const void*)stream_decode_kernel<128, 4> : (const void*)stream_decode_kernel<128, 8>;
-    return G <= 4 ? (const void*)stream_decode_kernel<64, 4> : (const void*)stream_decode_kernel<64, 8>;
+static const void* stream_kernel_for(int hd, int G, bool tp) {
+    if (tp) {
+        if (hd == 128) return G <= 4 ? (const void*)stream_decode_kernel<128, 4, true> : (const void*)stream_decode_kernel<128, 8, true>;
+        return G <= 4 ? (const void*)stream_decode_kernel<64, 4, true> : (const void*)stream_decode_kernel<64, 8, true>;
+    }
+    if (hd == 128) return G <= 4 ? (const void*)stream_decode_kernel<128, 4, false> : (const void*)stream_decode_kernel<128, 8, false>;
+    return G <= 4 ? (const void*)stream_decode_kernel<64, 4, false> : (const void*)stream_decode_kernel<64, 8, false>;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1026,7 +1030,7 @@ static int stream_build(b200_ctx* c) {
             max_K = std::max(max_K, m.K);
         }
     }
-    const void* kern = stream_kernel_for(hd, G);
+    const void* kern = stream_kernel_for(hd, G, c->par.world_size > 1);
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kern));
     size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn_item_floats(hd, G <= 4 ? 4 : 8, kSW, c->mega_splits, G) * sizeof(float));
@@ -1095,7 +1099,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         sp.n_slots = c->stream_slots;
         sp.no_load = env_int("B200_STREAM_NOLOAD", 0);
         void* sargs[] = {&sp};
-        CU(cudaLaunchCooperativeKernel(stream_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kStreamThreads), sargs,
+        CU(cudaLaunchCooperativeKernel(stream_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads, c->par.world_size > 1), dim3(c->n_sm), dim3(kStreamThreads), sargs,
                                        c->stream_smem, c->stream));
     } else {
         void* args[] = {&mp};

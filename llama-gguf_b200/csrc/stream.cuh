@@ -218,7 +218,7 @@ __device__ __forceinline__ void stream_producer(const StreamParams& sp, const SR
 
 // ---------------------------------------------------------------- consumer side of one GEMV phase
 // seq0: number of ring entries this CTA has consumed before this phase (every consumer thread keeps the same count).
-template <class Pre, class Post>
+template <bool TP, class Pre, class Post>
 __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem, const SRing& rg, uint32_t& seq0, float* s_red,
                                                 float (*s_part)[2][2][32], volatile int* s_dead, Pre pre_fn, Post post_fn) {
     pre_fn();
@@ -262,7 +262,7 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
         if (valid) {
             val += e_bias;
             val += e_res;
-            if (p.n_peer > 0) {
+            if (TP && p.n_peer > 0) {
                 for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;   // partial of a row-parallel GEMV, to every rank (NVLink peer memory)
             } else {
                 sg.out[j] = val;
@@ -343,7 +343,8 @@ __device__ __forceinline__ void stream_gemv_cta(const MParams& p, uint8_t* smem,
         }
     } else {
         XStage xst;
-        const XSource xsrc{p.x, p.xsum, p.n_sum, p.sum_stride, p.x_res, p.x_full_out};   // tensor parallel: x = sum of the ranks' partial vectors (+ residual)
+        // tensor parallel: x = sum of the ranks' partial vectors (+ residual)
+        const XSource xsrc{p.x, TP ? p.xsum : nullptr, TP ? p.n_sum : 0, TP ? p.sum_stride : 0, TP ? p.x_res : nullptr, TP ? p.x_full_out : nullptr};
         stage_x_load(xst, xsrc, p.norm_w, K, kSNT);
         MMA_STAMP(2);
         stage_x_finish(xst, xsrc, p.norm_w, K, smem, s_red, kSNT);
@@ -539,7 +540,9 @@ __device__ __forceinline__ bool s_tp_exchange(const MegaParams& mp, unsigned int
     return *s_flag != 0;
 }
 
-template <int HD, int GMAX>
+// TP = false is the single-GPU instantiation: no tensor-parallel code in it (it cost 3-4 % of the token when it was a
+// run-time branch: registers and instruction footprint)
+template <int HD, int GMAX, bool TP>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const __grid_constant__ StreamParams sp) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long s_bars[2 * kStreamMaxSlots];
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
         bool prev_tp_sync = false;   // the predecessor left partial sums in peer memory
         int stamp = 0;
         auto bar_arrive = [&]() {
-            if (prev_tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
+            if (TP && prev_tp_sync) {  // the CTA's stores to peer memory must be visible system-wide before the barrier says so
                 cons_sync();
                 if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
             }
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
         auto bar_wait = [&]() {
             fetch_desc(gph + 2);
             ok = s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
-            if (prev_tp_sync) ok = s_tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag, &s_dead) && ok;
+            if (TP && prev_tp_sync) ok = s_tp_exchange(mp, mp.tp_epoch0 + (++tp_n), &s_flag, &s_dead) && ok;
             if (mp.dbg && blockIdx.x == 0 && tid == 0) mp.dbg[stamp] = gtimer();
             stamp++;
         };
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
         for (int ph = 0; ph < n_run; ph++, gph++) {
             const MegaPhase& cur = s_phs[gph % 3];
             if (cur.kind == PH_GEMV) {
-                stream_gemv_cta(cur.gemv, smem, rg, seq0, s_red, s_part, &s_dead, bar_arrive, bar_wait);
+                stream_gemv_cta<TP>(cur.gemv, smem, rg, seq0, s_red, s_part, &s_dead, bar_arrive, bar_wait);
             } else {
                 attn_stamp(cur.attn, 0);
                 bar_arrive();
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
                     cons_sync();
                 }
             }
-            prev_tp_sync = cur.tp_sync != 0;
+            if (TP) prev_tp_sync = cur.tp_sync != 0;
         }
         // the barrier that ends the last phase of the token
         gph--;
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
         }
         s_grid_arrive(mp.bar, target);
         s_grid_wait(mp.bar, target, mp.err, &s_flag, &s_dead);
-        const unsigned int cand_epoch = mp.tp_epoch0 + (mp.tp_size > 1 ? ++tp_n : 0u);  // uniform over the grid
+        const unsigned int cand_epoch = mp.tp_epoch0 + ((TP && mp.tp_size > 1) ? ++tp_n : 0u);  // uniform over the grid
         if (blockIdx.x == 0) {
             if (warp == 0) {
                 float best = -INFINITY;
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_decode_kernel(const 
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
                 }
-                if (mp.tp_size > 1) {  // every rank picks the same winner among the per-rank candidates (ties: largest index)
+                if (TP && mp.tp_size > 1) {  // every rank picks the same winner among the per-rank candidates (ties: largest index)
                     bi += mp.tp_rank * mp.vocab_local;
                     if (lane < mp.tp_size) {
                         float* dst = mp.tp_peer_cand[lane] + 2 * mp.tp_rank;
