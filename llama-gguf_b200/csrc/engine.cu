@@ -161,6 +161,9 @@ struct b200_ctx {
     uint8_t* pf_rows = nullptr;      // batched decode: per-row position | KV base pointer | SeqState pointer
     float* pf_logits = nullptr;      // batched decode: [rows][vocab]
     float* pf_split = nullptr;       // split-K partial tiles of the small-T GEMMs
+    void* pf_tmaps = nullptr;        // TMA tensor maps (128-row boxes) of the GEMM weights
+    std::map<const void*, int> pf_tmap_of;
+    bool pf_tmaps_built = false;
     size_t pf_split_floats = 0;
     int pf_logits_rows = 0;
     int batch_gemm_min = 12;   // measured crossover on Llama-3-8B: the GEMM pass costs ~18 ms whatever the row count, a sequence alone 2 ms
@@ -580,6 +583,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_rows);
     cudaFree(c->pf_logits);
     cudaFree(c->pf_split);
+    cudaFree(c->pf_tmaps);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
@@ -1122,6 +1126,51 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
 // 1024-row k / v projections; 47 K floats of activations per token (Llama-3-8B) = 386 MB at 2048
 static int prefill_chunk() { static int v = std::max(32, std::min(4096, env_int("B200_PREFILL_CHUNK", 2048))); return v; }
 
+
+// TMA tensor maps for the dequant-GEMM's weight tiles: box = 128 rows x one 256-element block (stream_pitch(type, 1) bytes).
+// Matrices whose rows are not 16-byte multiples keep the direct global reads.
+static int umma_tmaps_build(b200_ctx* c) {
+    if (c->pf_tmaps_built) return B200_OK;
+    c->pf_tmaps_built = true;
+    if (!env_int("B200_GEMM_TMA", 0)) return B200_OK;   // opt-in until verified on the GPU box
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return B200_OK;
+    }
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
+    std::vector<CUtensorMap> maps;
+    auto add = [&](const DevTensor& w) {
+        if (!w.present() || !umma_type_ok(w.type) || (w.row_bytes & 15) || ((uintptr_t)w.d & 15) || (w.ne[0] % 256)) return;
+        const int pitch = stream_pitch(w.type, 1);
+        CUtensorMap tm;
+        const cuuint64_t dims[2] = {(cuuint64_t)(w.row_bytes / 4), (cuuint64_t)w.ne[1]};
+        const cuuint64_t strides[1] = {(cuuint64_t)w.row_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)(pitch / 4), (cuuint32_t)kUmmaM};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)w.d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+        c->pf_tmap_of[w.d] = (int)maps.size();
+        maps.push_back(tm);
+    };
+    for (const Layer& L : c->layers) { add(L.wq); add(L.wk); add(L.wv); add(L.wo); add(L.gate); add(L.up); add(L.down); }
+    add(c->output.present() ? c->output : c->token_embd);
+    if (maps.empty()) return B200_OK;
+    CU_ALLOC(cudaMalloc(&c->pf_tmaps, maps.size() * sizeof(CUtensorMap)));
+    CU(cudaMemcpy(c->pf_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+static void umma_set_tmap(b200_ctx* c, UmmaParams& p) {
+    p.tmap = nullptr;
+    auto it = c->pf_tmap_of.find(p.w);
+    if (it == c->pf_tmap_of.end() || !c->pf_tmaps) return;
+    p.tmap = (const CUtensorMap*)c->pf_tmaps + it->second;
+    p.raw_pitch = stream_pitch(p.type, 1);
+    p.raw_bytes = 256 / type_block_elems(p.type) * type_block_bytes(p.type);
+}
+
 static bool prefill_gemm_ok(const b200_ctx* c) {
     const b200_model_desc& d = c->d;
     if (!c->use_prefill_gemm || c->par.world_size > 1 || d.n_experts > 0 || c->use_taps) return false;
@@ -1153,6 +1202,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         CU_ALLOC(cudaMalloc((void**)&c->pf_tok, cap * sizeof(int)));
         CU_ALLOC(cudaMalloc((void**)&c->pf_rows, (size_t)cap * 24));
     }
+    { int rc_t = umma_tmaps_build(c); if (rc_t) return rc_t; }
     if (!c->pf_split) {   // split-K scratch for passes of <= 64 rows: 8 partial tiles of the widest projection
         c->pf_split_floats = (size_t)8 * 64 * std::max(std::max(I, QKV), H);
         CU_ALLOC(cudaMalloc((void**)&c->pf_split, c->pf_split_floats * sizeof(float)));
@@ -1197,6 +1247,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         p.x = x; p.ldx = ldx; p.T = T; p.y = y; p.ldy = ldy;
         p.bias = (bias && bias->present()) ? bias->f32() : nullptr;
         p.accumulate = acc; p.err = c->mma_err;
+        umma_set_tmap(c, p);
         umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
         c->launches += p.k_split ? 2 : 1;
         return umma_launch(p, st);
@@ -1252,6 +1303,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         UmmaParams hp{};
         hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = d.vocab; hp.K = H;
         hp.x = XNh; hp.ldx = H; hp.T = n; hp.y = c->pf_logits; hp.ldy = d.vocab; hp.err = c->mma_err;
+        umma_set_tmap(c, hp);
         CU(umma_launch(hp, st));
         c->launches += 3;
         return B200_OK;
