@@ -24,7 +24,11 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemv.cuh"
+#ifdef B200_GEMM_TMA_EXPERIMENT
+#include "gemm_umma_tma.cuh"   // TMA-fed weight tiles: not yet verified on a GPU (see the file header)
+#else
 #include "gemm_umma.cuh"
+#endif
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -1127,6 +1131,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
 static int prefill_chunk() { static int v = std::max(32, std::min(4096, env_int("B200_PREFILL_CHUNK", 2048))); return v; }
 
 
+#ifdef B200_GEMM_TMA_EXPERIMENT
 // TMA tensor maps for the dequant-GEMM's weight tiles: box = 128 rows x one 256-element block (stream_pitch(type, 1) bytes).
 // Matrices whose rows are not 16-byte multiples keep the direct global reads.
 static int umma_tmaps_build(b200_ctx* c) {
@@ -1170,6 +1175,11 @@ static void umma_set_tmap(b200_ctx* c, UmmaParams& p) {
     p.raw_pitch = stream_pitch(p.type, 1);
     p.raw_bytes = 256 / type_block_elems(p.type) * type_block_bytes(p.type);
 }
+
+#else
+static int umma_tmaps_build(b200_ctx*) { return B200_OK; }
+static void umma_set_tmap(b200_ctx*, UmmaParams&) {}
+#endif
 
 static bool prefill_gemm_ok(const b200_ctx* c) {
     const b200_model_desc& d = c->d;
