@@ -8,6 +8,8 @@
 //
 // One CTA (128 threads) per (128 weight rows, TN tokens) output tile.  Per K step of 64 elements (128 bytes of fp16 =
 // one row of a 128B-swizzle atom):
+//   * (small T, TMA-fed: one cp.async.bulk.tensor.2d box of 128 rows x one 256-element GGUF block per row lands in a
+//     two-stage raw buffer per 4 K steps, and the threads read their row from shared memory; large T: straight from global)
 //   * thread r dequantises 64 elements of ITS weight row in registers with the reference arithmetic in f32
 //     (dequant.rs:205-356: d*sc*q - dmin*m, (d*sc)*q for Q6_K, q*d for Q8_0), rounds to fp16 and writes the row's eight
 //     16-byte chunks into the K-major SWIZZLE_128B shared-memory tile (chunk c of row r at chunk c ^ (r & 7));
@@ -29,6 +31,7 @@ namespace b200 {
 
 constexpr int kUmmaM = 128;   // weight rows per CTA
 constexpr int kUmmaK = 64;    // K elements per step
+constexpr int kUmmaRawStage = kUmmaM * 272;   // raw (quantised) tile of 128 rows x one 256-element block, widest type
 
 __device__ __forceinline__ uint32_t umma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,24 +73,31 @@ __device__ __forceinline__ uint32_t umma_pack_h2(float a, float b) {
 __device__ __forceinline__ uint32_t umma_sw128(int r, int c) {
     return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
 }
-__device__ __forceinline__ uint32_t umma_ld16(const uint8_t* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
+// weight bytes come either straight from global memory (read-only path) or from the raw tile a TMA load left in shared memory
+template <bool SM, class T>
+__device__ __forceinline__ T umma_ldw(const T* p) {
+    if constexpr (SM) return *p; else return __ldg(p);
+}
+template <bool SM>
+__device__ __forceinline__ uint32_t umma_ld16(const uint8_t* p) { return (uint32_t)umma_ldw<SM>(reinterpret_cast<const unsigned short*>(p)); }
 
 // Eight consecutive elements k0 + 8c .. k0 + 8c + 7 (k0 % 64 == 0) of the weight row `row`, as four packed half2.
+template <bool SM>
 __device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0, int c) {
     float v[8];
     if (type == T_Q4_K || type == T_Q5_K) {   // dequant.rs:205-315
         const bool q5 = type == T_Q5_K;
         const uint8_t* blk = row + (long long)(k0 >> 8) * (q5 ? 176 : 144);
         const int gp = (k0 & 255) >> 6, hi = c >> 2;        // sub-block 2gp (low nibbles) or 2gp + 1 (high nibbles)
-        const uint32_t dd = __ldg(reinterpret_cast<const uint32_t*>(blk));
+        const uint32_t dd = umma_ldw<SM>(reinterpret_cast<const uint32_t*>(blk));
         const float d = half_bits_to_float(dd), dmin = half_bits_to_float(dd >> 16);
         int sc, mn;
         scale_min_k4(blk + 4, 2 * gp + hi, sc, mn);
         const float d1 = __fmul_rn(d, (float)sc), m1 = __fmul_rn(dmin, (float)mn);
         const uint8_t* qs = blk + (q5 ? 48 : 16) + 32 * gp + 8 * (c & 3);
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(qs));
+        const uint2 w = umma_ldw<SM>(reinterpret_cast<const uint2*>(qs));
         uint2 h = make_uint2(0u, 0u);
-        if (q5) h = __ldg(reinterpret_cast<const uint2*>(blk + 16 + 8 * (c & 3)));
+        if (q5) h = umma_ldw<SM>(reinterpret_cast<const uint2*>(blk + 16 + 8 * (c & 3)));
         const int sh = 4 * hi, hb = 2 * gp + hi;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -99,14 +109,14 @@ __device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0,
     } else if (type == T_Q6_K) {   // dequant.rs:321-356; blocks are only 2-byte aligned
         const uint8_t* blk = row + (long long)(k0 >> 8) * 210;
         const int ks = (k0 & 255) >> 6, n = ks >> 1, qq = 2 * (ks & 1) + (c >> 2), l0 = 8 * (c & 3);
-        const float d = half_bits_to_float(umma_ld16(blk + 208));
-        const int sc = (int)(signed char)__ldg(blk + 192 + 8 * n + (l0 >> 4) + 2 * qq);
+        const float d = half_bits_to_float(umma_ld16<SM>(blk + 208));
+        const int sc = (int)(signed char)umma_ldw<SM>(blk + 192 + 8 * n + (l0 >> 4) + 2 * qq);
         const float ds = __fmul_rn(d, (float)sc);
         const uint8_t* ql = blk + 64 * n + 32 * (qq & 1) + l0;
         const uint8_t* qh = blk + 128 + 32 * n + l0;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-            const uint32_t a = umma_ld16(ql + i), b = umma_ld16(qh + i);
+            const uint32_t a = umma_ld16<SM>(ql + i), b = umma_ld16<SM>(qh + i);
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const uint32_t lo = (a >> (8 * j + 4 * (qq >> 1))) & 15u, hb = (b >> (8 * j + 2 * qq)) & 3u;
@@ -115,11 +125,11 @@ __device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0,
         }
     } else {   // Q8_0, dequant.rs:103-109
         const uint8_t* blk = row + (long long)((k0 >> 5) + (c >> 2)) * 34;
-        const float d = half_bits_to_float(umma_ld16(blk));
+        const float d = half_bits_to_float(umma_ld16<SM>(blk));
         const uint8_t* q = blk + 2 + 8 * (c & 3);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-            const uint32_t a = umma_ld16(q + i);
+            const uint32_t a = umma_ld16<SM>(q + i);
             v[i] = __fmul_rn((float)(int)(signed char)(a & 255u), d);
             v[i + 1] = __fmul_rn((float)(int)(signed char)(a >> 8), d);
         }
@@ -129,10 +139,11 @@ __device__ __forceinline__ uint4 umma_deq8(int type, const uint8_t* row, int k0,
 
 // Q4_K, 16-byte aligned rows: the 64 elements k0 .. k0 + 63 of a row are the low and high nibbles of 32 consecutive qs
 // bytes (one scale / min pair each): header and scales decoded once, two 16-byte loads, written as the row's 8 chunks.
+template <bool SM>
 __device__ __forceinline__ void umma_deq64_q4k(const uint8_t* row, int k0, uint8_t* sA, int r) {
     const uint8_t* blk = row + (long long)(k0 >> 8) * 144;
     const int gp = (k0 & 255) >> 6;
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(blk));   // d | dmin, scales[12]
+    const uint4 hdr = umma_ldw<SM>(reinterpret_cast<const uint4*>(blk));   // d | dmin, scales[12]
     const float d = half_bits_to_float(hdr.x), dmin = half_bits_to_float(hdr.x >> 16);
     const uint8_t sc[12] = {(uint8_t)hdr.y, (uint8_t)(hdr.y >> 8), (uint8_t)(hdr.y >> 16), (uint8_t)(hdr.y >> 24),
                             (uint8_t)hdr.z, (uint8_t)(hdr.z >> 8), (uint8_t)(hdr.z >> 16), (uint8_t)(hdr.z >> 24),
@@ -142,7 +153,7 @@ __device__ __forceinline__ void umma_deq64_q4k(const uint8_t* row, int k0, uint8
     scale_min_k4(sc, 2 * gp + 1, s2, m2);
     const float d1 = __fmul_rn(d, (float)s1), mm1 = __fmul_rn(dmin, (float)m1), d2 = __fmul_rn(d, (float)s2), mm2 = __fmul_rn(dmin, (float)m2);
     const uint4* q4 = reinterpret_cast<const uint4*>(blk + 16 + 32 * gp);
-    const uint4 qa = __ldg(q4), qb = __ldg(q4 + 1);
+    const uint4 qa = umma_ldw<SM>(q4), qb = umma_ldw<SM>(q4 + 1);
     const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
     for (int c = 0; c < 4; c++) {   // chunk c: elements 8c..8c+7 (low nibbles), chunk 4 + c: elements 32 + 8c.. (high nibbles)
@@ -181,12 +192,17 @@ struct UmmaParams {
     int k_split;         // 0 = no split
     float* part;
     int* err;            // watchdog word (set to 5 if the MMA completion never arrives)
+    // TMA-fed weights: tensor map of the matrix ([n_rows][row_bytes / 4] UINT32, box = 128 rows x raw_pitch bytes = one
+    // 256-element block per row); nullptr = the threads read their rows straight from global memory
+    const void* tmap;
+    int raw_pitch;       // bytes between the rows of a raw tile
+    int raw_bytes;       // bytes of 256 elements of one row (144 / 176 / 210 / 272)
 };
 
 template <int TN>
 __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams p) {
     extern __shared__ __align__(1024) uint8_t umma_smem[];
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar[4];   // [0,1]: MMA commits per fp16 stage, [2,3]: TMA raw tiles
     __shared__ uint32_t s_tmem;
     constexpr int kStageBytes = (kUmmaM + TN) * 128;
     uint8_t* base = umma_smem + ((1024u - (umma_smem_u32(umma_smem) & 1023u)) & 1023u);   // the swizzle pattern is on absolute address bits
@@ -199,7 +215,10 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 16u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 24u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma_smem_u32(&s_tmem)), "n"(kCols) : "memory");
@@ -218,6 +237,26 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
     const bool q4_fast = p.type == T_Q4_K && !(((uintptr_t)p.w | (uintptr_t)p.row_bytes) & 15);
     int it = 0;
     const int kb = p.k_split ? (int)blockIdx.z * p.k_split : 0, ke = p.k_split ? min(p.K, kb + p.k_split) : p.K;
+    // TMA-fed weights: one box of 128 rows x one 256-element block per row lands in a raw stage while the previous block is
+    // dequantised from the other one (the per-thread global reads of a row are 2304 bytes apart: uncoalesced and latency
+    // bound, which is what held small-T passes at ~250 GB/s)
+    const bool tma = p.tmap != nullptr;
+    uint8_t* sRaw = sB + 2 * kStageBytes - kUmmaM * 128;   // after the two fp16 stages
+    uint32_t rph0 = 0, rph1 = 0;
+    auto raw_issue = [&](int blk) {   // tid 0 only
+        const int st = blk & 1;
+        const uint32_t rb = bar + 16u + 8u * st;
+        const int start = blk * p.raw_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rb), "r"(p.raw_pitch * kUmmaM) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         umma_smem_u32(sRaw + st * kUmmaRawStage)),
+                     "l"(p.tmap), "r"((start & ~15) >> 2), "r"(row0), "r"(rb)
+                     : "memory");
+    };
+    if (tma && tid == 0) {
+        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(p.tmap) : "memory");
+        raw_issue(kb >> 8);
+    }
     for (int k0 = kb; k0 < ke; k0 += kUmmaK, it++) {
         const int sidx = it & 1;
         uint8_t* tA = sA + sidx * kStageBytes;
@@ -229,11 +268,27 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
             }
             if (sidx) ph1 ^= 1u; else ph0 ^= 1u;
         }
-        if (q4_fast) {
-            umma_deq64_q4k(wrow, k0, tA, tid);
+        if (tma) {
+            const int blk = k0 >> 8, st = blk & 1;
+            if ((k0 & 255) == 0) {   // first step of a block: its raw tile must have landed
+                if (alive && !umma_mbar_wait(bar + 16u + 8u * st, st ? rph1 : rph0)) {
+                    alive = false;
+                    if (p.err) atomicExch(p.err, 6);
+                }
+                if (st) rph1 ^= 1u; else rph0 ^= 1u;
+            }
+            const uint8_t* rrow = sRaw + st * kUmmaRawStage + tid * p.raw_pitch + ((blk * p.raw_bytes) & 15);
+            if (p.type == T_Q4_K) {
+                umma_deq64_q4k<true>(rrow, k0 & 255, tA, tid);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tA + umma_sw128(tid, c)) = umma_deq8<true>(p.type, rrow, k0 & 255, c);
+            }
+        } else if (q4_fast) {
+            umma_deq64_q4k<false>(wrow, k0, tA, tid);
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tA + umma_sw128(tid, c)) = umma_deq8(p.type, wrow, k0, c);
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tA + umma_sw128(tid, c)) = umma_deq8<false>(p.type, wrow, k0, c);
         }
         {
             constexpr int NB = TN * 8 / 128;   // 16-byte chunks of the activation tile per thread
@@ -251,6 +306,7 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncthreads();
+        if (tma && tid == 0 && (k0 & 255) == 0 && k0 + 256 < ke) raw_issue((k0 >> 8) + 1);   // everybody is past the previous block: its stage is free
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t da = umma_desc(umma_smem_u32(tA)), db = umma_desc(umma_smem_u32(tB));
@@ -328,10 +384,11 @@ inline bool umma_eligible(const UmmaParams& p) {
 }
 template <int TN>
 inline cudaError_t umma_launch_tn(const UmmaParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)2 * (kUmmaM + TN) * 128 + 1024;   // two stages
-    static bool once = false;   // per instantiation
+    const size_t smem = (size_t)2 * (kUmmaM + TN) * 128 + (p.tmap ? 2 * kUmmaRawStage : 0) + 1024;   // two fp16 stages (+ two raw stages)
+    static bool once = false;   // per instantiation: the larger of the two layouts
     if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(dequant_gemm_umma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dequant_gemm_umma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)2 * (kUmmaM + TN) * 128 + 2 * kUmmaRawStage + 1024));
         if (e != cudaSuccess) return e;
         once = true;
     }

@@ -65,7 +65,7 @@ def test_short_prompts_and_disabled_gemm_stay_exact(b200, oracle):
 
 @pytest.mark.parametrize("preset,mix", [("llama-tiny", "Q4_K_M"), ("qwen-kq-tiny", "Q5_K_M")])
 def test_batched_decode_through_the_gemm(b200, oracle, preset, mix):
-    """b200_decode_batch with >= 12 sequences: one pass of the dequant-GEMMs for all rows, each row at ITS slot's position
+    """b200_decode_batch with >= 8 sequences: one pass of the dequant-GEMMs for all rows, each row at ITS slot's position
     and on ITS slot's KV cache.  Same fp16 tolerance as the GEMM prefill."""
     nseq = 12
     arch, desc, tensors = synth.synth_model(preset, mix, 64, max_batch=nseq)
