@@ -425,10 +425,10 @@ class GpuOnlyInference:
             pass
 
     def path(self):
-        """Decode path chosen at finalize: "graph" | "mega" | "stream"."""
+        """Decode path chosen at finalize: "graph" | "mega" | "stream" | "stream2"."""
         v = C.c_int(0)
         _check(lib().b200_ctx_path(self._h, C.byref(v)))
-        return ("graph", "mega", "stream")[v.value]
+        return ("graph", "mega", "stream", "stream2")[v.value]
 
     def watchdog(self):
         """The eight watchdog words of the megakernel paths (all zero = no bounded wait ever gave up); clears them."""

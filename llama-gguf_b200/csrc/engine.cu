@@ -31,6 +31,7 @@
 #include "prefill.cuh"
 #include "quant.cuh"
 #include "stream.cuh"
+#include "stream2.cuh"
 
 using namespace b200;
 
@@ -98,6 +99,7 @@ struct Slot {
     cudaGraphExec_t graph[MODE_COUNT] = {nullptr, nullptr, nullptr};
     uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
     MegaPhase* d_phases = nullptr;  // per-token megakernel program of this slot (mega.cuh)
+    MegaPhase* d_phases2 = nullptr; // the same program for stream2.cuh: EMBED phase first
 };
 
 constexpr int kMaxGenerated = 1 << 16;
@@ -140,6 +142,14 @@ struct b200_ctx {
     unsigned long long* mega_dbg = nullptr;
     // streamed megakernel (stream.cuh): TMA tensor maps of the weight matrices, ring geometry
     bool use_stream = true, stream_ok = false;
+    // second streamed megakernel (stream2.cuh)
+    bool use_stream2 = true, stream2_ok = false;
+    int s2_phases = 0, s2_xr_off = 0, s2_tpart_off = 0, s2_desc_off = 0, s2_ring_off = 0, s2_slots = 0;
+    size_t s2_smem = 0;
+    uint2* s2_ll = nullptr;
+    unsigned int s2_epoch = 0;
+    float* s2_cand_val = nullptr;
+    int* s2_cand_idx = nullptr;
     void* d_tmaps = nullptr;
     size_t stream_smem = 0;
     int stream_ring_off = 0, stream_slots = 0;
@@ -255,6 +265,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_mma = env_int("B200_GEMV_MMA", 1) != 0;
     c->use_mega = env_int("B200_MEGA", 1) != 0;
     c->use_stream = env_int("B200_STREAM", 1) != 0;
+    c->use_stream2 = env_int("B200_STREAM2", 1) != 0;
     c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
@@ -569,6 +580,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         cudaFree(s.d_generated);
         cudaFree(s.kv);
         cudaFree(s.d_phases);
+        cudaFree(s.d_phases2);
     }
     for (int r = 0; r < c->par.world_size && r < kMmaMaxPeers; r++)
         if (r != c->par.rank && c->tp_peer[r]) cudaIpcCloseMemHandle(c->tp_peer[r]);
@@ -765,6 +777,7 @@ static const void* mega_kernel_for(int hd, int G) {
 }
 
 static int stream_build(b200_ctx* c);
+static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs, int max_K);
 
 // Builds the phase program of every slot.  Leaves mega_ok = false (graph path) when a launch is not eligible:
 // MoE, taps, a weight type/shape the tensor-pipe GEMV does not take, or a shape that does not fit shared memory.
@@ -998,6 +1011,17 @@ static int stream_build(b200_ctx* c) {
                 const int per_cta = (tiles_all + c->n_sm - 1) / c->n_sm;
                 const int entries = per_cta * (m.epi == ME_SWIGLU ? 2 : 1) * ((m.chunks + C - 1) / C);
                 if (C > 1 && entries < env_int("B200_STREAM_MIN_ENTRIES", 0)) C = 1;
+                if (C > 1 && c->use_stream2 && c->par.world_size == 1) {
+                    // stream2.cuh deals entries evenly to CTAs and round-robin to 7 warp pairs: take the entry size whose
+                    // last round is fullest (gate/up of Llama-3-8B: 48.4 two-chunk entries per CTA = 6.9 rounds; down:
+                    // 24.2 = 3.5 rounds -> one-chunk entries, 6.9 rounds)
+                    auto waste = [&](int cc) {
+                        const double per = (double)tiles_all * (m.epi == ME_SWIGLU ? 2 : 1) * ((m.chunks + cc - 1) / cc) / c->n_sm;
+                        return std::ceil(per / kS2Pairs) * kS2Pairs / std::max(per, 1e-9);
+                    };
+                    const int force = env_int("B200_S2_C", 0);
+                    if (force == 1 || (force == 0 && waste(1) + 0.02 < waste(C))) C = 1;
+                }
             }
             for (int s = 0; s < m.n_seg; s++) {
                 MSeg& sg = m.seg[s];
@@ -1066,6 +1090,83 @@ static int stream_build(b200_ctx* c) {
     c->stream_slots = slots;
     c->stream_ok = true;
     if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: ok, %d slots, ring_off %d, smem %zu, %zu tensor maps\n", slots, (int)x_region, smem, maps.size());
+    return stream2_build(c, progs, max_K);
+}
+
+static const void* stream2_kernel_for(int hd, int G) {
+    if (hd == 128) return G <= 4 ? (const void*)stream2_decode_kernel<128, 4> : (const void*)stream2_decode_kernel<128, 8>;
+    return G <= 4 ? (const void*)stream2_decode_kernel<64, 4> : (const void*)stream2_decode_kernel<64, 8>;
+}
+
+// Upgrades the (stream-eligible) phase programs to the second streamed megakernel: single GPU, dense.  The program gets an
+// EMBED phase in front (CTA 0: pick of the previous token in greedy mode, embedding row, its staged form for layer 0's
+// QKV), every GEMV reads a staged input, the vocab head collects argmax candidates.  Leaves stream2_ok = false otherwise.
+static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs, int max_K) {
+    const b200_model_desc& d = c->d;
+    c->stream2_ok = false;
+    if (!c->use_stream2 || c->par.world_size > 1 || !c->mega_stage[0]) return B200_OK;
+    const int hd = d.head_dim, G = d.n_heads / d.n_kv_heads, gmax = G <= 4 ? 4 : 8;
+    const void* kern = stream2_kernel_for(hd, G);
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kern));
+    size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn2_smem_floats(hd, gmax, kS2Cons, c->mega_splits, G) * sizeof(float));
+    x_region = (x_region + 127) & ~(size_t)127;
+    const size_t xr_off = kS2ZeroBytes;
+    const size_t tpart_off = xr_off + x_region;
+    const size_t desc_off = tpart_off + (size_t)kS2TileSlots * kS2Cons * 2 * 32 * sizeof(float);
+    const size_t ring_off = (desc_off + 2 * sizeof(MegaPhase) + 127) & ~(size_t)127;
+    const size_t avail = c->smem_optin - fa.sharedSizeBytes;
+    if (avail < ring_off + (size_t)(kS2Pairs + 1) * kS2SlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: not eligible (shared memory)\n"); return B200_OK; }
+    int slots = (int)std::min<size_t>(kS2MaxSlots, (avail - ring_off) / kS2SlotBytes);
+    slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kS2MaxSlots)));
+    if (slots <= kS2Pairs) return B200_OK;   // the parity protocol needs more slots than consumer pairs
+    const size_t smem = ring_off + (size_t)slots * kS2SlotBytes;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kS2Threads, smem));
+    if (per_sm < 1) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: not eligible (occupancy)\n"); return B200_OK; }
+    if (!c->s2_ll) {
+        CU_ALLOC(cudaMalloc((void**)&c->s2_ll, (size_t)c->n_sm * 64 * sizeof(uint2)));
+        CU(cudaMemset(c->s2_ll, 0, (size_t)c->n_sm * 64 * sizeof(uint2)));
+        CU_ALLOC(cudaMalloc((void**)&c->s2_cand_val, (size_t)c->n_sm * kS2Cons * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->s2_cand_idx, (size_t)c->n_sm * kS2Cons * sizeof(int)));
+        CU(cudaMemset(c->s2_cand_idx, 0xff, (size_t)c->n_sm * kS2Cons * sizeof(int)));
+        CU(cudaMemset(c->s2_cand_val, 0, (size_t)c->n_sm * kS2Cons * sizeof(float)));
+    }
+    const int min_chunk2 = env_int("B200_ATTN_MIN_CHUNK", 256);
+    for (size_t si = 0; si < c->slots.size(); si++) {
+        std::vector<MegaPhase> prog2;
+        MegaPhase em{};
+        em.kind = PH_EMBED;
+        em.gemv.stage_out = c->mega_stage[0];
+        em.gemv.stage_w = c->layers[0].attn_norm.f32();
+        em.gemv.stage_K = d.hidden;
+        prog2.push_back(em);
+        for (size_t pi = 0; pi < progs[si].size(); pi++) {
+            MegaPhase ph = progs[si][pi];
+            if (ph.kind == PH_GEMV) {
+                MParams& m = ph.gemv;
+                m.x_staged = pi == 0 ? c->mega_stage[0] : m.x_staged;   // layer 0's QKV reads the staged embedding row
+                if (!m.x_staged) return B200_OK;
+                m.s_E = m.s_tiles * m.s_parts * m.s_ept;
+                m.cand = (pi + 1 == progs[si].size()) ? 1 : 0;
+            } else {
+                ph.attn.min_chunk = min_chunk2;
+            }
+            prog2.push_back(ph);
+        }
+        Slot& sl = c->slots[si];
+        if (sl.d_phases2) cudaFree(sl.d_phases2);
+        sl.d_phases2 = nullptr;
+        CU_ALLOC(cudaMalloc((void**)&sl.d_phases2, prog2.size() * sizeof(MegaPhase)));
+        CU(cudaMemcpy(sl.d_phases2, prog2.data(), prog2.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+        c->s2_phases = (int)prog2.size();
+    }
+    c->s2_xr_off = (int)xr_off; c->s2_tpart_off = (int)tpart_off; c->s2_desc_off = (int)desc_off; c->s2_ring_off = (int)ring_off;
+    c->s2_slots = slots;
+    c->s2_smem = smem;
+    c->stream2_ok = true;
+    if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: ok, %d slots, x region %zu, ring_off %zu, smem %zu, %d phases, %d regs\n", slots, x_region, ring_off, smem, c->s2_phases, fa.numRegs);
     return B200_OK;
 }
 
@@ -1096,7 +1197,22 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         c->tp_epoch += (unsigned int)(per_token * n_tokens);
     }
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
-    if (c->stream_ok) {
+    if (c->stream2_ok) {
+        Stream2Params sp{};
+        sp.mp = mp;
+        sp.mp.phases = sl.d_phases2;
+        sp.mp.n_phases = c->s2_phases;
+        sp.xr_off = c->s2_xr_off; sp.tpart_off = c->s2_tpart_off; sp.desc_off = c->s2_desc_off; sp.ring_off = c->s2_ring_off;
+        sp.n_slots = c->s2_slots;
+        sp.no_load = env_int("B200_STREAM_NOLOAD", 0);
+        sp.ll = c->s2_ll;
+        sp.epoch0 = c->s2_epoch;
+        c->s2_epoch += (unsigned int)(n_tokens * c->s2_phases + 2);
+        sp.cand_val = c->s2_cand_val; sp.cand_idx = c->s2_cand_idx;
+        void* sargs[] = {&sp};
+        CU(cudaLaunchCooperativeKernel(stream2_kernel_for(d.head_dim, d.n_heads / d.n_kv_heads), dim3(c->n_sm), dim3(kS2Threads), sargs, c->s2_smem,
+                                       c->stream));
+    } else if (c->stream_ok) {
         StreamParams sp{};
         sp.mp = mp;
         sp.ring_off = c->stream_ring_off;
@@ -1565,7 +1681,7 @@ extern "C" int b200_get_hidden(b200_ctx* c, int seq, int layer, float* out) {
 extern "C" int b200_debug_mega_timeline(b200_ctx* c, unsigned long long* out, int max_n) {
     if (!c || !c->mega_ok) return 0;
     cudaSetDevice(c->par.device);
-    const int n = c->mega_phases + 1;
+    const int n = (c->stream2_ok ? c->s2_phases : c->mega_phases) + 1;
     if (!c->mega_dbg) {
         if (cudaMalloc((void**)&c->mega_dbg, (size_t)(n + 2) * 8) != cudaSuccess) return 0;
         cudaMemset(c->mega_dbg, 0, (size_t)(n + 2) * 8);
@@ -1620,10 +1736,10 @@ extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* 
 }
 
 // Which decode path finalize selected: 0 = CUDA graph of per-op kernels, 1 = per-token megakernel (mega.cuh),
-// 2 = streamed megakernel (stream.cuh).
+// 2 = streamed megakernel (stream.cuh), 3 = second streamed megakernel (stream2.cuh).
 extern "C" int b200_ctx_path(b200_ctx* c, int* out) {
     if (!c || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_path: null argument");
-    *out = c->mega_ok ? (c->stream_ok ? 2 : 1) : 0;
+    *out = c->mega_ok ? (c->stream2_ok ? 3 : c->stream_ok ? 2 : 1) : 0;
     return B200_OK;
 }
 

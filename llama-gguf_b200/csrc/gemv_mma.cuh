@@ -84,6 +84,9 @@ struct MParams {
     // streamed megakernel: a ring entry is 32 rows x s_C chunks; a tile (x matrix part) is s_ept entries; whole tiles
     // are dealt to CTAs: CTA b (rotated by s_rot) owns s_cbase (+1 for the first s_crem) tiles of the s_tiles logical ones
     int s_C, s_ept, s_parts, s_tiles, s_ncta, s_cbase, s_crem, s_rot;
+    // second streamed megakernel (stream2.cuh): s_E = s_tiles * s_parts * s_ept ring entries, dealt to CTAs as equal contiguous
+    // ranges; cand: (vocab head, greedy mode) collect argmax candidates in the epilogue instead of storing the logits
+    int s_E, cand;
     const float* x;        // [K] f32
     // Producer-staged input (per-token megakernel, single GPU): the phase that produced x also wrote its int8 planes,
     // group scales / sums and per-group sums of squares (stage_out32); this launch copies them instead of converting

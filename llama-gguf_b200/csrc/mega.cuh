@@ -26,7 +26,7 @@ namespace b200 {
 enum : int { PH_GEMV = 0, PH_ATTN = 1 };
 enum : int { MEGA_LOGITS = 0, MEGA_PREFILL = 1, MEGA_GREEDY = 2 };
 
-struct MegaPhase {
+struct alignas(16) MegaPhase {   // 16-byte multiple: stream2.cuh moves descriptors with cp.async.bulk
     int kind;
     int tp_sync;   // tensor parallel: the phase wrote partial sums to the peers; exchange flags before the next one
     int pad[2];
