@@ -1012,15 +1012,9 @@ static int stream_build(b200_ctx* c) {
                 const int entries = per_cta * (m.epi == ME_SWIGLU ? 2 : 1) * ((m.chunks + C - 1) / C);
                 if (C > 1 && entries < env_int("B200_STREAM_MIN_ENTRIES", 0)) C = 1;
                 if (C > 1 && c->use_stream2 && c->par.world_size == 1) {
-                    // stream2.cuh deals entries evenly to CTAs and round-robin to 7 warp pairs: take the entry size whose
-                    // last round is fullest (gate/up of Llama-3-8B: 48.4 two-chunk entries per CTA = 6.9 rounds; down:
-                    // 24.2 = 3.5 rounds -> one-chunk entries, 6.9 rounds)
-                    auto waste = [&](int cc) {
-                        const double per = (double)tiles_all * (m.epi == ME_SWIGLU ? 2 : 1) * ((m.chunks + cc - 1) / cc) / c->n_sm;
-                        return std::ceil(per / kS2Pairs) * kS2Pairs / std::max(per, 1e-9);
-                    };
-                    const int force = env_int("B200_S2_C", 0);
-                    if (force == 1 || (force == 0 && waste(1) + 0.02 < waste(C))) C = 1;
+                    // stream2.cuh deals work as jobs = (entry, chunk): two-chunk entries halve the TMA operations the single producer
+                    // thread has to issue without coarsening the deal; every entry must then have both chunks
+                    if ((m.chunks & 1) || env_int("B200_S2_C", 0) == 1) C = 1;
                 }
             }
             for (int s = 0; s < m.n_seg; s++) {
@@ -1116,10 +1110,11 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
     const size_t desc_off = tpart_off + (size_t)kS2TileSlots * kS2Cons * 2 * 32 * sizeof(float);
     const size_t ring_off = (desc_off + 2 * sizeof(MegaPhase) + 127) & ~(size_t)127;
     const size_t avail = c->smem_optin - fa.sharedSizeBytes;
-    if (avail < ring_off + (size_t)(kS2Pairs + 1) * kS2SlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: not eligible (shared memory)\n"); return B200_OK; }
+    if (avail < ring_off + (size_t)kS2Cons * kS2SlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: not eligible (shared memory)\n"); return B200_OK; }
     int slots = (int)std::min<size_t>(kS2MaxSlots, (avail - ring_off) / kS2SlotBytes);
     slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kS2MaxSlots)));
-    if (slots <= kS2Pairs) return B200_OK;   // the parity protocol needs more slots than consumer pairs
+    slots = slots / kS2Cons * kS2Cons;       // a multiple of 14: a slot always serves the same consumer warps (no parity aliasing)
+    if (slots < kS2Cons) return B200_OK;
     const size_t smem = ring_off + (size_t)slots * kS2SlotBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -1133,7 +1128,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
         CU(cudaMemset(c->s2_cand_idx, 0xff, (size_t)c->n_sm * kS2Cons * sizeof(int)));
         CU(cudaMemset(c->s2_cand_val, 0, (size_t)c->n_sm * kS2Cons * sizeof(float)));
     }
-    const int min_chunk2 = env_int("B200_ATTN_MIN_CHUNK", 256);
+    const int min_chunk2 = env_int("B200_ATTN_MIN_CHUNK", 32);   // measured: 11.5 us per layer at kv_len 144 with 32, 16.7 with 256
     for (size_t si = 0; si < c->slots.size(); si++) {
         std::vector<MegaPhase> prog2;
         MegaPhase em{};
@@ -1150,6 +1145,23 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                 if (!m.x_staged) return B200_OK;
                 m.s_E = m.s_tiles * m.s_parts * m.s_ept;
                 m.cand = (pi + 1 == progs[si].size()) ? 1 : 0;
+                {   // jobs per entry (stream2.cuh): the coarsest split whose last round of the 14 consumer warps is (nearly) as full as the best
+                    const double per = (double)m.s_E / c->n_sm;
+                    auto waste = [&](int n) { return std::ceil(per * n / kS2Cons) * kS2Cons / std::max(per * n, 1e-9); };
+                    const int cand_J[3] = {1, m.s_C == 2 ? 2 : 1, m.s_C == 2 ? 2 : 1}, cand_R[3] = {1, 1, 2};
+                    double best = 1e9;
+                    const int n_cand = kS2Cons == 8 ? 2 : 3;   // (8 fat consumers: whole units only)
+                    for (int k = 0; k < n_cand; k++) best = std::min(best, waste(cand_J[k] * cand_R[k]));
+                    int pick = n_cand - 1;
+                    for (int k = 0; k < n_cand; k++)
+                        if (waste(cand_J[k] * cand_R[k]) <= best + 0.04) { pick = k; break; }
+                    const int force = env_int("B200_S2_JOBS", 0);   // 1, 2 or 4 jobs per entry
+                    if (force == 1) pick = 0; else if (force == 2) pick = 1; else if (force == 4 && n_cand == 3) pick = 2;
+                    m.s_J = cand_J[pick]; m.s_R = cand_R[pick];
+                    m.s_jsh = (m.s_J == 2 ? 1 : 0) + (m.s_R == 2 ? 1 : 0);
+                    if (env_int("B200_LOG", 0) && si == 0 && pi < 6) fprintf(stderr, "[b200] stream2 phase %zu: E %d (%.1f per CTA), C %d, jobs per entry %d x %d, waste %.3f\n", pi, m.s_E, per, m.s_C, m.s_J, m.s_R, waste(m.s_J * m.s_R));
+                }
+                m.x_bytes = (int)x_staged_bytes(m.K);
             } else {
                 ph.attn.min_chunk = min_chunk2;
             }
@@ -1699,17 +1711,18 @@ extern "C" int b200_debug_mega_phase(b200_ctx* c, int phase, unsigned long long*
     if (!c || !c->mega_ok) return 0;
     cudaSetDevice(c->par.device);
     static unsigned long long* buf = nullptr;
-    const size_t n = (size_t)c->n_sm * kMmaMaxWarps * 8;
+    const size_t n = (size_t)c->n_sm * 16 * 8;
     if (!buf && cudaMalloc((void**)&buf, n * 8) != cudaSuccess) return 0;
     cudaStreamSynchronize(c->stream);
     if (phase >= 0) {
-        if (phase >= c->mega_phases) return 0;
+        MegaPhase* prog = c->stream2_ok ? c->slots[0].d_phases2 : c->slots[0].d_phases;
+        if (phase >= (c->stream2_ok ? c->s2_phases : c->mega_phases)) return 0;
         cudaMemset(buf, 0, n * 8);
         MegaPhase ph;
-        cudaMemcpy(&ph, c->slots[0].d_phases + phase, sizeof ph, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&ph, prog + phase, sizeof ph, cudaMemcpyDeviceToHost);
         if (ph.kind == PH_GEMV) ph.gemv.dbg = buf;
-        else ph.attn.dbg = buf;
-        cudaMemcpy(c->slots[0].d_phases + phase, &ph, sizeof ph, cudaMemcpyHostToDevice);
+        else if (ph.kind == PH_ATTN) ph.attn.dbg = buf;
+        cudaMemcpy(prog + phase, &ph, sizeof ph, cudaMemcpyHostToDevice);
         return 1;
     }
     const int m = (int)std::min<size_t>(n, (size_t)max_n);

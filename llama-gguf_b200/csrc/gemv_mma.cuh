@@ -87,6 +87,8 @@ struct MParams {
     // second streamed megakernel (stream2.cuh): s_E = s_tiles * s_parts * s_ept ring entries, dealt to CTAs as equal contiguous
     // ranges; cand: (vocab head, greedy mode) collect argmax candidates in the epilogue instead of storing the logits
     int s_E, cand;
+    int s_J, s_R, s_jsh;   // stream2.cuh: jobs per entry along K (1, or 2 = one per chunk) and along the rows (1, or 2 = one per 16-row block); log2(J R)
+    int x_bytes;           // bytes of the staged input (x_staged_bytes(K)): what the loader warp's bulk copy moves
     const float* x;        // [K] f32
     // Producer-staged input (per-token megakernel, single GPU): the phase that produced x also wrote its int8 planes,
     // group scales / sums and per-group sums of squares (stage_out32); this launch copies them instead of converting

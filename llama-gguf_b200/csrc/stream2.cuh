@@ -40,11 +40,17 @@
 
 namespace b200 {
 
-constexpr int kS2Cons = 14;                       // consumer warps
-constexpr int kS2Pairs = kS2Cons / 2;              // a ring entry is computed by a PAIR of warps: even warp K half 0, odd warp K half 1
+#ifndef B200_S2_CONS
+#define B200_S2_CONS 14
+#endif
+constexpr int kS2Cons = B200_S2_CONS;             // consumer warps (14 at 128 registers; 12: warpgroups 0-2 take kS2ConsRegs registers with setmaxnreg)
 constexpr int kS2NT = kS2Cons * 32;               // consumer threads
-constexpr int kS2Threads = 512;                   // + loader warp (14) + producer warp (15)
-constexpr int kS2LoaderWarp = 14, kS2ProdWarp = 15;
+// + the service warpgroup: loader warp, producer warp, two idle warps.  8 consumers: 256 x 200 + 128 x 96 = 63488 registers
+// (round 1's fully unrolled unit kernels: few fat warps); 12: 384 x 144 + 128 x 72 = 64512; 14: no setmaxnreg, 128 each
+constexpr int kS2Threads = kS2Cons == 8 ? 384 : 512;
+constexpr bool kS2Regs = kS2Cons != 14;
+constexpr int kS2ConsRegs = kS2Cons == 8 ? 200 : 144, kS2ServRegs = kS2Cons == 8 ? 96 : 72;   // (inc must fit in what dec released: 256 x 32 <= 128 x 72)
+constexpr int kS2LoaderWarp = kS2Cons, kS2ProdWarp = kS2Cons + 1;
 constexpr int kS2SlotBytes = kStreamSlotBytes;    // 9216: 32 rows x 288 bytes (Q4_K, two super-blocks)
 constexpr int kS2MaxSlots = 24;
 constexpr int kS2TileSlots = 4;
@@ -61,7 +67,7 @@ struct Stream2Params {
     int no_load;
     uint2* ll;                // [grid][2][32] (value, epoch) packets of tile pieces
     unsigned int epoch0;      // packets of this launch carry epoch0 + global phase number + 1
-    float* cand_val;          // [grid * kS2Cons] argmax candidates of the vocab head
+    float* cand_val;          // [grid] argmax candidates of the vocab head (one per CTA)
     int* cand_idx;
 };
 
@@ -70,12 +76,14 @@ __device__ __forceinline__ void s2_cons_sync() { asm volatile("bar.sync 1, %0;" 
 // ---------------------------------------------------------------- producer
 struct PDesc2 {
     int gemv, n_seg, ept, parts, swiglu, E;
+    unsigned long long* dbg;
     const void* tm[3];
     int nt[3], cstep[3], bytes[3];
 };
 __device__ __forceinline__ void pdesc2_load(PDesc2& d, const MegaPhase* P) {
     d.gemv = P->kind == PH_GEMV;
     const MParams* g = &P->gemv;
+    d.dbg = g->dbg;
     d.n_seg = g->n_seg; d.ept = g->s_ept; d.parts = g->s_parts; d.swiglu = g->epi == ME_SWIGLU; d.E = g->s_E;
     const int sC = g->s_C;
 #pragma unroll
@@ -112,7 +120,10 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
                 int T = e0 / per_tile;
                 const int r = e0 - T * per_tile;
                 int part = r / ept, ce = r - part * ept;
-                for (int e = e0; e < e1; e++) {
+                long long pw = 0;
+                const long long pt0 = clock64();
+                // what one entry needs: tensor map, box coordinates, bytes; then the cursor moves on
+                auto next_entry = [&](const void*& tmap, int& c0, int& c1, int& nby) {
                     int s = 0, tile = T;
                     if (cur.swiglu) {
                         s = part;
@@ -120,22 +131,60 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
                         if (cur.n_seg > 1 && tile >= cur.nt[0]) { tile -= cur.nt[0]; s = 1; }
                         if (s == 1 && cur.n_seg > 2 && tile >= cur.nt[1]) { tile -= cur.nt[1]; s = 2; }
                     }
-                    const void* tmap = s == 0 ? cur.tm[0] : s == 1 ? cur.tm[1] : cur.tm[2];
+                    tmap = s == 0 ? cur.tm[0] : s == 1 ? cur.tm[1] : cur.tm[2];
                     const int cs = s == 0 ? cur.cstep[0] : s == 1 ? cur.cstep[1] : cur.cstep[2];
-                    const int nby = s == 0 ? cur.bytes[0] : s == 1 ? cur.bytes[1] : cur.bytes[2];
-                    const int c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
-                    if (!s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, mp.err, 1000, round * (uint32_t)rg.n_slots + slot)) return;
-                    if (sp.no_load) {
-                        mbar_arrive(rg.full + 8u * slot);
-                    } else {
-                        mbar_arrive_expect_tx(rg.full + 8u * slot, (uint32_t)nby);
-                        tma_load_2d(rg.base + slot * (uint32_t)kS2SlotBytes, tmap, c0, tile * kMmaRows, rg.full + 8u * slot);
-                    }
-                    if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
+                    nby = s == 0 ? cur.bytes[0] : s == 1 ? cur.bytes[1] : cur.bytes[2];
+                    c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
+                    c1 = tile * kMmaRows;
                     if (++ce == ept) {
                         ce = 0;
                         if (++part == cur.parts) { part = 0; T++; }
                     }
+                };
+                // Two entries per iteration: the single issuing thread is latency-bound (a try_wait that succeeds at once still takes
+                // ~90 clocks, expect_tx and the TMA issue ~100 more: 385 clocks per entry one at a time = 12 B/clk for a 4.6 KB entry,
+                // half of what HBM delivers per SM), so the two try_waits are issued back to back and overlap.
+                for (int e = e0; e < e1; e += 2) {
+                    const bool two = e + 1 < e1;
+                    const void *tmA, *tmB = nullptr;
+                    int a0, a1, an, b0 = 0, b1 = 0, bn = 0;
+                    next_entry(tmA, a0, a1, an);
+                    const uint32_t slotA = slot, parA = (round & 1u) ^ 1u;
+                    if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
+                    const uint32_t slotB = slot, parB = (round & 1u) ^ 1u;
+                    if (two) {
+                        next_entry(tmB, b0, b1, bn);
+                        if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
+                    }
+                    if (cur.dbg) pw -= clock64();
+                    const bool okA = mbar_try_wait(rg.empty + 8u * slotA, parA);
+                    const bool okB = two ? mbar_try_wait(rg.empty + 8u * slotB, parB) : true;
+                    if (!okA && !s_wait(rg.empty + 8u * slotA, parA, s_dead, mp.err, 1000, slotA)) return;
+                    if (cur.dbg) pw += clock64();
+                    if (sp.no_load) {
+                        mbar_arrive(rg.full + 8u * slotA);
+                    } else {
+                        mbar_arrive_expect_tx(rg.full + 8u * slotA, (uint32_t)an);
+                        tma_load_2d(rg.base + slotA * (uint32_t)kS2SlotBytes, tmA, a0, a1, rg.full + 8u * slotA);
+                    }
+                    if (two) {
+                        if (cur.dbg) pw -= clock64();
+                        if (!okB && !s_wait(rg.empty + 8u * slotB, parB, s_dead, mp.err, 1001, slotB)) return;
+                        if (cur.dbg) pw += clock64();
+                        if (sp.no_load) {
+                            mbar_arrive(rg.full + 8u * slotB);
+                        } else {
+                            mbar_arrive_expect_tx(rg.full + 8u * slotB, (uint32_t)bn);
+                            tma_load_2d(rg.base + slotB * (uint32_t)kS2SlotBytes, tmB, b0, b1, rg.full + 8u * slotB);
+                        }
+                    }
+                }
+                if (cur.dbg) {   // (debug) producer warp's row of the phase's stamp buffer: first issue, last issue, clocks waiting for slots, entries
+                    unsigned long long* d = cur.dbg + ((size_t)blockIdx.x * 16 + kS2ProdWarp) * 8;
+                    d[0] = (unsigned long long)pt0;
+                    d[1] = (unsigned long long)clock64();
+                    d[2] = (unsigned long long)pw;
+                    d[3] = (unsigned long long)(e1 - e0);
                 }
             }
         }
@@ -144,220 +193,190 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
 }
 
 // ---------------------------------------------------------------- consumer side of one GEMV phase
+// Register discipline (128 per thread, no L1 to spill into: the whole carve-out is shared memory): the only state that
+// lives across a unit kernel is the cursor (i, T, part, ce), the ring position (slot, round), one accumulator pair, three
+// lane-table words and a few phase constants; everything else is re-read from the phase descriptor in shared memory.
+// A consumer warp never touches global memory: merge, cross-CTA packets and the epilogue belong to the loader warp.
+// which form of the unit kernels the consumers run (units2.cuh): 5 = K-half outer (B operands of one half live), 4 = row-block outer
+#ifndef B200_S2_UNITS
+#define B200_S2_UNITS 5
+#endif
+#define S2_CAT2(a, b) a##b
+#define S2_CAT(a, b) S2_CAT2(a, b)
+#define S2_UNIT(name) S2_CAT(S2_CAT(unit, B200_S2_UNITS), _##name)
 struct S2Cons {
     uint32_t seq0;     // ring entries this CTA has consumed before this phase
     uint32_t tseq0;    // tiles this CTA has touched before this phase (tile slot = sequence & 3, generation = sequence >> 2)
-    float best_v;      // greedy: this lane's best logit so far (vocab head phase)
-    int best_i;
 };
+struct S2Deal {
+    int e0, nloc, T_first, n_ltiles;
+};
+__device__ __forceinline__ S2Deal s2_deal(const MParams& p) {
+    const long long nb = gridDim.x, b = blockIdx.x, E = p.s_E;
+    const int per_tile = p.s_parts * p.s_ept;
+    S2Deal d;
+    d.e0 = (int)(b * E / nb);
+    d.nloc = (int)((b + 1) * E / nb) - d.e0;
+    d.T_first = d.e0 / per_tile;
+    d.n_ltiles = d.nloc > 0 ? (d.e0 + d.nloc - 1) / per_tile - d.T_first + 1 : 0;
+    return d;
+}
+__device__ __forceinline__ void pin2(float (&a)[2]) { asm volatile("" : "+f"(a[0]), "+f"(a[1])::"memory"); }
+// debug timeline (b200_debug_mega_phase): SM-clock stamps of lane 0 of every warp.  Consumers: 0 phase entered, 1 x landed, 2 first
+// entry landed, 3 last entry computed, 4 phase left.  Loader: 0 consumers done, 1 arrived at the grid barrier, 2 barrier open, 3 x
+// issued, 4 first tile merged, 5 last tile's epilogue done
+#define S2_STAMP(DBG, k) do { if ((DBG) && (threadIdx.x & 31) == 0) (DBG)[((size_t)blockIdx.x * 16 + (threadIdx.x >> 5)) * 8 + (k)] = (unsigned long long)clock64(); } while (0)
 
 __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Params& sp, uint8_t* smem, const SRing& rg, S2Cons& cs,
                                             uint32_t xfull, uint32_t xpar, int* s_tcnt, volatile unsigned int* s_tdone,
-                                            volatile int* s_dead, unsigned int epoch, bool greedy) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int K = p.K;
+                                            volatile int* s_dead, unsigned int epoch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem);
     const bool swiglu = p.epi == ME_SWIGLU;
-    const int ept = p.s_ept, n_parts = p.s_parts, per_tile = n_parts * ept;
-    const long long nb = gridDim.x, b = blockIdx.x, E = p.s_E;
-    const int e0 = (int)(b * E / nb), e1 = (int)((b + 1) * E / nb), nloc = e1 - e0;
-    const int T_first = e0 / per_tile;
-    const int n_ltiles = nloc > 0 ? (e1 - 1) / per_tile - T_first + 1 : 0;
+    const int ept = p.s_ept, per_tile = p.s_parts * ept;
+    const S2Deal dl = s2_deal(p);
+    const int e0 = dl.e0, nloc = dl.nloc;
     float (*s_tpart)[kS2Cons][2][32] = reinterpret_cast<float (*)[kS2Cons][2][32]>(smem + sp.tpart_off);
-    const bool cand = greedy && p.cand;
-
-    const XLayout XL = x_layout(K);
-    XSmem sm;
     const uint32_t xb = sbase + (uint32_t)sp.xr_off;
-    sm.p0 = xb + XL.p0;
-    sm.p1 = xb + XL.p1;
-    sm.p2 = xb + XL.p2;
-    sm.sx = xb + XL.sx;
-    sm.x16 = xb + XL.x16;
-    sm.zero = sbase + 96u;
-
-    // logical tile T of the phase -> (segment, tile within the segment)
-    auto seg_of = [&](int T, int& s, int& tile) {
-        s = 0;
-        tile = T;
+#define dbg p.dbg   /* re-read from the descriptor in shared memory at every stamp: no register lives across the unit kernels */
+    S2_STAMP(dbg, 0);
+    XAddr sm;
+    {
+        const XLayout XL = x_layout(p.K);
+        sm.sx = xb + XL.sx;
+        sm.x16 = xb + XL.x16;
+        sm.zero = sbase + 96u;
+    }
+    // logical tile T of the phase -> segment
+    auto seg_of = [&](int TT) {
+        int es = 0;
         if (!swiglu)
-            while (s + 1 < p.n_seg && tile >= p.seg[s].n_tiles) { tile -= p.seg[s].n_tiles; s++; }
+            while (es + 1 < p.n_seg && TT >= p.seg[es].n_tiles) { TT -= p.seg[es].n_tiles; es++; }
+        return es;
     };
-    // cursor of this warp's pair: local entry index i = pair, pair + 7, ...
-    const int pair = warp >> 1, half = warp & 1;
-    int i = pair, T = 0, part = 0, ce = 0, s = 0, tile = 0;
-    if (i < nloc) {
+    // Work is dealt in JOBS, one warp each: an entry (32 rows x C chunks) is s_J jobs along K (a two-chunk entry: one job of two
+    // chunks or two of one) times s_R jobs along the rows (both 16-row blocks or one), chosen per phase by the host so that the
+    // last round of the 14 warps is full.  Job jj = (J R) i + sub of the CTA's range goes to warp jj mod 14; (T, part, ce) locate entry i.
+    const int jsh = p.s_jsh, njobs = nloc << jsh;
+    int jj = warp, i = jj >> jsh, T = 0, part = 0, ce = 0, s = 0;
+    if (jj < njobs) {
         const int e = e0 + i;
         T = e / per_tile;
         const int r = e - T * per_tile;
         part = r / ept;
         ce = r - part * ept;
-        seg_of(T, s, tile);
+        s = seg_of(T);
     }
-    uint32_t q = cs.seq0 + (uint32_t)pair;
-    uint32_t slot = q % (uint32_t)rg.n_slots, round = q / (uint32_t)rg.n_slots;
-    int type = -1, nb_row = 0, cb = 0;
-    uint32_t RS = 0, cbytes = 0;
-    LaneB lb{};
+    uint32_t slot, round;
+    {
+        const uint32_t q = cs.seq0 + (uint32_t)i;
+        slot = q % (uint32_t)rg.n_slots;
+        round = q / (uint32_t)rg.n_slots;
+    }
+    int type = -1;
+    LaneT lt{0u, 0u, 0u, 0u};
+    int ginv = lane & 7;   // lane group that computes row (lane & 7) of a row block (units2.cuh: s2_row_perm)
+    uint32_t xtok = 0u;   // becomes an opaque zero after the wait for x: no shared-memory read of x is hoisted above it
     auto load_mat = [&]() {
-        const MSeg& wsg = p.seg[swiglu ? part : s];
-        RS = (uint32_t)wsg.s_pitch;
-        cbytes = (uint32_t)wsg.chunk_bytes;
-        nb_row = wsg.nb_row;
-        cb = wsg.cb;
-        if (wsg.type != type) {
-            type = wsg.type;
-            lb = (type == T_Q6_K) ? lane_b_q6k(sm, g, t) : (type == T_Q8_0) ? lane_b_q80(sm, g, t) : lane_b_k45(sm, g, t, type == T_Q5_K);
+        const MSeg& msg = p.seg[swiglu ? part : s];
+        const int ty = msg.type;
+        if (ty != type) {   // (within a phase a type has one pitch; the rows of a tile all come from matrices of one type)
+            type = ty;
+            const XLayout XL = x_layout(p.K);
+            const uint32_t p0 = xb + XL.p0, p1 = xb + XL.p1, p2 = xb + XL.p2;
+            lt = (type == T_Q6_K) ? lane_t_q6k(p0, p1, p2, g, t) : (type == T_Q8_0) ? lane_t_q80(p0, p1, p2, g, t) : lane_t_k45(p0, p1, p2, g, t);
+            lt.c1 += xtok;
+            lt.c2 += xtok;
+            lt.grow = s2_row_perm((uint32_t)msg.s_pitch, g);
+            ginv = s2_row_perm_inv((uint32_t)msg.s_pitch, lane & 7);
         }
     };
-    if (i < nloc) load_mat();
-    const int sC = p.s_C, n_chunks = p.chunks;
+    if (jj < njobs) load_mat();
 
     // ---- the phase's input: staged by its producer, copied by the loader warp; everything above overlapped the boundary ----
     s_wait(xfull, xpar, s_dead, p.err, 6000, epoch);
-    float unscale = 1.0f;
-    if (p.norm_w) {   // sum of x^2 from the per-group partial sums, in the same order in every warp and CTA
-        const uint32_t ssq = xb + XL.ssq + smem_token();
-        float tot = 0.0f;
-        for (int k = lane; k < (K >> 5); k += 32) tot += lds_f32(ssq + 4u * (uint32_t)k);
-        tot = warp_sum(tot);
-        unscale = 1.0f / sqrtf(tot / (float)K + p.eps);
-    }
-    {   // no shared-memory read of x may be hoisted above the wait (lane tables hold differences: they stay valid)
-        const uint32_t tokx = smem_token();
-        sm.sx += tokx;
-        sm.x16 += tokx;
-        sm.zero += tokx;
+    S2_STAMP(dbg, 1);
+    {
+        xtok = smem_token();
+        sm.sx += xtok;
+        sm.x16 += xtok;
+        sm.zero += xtok;
+        lt.c1 += xtok;
+        lt.c2 += xtok;
     }
 
-    // ---- epilogue of a finished tile: lane L owns row tile * 32 + L of segment s (vu: the up row for SwiGLU) ----
-    auto epilogue = [&](int es, int etile, float v, float vu) {
-        const MSeg& sg = p.seg[es];
-        const int j = etile * kMmaRows + lane;
-        const bool valid = j < sg.n_rows;
-        const float e_bias = (valid && sg.bias) ? sg.bias[j] : 0.0f;
-        const float e_res = (valid && p.epi == ME_RESIDUAL) ? __ldcg(p.residual + j) : 0.0f;
-        const float e_w = (p.stage_out && p.stage_w && j < p.stage_K) ? p.stage_w[j] : 1.0f;
-        v *= unscale;
-        float val = v;
-        if (swiglu) val = mma_silu(v) * (vu * unscale);
-        if (valid) {
-            val += e_bias;
-            val += e_res;
-            if (cand) {   // raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821)
-                if (val > cs.best_v || (val == cs.best_v && j > cs.best_i) || cs.best_i < 0) { cs.best_v = val; cs.best_i = j; }
-            } else {
-                sg.out[j] = val;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int wrote = 0;   // parts of the current tile this warp has already left in the tile slot
+    bool first = true;
+#ifdef B200_S2_DEBUG
+    unsigned int t_wait = 0;   // SM clocks spent waiting for ring entries
+#endif
+    while (jj < njobs) {
+        {
+            const MSeg& wsg = p.seg[swiglu ? part : s];
+            const uint32_t RS = (uint32_t)wsg.s_pitch, cbytes = (uint32_t)wsg.chunk_bytes;
+            const int sub = jj & ((1 << jsh) - 1), rsh = p.s_R == 2 ? 1 : 0;
+#if B200_S2_CONS == 8
+            const int rt0 = 0, rt1 = 2;   // (whole units only: the row-block loop of the unit kernels is unrolled)
+#else
+            const int rt0 = rsh ? (sub & 1) : 0, rt1 = rsh ? rt0 + 1 : 2;
+#endif
+            const int sC = p.s_C, cpj = sC >> (jsh - rsh);           // chunks per entry / per job
+            const int cj = (sub >> rsh) * cpj, c0 = ce * sC;          // first chunk of the job within the entry; of the entry within the row
+            const uint32_t e00 = (uint32_t)(c0 + cj) * kMmaChunk;
+            const uint32_t doff = ((uint32_t)c0 * cbytes) & 15u;     // the box starts 16-byte aligned (Q6_K: any even residue)
+            // A slot always serves the same warps within a phase (n_slots = 14, (J R) x 14 = 0 mod 14) and phases are separated by
+            // the grid barrier: "parity r of `full`" can never be a stale phase (stream.cuh needed a guard wait on `empty` here)
+#ifdef B200_S2_DEBUG
+            t_wait -= (unsigned int)clock();
+#endif
+            s_wait(rg.full + 8u * slot, round & 1u, s_dead, p.err, 2000 + warp, slot);
+#ifdef B200_S2_DEBUG
+            t_wait += (unsigned int)clock();
+#endif
+            if (first) { S2_STAMP(dbg, 2); first = false; }
+            const uint32_t a0 = rg.base + slot * (uint32_t)kS2SlotBytes + doff + (uint32_t)cj * cbytes + smem_token();
+            for (int c = 0; c < cpj; c++) {
+                const uint32_t a = a0 + (uint32_t)c * cbytes, ee = e00 + (uint32_t)c * kMmaChunk;
+                switch (type) {
+                    case T_Q4_K: S2_UNIT(k45<false>)(a, RS, ee, sm, lt, g, t, rt0, rt1, acc); break;
+                    case T_Q5_K: S2_UNIT(k45<true>)(a, RS, ee, sm, lt, g, t, rt0, rt1, acc); break;
+                    case T_Q6_K:
+                        if (((a - rg.base) & 3u) == 0u) S2_UNIT(q6k<4>)(a, RS, ee, sm, lt, g, t, rt0, rt1, acc);   // (slots and 16 x pitch are 16-byte multiples)
+                        else S2_UNIT(q6k<2>)(a, RS, ee, sm, lt, g, t, rt0, rt1, acc);
+                        break;
+                    default: S2_UNIT(q80)(a, RS, ee, min(wsg.cb, wsg.nb_row - (int)(ee >> 5)), sm, lt, g, t, rt0, rt1, acc); break;
+                }
             }
-        }
-        if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
-    };
-
-    float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
-    while (i < nloc) {
-        const int c0 = ce * sC, nc = min(sC, n_chunks - c0);
-        const uint32_t e00 = (uint32_t)c0 * kMmaChunk;
-        const uint32_t doff = ((uint32_t)c0 * cbytes) & 15u;   // the box starts 16-byte aligned (Q6_K: any even residue)
-        // parity protocol of stream.cuh: the slot's previous round must have been released before "parity r" of `full`
-        // can be trusted (no pair is ever more than n_slots entries ahead of the slowest one: n_slots > kS2Pairs)
-        s_wait(rg.empty + 8u * slot, (round & 1u) ^ 1u, s_dead, p.err, 4000 + warp, q);
-        s_wait(rg.full + 8u * slot, round & 1u, s_dead, p.err, 2000 + warp, q);
-        const uint32_t spb = rg.base + slot * (uint32_t)kS2SlotBytes + doff + smem_token();
-        float ua[4] = {0.f, 0.f, 0.f, 0.f};
-        switch (type) {
-            case T_Q4_K:
-                for (int c = 0; c < nc; c++) {
-                    if (half == 0) unit2_k45_half<false, 0>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
-                    else unit2_k45_half<false, 1>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
-                }
-                break;
-            case T_Q5_K:
-                for (int c = 0; c < nc; c++) {
-                    if (half == 0) unit2_k45_half<true, 0>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
-                    else unit2_k45_half<true, 1>(spb + (uint32_t)c * cbytes, RS, e00 + (uint32_t)c * kMmaChunk, sm, lb, g, t, ua);
-                }
-                break;
-            case T_Q6_K:
-                for (int c = 0; c < nc; c++) {
-                    const uint32_t a = spb + (uint32_t)c * cbytes, ee = e00 + (uint32_t)c * kMmaChunk;
-                    const uint32_t al = (doff + (uint32_t)c * cbytes) & 7u;
-                    if (half == 0) {
-                        if (al == 0u) unit2_q6k_half<8, 0>(a, RS, ee, sm, lb, g, t, ua);
-                        else if (al == 4u) unit2_q6k_half<4, 0>(a, RS, ee, sm, lb, g, t, ua);
-                        else unit2_q6k_half<2, 0>(a, RS, ee, sm, lb, g, t, ua);
-                    } else {
-                        if (al == 0u) unit2_q6k_half<8, 1>(a, RS, ee, sm, lb, g, t, ua);
-                        else if (al == 4u) unit2_q6k_half<4, 1>(a, RS, ee, sm, lb, g, t, ua);
-                        else unit2_q6k_half<2, 1>(a, RS, ee, sm, lb, g, t, ua);
-                    }
-                }
-                break;
-            default:
-                for (int c = 0; c < nc; c++) {
-                    const uint32_t ee = e00 + (uint32_t)c * kMmaChunk;
-                    const int nblk = min(cb, nb_row - (int)(ee >> 5));
-                    if (half == 0) unit2_q80_half<0>(spb + (uint32_t)c * cbytes, RS, ee, nblk, sm, lb, g, t, ua);
-                    else unit2_q80_half<1>(spb + (uint32_t)c * cbytes, RS, ee, nblk, sm, lb, g, t, ua);
-                }
-                break;
-        }
-        pin4(ua);   // every shared-memory read of the entry has completed before the slot is handed back
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rg.empty + 8u * slot);
-        q += (uint32_t)kS2Pairs;
-        slot += (uint32_t)kS2Pairs;
-        while (slot >= (uint32_t)rg.n_slots) { slot -= (uint32_t)rg.n_slots; round++; }
-        if (swiglu && part == 1) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) au[k] += ua[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) ag[k] += ua[k];
+            pin4(acc);   // every shared-memory read of the job has completed before the slot is handed back
+            __syncwarp();
+            if (lane == 0)   // a slot is free after 4 arrivals: one job arrives 4 / (jobs per entry) times
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(rg.empty + 8u * slot), "r"(4 >> jsh) : "memory");
         }
 
-        // ---- advance the cursor by 7 entries ----
-        const int cur_T = T, cur_s = s, cur_tile = tile;
-        i += kS2Pairs;
-        ce += kS2Pairs;
-        bool mat_change = false;
+        // ---- advance the cursor by 14 jobs ----
+        const int cur_T = T, cur_part = part;
+        jj += kS2Cons;
+        {
+            const int ni = jj >> jsh, di = ni - i;
+            i = ni;
+            ce += di;
+            slot += (uint32_t)di;
+            if (slot >= (uint32_t)rg.n_slots) { slot -= (uint32_t)rg.n_slots; round++; }
+        }
         while (ce >= ept) {
             ce -= ept;
-            mat_change = true;
-            if (++part == n_parts) { part = 0; T++; }
+            if (++part == p.s_parts) { part = 0; T++; }
         }
-        if (i < nloc && mat_change) {
-            if (T != cur_T) seg_of(T, s, tile);
-            load_mat();
-        }
-        if (i < nloc && T == cur_T) continue;
-
-        // ---- this warp is done with tile cur_T: its 32 row sums go to the tile's slot; the last warp to arrive finishes the tile ----
-        float vg = 0.f, vu = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            ag[k] += __shfl_xor_sync(0xffffffffu, ag[k], 1);
-            ag[k] += __shfl_xor_sync(0xffffffffu, ag[k], 2);
-            const float x = __shfl_sync(0xffffffffu, ag[k], 4 * (lane & 7));
-            if ((lane >> 3) == k) vg = x;
-            ag[k] = 0.f;
-        }
-        if (swiglu) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                au[k] += __shfl_xor_sync(0xffffffffu, au[k], 1);
-                au[k] += __shfl_xor_sync(0xffffffffu, au[k], 2);
-                const float x = __shfl_sync(0xffffffffu, au[k], 4 * (lane & 7));
-                if ((lane >> 3) == k) vu = x;
-                au[k] = 0.f;
-            }
-        }
-        const int t_lo = max(cur_T * per_tile, e0) - e0, t_hi = min((cur_T + 1) * per_tile, e1) - e0;   // local entries of the tile
-        const int n_cpairs = min(t_hi - t_lo, kS2Pairs), n_contrib = 2 * n_cpairs;   // both warps of a pair always contribute
-        const uint32_t ts = cs.tseq0 + (uint32_t)(cur_T - T_first);
-        const int tslot = (int)(ts & (kS2TileSlots - 1));
-        const unsigned int gen = ts >> 2;
-        {
-            {   // the slot's previous tile must have been merged (practically always true: warps are at most a ring apart)
+        const bool more = jj < njobs;
+        if (!more) S2_STAMP(dbg, 3);
+        const bool tile_end = !more || T != cur_T;
+        if (tile_end || part != cur_part) {
+            // ---- this warp leaves (tile cur_T, part cur_part): its 32 row sums go to the tile's slot ----
+            const uint32_t ts = cs.tseq0 + (uint32_t)(cur_T - dl.T_first);
+            const int tslot = (int)(ts & (kS2TileSlots - 1));
+            if (wrote == 0) {   // first store into the slot for this tile: its previous tile (4 tiles ago) must have been merged
+                const unsigned int gen = ts >> 2;
                 const long long w0 = clock64();
                 while (s_tdone[tslot] != gen) {
                     if (*s_dead) break;
@@ -368,42 +387,129 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
                     }
                 }
             }
-            s_tpart[tslot][warp][0][lane] = vg;
-            s_tpart[tslot][warp][1][lane] = vu;
-            __syncwarp();
-            int old = 0;
-            if (lane == 0) {
-                __threadfence_block();
-                old = atomicAdd(&s_tcnt[tslot], 1);
+            s_tpart[tslot][warp][cur_part][lane] = rows32_from_acc(acc, lane, ginv);
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[k] = 0.f;
+            wrote |= 1 << cur_part;
+            if (tile_end) {
+                if (swiglu && wrote != 3) s_tpart[tslot][warp][wrote == 1 ? 1 : 0][lane] = 0.f;   // this warp had no job of the other matrix
+                wrote = 0;
+                __syncwarp();
+                if (lane == 0) {   // the loader warp adds the pieces (in job order) when the tile's count is complete
+                    __threadfence_block();
+                    atomicAdd(&s_tcnt[tslot], 1);
+                }
             }
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old != n_contrib - 1) continue;
-            __threadfence_block();
-            vg = 0.f;
-            vu = 0.f;
-            int w = 2 * (t_lo % kS2Pairs);
-            for (int k = 0; k < n_contrib; k++) {   // entry order, half 0 before half 1: fixed, whoever arrives last
-                vg += s_tpart[tslot][w][0][lane];
-                vu += s_tpart[tslot][w][1][lane];
-                if (++w == kS2Cons) w = 0;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                s_tcnt[tslot] = 0;
-                __threadfence_block();
-                s_tdone[tslot] = gen + 1u;
+            if (more) {   // (after the flush: the row permutation of the finished tile's matrix was still needed)
+                if (T != cur_T) s = seg_of(T);
+                load_mat();
             }
         }
-        // ---- a tile cut by a CTA boundary: tail pieces are published, the head's CTA collects them ----
-        const bool head_local = cur_T * per_tile >= e0, tail_local = (cur_T + 1) * per_tile <= e1;
-        if (!head_local) {
+    }
+    S2_STAMP(dbg, 4);
+#ifdef B200_S2_DEBUG
+    if (dbg && lane == 0) dbg[((size_t)blockIdx.x * 16 + warp) * 8 + 5] = (unsigned long long)t_wait;
+#endif
+#undef dbg
+    cs.seq0 += (uint32_t)nloc;
+    cs.tseq0 += (uint32_t)dl.n_ltiles;
+}
+
+// ---------------------------------------------------------------- loader warp, GEMV phase: merge, cross-CTA packets, epilogues
+// Runs while the consumers compute: for every tile of this CTA, in order, wait until all contributing warps have left their
+// row sums, add them in entry order (fixed: results are run-to-run identical), then
+//   * a piece whose head lives in an earlier CTA is published as 32 (value, epoch) packets (the owner polls them);
+//   * a tile whose tail lives in later CTAs collects their packets (they were computed FIRST by those CTAs);
+//   * the epilogue: 1/rms, bias, residual, SwiGLU, store, staged int8 form of the output, argmax candidates (vocab head).
+// The operands of a tile's epilogue (bias / residual / norm weight of the output) are requested BEFORE the tile's count is
+// waited for.  Residuals are at least two phases old, so none of this depends on the boundary just crossed.
+struct S2Best {
+    float v;
+    int i;
+};
+__device__ __forceinline__ void s2_gemv_epilogues(const MParams& p, const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t xpar,
+                                                  uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead,
+                                                  unsigned int epoch, bool greedy, S2Best& best) {
+    const int lane = threadIdx.x & 31;
+    const bool swiglu = p.epi == ME_SWIGLU;
+    const int per_tile = p.s_parts * p.s_ept;
+    const S2Deal dl = s2_deal(p);
+    const int e0 = dl.e0, e1 = dl.e0 + dl.nloc;
+    if (dl.n_ltiles == 0) {
+        if (greedy && p.cand && lane == 0) {   // no tile of the vocab head here: no candidate
+            sp.cand_val[blockIdx.x] = -INFINITY;
+            sp.cand_idx[blockIdx.x] = -1;
+        }
+        return;
+    }
+    float (*s_tpart)[kS2Cons][2][32] = reinterpret_cast<float (*)[kS2Cons][2][32]>(smem + sp.tpart_off);
+    unsigned long long* const dbg = p.dbg;
+    float unscale = 1.0f;
+    if (p.norm_w) {   // sum of x^2 from the per-group partial sums of the staged input: the loader waits for its own copy
+        s_wait(xfull, xpar, s_dead, p.err, 6400, epoch);
+        const uint32_t ssq = smem_u32(smem) + (uint32_t)sp.xr_off + x_layout(p.K).ssq + smem_token();
+        float tot = 0.0f;
+        for (int k = lane; k < (p.K >> 5); k += 32) tot += lds_f32(ssq + 4u * (uint32_t)k);
+        tot = warp_sum(tot);
+        unscale = 1.0f / sqrtf(tot / (float)p.K + p.eps);
+    }
+    const bool cand = greedy && p.cand;
+    for (int tl = 0; tl < dl.n_ltiles; tl++) {
+        const int T = dl.T_first + tl;
+        int es = 0, etile = T;
+        if (!swiglu)
+            while (es + 1 < p.n_seg && etile >= p.seg[es].n_tiles) { etile -= p.seg[es].n_tiles; es++; }
+        const MSeg& sg = p.seg[es];
+        const int j = etile * kMmaRows + lane;
+        const bool valid = j < sg.n_rows;
+        const bool head_local = T * per_tile >= e0, tail_local = (T + 1) * per_tile <= e1;
+        float e_bias = 0.0f, e_res = 0.0f, e_w = 1.0f;
+        if (head_local) {   // this CTA finishes the tile: its epilogue operands, in flight while the tile is computed
+            if (valid && sg.bias) e_bias = sg.bias[j];
+            if (valid && p.epi == ME_RESIDUAL) e_res = __ldcg(p.residual + j);
+            if (p.stage_out && p.stage_w && j < p.stage_K) e_w = p.stage_w[j];
+        }
+        const int t_lo = (max(T * per_tile, e0) - e0) << p.s_jsh, t_hi = (min((T + 1) * per_tile, e1) - e0) << p.s_jsh;   // local jobs of the tile
+        const int n_cw = min(t_hi - t_lo, kS2Cons);   // warps that hold a piece of it
+        const uint32_t ts = tseq0 + (uint32_t)tl;
+        const int tslot = (int)(ts & (kS2TileSlots - 1));
+        {
+            const long long w0 = clock64();
+            while (*(volatile int*)&s_tcnt[tslot] != n_cw) {
+                if (*s_dead) break;
+                if (clock64() - w0 > 2000000000LL) {
+                    *s_dead = 1;
+                    if (atomicExch(p.err, 7) == 0) { p.err[1] = 7500; p.err[2] = (int)blockIdx.x; p.err[3] = (int)ts; }
+                    break;
+                }
+            }
+        }
+        __threadfence_block();
+        float vg = 0.f, vu = 0.f;
+        {
+            int w = t_lo % kS2Cons;
+            for (int k = 0; k < n_cw; k++) {   // job order: fixed
+                vg += s_tpart[tslot][w][0][lane];
+                if (swiglu) vu += s_tpart[tslot][w][1][lane];
+                if (++w == kS2Cons) w = 0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            s_tcnt[tslot] = 0;
+            __threadfence_block();
+            s_tdone[tslot] = (ts >> 2) + 1u;
+        }
+        if (tl == 0) S2_STAMP(dbg, 4);
+        if (!head_local) {   // the tile's head lives in an earlier CTA: publish this piece
             uint2* mine = sp.ll + (size_t)blockIdx.x * 64;
             asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(mine + lane), "r"(__float_as_uint(vg)), "r"(epoch) : "memory");
             if (swiglu) asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(mine + 32 + lane), "r"(__float_as_uint(vu)), "r"(epoch) : "memory");
             continue;
         }
-        if (!tail_local) {
-            const int h_last = (int)((((long long)(cur_T + 1) * per_tile) * nb - 1) / E);   // CTA of the tile's last entry
+        if (!tail_local) {   // its tail lives in later CTAs
+            const long long nb = gridDim.x, E = p.s_E;
+            const int h_last = (int)((((long long)(T + 1) * per_tile) * nb - 1) / E);   // CTA of the tile's last entry
             for (int h = (int)blockIdx.x + 1; h <= h_last; h++) {
                 if ((long long)h * E / nb == (long long)(h + 1) * E / nb) continue;   // a CTA without entries publishes nothing
                 const uint2* theirs = sp.ll + (size_t)h * 64;
@@ -416,7 +522,7 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
                     if (__all_sync(0xffffffffu, a1 == epoch && b1 == epoch)) break;
                     if (*s_dead || clock64() - w0 > 2000000000LL) {
                         *s_dead = 1;
-                        if (atomicExch(p.err, 6) == 0) { p.err[1] = 8000 + warp; p.err[2] = (int)blockIdx.x; p.err[3] = h; }
+                        if (atomicExch(p.err, 6) == 0) { p.err[1] = 8000; p.err[2] = (int)blockIdx.x; p.err[3] = h; }
                         break;
                     }
                 }
@@ -424,13 +530,25 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
                 vu += __uint_as_float(b0);
             }
         }
-        epilogue(cur_s, cur_tile, vg, vu);
+        // ---- epilogue: lane L owns row etile * 32 + L of segment es (vu: the up row for SwiGLU) ----
+        vg *= unscale;
+        float val = vg;
+        if (swiglu) val = mma_silu(vg) * (vu * unscale);
+        if (valid) {
+            val += e_bias;
+            val += e_res;
+            if (cand) {   // raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821)
+                if (val > best.v || (val == best.v && j > best.i) || best.i < 0) { best.v = val; best.i = j; }
+            } else {
+                sg.out[j] = val;
+            }
+        }
+        if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
     }
-    cs.seq0 += (uint32_t)nloc;
-    cs.tseq0 += (uint32_t)n_ltiles;
-    if (cand) {   // the warp's candidate of this token: larger value, then larger index
-        float bv = cs.best_v;
-        int bi = cs.best_i;
+    S2_STAMP(dbg, 5);
+    if (cand) {   // the CTA's candidate of this token: larger value, then larger index
+        float bv = best.v;
+        int bi = best.i;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -438,11 +556,11 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
             if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
         }
         if (lane == 0) {
-            sp.cand_val[blockIdx.x * kS2Cons + warp] = bv;
-            sp.cand_idx[blockIdx.x * kS2Cons + warp] = bi;
+            sp.cand_val[blockIdx.x] = bv;
+            sp.cand_idx[blockIdx.x] = bi;
         }
-        cs.best_v = -INFINITY;
-        cs.best_i = -1;
+        best.v = -INFINITY;
+        best.i = -1;
     }
 }
 
@@ -732,7 +850,7 @@ __device__ __forceinline__ void attn2_phase(const AttnParams& p, int kv_len, flo
 __device__ __forceinline__ void s2_pick(const Stream2Params& sp, float* s_av, int* s_ai, int* s_tok) {
     const MegaParams& mp = sp.mp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = (int)gridDim.x * kS2Cons;
+    const int n = (int)gridDim.x;   // one candidate per CTA (its loader warp ran the vocab head's epilogues)
     float best = -INFINITY;
     int bi = -1;
     for (int c = tid; c < n; c += kS2NT) {
@@ -788,29 +906,34 @@ __device__ __forceinline__ void s2_embed(const MParams& p, const Stream2Params& 
     }
 }
 
-// ---------------------------------------------------------------- loader warp: the phase boundary
+// ---------------------------------------------------------------- loader warp: the phase boundary, then the phase's epilogues
 __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t done, int* s_pos, float* s_rope,
-                                          int hd, volatile int* s_dead) {
+                                          int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead) {
     const MegaParams& mp = sp.mp;
     const int lane = threadIdx.x & 31;
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
     const long long total = (long long)mp.n_tokens * n_run;
-    const bool final_pick = mp.mode == MEGA_GREEDY;
+    const bool greedy = mp.mode == MEGA_GREEDY;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t xr = sbase + (uint32_t)sp.xr_off;
     const MegaPhase* s_desc = reinterpret_cast<const MegaPhase*>(smem + sp.desc_off);
     unsigned int target = 0;
+    uint32_t tseq0 = 0;
+    S2Best best{-INFINITY, -1};
     int kv_len = 1;
     int ph = 0;
-    for (long long gb = 0; gb < total + (final_pick ? 1 : 0); gb++) {
+    for (long long gb = 0; gb < total + (greedy ? 1 : 0); gb++) {
         const bool last = gb == total;     // the boundary after the last vocab head (greedy: CTA 0 picks the last token)
-        bool ok = true;
-        uint32_t tx = 0;
+        const MegaPhase& cur = s_desc[gb & 1];
+        unsigned long long* ldbg = nullptr;   // stamps of the boundary BEFORE a phase go to that phase's debug buffer
         if (lane == 0) {
+            uint32_t tx = 0;
             if (gb > 0) {
-                ok = s_wait(done, (uint32_t)((gb - 1) & 1), s_dead, mp.err, 9000, (uint32_t)gb);
+                s_wait(done, (uint32_t)((gb - 1) & 1), s_dead, mp.err, 9000, (uint32_t)gb);
                 s_wait(xfull, (uint32_t)((gb - 1) & 1), s_dead, mp.err, 9100, (uint32_t)gb);   // s_desc[gb & 1] has landed
             }
+            if (!last && cur.kind == PH_GEMV && cur.gemv.dbg) ldbg = cur.gemv.dbg + ((size_t)blockIdx.x * 16 + kS2LoaderWarp) * 8;
+            if (ldbg) ldbg[0] = (unsigned long long)clock64();
             if (!last && gb + 1 < total) {   // descriptor of the NEXT phase: constant data, issued before the barrier is polled
                 int nph = ph + 1;
                 if (nph == n_run) nph = 0;
@@ -818,9 +941,33 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
                 bulk_g2s(sbase + (uint32_t)sp.desc_off + (uint32_t)(((gb + 1) & 1) * sizeof(MegaPhase)), mp.phases + nph,
                          (uint32_t)sizeof(MegaPhase), xfull);
             }
+            // what the phase's input is: known before the barrier opens, so the mbarrier is armed first and the copy is the only
+            // thing left to do afterwards.  Phases without an input copy (EMBED, idle CTAs of an attention phase, the final pick)
+            // must not open before the grid barrier has: their arrive comes after the poll.
+            const void* src[3] = {nullptr, nullptr, nullptr};
+            uint32_t dst[3] = {xr, 0u, 0u}, nby[3] = {0u, 0u, 0u};
+            if (!last && cur.kind == PH_GEMV) {
+                src[0] = cur.gemv.x_staged;
+                nby[0] = (uint32_t)cur.gemv.x_bytes;
+            } else if (!last && cur.kind == PH_ATTN && ph != 1) {
+                const AttnParams& ap = cur.attn;
+                const int ns = attn_eff_splits(kv_len, ap.n_splits, ap.min_chunk);
+                if ((int)blockIdx.x < ap.n_kv * ns) {
+                    const int kh = (int)blockIdx.x / ns, gmax = ap.G <= 4 ? 4 : 8;
+                    src[0] = ap.qkv_raw + (size_t)kh * ap.G * hd;                                    nby[0] = (uint32_t)(ap.G * hd * 4);
+                    src[1] = ap.qkv_raw + (size_t)ap.n_heads * hd + (size_t)kh * hd;                nby[1] = (uint32_t)(hd * 4);
+                    src[2] = ap.qkv_raw + (size_t)(ap.n_heads + ap.n_kv) * hd + (size_t)kh * hd;    nby[2] = (uint32_t)(hd * 4);
+                    dst[1] = xr + (uint32_t)(gmax * hd * 4);
+                    dst[2] = xr + (uint32_t)((gmax + 1) * hd * 4);
+                }
+            }
+            const bool early = nby[0] != 0u;
+            tx += nby[0] + nby[1] + nby[2];
+            if (early) mbar_arrive_expect_tx(xfull, tx);
             if (gb > 0) {   // grid barrier: everything every CTA wrote in phase gb - 1 is visible after this
                 target += gridDim.x;
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(mp.bar) : "memory");
+                if (ldbg) ldbg[1] = (unsigned long long)clock64();
                 unsigned int v = 0;
                 const long long t0 = clock64();
                 for (;;) {
@@ -833,44 +980,24 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
                     }
                 }
                 if (mp.dbg && blockIdx.x == 0) mp.dbg[last ? n_run : ph] = gtimer();   // boundary BEFORE phase ph of the current token
+                if (ldbg) ldbg[2] = (unsigned long long)clock64();
                 asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> this thread's bulk copies
             }
-        }
-        if (!last) {
-            const MegaPhase& cur = s_desc[gb & 1];
-            if (ph == 1) {   // first phase after the embedding: the token's position (written by CTA 0 in the EMBED phase)
-                int pc = 0;
-                if (lane == 0) pc = __ldcg(&mp.st->pos_cur);
-                pc = __shfl_sync(0xffffffffu, pc, 0);
-                kv_len = pc + 1;
-                if (lane == 0) *s_pos = pc;
+            if (!last && ph == 1) {   // first phase after the embedding: the token's position (written by CTA 0 in the EMBED phase)
+                const int pc = __ldcg(&mp.st->pos_cur);
+                *s_pos = pc;
+                __threadfence_block();   // (the consumers' acquire is the copy's completion, not this thread's arrive)
             }
-            if (lane == 0) {
-                if (cur.kind == PH_GEMV) {
-                    const uint32_t nbx = (uint32_t)x_staged_bytes(cur.gemv.K);
-                    tx += nbx;
-                    bulk_g2s(xr, cur.gemv.x_staged, nbx, xfull);
-                } else if (cur.kind == PH_ATTN) {
-                    const AttnParams& ap = cur.attn;
-                    const int ns = attn_eff_splits(kv_len, ap.n_splits, ap.min_chunk);
-                    const int item = blockIdx.x;
-                    if (item < ap.n_kv * ns) {
-                        const int kh = item / ns;
-                        const int gmax = ap.G <= 4 ? 4 : 8;
-                        const uint32_t qb = (uint32_t)(ap.G * hd * 4), rb = (uint32_t)(hd * 4);
-                        tx += qb + 2u * rb;
-                        bulk_g2s(xr, ap.qkv_raw + (size_t)kh * ap.G * hd, qb, xfull);
-                        bulk_g2s(xr + (uint32_t)(gmax * hd * 4), ap.qkv_raw + (size_t)ap.n_heads * hd + (size_t)kh * hd, rb, xfull);
-                        bulk_g2s(xr + (uint32_t)((gmax + 1) * hd * 4), ap.qkv_raw + (size_t)(ap.n_heads + ap.n_kv) * hd + (size_t)kh * hd, rb, xfull);
-                    }
-                }
-            }
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (nby[k]) bulk_g2s(dst[k], src[k], nby[k], xfull);
+            if (!early) mbar_arrive_expect_tx(xfull, tx);
+            if (ldbg) ldbg[3] = (unsigned long long)clock64();
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(xfull, tx);
-        if (!last && ph == 1) {   // the rotation angles of this token (Backend::rope, cpu/ops.rs:1216-1337): needed from phase 2 on
-            const MegaPhase& nxt = s_desc[gb & 1];   // (any descriptor would do: freq / rope_scale live in the ATTN phases)
-            (void)nxt;
+        if (last) break;
+        if (ph == 1) {   // the rotation angles of this token (Backend::rope, cpu/ops.rs:1216-1337): needed from phase 2 on
+            kv_len = *(volatile int*)s_pos + 1;
             const AttnParams& ap = reinterpret_cast<const MegaPhase*>(mp.phases + 2)->attn;
             const float position = (float)(kv_len - 1) / ap.rope_scale;
             for (int pi = lane; pi < hd / 2; pi += 32) {
@@ -880,7 +1007,11 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
             }
             __syncwarp();
         }
-        (void)ok;
+        if (cur.kind == PH_GEMV) {
+            s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), tseq0, s_tcnt, s_tdone, s_dead, sp.epoch0 + (unsigned int)gb + 1u,
+                              greedy, best);
+            tseq0 += (uint32_t)s2_deal(cur.gemv).n_ltiles;
+        }
         if (++ph == n_run) ph = 0;
     }
 }
@@ -911,7 +1042,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     if (tid == 0) {
         for (int i = 0; i < sp.n_slots; i++) {
             mbar_init(rg.full + 8u * i, 1);
-            mbar_init(rg.empty + 8u * i, 2);   // both warps of the consuming pair hand the slot back
+            mbar_init(rg.empty + 8u * i, 4);   // both warps of the pair(s) that computed the entry's chunks hand the slot back (see s2_gemv_cta)
         }
         mbar_init(xfull, 1);
         mbar_init(done, kS2Cons);
@@ -929,22 +1060,27 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     }
     __syncthreads();   // the only CTA-wide barrier
 
-    if (warp == kS2ProdWarp) {
-        if (lane == 0) s2_producer(sp, rg, &s_dead);
-        s_drain(&s_dead);
+    // 16 warps at 128 registers cannot hold a unit kernel plus the loop state without spilling (and the carve-out leaves little
+    // L1 to spill into): the service warpgroup hands registers to the three consumer warpgroups
+    // (the two register budgets must be separate regions of the program: code after a join would be compiled for the smaller one)
+    if (warp >= kS2Cons) {
+        if (kS2Regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kS2ServRegs));
+        if (warp == kS2ProdWarp) {
+            if (lane == 0) s2_producer(sp, rg, &s_dead);
+            s_drain(&s_dead);
+        } else if (warp == kS2LoaderWarp) {
+            s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead);
+            s_drain(&s_dead);
+        }
         return;
     }
-    if (warp == kS2LoaderWarp) {
-        s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, &s_dead);
-        s_drain(&s_dead);
-        return;
-    }
+    if (kS2Regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kS2ConsRegs));
 
     // ---------------- consumer warps ----------------
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
     const bool greedy = mp.mode == MEGA_GREEDY;
     const MegaPhase* s_desc = reinterpret_cast<const MegaPhase*>(smem + sp.desc_off);
-    S2Cons cs{0u, 0u, -INFINITY, -1};
+    S2Cons cs{0u, 0u};
     long long gph = 0;
     for (int tok = 0; tok < mp.n_tokens; tok++) {
         for (int ph = 0; ph < n_run; ph++, gph++) {
@@ -952,7 +1088,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
             const uint32_t xpar = (uint32_t)(gph & 1);
             const unsigned int epoch = sp.epoch0 + (unsigned int)gph + 1u;
             if (cur.kind == PH_GEMV) {
-                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, s_tcnt, s_tdone, &s_dead, epoch, greedy);
+                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, s_tcnt, s_tdone, &s_dead, epoch);
             } else if (cur.kind == PH_ATTN) {
                 attn2_phase<HD, GMAX, kS2Cons>(cur.attn, s_pos + 1, reinterpret_cast<float*>(smem + sp.xr_off), xfull, xpar, &s_dead, mp.err,
                                                epoch, &s_ticket, s_rope);

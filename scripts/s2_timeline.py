@@ -41,3 +41,46 @@ body = body[: (len(body) // 5) * 5].reshape(-1, 5)
 for i, nm in enumerate(names):
     print(f"  {nm:14s} mean {body[:, i].mean():7.2f} us  min {body[:, i].min():7.2f}  max {body[:, i].max():7.2f}   x{body.shape[0]} = {body[:, i].sum():8.1f} us")
 print(f"  {'vocab head':14s} {d[-1]:7.2f} us;  sum of phases {d.sum():.1f} us")
+
+# ---- inside one GEMV phase (stream2): SM-clock stamps per warp, relative to the moment the CTA's loader saw the grid barrier open ----
+if gpu.path() == "stream2" and os.environ.get("PHASES", "1") == "1":
+    MHZ = 1965.0
+    NC = int(os.environ.get("S2_CONS", "12"))   # consumer warps (kS2Cons); loader = warp NC, producer = warp NC + 1
+    lay = int(os.environ.get("LAYER", "16"))
+    for label, k in [("QKV gemv", 0), ("O gemv", 2), ("gate/up gemv", 3), ("down gemv", 4)]:
+        phase = 1 + lay * 5 + k
+        if not L.b200_debug_mega_phase(ctxh, phase, None, 0):
+            continue
+        gpu.decode_greedy(1, 2)
+        big = (C.c_uint64 * (148 * 16 * 8))()
+        m = L.b200_debug_mega_phase(ctxh, -1, big, 148 * 16 * 8)
+        a = np.array(big[:m], dtype=np.float64).reshape(148, 16, 8)
+        ld = a[:, NC, :4]                       # loader: consumers done, arrived, barrier open, x issued
+        ref = ld[:, 2][:, None]
+        cons = a[:, :NC, :5]
+        ok = cons[:, :, 0] > 0
+        def st(name, v):
+            v = v[np.isfinite(v)]
+            if v.size:
+                print(f"   {name:46s} min {v.min() / MHZ:7.2f}  mean {v.mean() / MHZ:7.2f}  max {v.max() / MHZ:7.2f} us  ({v.size})")
+        print(f"{label} (layer {lay}), per CTA, us relative to 'barrier seen open' by the CTA's loader:")
+        st("loader: consumers of previous phase done", (ld[:, 0] - ld[:, 2]))
+        st("loader: arrived at grid barrier", (ld[:, 1] - ld[:, 2]))
+        st("loader: x copy issued + arrive", (ld[:, 3] - ld[:, 2]))
+        rel = np.where(ok[:, :, None], cons - ref[:, :, None], np.nan)
+        st("warp: entered phase (previous phase left)", rel[:, :, 0].ravel())
+        st("warp: x landed (xfull passed)", rel[:, :, 1].ravel())
+        st("warp: first ring entry landed", rel[:, :, 2].ravel())
+        st("warp: last entry computed", rel[:, :, 3].ravel())
+        st("warp: phase left", rel[:, :, 4].ravel())
+        st("CTA: last warp left the phase", np.nanmax(rel[:, :, 4], axis=1))
+        st("warp: compute span (first landed -> last computed)", (rel[:, :, 3] - rel[:, :, 2]).ravel())
+        st("warp: of which waiting for ring entries", np.where(ok, a[:, :NC, 5], np.nan).ravel())
+        st("loader: first tile merged", (a[:, NC, 4] - ld[:, 2]))
+        st("loader: last tile's epilogue done", (a[:, NC, 5] - ld[:, 2]))
+        pr = a[:, NC + 1, :4]
+        st("producer: issue span of the phase's entries", (pr[:, 1] - pr[:, 0]))
+        st("producer: of which waiting for free slots", pr[:, 2])
+        st("producer: issue span per entry (ns)", (pr[:, 1] - pr[:, 0]) / np.maximum(pr[:, 3], 1) * 1000.0)
+        st("producer: non-waiting clocks per entry (x1000)", (pr[:, 1] - pr[:, 0] - pr[:, 2]) / np.maximum(pr[:, 3], 1) * MHZ * 1000.0 / 1000.0)
+        L.b200_debug_mega_phase(ctxh, phase, None, 0)  # (re-arming the same phase keeps the buffer; harmless)

@@ -20,6 +20,9 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             print(f"{k} = {r[i]} {units[i]}")
+    for i, k in enumerate(hdr):   # everything about the shared-memory / LSU pipes
+        if ('shared' in k or 'pipe_lsu' in k or 'inst_executed_pipe_uniform' in k or 'l1tex__lsu_writeback' in k) and k not in keys:
+            print(f"{k} = {r[i]} {units[i]}")
     print('---')
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
