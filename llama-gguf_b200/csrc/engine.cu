@@ -1154,7 +1154,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                     for (int k = 0; k < n_cand; k++) best = std::min(best, waste(cand_J[k] * cand_R[k]));
                     int pick = n_cand - 1;
                     for (int k = 0; k < n_cand; k++)
-                        if (waste(cand_J[k] * cand_R[k]) <= best + 0.04) { pick = k; break; }
+                        if (waste(cand_J[k] * cand_R[k]) <= best + 0.09) { pick = k; break; }   // (coarser jobs amortise the per-job overhead: measured)
                     const int force = env_int("B200_S2_JOBS", 0);   // 1, 2 or 4 jobs per entry
                     if (force == 1) pick = 0; else if (force == 2) pick = 1; else if (force == 4 && n_cand == 3) pick = 2;
                     m.s_J = cand_J[pick]; m.s_R = cand_R[pick];

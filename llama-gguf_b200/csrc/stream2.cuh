@@ -41,13 +41,16 @@
 namespace b200 {
 
 #ifndef B200_S2_CONS
-#define B200_S2_CONS 14
+#define B200_S2_CONS 8
 #endif
 constexpr int kS2Cons = B200_S2_CONS;             // consumer warps (14 at 128 registers; 12: warpgroups 0-2 take kS2ConsRegs registers with setmaxnreg)
 constexpr int kS2NT = kS2Cons * 32;               // consumer threads
 // + the service warpgroup: loader warp, producer warp, two idle warps.  8 consumers: 256 x 200 + 128 x 96 = 63488 registers
 // (round 1's fully unrolled unit kernels: few fat warps); 12: 384 x 144 + 128 x 72 = 64512; 14: no setmaxnreg, 128 each
 constexpr int kS2Threads = kS2Cons == 8 ? 384 : 512;
+// producer warps (the rest of the service warpgroup).  n_slots must be a multiple of it as well: a slot is then always filled by the
+// same producer, in order, so its wait on `empty` by phase parity can never see a stale phase
+constexpr int kS2Prods = kS2Cons == 8 ? 2 : kS2Cons == 12 ? 3 : 1;
 constexpr bool kS2Regs = kS2Cons != 14;
 constexpr int kS2ConsRegs = kS2Cons == 8 ? 200 : 144, kS2ServRegs = kS2Cons == 8 ? 96 : 72;   // (inc must fit in what dec released: 256 x 32 <= 128 x 72)
 constexpr int kS2LoaderWarp = kS2Cons, kS2ProdWarp = kS2Cons + 1;
@@ -96,12 +99,17 @@ __device__ __forceinline__ void pdesc2_load(PDesc2& d, const MegaPhase* P) {
     }
 }
 
-__device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing& rg, volatile int* s_dead) {
+// One issuing thread is latency-bound: a try_wait that succeeds at once, expect_tx, the operand moves to uniform registers and the
+// UTMALDG issue take ~400 clocks per entry (measured: producer stamps of b200_debug_mega_phase), i.e. 23 B/clk for a 9 KB entry --
+// the HBM rate per SM with no slack, and the reason round 1's gate/up phase never went below 19 us.  So the ring is fed by
+// kS2Prods producer warps; producer `pidx` issues the entries whose global sequence number is pidx modulo kS2Prods (the slot of
+// an entry is its sequence number modulo n_slots, whoever issues it).
+__device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing& rg, volatile int* s_dead, int pidx) {
     const MegaParams& mp = sp.mp;
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
     const long long total = (long long)mp.n_tokens * n_run;
     const long long nb = gridDim.x, b = blockIdx.x;
-    uint32_t slot = 0, round = 0;
+    uint32_t Q0 = 0;                       // entries of this CTA before the current phase
     PDesc2 cur, nxt;
     pdesc2_load(cur, mp.phases);
     int ph_next = 1 % n_run;
@@ -109,21 +117,24 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
         pdesc2_load(nxt, mp.phases + ph_next);   // in flight while this phase's entries are issued
         if (++ph_next == n_run) ph_next = 0;
         if (cur.gemv) {
-            const int e0 = (int)(b * cur.E / nb), e1 = (int)((b + 1) * cur.E / nb);
-            if (e1 > e0) {
+            const int e0 = (int)(b * cur.E / nb), e1 = (int)((b + 1) * cur.E / nb), nloc = e1 - e0;
+            int k = (int)(((uint32_t)pidx + (uint32_t)kS2Prods * 1024u - Q0 % (uint32_t)kS2Prods) % (uint32_t)kS2Prods);   // first local entry of this producer
+            if (k < nloc) {
                 if (it < n_run) {
 #pragma unroll
                     for (int s = 0; s < 3; s++)
                         if (s < cur.n_seg) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(cur.tm[s]) : "memory");
                 }
                 const int ept = cur.ept, per_tile = cur.parts * ept;
-                int T = e0 / per_tile;
-                const int r = e0 - T * per_tile;
+                int T = (e0 + k) / per_tile;
+                const int r = (e0 + k) - T * per_tile;
                 int part = r / ept, ce = r - part * ept;
+                uint32_t slot = (Q0 + (uint32_t)k) % (uint32_t)rg.n_slots, round = (Q0 + (uint32_t)k) / (uint32_t)rg.n_slots;
                 long long pw = 0;
                 const long long pt0 = clock64();
-                // what one entry needs: tensor map, box coordinates, bytes; then the cursor moves on
-                auto next_entry = [&](const void*& tmap, int& c0, int& c1, int& nby) {
+                int n_mine = 0;
+                // what one entry needs: tensor map, box coordinates, bytes, slot; then the cursor moves on by kS2Prods entries
+                auto next_entry = [&](const void*& tmap, int& c0, int& c1, int& nby, uint32_t& sl, uint32_t& par) {
                     int s = 0, tile = T;
                     if (cur.swiglu) {
                         s = part;
@@ -136,26 +147,26 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
                     nby = s == 0 ? cur.bytes[0] : s == 1 ? cur.bytes[1] : cur.bytes[2];
                     c0 = ((ce * cs) & ~15) >> 2;   // box start, 16-byte aligned, in 4-byte tensor-map elements
                     c1 = tile * kMmaRows;
-                    if (++ce == ept) {
-                        ce = 0;
+                    sl = slot;
+                    par = (round & 1u) ^ 1u;
+                    k += kS2Prods;
+                    ce += kS2Prods;
+                    while (ce >= ept) {
+                        ce -= ept;
                         if (++part == cur.parts) { part = 0; T++; }
                     }
+                    slot += (uint32_t)kS2Prods;
+                    if (slot >= (uint32_t)rg.n_slots) { slot -= (uint32_t)rg.n_slots; round++; }
+                    n_mine++;
                 };
-                // Two entries per iteration: the single issuing thread is latency-bound (a try_wait that succeeds at once still takes
-                // ~90 clocks, expect_tx and the TMA issue ~100 more: 385 clocks per entry one at a time = 12 B/clk for a 4.6 KB entry,
-                // half of what HBM delivers per SM), so the two try_waits are issued back to back and overlap.
-                for (int e = e0; e < e1; e += 2) {
-                    const bool two = e + 1 < e1;
+                // two entries per iteration: their try_waits are issued back to back and overlap
+                while (k < nloc) {
                     const void *tmA, *tmB = nullptr;
                     int a0, a1, an, b0 = 0, b1 = 0, bn = 0;
-                    next_entry(tmA, a0, a1, an);
-                    const uint32_t slotA = slot, parA = (round & 1u) ^ 1u;
-                    if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
-                    const uint32_t slotB = slot, parB = (round & 1u) ^ 1u;
-                    if (two) {
-                        next_entry(tmB, b0, b1, bn);
-                        if (++slot == (uint32_t)rg.n_slots) { slot = 0; round++; }
-                    }
+                    uint32_t slotA, parA, slotB = 0, parB = 0;
+                    next_entry(tmA, a0, a1, an, slotA, parA);
+                    const bool two = k < nloc;
+                    if (two) next_entry(tmB, b0, b1, bn, slotB, parB);
                     if (cur.dbg) pw -= clock64();
                     const bool okA = mbar_try_wait(rg.empty + 8u * slotA, parA);
                     const bool okB = two ? mbar_try_wait(rg.empty + 8u * slotB, parB) : true;
@@ -179,14 +190,15 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
                         }
                     }
                 }
-                if (cur.dbg) {   // (debug) producer warp's row of the phase's stamp buffer: first issue, last issue, clocks waiting for slots, entries
+                if (cur.dbg && pidx == 0) {   // (debug) producer 0's row of the phase's stamp buffer: first issue, last issue, clocks waiting for slots, entries
                     unsigned long long* d = cur.dbg + ((size_t)blockIdx.x * 16 + kS2ProdWarp) * 8;
                     d[0] = (unsigned long long)pt0;
                     d[1] = (unsigned long long)clock64();
                     d[2] = (unsigned long long)pw;
-                    d[3] = (unsigned long long)(e1 - e0);
+                    d[3] = (unsigned long long)n_mine;
                 }
             }
+            Q0 += (uint32_t)nloc;
         }
         cur = nxt;
     }
@@ -199,7 +211,7 @@ __device__ __forceinline__ void s2_producer(const Stream2Params& sp, const SRing
 // A consumer warp never touches global memory: merge, cross-CTA packets and the epilogue belong to the loader warp.
 // which form of the unit kernels the consumers run (units2.cuh): 5 = K-half outer (B operands of one half live), 4 = row-block outer
 #ifndef B200_S2_UNITS
-#define B200_S2_UNITS 5
+#define B200_S2_UNITS 4
 #endif
 #define S2_CAT2(a, b) a##b
 #define S2_CAT(a, b) S2_CAT2(a, b)
@@ -427,7 +439,7 @@ struct S2Best {
     float v;
     int i;
 };
-__device__ __forceinline__ void s2_gemv_epilogues(const MParams& p, const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t xpar,
+__device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t xpar,
                                                   uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead,
                                                   unsigned int epoch, bool greedy, S2Best& best) {
     const int lane = threadIdx.x & 31;
@@ -440,7 +452,7 @@ __device__ __forceinline__ void s2_gemv_epilogues(const MParams& p, const Stream
             sp.cand_val[blockIdx.x] = -INFINITY;
             sp.cand_idx[blockIdx.x] = -1;
         }
-        return;
+        return 0;
     }
     float (*s_tpart)[kS2Cons][2][32] = reinterpret_cast<float (*)[kS2Cons][2][32]>(smem + sp.tpart_off);
     unsigned long long* const dbg = p.dbg;
@@ -486,12 +498,18 @@ __device__ __forceinline__ void s2_gemv_epilogues(const MParams& p, const Stream
         }
         __threadfence_block();
         float vg = 0.f, vu = 0.f;
-        {
+        {   // all loads first (independent), then the additions in job order: fixed, whoever arrived last
+            float pg[kS2Cons], pu[kS2Cons];
             int w = t_lo % kS2Cons;
-            for (int k = 0; k < n_cw; k++) {   // job order: fixed
-                vg += s_tpart[tslot][w][0][lane];
-                if (swiglu) vu += s_tpart[tslot][w][1][lane];
+#pragma unroll
+            for (int k = 0; k < kS2Cons; k++) {
+                pg[k] = (k < n_cw) ? s_tpart[tslot][w][0][lane] : 0.f;
+                pu[k] = (k < n_cw && swiglu) ? s_tpart[tslot][w][1][lane] : 0.f;
                 if (++w == kS2Cons) w = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < kS2Cons; k++) {
+                if (k < n_cw) { vg += pg[k]; vu += pu[k]; }
             }
         }
         __syncwarp();
@@ -562,6 +580,7 @@ __device__ __forceinline__ void s2_gemv_epilogues(const MParams& p, const Stream
         best.v = -INFINITY;
         best.i = -1;
     }
+    return dl.n_ltiles;
 }
 
 // ---------------------------------------------------------------- attention phase (consumer warps)
@@ -1008,9 +1027,8 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
             __syncwarp();
         }
         if (cur.kind == PH_GEMV) {
-            s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), tseq0, s_tcnt, s_tdone, s_dead, sp.epoch0 + (unsigned int)gb + 1u,
-                              greedy, best);
-            tseq0 += (uint32_t)s2_deal(cur.gemv).n_ltiles;
+            tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), tseq0, s_tcnt, s_tdone, s_dead,
+                                                 sp.epoch0 + (unsigned int)gb + 1u, greedy, best);
         }
         if (++ph == n_run) ph = 0;
     }
@@ -1065,8 +1083,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     // (the two register budgets must be separate regions of the program: code after a join would be compiled for the smaller one)
     if (warp >= kS2Cons) {
         if (kS2Regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kS2ServRegs));
-        if (warp == kS2ProdWarp) {
-            if (lane == 0) s2_producer(sp, rg, &s_dead);
+        if (warp >= kS2ProdWarp && warp < kS2ProdWarp + kS2Prods) {
+            if (lane == 0) s2_producer(sp, rg, &s_dead, warp - kS2ProdWarp);
             s_drain(&s_dead);
         } else if (warp == kS2LoaderWarp) {
             s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead);
