@@ -133,18 +133,24 @@ def model_weight_bytes(preset, mix):
 
 
 def run_cpu_reference(preset, mix, ctx_len, prompt_len, steps, warmup, n_layers_sample, seed):
-    """Times the oracle's LlamaModel::forward (one decoded token per step) on a layer-bounded sample of the
-    workload and scales by weight bytes to the full model.  Returns (tok/s, info)."""
+    """Times the oracle's LlamaModel::forward (one decoded token per step) on the box's host cores.
+
+    n_layers_sample = 0: the FULL model, nothing scaled (the --impl reference arm).  n_layers_sample > 0: a layer-bounded sample of
+    the workload whose time is scaled by weight bytes to the full model (the bounded cpu_baseline leg of the default run).
+    Threads are pinned to the box's core count whatever OMP_NUM_THREADS says (torchrun sets it to 1).  Returns (tok/s, info, ms)."""
     import oracle as O
     from llama_gguf_b200.randmodel import random_model
 
     O.build()
-    ps = sampled_preset(preset, n_layers_sample)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.set_num_threads(cores)
+    full = n_layers_sample <= 0 or n_layers_sample >= preset["n_layers"]
+    ps = dict(preset) if full else sampled_preset(preset, n_layers_sample)
     desc, tensors = random_model(ps, mix, ctx_len, seed=seed)
     ref = O.OracleModel(desc, tensors)
-    cores = O.num_threads()
     tok = 1
-    for i in range(min(prompt_len, 4)):  # short prompt: the CPU arm measures decode steps, not prefill
+    n_prompt = min(prompt_len, 4)   # short prompt: the CPU arm measures decode steps, not prefill
+    for i in range(n_prompt):
         ref.forward([(i * 7919 + 1) % desc["vocab"]], want_logits=False)
     for _ in range(warmup):
         tok = O.argmax_last(ref.forward([tok]))
@@ -155,11 +161,12 @@ def run_cpu_reference(preset, mix, ctx_len, prompt_len, steps, warmup, n_layers_
     frac = model_weight_bytes(ps, mix) / model_weight_bytes(preset, mix)
     ms_sample = dt / steps * 1e3
     ms_full = ms_sample / frac
-    info = {"cores": cores, "kind": "port",
-            "sample": (f"{steps} greedy decode tokens through {ps['n_layers']} of {preset['n_layers']} layers + full vocab head "
-                       f"({frac * 100:.1f}% of the per-token weight bytes), time scaled by weight bytes to the full model; "
-                       f"C++ restatement of the reference CPU path (scalar quant dots, threads over output rows), "
-                       f"hot-path-only embedding (one row per token)"),
+    what = (f"{steps} greedy decode tokens through the full {preset['n_layers']}-layer model (nothing scaled)" if full else
+            f"{steps} greedy decode tokens through {ps['n_layers']} of {preset['n_layers']} layers + full vocab head "
+            f"({frac * 100:.1f}% of the per-token weight bytes), time scaled by weight bytes to the full model")
+    info = {"cores": O.num_threads(), "kind": "port",
+            "sample": (what + f", after a {n_prompt}-token prompt; C++ restatement of the reference CPU path (scalar quant dots, threads over "
+                       "output rows), hot-path-only embedding (one row per token)"),
             "ms_per_step_sample": ms_sample, "avx512": bool(O.lib().orc_has_avx512())}
     return 1000.0 / ms_full, info, ms_full
 
@@ -175,7 +182,10 @@ def main():
     ap.add_argument("--mix", default="Q4_K_M")
     ap.add_argument("--ctx", type=int, default=8192)
     ap.add_argument("--prompt-len", type=int, default=128)
-    ap.add_argument("--cpu-layers", type=int, default=4, help="layers in the CPU baseline sample")
+    ap.add_argument("--cpu-layers", type=int, default=4, help="layers in the bounded cpu_baseline sample of the default run")
+    ap.add_argument("--ref-layers", type=int, default=0, help="--impl reference: layers timed (0 = the full model, nothing scaled)")
+    ap.add_argument("--depth", type=int, default=8000, help="extra line: decode at this KV depth (prompt through b200_prefill; 0 = skip)")
+    ap.add_argument("--batch", type=int, default=32, help="extra line: batched decode with this many sequences (0 = skip)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefill-len", type=int, default=2048, help="tokens of the GEMM-prefill measurement (0 = skip)")
@@ -200,7 +210,7 @@ def main():
         if rank != 0:
             return 0
         v, info, ms_full = run_cpu_reference(preset, args.mix, args.ctx, args.prompt_len, args.steps, args.warmup,
-                                             args.cpu_layers, args.seed)
+                                             args.ref_layers, args.seed)
         info["value"] = v
         info["unit"] = UNIT
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
@@ -227,7 +237,7 @@ def main():
     t0 = time.time()
     from llama_gguf_b200.presets import make_desc
 
-    desc = make_desc(preset, args.ctx)
+    desc = make_desc(preset, args.ctx, max(1, args.batch))   # one KV cache per sequence slot (batch extra below)
     # tensors are streamed straight into the context (host memory stays at one tensor)
     gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up))
     log(f"model built and uploaded in {time.time() - t0:.1f} s")
@@ -271,26 +281,33 @@ def main():
     # ---- roofline of the dominant kernel ----
     peaks, peaks_kind = measured_peaks()
     gms, glaunches, gbytes = gpu.bench_gemv_pass(20)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemv_dram_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    # DRAM traffic per token is an ncu measurement (dram__bytes_read + write of one launch / its tokens): it cannot be taken inside a
+    # timed run, so it is read from the capture committed for THIS kernel and labelled with its source; null if there is none
+    traffic, traffic_src = None, None
+    for tname in ("r02_stream2_dram_traffic.json", "gemv_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("kernel", "").startswith(gpu.path() if gpu.path() != "stream2" else "stream2"):
+                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/" + tname + ": " + tj.get("how", "")
+                    break
+            except Exception:
+                pass
     token_bytes = wbytes + kvpp * kv_len_mid
     mega = launches <= 2  # the per-token megakernel ran: ONE launch covers every decoded token of the timed region
     if mega:
         # the dominant (only) kernel is mega_decode_kernel: algorithmic bytes per token = weights + KV rows read,
         # duration = CUDA-event time per token of the timed region above
         achieved = token_bytes / (ms_per_step * 1e-3) / 1e9
-        kname = "stream_decode_kernel" if gpu.path() == "stream" else "mega_decode_kernel"
+        kname = {"stream2": "stream2_decode_kernel", "stream": "stream_decode_kernel"}.get(gpu.path(), "mega_decode_kernel")
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)",
-                    "traffic": traffic, "bytes_per_launch": token_bytes, "avg_launch_us": ms_per_step * 1e3,
+                    "traffic": traffic, "traffic_source": traffic_src, "bytes_per_launch": token_bytes, "avg_launch_us": ms_per_step * 1e3,
                     "launches_per_token": 1, "frac_of_nominal_8TBs": achieved / 8000.0,
-                    "note": "one persistent kernel per token (161 phases for Llama-3-8B; stream = TMA producer warp + mbarrier ring "
-                            "across phase boundaries); per launch = per token",
+                    "note": "one persistent kernel per token (162 phases for Llama-3-8B; stream2 = TMA producer warps + mbarrier ring "
+                            "across phase boundaries, stream-K jobs, loader-warp boundary); per launch = per token; the timed region is "
+                            f"{args.steps} tokens in ONE launch",
                     "gemv_standalone": {"kernel": "gemv_mma_kernel", "GBps": gbytes / (gms * 1e-3) / 1e9,
                                         "launches_per_token": glaunches, "ms_per_token": gms,
                                         "what": "the same GEMVs as 129 separate PDL-chained launches"}}
@@ -302,6 +319,53 @@ def main():
                     "launches_per_token": glaunches, "gemv_ms_per_token": gms,
                     "whole_token_frac": token_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- extras: BASELINE configs[2] also names an 8K context and batch 32 ----
+    extras = {}
+    if args.depth > 0 and args.depth + args.steps + args.warmup + 8 <= args.ctx:
+        try:
+            gpu.reset()
+            gpu.prefill([(i * 7919 + 1) % desc["vocab"] for i in range(args.depth)])   # (GEMM prefill: writes the KV cache)
+            td, _ = gpu.decode_greedy(1, args.warmup)
+            torch.cuda.synchronize()
+            kv_mid_d = gpu.position() + args.steps // 2
+            td, ms_d = gpu.decode_greedy(int(td[-1]), args.steps)
+            bytes_d = wbytes + kvpp * kv_mid_d
+            ach_d = bytes_d / (ms_d / args.steps * 1e-3) / 1e9
+            extras["decode_at_depth"] = {"kv_len": int(kv_mid_d), "value": 1000.0 * args.steps / ms_d, "unit": UNIT,
+                                         "ms_per_step": ms_d / args.steps, "bytes_per_token": int(bytes_d),
+                                         "kv_bytes_per_token": int(kvpp * kv_mid_d), "achieved_GBps": ach_d,
+                                         "frac": ach_d / peaks["hbm_gbs"],
+                                         "what": f"device-resident greedy decode after a {args.depth}-token prompt (b200_prefill), batch 1"}
+        except Exception as e:
+            extras["decode_at_depth"] = {"error": str(e)}
+    if args.batch > 1:
+        try:
+            nb = args.batch
+            for sq in range(nb):
+                gpu.reset(sq)
+                gpu.prefill([((i + sq) * 7919 + 1) % desc["vocab"] for i in range(16)], sq)
+            seqs = list(range(nb))
+            btoks = [1 + sq for sq in range(nb)]
+            def bstep(tk):
+                lg = gpu.decode_batch(seqs, tk)
+                return [host_argmax_last(lg[i]) for i in range(nb)]
+            for _ in range(args.warmup):
+                btoks = bstep(btoks)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            nsteps_b = max(4, min(args.steps, 32))
+            for _ in range(nsteps_b):
+                btoks = bstep(btoks)
+            torch.cuda.synchronize()
+            sb = time.perf_counter() - tb
+            ach_b = wbytes / (sb / nsteps_b) / 1e9
+            extras["decode_batch"] = {"batch": nb, "value": nb * nsteps_b / sb, "unit": UNIT, "ms_per_step": sb / nsteps_b * 1e3,
+                                      "weight_stream_GBps": ach_b, "frac": ach_b / peaks["hbm_gbs"],
+                                      "what": f"b200_decode_batch, {nb} sequences, host tokens in / host logits out every step "
+                                              "(wall clock): one pass over the weights per step (tcgen05 dequant-GEMM path)"}
+        except Exception as e:
+            extras["decode_batch"] = {"error": str(e)}
 
     # ---- prefill: the whole prompt through the batch entry point (tcgen05 dequant-GEMM, csrc/gemm_umma.cuh) ----
     prefill = None
@@ -344,7 +408,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": desc["vocab"] * 4},
-           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "prefill": prefill,
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "prefill": prefill, "extras": extras,
            "weight_bytes_per_token": wbytes, "kv_bytes_per_token_at_mid": kvpp * kv_len_mid,
            "greedy_tokens_head": [int(t) for t in toks_head]}
     print(json.dumps(out))

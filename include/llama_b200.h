@@ -169,6 +169,12 @@ B200_API int b200_op_silu(const float* x, float* out, size_t n);
 B200_API int b200_op_gelu(const float* x, float* out, size_t n);
 B200_API int b200_op_softmax(const float* x, float* out, size_t n);
 B200_API int b200_op_rms_norm(const float* x, const float* weight, float eps, float* out, size_t n_rows, size_t hidden);
+/* matmul: a[m][k] @ b[k][n] -> out[m][n], row-major f32 (Backend::matmul, src/backend/mod.rs:90; cpu/ops.rs:429-487).
+ * matvec: a[m][k] @ b[k] -> out[m] (mod.rs:93; cpu/ops.rs:531-575).  matvec_q: a = m rows of k/bs quantised blocks (mod.rs:107;
+ * cpu/ops.rs:922-946).  Required trait methods; the model code never calls them (compatibility surface). */
+B200_API int b200_op_matmul(const float* a, const float* b, float* out, size_t m, size_t k, size_t n);
+B200_API int b200_op_matvec(const float* a, const float* b, float* out, size_t m, size_t k);
+B200_API int b200_op_matvec_q(const void* a, uint32_t ggml_type, const float* b, float* out, size_t m, size_t k);
 /* vec_mat: a[k] @ W[k,n] (f32 W, GGUF layout: n rows of k). */
 B200_API int b200_op_vec_mat(const float* a, const float* w, float* out, size_t k, size_t n);
 /* vec_mat_q: W quantised, n rows of k/bs blocks (backend/mod.rs:110). */

@@ -126,6 +126,9 @@ def lib():
     L.b200_op_softmax.argtypes = [fp, fp, C.c_size_t]
     L.b200_op_rms_norm.argtypes = [fp, fp, C.c_float, fp, C.c_size_t, C.c_size_t]
     L.b200_op_vec_mat.argtypes = [fp, fp, fp, C.c_size_t, C.c_size_t]
+    L.b200_op_matmul.argtypes = [fp, fp, fp, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.b200_op_matvec.argtypes = [fp, fp, fp, C.c_size_t, C.c_size_t]
+    L.b200_op_matvec_q.argtypes = [vp, C.c_uint32, fp, fp, C.c_size_t, C.c_size_t]
     L.b200_op_vec_mat_q.argtypes = [fp, vp, C.c_uint32, fp, C.c_size_t, C.c_size_t]
     L.b200_op_mat_mat_q.argtypes = [fp, vp, C.c_uint32, fp, C.c_size_t, C.c_size_t, C.c_size_t]
     L.b200_op_dequantize.argtypes = [vp, C.c_uint32, fp, C.c_size_t]
@@ -286,8 +289,41 @@ class CudaB200Backend:
         return out
 
     def matvec_q(self, raw, ggml_type, x, m, k):
-        """A [m rows of k] quantised @ x [k] -> [m] (same block walk as vec_mat_q, cpu/ops.rs:1047-1120)."""
-        return self.vec_mat_q(x, raw, ggml_type, k, m)
+        """A [m rows of k] quantised @ x [k] -> [m] (Backend::matvec_q, cpu/ops.rs:922-946: the block walk of vec_mat_q)."""
+        if ggml_type not in BLOCK:
+            raise UnsupportedDType(f"matvec_q: ggml type {ggml_type}")
+        be, bb = BLOCK[ggml_type]
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.size != k or k % be or raw.size != m * (k // be) * bb:
+            raise ShapeMismatch(f"matvec_q: a {raw.size} bytes for [{m}, {k}] type {ggml_type}, b {x.size}")
+        out = np.empty(m, dtype=np.float32)
+        _check(lib().b200_op_matvec_q(raw.ctypes.data_as(C.c_void_p), ggml_type, _fp(x), _fp(out), m, k))
+        return out
+
+    def matmul(self, a, b):
+        """Backend::matmul (cpu/ops.rs:429-487): a [m, k] @ b [k, n], row-major f32."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        if a.ndim != 2 or b.ndim != 2:
+            raise InvalidArgument("matmul requires 2D tensors")
+        if a.shape[1] != b.shape[0]:
+            raise ShapeMismatch(f"matmul: expected {[a.shape[0], a.shape[1]]}, got {list(b.shape)}")
+        out = np.empty((a.shape[0], b.shape[1]), dtype=np.float32)
+        _check(lib().b200_op_matmul(_fp(a), _fp(b), _fp(out), a.shape[0], a.shape[1], b.shape[1]))
+        return out
+
+    def matvec(self, a, b):
+        """Backend::matvec (cpu/ops.rs:531-575): a [m, k] @ b [k] -> [m]."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        if a.ndim != 2 or b.ndim != 1:
+            raise InvalidArgument("matvec requires 2D matrix and 1D vector")
+        if b.shape[0] != a.shape[1]:
+            raise ShapeMismatch(f"matvec: expected {[a.shape[1]]}, got {list(b.shape)}")
+        out = np.empty(a.shape[0], dtype=np.float32)
+        _check(lib().b200_op_matvec(_fp(a), _fp(b), _fp(out), a.shape[0], a.shape[1]))
+        return out
 
     def dequantize(self, raw, ggml_type, n_elems):
         if ggml_type not in BLOCK:

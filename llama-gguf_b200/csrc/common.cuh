@@ -48,6 +48,10 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// f32 -> fp16 operand of the tcgen05 dequant-GEMM path, saturating: a finite activation above 65504 (Qwen2 FFN intermediates can get
+// there) must not become inf and then NaN in the residual stream.  NaN stays NaN.
+__device__ __forceinline__ __half f2h_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
+
 // Streaming (read-once) weight loads: non-coherent path, do not allocate in L1.
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 r;

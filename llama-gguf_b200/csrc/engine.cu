@@ -100,6 +100,7 @@ struct Slot {
     uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
     MegaPhase* d_phases = nullptr;  // per-token megakernel program of this slot (mega.cuh)
     MegaPhase* d_phases2 = nullptr; // the same program for stream2.cuh: EMBED phase first
+    std::vector<uint32_t> pending;  // tokens queued by b200_prefill_token (B200_PREFILL_QUEUE=1), not yet run
 };
 
 constexpr int kMaxGenerated = 1 << 16;
@@ -166,6 +167,8 @@ struct b200_ctx {
     // GEMM prefill (gemm_umma.cuh + prefill.cuh): activation rows of one chunk of prompt tokens
     bool use_prefill_gemm = true;
     int prefill_gemm_min = 32;
+    bool queue_bypass = false;    // (set while a queue is being flushed: its short tail runs token by token)
+    bool prefill_queue = false;   // b200_prefill_token queues; the queue runs as ONE GEMM prefill at the next call that needs the state
     float* pf_buf = nullptr;
     int* pf_tok = nullptr;
     uint8_t* pf_rows = nullptr;      // batched decode: per-row position | KV base pointer | SeqState pointer
@@ -268,6 +271,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_stream2 = env_int("B200_STREAM2", 1) != 0;
     c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
+    c->prefill_queue = env_int("B200_PREFILL_QUEUE", 0) != 0;
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
@@ -460,6 +464,11 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     c->out_scratch_elems = std::max<uint64_t>(std::max<uint64_t>(V, ffn_w), std::max<uint64_t>(H, nh * hd));
     CU_ALLOC(cudaMalloc((void**)&c->logits, c->out_scratch_elems * 4));
     c->n_splits = (int)std::min<uint64_t>(64, std::max<uint64_t>(1, (2 * (uint64_t)c->n_sm + nkv - 1) / nkv));
+    {   // the split merge stages n_splits * G * (hd + 2) floats in shared memory: it must fit the opt-in limit (G = 7..8 with hd = 128
+        // and 64 splits would need 233-266 KB: Qwen2.5-3B / Qwen2-7B shapes)
+        const uint64_t G = nh / nkv, lim = ((uint64_t)c->smem_optin - 2048) / (G * (hd + 2) * 4);
+        c->n_splits = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->n_splits, lim));
+    }
     CU_ALLOC(cudaMalloc((void**)&c->attn_part, nkv * c->n_splits * (nh / nkv) * (hd + 2) * 4));
     CU_ALLOC(cudaMalloc((void**)&c->tickets, nkv * sizeof(unsigned int)));
     CU(cudaMemset(c->tickets, 0, nkv * sizeof(unsigned int)));
@@ -791,6 +800,7 @@ static int mega_build(b200_ctx* c) {
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, G = nh / nkv;
     const size_t lim = c->smem_optin - 8192;
     c->mega_splits = (int)std::max(1, std::min(64, c->n_sm / nkv));
+    c->mega_splits = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->mega_splits, (lim - 4096) / ((size_t)G * (hd + 2) * 4)));   // merge scratch must fit
     size_t smem = attn_item_floats(hd, G <= 4 ? 4 : 8, kMmaMaxWarps, c->mega_splits, G) * sizeof(float);
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
     DevTensor head = c->output.present() ? c->output : c->token_embd;
@@ -1525,13 +1535,37 @@ static int watchdog_check(b200_ctx* c, const char* who) {
     char msg[200];
     snprintf(msg, sizeof msg, "%s: device watchdog tripped (code %d, wait %d, CTA %d, sequence %d): results discarded", who, c->h_err[0],
              c->h_err[1], c->h_err[2], c->h_err[3]);
+    // reported once: clear the words (a later call starts clean) and resynchronise every slot's host position with the device's
+    // (the launch may have advanced pos_next before it gave up)
+    cudaMemset(c->mma_err, 0, 8 * sizeof(int));
+    memset(c->h_err, 0, 8 * sizeof(int));
+    for (Slot& sl : c->slots) {
+        SeqState st{};
+        if (cudaMemcpy(&st, sl.d_state, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) sl.host_pos = (uint64_t)std::max(st.pos_next, 0);
+    }
     return fail(B200_ERR_OPERATION_FAILED, msg);
+}
+
+// GpuModelWrapper::forward prefills a prompt by calling prefill_token once per token (src/backend/mod.rs:343-346), which would keep
+// the tcgen05 GEMM prefill out of reach of an unchanged engine.  With B200_PREFILL_QUEUE=1 b200_prefill_token only queues the token
+// (position() counts it); the queue runs as one b200_prefill at the next call that needs the sequence state.  Off by default: the
+// GEMM path rounds its operands to fp16 (logits within 3e-3 of the exact path), the token-by-token path is exact.
+static int flush_pending(b200_ctx* c, int seq) {
+    Slot& sl = c->slots[seq];
+    if (sl.pending.empty()) return B200_OK;
+    std::vector<uint32_t> toks;
+    toks.swap(sl.pending);
+    c->queue_bypass = true;
+    const int rc = b200_prefill(c, seq, toks.data(), (int)toks.size(), nullptr);
+    c->queue_bypass = false;
+    return rc;
 }
 
 extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_out) {
     int rc;
     if ((rc = check_slot(c, seq, "b200_forward"))) return rc;
     if (!logits_out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_forward: null logits_out");
+    if ((rc = flush_pending(c, seq))) return rc;
     if ((rc = check_token(c, seq, token, "b200_forward"))) return rc;
     CU(cudaSetDevice(c->par.device));
     Slot& sl = c->slots[seq];
@@ -1553,6 +1587,12 @@ extern "C" int b200_prefill_token(b200_ctx* c, int seq, uint32_t token) {
     if ((rc = check_token(c, seq, token, "b200_prefill_token"))) return rc;
     CU(cudaSetDevice(c->par.device));
     Slot& sl = c->slots[seq];
+    if (c->prefill_queue && !c->queue_bypass && prefill_gemm_ok(c)) {
+        if (sl.host_pos + sl.pending.size() + 1 > (uint64_t)c->d.max_seq_len)
+            return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill_token: context length exceeded");
+        sl.pending.push_back(token);
+        return B200_OK;
+    }
     if ((rc = set_token(c, sl, token))) return rc;
     if ((rc = run_token(c, seq, MODE_PREFILL))) return rc;
     WATCHDOG_FETCH(c);
@@ -1566,6 +1606,7 @@ extern "C" int b200_prefill(b200_ctx* c, int seq, const uint32_t* tokens, int n,
     int rc;
     if ((rc = check_slot(c, seq, "b200_prefill"))) return rc;
     if (!tokens || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: no tokens");
+    if (!c->slots[seq].pending.empty() && (rc = flush_pending(c, seq))) return rc;
     if (n >= c->prefill_gemm_min && prefill_gemm_ok(c)) {
         for (int i = 0; i < n; i++)
             if (tokens[i] >= (uint32_t)c->d.vocab) return fail(B200_ERR_INVALID_ARGUMENT, "b200_prefill: token id exceeds vocab size");
@@ -1590,10 +1631,14 @@ extern "C" int b200_prefill(b200_ctx* c, int seq, const uint32_t* tokens, int n,
 
 extern "C" int b200_decode_batch(b200_ctx* c, const int* seqs, const uint32_t* tokens, int n, float* logits_out) {
     if (!c || !seqs || !tokens || !logits_out || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch: bad argument");
+    if (c->par.world_size > 1)   // a rank produces vocab / world_size logits per row: the n x vocab layout of this call does not apply
+        return fail(B200_ERR_UNSUPPORTED, "b200_decode_batch: not available under tensor parallelism (use b200_forward per sequence)");
     for (int i = 0; i < n; i++)
         for (int j = 0; j < i; j++)
             if (seqs[i] == seqs[j]) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch: duplicate sequence slot");
     int rc;
+    for (int i = 0; i < n; i++)
+        if (seqs[i] >= 0 && seqs[i] < (int)c->slots.size() && (rc = flush_pending(c, seqs[i]))) return rc;
     // n >= batch_gemm_min rows of an eligible dense model: ONE pass of the tcgen05 dequant-GEMMs for all the sequences (the
     // weights are read once per step instead of once per sequence); fp16 tensor-core operands, see gemm_umma.cuh
     if (n >= c->batch_gemm_min && prefill_gemm_ok(c)) {
@@ -1626,6 +1671,7 @@ extern "C" int b200_reset(b200_ctx* c, int seq) {
     if ((rc = check_slot(c, seq, "b200_reset"))) return rc;
     CU(cudaSetDevice(c->par.device));
     Slot& sl = c->slots[seq];
+    sl.pending.clear();
     CU(cudaMemsetAsync(sl.d_state, 0, sizeof(SeqState), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     sl.host_pos = 0;
@@ -1636,7 +1682,7 @@ extern "C" int b200_position(b200_ctx* c, int seq, uint64_t* out) {
     int rc;
     if ((rc = check_slot(c, seq, "b200_position"))) return rc;
     if (!out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_position: null out");
-    *out = c->slots[seq].host_pos;
+    *out = c->slots[seq].host_pos + c->slots[seq].pending.size();   // queued prefill tokens count (GpuInference::position)
     return B200_OK;
 }
 
@@ -1646,31 +1692,33 @@ extern "C" int b200_decode_greedy(b200_ctx* c, int seq, uint32_t first_token, in
     if ((rc = check_slot(c, seq, "b200_decode_greedy"))) return rc;
     if (n_steps <= 0 || n_steps > kMaxGenerated) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: bad n_steps");
     if (first_token >= (uint32_t)c->d.vocab) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: token exceeds vocab size");
+    if ((rc = flush_pending(c, seq))) return rc;
     Slot& sl = c->slots[seq];
     if (sl.host_pos + (uint64_t)n_steps > (uint64_t)c->d.max_seq_len)
         return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_greedy: context length exceeded");
     CU(cudaSetDevice(c->par.device));
     if ((rc = set_token(c, sl, first_token))) return rc;
     CU(cudaMemsetAsync(&sl.d_state->n_generated, 0, sizeof(int), c->stream));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    struct Events {   // destroyed on every exit path
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } ev;
+    CU(cudaEventCreate(&ev.e0));
+    CU(cudaEventCreate(&ev.e1));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaEventRecord(e0, c->stream));
+    CU(cudaEventRecord(ev.e0, c->stream));
     if (c->mega_ok) {
         if ((rc = mega_launch(c, seq, MEGA_GREEDY, n_steps))) return rc;
     } else {
         for (int i = 0; i < n_steps; i++)
             if ((rc = run_token(c, seq, MODE_GREEDY))) return rc;
     }
-    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventRecord(ev.e1, c->stream));
     WATCHDOG_FETCH(c);
     CU(cudaStreamSynchronize(c->stream));
     if ((rc = watchdog_check(c, "b200_decode_greedy"))) return rc;
     float ms = 0.0f;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CU(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     if (elapsed_ms) *elapsed_ms = ms;
     sl.host_pos += (uint64_t)n_steps;
     if (tokens_out) CU(cudaMemcpy(tokens_out, sl.d_generated, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1973,6 +2021,29 @@ extern "C" int b200_op_vec_mat(const float* a, const float* w, float* out, size_
 // Backend extension for prefill / batched decode: T input rows at once through the tcgen05 dequant-GEMM
 // (csrc/gemm_umma.cuh).  out[t][j] = sum_k a[t][k] * deq(W)[j][k]: the same contraction as T calls of vec_mat_q, fp16
 // operands with f32 accumulation (documented tolerance 2e-3 of the largest output).
+// Backend::matmul / matvec / matvec_q (src/backend/mod.rs:90, 93, 107): required trait methods that the model code never calls
+extern "C" int b200_op_matmul(const float* a, const float* b, float* out, size_t m, size_t k, size_t n) {
+    int rc;
+    if ((rc = op_ready())) return rc;
+    if (!a || !b || !out) return fail(B200_ERR_INVALID_ARGUMENT, "matmul: null pointer");
+    if (m == 0 || k == 0 || n == 0) return fail(B200_ERR_SHAPE_MISMATCH, "matmul: empty shape");
+    DevBuf da, db, dout;
+    if (da.alloc(m * k * 4) || db.alloc(k * n * 4) || dout.alloc(m * n * 4)) return fail(B200_ERR_ALLOCATION_FAILED, "matmul");
+    CU(cudaMemcpy(da.p, a, m * k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db.p, b, k * n * 4, cudaMemcpyHostToDevice));
+    matmul_f32_kernel<<<(int)((m * n + 255) / 256), 256>>>(da.as<float>(), db.as<float>(), dout.as<float>(), (int)m, (int)k, (int)n);
+    if ((rc = op_finish("matmul"))) return rc;
+    CU(cudaMemcpy(out, dout.p, m * n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+// matvec: a [m][k] row-major @ b [k] -> [m] (cpu/ops.rs:531-575): row i of a is k contiguous floats, exactly vec_mat's GGUF layout
+extern "C" int b200_op_matvec(const float* a, const float* b, float* out, size_t m, size_t k) { return b200_op_vec_mat(b, a, out, k, m); }
+// matvec_q: a = m rows of k / bs quantised blocks @ b [k] -> [m] (cpu/ops.rs:922-946): the block walk of vec_mat_q
+extern "C" int b200_op_vec_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t k, size_t n);
+extern "C" int b200_op_matvec_q(const void* a, uint32_t ggml_type, const float* b, float* out, size_t m, size_t k) {
+    return b200_op_vec_mat_q(b, a, ggml_type, out, k, m);
+}
+
 extern "C" int b200_op_mat_mat_q(const float* a, const void* w, uint32_t ggml_type, float* out, size_t t_rows, size_t k, size_t n) {
     int rc;
     if ((rc = op_ready())) return rc;

@@ -173,7 +173,7 @@ __device__ __forceinline__ void umma_deq64_q4k(const uint8_t* row, int k0, uint8
 
 // f32 -> fp16 of a GEMM input (per-op entry point; the prefill kernels write fp16 themselves)
 __global__ void umma_to_half_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = f2h_sat(x[i]);
 }
 
 struct UmmaParams {
@@ -385,12 +385,14 @@ inline bool umma_eligible(const UmmaParams& p) {
 template <int TN>
 inline cudaError_t umma_launch_tn(const UmmaParams& p, cudaStream_t st) {
     const size_t smem = (size_t)2 * (kUmmaM + TN) * 128 + (p.tmap ? 2 * kUmmaRawStage : 0) + 1024;   // two fp16 stages (+ two raw stages)
-    static bool once = false;   // per instantiation: the larger of the two layouts
-    if (!once) {
+    static bool once[64] = {};   // per instantiation AND device (function attributes are per device): the larger of the two layouts
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !once[dev]) {
         cudaError_t e = cudaFuncSetAttribute(dequant_gemm_umma_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)((size_t)2 * (kUmmaM + TN) * 128 + 2 * kUmmaRawStage + 1024));
         if (e != cudaSuccess) return e;
-        once = true;
+        if (dev >= 0 && dev < 64) once[dev] = true;
     }
     const int splits = p.k_split ? (p.K + p.k_split - 1) / p.k_split : 1;
     dim3 grid((p.n_rows + kUmmaM - 1) / kUmmaM, (p.T + TN - 1) / TN, splits);

@@ -229,4 +229,15 @@ __global__ void rope_inplace_kernel(float* q, float* k, const float* freq, int n
     }
 }
 
+// Backend::matmul (src/backend/cpu/ops.rs:429-487): out[m][n] = a[m][k] @ b[k][n], all row-major f32; one thread per output element,
+// k summed in order with separate multiply and add like matmul_simple (no FMA contraction in the reference).  Compatibility surface.
+__global__ void matmul_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int m, int k, int n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * n) return;
+    const int i = (int)(idx / n), j = (int)(idx - (long long)i * n);
+    float sum = 0.0f;
+    for (int kk = 0; kk < k; kk++) sum = __fadd_rn(sum, __fmul_rn(a[(size_t)i * k + kk], b[(size_t)kk * n + j]));
+    out[idx] = sum;
+}
+
 }  // namespace b200

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
         if (g < G) {
             const float inv = 1.0f / l[g];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) p.out[(size_t)t * p.ldo + (size_t)(kh * G + g) * HD + lane * VEC + v] = __float2half_rn(acc[g][v] * inv);
+            for (int v = 0; v < VEC; v++) p.out[(size_t)t * p.ldo + (size_t)(kh * G + g) * HD + lane * VEC + v] = f2h_sat(acc[g][v] * inv);
         }
     }
 }
@@ -208,14 +208,14 @@ __global__ void __launch_bounds__(256) prefill_rms_norm_kernel(const float* x, c
     float tot = 0.0f;
     for (int k = 0; k < 8; k++) tot += red[k];
     const float inv = 1.0f / sqrtf(tot / (float)n + eps);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) orow[i] = __float2half_rn(__fmul_rn(__fmul_rn(xr[i], inv), w[i]));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) orow[i] = f2h_sat(__fmul_rn(__fmul_rn(xr[i], inv), w[i]));
 }
 
 // g[i] = silu(g[i]) * u[i]  (silu rounded to f32 first, then the product: simd.rs:598-649)
 __global__ void prefill_swiglu_kernel(const float* __restrict__ g, const float* __restrict__ u, __half* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x = g[i];
-        out[i] = __float2half_rn((x / (1.0f + expf(-x))) * u[i]);
+        out[i] = f2h_sat((x / (1.0f + expf(-x))) * u[i]);
     }
 }
 

@@ -10,6 +10,7 @@ import numpy as np
 
 NEOX_ARCHS = {"qwen2", "qwen2moe", "qwen3", "qwen3moe", "gptneox", "falcon", "phi2", "phi3", "stablelm"}
 SUPPORTED_TYPES = {0, 1, 2, 6, 8, 12, 13, 14}
+SUPPORTED_ARCHS = {"llama", "mistral", "mixtral", "qwen2", "qwen2moe"}
 
 
 def load_gguf(path, max_batch=1):
@@ -24,6 +25,10 @@ def load_gguf(path, max_batch=1):
     arch = field("general.architecture")
     if arch is None:
         raise ValueError("missing metadata general.architecture")
+    if arch not in SUPPORTED_ARCHS:
+        # gemma (GELU), phi / gptneox (LayerNorm, fused QKV) ... share tensor names with llama but not its arithmetic
+        # (src/model/loader.rs:145-162, layers.rs uses_gelu): refuse instead of returning wrong logits
+        raise ValueError(f"unsupported architecture '{arch}': cuda-b200 implements {sorted(SUPPORTED_ARCHS)} (RMSNorm + SwiGLU + RoPE)")
 
     def u32(key, default=None):
         v = field(f"{arch}.{key}")
@@ -56,6 +61,9 @@ def load_gguf(path, max_batch=1):
         "expert_ffn": u32("expert_feed_forward_length", 0),
         "max_batch": max_batch,
     }
+    rd = field(f"{arch}.rope.dimension_count")
+    if rd is not None and int(rd) != desc["head_dim"]:
+        raise ValueError(f"partial RoPE (rope.dimension_count {int(rd)} != head_dim {desc['head_dim']}) is not implemented")
     tensors = {}
     for t in r.tensors:
         ttype = int(t.tensor_type)
