@@ -79,7 +79,7 @@ def main(args, preset, config, rank, world, local_rank):
     bytes_rank = wbytes_local + kvpp_local * kv_len_mid
     achieved = bytes_rank / (ms_per_step * 1e-3) / 1e9
     if rank == 0:
-        roofline = {"bound": "hbm", "kernel": ("stream_decode_kernel" if tp.path() == "stream" else "mega_decode_kernel") + " (per rank)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        roofline = {"bound": "hbm", "kernel": {"stream2": "stream2_decode_kernel", "stream": "stream_decode_kernel"}.get(tp.path(), "mega_decode_kernel") + " (per rank)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)", "traffic": None,
                     "bytes_per_launch": bytes_rank, "avg_launch_us": ms_per_step * 1e3,

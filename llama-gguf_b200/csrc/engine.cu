@@ -1108,8 +1108,17 @@ static const void* stream2_kernel_for(int hd, int G) {
 static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs, int max_K) {
     const b200_model_desc& d = c->d;
     c->stream2_ok = false;
-    if (!c->use_stream2 || c->par.world_size > 1 || !c->mega_stage[0]) return B200_OK;
+    if (!c->use_stream2 || (c->par.world_size > 1 && !env_int("B200_STREAM2_TP", 1))) return B200_OK;
+    const int P = c->par.world_size;
     const int hd = d.head_dim, G = d.n_heads / d.n_kv_heads, gmax = G <= 4 ? 4 : 8;
+    if (!c->mega_stage[0]) {   // tensor parallel: mega_build keeps no staged vectors (its kernels sum the partials while staging); this one does
+        if (P == 1 || d.hidden % 32 || (d.n_heads * hd) % 32 || d.ffn % 32) return B200_OK;
+        const int ks[4] = {d.hidden, d.hidden, d.n_heads * hd, (int)d.ffn};
+        for (int i = 0; i < 4; i++) {
+            CU_ALLOC(cudaMalloc((void**)&c->mega_stage[i], x_staged_bytes(ks[i]) + 256));
+            CU(cudaMemset(c->mega_stage[i], 0, x_staged_bytes(ks[i]) + 256));
+        }
+    }
     const void* kern = stream2_kernel_for(hd, G);
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kern));
@@ -1149,12 +1158,47 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
         prog2.push_back(em);
         for (size_t pi = 0; pi < progs[si].size(); pi++) {
             MegaPhase ph = progs[si][pi];
+            const int li = (int)(pi / 5), k5 = (int)(pi % 5);          // mega_build's program: 5 phases per layer (QKV, ATTN, O, GATE/UP, DOWN), then the head
+            const bool is_head = pi + 1 == progs[si].size();
+            MegaPhase red{};                                            // tensor parallel: the REDUCE phase that follows a row-parallel GEMV
+            bool have_red = false;
             if (ph.kind == PH_GEMV) {
                 MParams& m = ph.gemv;
-                m.x_staged = pi == 0 ? c->mega_stage[0] : m.x_staged;   // layer 0's QKV reads the staged embedding row
+                if (P == 1) {
+                    m.x_staged = pi == 0 ? c->mega_stage[0] : m.x_staged;   // layer 0's QKV reads the staged embedding row
+                } else {
+                    // the staged-vector wiring mega_build does for one GPU, plus the all-reduce: the ranks' partial vectors are summed (in
+                    // rank order, + residual) by a REDUCE phase that also writes the staged form the next GEMV copies
+                    const float* next_norm = is_head ? nullptr : (li + 1 < d.n_layers ? c->layers[li + 1].attn_norm.f32() : c->output_norm.f32());
+                    m.xsum = nullptr; m.n_sum = 0; m.x_res = nullptr; m.x_full_out = nullptr;   // (consumer-side summation is mega.cuh's protocol)
+                    if (is_head || k5 == 0) {
+                        m.x_staged = c->mega_stage[0];
+                    } else if (k5 == 2) {            // O projection: partial vectors -> buffer 0 of every rank; REDUCE: xb = sum + xa, staged with ffn_norm
+                        m.x_staged = c->mega_stage[2];
+                        m.stage_out = nullptr;
+                        red.gemv.xsum = tp_ar(c, c->tp_region, 0, 0); red.gemv.x_res = c->xa; red.gemv.x_full_out = c->xb;
+                        red.gemv.stage_out = c->mega_stage[1]; red.gemv.stage_w = c->layers[li].ffn_norm.f32();
+                        have_red = true;
+                    } else if (k5 == 3) {            // gate | up + SwiGLU -> staged hbuf (this rank's slice of the FFN)
+                        m.x_staged = c->mega_stage[1];
+                        m.stage_out = c->mega_stage[3]; m.stage_w = nullptr; m.stage_K = (int)d.ffn;
+                    } else if (k5 == 4) {            // down projection: partial vectors -> buffer 1; REDUCE: xa = sum + xb, staged with the next norm
+                        m.x_staged = c->mega_stage[3];
+                        m.stage_out = nullptr;
+                        red.gemv.xsum = tp_ar(c, c->tp_region, 1, 0); red.gemv.x_res = c->xb; red.gemv.x_full_out = c->xa;
+                        red.gemv.stage_out = c->mega_stage[0]; red.gemv.stage_w = next_norm;
+                        have_red = true;
+                    }
+                    if (have_red) {
+                        red.kind = PH_REDUCE;
+                        red.gemv.K = d.hidden; red.gemv.stage_K = d.hidden;
+                        red.gemv.n_sum = P; red.gemv.sum_stride = d.hidden;
+                        if (!ph.tp_sync || m.n_peer != P) return B200_OK;   // (mega_build marks the row-parallel phases)
+                    }
+                }
                 if (!m.x_staged) return B200_OK;
                 m.s_E = m.s_tiles * m.s_parts * m.s_ept;
-                m.cand = (pi + 1 == progs[si].size()) ? 1 : 0;
+                m.cand = is_head ? 1 : 0;
                 {   // jobs per entry (stream2.cuh): the coarsest split whose last round of the 14 consumer warps is (nearly) as full as the best
                     const double per = (double)m.s_E / c->n_sm;
                     auto waste = [&](int n) { return std::ceil(per * n / kS2Cons) * kS2Cons / std::max(per * n, 1e-9); };
@@ -1174,8 +1218,10 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                 m.x_bytes = (int)x_staged_bytes(m.K);
             } else {
                 ph.attn.min_chunk = min_chunk2;
+                if (P > 1) { ph.attn.stage_out = c->mega_stage[2]; ph.attn.stage_K = d.n_heads * hd; }
             }
             prog2.push_back(ph);
+            if (have_red) prog2.push_back(red);
         }
         Slot& sl = c->slots[si];
         if (sl.d_phases2) cudaFree(sl.d_phases2);
@@ -1216,7 +1262,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         }
         mp.tp_epoch0 = c->tp_epoch;
         const int per_token = 2 * d.n_layers + (mode == MEGA_GREEDY ? 1 : 0);
-        c->tp_epoch += (unsigned int)(per_token * n_tokens);
+        c->tp_epoch += (unsigned int)(per_token * n_tokens) + (c->stream2_ok ? 1u : 0u);   // (stream2: the last token's pick is one more exchange)
     }
     CU(cudaMemsetAsync(c->mega_bar, 0, sizeof(unsigned int), c->stream));
     if (c->stream2_ok) {
@@ -1228,6 +1274,7 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
         sp.n_slots = c->s2_slots;
         sp.no_load = env_int("B200_STREAM_NOLOAD", 0);
         sp.ll = c->s2_ll;
+        sp.tp_per_token = 2 * d.n_layers + (mode == MEGA_GREEDY ? 1 : 0);
         sp.epoch0 = c->s2_epoch;
         c->s2_epoch += (unsigned int)(n_tokens * c->s2_phases + 2);
         sp.cand_val = c->s2_cand_val; sp.cand_idx = c->s2_cand_idx;

@@ -58,7 +58,7 @@ constexpr int kS2SlotBytes = kStreamSlotBytes;    // 9216: 32 rows x 288 bytes (
 constexpr int kS2MaxSlots = 24;
 constexpr int kS2TileSlots = 4;
 constexpr int kS2ZeroBytes = 512;                 // zero page in front of the x region; B operands of idle columns read base + 96
-enum : int { PH_EMBED = 2 };
+enum : int { PH_EMBED = 2, PH_REDUCE = 3 };   // REDUCE (tensor parallel): sum of the ranks' partial vectors + residual -> f32 vector + staged form
 
 struct Stream2Params {
     MegaParams mp;            // mp.phases: [EMBED, L x (QKV, ATTN, O, GATE/UP, DOWN), HEAD]
@@ -70,6 +70,8 @@ struct Stream2Params {
     int no_load;
     uint2* ll;                // [grid][2][32] (value, epoch) packets of tile pieces
     unsigned int epoch0;      // packets of this launch carry epoch0 + global phase number + 1
+    int tp_per_token;         // tensor parallel: cross-GPU exchanges per token E (2 per layer, + 1 for the greedy pick); exchange ids of a launch:
+                              // token t's k-th row-parallel exchange = t E + k, the pick that opens token t >= 1 = t E, the final pick = n_tokens E
     float* cand_val;          // [grid] argmax candidates of the vocab head (one per CTA)
     int* cand_idx;
 };
@@ -557,6 +559,8 @@ __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2
             val += e_res;
             if (cand) {   // raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821)
                 if (val > best.v || (val == best.v && j > best.i) || best.i < 0) { best.v = val; best.i = j; }
+            } else if (p.n_peer > 0) {   // partial of a row-parallel GEMV, to every rank's buffer (NVLink peer memory); summed by the REDUCE phase
+                for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;
             } else {
                 sg.out[j] = val;
             }
@@ -866,7 +870,8 @@ __device__ __forceinline__ void attn2_phase(const AttnParams& p, int kv_len, flo
 }
 
 // ---------------------------------------------------------------- CTA 0: pick (greedy) + embedding row + its staged form
-__device__ __forceinline__ void s2_pick(const Stream2Params& sp, float* s_av, int* s_ai, int* s_tok) {
+// tp_ep: (tensor parallel) number of this cross-GPU exchange within the launch, the same on every rank
+__device__ __forceinline__ void s2_pick(const Stream2Params& sp, float* s_av, int* s_ai, int* s_tok, unsigned int tp_ep = 0) {
     const MegaParams& mp = sp.mp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)gridDim.x;   // one candidate per CTA (its loader warp ran the vocab head's epilogues)
@@ -888,6 +893,34 @@ __device__ __forceinline__ void s2_pick(const Stream2Params& sp, float* s_av, in
     if (tid == 0) {
         for (int w = 1; w < kS2Cons; w++)
             if (s_ai[w] >= 0 && (bi < 0 || s_av[w] > best || (s_av[w] == best && s_ai[w] > bi))) { best = s_av[w]; bi = s_ai[w]; }
+        if (mp.tp_size > 1) {   // every rank picks the same winner among the per-rank candidates (ties: largest global index)
+            const unsigned int ep = mp.tp_epoch0 + tp_ep;
+            if (bi >= 0) bi += mp.tp_rank * mp.vocab_local;
+            for (int r = 0; r < mp.tp_size; r++) {
+                float* dst = mp.tp_peer_cand[r] + 2 * mp.tp_rank;
+                asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(best) : "memory");
+                asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + 1), "f"(__int_as_float(bi)) : "memory");
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int r = 0; r < mp.tp_size; r++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[r] + mp.tp_rank), "r"(ep) : "memory");
+            const long long t0 = clock64();
+            best = -INFINITY;
+            bi = -1;
+            for (int r = 0; r < mp.tp_size; r++) {
+                for (;;) {
+                    unsigned int fv;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(fv) : "l"(mp.tp_flags + r) : "memory");
+                    if ((int)(fv - ep) >= 0) break;
+                    if (clock64() - t0 > 3000000000LL) { atomicExch(mp.err, 3); break; }
+                }
+                float cv, ci;
+                asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(cv) : "l"(mp.tp_cand + 2 * r) : "memory");
+                asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(ci) : "l"(mp.tp_cand + 2 * r + 1) : "memory");
+                const int ii = __float_as_int(ci);
+                if (ii >= 0 && (bi < 0 || cv > best || (cv == best && ii > bi))) { best = cv; bi = ii; }
+            }
+        }
         mp.st->token = bi;
         const int gcount = mp.st->n_generated;
         if (gcount < mp.max_generated) mp.generated[gcount] = bi;
@@ -897,11 +930,11 @@ __device__ __forceinline__ void s2_pick(const Stream2Params& sp, float* s_av, in
     s2_cons_sync();
 }
 
-__device__ __forceinline__ void s2_embed(const MParams& p, const Stream2Params& sp, bool pick, float* s_av, int* s_ai, int* s_tok) {
+__device__ __forceinline__ void s2_embed(const MParams& p, const Stream2Params& sp, bool pick, float* s_av, int* s_ai, int* s_tok, unsigned int tp_ep) {
     const MegaParams& mp = sp.mp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (pick) {
-        s2_pick(sp, s_av, s_ai, s_tok);
+        s2_pick(sp, s_av, s_ai, s_tok, tp_ep);
     } else {
         if (tid == 0) *s_tok = __ldcg(&mp.st->token);
         s2_cons_sync();
@@ -925,6 +958,23 @@ __device__ __forceinline__ void s2_embed(const MParams& p, const Stream2Params& 
     }
 }
 
+// ---------------------------------------------------------------- REDUCE phase (tensor parallel)
+// The all-reduce of a row-parallel GEMV, finished locally and identically on every rank: x[j] = sum over ranks (rank order) of the partial
+// vectors the ranks left in this GPU's buffer + the residual; stored as f32 (it is the residual of a later phase) and in the staged form the
+// next GEMV's bulk copy reads.  32 consecutive elements per warp step (the staged form needs whole groups).
+__device__ __forceinline__ void s2_reduce_phase(const MParams& p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_grp = p.K >> 5;
+    for (int grp = (int)blockIdx.x * kS2Cons + warp; grp < n_grp; grp += (int)gridDim.x * kS2Cons) {
+        const int j = grp * 32 + lane;
+        float v = __ldcg(p.xsum + j);
+        for (int r = 1; r < p.n_sum; r++) v += __ldcg(p.xsum + (size_t)r * p.sum_stride + j);
+        if (p.x_res) v += __ldcg(p.x_res + j);
+        if (p.x_full_out) p.x_full_out[j] = v;
+        stage_out32(v, p.stage_w ? p.stage_w[j] : 1.0f, j, p.stage_K, p.stage_out);
+    }
+}
+
 // ---------------------------------------------------------------- loader warp: the phase boundary, then the phase's epilogues
 __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t done, int* s_pos, float* s_rope,
                                           int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead) {
@@ -941,10 +991,13 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
     S2Best best{-INFINITY, -1};
     int kv_len = 1;
     int ph = 0;
+    bool prev_tp = false;          // the phase that just ended left partial sums in the peers' memory
+    unsigned int tp_tok = 0, tp_k = 0;   // token of the launch, row-parallel exchanges of that token so far
     for (long long gb = 0; gb < total + (greedy ? 1 : 0); gb++) {
         const bool last = gb == total;     // the boundary after the last vocab head (greedy: CTA 0 picks the last token)
         const MegaPhase& cur = s_desc[gb & 1];
         unsigned long long* ldbg = nullptr;   // stamps of the boundary BEFORE a phase go to that phase's debug buffer
+        __syncwarp();   // the epilogue stores of every lane are ordered before lane 0's release below
         if (lane == 0) {
             uint32_t tx = 0;
             if (gb > 0) {
@@ -985,7 +1038,8 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
             if (early) mbar_arrive_expect_tx(xfull, tx);
             if (gb > 0) {   // grid barrier: everything every CTA wrote in phase gb - 1 is visible after this
                 target += gridDim.x;
-                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(mp.bar) : "memory");
+                if (prev_tp) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(mp.bar) : "memory");   // stores to peer memory included
+                else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(mp.bar) : "memory");
                 if (ldbg) ldbg[1] = (unsigned long long)clock64();
                 unsigned int v = 0;
                 const long long t0 = clock64();
@@ -996,6 +1050,26 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
                         *s_dead = 1;
                         if (atomicExch(mp.err, 2) == 0) { mp.err[1] = 3000; mp.err[2] = (int)blockIdx.x; mp.err[3] = (int)target; }
                         break;
+                    }
+                }
+                if (prev_tp) {
+                    // every CTA of THIS GPU has arrived, i.e. this rank's partial sums are in every peer's memory: CTA 0 says so to
+                    // the peers; every CTA waits (in local memory) until every rank has said so
+                    const unsigned int ep = mp.tp_epoch0 + tp_tok * (unsigned int)sp.tp_per_token + (++tp_k);
+                    if (blockIdx.x == 0)
+                        for (int r = 0; r < mp.tp_size; r++)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mp.tp_peer_flags[r] + mp.tp_rank), "r"(ep) : "memory");
+                    for (int r = 0; r < mp.tp_size; r++) {
+                        for (;;) {
+                            unsigned int fv;
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(fv) : "l"(mp.tp_flags + r) : "memory");
+                            if ((int)(fv - ep) >= 0) break;
+                            if (*s_dead || clock64() - t0 > 3000000000LL) {
+                                *s_dead = 1;
+                                if (atomicExch(mp.err, 3) == 0) { mp.err[1] = 5000 + r; mp.err[2] = (int)blockIdx.x; mp.err[3] = (int)ep; }
+                                break;
+                            }
+                        }
                     }
                 }
                 if (mp.dbg && blockIdx.x == 0) mp.dbg[last ? n_run : ph] = gtimer();   // boundary BEFORE phase ph of the current token
@@ -1026,11 +1100,12 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
             }
             __syncwarp();
         }
+        prev_tp = cur.tp_sync != 0;
         if (cur.kind == PH_GEMV) {
             tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), tseq0, s_tcnt, s_tdone, s_dead,
                                                  sp.epoch0 + (unsigned int)gb + 1u, greedy, best);
         }
-        if (++ph == n_run) ph = 0;
+        if (++ph == n_run) { ph = 0; tp_tok++; tp_k = 0; }
     }
 }
 
@@ -1110,9 +1185,12 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
             } else if (cur.kind == PH_ATTN) {
                 attn2_phase<HD, GMAX, kS2Cons>(cur.attn, s_pos + 1, reinterpret_cast<float*>(smem + sp.xr_off), xfull, xpar, &s_dead, mp.err,
                                                epoch, &s_ticket, s_rope);
+            } else if (cur.kind == PH_REDUCE) {
+                s_wait(xfull, xpar, &s_dead, mp.err, 6250, epoch);
+                s2_reduce_phase(cur.gemv);
             } else {
                 s_wait(xfull, xpar, &s_dead, mp.err, 6200, epoch);
-                if (blockIdx.x == 0) s2_embed(cur.gemv, sp, greedy && tok > 0, s_av, s_ai, &s_tok);
+                if (blockIdx.x == 0) s2_embed(cur.gemv, sp, greedy && tok > 0, s_av, s_ai, &s_tok, (unsigned int)(tok * sp.tp_per_token));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(done);
@@ -1120,7 +1198,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     }
     if (greedy) {   // the last token's pick, after the boundary that follows its vocab head
         s_wait(xfull, (uint32_t)(gph & 1), &s_dead, mp.err, 6300, (uint32_t)gph);
-        if (blockIdx.x == 0) s2_pick(sp, s_av, s_ai, &s_tok);
+        if (blockIdx.x == 0) s2_pick(sp, s_av, s_ai, &s_tok, (unsigned int)(mp.n_tokens * sp.tp_per_token));
     }
     s_drain(&s_dead);
 }

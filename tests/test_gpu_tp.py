@@ -91,7 +91,7 @@ def test_tp2_matches_single_gpu_and_oracle(b200, mix, preset):
         assert p.exitcode == 0
     r0, r1 = outs[0], outs[1]
     # shards whose rows are 16-byte multiples run the streamed megakernel under TP too, the rest the first megakernel
-    assert r0["path"] == r1["path"] == ("stream" if preset == "llama-stream-tiny" or mix == "Q8_0" else "mega")
+    assert r0["path"] == r1["path"] == ("stream2" if preset == "llama-stream-tiny" or mix == "Q8_0" else "mega")
     assert np.array_equal(r0["logits"], r1["logits"])                      # every rank sees the same gathered logits
     assert synth.rel_err(r0["logits"], r0["want"]) < 1e-3                   # north_star tolerance vs the CPU reference path
     assert synth.rel_err(r0["logits"], r0["single_logits"]) < 1e-4          # summation order differs, nothing else
