@@ -629,7 +629,7 @@ static void fill_seg(GemvSeg& s, const DevTensor& w, float* out, const DevTensor
 }
 
 // Tensor-pipe kernel when the launch is eligible (K-quants / Q8_0, shapes that fit), else the CUDA-core kernel.
-static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& plan) {
+static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& plan, size_t smem_limit = 0) {
     m = MParams{};
     for (int s = 0; s < p.n_seg; s++) {
         MSeg& d = m.seg[s];
@@ -641,7 +641,7 @@ static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& p
     m.epi = p.epi == EPI_STORE ? ME_STORE : p.epi == EPI_RESIDUAL ? ME_RESIDUAL : p.epi == EPI_SWIGLU ? ME_SWIGLU : ME_SCALED_ACC;
     m.expert_sel = p.expert_sel; m.expert_wt = p.expert_wt; m.expert_slot = p.expert_slot;
     m.part = c->mma_part; m.tickets = c->mma_tickets; m.err = c->mma_err;
-    if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, c->smem_optin - 8192, plan)) return false;
+    if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, smem_limit ? smem_limit : c->smem_optin - 8192, plan)) return false;
     int tiles = 0;
     for (int s = 0; s < m.n_seg; s++) tiles += m.seg[s].n_tiles;
     return tiles <= c->mma_tickets_n;
@@ -842,10 +842,16 @@ static int mega_build(b200_ctx* c) {
         const int w = c->mma_warps, st = c->mma_stages;
         c->mma_warps = kMmaMaxWarps;
         c->mma_stages = kMegaStages;
-        const bool ok = to_mma_params(c, g, m, plan);
+        // (second try without a shared-memory limit: a phase whose x + cp.async rings do not fit the first megakernel -- K = 28672 -- still gets its
+        // program entry; mega_fits below decides whether that kernel can run, the streamed kernels have their own plans)
+        bool ok = to_mma_params(c, g, m, plan);
+        if (!ok) ok = to_mma_params(c, g, m, plan, (size_t)1 << 30);
         c->mma_warps = w;
         c->mma_stages = st;
-        if (!ok || plan.warps != kMmaMaxWarps) return false;
+        if (!ok || plan.warps != kMmaMaxWarps) {
+            if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] mega_build: phase not eligible (K %d, %d segments, type %d, rows %d, plan %s, warps %d)\n", g.K, g.n_seg, g.seg[0].type, g.seg[0].n_rows, ok ? "ok" : "failed", plan.warps);
+            return false;
+        }
         mma_deal(m, c->n_sm);  // every phase runs on the full grid of the megakernel
         ph = MegaPhase{};
         ph.kind = PH_GEMV;
@@ -955,15 +961,23 @@ static int mega_build(b200_ctx* c) {
         CU(cudaMemcpy(sl.d_phases, prog.data(), prog.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
         c->mega_phases = (int)prog.size();
     }
-    if (smem > lim) return B200_OK;
+    // The first megakernel keeps x AND a cp.async ring per warp in shared memory: K = 28672 (Llama-3-70B's FFN) does not fit.  The streamed
+    // kernels only need the phase program built above, so they are tried either way; mega_ok then means "some per-token megakernel runs".
+    bool mega_fits = smem <= lim;
     c->mega_smem = smem;
-    const void* kern = mega_kernel_for(hd, G);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMmaMaxWarps * 32, smem));
-    if (per_sm < 1) return B200_OK;
-    c->mega_ok = true;
-    return stream_build(c);
+    if (mega_fits) {
+        const void* kern = mega_kernel_for(hd, G);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMmaMaxWarps * 32, smem));
+        mega_fits = per_sm >= 1;
+    }
+    c->mega_ok = true;   // (stream_build / stream2_build read the phase programs; they do not look at this flag)
+    const int rc = stream_build(c);
+    if (rc != B200_OK) return rc;
+    if (!mega_fits) c->mega_ok = c->stream_ok || c->stream2_ok;
+    if (!mega_fits && env_int("B200_LOG", 0)) fprintf(stderr, "[b200] mega_build: first megakernel does not fit (%zu bytes of shared memory), streamed kernel %s\n", smem, c->mega_ok ? "runs" : "not eligible either");
+    return B200_OK;
 }
 
 
@@ -1068,15 +1082,23 @@ static int stream_build(b200_ctx* c) {
     size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn_item_floats(hd, G <= 4 ? 4 : 8, kSW, c->mega_splits, G) * sizeof(float));
     x_region = (x_region + 127) & ~(size_t)127;
     const size_t avail = c->smem_optin - fa.sharedSizeBytes;
-    if (avail < x_region + 3 * (size_t)kStreamSlotBytes) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 7, line %d)\n", __LINE__); return B200_OK; }
-    int slots = (int)std::min<size_t>(kStreamMaxSlots, (avail - x_region) / kStreamSlotBytes);
-    slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kStreamMaxSlots)));
-    if (slots <= kSW) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (%d ring slots)\n", slots); return B200_OK; }   // the parity protocol needs more slots than consumer warps
-    const size_t smem = x_region + (size_t)slots * kStreamSlotBytes;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
-    if (per_sm < 1) { if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: not eligible (check 8, line %d)\n", __LINE__); return B200_OK; }
+    // whether the FIRST streamed kernel can run (the second one has its own shared-memory plan: stream2_build, tried either way)
+    bool s1_ok = avail >= x_region + 3 * (size_t)kStreamSlotBytes;
+    int slots = 0;
+    size_t smem = 0;
+    if (s1_ok) {
+        slots = (int)std::min<size_t>(kStreamMaxSlots, (avail - x_region) / kStreamSlotBytes);
+        slots = std::min(slots, std::max(2, env_int("B200_STREAM_SLOTS", kStreamMaxSlots)));
+        s1_ok = slots > kSW;   // the parity protocol needs more slots than consumer warps
+    }
+    if (s1_ok) {
+        smem = x_region + (size_t)slots * kStreamSlotBytes;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamThreads, smem));
+        s1_ok = per_sm >= 1;
+    }
+    if (!s1_ok && env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: first streamed kernel not eligible (x region %zu of %zu bytes, %d slots)\n", x_region, avail, slots);
     if (c->d_tmaps) cudaFree(c->d_tmaps);
     c->d_tmaps = nullptr;
     CU_ALLOC(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
@@ -1092,8 +1114,8 @@ static int stream_build(b200_ctx* c) {
     c->stream_smem = smem;
     c->stream_ring_off = (int)x_region;
     c->stream_slots = slots;
-    c->stream_ok = true;
-    if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: ok, %d slots, ring_off %d, smem %zu, %zu tensor maps\n", slots, (int)x_region, smem, maps.size());
+    c->stream_ok = s1_ok;
+    if (s1_ok && env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream_build: ok, %d slots, ring_off %d, smem %zu, %zu tensor maps\n", slots, (int)x_region, smem, maps.size());
     return stream2_build(c, progs, max_K);
 }
 
@@ -1110,6 +1132,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
     c->stream2_ok = false;
     if (!c->use_stream2 || (c->par.world_size > 1 && !env_int("B200_STREAM2_TP", 1))) return B200_OK;
     const int P = c->par.world_size;
+    const bool tp_fold = P > 1 && env_int("B200_TP_FOLD", 1);
     const int hd = d.head_dim, G = d.n_heads / d.n_kv_heads, gmax = G <= 4 ? 4 : 8;
     if (!c->mega_stage[0]) {   // tensor parallel: mega_build keeps no staged vectors (its kernels sum the partials while staging); this one does
         if (P == 1 || d.hidden % 32 || (d.n_heads * hd) % 32 || d.ffn % 32) return B200_OK;
@@ -1170,8 +1193,19 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                     // the staged-vector wiring mega_build does for one GPU, plus the all-reduce: the ranks' partial vectors are summed (in
                     // rank order, + residual) by a REDUCE phase that also writes the staged form the next GEMV copies
                     const float* next_norm = is_head ? nullptr : (li + 1 < d.n_layers ? c->layers[li + 1].attn_norm.f32() : c->output_norm.f32());
-                    m.xsum = nullptr; m.n_sum = 0; m.x_res = nullptr; m.x_full_out = nullptr;   // (consumer-side summation is mega.cuh's protocol)
-                    if (is_head || k5 == 0) {
+                    // B200_TP_FOLD=1 (default): no REDUCE phase -- the GEMV that consumes the sum keeps mega_build's xsum / x_res / x_full_out
+                    // wiring and its consumer warps finish the all-reduce while they stage x in shared memory (stream2.cuh: s2_gemv_cta)
+                    const bool fold = tp_fold && m.n_sum > 0;
+                    if (!fold) { m.xsum = nullptr; m.n_sum = 0; m.x_res = nullptr; m.x_full_out = nullptr; }
+                    if (fold) {
+                        if (!m.norm_w || m.K != d.hidden || (k5 != 0 && k5 != 3 && !is_head)) return B200_OK;
+                        m.x_staged = nullptr;
+                        if (k5 == 3) { m.stage_out = c->mega_stage[3]; m.stage_w = nullptr; m.stage_K = (int)d.ffn; }
+                    } else if (tp_fold && (k5 == 2 || k5 == 4)) {   // row-parallel: partial vectors to every rank, nothing staged
+                        m.x_staged = c->mega_stage[k5 == 2 ? 2 : 3];
+                        m.stage_out = nullptr;
+                        if (!ph.tp_sync || m.n_peer != P) return B200_OK;
+                    } else if (is_head || k5 == 0) {
                         m.x_staged = c->mega_stage[0];
                     } else if (k5 == 2) {            // O projection: partial vectors -> buffer 0 of every rank; REDUCE: xb = sum + xa, staged with ffn_norm
                         m.x_staged = c->mega_stage[2];
@@ -1196,7 +1230,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                         if (!ph.tp_sync || m.n_peer != P) return B200_OK;   // (mega_build marks the row-parallel phases)
                     }
                 }
-                if (!m.x_staged) return B200_OK;
+                if (!m.x_staged && m.n_sum == 0) return B200_OK;
                 m.s_E = m.s_tiles * m.s_parts * m.s_ept;
                 m.cand = is_head ? 1 : 0;
                 {   // jobs per entry (stream2.cuh): the coarsest split whose last round of the 14 consumer warps is (nearly) as full as the best
@@ -1215,7 +1249,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                     m.s_jsh = (m.s_J == 2 ? 1 : 0) + (m.s_R == 2 ? 1 : 0);
                     if (env_int("B200_LOG", 0) && si == 0 && pi < 6) fprintf(stderr, "[b200] stream2 phase %zu: E %d (%.1f per CTA), C %d, jobs per entry %d x %d, waste %.3f\n", pi, m.s_E, per, m.s_C, m.s_J, m.s_R, waste(m.s_J * m.s_R));
                 }
-                m.x_bytes = (int)x_staged_bytes(m.K);
+                m.x_bytes = m.x_staged ? (int)x_staged_bytes(m.K) : 0;
             } else {
                 ph.attn.min_chunk = min_chunk2;
                 if (P > 1) { ph.attn.stage_out = c->mega_stage[2]; ph.attn.stage_K = d.n_heads * hd; }

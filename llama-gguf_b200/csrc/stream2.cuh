@@ -241,8 +241,43 @@ __device__ __forceinline__ void pin2(float (&a)[2]) { asm volatile("" : "+f"(a[0
 // issued, 4 first tile merged, 5 last tile's epilogue done
 #define S2_STAMP(DBG, k) do { if ((DBG) && (threadIdx.x & 31) == 0) (DBG)[((size_t)blockIdx.x * 16 + (threadIdx.x >> 5)) * 8 + (k)] = (unsigned long long)clock64(); } while (0)
 
+// Tensor parallel, input of a GEMV that follows a row-parallel one: the all-reduce is finished by the consumer warps of EVERY CTA of every
+// rank, identically -- x[j] = sum over ranks (rank order) of the partial vectors the ranks left in this GPU's buffer + the residual, staged
+// straight into shared memory (the bytes a REDUCE phase would have written to global memory and the loader copied back: one grid boundary
+// less per exchange).  CTA b also stores the groups b, b + grid, ... of the f32 vector (a later residual).  Not inlined: the single-GPU
+// register allocation of s2_gemv_cta must not see this code (measured: 1 % slower inlined).
+__device__ __noinline__ void s2_fold_stage(const MParams& p, uint8_t* xs, uint32_t xstg) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_grp = p.K >> 5;
+    for (int g0 = warp; g0 < n_grp; g0 += 4 * kS2Cons) {
+        float v[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int grp = g0 + u * kS2Cons, j = grp * 32 + lane;
+            v[u] = 0.f; w[u] = 1.f;
+            if (grp < n_grp) {
+                v[u] = __ldcg(p.xsum + j);
+                for (int r = 1; r < p.n_sum; r++) v[u] += __ldcg(p.xsum + (size_t)r * p.sum_stride + j);
+                if (p.x_res) v[u] += __ldcg(p.x_res + j);
+                if (p.norm_w) w[u] = p.norm_w[j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int grp = g0 + u * kS2Cons, j = grp * 32 + lane;
+            if (grp < n_grp) {
+                if (p.x_full_out && grp % (int)gridDim.x == (int)blockIdx.x) p.x_full_out[j] = v[u];
+                stage_out32(v[u], w[u], j, p.K, xs);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the region is the target of later bulk copies)
+    s2_cons_sync();
+    if (threadIdx.x == 0) mbar_arrive(xstg);   // the loader warp reads the groups' sums of squares (1 / rms)
+}
+
 __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Params& sp, uint8_t* smem, const SRing& rg, S2Cons& cs,
-                                            uint32_t xfull, uint32_t xpar, int* s_tcnt, volatile unsigned int* s_tdone,
+                                            uint32_t xfull, uint32_t xpar, uint32_t xstg, int* s_tcnt, volatile unsigned int* s_tdone,
                                             volatile int* s_dead, unsigned int epoch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem);
@@ -309,6 +344,7 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
 
     // ---- the phase's input: staged by its producer, copied by the loader warp; everything above overlapped the boundary ----
     s_wait(xfull, xpar, s_dead, p.err, 6000, epoch);
+    if (p.n_sum > 0) s2_fold_stage(p, smem + sp.xr_off, xstg);
     S2_STAMP(dbg, 1);
     {
         xtok = smem_token();
@@ -442,13 +478,16 @@ struct S2Best {
     int i;
 };
 __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t xpar,
-                                                  uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead,
-                                                  unsigned int epoch, bool greedy, S2Best& best) {
+                                                  uint32_t xstg, uint32_t& n_fold, uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone,
+                                                  volatile int* s_dead, unsigned int epoch, bool greedy, S2Best& best) {
     const int lane = threadIdx.x & 31;
     const bool swiglu = p.epi == ME_SWIGLU;
     const int per_tile = p.s_parts * p.s_ept;
     const S2Deal dl = s2_deal(p);
     const int e0 = dl.e0, e1 = dl.e0 + dl.nloc;
+    const bool fold = p.n_sum > 0;             // (tensor parallel) the consumers stage the input themselves: see s2_gemv_cta
+    const uint32_t fold_par = n_fold & 1u;
+    if (fold) n_fold++;
     if (dl.n_ltiles == 0) {
         if (greedy && p.cand && lane == 0) {   // no tile of the vocab head here: no candidate
             sp.cand_val[blockIdx.x] = -INFINITY;
@@ -460,7 +499,8 @@ __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2
     unsigned long long* const dbg = p.dbg;
     float unscale = 1.0f;
     if (p.norm_w) {   // sum of x^2 from the per-group partial sums of the staged input: the loader waits for its own copy
-        s_wait(xfull, xpar, s_dead, p.err, 6400, epoch);
+        if (fold) s_wait(xstg, fold_par, s_dead, p.err, 6450, epoch);
+        else s_wait(xfull, xpar, s_dead, p.err, 6400, epoch);
         const uint32_t ssq = smem_u32(smem) + (uint32_t)sp.xr_off + x_layout(p.K).ssq + smem_token();
         float tot = 0.0f;
         for (int k = lane; k < (p.K >> 5); k += 32) tot += lds_f32(ssq + 4u * (uint32_t)k);
@@ -649,9 +689,12 @@ __device__ __forceinline__ void attn2_phase(const AttnParams& p, int kv_len, flo
         }
     };
     // rows of earlier positions do not depend on this token: request the first batch before waiting for the boundary
-    float kA[UB][VEC], vA[UB][VEC];
+    float kA[UB][VEC], vA[UB][VEC], kB[UB][VEC], vB[UB][VEC];
     int pos0 = start + warp;
     if (active && pos0 < end_g) load(pos0, kA, vA);
+#ifndef B200_NO_ATTN_PRE2
+    if (active && pos0 + STEP < end_g) load(pos0 + STEP, kB, vB);   // (32 positions per split = two batches per warp: nothing is left to fetch after the boundary)
+#endif
 
     s_wait(xfull, xpar, s_dead, err, 6100, epoch);
     if (!active) return;   // the whole CTA (all consumer threads) leaves together
@@ -741,17 +784,17 @@ __device__ __forceinline__ void attn2_phase(const AttnParams& p, int kv_len, flo
             }
         }
     };
-    {
-        float kB[UB][VEC], vB[UB][VEC];
-        while (pos0 < end_g) {
-            if (pos0 + STEP < end_g) load(pos0 + STEP, kB, vB);
-            compute(pos0, end_g, kA, vA);
-            pos0 += STEP;
-            if (pos0 >= end_g) break;
-            if (pos0 + STEP < end_g) load(pos0 + STEP, kA, vA);
-            compute(pos0, end_g, kB, vB);
-            pos0 += STEP;
-        }
+#ifdef B200_NO_ATTN_PRE2
+    if (pos0 + STEP < end_g) load(pos0 + STEP, kB, vB);
+#endif
+    while (pos0 < end_g) {   // kA = batch at pos0, kB = batch at pos0 + STEP (both in flight or landed)
+        compute(pos0, end_g, kA, vA);
+        if (pos0 + 2 * STEP < end_g) load(pos0 + 2 * STEP, kA, vA);
+        pos0 += STEP;
+        if (pos0 >= end_g) break;
+        compute(pos0, end_g, kB, vB);
+        if (pos0 + 2 * STEP < end_g) load(pos0 + 2 * STEP, kB, vB);
+        pos0 += STEP;
     }
     if (own && warp == (pos - start) % NW) {   // the new position, from shared memory (one valid row in a batch of UB)
         float kr[UB][VEC], vr[UB][VEC];
@@ -977,9 +1020,10 @@ __device__ __forceinline__ void s2_reduce_phase(const MParams& p) {
 
 // ---------------------------------------------------------------- loader warp: the phase boundary, then the phase's epilogues
 __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t done, int* s_pos, float* s_rope,
-                                          int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead) {
+                                          int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead, uint32_t xstg) {
     const MegaParams& mp = sp.mp;
     const int lane = threadIdx.x & 31;
+    uint32_t n_fold = 0;
     const int n_run = (mp.mode == MEGA_PREFILL) ? mp.n_phases - 1 : mp.n_phases;
     const long long total = (long long)mp.n_tokens * n_run;
     const bool greedy = mp.mode == MEGA_GREEDY;
@@ -1102,7 +1146,7 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
         }
         prev_tp = cur.tp_sync != 0;
         if (cur.kind == PH_GEMV) {
-            tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), tseq0, s_tcnt, s_tdone, s_dead,
+            tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), xstg, n_fold, tseq0, s_tcnt, s_tdone, s_dead,
                                                  sp.epoch0 + (unsigned int)gb + 1u, greedy, best);
         }
         if (++ph == n_run) { ph = 0; tp_tok++; tp_k = 0; }
@@ -1113,7 +1157,7 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
 template <int HD, int GMAX>
 __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __grid_constant__ Stream2Params sp) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) unsigned long long s_bars[2 * kS2MaxSlots + 2];
+    __shared__ __align__(8) unsigned long long s_bars[2 * kS2MaxSlots + 3];
     __shared__ int s_tcnt[kS2TileSlots];
     __shared__ unsigned int s_tdone[kS2TileSlots];
     __shared__ unsigned int s_ticket;
@@ -1131,7 +1175,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     rg.full = smem_u32(s_bars);
     rg.empty = rg.full + 8u * (uint32_t)sp.n_slots;
     rg.n_slots = sp.n_slots;
-    const uint32_t xfull = rg.full + 16u * (uint32_t)kS2MaxSlots, done = xfull + 8u;
+    const uint32_t xfull = rg.full + 16u * (uint32_t)kS2MaxSlots, done = xfull + 8u, xstg = done + 8u;
     if (tid == 0) {
         for (int i = 0; i < sp.n_slots; i++) {
             mbar_init(rg.full + 8u * i, 1);
@@ -1139,6 +1183,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
         }
         mbar_init(xfull, 1);
         mbar_init(done, kS2Cons);
+        mbar_init(xstg, 1);
         s_dead = 0;
         s_pos = 0;
         for (int i = 0; i < kS2TileSlots; i++) { s_tcnt[i] = 0; s_tdone[i] = 0u; }
@@ -1162,7 +1207,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
             if (lane == 0) s2_producer(sp, rg, &s_dead, warp - kS2ProdWarp);
             s_drain(&s_dead);
         } else if (warp == kS2LoaderWarp) {
-            s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead);
+            s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead, xstg);
             s_drain(&s_dead);
         }
         return;
@@ -1181,7 +1226,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
             const uint32_t xpar = (uint32_t)(gph & 1);
             const unsigned int epoch = sp.epoch0 + (unsigned int)gph + 1u;
             if (cur.kind == PH_GEMV) {
-                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, s_tcnt, s_tdone, &s_dead, epoch);
+                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, xstg, s_tcnt, s_tdone, &s_dead, epoch);
             } else if (cur.kind == PH_ATTN) {
                 attn2_phase<HD, GMAX, kS2Cons>(cur.attn, s_pos + 1, reinterpret_cast<float*>(smem + sp.xr_off), xfull, xpar, &s_dead, mp.err,
                                                epoch, &s_ticket, s_rope);

@@ -45,7 +45,7 @@ print(f"  {'vocab head':14s} {d[-1]:7.2f} us;  sum of phases {d.sum():.1f} us")
 # ---- inside one GEMV phase (stream2): SM-clock stamps per warp, relative to the moment the CTA's loader saw the grid barrier open ----
 if gpu.path() == "stream2" and os.environ.get("PHASES", "1") == "1":
     MHZ = 1965.0
-    NC = int(os.environ.get("S2_CONS", "12"))   # consumer warps (kS2Cons); loader = warp NC, producer = warp NC + 1
+    NC = int(os.environ.get("S2_CONS", "8"))   # consumer warps (kS2Cons); loader = warp NC, producer = warp NC + 1
     lay = int(os.environ.get("LAYER", "16"))
     for label, k in [("QKV gemv", 0), ("O gemv", 2), ("gate/up gemv", 3), ("down gemv", 4)]:
         phase = 1 + lay * 5 + k
