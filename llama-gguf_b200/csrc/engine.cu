@@ -534,8 +534,13 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
 // ---- tensor-parallel plumbing: every rank exports one region (partial sums, flags, argmax candidates) as a CUDA IPC
 // handle; the host side (torch.distributed all_gather in the Python mirror, MPI/gRPC in the Rust shim) passes the
 // handles around; the kernels then read and write peer memory directly over NVLink.
-static size_t tp_region_bytes(const b200_ctx* c) {
-    return (size_t)2 * kMmaMaxPeers * c->d.hidden * sizeof(float) + 64 * sizeof(unsigned int) + kMmaMaxPeers * 2 * sizeof(float) + 256;
+static size_t tp_ll_off(const b200_ctx* c) {
+    return ((size_t)2 * kMmaMaxPeers * c->d.hidden * sizeof(float) + 64 * sizeof(unsigned int) + kMmaMaxPeers * 2 * sizeof(float) + 255) & ~(size_t)255;
+}
+// ... | [2][P][H] (value, epoch) packets (stream2.cuh, ll_red: the all-reduce inside the row-parallel GEMV's phase)
+static size_t tp_region_bytes(const b200_ctx* c) { return tp_ll_off(c) + (size_t)2 * kMmaMaxPeers * c->d.hidden * sizeof(uint2) + 256; }
+static uint2* tp_ll(const b200_ctx* c, uint8_t* base, int buf, int rank_slot) {
+    return reinterpret_cast<uint2*>(base + tp_ll_off(c)) + ((size_t)buf * kMmaMaxPeers + rank_slot) * c->d.hidden;
 }
 static float* tp_ar(const b200_ctx* c, uint8_t* base, int buf, int rank_slot) {
     return reinterpret_cast<float*>(base) + ((size_t)buf * kMmaMaxPeers + rank_slot) * c->d.hidden;
@@ -1132,7 +1137,8 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
     c->stream2_ok = false;
     if (!c->use_stream2 || (c->par.world_size > 1 && !env_int("B200_STREAM2_TP", 1))) return B200_OK;
     const int P = c->par.world_size;
-    const bool tp_fold = P > 1 && env_int("B200_TP_FOLD", 1);
+    const bool use_ll = P > 1 && env_int("B200_TP_LL", 1);       // all-reduce inside the row-parallel GEMV's phase (packets); 0: flag exchange + REDUCE phase
+    const bool tp_fold = P > 1 && env_int("B200_TP_FOLD", 0);   // (measured slower) REDUCE folded into the consuming GEMV's staging
     const int hd = d.head_dim, G = d.n_heads / d.n_kv_heads, gmax = G <= 4 ? 4 : 8;
     if (!c->mega_stage[0]) {   // tensor parallel: mega_build keeps no staged vectors (its kernels sum the partials while staging); this one does
         if (P == 1 || d.hidden % 32 || (d.n_heads * hd) % 32 || d.ffn % 32) return B200_OK;
@@ -1195,12 +1201,33 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                     const float* next_norm = is_head ? nullptr : (li + 1 < d.n_layers ? c->layers[li + 1].attn_norm.f32() : c->output_norm.f32());
                     // B200_TP_FOLD=1 (default): no REDUCE phase -- the GEMV that consumes the sum keeps mega_build's xsum / x_res / x_full_out
                     // wiring and its consumer warps finish the all-reduce while they stage x in shared memory (stream2.cuh: s2_gemv_cta)
-                    const bool fold = tp_fold && m.n_sum > 0;
+                    const bool fold = tp_fold && !use_ll && m.n_sum > 0;
                     if (!fold) { m.xsum = nullptr; m.n_sum = 0; m.x_res = nullptr; m.x_full_out = nullptr; }
                     if (fold) {
                         if (!m.norm_w || m.K != d.hidden || (k5 != 0 && k5 != 3 && !is_head)) return B200_OK;
                         m.x_staged = nullptr;
                         if (k5 == 3) { m.stage_out = c->mega_stage[3]; m.stage_w = nullptr; m.stage_K = (int)d.ffn; }
+                    } else if (use_ll && (k5 == 2 || k5 == 4)) {
+                        // row-parallel GEMV with the all-reduce inside its phase (stream2.cuh: ll_red): packets to every rank, polled by the
+                        // consumer warps; buffer 0 / xb = sum + xa staged with ffn_norm (O), buffer 1 / xa = sum + xb staged with the next norm (down)
+                        const int buf = k5 == 2 ? 0 : 1;
+                        if (!ph.tp_sync || m.n_peer != P) return B200_OK;
+                        m.x_staged = c->mega_stage[k5 == 2 ? 2 : 3];
+                        m.ll_red = 1;
+                        ph.tp_sync = 0;
+                        for (int r = 0; r < P; r++) m.peer_out[r] = reinterpret_cast<float*>(tp_ll(c, c->tp_peer[r], buf, c->par.rank));
+                        m.xsum = reinterpret_cast<const float*>(tp_ll(c, c->tp_region, buf, 0));
+                        m.n_sum = P; m.sum_stride = d.hidden;
+                        m.x_res = k5 == 2 ? c->xa : c->xb;
+                        m.x_full_out = k5 == 2 ? c->xb : c->xa;
+                        m.stage_out = c->mega_stage[k5 == 2 ? 1 : 0];
+                        m.stage_w = k5 == 2 ? c->layers[li].ffn_norm.f32() : next_norm;
+                        m.stage_K = d.hidden;
+                    } else if (use_ll && k5 == 3) {
+                        m.x_staged = c->mega_stage[1];
+                        m.stage_out = c->mega_stage[3]; m.stage_w = nullptr; m.stage_K = (int)d.ffn;
+                    } else if (use_ll) {   // QKV, vocab head
+                        m.x_staged = c->mega_stage[0];
                     } else if (tp_fold && (k5 == 2 || k5 == 4)) {   // row-parallel: partial vectors to every rank, nothing staged
                         m.x_staged = c->mega_stage[k5 == 2 ? 2 : 3];
                         m.stage_out = nullptr;

@@ -116,6 +116,12 @@ struct MParams {
     float* x_full_out;
     float* peer_out[kMmaMaxPeers];
     int n_peer;
+    // stream2.cuh, tensor parallel: the all-reduce of this row-parallel GEMV is finished inside the phase.  The epilogue writes its partial
+    // tiles as 8-byte (value, epoch) packets (peer_out[r] then points to uint2 slots), and the consumer warps, when their jobs are done, poll
+    // the packets of every rank in local memory, add them in rank order + x_res, and write x_full_out and its staged form (stage_out /
+    // stage_w / stage_K describe THAT vector; xsum = packet slots of rank 0, sum_stride in packets).  No fence, no flag, no grid barrier
+    // between the GEMV and the reduction.
+    int ll_red;
     // cross-CTA merge scratch
     float* part;             // [grid][2][2][32]
     unsigned int* tickets;   // [total logical tiles], zero between launches

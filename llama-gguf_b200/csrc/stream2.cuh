@@ -246,38 +246,50 @@ __device__ __forceinline__ void pin2(float (&a)[2]) { asm volatile("" : "+f"(a[0
 // straight into shared memory (the bytes a REDUCE phase would have written to global memory and the loader copied back: one grid boundary
 // less per exchange).  CTA b also stores the groups b, b + grid, ... of the f32 vector (a later residual).  Not inlined: the single-GPU
 // register allocation of s2_gemv_cta must not see this code (measured: 1 % slower inlined).
-__device__ __noinline__ void s2_fold_stage(const MParams& p, uint8_t* xs, uint32_t xstg) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_grp = p.K >> 5;
-    for (int g0 = warp; g0 < n_grp; g0 += 4 * kS2Cons) {
-        float v[4], w[4];
+__device__ __noinline__ void s2_fold_stage(const MParams& p, uint8_t* xs, float* s_red, uint32_t xstg) {
+    const int tid = threadIdx.x;   // consumer threads only: 0 .. kS2NT - 1
+    const XLayout L = x_layout(p.K);
+    float ss = 0.0f;
+    // four float4 per thread and batch, every load of a batch in flight at once (K = 4096: one batch); the 8 lanes that hold a group of 32
+    // agree on its scale with three shuffles (split_store4, the staging code of the first megakernel)
+    for (int e0 = tid * 4; e0 < p.K; e0 += kS2NT * 16) {
+        float4 v[4], w[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int grp = g0 + u * kS2Cons, j = grp * 32 + lane;
-            v[u] = 0.f; w[u] = 1.f;
-            if (grp < n_grp) {
-                v[u] = __ldcg(p.xsum + j);
-                for (int r = 1; r < p.n_sum; r++) v[u] += __ldcg(p.xsum + (size_t)r * p.sum_stride + j);
-                if (p.x_res) v[u] += __ldcg(p.x_res + j);
-                if (p.norm_w) w[u] = p.norm_w[j];
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + i * kS2NT * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (e < p.K) {
+                v[i] = __ldcg(reinterpret_cast<const float4*>(p.xsum + e));
+                for (int r = 1; r < p.n_sum; r++) {
+                    const float4 b = __ldcg(reinterpret_cast<const float4*>(p.xsum + (size_t)r * p.sum_stride + e));
+                    v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+                }
+                if (p.x_res) {
+                    const float4 b = __ldcg(reinterpret_cast<const float4*>(p.x_res + e));
+                    v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+                }
+                if (p.norm_w) w[i] = *reinterpret_cast<const float4*>(p.norm_w + e);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int grp = g0 + u * kS2Cons, j = grp * 32 + lane;
-            if (grp < n_grp) {
-                if (p.x_full_out && grp % (int)gridDim.x == (int)blockIdx.x) p.x_full_out[j] = v[u];
-                stage_out32(v[u], w[u], j, p.K, xs);
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + i * kS2NT * 4;
+            if (e < p.K) {
+                if (p.x_full_out && (e >> 5) % (int)gridDim.x == (int)blockIdx.x) *reinterpret_cast<float4*>(p.x_full_out + e) = v[i];
+                ss += split_store4(v[i], w[i], e, xs, L, __activemask());
             }
         }
     }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;   // sum of x^2 (before the norm weight), one partial per warp: the loader adds them (1 / rms)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the region is the target of later bulk copies)
     s2_cons_sync();
-    if (threadIdx.x == 0) mbar_arrive(xstg);   // the loader warp reads the groups' sums of squares (1 / rms)
+    if (tid == 0) mbar_arrive(xstg);
 }
 
 __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Params& sp, uint8_t* smem, const SRing& rg, S2Cons& cs,
-                                            uint32_t xfull, uint32_t xpar, uint32_t xstg, int* s_tcnt, volatile unsigned int* s_tdone,
+                                            uint32_t xfull, uint32_t xpar, uint32_t xstg, float* s_red, int* s_tcnt, volatile unsigned int* s_tdone,
                                             volatile int* s_dead, unsigned int epoch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(smem);
@@ -344,7 +356,7 @@ __device__ __forceinline__ void s2_gemv_cta(const MParams& p, const Stream2Param
 
     // ---- the phase's input: staged by its producer, copied by the loader warp; everything above overlapped the boundary ----
     s_wait(xfull, xpar, s_dead, p.err, 6000, epoch);
-    if (p.n_sum > 0) s2_fold_stage(p, smem + sp.xr_off, xstg);
+    if (p.n_sum > 0 && !p.ll_red) s2_fold_stage(p, smem + sp.xr_off, s_red, xstg);
     S2_STAMP(dbg, 1);
     {
         xtok = smem_token();
@@ -478,14 +490,14 @@ struct S2Best {
     int i;
 };
 __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t xpar,
-                                                  uint32_t xstg, uint32_t& n_fold, uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone,
-                                                  volatile int* s_dead, unsigned int epoch, bool greedy, S2Best& best) {
+                                                  uint32_t xstg, const float* s_red, uint32_t& n_fold, uint32_t tseq0, int* s_tcnt, volatile unsigned int* s_tdone,
+                                                  volatile int* s_dead, unsigned int epoch, bool greedy, S2Best& best, unsigned int ll_ep) {
     const int lane = threadIdx.x & 31;
     const bool swiglu = p.epi == ME_SWIGLU;
     const int per_tile = p.s_parts * p.s_ept;
     const S2Deal dl = s2_deal(p);
     const int e0 = dl.e0, e1 = dl.e0 + dl.nloc;
-    const bool fold = p.n_sum > 0;             // (tensor parallel) the consumers stage the input themselves: see s2_gemv_cta
+    const bool fold = p.n_sum > 0 && !p.ll_red;   // (tensor parallel) the consumers stage the input themselves: see s2_gemv_cta
     const uint32_t fold_par = n_fold & 1u;
     if (fold) n_fold++;
     if (dl.n_ltiles == 0) {
@@ -499,11 +511,15 @@ __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2
     unsigned long long* const dbg = p.dbg;
     float unscale = 1.0f;
     if (p.norm_w) {   // sum of x^2 from the per-group partial sums of the staged input: the loader waits for its own copy
-        if (fold) s_wait(xstg, fold_par, s_dead, p.err, 6450, epoch);
-        else s_wait(xfull, xpar, s_dead, p.err, 6400, epoch);
-        const uint32_t ssq = smem_u32(smem) + (uint32_t)sp.xr_off + x_layout(p.K).ssq + smem_token();
         float tot = 0.0f;
-        for (int k = lane; k < (p.K >> 5); k += 32) tot += lds_f32(ssq + 4u * (uint32_t)k);
+        if (fold) {
+            s_wait(xstg, fold_par, s_dead, p.err, 6450, epoch);
+            if (lane < kS2Cons) tot = *(volatile const float*)(s_red + lane);
+        } else {
+            s_wait(xfull, xpar, s_dead, p.err, 6400, epoch);
+            const uint32_t ssq = smem_u32(smem) + (uint32_t)sp.xr_off + x_layout(p.K).ssq + smem_token();
+            for (int k = lane; k < (p.K >> 5); k += 32) tot += lds_f32(ssq + 4u * (uint32_t)k);
+        }
         tot = warp_sum(tot);
         unscale = 1.0f / sqrtf(tot / (float)p.K + p.eps);
     }
@@ -521,7 +537,7 @@ __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2
         if (head_local) {   // this CTA finishes the tile: its epilogue operands, in flight while the tile is computed
             if (valid && sg.bias) e_bias = sg.bias[j];
             if (valid && p.epi == ME_RESIDUAL) e_res = __ldcg(p.residual + j);
-            if (p.stage_out && p.stage_w && j < p.stage_K) e_w = p.stage_w[j];
+            if (p.stage_out && p.stage_w && !p.ll_red && j < p.stage_K) e_w = p.stage_w[j];
         }
         const int t_lo = (max(T * per_tile, e0) - e0) << p.s_jsh, t_hi = (min((T + 1) * per_tile, e1) - e0) << p.s_jsh;   // local jobs of the tile
         const int n_cw = min(t_hi - t_lo, kS2Cons);   // warps that hold a piece of it
@@ -599,13 +615,16 @@ __device__ __forceinline__ int s2_gemv_epilogues(const MParams& p, const Stream2
             val += e_res;
             if (cand) {   // raw-logit argmax, LAST maximal index wins (src/main.rs:1816-1821)
                 if (val > best.v || (val == best.v && j > best.i) || best.i < 0) { best.v = val; best.i = j; }
-            } else if (p.n_peer > 0) {   // partial of a row-parallel GEMV, to every rank's buffer (NVLink peer memory); summed by the REDUCE phase
+            } else if (p.n_peer > 0 && p.ll_red) {   // partial of a row-parallel GEMV as (value, epoch) packets to every rank (NVLink peer memory)
+                for (int r = 0; r < p.n_peer; r++)
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(p.peer_out[r]) + j), "r"(__float_as_uint(val)), "r"(ll_ep) : "memory");
+            } else if (p.n_peer > 0) {   // ... as plain floats; summed by the REDUCE phase after the flag exchange
                 for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;
             } else {
                 sg.out[j] = val;
             }
         }
-        if (p.stage_out) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
+        if (p.stage_out && !p.ll_red) stage_out32(val, e_w, j, p.stage_K, p.stage_out);
     }
     S2_STAMP(dbg, 5);
     if (cand) {   // the CTA's candidate of this token: larger value, then larger index
@@ -1018,9 +1037,51 @@ __device__ __forceinline__ void s2_reduce_phase(const MParams& p) {
     }
 }
 
+// ---------------------------------------------------------------- all-reduce inside a row-parallel GEMV phase (tensor parallel, ll_red)
+// Consumer warps, after their last job: one group of 32 elements per warp and step.  The P partial values of an element arrive as 8-byte
+// (value, epoch) packets written by the loader warps of every rank (this one included) straight from their epilogues: a packet is valid
+// when its epoch is this exchange's -- no fence, no flag round trip, no grid barrier in front of the reduction.  Sum in rank order +
+// residual (identical on every rank), f32 vector (a later residual) and the staged form the next GEMV's bulk copy reads.
+__device__ __noinline__ void s2_reduce_ll(const MParams& p, unsigned int ep, volatile int* s_dead) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_grp = p.stage_K >> 5;
+    const uint2* base = reinterpret_cast<const uint2*>(p.xsum);
+    for (int grp = (int)blockIdx.x * kS2Cons + warp; grp < n_grp; grp += (int)gridDim.x * kS2Cons) {
+        const int j = grp * 32 + lane;
+        const float res = p.x_res ? __ldcg(p.x_res + j) : 0.0f;
+        const float sw = p.stage_w ? p.stage_w[j] : 1.0f;
+        uint32_t val[kMmaMaxPeers];
+        const long long t0 = clock64();
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int r = 0; r < kMmaMaxPeers; r++) {
+                if (r < p.n_sum) {
+                    uint32_t e;
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[r]), "=r"(e) : "l"(base + (size_t)r * p.sum_stride + j) : "memory");
+                    ok = ok && e == ep;
+                }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (*s_dead || clock64() - t0 > 3000000000LL) {
+                *s_dead = 1;
+                if (atomicExch(p.err, 3) == 0) { p.err[1] = 5100; p.err[2] = (int)blockIdx.x; p.err[3] = (int)ep; }
+                break;
+            }
+        }
+        float v = __uint_as_float(val[0]);
+#pragma unroll
+        for (int r = 1; r < kMmaMaxPeers; r++)
+            if (r < p.n_sum) v += __uint_as_float(val[r]);
+        v += res;
+        if (p.x_full_out) p.x_full_out[j] = v;
+        stage_out32(v, sw, j, p.stage_K, p.stage_out);
+    }
+}
+
 // ---------------------------------------------------------------- loader warp: the phase boundary, then the phase's epilogues
 __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem, uint32_t xfull, uint32_t done, int* s_pos, float* s_rope,
-                                          int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead, uint32_t xstg) {
+                                          int hd, int* s_tcnt, volatile unsigned int* s_tdone, volatile int* s_dead, uint32_t xstg, const float* s_red) {
     const MegaParams& mp = sp.mp;
     const int lane = threadIdx.x & 31;
     uint32_t n_fold = 0;
@@ -1146,8 +1207,10 @@ __device__ __forceinline__ void s2_loader(const Stream2Params& sp, uint8_t* smem
         }
         prev_tp = cur.tp_sync != 0;
         if (cur.kind == PH_GEMV) {
-            tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), xstg, n_fold, tseq0, s_tcnt, s_tdone, s_dead,
-                                                 sp.epoch0 + (unsigned int)gb + 1u, greedy, best);
+            unsigned int ll_ep = 0u;   // (ll_red) the exchange's epoch: the same count on every rank, in every loader and consumer warp
+            if (cur.gemv.ll_red) ll_ep = mp.tp_epoch0 + tp_tok * (unsigned int)sp.tp_per_token + (++tp_k);
+            tseq0 += (uint32_t)s2_gemv_epilogues(cur.gemv, sp, smem, xfull, (uint32_t)(gb & 1), xstg, s_red, n_fold, tseq0, s_tcnt, s_tdone, s_dead,
+                                                 sp.epoch0 + (unsigned int)gb + 1u, greedy, best, ll_ep);
         }
         if (++ph == n_run) { ph = 0; tp_tok++; tp_k = 0; }
     }
@@ -1167,6 +1230,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     __shared__ float s_rope[HD];
     __shared__ float s_av[kS2Cons];
     __shared__ int s_ai[kS2Cons];
+    __shared__ float s_red[kS2Cons];
 
     const MegaParams& mp = sp.mp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1207,7 +1271,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
             if (lane == 0) s2_producer(sp, rg, &s_dead, warp - kS2ProdWarp);
             s_drain(&s_dead);
         } else if (warp == kS2LoaderWarp) {
-            s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead, xstg);
+            s2_loader(sp, smem, xfull, done, &s_pos, s_rope, HD, s_tcnt, s_tdone, &s_dead, xstg, s_red);
             s_drain(&s_dead);
         }
         return;
@@ -1221,12 +1285,14 @@ __global__ void __launch_bounds__(kS2Threads, 1) stream2_decode_kernel(const __g
     S2Cons cs{0u, 0u};
     long long gph = 0;
     for (int tok = 0; tok < mp.n_tokens; tok++) {
+        unsigned int tp_k = 0;   // (ll_red) row-parallel exchanges of this token so far
         for (int ph = 0; ph < n_run; ph++, gph++) {
             const MegaPhase& cur = s_desc[gph & 1];
             const uint32_t xpar = (uint32_t)(gph & 1);
             const unsigned int epoch = sp.epoch0 + (unsigned int)gph + 1u;
             if (cur.kind == PH_GEMV) {
-                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, xstg, s_tcnt, s_tdone, &s_dead, epoch);
+                s2_gemv_cta(cur.gemv, sp, smem, rg, cs, xfull, xpar, xstg, s_red, s_tcnt, s_tdone, &s_dead, epoch);
+                if (cur.gemv.ll_red) s2_reduce_ll(cur.gemv, mp.tp_epoch0 + (unsigned int)tok * (unsigned int)sp.tp_per_token + (++tp_k), &s_dead);
             } else if (cur.kind == PH_ATTN) {
                 attn2_phase<HD, GMAX, kS2Cons>(cur.attn, s_pos + 1, reinterpret_cast<float*>(smem + sp.xr_off), xfull, xpar, &s_dead, mp.err,
                                                epoch, &s_ticket, s_rope);
