@@ -238,8 +238,9 @@ def main():
     from llama_gguf_b200.presets import make_desc
 
     desc = make_desc(preset, args.ctx, max(1, args.batch))   # one KV cache per sequence slot (batch extra below)
+    repeat = (16 << 20) if args.model in ("llama-3-70b", "mixtral-8x7b") else None   # (host generation time of the 40 GB presets)
     # tensors are streamed straight into the context (host memory stays at one tensor)
-    gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up))
+    gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up, repeat_bytes=repeat))
     log(f"model built and uploaded in {time.time() - t0:.1f} s")
     st0 = gpu.stats()
     wbytes, kvpp = st0["weight_bytes_per_token"], st0["kv_bytes_per_pos"]

@@ -434,7 +434,9 @@ class GpuOnlyInference:
         except Exception:
             self.close()
             raise
-        self.vocab = self.desc["vocab"] // world  # tensor parallel: this rank's slice of the logits
+        # tensor parallel: this rank's slice of the logits; expert parallel (MoE + world > 1): the head is replicated, full logits
+        self.expert_parallel = world > 1 and self.desc.get("n_experts", 0) > 0
+        self.vocab = self.desc["vocab"] if self.expert_parallel else self.desc["vocab"] // world
 
     @classmethod
     def from_model(cls, model, max_seq_len, **kw):

@@ -118,6 +118,12 @@ struct b200_ctx {
     float *xa = nullptr, *xb = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *logits = nullptr;
     float *attn_part = nullptr, *rope_freq = nullptr, *taps = nullptr, *moe_wt = nullptr;
     int* moe_sel = nullptr;
+    // expert parallel (MoE model, world_size > 1): experts [rank * ep_local, (rank + 1) * ep_local) are resident here; everything else is
+    // replicated; the weighted expert outputs are combined through (value, epoch) packets in the peers' exchange regions (misc.cuh)
+    bool ep = false;
+    int ep_local = 0;
+    float* ep_y = nullptr;             // [8][hidden] weighted outputs of the local selected experts
+    unsigned int* ep_epoch = nullptr;  // device counter, bumped by the routing kernel once per layer
     unsigned int* tickets = nullptr;
     int n_splits = 1;
     // tensor-pipe GEMV (gemv_mma.cuh): stream-K scratch, watchdog flag, launch knobs
@@ -247,15 +253,22 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     if (c->par.world_size != 1) {
         const int P = c->par.world_size;
         if (P != 2 && P != 4 && P != 8) return bad("tensor-parallel world size must be 2, 4 or 8");
-        if (d.n_experts > 0) return bad("tensor parallelism for MoE models is not built yet");
+        if (d.n_experts > 0) {
+            // MoE: EXPERT parallel -- attention, norms, router and the vocab head replicated, expert e on rank e / (E / P); at batch 1 the
+            // dispatch is free (every rank routes), the combine is the only exchange (replaces moe.rs:352-361 on one host)
+            if (d.n_experts % P) return bad("n_experts must be divisible by the world size");
+            c->ep = true;
+            c->ep_local = d.n_experts / P;
+        } else {
         // ShardingPlan::from_config's divisibility rules (src/backend/tensor_parallel.rs:69-106)
         if (d.n_heads % P || d.n_kv_heads % P || d.ffn % P || d.vocab % P) return bad("heads, kv heads, ffn and vocab must be divisible by the world size");
         if ((d.vocab / P) % 16) return bad("vocab / world_size must be a multiple of 16");
         d.n_heads /= P;
         d.n_kv_heads /= P;
         d.ffn /= P;
+        }
     }
-    c->vocab_l = d.vocab / c->par.world_size;
+    c->vocab_l = c->ep ? d.vocab : d.vocab / c->par.world_size;
     if (c->par.device >= n_dev) return bad("device ordinal out of range");
     CU(cudaSetDevice(c->par.device));
     cudaDeviceProp prop{};
@@ -347,12 +360,21 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     uint64_t lne[4] = {1, 1, 1, 1};
     for (int i = 0; i < n_dims; i++) lne[i] = ne[i];
     const uint64_t row_bytes_full = ne[0] / be * bb;
-    const int kind = (P > 1) ? tp_shard_kind(gguf_name) : 0;
+    const bool is_exps = std::string(gguf_name).find("_exps.weight") != std::string::npos;
+    const int kind = (P > 1 && c->ep) ? (is_exps ? 3 : 0) : (P > 1) ? tp_shard_kind(gguf_name) : 0;
     long long tp_pitch = 0;
     if (kind == 1) {
         const int dim = n_dims == 1 ? 0 : 1;
         if (ne[dim] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": rows not divisible by the world size");
         lne[dim] = ne[dim] / P;
+        const size_t lbytes = nbytes / P;
+        CU_ALLOC(cudaMalloc((void**)&t->d, lbytes + 256));
+        CU(cudaMemcpy(t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes, cudaMemcpyHostToDevice));
+        CU(cudaMemset(t->d + lbytes, 0, 256));
+        t->nbytes = lbytes;
+    } else if (kind == 3) {   // expert parallel: the experts are the outermost dimension -> a contiguous byte range per rank
+        if (n_dims != 3 || ne[2] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": experts not divisible by the world size");
+        lne[2] = ne[2] / P;
         const size_t lbytes = nbytes / P;
         CU_ALLOC(cudaMalloc((void**)&t->d, lbytes + 256));
         CU(cudaMemcpy(t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes, cudaMemcpyHostToDevice));
@@ -432,19 +454,19 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
         if ((rc = check_f32_vec(L.bv, "attn_v.bias", nkv * hd, l, false))) return rc;
         wbytes += L.wq.nbytes + L.wk.nbytes + L.wv.nbytes + L.wo.nbytes + 2 * H * 4;
         if (d.n_experts > 0) {
-            const uint64_t EI = d.expert_ffn, E = d.n_experts;
+            const uint64_t EI = d.expert_ffn, E = d.n_experts, EL = c->ep ? (uint64_t)c->ep_local : E;   // (EL: experts resident on this GPU)
             if (!L.router.present() || L.router.type != T_F32 || L.router.ne[0] != H || L.router.ne[1] != E)
                 return fail(B200_ERR_DTYPE_MISMATCH, "ffn_gate_inp.weight must be F32 [hidden, n_experts] (moe.rs:133)");
             for (const DevTensor* t : {&L.gate_exps, &L.up_exps}) {
                 if ((rc = check_weight(*t, "ffn_{gate,up}_exps.weight", H, EI, l))) return rc;
-                if (t->ne[2] != E) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
+                if (t->ne[2] != EL) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
             }
             if ((rc = check_weight(L.down_exps, "ffn_down_exps.weight", EI, H, l))) return rc;
-            if (L.down_exps.ne[2] != E) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
+            if (L.down_exps.ne[2] != EL) return fail(B200_ERR_SHAPE_MISMATCH, "expert tensor: ne[2] != n_experts");
             if (L.gate_exps.type != L.up_exps.type)
                 return fail(B200_ERR_UNSUPPORTED, "gate/up expert tensors must share one quant type");
             wbytes += L.router.nbytes +
-                      (L.gate_exps.nbytes + L.up_exps.nbytes + L.down_exps.nbytes) / E * d.n_experts_used;
+                      (L.gate_exps.nbytes + L.up_exps.nbytes + L.down_exps.nbytes) / EL * d.n_experts_used;   // (expert parallel: summed over the GPUs)
         } else {
             if ((rc = check_weight(L.gate, "ffn_gate.weight", H, I, l))) return rc;
             if ((rc = check_weight(L.up, "ffn_up.weight", H, I, l))) return rc;
@@ -478,6 +500,12 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
     CU(cudaMemset(c->mma_tickets, 0, (size_t)c->mma_tickets_n * sizeof(unsigned int)));
     CU_ALLOC(cudaMalloc((void**)&c->mma_err, 8 * sizeof(int)));
     CU(cudaMemset(c->mma_err, 0, 8 * sizeof(int)));
+    if (c->ep) {
+        CU_ALLOC(cudaMalloc((void**)&c->ep_y, (size_t)8 * H * sizeof(float)));
+        CU(cudaMemset(c->ep_y, 0, (size_t)8 * H * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->ep_epoch, sizeof(unsigned int)));
+        CU(cudaMemset(c->ep_epoch, 0, sizeof(unsigned int)));
+    }
     CU_ALLOC(cudaMalloc((void**)&c->moe_sel, 8 * sizeof(int)));
     CU_ALLOC(cudaMalloc((void**)&c->moe_wt, 8 * sizeof(float)));
     CU(cudaMemset(c->moe_sel, 0, 8 * sizeof(int)));
@@ -524,7 +552,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
             }
     }
     if ((rc = mega_build(c))) return rc;
-    if (c->par.world_size > 1 && !c->mega_ok) {
+    if (c->par.world_size > 1 && !c->ep && !c->mega_ok) {
         c->finalized = false;
         return fail(B200_ERR_UNSUPPORTED, "tensor parallelism needs the megakernel path (dense model, K-quant / Q8_0 weights with 256-aligned shards)");
     }
@@ -645,6 +673,7 @@ static bool to_mma_params(b200_ctx* c, const GemvParams& p, MParams& m, MPlan& p
     m.n_seg = p.n_seg; m.K = p.K; m.x = p.x; m.norm_w = p.norm_w; m.eps = p.eps; m.residual = p.residual;
     m.epi = p.epi == EPI_STORE ? ME_STORE : p.epi == EPI_RESIDUAL ? ME_RESIDUAL : p.epi == EPI_SWIGLU ? ME_SWIGLU : ME_SCALED_ACC;
     m.expert_sel = p.expert_sel; m.expert_wt = p.expert_wt; m.expert_slot = p.expert_slot;
+    m.expert_base = p.expert_base; m.expert_count = p.expert_count;
     m.part = c->mma_part; m.tickets = c->mma_tickets; m.err = c->mma_err;
     if (!mma_plan(m, c->n_sm, c->mma_warps, c->mma_stages, smem_limit ? smem_limit : c->smem_optin - 8192, plan)) return false;
     int tiles = 0;
@@ -739,20 +768,40 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
             RouteParams rt{};
             rt.x = c->xb; rt.norm_w = L.ffn_norm.f32(); rt.eps = d.norm_eps; rt.w_router = L.router.f32();
             rt.hidden = H; rt.n_experts = d.n_experts; rt.top_k = d.n_experts_used; rt.sel = c->moe_sel; rt.wt = c->moe_wt;
+            rt.epoch = c->ep ? c->ep_epoch : nullptr;
             if (!only_gemv) CK(launch_k(c, moe_route_kernel, dim3(1), dim3(256), 0, rt));
             for (int s = 0; s < d.n_experts_used; s++) {
+                const int e_base = c->ep ? c->par.rank * c->ep_local : 0, e_count = c->ep ? c->ep_local : 0;
                 GemvParams p{};
                 fill_seg(p.seg[0], L.gate_exps, c->hbuf, nullptr, 1);
                 fill_seg(p.seg[1], L.up_exps, c->hbuf, nullptr, 1);
                 p.n_seg = 2; p.K = H; p.x = c->xb; p.norm_w = L.ffn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_SWIGLU;
                 p.expert_sel = c->moe_sel; p.expert_wt = c->moe_wt; p.expert_slot = s;
+                p.expert_base = e_base; p.expert_count = e_count;
                 CK(launch_gemv(c, p));
                 GemvParams q2{};
-                fill_seg(q2.seg[0], L.down_exps, c->xa, nullptr, 1);
+                fill_seg(q2.seg[0], L.down_exps, c->ep ? c->ep_y + (size_t)s * H : c->xa, nullptr, 1);
                 q2.n_seg = 1; q2.K = d.expert_ffn; q2.x = c->hbuf; q2.epi = EPI_SCALED_ACC;
                 q2.residual = (s == d.n_experts_used - 1) ? c->xb : nullptr;
                 q2.expert_sel = c->moe_sel; q2.expert_wt = c->moe_wt; q2.expert_slot = s;
+                q2.expert_base = e_base; q2.expert_count = e_count;
                 CK(launch_gemv(c, q2));
+            }
+            if (c->ep && !only_gemv) {   // combine across the GPUs: xa = ((0 + y_0) + y_1 ...) + xb (misc.cuh)
+                EpParams ep{};
+                ep.sel = c->moe_sel; ep.epoch = c->ep_epoch; ep.top_k = d.n_experts_used; ep.hidden = H;
+                ep.rank = c->par.rank; ep.world = c->par.world_size; ep.experts_per_rank = c->ep_local;
+                ep.y = c->ep_y;
+                for (int r = 0; r < c->par.world_size; r++) {
+                    ep.peer_ll[r] = tp_ll(c, c->tp_peer[r], 0, 0);
+                    ep.peer_mark[r] = tp_flags(c, c->tp_peer[r]) + 32;
+                }
+                ep.ll = tp_ll(c, c->tp_region, 0, 0);
+                ep.mark = tp_flags(c, c->tp_region) + 32;
+                ep.h = c->xb; ep.out = c->xa; ep.err = c->mma_err;
+                const int nb = std::max(1, std::min(32, H / 256));
+                CK(launch_k(c, ep_push_kernel, dim3(nb), dim3(256), 0, ep));
+                CK(launch_k(c, ep_combine_kernel, dim3(nb), dim3(256), 0, ep));
             }
         } else {
             GemvParams p{};
@@ -1151,7 +1200,15 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
     const void* kern = stream2_kernel_for(hd, G);
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kern));
-    size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn2_smem_floats(hd, gmax, kS2Cons, c->mega_splits, G) * sizeof(float));
+    // KV splits per kv head: the ticket merge stages [splits][G][hd + 2] floats in the x region.  Few kv heads per GPU (tensor parallel,
+    // G = 8: 37 splits x 8 x 130 floats = 154 KB) would leave no room for the ring: the splits are capped so that the scratch stays within
+    // the larger of the GEMV input and 64 KB (the descriptors of this kernel carry their own n_splits; partials are indexed with it)
+    int s2_splits = c->mega_splits;
+    {
+        const size_t budget = std::max(x_smem_bytes(max_K) + 16, (size_t)64 << 10);
+        while (s2_splits > 1 && attn2_smem_floats(hd, gmax, kS2Cons, s2_splits, G) * sizeof(float) > budget) s2_splits--;
+    }
+    size_t x_region = std::max(x_smem_bytes(max_K) + 16, attn2_smem_floats(hd, gmax, kS2Cons, s2_splits, G) * sizeof(float));
     x_region = (x_region + 127) & ~(size_t)127;
     const size_t xr_off = kS2ZeroBytes;
     const size_t tpart_off = xr_off + x_region;
@@ -1279,6 +1336,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
                 m.x_bytes = m.x_staged ? (int)x_staged_bytes(m.K) : 0;
             } else {
                 ph.attn.min_chunk = min_chunk2;
+                ph.attn.n_splits = s2_splits;
                 if (P > 1) { ph.attn.stage_out = c->mega_stage[2]; ph.attn.stage_K = d.n_heads * hd; }
             }
             prog2.push_back(ph);
@@ -1295,7 +1353,7 @@ static int stream2_build(b200_ctx* c, std::vector<std::vector<MegaPhase>>& progs
     c->s2_slots = slots;
     c->s2_smem = smem;
     c->stream2_ok = true;
-    if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: ok, %d slots, x region %zu, ring_off %zu, smem %zu, %d phases, %d regs\n", slots, x_region, ring_off, smem, c->s2_phases, fa.numRegs);
+    if (env_int("B200_LOG", 0)) fprintf(stderr, "[b200] stream2_build: ok, %d slots, x region %zu, ring_off %zu, smem %zu, %d phases, %d regs, %d KV splits\n", slots, x_region, ring_off, smem, c->s2_phases, fa.numRegs, s2_splits);
     return B200_OK;
 }
 

@@ -52,6 +52,10 @@ struct GemvParams {
     const int* expert_sel;     // device [top_k] or nullptr
     const float* expert_wt;    // device [top_k] (EPI_SCALED_ACC: out[j] += wt * acc)
     int expert_slot;
+    // expert parallel (one context per GPU, experts [expert_base, expert_base + expert_count) resident here): a launch whose selected
+    // expert lives on another GPU returns at once; EPI_SCALED_ACC writes out[j] = wt * acc (no accumulate, no residual): the
+    // weighted output of ONE expert, combined across GPUs by ep_combine_kernel (misc.cuh).  expert_count == 0: off.
+    int expert_base, expert_count;
 };
 
 __device__ __forceinline__ float u8f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
@@ -342,7 +346,11 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
     }
     pdl_wait();
     // MoE: the selected expert is written by the routing kernel (a predecessor): read it only after the wait
-    const long long eoff = p.expert_sel ? (long long)p.expert_sel[p.expert_slot] : 0;
+    long long eoff = p.expert_sel ? (long long)p.expert_sel[p.expert_slot] : 0;
+    if (p.expert_count > 0) {   // expert parallel: not this GPU's expert -> nothing to do (uniform over the grid)
+        eoff -= p.expert_base;
+        if (eoff < 0 || eoff >= p.expert_count) return;
+    }
     stage_x(p, xs, red);
 
     for (int task = blockIdx.x * kGemvWarps + warp; task < n_tasks; task += gridDim.x * kGemvWarps) {
@@ -393,9 +401,9 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
                         if (sg.bias) v += sg.bias[jrow];
                         if (p.epi == EPI_RESIDUAL) v += p.residual[jrow];
                         if (p.epi == EPI_SCALED_ACC) {  // moe.rs:363-368: out (zeros) += w_e * y_e, in selection order
-                            const float prev = p.expert_slot == 0 ? 0.0f : sg.out[jrow];
+                            const float prev = (p.expert_slot == 0 || p.expert_count > 0) ? 0.0f : sg.out[jrow];
                             v = prev + p.expert_wt[p.expert_slot] * v;
-                            if (p.residual) v += p.residual[jrow];  // last selected expert: + h (layers.rs:1235-1241)
+                            if (p.residual && p.expert_count == 0) v += p.residual[jrow];  // last selected expert: + h (layers.rs:1235-1241)
                         }
                         sg.out[jrow] = v;
                     }

@@ -106,6 +106,7 @@ struct MParams {
     const int* expert_sel;
     const float* expert_wt;
     int expert_slot;
+    int expert_base, expert_count;   // expert parallel: see GemvParams (gemv.cuh)
     // tensor parallel (megakernel only).  Input side: x = sum_r xsum[r * sum_stride + e] (+ x_res[e]) -- the
     // all-reduce of a row-parallel GEMV is finished by its consumer, in rank order on every rank; CTA 0 also
     // stores the summed vector to x_full_out (it is the residual of a later phase).  Output side: the finished
@@ -921,6 +922,10 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
 
     if (p.expert_sel) {
         eoff = (long long)p.expert_sel[p.expert_slot];
+        if (p.expert_count > 0) {   // expert parallel: not this GPU's expert -> nothing to do (uniform over the grid)
+            eoff -= p.expert_base;
+            if (eoff < 0 || eoff >= p.expert_count) return;
+        }
         if (n_units > 0) { cur_init(cp, u0); cc = cp; prod_run(); }
     }
     const XLayout XL = x_layout(K);
@@ -989,9 +994,9 @@ __device__ __forceinline__ void mma_gemv_cta(const MParams& p, uint8_t* smem, fl
             val += e_bias;
             val += e_res;
             if (p.epi == ME_SCALED_ACC) {  // moe.rs:363-368
-                const float prev = p.expert_slot == 0 ? 0.0f : sg.out[j];
+                const float prev = (p.expert_slot == 0 || p.expert_count > 0) ? 0.0f : sg.out[j];
                 val = prev + p.expert_wt[p.expert_slot] * val;
-                if (p.residual) val += p.residual[j];
+                if (p.residual && p.expert_count == 0) val += p.residual[j];
             }
             if (p.n_peer > 0) {
                 for (int r = 0; r < p.n_peer; r++) p.peer_out[r][j] = val;  // partial of a row-parallel GEMV, to every rank

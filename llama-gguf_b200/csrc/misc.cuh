@@ -89,6 +89,7 @@ struct RouteParams {
     int hidden, n_experts, top_k;
     int* sel;              // out [top_k]
     float* wt;             // out [top_k]
+    unsigned int* epoch;   // optional (expert parallel): bumped once per call -- the layer's exchange epoch, the same on every GPU
 };
 __global__ void __launch_bounds__(256) moe_route_kernel(const RouteParams p) {
     pdl_launch_dependents();
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) moe_route_kernel(const RouteParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (p.epoch) *p.epoch += 1u;
         unsigned long long taken = 0ull;
         float sel_l[8];
         float mx = -INFINITY;
@@ -238,6 +240,79 @@ __global__ void matmul_f32_kernel(const float* __restrict__ a, const float* __re
     float sum = 0.0f;
     for (int kk = 0; kk < k; kk++) sum = __fadd_rn(sum, __fmul_rn(a[(size_t)i * k + kk], b[(size_t)kk * n + j]));
     out[idx] = sum;
+}
+
+
+// ---------------------------------------------------------------- expert parallel (Mixtral across the GPUs of one box)
+// Replaces the reference's rayon loop over the selected experts on ONE host (src/model/moe.rs:352-361) and its per-token H2D copies
+// (src/backend/cuda/gpu_only.rs:1834-1857).  Every GPU runs attention and the router (replicated: the same selection everywhere);
+// expert e lives on GPU e / (E / P).  After the expert GEMVs of a layer:
+//   ep_push_kernel    : for every slot whose expert is local, the weighted output y_s = w_s * down_s(...) goes to EVERY GPU's buffer as
+//                       8-byte (value, epoch) packets over NVLink peer memory -- no fence, no flag: a packet is valid when its epoch is
+//                       this layer's; thread 0 also leaves this GPU's arrival mark with every peer (lock step: nobody runs two layers
+//                       ahead of a GPU that owned nothing, so the two packet buffers can alternate);
+//   ep_combine_kernel : polls the k slots' packets (and the arrival marks) in local memory and writes xa = ((0 + y_0) + y_1 ...) + h,
+//                       the order of moe.rs:363-368 + layers.rs:1235-1241 -- bit-identical to the single-GPU path.
+// At batch 1 the dispatch is free (the router runs everywhere); the combine is the only exchange.
+struct EpParams {
+    const int* sel;               // [top_k] selected experts (device, written by moe_route_kernel)
+    const unsigned int* epoch;    // device counter: moe_route_kernel bumps it once per layer (the same count on every GPU)
+    int top_k, hidden, rank, world, experts_per_rank;
+    const float* y;               // [top_k][hidden] local weighted expert outputs (only the local slots are meaningful)
+    uint2* peer_ll[8];            // every GPU's [2][8][hidden] packet buffers as mapped here
+    unsigned int* peer_mark[8];   // every GPU's [8] arrival marks as mapped here
+    const uint2* ll;              // this GPU's packet buffers
+    const unsigned int* mark;     // this GPU's arrival marks
+    const float* h;               // residual
+    float* out;                   // [hidden]
+    int* err;
+};
+__global__ void __launch_bounds__(256) ep_push_kernel(const EpParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned int ep = *p.epoch;
+    const size_t buf = (size_t)(ep & 1u) * 8 * p.hidden;
+    for (int s = 0; s < p.top_k; s++) {
+        if (p.sel[s] / p.experts_per_rank != p.rank) continue;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.hidden; j += gridDim.x * blockDim.x) {
+            const unsigned int v = __float_as_uint(p.y[(size_t)s * p.hidden + j]);
+            for (int r = 0; r < p.world; r++)
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p.peer_ll[r] + buf + (size_t)s * p.hidden + j), "r"(v), "r"(ep) : "memory");
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int r = 0; r < p.world; r++) asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p.peer_mark[r] + p.rank), "r"(ep) : "memory");
+}
+__global__ void __launch_bounds__(256) ep_combine_kernel(const EpParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned int ep = *p.epoch;
+    const size_t buf = (size_t)(ep & 1u) * 8 * p.hidden;
+    const long long t0 = clock64();
+    bool dead = false;
+    if (threadIdx.x < p.world) {   // lock step: every GPU has reached this layer's push
+        unsigned int v;
+        for (;;) {
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p.mark + threadIdx.x) : "memory");
+            if ((int)(v - ep) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) { dead = true; break; }
+        }
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.hidden; j += gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (int s = 0; s < p.top_k; s++) {
+            unsigned int v, e;
+            for (;;) {
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(p.ll + buf + (size_t)s * p.hidden + j) : "memory");
+                if (e == ep) break;
+                if (clock64() - t0 > 4000000000LL) { dead = true; break; }
+            }
+            acc += __uint_as_float(v);
+        }
+        p.out[j] = acc + p.h[j];
+    }
+    if (dead && p.err) atomicExch(p.err, 8);
+    __syncthreads();   // (the arrival-mark wait of the first threads holds the whole CTA)
 }
 
 }  // namespace b200

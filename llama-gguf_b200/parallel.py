@@ -1,6 +1,7 @@
-"""Tensor-parallel host side of the cuda-b200 backend: one process per GPU (torch.distributed for the plumbing),
-Megatron-style column / row shards of the quantised weights, all-reduce inside the per-token kernel over NVLink
-peer memory.
+"""Tensor-parallel (dense models) and expert-parallel (MoE models) host side of the cuda-b200 backend: one process per GPU
+(torch.distributed for the plumbing), Megatron-style column / row shards of the quantised weights with the all-reduce inside
+the per-token kernel, or experts spread over the GPUs (everything else replicated) with the combine through (value, epoch)
+packets -- both over NVLink peer memory, no NCCL call on the data path.
 
 Mirrors the reference's ShardingPlan (src/backend/tensor_parallel.rs:69-106) and replaces its gRPC
 all-reduce-via-rank-0 (src/distributed/tensor_parallel_distributed.rs:135-187).  `shard_plan` / `shard_tensor` /
@@ -28,20 +29,35 @@ def shard_plan(desc: dict, world: int) -> dict:
     """Local dimensions of one rank, or InvalidArgument if the model does not divide (tensor_parallel.rs:69-106)."""
     if world not in (1, 2, 4, 8):
         raise InvalidArgument("tensor-parallel world size must be 1, 2, 4 or 8")
-    for k in ("n_heads", "n_kv_heads", "ffn", "vocab"):
+    moe = desc.get("n_experts", 0) > 0
+    for k in (() if moe and world > 1 else ("n_heads", "n_kv_heads", "ffn", "vocab")):
         if desc[k] % world:
             raise InvalidArgument(f"{k}={desc[k]} is not divisible by the world size {world}")
-    if world > 1 and (desc["vocab"] // world) % 16:
+    if world > 1 and not moe and (desc["vocab"] // world) % 16:
         raise InvalidArgument("vocab / world_size must be a multiple of 16")
     if world > 1 and desc.get("n_experts", 0) > 0:
-        raise InvalidArgument("tensor parallelism for MoE models is not built yet")
+        # MoE: EXPERT parallel (attention / norms / router / head replicated, expert e on rank e // (E / world))
+        if desc["n_experts"] % world:
+            raise InvalidArgument(f"n_experts={desc['n_experts']} is not divisible by the world size {world}")
+        return {"n_heads": desc["n_heads"], "n_kv_heads": desc["n_kv_heads"], "ffn": desc["ffn"], "vocab": desc["vocab"],
+                "hidden": desc["hidden"], "n_experts": desc["n_experts"] // world, "expert_parallel": True}
     return {"n_heads": desc["n_heads"] // world, "n_kv_heads": desc["n_kv_heads"] // world, "ffn": desc["ffn"] // world,
             "vocab": desc["vocab"] // world, "hidden": desc["hidden"]}
 
 
-def shard_tensor(name: str, ggml_type: int, ne, data: np.ndarray, world: int, rank: int):
-    """(ne_local, bytes_local) of `rank`'s shard of a tensor in GGUF block layout (rows of ne[0]/bs blocks)."""
+def shard_tensor(name: str, ggml_type: int, ne, data: np.ndarray, world: int, rank: int, expert_parallel: bool = False):
+    """(ne_local, bytes_local) of `rank`'s shard of a tensor in GGUF block layout (rows of ne[0]/bs blocks).
+    expert_parallel: only the *_exps tensors are split (by expert: the outermost dimension), everything else is replicated."""
     raw = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    if expert_parallel and world > 1:
+        ne = list(ne)
+        if "_exps.weight" not in name:
+            return ne, raw
+        if len(ne) != 3 or ne[2] % world:
+            raise InvalidArgument(f"{name}: experts not divisible by the world size")
+        n = raw.size // world
+        ne[2] //= world
+        return ne, raw[rank * n:(rank + 1) * n]
     kind = shard_kind(name) if world > 1 else 0
     be, bb = BLOCK[ggml_type]
     ne = list(ne)
@@ -101,13 +117,14 @@ class TensorParallelInference:
         self.gpu = GpuOnlyInference(desc, tensors, device=device, feeder=feeder, parallel=(self.world, self.rank),
                                     exchange=lambda b: all_gather_bytes(b, group))
         self.vocab = desc["vocab"]
+        self.expert_parallel = self.gpu.expert_parallel   # MoE: every rank holds the full logits (replicated head), nothing to gather
         dist.barrier(group)
 
     def _gather(self, local):
         import torch
         import torch.distributed as dist
 
-        if self.world == 1:
+        if self.world == 1 or self.expert_parallel:
             return local
         backend = dist.get_backend(self.group)
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")

@@ -28,7 +28,7 @@ def test_plan_rejects_what_does_not_divide():
     with pytest.raises(B.InvalidArgument):
         TP.shard_plan(dict(d, n_kv_heads=2), 4)
     with pytest.raises(B.InvalidArgument):
-        TP.shard_plan(make_desc(PRESETS["mixtral-8x7b"], 8192), 2)   # MoE + TP not built yet
+        TP.shard_plan(dict(make_desc(PRESETS["mixtral-8x7b"], 8192), n_experts=6), 4)   # experts must divide
     with pytest.raises(B.InvalidArgument):
         TP.shard_plan(dict(d, vocab=128264), 8)          # vocab / 8 not a multiple of 16
 
@@ -123,3 +123,19 @@ def test_tp_context_needs_a_gpu_or_fails_loudly():
         pytest.skip("a CUDA device is present")
     with pytest.raises(B.NotAvailable):
         B.GpuOnlyInference(make_desc(PRESETS["llama-3-8b"], 64), {}, parallel=(2, 0), exchange=lambda b: [b, b])
+
+
+def test_expert_parallel_plan_and_shards():
+    """MoE + world > 1 = EXPERT parallel: experts split by the outermost dimension, everything else replicated
+    (replaces the single-host rayon loop of src/model/moe.rs:352-361)."""
+    d = make_desc(PRESETS["mixtral-8x7b"], 8192)
+    plan = TP.shard_plan(d, 8)
+    assert plan["expert_parallel"] and plan["n_experts"] == 1 and plan["n_heads"] == d["n_heads"] and plan["vocab"] == d["vocab"]
+    rng = np.random.default_rng(3)
+    ne = [256, 64, 4]                                  # [K, rows, experts] Q4_K: 144 bytes per row
+    data = rng.integers(0, 256, size=4 * 64 * 144, dtype=np.uint8)
+    parts = [TP.shard_tensor("blk.0.ffn_gate_exps.weight", B.Q4_K, ne, data, 2, r, expert_parallel=True) for r in range(2)]
+    assert parts[0][0] == [256, 64, 2] and parts[1][0] == [256, 64, 2]
+    assert np.array_equal(np.concatenate([parts[0][1], parts[1][1]]), data)
+    full_ne, full = TP.shard_tensor("blk.0.attn_q.weight", B.Q4_K, [256, 64], data[: 64 * 144], 2, 1, expert_parallel=True)
+    assert full_ne == [256, 64] and np.array_equal(full, data[: 64 * 144])   # replicated
