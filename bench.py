@@ -104,8 +104,7 @@ class ClockSampler:
 
 def host_argmax_last(v):
     """max_by(partial_cmp): the LAST maximal element wins (src/main.rs:1816-1821)."""
-    m = v.max()
-    return int(v.size - 1 - np.argmax(v[::-1] == m))
+    return int(v.size - 1 - np.argmax(v[::-1]))   # (np.argmax returns the FIRST maximum of the reversed view; one pass, no temporaries)
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -203,7 +202,7 @@ def main():
     workload = (f"{args.model} arch, {args.mix} random-init GGUF blocks, batch-1 greedy decode after a "
                 f"{args.prompt_len}-token prompt, {args.ctx}-token context window (f32 KV)")
     config = {"workload": workload, "model_arch": args.model, "quant_mix": args.mix, "batch": 1, "context_window": args.ctx,
-              "prompt_len": args.prompt_len, "parallelism": f"tp{args.gpus}" if args.gpus > 1 else "single-gpu",
+              "prompt_len": args.prompt_len, "parallelism": (f"ep{args.gpus}" if preset.get("n_experts", 0) else f"tp{args.gpus}") if args.gpus > 1 else "single-gpu",
               "l2_policy": "inputs larger than L2: each step streams the whole weight set (>= 4.6 GB) through the 126 MB L2"}
 
     if args.impl == "reference":

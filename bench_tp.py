@@ -80,11 +80,12 @@ def main(args, preset, config, rank, world, local_rank):
     bytes_rank = wbytes_local + kvpp_local * kv_len_mid
     achieved = bytes_rank / (ms_per_step * 1e-3) / 1e9
     if rank == 0:
-        roofline = {"bound": "hbm", "kernel": {"stream2": "stream2_decode_kernel", "stream": "stream_decode_kernel"}.get(tp.path(), "mega_decode_kernel") + " (per rank)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        roofline = {"bound": "hbm", "kernel": {"stream2": "stream2_decode_kernel", "stream": "stream_decode_kernel", "graph": "gemv_mma_kernel (CUDA graph of per-op kernels)"}.get(tp.path(), "mega_decode_kernel") + " (per rank)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "peak_kind": f"{peaks_kind} copy bandwidth (MEASURED_PEAKS.json)", "traffic": None,
                     "bytes_per_launch": bytes_rank, "avg_launch_us": ms_per_step * 1e3,
-                    "note": "one persistent kernel per token and rank; bytes = this rank's weight shard + its KV heads"}
+                    "note": ("expert parallel: bytes = the replicated attention / head weights + the selected experts' weights (summed over the GPUs that own them) + KV"
+                             if tp.expert_parallel else "one persistent kernel per token and rank; bytes = this rank's weight shard + its KV heads")}
         out = {"metric": BM.METRIC, "value": value, "unit": BM.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": config, "clocks": clocks,

@@ -1,12 +1,13 @@
 #!/bin/bash
-# N-GPU visit: TP bench lines of Llama-3-8B and Llama-3-70B (BASELINE configs[2], configs[3])
+# N-GPU visit: TP / EP bench lines (BASELINE configs[2], [3], [4]); SPECS="model steps mix;..."
 set -u
 N=${1:-8}
 mkdir -p gpurun_out
-for spec in ${SPECS:-"llama-3-8b 32" "llama-3-70b 16"}; do
+IFS=";" read -ra SPECA <<< "${SPECS:-llama-3-8b 32;llama-3-70b 16}"
+for spec in "${SPECA[@]}"; do
   set -- $spec
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
-      bench.py --gpus $N --model $1 --steps $2 --warmup 4 > gpurun_out/tp${N}_$1.json 2> gpurun_out/tp${N}_$1.err
+      bench.py --gpus $N --model $1 --steps $2 --mix ${3:-Q4_K_M} --warmup 4 > gpurun_out/tp${N}_$1.json 2> gpurun_out/tp${N}_$1.err
   echo "bench tp$N $1 exit $?"; grep -a "built and sharded" gpurun_out/tp${N}_$1.err | head -1 | cut -c1-200
   python - <<PY
 import json

@@ -192,7 +192,7 @@ def test_error_mapping(be, b200):
 
 
 # ---- tcgen05 / TMEM dequant-GEMM (csrc/gemm_umma.cuh): T rows of vec_mat_q at once, fp16 operands, f32 accumulation ----
-# tolerance: 2e-3 of the typical output magnitude (fp16 rounding of both operands, ~3e-4 measured), stated here because
+# tolerance: 1e-3 of the typical output magnitude (fp16 rounding of both operands, ~3e-4 measured), stated here because
 # this path trades the exact f32 arithmetic of the GEMV for the tensor cores (prefill / batched decode).
 @pytest.mark.parametrize("t", [12, 13, 14, 8])
 @pytest.mark.parametrize("rows,k,n", [(1, 256, 5), (32, 512, 130), (33, 1024, 128), (70, 4096, 257), (300, 2048, 64)])
@@ -204,4 +204,4 @@ def test_mat_mat_q_tensor_core_gemm(be, oracle, t, rows, k, n):
     assert got.shape == (rows, n)
     for r in sorted({0, rows // 2, rows - 1}):
         want = oracle.vec_mat_q(t, w, x[r], n)
-        assert gemv_err(got[r], want, k, 0.05, x[r]) < 2e-3, f"row {r}"
+        assert gemv_err(got[r], want, k, 0.05, x[r]) < 1e-3, f"row {r}"

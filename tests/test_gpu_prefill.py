@@ -1,9 +1,10 @@
 """GEMM prefill (csrc/gemm_umma.cuh tcgen05/TMEM dequant-GEMM + csrc/prefill.cuh) through the batch entry point
 b200_prefill, against the oracle's token-by-token LlamaModel::forward (src/model/llama.rs:275-362).
 
-Tolerance: this path rounds both GEMM operands to fp16 (f32 accumulation in TMEM), so it is held to 3e-3 relative
-(max|a-b| / max|b|) on the logits -- looser than the 1e-3 of the exact paths, which the token-by-token entry points
-(prefill_token / forward) keep.  The KV cache it leaves must let the exact decode path continue within the same bound."""
+Tolerance: north_star's 1e-3 relative (max|a-b| / max|b|) on the logits.  This path rounds both GEMM operands to fp16 (f32
+accumulation in TMEM); measured on these cases (scripts/gemm_err.py on a B200): 0.9e-4 ... 5.3e-4, so it holds the same
+bound as the exact token-by-token entry points (which measure ~2e-6).  The KV cache it leaves must let the exact decode
+path continue within the same bound."""
 import os
 
 import numpy as np
@@ -13,7 +14,7 @@ import synth
 from synth import rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 3e-3
+TOL = 1e-3
 
 synth.TINY["qwen-kq-tiny"] = dict(arch="qwen2", hidden=512, n_layers=2, n_heads=8, n_kv_heads=2, head_dim=64, ffn=1024,
                                   vocab=600, norm_eps=1e-6, rope_base=1e6, rope_neox=1, bias=True, tied=True)
@@ -66,7 +67,7 @@ def test_short_prompts_and_disabled_gemm_stay_exact(b200, oracle):
 @pytest.mark.parametrize("preset,mix", [("llama-tiny", "Q4_K_M"), ("qwen-kq-tiny", "Q5_K_M")])
 def test_batched_decode_through_the_gemm(b200, oracle, preset, mix):
     """b200_decode_batch with >= 8 sequences: one pass of the dequant-GEMMs for all rows, each row at ITS slot's position
-    and on ITS slot's KV cache.  Same fp16 tolerance as the GEMM prefill."""
+    and on ITS slot's KV cache.  Same 1e-3 bound as the GEMM prefill."""
     nseq = 12
     arch, desc, tensors = synth.synth_model(preset, mix, 64, max_batch=nseq)
     gpu = b200.GpuOnlyInference(desc, tensors)
