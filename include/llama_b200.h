@@ -113,6 +113,27 @@ B200_API void b200_ctx_destroy(b200_ctx* ctx);
 B200_API int b200_ctx_tp_handle(b200_ctx* ctx, void* handle_out64);
 B200_API int b200_ctx_tp_set_peer(b200_ctx* ctx, int peer_rank, const void* handle64);
 
+/* Single-process tensor / expert parallelism ("TP ranks are threads inside the library; callers never see ranks";
+ * TensorParallel trait, src/backend/tensor_parallel.rs:13-32).  A group owns one context per device and one host thread per context;
+ * peers are connected with cudaDeviceEnablePeerAccess (no IPC handles, no other process).  Dense models are tensor parallel
+ * (ShardingPlan::from_config, tensor_parallel.rs:69-106), MoE models expert parallel.  Every call below fans out to the ranks and
+ * returns when all of them are done; logits_out always receives the FULL `vocab` row.  devices == NULL: ordinals 0 .. n_devices-1.
+ * n_devices == 1 is an ordinary single-GPU context behind the same interface.  The Rust shim creates a group when B200_TP is set:
+ * nothing above GpuOnlyInference changes. */
+typedef struct b200_group b200_group;
+B200_API int b200_group_create(const b200_model_desc* desc, int n_devices, const int* devices, b200_group** out);
+B200_API int b200_group_upload_tensor(b200_group* g, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne, int n_dims,
+                             const void* host, size_t nbytes);   /* the FULL tensor; every rank keeps its shard */
+B200_API int b200_group_finalize(b200_group* g);
+B200_API void b200_group_destroy(b200_group* g);
+B200_API int b200_group_forward(b200_group* g, int seq, uint32_t token, float* logits_out);
+B200_API int b200_group_prefill_token(b200_group* g, int seq, uint32_t token);
+B200_API int b200_group_reset(b200_group* g, int seq);
+B200_API int b200_group_position(b200_group* g, int seq, uint64_t* out);
+B200_API int b200_group_decode_greedy(b200_group* g, int seq, uint32_t first_token, int n_steps, uint32_t* tokens_out, float* elapsed_ms);
+B200_API int b200_group_size(b200_group* g, int* out);
+B200_API int b200_group_ctx(b200_group* g, int rank, b200_ctx** out);   /* rank's context (stats, path, debug); do not destroy */
+
 /* GpuInference::forward (backend/mod.rs:285): one token through every layer;
  * logits_out receives `vocab` f32 on the host. */
 B200_API int b200_forward(b200_ctx* ctx, int seq, uint32_t token, float* logits_out);

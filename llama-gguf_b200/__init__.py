@@ -108,6 +108,21 @@ def lib():
     L.b200_ctx_stats.argtypes = [vp, u64p, u64p, u64p]
     L.b200_ctx_tp_handle.argtypes = [vp, vp]
     L.b200_ctx_tp_set_peer.argtypes = [vp, C.c_int, vp]
+    try:   # single-process group (one context + one host thread per device inside the library)
+        L.b200_group_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.b200_group_upload_tensor.argtypes = [vp, C.c_char_p, C.c_uint32, u64p, C.c_int, vp, C.c_size_t]
+        L.b200_group_finalize.argtypes = [vp]
+        L.b200_group_destroy.argtypes = [vp]
+        L.b200_group_destroy.restype = None
+        L.b200_group_forward.argtypes = [vp, C.c_int, C.c_uint32, fp]
+        L.b200_group_prefill_token.argtypes = [vp, C.c_int, C.c_uint32]
+        L.b200_group_reset.argtypes = [vp, C.c_int]
+        L.b200_group_position.argtypes = [vp, C.c_int, u64p]
+        L.b200_group_decode_greedy.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), fp]
+        L.b200_group_size.argtypes = [vp, C.POINTER(C.c_int)]
+        L.b200_group_ctx.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    except AttributeError:  # an older build of the library (B200_LIB override)
+        pass
     L.b200_debug_mega_timeline.argtypes = [vp, u64p, C.c_int]
     L.b200_debug_err.argtypes = [vp, C.POINTER(C.c_int)]
     L.b200_ctx_path.argtypes = [vp, C.POINTER(C.c_int)]
@@ -538,6 +553,87 @@ class GpuOnlyInference:
         ms, nbytes = C.c_float(0), C.c_uint64(0)
         _check(lib().b200_bench_weight_gemv(self._h, name.encode(), iters, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+
+class GroupInference:
+    """GpuInference over the GPUs of ONE process (b200_group_*): tensor parallel for dense models, expert parallel for MoE models,
+    one host thread per device inside the library -- the caller never sees ranks (TensorParallel trait,
+    src/backend/tensor_parallel.rs:13-32).  Same surface as GpuOnlyInference: forward() returns the full logits row."""
+
+    def __init__(self, desc: dict, tensors: dict, n_devices=1, devices=None, feeder=None):
+        L = lib()
+        if device_count() < n_devices:
+            raise NotAvailable(f"cuda-b200: {n_devices} CUDA devices needed, {device_count()} present (no CPU fallback)")
+        d = ModelDesc()
+        for k, v in desc.items():
+            if k not in DESC_KEYS:
+                raise InvalidArgument(f"unknown model desc field {k}")
+            setattr(d, k, v)
+        self.desc = {k: getattr(d, k) for k in DESC_KEYS}
+        self.world = n_devices
+        self.vocab = self.desc["vocab"]
+        devs = (C.c_int * n_devices)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        _check(L.b200_group_create(C.byref(d), n_devices, devs, C.byref(h)))
+        self._h = h
+        try:
+            for name, (t, ne, data) in (tensors or {}).items():
+                self.upload_tensor(name, t, ne, data)
+            if feeder is not None:
+                feeder(self.upload_tensor)
+            _check(L.b200_group_finalize(self._h))
+        except Exception:
+            self.close()
+            raise
+
+    def upload_tensor(self, name, ggml_type, ne, data):
+        a = np.ascontiguousarray(data)
+        nd = (C.c_uint64 * 4)(*(list(ne) + [1] * (4 - len(ne))))
+        _check(lib().b200_group_upload_tensor(self._h, name.encode(), int(ggml_type), nd, len(ne), a.ctypes.data, a.nbytes))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ctx(self, rank=0):
+        h = C.c_void_p()
+        _check(lib().b200_group_ctx(self._h, rank, C.byref(h)))
+        return h
+
+    def path(self):
+        v = C.c_int(0)
+        _check(lib().b200_ctx_path(self._ctx(0), C.byref(v)))
+        return ("graph", "mega", "stream", "stream2")[v.value]
+
+    def forward(self, token_id, seq=0):
+        logits = np.empty(self.vocab, dtype=np.float32)
+        _check(lib().b200_group_forward(self._h, int(seq), int(token_id), logits.ctypes.data_as(C.POINTER(C.c_float))))
+        return logits
+
+    def prefill_token(self, token_id, seq=0):
+        _check(lib().b200_group_prefill_token(self._h, int(seq), int(token_id)))
+
+    def reset(self, seq=0):
+        _check(lib().b200_group_reset(self._h, int(seq)))
+
+    def position(self, seq=0):
+        v = C.c_uint64(0)
+        _check(lib().b200_group_position(self._h, int(seq), C.byref(v)))
+        return int(v.value)
+
+    def decode_greedy(self, first_token, n_steps, seq=0):
+        toks = np.empty(n_steps, dtype=np.uint32)
+        ms = C.c_float(0.0)
+        _check(lib().b200_group_decode_greedy(self._h, int(seq), int(first_token), int(n_steps),
+                                              toks.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(ms)))
+        return toks, float(ms.value)
 
 
 class GpuModelWrapper:

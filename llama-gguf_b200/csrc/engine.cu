@@ -16,8 +16,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/llama_b200.h"
@@ -1888,6 +1894,190 @@ extern "C" int b200_decode_greedy(b200_ctx* c, int seq, uint32_t first_token, in
     if (elapsed_ms) *elapsed_ms = ms;
     sl.host_pos += (uint64_t)n_steps;
     if (tokens_out) CU(cudaMemcpy(tokens_out, sl.d_generated, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ single-process group: one context and one host thread per device
+// The per-token kernels of the ranks wait for each other on the device, so the ranks' calls must be in flight together: every group call
+// is handed to the persistent worker thread of each rank and returns when all of them have finished.
+struct GroupWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = true, quit = false;
+    int rc = 0;
+    std::string msg;
+};
+struct b200_group {
+    std::vector<b200_ctx*> ctx;
+    std::vector<std::unique_ptr<GroupWorker>> workers;
+    bool ep = false;
+    int vocab = 0, vocab_l = 0;
+};
+static void group_worker_loop(GroupWorker* w) {
+    for (;;) {
+        std::function<int()> job;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+            if (w->quit) return;
+            job = w->job;
+            w->has_job = false;
+        }
+        const int rc = job();
+        const char* m = rc ? b200_last_error() : "";
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->rc = rc;
+            w->msg = m ? m : "";
+            w->done = true;
+        }
+        w->cv.notify_all();
+    }
+}
+// runs fn(rank) on every rank's thread; the first failure (lowest rank) is returned with its message
+template <class F>
+static int group_run(b200_group* g, F fn) {
+    const int n = (int)g->ctx.size();
+    for (int r = 0; r < n; r++) {
+        GroupWorker* w = g->workers[r].get();
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->job = [fn, r]() { return fn(r); };
+            w->has_job = true;
+            w->done = false;
+        }
+        w->cv.notify_all();
+    }
+    int rc = B200_OK;
+    std::string msg;
+    for (int r = 0; r < n; r++) {
+        GroupWorker* w = g->workers[r].get();
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc && !rc) { rc = w->rc; msg = w->msg; }
+    }
+    return rc ? fail(rc, msg) : B200_OK;
+}
+
+extern "C" void b200_group_destroy(b200_group* g) {
+    if (!g) return;
+    for (auto& w : g->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    for (b200_ctx* c : g->ctx) {
+        if (!c) continue;
+        for (int r = 0; r < c->par.world_size && r < kMmaMaxPeers; r++) c->tp_peer[r] = (r == c->par.rank) ? c->tp_peer[r] : nullptr;   // (not IPC mappings)
+        b200_ctx_destroy(c);
+    }
+    delete g;
+}
+
+extern "C" int b200_group_create(const b200_model_desc* desc, int n_devices, const int* devices, b200_group** out) {
+    if (!desc || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_create: null argument");
+    if (n_devices != 1 && n_devices != 2 && n_devices != 4 && n_devices != 8) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_create: n_devices must be 1, 2, 4 or 8");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(B200_ERR_NOT_AVAILABLE, "cuda-b200: no CUDA device (this backend has no CPU fallback)"); }
+    std::vector<int> dev(n_devices);
+    for (int r = 0; r < n_devices; r++) {
+        dev[r] = devices ? devices[r] : r;
+        if (dev[r] < 0 || dev[r] >= n_dev) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_create: device ordinal out of range");
+        for (int q = 0; q < r; q++) if (dev[q] == dev[r]) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_create: duplicate device");
+    }
+    b200_group* g = new b200_group();
+    g->ctx.assign(n_devices, nullptr);
+    for (int r = 0; r < n_devices; r++) {
+        b200_parallel_desc par{n_devices, r, dev[r]};
+        const int rc = b200_ctx_create(desc, &par, &g->ctx[r]);
+        if (rc) { b200_group_destroy(g); return rc; }
+    }
+    g->ep = g->ctx[0]->ep;
+    g->vocab = g->ctx[0]->d.vocab;
+    g->vocab_l = g->ctx[0]->vocab_l;
+    if (n_devices > 1) {
+        // peer access both ways, then every rank's exchange region as every other rank sees it: the plain device pointer
+        for (int r = 0; r < n_devices; r++) {
+            cudaSetDevice(dev[r]);
+            for (int q = 0; q < n_devices; q++) {
+                if (q == r) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, dev[r], dev[q]);
+                if (!can) { b200_group_destroy(g); return fail(B200_ERR_UNSUPPORTED, "b200_group_create: no peer access between the devices"); }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dev[q], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { b200_group_destroy(g); return fail(B200_ERR_INITIALIZATION_FAILED, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+                cudaGetLastError();
+            }
+        }
+        uint8_t h[64];
+        for (int r = 0; r < n_devices; r++) {   // (allocates the region)
+            const int rc = b200_ctx_tp_handle(g->ctx[r], h);
+            if (rc) { b200_group_destroy(g); return rc; }
+        }
+        for (int r = 0; r < n_devices; r++)
+            for (int q = 0; q < n_devices; q++) {
+                g->ctx[r]->tp_peer[q] = g->ctx[q]->tp_region;
+                g->ctx[r]->tp_peer_set[q] = true;
+            }
+    }
+    for (int r = 0; r < n_devices; r++) {
+        g->workers.emplace_back(new GroupWorker());
+        GroupWorker* w = g->workers.back().get();
+        w->th = std::thread(group_worker_loop, w);
+    }
+    *out = g;
+    return B200_OK;
+}
+
+extern "C" int b200_group_upload_tensor(b200_group* g, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne, int n_dims,
+                                        const void* host, size_t nbytes) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_upload_tensor: null group");
+    return group_run(g, [=](int r) { return b200_ctx_upload_tensor(g->ctx[r], gguf_name, ggml_type, ne, n_dims, host, nbytes); });
+}
+extern "C" int b200_group_finalize(b200_group* g) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_finalize: null group");
+    return group_run(g, [=](int r) { return b200_ctx_finalize(g->ctx[r]); });
+}
+extern "C" int b200_group_forward(b200_group* g, int seq, uint32_t token, float* logits_out) {
+    if (!g || !logits_out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_forward: null argument");
+    if (g->ctx.size() == 1) return b200_forward(g->ctx[0], seq, token, logits_out);
+    // tensor parallel: rank r produces rows [r * vocab / P, (r + 1) * vocab / P) of the logits, straight into the caller's row;
+    // expert parallel: the head is replicated -- rank 0's row is the answer, the others land in their contexts' scratch rows
+    return group_run(g, [=](int r) {
+        if (g->ep && r > 0) return b200_prefill_token(g->ctx[r], seq, token);   // (same token, same layers; its logits are not needed)
+        return b200_forward(g->ctx[r], seq, token, logits_out + (g->ep ? 0 : (size_t)r * g->vocab_l));
+    });
+}
+extern "C" int b200_group_prefill_token(b200_group* g, int seq, uint32_t token) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_prefill_token: null group");
+    return group_run(g, [=](int r) { return b200_prefill_token(g->ctx[r], seq, token); });
+}
+extern "C" int b200_group_reset(b200_group* g, int seq) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_reset: null group");
+    return group_run(g, [=](int r) { return b200_reset(g->ctx[r], seq); });
+}
+extern "C" int b200_group_position(b200_group* g, int seq, uint64_t* out) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_position: null group");
+    return b200_position(g->ctx[0], seq, out);
+}
+extern "C" int b200_group_decode_greedy(b200_group* g, int seq, uint32_t first_token, int n_steps, uint32_t* tokens_out, float* elapsed_ms) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_decode_greedy: null group");
+    std::vector<float> ms(g->ctx.size(), 0.0f);
+    float* msp = ms.data();
+    const int rc = group_run(g, [=](int r) { return b200_decode_greedy(g->ctx[r], seq, first_token, n_steps, r == 0 ? tokens_out : nullptr, msp + r); });
+    if (elapsed_ms) *elapsed_ms = *std::max_element(ms.begin(), ms.end());   // device time, max over the ranks
+    return rc;
+}
+extern "C" int b200_group_size(b200_group* g, int* out) {
+    if (!g || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_size: null argument");
+    *out = (int)g->ctx.size();
+    return B200_OK;
+}
+extern "C" int b200_group_ctx(b200_group* g, int rank, b200_ctx** out) {
+    if (!g || !out || rank < 0 || rank >= (int)g->ctx.size()) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_ctx: bad argument");
+    *out = g->ctx[rank];
     return B200_OK;
 }
 
