@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "gemv.cuh"
 #include "gemm_umma.cuh"
+#include "gemm_umma2.cuh"
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -1437,6 +1438,32 @@ static int mega_launch(b200_ctx* c, int slot_i, int mode, int n_tokens) {
 static int prefill_chunk() { static int v = std::max(32, std::min(4096, env_int("B200_PREFILL_CHUNK", 2048))); return v; }
 
 
+// Dequant-GEMM dispatch: the warp-specialised persistent kernel (gemm_umma2.cuh) when the matrix has a raw-tile tensor map
+// (B200_GEMM2=0: the first kernel everywhere), else the first kernel (gemm_umma.cuh; TMA-fed only for passes of <= 64 rows).
+static Umma2EncodeFn gemm_encode_fn() {
+    static Umma2EncodeFn fn = []() -> Umma2EncodeFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (Umma2EncodeFn)f;
+    }();
+    return fn;
+}
+static bool gemm2_enabled() { static int v = env_int("B200_GEMM2", 1); return v != 0; }
+static cudaError_t gemm_dispatch(UmmaParams& p, int n_sm, cudaStream_t st, uint64_t* launches = nullptr) {
+    if (gemm2_enabled() && gemm_encode_fn() && umma2_eligible(p)) {
+        static int ng = std::max(2, std::min(3, env_int("B200_GEMM2_GROUPS", 2)));
+        if (launches) *launches += p.k_split ? 2 : 1;
+        return umma2_launch(gemm_encode_fn(), p, n_sm, 227 * 1024 - 2048, st, ng);
+    }
+    if (p.T > env_int("B200_GEMM_TMA_MAX_T", 64)) p.tmap = nullptr;   // first kernel: large tiles keep the direct reads (measured, round 1)
+    if (launches) *launches += p.k_split ? 2 : 1;
+    return umma_launch(p, st);
+}
+
 // TMA tensor maps for the dequant-GEMM's weight tiles: box = 128 rows x one 256-element block (stream_pitch(type, 1) bytes).
 // Matrices whose rows are not 16-byte multiples keep the direct global reads.
 static int umma_tmaps_build(b200_ctx* c) {
@@ -1474,9 +1501,7 @@ static int umma_tmaps_build(b200_ctx* c) {
 }
 static void umma_set_tmap(b200_ctx* c, UmmaParams& p) {
     p.tmap = nullptr;
-    // measured: passes of <= 64 rows (batched decode) gain 1.5x from the TMA-fed tiles; 2048-row prefill tiles lose ~4 %
-    // (the raw stages cost the second resident CTA per SM), so large T keeps the direct reads
-    if (p.T > env_int("B200_GEMM_TMA_MAX_T", 64)) return;
+    // (the first kernel only uses the map for passes of <= 64 rows: gemm_dispatch drops it for larger ones)
     auto it = c->pf_tmap_of.find(p.w);
     if (it == c->pf_tmap_of.end() || !c->pf_tmaps) return;
     p.tmap = (const CUtensorMap*)c->pf_tmaps + it->second;
@@ -1562,8 +1587,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         p.accumulate = acc; p.err = c->mma_err;
         umma_set_tmap(c, p);
         umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
-        c->launches += p.k_split ? 2 : 1;
-        return umma_launch(p, st);
+        return gemm_dispatch(p, c->n_sm, st, &c->launches);
     };
     int last_T = 0;
     for (int done = 0; done < n; done += cap) {
@@ -1617,7 +1641,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = d.vocab; hp.K = H;
         hp.x = XNh; hp.ldx = H; hp.T = n; hp.y = c->pf_logits; hp.ldy = d.vocab; hp.err = c->mma_err;
         umma_set_tmap(c, hp);
-        CU(umma_launch(hp, st));
+        CU(gemm_dispatch(hp, c->n_sm, st));
         c->launches += 3;
         return B200_OK;
     }
@@ -2418,7 +2442,24 @@ extern "C" int b200_op_mat_mat_q(const float* a, const void* w, uint32_t ggml_ty
     p.w = dw.as<uint8_t>(); p.row_bytes = (long long)row_bytes; p.type = t; p.n_rows = (int)n; p.K = (int)k;
     p.x = dh.as<__half>(); p.ldx = (int)k; p.T = (int)t_rows; p.y = dout.as<float>(); p.ldy = (int)n;
     if (!umma_eligible(p)) return fail(B200_ERR_SHAPE_MISMATCH, "mat_mat_q: rows of this type / length are not aligned for the tensor-core path");
-    CU(umma_launch(p, 0));
+    // raw-tile tensor map for the persistent kernel (what b200_ctx_finalize builds once per weight matrix)
+    DevBuf dmap;
+    if (gemm2_enabled() && gemm_encode_fn() && !(row_bytes & 15) && k % 256 == 0 && !dmap.alloc(sizeof(CUtensorMap))) {
+        const int pitch = stream_pitch(t, 1);
+        CUtensorMap tm;
+        const cuuint64_t dims[2] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)n};
+        const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)(pitch / 4), (cuuint32_t)kUmmaM};
+        const cuuint32_t estr[2] = {1, 1};
+        if (gemm_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dw.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            CU(cudaMemcpy(dmap.p, &tm, sizeof tm, cudaMemcpyHostToDevice));
+            p.tmap = dmap.p; p.raw_pitch = pitch; p.raw_bytes = 256 / be * bb;
+        }
+    }
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    CU(gemm_dispatch(p, n_sm, 0));
     if ((rc = op_finish("mat_mat_q"))) return rc;
     CU(cudaMemcpy(out, dout.p, t_rows * n * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
