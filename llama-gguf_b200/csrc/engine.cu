@@ -32,6 +32,7 @@
 #include "gemv.cuh"
 #include "gemm_umma.cuh"
 #include "gemm_umma2.cuh"
+#include "attn_umma.cuh"
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -187,6 +188,11 @@ struct b200_ctx {
     uint8_t* pf_rows = nullptr;      // batched decode: per-row position | KV base pointer | SeqState pointer
     float* pf_logits = nullptr;      // batched decode: [rows][vocab]
     float* pf_split = nullptr;       // split-K partial tiles of the small-T GEMMs
+    __half* pf_k16 = nullptr;        // fp16 copies of one layer's K rows / transposed V rows for the tensor-core prefill attention
+    __half* pf_vt16 = nullptr;
+    int pf_kv16_P = 0;
+    CUtensorMap pf_kmap, pf_vmap;
+    bool pf_attn_tc = true;          // B200_PREFILL_ATTN_TC=0: the CUDA-core prefill attention
     void* pf_tmaps = nullptr;        // TMA tensor maps (128-row boxes) of the GEMM weights
     std::map<const void*, int> pf_tmap_of;
     bool pf_tmaps_built = false;
@@ -290,6 +296,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_stream = env_int("B200_STREAM", 1) != 0;
     c->use_stream2 = env_int("B200_STREAM2", 1) != 0;
     c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
+    c->pf_attn_tc = env_int("B200_PREFILL_ATTN_TC", 1) != 0;
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
     c->prefill_queue = env_int("B200_PREFILL_QUEUE", 0) != 0;
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
@@ -645,6 +652,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_logits);
     cudaFree(c->pf_split);
     cudaFree(c->pf_tmaps);
+    cudaFree(c->pf_k16);
+    cudaFree(c->pf_vt16);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
     for (void* p : {(void*)c->xa, (void*)c->xb, (void*)c->qkv, (void*)c->attn, (void*)c->hbuf, (void*)c->logits,
                     (void*)c->attn_part, (void*)c->tickets, (void*)c->moe_sel, (void*)c->moe_wt, (void*)c->taps,
@@ -1547,6 +1556,18 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     }
     // batched decode: per-row (position, KV base of the slot, SeqState of the slot)
     const bool rows = seqs != nullptr;
+    // tensor-core attention of a prompt chunk (attn_umma.cuh): fp16 K / V^T copies of ONE layer (rewritten per layer and chunk)
+    bool attn_tc = !rows && c->pf_attn_tc && gemm_encode_fn() && attn_umma_ok(hd, nh, nkv);
+    if (attn_tc && !c->pf_k16) {
+        const int P = (d.max_seq_len + 127) & ~127;
+        CU_ALLOC(cudaMalloc((void**)&c->pf_k16, (size_t)2 * nkv * P * hd * sizeof(__half)));    // hi rows, then lo rows
+        CU_ALLOC(cudaMalloc((void**)&c->pf_vt16, (size_t)2 * nkv * P * hd * sizeof(__half)));   // hi rows, then lo rows
+        c->pf_kv16_P = P;
+        if (!attn_umma_encode(gemm_encode_fn(), c->pf_k16, c->pf_vt16, nkv, hd, P, &c->pf_kmap, &c->pf_vmap)) {
+            c->pf_attn_tc = false;
+            attn_tc = false;
+        }
+    }
     int* d_pos = reinterpret_cast<int*>(c->pf_rows);
     float** d_kv = reinterpret_cast<float**>(c->pf_rows + (size_t)cap * 8);
     SeqState** d_st = reinterpret_cast<SeqState**>(c->pf_rows + (size_t)cap * 16);
@@ -1613,14 +1634,29 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = ATh; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
             ap.n_heads = nh; ap.n_kv = nkv; ap.max_seq = d.max_seq_len; ap.scale = 1.0f / sqrtf((float)hd);
             if (rows) { ap.row_pos = d_pos; ap.row_kv = d_kv; ap.k_off = rp.k_off; ap.v_off = rp.v_off; }
-            const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
-            const int Gq = nh / nkv;
-            if (hd == 128) {
-                if (Gq <= 4) prefill_attn_kernel<128, 4><<<ablocks, 128, 0, st>>>(ap);
-                else prefill_attn_kernel<128, 8><<<ablocks, 128, 0, st>>>(ap);
+            if (attn_tc) {
+                const int kv_end = pos0 + T, kv_pad = (kv_end + 127) & ~127;
+                AttnUmmaParams up{};
+                up.qkv = Q; up.ld = QKV; up.out = ATh; up.ldo = A; up.pos0 = pos0; up.T = T; up.n_heads = nh; up.n_kv = nkv; up.G = nh / nkv;
+                up.P = c->pf_kv16_P; up.scale = ap.scale; up.err = c->mma_err;
+                if (hd == 128) {
+                    prefill_kv16_kernel<128><<<dim3(kv_pad / 64, nkv), 256, 0, st>>>(kc, vc, d.max_seq_len, kv_end, c->pf_kv16_P, c->pf_k16, c->pf_vt16);
+                    CU(attn_umma_launch_hd<128>(c->pf_kmap, c->pf_vmap, up, st));
+                } else {
+                    prefill_kv16_kernel<64><<<dim3(kv_pad / 64, nkv), 256, 0, st>>>(kc, vc, d.max_seq_len, kv_end, c->pf_kv16_P, c->pf_k16, c->pf_vt16);
+                    CU(attn_umma_launch_hd<64>(c->pf_kmap, c->pf_vmap, up, st));
+                }
+                c->launches += 1;
             } else {
-                if (Gq <= 4) prefill_attn_kernel<64, 4><<<ablocks, 128, 0, st>>>(ap);
-                else prefill_attn_kernel<64, 8><<<ablocks, 128, 0, st>>>(ap);
+                const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
+                const int Gq = nh / nkv;
+                if (hd == 128) {
+                    if (Gq <= 4) prefill_attn_kernel<128, 4><<<ablocks, 128, 0, st>>>(ap);
+                    else prefill_attn_kernel<128, 8><<<ablocks, 128, 0, st>>>(ap);
+                } else {
+                    if (Gq <= 4) prefill_attn_kernel<64, 4><<<ablocks, 128, 0, st>>>(ap);
+                    else prefill_attn_kernel<64, 8><<<ablocks, 128, 0, st>>>(ap);
+                }
             }
             CU(gemm(L.wo, A, ATh, A, T, X, H, nullptr, 1));                       // X += Wo attn
             prefill_rms_norm_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XNh, H);

@@ -94,3 +94,28 @@ def test_batched_decode_through_the_gemm(b200, oracle, preset, mix):
     for s in range(3):
         assert rel_err(got[s], refs[s].forward([3 + s])) < TOL
     gpu.close()
+
+
+@pytest.mark.parametrize("preset,n", [("llama-tiny", 200), ("tinyllama-tiny", 333), ("llama-stream-tiny", 130)])
+def test_tensor_core_prefill_attention_with_peaked_softmax(b200, oracle, preset, n):
+    """csrc/attn_umma.cuh (tcgen05 Q K^T and P V, two-pass softmax) against attention_cached (src/backend/cpu/ops.rs:1479-1537) where
+    attention matters: weights drawn 2.5x wider than the default so that the scores spread over several units and the softmax is
+    peaked (default random-init scores are ~0.1: a uniform average).  Also against the CUDA-core prefill attention on the same
+    GEMM path (B200_PREFILL_ATTN_TC=0), which isolates the attention kernel's own fp16 rounding."""
+    arch, desc, tensors = synth.synth_model(preset, "Q4_K_M", n + 8, sigma=0.05)
+    ref = oracle.OracleModel(desc, tensors)
+    prompt = synth.prompt_tokens(n, desc["vocab"])
+    want = ref.forward(prompt)
+    gpu = b200.GpuOnlyInference(desc, tensors)
+    got = gpu.prefill(prompt)
+    gpu.close()
+    os.environ["B200_PREFILL_ATTN_TC"] = "0"
+    try:
+        gpu = b200.GpuOnlyInference(desc, tensors)
+        simt = gpu.prefill(prompt)
+        gpu.close()
+    finally:
+        os.environ.pop("B200_PREFILL_ATTN_TC", None)
+    e_tc, e_simt, e_ab = rel_err(got, want), rel_err(simt, want), rel_err(got, simt)
+    print(f"peaked softmax {preset} n={n}: tensor-core vs oracle {e_tc:.2e}, CUDA-core vs oracle {e_simt:.2e}, tensor-core vs CUDA-core {e_ab:.2e}")
+    assert e_tc < TOL and e_ab < TOL
