@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) prefill_attn_umma_kernel(const __grid_
 #pragma unroll
                 for (int q = 0; q < 32; q++) {
                     const float s = __uint_as_float(v[q]);
-                    add += (s == -INFINITY) ? 0.0f : expf(s - mt);
+                    add += (s == -INFINITY) ? 0.0f : __expf(s - mt);
                 }
                 l = (m == -INFINITY ? 0.0f : l * expf(m - mt)) + add;
                 m = mt;
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(256, 1) prefill_attn_umma_kernel(const __grid_
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
                     const int q = 8 * c + 2 * h, key = key0 + q;
-                    const float e0 = (key <= pos_q) ? expf(__uint_as_float(v[q]) * p.scale - m) : 0.0f;
-                    const float e1 = (key + 1 <= pos_q) ? expf(__uint_as_float(v[q + 1]) * p.scale - m) : 0.0f;
+                    const float e0 = (key <= pos_q) ? __expf(__uint_as_float(v[q]) * p.scale - m) : 0.0f;
+                    const float e1 = (key + 1 <= pos_q) ? __expf(__uint_as_float(v[q + 1]) * p.scale - m) : 0.0f;
                     const __half2 hi = __floats2half2_rn(e0, e1);
                     const float2 hf = __half22float2(hi);
                     wh[h] = *reinterpret_cast<const uint32_t*>(&hi);

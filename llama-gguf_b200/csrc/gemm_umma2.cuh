@@ -132,6 +132,29 @@ __device__ __forceinline__ void u2_deq64_q4k(const uint8_t* blk, int kin, uint8_
     }
 }
 
+// Q6_K (dequant.rs:321-356), warp-cooperative: blocks are only 2-byte aligned and a raw row pitch of 224 bytes puts the same
+// offset of every fourth row on one bank, so thread-per-row reads conflict 8 ways.  Here the 32 lanes walk ONE row together: lane
+// (second, i) owns elements e = 32*second + 2i, 2i+1 of the 64-element step (one 16-bit load of ql, one of qh: 64 contiguous
+// bytes per warp), and a warp stores one whole 128-byte row of the swizzled tile per instruction.  value = (d * sc) * (q - 32).
+__device__ __forceinline__ void u2_deq64_q6k_rows(const uint8_t* raw, int pitch, int kin, uint8_t* sA, int row0, int lane) {
+    const int n = kin >> 7, hi = (kin >> 6) & 1, i = lane & 15, second = lane >> 4, qq = 2 * hi + second;
+    const int ql_off = 64 * n + 32 * second + 2 * i, qh_off = 128 + 32 * n + 2 * i, sc_off = 192 + 8 * n + (i >> 3) + 2 * qq;
+    const int e = 32 * second + 2 * i, sh_lo = 4 * hi, sh_hi = 2 * qq;
+    const uint32_t dst = (uint32_t)((e & 7) * 2);
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr++) {
+        const int r = row0 + rr;
+        const uint8_t* blk = raw + r * pitch;
+        const uint32_t a = *reinterpret_cast<const unsigned short*>(blk + ql_off), b = *reinterpret_cast<const unsigned short*>(blk + qh_off);
+        const float d = half_bits_to_float(*reinterpret_cast<const unsigned short*>(blk + 208));
+        const float ds = __fmul_rn(d, (float)(int)*reinterpret_cast<const signed char*>(blk + sc_off));
+        const uint32_t q0 = ((a >> sh_lo) & 15u) | (((b >> sh_hi) & 3u) << 4), q1 = ((a >> (8 + sh_lo)) & 15u) | (((b >> (8 + sh_hi)) & 3u) << 4);
+        // 0x4B000000 | q is the float 2^23 + q: subtracting 2^23 + 32 gives q - 32 exactly
+        const float f0 = __uint_as_float(0x4B000000u | q0) - 8388640.0f, f1 = __uint_as_float(0x4B000000u | q1) - 8388640.0f;
+        *reinterpret_cast<uint32_t*>(sA + umma_sw128(r, e >> 3) + dst) = umma_pack_h2(__fmul_rn(ds, f0), __fmul_rn(ds, f1));
+    }
+}
+
 struct U2Ring {   // ring cursor: stage index + phase parity, advanced without divisions (the role loops are single threads)
     uint32_t i, ph;
     __device__ __forceinline__ void next(uint32_t n) { if (++i == n) { i = 0; ph ^= 1u; } }
@@ -311,6 +334,8 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
                 if (pl.dbg & 1) {
                 } else if (p.type == T_Q4_K) {
                     u2_deq64_q4k(rrow, kin, tA, r);
+                } else if (p.type == T_Q6_K) {
+                    u2_deq64_q6k_rows(sR + rr.i * (uint32_t)pl.raw_stage + ((blk * p.raw_bytes) & 15), p.raw_pitch, kin, tA, r & ~31, lane);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tA + umma_sw128(r, c)) = umma_deq8<true>(p.type, rrow, kin, c);
@@ -354,18 +379,26 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
                       "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (j < p.n_rows) {
+                    if (p.k_split) {
 #pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const int tk = tok0 + n0 + q;
-                    if (tk < p.T && j < p.n_rows) {
-                        if (p.k_split) {
-                            p.part[((long long)z * p.T + tk) * p.n_rows + j] = __uint_as_float(v[q]);
-                        } else {
-                            float* yp = p.y + (long long)tk * p.ldy + j;
-                            float val = __uint_as_float(v[q]) + bj;
-                            if (p.accumulate) val += *yp;
-                            *yp = val;
-                        }
+                        for (int q = 0; q < 32; q++)
+                            if (tok0 + n0 + q < p.T) p.part[((long long)z * p.T + tok0 + n0 + q) * p.n_rows + j] = __uint_as_float(v[q]);
+                    } else if (p.accumulate) {
+                        // residual rows first (32 independent loads in flight: a load after a store to the same array would be
+                        // serialised by the compiler -- measured 3x on the O projection), then the sums
+                        float* yp = p.y + (long long)(tok0 + n0) * p.ldy + j;
+                        float old[32];
+#pragma unroll
+                        for (int q = 0; q < 32; q++) old[q] = (tok0 + n0 + q < p.T) ? __ldcg(yp + (long long)q * p.ldy) : 0.0f;
+#pragma unroll
+                        for (int q = 0; q < 32; q++)
+                            if (tok0 + n0 + q < p.T) yp[(long long)q * p.ldy] = (__uint_as_float(v[q]) + bj) + old[q];
+                    } else {
+                        float* yp = p.y + (long long)(tok0 + n0) * p.ldy + j;
+#pragma unroll
+                        for (int q = 0; q < 32; q++)
+                            if (tok0 + n0 + q < p.T) yp[(long long)q * p.ldy] = __uint_as_float(v[q]) + bj;
                     }
                 }
             }

@@ -118,4 +118,6 @@ def test_tensor_core_prefill_attention_with_peaked_softmax(b200, oracle, preset,
         os.environ.pop("B200_PREFILL_ATTN_TC", None)
     e_tc, e_simt, e_ab = rel_err(got, want), rel_err(simt, want), rel_err(got, simt)
     print(f"peaked softmax {preset} n={n}: tensor-core vs oracle {e_tc:.2e}, CUDA-core vs oracle {e_simt:.2e}, tensor-core vs CUDA-core {e_ab:.2e}")
-    assert e_tc < TOL and e_ab < TOL
+    # wider weights also widen the fp16 GEMMs' own error (it can pass 1e-3 here with either attention kernel): the claims are that the
+    # two attention kernels agree within the bound and that the tensor-core one is no further from the oracle than the CUDA-core one
+    assert e_ab < TOL and e_tc < max(TOL, 1.25 * e_simt)
