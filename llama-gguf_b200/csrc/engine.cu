@@ -193,6 +193,7 @@ struct b200_ctx {
     int pf_kv16_P = 0;
     CUtensorMap pf_kmap, pf_vmap;
     bool pf_attn_tc = true;          // B200_PREFILL_ATTN_TC=0: the CUDA-core prefill attention
+    int* pf_tile_cnt = nullptr;      // split-K tile counters of the persistent dequant-GEMM (zeroed once; the kernel re-zeroes them)
     void* pf_tmaps = nullptr;        // TMA tensor maps (128-row boxes) of the GEMM weights
     std::map<const void*, int> pf_tmap_of;
     bool pf_tmaps_built = false;
@@ -652,6 +653,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_logits);
     cudaFree(c->pf_split);
     cudaFree(c->pf_tmaps);
+    cudaFree(c->pf_tile_cnt);
     cudaFree(c->pf_k16);
     cudaFree(c->pf_vt16);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
@@ -1465,10 +1467,11 @@ static bool gemm2_enabled() { static int v = env_int("B200_GEMM2", 1); return v 
 static cudaError_t gemm_dispatch(UmmaParams& p, int n_sm, cudaStream_t st, uint64_t* launches = nullptr) {
     if (gemm2_enabled() && gemm_encode_fn() && umma2_eligible(p)) {
         static int ng = std::max(2, std::min(3, env_int("B200_GEMM2_GROUPS", 2)));
-        if (launches) *launches += p.k_split ? 2 : 1;
+        if (launches) *launches += (p.k_split && !p.tile_cnt) ? 2 : 1;
         return umma2_launch(gemm_encode_fn(), p, n_sm, 227 * 1024 - 2048, st, ng);
     }
     if (p.T > env_int("B200_GEMM_TMA_MAX_T", 64)) p.tmap = nullptr;   // first kernel: large tiles keep the direct reads (measured, round 1)
+    p.tile_cnt = nullptr;                                             // first kernel: separate reduce kernel
     if (launches) *launches += p.k_split ? 2 : 1;
     return umma_launch(p, st);
 }
@@ -1553,6 +1556,8 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     if (!c->pf_split) {   // split-K scratch for passes of <= 64 rows: 8 partial tiles of the widest projection
         c->pf_split_floats = (size_t)8 * 64 * std::max(std::max(I, QKV), H);
         CU_ALLOC(cudaMalloc((void**)&c->pf_split, c->pf_split_floats * sizeof(float)));
+        CU_ALLOC(cudaMalloc((void**)&c->pf_tile_cnt, 8192 * sizeof(int)));
+        CU(cudaMemset(c->pf_tile_cnt, 0, 8192 * sizeof(int)));
     }
     // batched decode: per-row (position, KV base of the slot, SeqState of the slot)
     const bool rows = seqs != nullptr;
@@ -1608,6 +1613,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         p.accumulate = acc; p.err = c->mma_err;
         umma_set_tmap(c, p);
         umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
+        if (p.k_split && (p.n_rows + kUmmaM - 1) / kUmmaM <= 8192 && env_int("B200_GEMM2_FUSED_REDUCE", 0)) p.tile_cnt = c->pf_tile_cnt;
         return gemm_dispatch(p, c->n_sm, st, &c->launches);
     };
     int last_T = 0;

@@ -192,6 +192,9 @@ struct UmmaParams {
     int k_split;         // 0 = no split
     float* part;
     int* err;            // watchdog word (set to 5 if the MMA completion never arrives)
+    // gemm_umma2.cuh only: one zeroed counter per (row tile, token tile).  With it the split-K partials are summed by the LAST
+    // CTA to finish a tile (in z order, so the result does not depend on which one that is) and umma_reduce_kernel is not launched
+    int* tile_cnt;
     // TMA-fed weights: tensor map of the matrix ([n_rows][row_bytes / 4] UINT32, box = 128 rows x raw_pitch bytes = one
     // 256-element block per row); nullptr = the threads read their rows straight from global memory
     const void* tmap;

@@ -40,7 +40,8 @@ struct Umma2Plan {
     int raw_stage;           // bytes per raw stage (128 rows x raw_pitch, rounded up to 128)
     int off_b, off_raw;      // byte offsets of the B and raw rings from the 1024-aligned base (A ring at 0)
     int x3d;                 // activations through the 3-D tensor map (1) or the 2-D fallback {K, T} (0: one load per 64-element slab)
-    int dbg;                 // lab only (tools/gemm_lab): 1 = no dequant math, 2 = no raw loads, 4 = no activation loads, 8 = no MMAs
+    int dbg;                 // lab only (tools/gemm_lab): 1 = no dequant math, 2 = no raw loads, 4 = no activation loads, 8 = no MMAs,
+                             // 64 = no tcgen05.fence in the MMA loop, 128 = plain mbarrier arrives instead of tcgen05.commit (timing only)
     long long* prof;         // lab only: per CTA and role {clocks in the role loop, clocks spent waiting}
 };
 
@@ -166,6 +167,7 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
     extern __shared__ __align__(1024) uint8_t u2_smem[];
     __shared__ Umma2Bars bars;
     __shared__ uint32_t s_tmem;
+    __shared__ int s_last;
     constexpr int kCols = 2 * (TN < 32 ? 32 : TN);   // two accumulators
     // activations: one ring stage per 64-element K step (wide token tiles) or per 256-element block = 4 slabs of TN x 128 bytes
     // (token tiles of <= 64 rows: one TMA issue, one barrier round trip and one commit per block instead of four)
@@ -278,7 +280,7 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
                     for (int s = 0; s < 4; s++) {
                         if (!kBBlock) u2_wait(bB_full + 8u * rb.i, rb.ph, alive, p.err, 14, waited);
                         u2_wait(bA_full + 8u * ra.i, ra.ph, alive, p.err, 15, waited);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (!(pl.dbg & 64)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da = da0 + (uint64_t)(ra.i * (uint32_t)(kUmmaM * 128 / 16));
                         const uint64_t db = db0 + (uint64_t)(rb.i * (uint32_t)(kBStage / 16) + (kBBlock ? (uint32_t)s * (uint32_t)(kBSlab / 16) : 0u));
                         if (!(pl.dbg & 8)) {
@@ -286,15 +288,15 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
                             for (int kk = 0; kk < kUmmaK / 16; kk++)
                                 umma_f16(acc, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (b > 0 || s > 0 || kk > 0) ? 1u : 0u);
                         }
-                        umma_commit(bA_empty + 8u * ra.i);
+                        if (pl.dbg & 128) u2_mbar_arrive(bA_empty + 8u * ra.i); else umma_commit(bA_empty + 8u * ra.i);
                         ra.next(SA);
                         if (!kBBlock) {
-                            umma_commit(bB_empty + 8u * rb.i);
+                            if (pl.dbg & 128) u2_mbar_arrive(bB_empty + 8u * rb.i); else umma_commit(bB_empty + 8u * rb.i);
                             rb.next(SB);
                         }
                     }
                     if (kBBlock) {
-                        umma_commit(bB_empty + 8u * rb.i);
+                        if (pl.dbg & 128) u2_mbar_arrive(bB_empty + 8u * rb.i); else umma_commit(bB_empty + 8u * rb.i);
                         rb.next(SB);
                     }
                 }
@@ -405,6 +407,48 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) u2_mbar_arrive(bAcc_empty + 8u * buf);
+            if (p.k_split && p.tile_cnt) {
+                // split-K without a second kernel: the last CTA to finish this (row tile, token tile) adds the n_z partial tiles in
+                // z order (threadFenceReduction pattern: partials -> fence -> counter; the epilogue warps meet on named barrier 1)
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 0) {
+                    int* cnt = p.tile_cnt + m * pl.n_nt + n;
+                    const int last = atomicAdd(cnt, 1) == pl.n_z - 1;
+                    if (last) *cnt = 0;        // ready for the next launch
+                    s_last = last;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_last) {
+                    __threadfence();
+                    const long long zs = (long long)p.T * p.n_rows;
+#pragma unroll 1
+                    for (int n0 = 0; n0 < TN && tok0 + n0 < p.T; n0 += 8) {
+                        float pv[8][8];        // [z][token]: up to 64 independent loads in flight (at most 8 splits: umma_plan_split)
+#pragma unroll
+                        for (int zz = 0; zz < 8; zz++)
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const int tk = tok0 + n0 + q;
+                                pv[zz][q] = (zz < pl.n_z && tk < p.T && j < p.n_rows) ? __ldcg(p.part + zz * zs + (long long)tk * p.n_rows + j) : 0.0f;
+                            }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const int tk = tok0 + n0 + q;
+                            if (tk < p.T && j < p.n_rows) {
+                                float a = 0.0f;
+#pragma unroll
+                                for (int zz = 0; zz < 8; zz++)
+                                    if (zz < pl.n_z) a += pv[zz][q];
+                                if (p.bias) a += bj;
+                                float* yp = p.y + (long long)tk * p.ldy + j;
+                                *yp = p.accumulate ? __ldcg(yp) + a : a;
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last is rewritten by the next item
+            }
         }
     }
     if (pl.prof && lane == 0 && (role < 2 || role == 5 ? true : ((warp - kU2FirstDeqWarp) & 3) == 0) && (role != 5 || warp == 0)) {
@@ -463,7 +507,7 @@ inline cudaError_t umma2_launch_tn(const CUtensorMap& xmap, const UmmaParams& p,
     const int n_items = pl.n_mt * pl.n_z * pl.n_nt;
     const int grid = std::min(n_items, n_sm);
     dequant_gemm_umma2_kernel<TN, NG><<<grid, (kU2FirstDeqWarp + 4 * NG) * 32, smem, st>>>(xmap, p, pl);
-    if (pl.n_z > 1) {
+    if (pl.n_z > 1 && !p.tile_cnt) {
         const long long n = (long long)p.T * p.n_rows;
         umma_reduce_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>(p, pl.n_z);
     }
@@ -517,6 +561,8 @@ inline cudaError_t umma2_launch(Umma2EncodeFn encode, const UmmaParams& p, int n
     if (ng == 3) {
         if (tn == 32) return umma2_launch_tn<32, 3>(xmap, p, pl, smem, n_sm, st);
         if (tn == 64) return umma2_launch_tn<64, 3>(xmap, p, pl, smem, n_sm, st);
+        if (tn == 128) return umma2_launch_tn<128, 3>(xmap, p, pl, smem, n_sm, st);
+        return umma2_launch_tn<256, 3>(xmap, p, pl, smem, n_sm, st);
     }
     if (tn == 32) return umma2_launch_tn<32, 2>(xmap, p, pl, smem, n_sm, st);
     if (tn == 64) return umma2_launch_tn<64, 2>(xmap, p, pl, smem, n_sm, st);

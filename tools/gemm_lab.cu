@@ -82,12 +82,14 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dmaps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
 
+    int* dcnt; CK(cudaMalloc(&dcnt, 8192 * 4)); CK(cudaMemset(dcnt, 0, 8192 * 4));
     auto params = [&](const uint8_t* wp, const CUtensorMap* tm, float* y, bool tma_old) {
         UmmaParams p{};
         p.w = wp; p.row_bytes = row_bytes; p.type = type; p.n_rows = n_rows; p.K = K; p.x = dx; p.ldx = K; p.T = T; p.y = y; p.ldy = n_rows;
         p.err = derr;
         if (tm && (tma_old ? T <= 64 : true)) { p.tmap = tm; p.raw_pitch = pitch; p.raw_bytes = 256 / be * bb; }
         umma_plan_split(p, scratch, scratch_floats, n_sm);
+        if (!tma_old && p.k_split && !(dbg & 32)) p.tile_cnt = dcnt;   // persistent kernel: in-kernel split-K reduce (dbg 32: separate kernel)
         return p;
     };
     // ---- correctness: first kernel vs persistent kernel on the same inputs
