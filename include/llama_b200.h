@@ -103,6 +103,14 @@ B200_API int b200_ctx_upload_tensor(b200_ctx* ctx, const char* gguf_name, uint32
 B200_API int b200_ctx_finalize(b200_ctx* ctx);
 B200_API void b200_ctx_destroy(b200_ctx* ctx);
 
+/* KV cache storage format (KVCacheFormat, src/model/kv_quantized.rs:11-20), chosen between b200_ctx_create and
+ * b200_ctx_finalize (or with B200_KV_FORMAT=int8 in the environment): 0 = F32 (the KVCache of src/model/mod.rs:83-108, default),
+ * 1 = Int8 -- QuantizedKVCache::write_kv / read_k_range semantics (kv_quantized.rs:143-216, 230-270, 366-392): one symmetric
+ * scale = max|x| / 127 per (kv head, position) row, q = round(x / scale), attention over q * scale.  A quarter of the KV bytes; the
+ * context then decodes on the per-op (graph) path and prefills token by token.  The FP8 formats are not built (UNSUPPORTED). */
+B200_API int b200_ctx_set_kv_format(b200_ctx* ctx, int format);
+B200_API int b200_ctx_kv_format(b200_ctx* ctx, int* out);
+
 /* Tensor parallel (replaces the gRPC all-reduce-via-rank-0 of
  * src/distributed/tensor_parallel_distributed.rs:135-187): one context per rank/GPU, created with
  * world_size/rank in b200_parallel_desc.  Between b200_ctx_create and b200_ctx_finalize every rank calls

@@ -95,6 +95,8 @@ def lib():
     L.b200_ctx_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(ParallelDesc), C.POINTER(vp)]
     L.b200_ctx_upload_tensor.argtypes = [vp, C.c_char_p, C.c_uint32, u64p, C.c_int, vp, C.c_size_t]
     L.b200_ctx_finalize.argtypes = [vp]
+    L.b200_ctx_set_kv_format.argtypes = [vp, C.c_int]
+    L.b200_ctx_kv_format.argtypes = [vp, C.POINTER(C.c_int)]
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_ctx_destroy.restype = None
     L.b200_forward.argtypes = [vp, C.c_int, C.c_uint32, fp]
@@ -399,13 +401,16 @@ class GpuOnlyInference:
     (ggml_type, ne, ndarray) with ne[0] = in_features.
     """
 
-    def __init__(self, desc: dict, tensors: dict, device=0, taps=False, feeder=None, parallel=None, exchange=None):
+    def __init__(self, desc: dict, tensors: dict, device=0, taps=False, feeder=None, parallel=None, exchange=None, kv_format="f32"):
         """`feeder(upload)` may stream tensors one by one (upload(name, type, ne, data)) instead of `tensors`.
 
         Tensor parallel: `parallel=(world_size, rank)` makes this the context of one rank (one process per GPU);
         `exchange(handle_bytes) -> [handle_bytes of every rank]` is the all-gather the host provides
         (parallel.all_gather_bytes over torch.distributed).  Every rank uploads the FULL tensors; the library keeps
-        its shard.  forward() then returns this rank's slice of the logits (see parallel.TensorParallelInference)."""
+        its shard.  forward() then returns this rank's slice of the logits (see parallel.TensorParallelInference).
+
+        `kv_format`: "f32" (KVCache, src/model/mod.rs:83-108) or "int8" (QuantizedKVCache's Int8 format,
+        src/model/kv_quantized.rs:143-216: one scale per (kv head, position) row, a quarter of the bytes)."""
         L = lib()
         if device_count() == 0:
             raise NotAvailable("cuda-b200: no CUDA device (this backend has no CPU fallback)")
@@ -432,6 +437,10 @@ class GpuOnlyInference:
                     os.environ["B200_TAPS"] = old
         self._h = h
         try:
+            if kv_format not in ("f32", "int8"):
+                raise Unsupported(f"kv_format {kv_format!r}: f32 or int8")
+            if kv_format == "int8":
+                _check(L.b200_ctx_set_kv_format(h, 1))
             if world > 1:
                 if exchange is None:
                     raise InvalidArgument("tensor parallel contexts need an `exchange` (all-gather of IPC handles)")
@@ -476,6 +485,11 @@ class GpuOnlyInference:
             self.close()
         except Exception:
             pass
+
+    def kv_format(self):
+        v = C.c_int(0)
+        _check(lib().b200_ctx_kv_format(self._h, C.byref(v)))
+        return ("f32", "int8")[v.value]
 
     def path(self):
         """Decode path chosen at finalize: "graph" | "mega" | "stream" | "stream2"."""

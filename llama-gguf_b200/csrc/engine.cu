@@ -33,6 +33,7 @@
 #include "gemm_umma.cuh"
 #include "gemm_umma2.cuh"
 #include "attn_umma.cuh"
+#include "kv_int8.cuh"
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -103,6 +104,8 @@ struct Slot {
     SeqState* d_state = nullptr;
     int* d_generated = nullptr;
     float* kv = nullptr;  // [L][2][n_kv][max_seq][hd]
+    signed char* kv8 = nullptr;   // int8 KV format (kv_int8.cuh): [L][2][n_kv][max_seq][hd] bytes ...
+    float* kv_scale = nullptr;    // ... and [L][2][n_kv][max_seq] scales; kv stays null
     uint64_t host_pos = 0;
     cudaGraphExec_t graph[MODE_COUNT] = {nullptr, nullptr, nullptr};
     uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
@@ -144,6 +147,9 @@ struct b200_ctx {
     size_t smem_optin = 227 * 1024;
     uint64_t mma_launches = 0, v1_launches = 0;
     // per-token megakernel (mega.cuh)
+    int kv_format = 0;            // 0 = f32 (model/mod.rs:83-108), 1 = int8 (model/kv_quantized.rs Int8): B200_KV_FORMAT / b200_ctx_set_kv_format
+    float* attn_q8_part = nullptr;
+    int attn_q8_splits = 0;
     bool use_mega = true, mega_ok = false;
     int mega_phases = 0;
     size_t mega_smem = 0;
@@ -298,6 +304,10 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->use_stream2 = env_int("B200_STREAM2", 1) != 0;
     c->use_prefill_gemm = env_int("B200_PREFILL_GEMM", 1) != 0;
     c->pf_attn_tc = env_int("B200_PREFILL_ATTN_TC", 1) != 0;
+    {
+        const char* kf = getenv("B200_KV_FORMAT");
+        if (kf && (!strcmp(kf, "int8") || !strcmp(kf, "1"))) c->kv_format = 1;
+    }
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
     c->prefill_queue = env_int("B200_PREFILL_QUEUE", 0) != 0;
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
@@ -545,8 +555,25 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
         CU_ALLOC(cudaMalloc((void**)&s.d_state, sizeof(SeqState)));
         CU(cudaMemset(s.d_state, 0, sizeof(SeqState)));
         CU_ALLOC(cudaMalloc((void**)&s.d_generated, kMaxGenerated * sizeof(int)));
-        CU_ALLOC(cudaMalloc((void**)&s.kv, kv_elems * 4));
-        CU(cudaMemset(s.kv, 0, kv_elems * 4));
+        if (c->kv_format == 1) {   // int8 KV: bytes + one f32 scale per (kv head, position) row, no f32 cache at all
+            CU_ALLOC(cudaMalloc((void**)&s.kv8, kv_elems));
+            CU(cudaMemset(s.kv8, 0, kv_elems));
+            CU_ALLOC(cudaMalloc((void**)&s.kv_scale, kv_elems / hd * 4));
+            CU(cudaMemset(s.kv_scale, 0, kv_elems / hd * 4));
+        } else {
+            CU_ALLOC(cudaMalloc((void**)&s.kv, kv_elems * 4));
+            CU(cudaMemset(s.kv, 0, kv_elems * 4));
+        }
+    }
+    if (c->kv_format == 1) {
+        if (c->par.world_size > 1) return fail(B200_ERR_UNSUPPORTED, "the int8 KV format is not available under tensor / expert parallelism");
+        if (hd != 64 && hd != 128) return fail(B200_ERR_UNSUPPORTED, "the int8 KV format needs head_dim 64 or 128");
+        if (nh % nkv || nh / nkv > 8) return fail(B200_ERR_UNSUPPORTED, "the int8 KV format needs at most 8 query heads per kv head");
+        // per-op (graph) decode path only: the megakernels and the tensor-core prefill read the f32 cache
+        c->use_mega = false;
+        c->use_prefill_gemm = false;
+        c->attn_q8_splits = std::max(1, std::min(128, (4 * c->n_sm + (int)nkv - 1) / (int)nkv));
+        CU_ALLOC(cudaMalloc((void**)&c->attn_q8_part, (size_t)nkv * c->attn_q8_splits * (nh / nkv) * (hd + 2) * sizeof(float)));
     }
     // kernels that may need more than 48 KB of dynamic shared memory
     CU(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -636,6 +663,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         cudaFree(s.d_state);
         cudaFree(s.d_generated);
         cudaFree(s.kv);
+        cudaFree(s.kv8);
+        cudaFree(s.kv_scale);
         cudaFree(s.d_phases);
         cudaFree(s.d_phases2);
     }
@@ -654,6 +683,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_split);
     cudaFree(c->pf_tmaps);
     cudaFree(c->pf_tile_cnt);
+    cudaFree(c->attn_q8_part);
     cudaFree(c->pf_k16);
     cudaFree(c->pf_vt16);
     for (uint8_t* p : c->mega_stage) cudaFree(p);
@@ -738,8 +768,10 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
     Slot& sl = c->slots[slot_i];
     const int H = d.hidden, hd = d.head_dim, nh = d.n_heads, nkv = d.n_kv_heads, G = nh / nkv;
     cudaError_t e;
-#define CK(x)                      \
-    if ((e = (x)) != cudaSuccess) return e
+#define CK(x)                                   \
+    do {                                        \
+        if ((e = (x)) != cudaSuccess) return e; \
+    } while (0)
     const int* pos_ptr = &sl.d_state->pos_cur;
     if (!only_gemv)
         CK(launch_k(c, embed_kernel, dim3(std::max(1, std::min(8, H / 256))), dim3(256), 0, c->token_embd.type,
@@ -761,7 +793,28 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
             p.n_seg = 3; p.K = H; p.x = c->xa; p.norm_w = L.attn_norm.f32(); p.eps = d.norm_eps; p.epi = EPI_STORE;
             CK(launch_gemv(c, p));
         }
-        if (!only_gemv) {   // RoPE + KV write
+        if (!only_gemv && c->kv_format == 1) {   // int8 KV cache: RoPE + quantised write, then attention over the dequantised rows
+            const size_t rows_layer = (size_t)2 * nkv * d.max_seq_len;
+            signed char* k8 = sl.kv8 + (size_t)l * rows_layer * hd;
+            signed char* v8 = k8 + rows_layer * hd / 2;
+            float* ks = sl.kv_scale + (size_t)l * rows_layer;
+            float* vs = ks + rows_layer / 2;
+            RopeKvQ8Params rp{};
+            rp.q = q; rp.k = k; rp.v = v; rp.k8 = k8; rp.v8 = v8; rp.k_scale = ks; rp.v_scale = vs; rp.freq = c->rope_freq; rp.pos = pos_ptr;
+            rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox; rp.rope_scale = d.rope_scale;
+            const int units = nh + 2 * nkv;
+            // (CK is a bare `if`: pick the kernel first, one CK per launch -- an `else CK` would bind to the macro's own `if`)
+            CK(launch_k(c, hd == 128 ? rope_kv_q8_kernel<4> : rope_kv_q8_kernel<2>, dim3((units + 3) / 4), dim3(128), 0, rp));
+            AttnQ8Params ap{};
+            ap.q = q; ap.k8 = k8; ap.v8 = v8; ap.k_scale = ks; ap.v_scale = vs; ap.part = c->attn_q8_part; ap.out = c->attn; ap.pos = pos_ptr;
+            ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len; ap.n_splits = c->attn_q8_splits; ap.scale = 1.0f / sqrtf((float)hd);
+            const dim3 grid(ap.n_splits, nkv);
+            void (*split_k)(AttnQ8Params) = hd == 128 ? (G <= 4 ? attn_q8_split_kernel<4, 4> : attn_q8_split_kernel<4, 8>)
+                                                      : (G <= 4 ? attn_q8_split_kernel<2, 4> : attn_q8_split_kernel<2, 8>);
+            CK(launch_k(c, split_k, grid, dim3(32), 0, ap));
+            CK(launch_k(c, attn_q8_merge_kernel, dim3(nh), dim3(hd), 0, ap, hd));
+        }
+        if (!only_gemv && c->kv_format == 0) {   // RoPE + KV write
             RopeKvParams rp{};
             rp.q = q; rp.k = k; rp.v = v; rp.k_cache = kc; rp.v_cache = vc; rp.freq = c->rope_freq; rp.pos = pos_ptr;
             rp.n_heads = nh; rp.n_kv = nkv; rp.hd = hd; rp.max_seq = d.max_seq_len; rp.neox = d.rope_neox;
@@ -769,7 +822,7 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
             int work = (nh + nkv) * hd / 2 + nkv * hd;
             CK(launch_k(c, rope_kv_kernel, dim3((work + 255) / 256), dim3(256), 0, rp));
         }
-        if (!only_gemv) {   // GQA decode attention over [0, pos]
+        if (!only_gemv && c->kv_format == 0) {   // GQA decode attention over [0, pos]
             AttnParams ap{};
             ap.q = q; ap.k_cache = kc; ap.v_cache = vc; ap.out = c->attn; ap.part = c->attn_part; ap.tickets = c->tickets;
             ap.pos = pos_ptr; ap.kv_len_fixed = 0; ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len;
@@ -1799,6 +1852,19 @@ static int flush_pending(b200_ctx* c, int seq) {
     return rc;
 }
 
+extern "C" int b200_ctx_set_kv_format(b200_ctx* c, int format) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_set_kv_format: null ctx");
+    if (c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_set_kv_format: the context is finalized already");
+    if (format != 0 && format != 1) return fail(B200_ERR_UNSUPPORTED, "b200_ctx_set_kv_format: 0 = f32, 1 = int8 (FP8 formats of kv_quantized.rs are not built)");
+    c->kv_format = format;
+    return B200_OK;
+}
+extern "C" int b200_ctx_kv_format(b200_ctx* c, int* out) {
+    if (!c || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_kv_format: bad argument");
+    *out = c->kv_format;
+    return B200_OK;
+}
+
 extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_out) {
     int rc;
     if ((rc = check_slot(c, seq, "b200_forward"))) return rc;
@@ -2214,7 +2280,8 @@ extern "C" int b200_ctx_stats(b200_ctx* c, uint64_t* kernel_launches, uint64_t* 
     if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_stats: null ctx");
     if (kernel_launches) *kernel_launches = c->launches;
     if (weight_bytes) *weight_bytes = c->weight_bytes_per_token;
-    if (kv_bytes_per_pos) *kv_bytes_per_pos = (uint64_t)2 * c->d.n_layers * c->d.n_kv_heads * c->d.head_dim * 4;
+    if (kv_bytes_per_pos)   // f32 rows, or int8 rows + one f32 scale each
+        *kv_bytes_per_pos = (uint64_t)2 * c->d.n_layers * c->d.n_kv_heads * (c->kv_format == 1 ? c->d.head_dim + 4 : c->d.head_dim * 4);
     return B200_OK;
 }
 

@@ -78,6 +78,10 @@ def lib():
         L.orc_model_reset.argtypes = [C.c_void_p]
         L.orc_model_position.argtypes = [C.c_void_p]
         L.orc_model_set_faithful_embedding.argtypes = [C.c_void_p, C.c_int]
+        L.orc_model_set_kv_format.argtypes = [C.c_void_p, C.c_int]
+        L.orc_kv_quantize_int8.restype = C.c_float
+        L.orc_kv_quantize_int8.argtypes = [fp, C.c_int, C.c_void_p]
+        L.orc_kv_dequantize_int8.argtypes = [C.c_void_p, C.c_int, C.c_float, fp]
         L.orc_model_get_hidden.argtypes = [C.c_void_p, C.c_int, fp]
         L.orc_model_get_kv.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.orc_model_forward.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_int, fp]
@@ -121,6 +125,22 @@ def quantize(t, x):
     rc = lib().orc_quantize(t, _fp(x), x.size, out.ctypes.data)
     if rc:
         raise ValueError("orc_quantize failed")
+    return out
+
+
+def kv_quantize_int8(x):
+    """quantize_int8 (src/model/kv_quantized.rs:366-387): (int8 ndarray, scale)."""
+    x = _f32(x).ravel()
+    q = np.empty(x.size, dtype=np.int8)
+    s = lib().orc_kv_quantize_int8(_fp(x), x.size, q.ctypes.data)
+    return q, float(s)
+
+
+def kv_dequantize_int8(q, scale):
+    """dequantize_int8 (src/model/kv_quantized.rs:390-392)."""
+    q = np.ascontiguousarray(q, dtype=np.int8)
+    out = np.empty(q.size, dtype=np.float32)
+    lib().orc_kv_dequantize_int8(q.ctypes.data, q.size, scale, _fp(out))
     return out
 
 
@@ -241,12 +261,14 @@ class OracleModel:
     `tensors` is {gguf_name: (ggml_type, ne tuple, uint8/float32 ndarray)}.
     """
 
-    def __init__(self, desc: dict, tensors: dict):
+    def __init__(self, desc: dict, tensors: dict, kv_format="f32"):
         d = OrcDesc()
         for k, v in desc.items():
             setattr(d, k, v)
         self.desc = dict(desc)
         self._h = lib().orc_model_create(C.byref(d))
+        if kv_format == "int8":   # QuantizedKVCache Int8 (src/model/kv_quantized.rs)
+            lib().orc_model_set_kv_format(self._h, 1)
         for name, (t, ne, data) in tensors.items():
             a = np.ascontiguousarray(data)
             nd = (C.c_int64 * 4)(*(list(ne) + [1] * (4 - len(ne))))

@@ -882,6 +882,7 @@ struct OrcModel {
     int position = 0;
     std::vector<float> hiddens;  // [(n_layers+1) * hidden] of the last processed token
     int faithful_embedding = 0;  // 1: dequantise the whole table per call (llama.rs:288)
+    int kv_format = 0;           // 1: rows pass through QuantizedKVCache's Int8 format on their way into the cache (kv_quantized.rs)
     const OrcTensor* get(const std::string& n) const {
         auto it = t.find(n);
         return it == t.end() ? nullptr : &it->second;
@@ -920,6 +921,28 @@ ORC_API void orc_model_reset(OrcModel* m) {
 }
 ORC_API int orc_model_position(const OrcModel* m) { return m->position; }
 ORC_API void orc_model_set_faithful_embedding(OrcModel* m, int on) { m->faithful_embedding = on; }
+
+// quantize_int8 (src/model/kv_quantized.rs:366-387): scale = max|x| / 127 (1.0 for an all-zero row), q = clamp(round(x / scale));
+// f32::round is half away from zero = roundf
+ORC_API float orc_kv_quantize_int8(const float* x, int n, int8_t* q) {
+    float max_abs = 0.0f;
+    for (int i = 0; i < n; i++) max_abs = std::max(max_abs, std::fabs(x[i]));
+    const float scale = max_abs > 1e-10f ? max_abs / 127.0f : 1.0f;
+    for (int i = 0; i < n; i++) {
+        float v = roundf(x[i] / scale);
+        v = std::min(std::max(v, -128.0f), 127.0f);
+        q[i] = (int8_t)v;
+    }
+    return scale;
+}
+// dequantize_int8 (kv_quantized.rs:390-392)
+ORC_API void orc_kv_dequantize_int8(const int8_t* q, int n, float scale, float* out) {
+    for (int i = 0; i < n; i++) out[i] = (float)q[i] * scale;
+}
+// 0 = F32 KVCache (model/mod.rs:83-108); 1 = QuantizedKVCache Int8: write_kv stores quantize_int8(row) per (head, position)
+// (kv_quantized.rs:143-216) and read_k_range / read_v_range return dequantize_int8 of it (:230-310) -- the attention then sees
+// q * scale, which is what the f32 cache of this model holds in that mode
+ORC_API void orc_model_set_kv_format(OrcModel* m, int format) { m->kv_format = format; }
 ORC_API void orc_model_get_hidden(const OrcModel* m, int layer, float* out) {
     memcpy(out, m->hiddens.data() + (size_t)layer * m->d.hidden, (size_t)m->d.hidden * 4);
 }
@@ -959,8 +982,18 @@ static int layer_forward(OrcModel* m, int l, float* hidden, int pos) {
     float* kc = m->kc[l].data();
     float* vc = m->vc[l].data();
     for (int hh = 0; hh < nkv; hh++) {  // layers.rs:580-600
-        memcpy(kc + ((int64_t)hh * d.max_seq_len + pos) * hd, k.data() + (int64_t)hh * hd, (size_t)hd * 4);
-        memcpy(vc + ((int64_t)hh * d.max_seq_len + pos) * hd, v.data() + (int64_t)hh * hd, (size_t)hd * 4);
+        float* kdst = kc + ((int64_t)hh * d.max_seq_len + pos) * hd;
+        float* vdst = vc + ((int64_t)hh * d.max_seq_len + pos) * hd;
+        if (m->kv_format == 1) {   // QuantizedKVCache::write_kv then read_*_range (kv_quantized.rs:143-216, 230-310)
+            std::vector<int8_t> q8((size_t)hd);
+            float s = orc_kv_quantize_int8(k.data() + (int64_t)hh * hd, hd, q8.data());
+            orc_kv_dequantize_int8(q8.data(), hd, s, kdst);
+            s = orc_kv_quantize_int8(v.data() + (int64_t)hh * hd, hd, q8.data());
+            orc_kv_dequantize_int8(q8.data(), hd, s, vdst);
+            continue;
+        }
+        memcpy(kdst, k.data() + (int64_t)hh * hd, (size_t)hd * 4);
+        memcpy(vdst, v.data() + (int64_t)hh * hd, (size_t)hd * 4);
     }
     float scale = 1.0f / sqrtf((float)hd);  // layers.rs:374
     orc_attention_cached(q.data(), kc, vc, attn.data(), nh, nkv, hd, d.max_seq_len, scale, pos + 1);
