@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefill-len", type=int, default=2048, help="tokens of the GEMM-prefill measurement (0 = skip)")
     ap.add_argument("--seed", type=int, default=1236)
+    ap.add_argument("--kv-format", default=os.environ.get("B200_KV_FORMAT", "f32"), choices=["f32", "int8"],
+                    help="KV cache storage (SURVEY 8f row 4): int8 = QuantizedKVCache Int8 rows + one scale per row (per-op decode path)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -200,7 +202,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"{args.model} arch, {args.mix} random-init GGUF blocks, batch-1 greedy decode after a "
-                f"{args.prompt_len}-token prompt, {args.ctx}-token context window (f32 KV)")
+                f"{args.prompt_len}-token prompt, {args.ctx}-token context window ({args.kv_format} KV)")
     config = {"workload": workload, "model_arch": args.model, "quant_mix": args.mix, "batch": 1, "context_window": args.ctx,
               "prompt_len": args.prompt_len, "parallelism": (f"ep{args.gpus}" if preset.get("n_experts", 0) else f"tp{args.gpus}") if args.gpus > 1 else "single-gpu",
               "l2_policy": "inputs larger than L2: each step streams the whole weight set (>= 4.6 GB) through the 126 MB L2"}
@@ -239,7 +241,8 @@ def main():
     desc = make_desc(preset, args.ctx, max(1, args.batch))   # one KV cache per sequence slot (batch extra below)
     repeat = (16 << 20) if args.model in ("llama-3-70b", "mixtral-8x7b") else None   # (host generation time of the 40 GB presets)
     # tensors are streamed straight into the context (host memory stays at one tensor)
-    gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up, repeat_bytes=repeat))
+    gpu = B.GpuOnlyInference(desc, None, feeder=lambda up: random_model(preset, args.mix, args.ctx, seed=args.seed, upload=up, repeat_bytes=repeat),
+                             kv_format=args.kv_format)
     log(f"model built and uploaded in {time.time() - t0:.1f} s")
     st0 = gpu.stats()
     wbytes, kvpp = st0["weight_bytes_per_token"], st0["kv_bytes_per_pos"]

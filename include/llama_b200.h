@@ -111,6 +111,40 @@ B200_API void b200_ctx_destroy(b200_ctx* ctx);
 B200_API int b200_ctx_set_kv_format(b200_ctx* ctx, int format);
 B200_API int b200_ctx_kv_format(b200_ctx* ctx, int* out);
 
+/* GGUF -> HBM direct load.  Replaces GgufFile::open (src/gguf/mod.rs:23-40, mmap), GgufReader::read
+ * (src/gguf/reader.rs:28-110: header, metadata, tensor infos, aligned data offset; versions 1-3), ModelLoader::parse_config
+ * (src/model/loader.rs:62-300: the {arch}.* keys with the same defaults and the same strict typed getters, gguf/types.rs:78-97)
+ * and the per-tensor Vec copy + upload of loader.rs:1341-1365 / cuda/gpu_only.rs:426-520: the file is mapped once, parsed in
+ * place, and every tensor the engine uses goes from the page cache to its HBM allocation through two pinned staging buffers
+ * (host threads fill one while the copy engine drains the other).  No tensor-sized host allocation, no f32 embedding table.
+ * b200_gguf_* need no CUDA device.  Errors: bad magic / truncated file / missing key -> INVALID_ARGUMENT, version other than
+ * 1-3 / architecture or feature outside the engine -> UNSUPPORTED, a used tensor of an unimplemented ggml type -> UNSUPPORTED_DTYPE. */
+typedef struct b200_gguf b200_gguf;
+typedef struct b200_load_stats {
+    uint64_t file_bytes;      /* size of the mapping */
+    uint64_t tensor_bytes;    /* bytes of the tensors handed to the engine (full tensors) */
+    uint64_t device_bytes;    /* bytes this context copied to HBM (its shard under tensor / expert parallelism) */
+    uint32_t tensors_loaded;
+    uint32_t tensors_skipped; /* tensors of the file the engine has no use for (rope_freqs.weight ...) */
+    double seconds;           /* wall time of the load loop including the final synchronisation of the load stream */
+} b200_load_stats;
+B200_API int b200_gguf_open(const char* path, b200_gguf** out);
+B200_API void b200_gguf_close(b200_gguf* file);
+B200_API int b200_gguf_info(b200_gguf* file, uint32_t* version, uint64_t* n_tensors, uint64_t* n_metadata, uint64_t* alignment,
+                            uint64_t* data_offset, uint64_t* file_bytes);
+B200_API int b200_gguf_architecture(b200_gguf* file, char* out, size_t cap);          /* general.architecture */
+/* max_seq_len > 0: min(it, {arch}.context_length); 0: the file's context length (default 2048, loader.rs:131). */
+B200_API int b200_gguf_model_desc(b200_gguf* file, int max_seq_len, int max_batch, b200_model_desc* out);
+/* Tensor i: name (owned by `file`), ggml type, ne[4] (ne[0] contiguous), rank, pointer into the mapping, byte size.  *data is NULL
+ * and *nbytes 0 for a ggml type the engine does not implement; every out pointer may be NULL. */
+B200_API int b200_gguf_tensor_info(b200_gguf* file, uint64_t i, const char** name, uint32_t* ggml_type, uint64_t* ne4, int* n_dims,
+                                   const void** data, size_t* nbytes);
+/* Between b200_ctx_create and b200_ctx_finalize: upload every tensor of the file the engine has a slot for (this rank's shard). */
+B200_API int b200_ctx_load_gguf(b200_ctx* ctx, b200_gguf* file, b200_load_stats* stats /* may be NULL */);
+/* GpuOnlyInference::from_model for a path: open + describe + create + load + finalize.  kv_format as b200_ctx_set_kv_format. */
+B200_API int b200_ctx_create_from_gguf(const char* path, const b200_parallel_desc* par /* NULL = 1 GPU, device 0 */, int max_seq_len,
+                                       int max_batch, int kv_format, b200_ctx** out, b200_load_stats* stats /* may be NULL */);
+
 /* Tensor parallel (replaces the gRPC all-reduce-via-rank-0 of
  * src/distributed/tensor_parallel_distributed.rs:135-187): one context per rank/GPU, created with
  * world_size/rank in b200_parallel_desc.  Between b200_ctx_create and b200_ctx_finalize every rank calls
@@ -132,6 +166,8 @@ typedef struct b200_group b200_group;
 B200_API int b200_group_create(const b200_model_desc* desc, int n_devices, const int* devices, b200_group** out);
 B200_API int b200_group_upload_tensor(b200_group* g, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne, int n_dims,
                              const void* host, size_t nbytes);   /* the FULL tensor; every rank keeps its shard */
+/* Every rank stages its own shard out of the shared mapping, in parallel (one host thread per device). */
+B200_API int b200_group_load_gguf(b200_group* g, b200_gguf* file, b200_load_stats* stats /* rank 0's; may be NULL */);
 B200_API int b200_group_finalize(b200_group* g);
 B200_API void b200_group_destroy(b200_group* g);
 B200_API int b200_group_forward(b200_group* g, int seq, uint32_t token, float* logits_out);
@@ -153,6 +189,45 @@ B200_API int b200_prefill(b200_ctx* ctx, int seq, const uint32_t* tokens, int n,
 /* One token for each of n DISTINCT sequence slots;
  * logits_out is n x vocab. */
 B200_API int b200_decode_batch(b200_ctx* ctx, const int* seqs, const uint32_t* tokens, int n, float* logits_out);
+/* b200_decode_batch with the greedy pick (last maximum wins, src/main.rs:1816-1821) made on the device: next_out receives n token
+ * ids instead of n x vocab logits. */
+B200_API int b200_decode_batch_greedy(b200_ctx* ctx, const int* seqs, const uint32_t* tokens, int n, uint32_t* next_out);
+
+/* Continuous batching: the peer of BatchedEngine (src/engine_batched.rs) below the tokenizer and the channels.
+ * Requests become sequences that each own one KV slot of the context; b200_batch_step is one iteration of the reference's
+ * background loop (engine_batched.rs:199-320) with step_sequence's rules (:366-411) -- the whole prompt on a sequence's first
+ * step, one token per step after that, finished when the last token is EOS or max_tokens were generated, EOS itself is not
+ * reported as a token, pending requests are promoted newest-first (Vec::pop, :291-304) -- except that all decoding sequences of
+ * a step share ONE pass over the weights (b200_decode_batch_greedy) instead of one Model::forward each.  Greedy sampling.
+ * The config's defaults are BatchedEngineConfig::default (:32-40); max_batch_size <= the context's max_batch. */
+typedef struct b200_batch b200_batch;
+typedef struct b200_batch_config {
+    int32_t max_batch_size;   /* concurrent sequences (8) */
+    int32_t max_seq_len;      /* prompts are cut to max_seq_len - 1 tokens (4096; never above the context's) */
+    int32_t max_queue_depth;  /* active + pending requests beyond which submit fails with "queue full" (64) */
+    uint32_t eos_token_id;
+} b200_batch_config;
+enum { B200_BATCH_TOKEN = 0, B200_BATCH_DONE = 1, B200_BATCH_ERROR = 2 };              /* BatchToken (:60-72) */
+enum { B200_FINISH_STOP = 0, B200_FINISH_MAX_TOKENS = 1, B200_FINISH_ERROR = 2 };      /* BatchFinishReason (:75-79) */
+typedef struct b200_batch_event {
+    uint64_t request_id;
+    int32_t kind;               /* B200_BATCH_* */
+    uint32_t token;             /* TOKEN: the generated id */
+    int32_t reason;             /* DONE: B200_FINISH_* */
+    int32_t prompt_tokens;      /* DONE: as BatchToken::Done */
+    int32_t completion_tokens;
+} b200_batch_event;
+B200_API int b200_batch_create(b200_ctx* ctx, const b200_batch_config* cfg /* NULL = defaults */, b200_batch** out);
+B200_API void b200_batch_destroy(b200_batch* batch);
+/* BatchedEngine::submit (:167-192): OPERATION_FAILED "queue full" past max_queue_depth; an empty prompt is accepted and answered
+ * with an ERROR event ("empty prompt", :329-334). */
+B200_API int b200_batch_submit(b200_batch* batch, const uint32_t* tokens, int n, int max_tokens, uint64_t* request_id);
+/* One loop iteration; up to `cap` events (oldest first) are copied out, the rest wait for the next call. */
+B200_API int b200_batch_step(b200_batch* batch, b200_batch_event* events, int cap, int* n_events);
+B200_API int b200_batch_counts(b200_batch* batch, int* active, int* pending, int* undelivered_events, uint64_t* steps,
+                               uint64_t* decode_rows);
+B200_API const char* b200_batch_last_error(b200_batch* batch);   /* message of the most recent ERROR event */
+
 /* GpuInference::reset / position (backend/mod.rs:292-295). */
 B200_API int b200_reset(b200_ctx* ctx, int seq);
 B200_API int b200_position(b200_ctx* ctx, int seq, uint64_t* out);

@@ -67,6 +67,28 @@ class ParallelDesc(C.Structure):
     _fields_ = [("world_size", C.c_int32), ("rank", C.c_int32), ("device", C.c_int32)]
 
 
+class LoadStats(C.Structure):
+    """b200_load_stats (include/llama_b200.h)."""
+    _fields_ = [("file_bytes", C.c_uint64), ("tensor_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
+                ("tensors_loaded", C.c_uint32), ("tensors_skipped", C.c_uint32), ("seconds", C.c_double)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["GBps"] = d["device_bytes"] / d["seconds"] / 1e9 if d["seconds"] > 0 else 0.0
+        return d
+
+
+class BatchConfig(C.Structure):
+    """b200_batch_config = BatchedEngineConfig (src/engine_batched.rs:23-40)."""
+    _fields_ = [("max_batch_size", C.c_int32), ("max_seq_len", C.c_int32), ("max_queue_depth", C.c_int32), ("eos_token_id", C.c_uint32)]
+
+
+class BatchEvent(C.Structure):
+    """b200_batch_event = BatchToken (src/engine_batched.rs:60-72)."""
+    _fields_ = [("request_id", C.c_uint64), ("kind", C.c_int32), ("token", C.c_uint32), ("reason", C.c_int32),
+                ("prompt_tokens", C.c_int32), ("completion_tokens", C.c_int32)]
+
+
 def build(verbose=False):
     """Compile csrc/ into libllama_b200.so with nvcc for sm_100a (cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"])
@@ -99,6 +121,26 @@ def lib():
     L.b200_ctx_kv_format.argtypes = [vp, C.POINTER(C.c_int)]
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_ctx_destroy.restype = None
+    u32p, i32p, szp = C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_size_t)
+    L.b200_decode_batch_greedy.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
+    L.b200_batch_create.argtypes = [vp, C.POINTER(BatchConfig), C.POINTER(vp)]
+    L.b200_batch_destroy.argtypes = [vp]
+    L.b200_batch_destroy.restype = None
+    L.b200_batch_submit.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int, C.c_int, u64p]
+    L.b200_batch_step.argtypes = [vp, C.POINTER(BatchEvent), C.c_int, i32p]
+    L.b200_batch_counts.argtypes = [vp, i32p, i32p, i32p, u64p, u64p]
+    L.b200_batch_last_error.argtypes = [vp]
+    L.b200_batch_last_error.restype = C.c_char_p
+    L.b200_gguf_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_gguf_close.argtypes = [vp]
+    L.b200_gguf_close.restype = None
+    L.b200_gguf_info.argtypes = [vp, u32p, u64p, u64p, u64p, u64p, u64p]
+    L.b200_gguf_architecture.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.b200_gguf_model_desc.argtypes = [vp, C.c_int, C.c_int, C.POINTER(ModelDesc)]
+    L.b200_gguf_tensor_info.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p), u32p, u64p, i32p, C.POINTER(vp), szp]
+    L.b200_ctx_load_gguf.argtypes = [vp, vp, C.POINTER(LoadStats)]
+    L.b200_ctx_create_from_gguf.argtypes = [C.c_char_p, C.POINTER(ParallelDesc), C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(LoadStats)]
+    L.b200_group_load_gguf.argtypes = [vp, vp, C.POINTER(LoadStats)]
     L.b200_forward.argtypes = [vp, C.c_int, C.c_uint32, fp]
     L.b200_prefill_token.argtypes = [vp, C.c_int, C.c_uint32]
     L.b200_prefill.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.c_int, fp]
@@ -392,6 +434,124 @@ class CudaB200Backend:
 DESC_KEYS = [f[0] for f in ModelDesc._fields_]
 
 
+class BatchedEngine:
+    """Continuous batching over the sequence slots of one context (b200_batch_*): the peer of BatchedEngine
+    (src/engine_batched.rs:114-197) below the tokenizer and the channels.  `submit` = BatchedEngine::submit, `step` = one iteration
+    of its background loop; events are ("token", request_id, token_id), ("done", request_id, reason, prompt_tokens,
+    completion_tokens) with reason "stop" | "max_tokens", and ("error", request_id, message)."""
+
+    REASONS = ("stop", "max_tokens", "error")
+
+    def __init__(self, gpu, max_batch_size=8, max_seq_len=4096, max_queue_depth=64, eos_token_id=2):
+        self._gpu = gpu          # keeps the context alive
+        self._h = C.c_void_p()
+        cfg = BatchConfig(max_batch_size, max_seq_len, max_queue_depth, eos_token_id)
+        _check(lib().b200_batch_create(gpu._h, C.byref(cfg), C.byref(self._h)))
+        self._cap = max(64, 2 * max_batch_size)
+        self._buf = (BatchEvent * self._cap)()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def submit(self, tokens, max_tokens):
+        """Request id.  Raises OperationFailed("queue full") past max_queue_depth."""
+        arr = (C.c_uint32 * max(1, len(tokens)))(*tokens)
+        rid = C.c_uint64()
+        _check(lib().b200_batch_submit(self._h, arr, len(tokens), int(max_tokens), C.byref(rid)))
+        return rid.value
+
+    def step(self):
+        n = C.c_int()
+        _check(lib().b200_batch_step(self._h, self._buf, self._cap, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            e = self._buf[i]
+            if e.kind == 0:
+                out.append(("token", e.request_id, e.token))
+            elif e.kind == 1:
+                out.append(("done", e.request_id, self.REASONS[e.reason], e.prompt_tokens, e.completion_tokens))
+            else:
+                out.append(("error", e.request_id, lib().b200_batch_last_error(self._h).decode()))
+        return out
+
+    def counts(self):
+        a, p, u = C.c_int(), C.c_int(), C.c_int()
+        st, rows = C.c_uint64(), C.c_uint64()
+        _check(lib().b200_batch_counts(self._h, C.byref(a), C.byref(p), C.byref(u), C.byref(st), C.byref(rows)))
+        return dict(active=a.value, pending=p.value, undelivered_events=u.value, steps=st.value, decode_rows=rows.value)
+
+    def run(self, max_steps=100000):
+        """Step until nothing is active or pending; all events in order."""
+        out = []
+        for _ in range(max_steps):
+            c = self.counts()
+            if c["active"] == 0 and c["pending"] == 0 and c["undelivered_events"] == 0:
+                break
+            out.extend(self.step())
+        return out
+
+
+class GgufFile:
+    """A GGUF file mapped and parsed by the library (b200_gguf_*; no CUDA device needed): what GgufFile::open + GgufReader::read +
+    ModelLoader::parse_config give the reference (src/gguf/mod.rs:23-54, reader.rs:28-110, model/loader.rs:62-300)."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        _check(lib().b200_gguf_open(os.fsencode(path), C.byref(self._h)))
+        self.path = path
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200_gguf_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self):
+        ver = C.c_uint32()
+        v = [C.c_uint64() for _ in range(5)]
+        _check(lib().b200_gguf_info(self._h, C.byref(ver), *[C.byref(x) for x in v]))
+        return dict(version=ver.value, n_tensors=v[0].value, n_metadata=v[1].value, alignment=v[2].value, data_offset=v[3].value,
+                    file_bytes=v[4].value)
+
+    def architecture(self):
+        buf = C.create_string_buffer(128)
+        _check(lib().b200_gguf_architecture(self._h, buf, 128))
+        return buf.value.decode()
+
+    def model_desc(self, max_seq_len=0, max_batch=1):
+        d = ModelDesc()
+        _check(lib().b200_gguf_model_desc(self._h, int(max_seq_len), int(max_batch), C.byref(d)))
+        return {k: getattr(d, k) for k in DESC_KEYS}
+
+    def tensor(self, i, with_data=False):
+        """(name, ggml_type, ne list, nbytes[, uint8 copy of the bytes or None for a type the engine does not implement])."""
+        name, t, ne, nd = C.c_char_p(), C.c_uint32(), (C.c_uint64 * 4)(), C.c_int()
+        data, nb = C.c_void_p(), C.c_size_t()
+        _check(lib().b200_gguf_tensor_info(self._h, i, C.byref(name), C.byref(t), ne, C.byref(nd), C.byref(data) if with_data else None,
+                                           C.byref(nb)))
+        out = (name.value.decode(), t.value, [int(ne[k]) for k in range(nd.value)], nb.value)
+        if with_data:
+            arr = None
+            if data.value:
+                arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
+            out = out + (arr,)
+        return out
+
+    def tensors(self, with_data=False):
+        return [self.tensor(i, with_data) for i in range(self.info()["n_tensors"])]
+
+
 class GpuOnlyInference:
     """`impl GpuInference for GpuOnlyInference` on cuda-b200.
 
@@ -470,6 +630,30 @@ class GpuOnlyInference:
         desc["max_seq_len"] = min(int(max_seq_len), desc.get("max_seq_len", max_seq_len)) if max_seq_len else desc["max_seq_len"]
         return cls(desc, tensors, **kw)
 
+    @classmethod
+    def from_gguf(cls, path, max_seq_len=0, max_batch=1, device=0, kv_format="f32"):
+        """GpuOnlyInference::from_model for a file path, entirely inside the library (b200_ctx_create_from_gguf): mmap, parse,
+        pinned double-buffered upload of every tensor the engine uses, finalize.  `load_stats` holds bytes / seconds / GB/s."""
+        L = lib()
+        if device_count() == 0:
+            raise NotAvailable("cuda-b200: no CUDA device (this backend has no CPU fallback)")
+        if kv_format not in ("f32", "int8"):
+            raise Unsupported(f"kv_format {kv_format!r}: f32 or int8")
+        self = cls.__new__(cls)
+        with GgufFile(path) as f:
+            self.desc = f.model_desc(max_seq_len, max_batch)
+            self.arch = f.architecture()
+        par = ParallelDesc(1, 0, device)
+        h, st = C.c_void_p(), LoadStats()
+        self._h = None
+        _check(L.b200_ctx_create_from_gguf(os.fsencode(path), C.byref(par), int(max_seq_len), int(max_batch),
+                                           1 if kv_format == "int8" else 0, C.byref(h), C.byref(st)))
+        self._h = h
+        self.load_stats = st.as_dict()
+        self.world, self.rank, self.expert_parallel = 1, 0, False
+        self.vocab = self.desc["vocab"]
+        return self
+
     def upload_tensor(self, name, ggml_type, ne, data):
         a = np.ascontiguousarray(data)
         nd = (C.c_uint64 * 4)(*(list(ne) + [1] * (4 - len(ne))))
@@ -539,6 +723,15 @@ class GpuOnlyInference:
                                        toks.ctypes.data_as(C.POINTER(C.c_uint32)), seqs.size, _fp(logits)))
         return logits
 
+    def decode_batch_greedy(self, seqs, tokens):
+        """b200_decode_batch_greedy: the next token of every sequence, picked on the device (last maximum wins)."""
+        n = len(seqs)
+        s_arr = (C.c_int * n)(*seqs)
+        t_arr = (C.c_uint32 * n)(*tokens)
+        out = (C.c_uint32 * n)()
+        _check(lib().b200_decode_batch_greedy(self._h, s_arr, t_arr, n, out))
+        return [int(x) for x in out]
+
     def decode_greedy(self, first_token, n_steps, seq=0):
         """n_steps device-resident greedy tokens; returns (tokens, elapsed_ms by CUDA events)."""
         out = np.empty(n_steps, dtype=np.uint32)
@@ -574,7 +767,17 @@ class GroupInference:
     one host thread per device inside the library -- the caller never sees ranks (TensorParallel trait,
     src/backend/tensor_parallel.rs:13-32).  Same surface as GpuOnlyInference: forward() returns the full logits row."""
 
-    def __init__(self, desc: dict, tensors: dict, n_devices=1, devices=None, feeder=None):
+    @classmethod
+    def from_gguf(cls, path, n_devices=1, devices=None, max_seq_len=0, max_batch=1):
+        """The group built straight from a GGUF file: every rank's host thread stages its own shard out of the one mapping
+        (b200_group_load_gguf)."""
+        f = GgufFile(path)
+        try:
+            return cls(f.model_desc(max_seq_len, max_batch), None, n_devices, devices, gguf=f)
+        finally:
+            f.close()
+
+    def __init__(self, desc: dict, tensors: dict, n_devices=1, devices=None, feeder=None, gguf=None):
         L = lib()
         if device_count() < n_devices:
             raise NotAvailable(f"cuda-b200: {n_devices} CUDA devices needed, {device_count()} present (no CPU fallback)")
@@ -595,6 +798,10 @@ class GroupInference:
                 self.upload_tensor(name, t, ne, data)
             if feeder is not None:
                 feeder(self.upload_tensor)
+            if gguf is not None:
+                st = LoadStats()
+                _check(L.b200_group_load_gguf(self._h, gguf._h, C.byref(st)))
+                self.load_stats = st.as_dict()
             _check(L.b200_group_finalize(self._h))
         except Exception:
             self.close()

@@ -34,6 +34,7 @@
 #include "gemm_umma2.cuh"
 #include "attn_umma.cuh"
 #include "kv_int8.cuh"
+#include "gguf_load.cuh"
 #include "gemv_mma.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -89,6 +90,7 @@ struct DevTensor {
     uint64_t ne[4] = {1, 1, 1, 1};
     size_t nbytes = 0;
     long long row_bytes = 0;  // bytes of one output row (ne[0] elements)
+    bool arena = false;       // d points into the context's load arena (b200_ctx_load_gguf): not freed on its own
     bool present() const { return d != nullptr; }
     const float* f32() const { return reinterpret_cast<const float*>(d); }
 };
@@ -147,6 +149,20 @@ struct b200_ctx {
     size_t smem_optin = 227 * 1024;
     uint64_t mma_launches = 0, v1_launches = 0;
     // per-token megakernel (mega.cuh)
+    // GGUF -> HBM load (gguf_load.cuh): two pinned staging buffers, worker threads fill one while the copy engine drains the other
+    struct LoadStage {
+        bool on = false;
+        uint8_t* pin[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        size_t chunk = 0;
+        int next = 0, threads = 4;
+        uint64_t bytes = 0;
+    } stage;
+    // one allocation for every tensor of a GGUF load (291 cudaMalloc + memset pairs cost more than copying Llama-3-8B's 4.9 GB):
+    // zeroed once, tensors carved out at 256-byte boundaries with the 256 zero bytes behind each that the kernels' tail reads expect
+    uint8_t* arena = nullptr;
+    size_t arena_size = 0, arena_off = 0;
     int kv_format = 0;            // 0 = f32 (model/mod.rs:83-108), 1 = int8 (model/kv_quantized.rs Int8): B200_KV_FORMAT / b200_ctx_set_kv_format
     float* attn_q8_part = nullptr;
     int attn_q8_splits = 0;
@@ -205,6 +221,8 @@ struct b200_ctx {
     bool pf_tmaps_built = false;
     size_t pf_split_floats = 0;
     int pf_logits_rows = 0;
+    int* pf_argmax = nullptr;        // batched decode with the pick on the device: [rows]
+    int pf_argmax_rows = 0;
     int batch_gemm_min = 8;    // measured crossover on Llama-3-8B: a GEMM pass costs ~12 ms up to 32 rows, a sequence alone 2 ms
     uint64_t prefill_gemm_tokens = 0;
     int* h_err = nullptr;   // pinned copy of the first watchdog word, fetched with every synchronising call
@@ -360,6 +378,71 @@ static int tp_shard_kind(const char* name) {
     return 0;
 }
 
+// Device memory of one tensor: `bytes` + 256 zero bytes behind it.  Out of the load arena while one is open (already zeroed),
+// else its own allocation; `zero_body` also clears the tensor's bytes (row-parallel shards: the pitch gaps must read as zero).
+static cudaError_t tensor_alloc(b200_ctx* c, DevTensor* t, size_t bytes, bool zero_body) {
+    const size_t need = (bytes + 256 + 255) & ~(size_t)255;
+    if (c->arena && c->arena_off + need <= c->arena_size) {
+        t->d = c->arena + c->arena_off;
+        t->arena = true;
+        c->arena_off += need;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc((void**)&t->d, bytes + 256);
+    if (e != cudaSuccess) return e;
+    t->arena = false;
+    return zero_body ? cudaMemset(t->d, 0, bytes + 256) : cudaMemset(t->d + bytes, 0, 256);
+}
+
+// Host -> device copies of b200_ctx_upload_tensor.  Plain cudaMemcpy for caller-owned buffers; while a GGUF load is running
+// (c->stage.on) the bytes come out of a file mapping and go through the pinned double buffer instead: fill buffer b with host
+// threads, cudaMemcpyAsync it on the load stream, and meanwhile fill buffer b ^ 1.  The load stream is a BLOCKING stream, so the
+// legacy-stream memsets of the allocation are ordered with the copies.
+static cudaError_t h2d(b200_ctx* c, void* dst, const void* src, size_t n) {
+    b200_ctx::LoadStage& s = c->stage;
+    if (!s.on) return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+    cudaError_t e;
+    for (size_t off = 0; off < n; off += s.chunk) {
+        const size_t len = std::min(s.chunk, n - off);
+        const int b = s.next;
+        s.next ^= 1;
+        if ((e = cudaEventSynchronize(s.ev[b])) != cudaSuccess) return e;
+        gguf_parallel_copy(s.pin[b], (const uint8_t*)src + off, len, s.threads);
+        if ((e = cudaMemcpyAsync((uint8_t*)dst + off, s.pin[b], len, cudaMemcpyHostToDevice, s.st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(s.ev[b], s.st)) != cudaSuccess) return e;
+        s.bytes += len;
+    }
+    return cudaSuccess;
+}
+// rows of `width` bytes, `spitch` apart on the host, `dpitch` apart on the device (row-parallel shards: a K range of every row)
+static cudaError_t h2d_2d(b200_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+    b200_ctx::LoadStage& s = c->stage;
+    if (!s.on) return cudaMemcpy2D(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice);
+    cudaError_t e;
+    const size_t rpc = std::max<size_t>(1, s.chunk / width);
+    if (width > s.chunk) return cudaErrorInvalidValue;
+    for (size_t r0 = 0; r0 < rows; r0 += rpc) {
+        const size_t nr = std::min(rpc, rows - r0);
+        const int b = s.next;
+        s.next ^= 1;
+        if ((e = cudaEventSynchronize(s.ev[b])) != cudaSuccess) return e;
+        uint8_t* pin = s.pin[b];
+        const uint8_t* from = (const uint8_t*)src + r0 * spitch;
+        const int nt = (int)std::min<size_t>((size_t)std::max(1, s.threads), nr);
+        std::vector<std::thread> th;
+        auto gather = [=](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) memcpy(pin + i * width, from + i * spitch, width); };
+        const size_t per = (nr + nt - 1) / nt;
+        for (int t = 1; t < nt; t++)
+            if (per * t < nr) th.emplace_back(gather, per * t, std::min(nr, per * (t + 1)));
+        gather(0, std::min(nr, per));
+        for (std::thread& t : th) t.join();
+        if ((e = cudaMemcpy2DAsync((uint8_t*)dst + r0 * dpitch, dpitch, pin, width, width, nr, cudaMemcpyHostToDevice, s.st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(s.ev[b], s.st)) != cudaSuccess) return e;
+        s.bytes += nr * width;
+    }
+    return cudaSuccess;
+}
+
 extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32_t ggml_type, const uint64_t* ne,
                                       int n_dims, const void* host, size_t nbytes) {
     if (!c || !gguf_name || !ne || !host) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_upload_tensor: null argument");
@@ -375,7 +458,7 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
     if (ne[0] % be) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": ne[0] not a multiple of the block size");
     if (numel / be * bb != nbytes) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": byte size does not match shape");
     CU(cudaSetDevice(c->par.device));
-    if (t->d) cudaFree(t->d);
+    if (t->d && !t->arena) cudaFree(t->d);
     *t = DevTensor();
     // Tensor-parallel shard of this rank (Megatron split; ShardingPlan, src/backend/tensor_parallel.rs:69-106):
     //   column-parallel = a contiguous range of output rows (attn_q/k/v + biases by head, ffn_gate/up, output),
@@ -393,17 +476,15 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
         if (ne[dim] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": rows not divisible by the world size");
         lne[dim] = ne[dim] / P;
         const size_t lbytes = nbytes / P;
-        CU_ALLOC(cudaMalloc((void**)&t->d, lbytes + 256));
-        CU(cudaMemcpy(t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes, cudaMemcpyHostToDevice));
-        CU(cudaMemset(t->d + lbytes, 0, 256));
+        CU_ALLOC(tensor_alloc(c, t, lbytes, false));
+        CU(h2d(c, t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes));
         t->nbytes = lbytes;
     } else if (kind == 3) {   // expert parallel: the experts are the outermost dimension -> a contiguous byte range per rank
         if (n_dims != 3 || ne[2] % P) return fail(B200_ERR_SHAPE_MISMATCH, std::string(gguf_name) + ": experts not divisible by the world size");
         lne[2] = ne[2] / P;
         const size_t lbytes = nbytes / P;
-        CU_ALLOC(cudaMalloc((void**)&t->d, lbytes + 256));
-        CU(cudaMemcpy(t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes, cudaMemcpyHostToDevice));
-        CU(cudaMemset(t->d + lbytes, 0, 256));
+        CU_ALLOC(tensor_alloc(c, t, lbytes, false));
+        CU(h2d(c, t->d, (const uint8_t*)host + (size_t)R * lbytes, lbytes));
         t->nbytes = lbytes;
     } else if (kind == 2) {
         const uint64_t nb = ne[0] / be;
@@ -413,15 +494,13 @@ extern "C" int b200_ctx_upload_tensor(b200_ctx* c, const char* gguf_name, uint32
         // tensor map of the streamed kernel needs (Llama-3-8B TP=2: 28 Q6_K blocks = 5880 bytes -> pitch 5888)
         const size_t slice = (size_t)(nb / P) * bb, rows = (size_t)(numel / ne[0]);
         const size_t pitch = (slice + 15) & ~(size_t)15;
-        CU_ALLOC(cudaMalloc((void**)&t->d, pitch * rows + 256));
-        CU(cudaMemset(t->d, 0, pitch * rows + 256));
-        CU(cudaMemcpy2D(t->d, pitch, (const uint8_t*)host + (size_t)R * slice, row_bytes_full, slice, rows, cudaMemcpyHostToDevice));
+        CU_ALLOC(tensor_alloc(c, t, pitch * rows, true));
+        CU(h2d_2d(c, t->d, pitch, (const uint8_t*)host + (size_t)R * slice, row_bytes_full, slice, rows));
         t->nbytes = pitch * rows;
         tp_pitch = (long long)pitch;
     } else {
-        CU_ALLOC(cudaMalloc((void**)&t->d, nbytes + 256));
-        CU(cudaMemcpy(t->d, host, nbytes, cudaMemcpyHostToDevice));
-        CU(cudaMemset(t->d + nbytes, 0, 256));
+        CU_ALLOC(tensor_alloc(c, t, nbytes, false));
+        CU(h2d(c, t->d, host, nbytes));
         t->nbytes = nbytes;
     }
     t->type = (int)ggml_type;
@@ -572,7 +651,7 @@ extern "C" int b200_ctx_finalize(b200_ctx* c) {
         // per-op (graph) decode path only: the megakernels and the tensor-core prefill read the f32 cache
         c->use_mega = false;
         c->use_prefill_gemm = false;
-        c->attn_q8_splits = std::max(1, std::min(128, (4 * c->n_sm + (int)nkv - 1) / (int)nkv));
+        c->attn_q8_splits = std::max(1, std::min(kAttnQ8MaxSplits, (2 * c->n_sm + (int)nkv - 1) / (int)nkv));   // two resident CTAs per SM
         CU_ALLOC(cudaMalloc((void**)&c->attn_q8_part, (size_t)nkv * c->attn_q8_splits * (nh / nkv) * (hd + 2) * sizeof(float)));
     }
     // kernels that may need more than 48 KB of dynamic shared memory
@@ -656,7 +735,9 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->par.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gemv_graph) cudaGraphExecDestroy(c->gemv_graph);
-    for (auto& kv : c->tensors) cudaFree(kv.second.d);
+    for (auto& kv : c->tensors)
+        if (!kv.second.arena) cudaFree(kv.second.d);
+    cudaFree(c->arena);
     for (Slot& s : c->slots) {
         for (int m = 0; m < MODE_COUNT; m++)
             if (s.graph[m]) cudaGraphExecDestroy(s.graph[m]);
@@ -680,6 +761,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_tok);
     cudaFree(c->pf_rows);
     cudaFree(c->pf_logits);
+    cudaFree(c->pf_argmax);
     cudaFree(c->pf_split);
     cudaFree(c->pf_tmaps);
     cudaFree(c->pf_tile_cnt);
@@ -809,9 +891,7 @@ static cudaError_t enqueue_token(b200_ctx* c, int slot_i, Mode mode, bool only_g
             ap.q = q; ap.k8 = k8; ap.v8 = v8; ap.k_scale = ks; ap.v_scale = vs; ap.part = c->attn_q8_part; ap.out = c->attn; ap.pos = pos_ptr;
             ap.n_kv = nkv; ap.G = G; ap.max_seq = d.max_seq_len; ap.n_splits = c->attn_q8_splits; ap.scale = 1.0f / sqrtf((float)hd);
             const dim3 grid(ap.n_splits, nkv);
-            void (*split_k)(AttnQ8Params) = hd == 128 ? (G <= 4 ? attn_q8_split_kernel<4, 4> : attn_q8_split_kernel<4, 8>)
-                                                      : (G <= 4 ? attn_q8_split_kernel<2, 4> : attn_q8_split_kernel<2, 8>);
-            CK(launch_k(c, split_k, grid, dim3(32), 0, ap));
+            CK(launch_k(c, hd == 128 ? attn_q8_split_kernel<128, 4> : attn_q8_split_kernel<64, 4>, grid, dim3(kAttnQ8Warps * 32), 0, ap));
             CK(launch_k(c, attn_q8_merge_kernel, dim3(nh), dim3(hd), 0, ap, hd));
         }
         if (!only_gemv && c->kv_format == 0) {   // RoPE + KV write
@@ -2741,3 +2821,575 @@ extern "C" int b200_op_attention(const float* q, const float* k, const float* v,
     CU(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
+
+// ------------------------------------------------------------------ GGUF -> HBM direct load (gguf_load.cuh)
+extern "C" int b200_gguf_open(const char* path, b200_gguf** out) {
+    if (!path || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_gguf_open: null argument");
+    *out = nullptr;
+    b200_gguf* g = new b200_gguf();
+    g->fd = open(path, O_RDONLY);
+    struct stat st;
+    if (g->fd < 0 || fstat(g->fd, &st) != 0) {
+        gguf_release(g);
+        return fail(B200_ERR_INVALID_ARGUMENT, std::string("b200_gguf_open: cannot open ") + path);
+    }
+    g->size = (size_t)st.st_size;
+    if (g->size < 8) {
+        gguf_release(g);
+        return fail(B200_ERR_INVALID_ARGUMENT, std::string(path) + ": not a GGUF file (shorter than its header)");
+    }
+    void* m = mmap(nullptr, g->size, PROT_READ, MAP_PRIVATE, g->fd, 0);
+    if (m == MAP_FAILED) {
+        g->map = nullptr;
+        gguf_release(g);
+        return fail(B200_ERR_ALLOCATION_FAILED, std::string("b200_gguf_open: mmap failed for ") + path);
+    }
+    g->map = (const uint8_t*)m;
+    madvise(m, g->size, MADV_SEQUENTIAL);
+    GgufCursor c{g->map, g->size};
+    const uint32_t magic = c.get<uint32_t>();
+    if (magic != 0x46554747u) {   // GgufError::InvalidMagic (reader.rs:35)
+        gguf_release(g);
+        char b[64];
+        snprintf(b, sizeof b, "invalid GGUF magic 0x%08x", magic);
+        return fail(B200_ERR_INVALID_ARGUMENT, b);
+    }
+    g->version = c.get<uint32_t>();
+    if (g->version < 1 || g->version > 3) {   // GgufError::UnsupportedVersion (reader.rs:41)
+        const uint32_t v = g->version;
+        gguf_release(g);
+        return fail(B200_ERR_UNSUPPORTED, "unsupported GGUF version " + std::to_string(v));
+    }
+    const uint64_t n_tensors = c.len(g->version), n_kv = c.len(g->version);
+    if (!c.ok || n_tensors > g->size || n_kv > g->size) {
+        gguf_release(g);
+        return fail(B200_ERR_INVALID_ARGUMENT, "GGUF header truncated or counts out of range");
+    }
+    for (uint64_t i = 0; i < n_kv; i++) {
+        std::string key = c.str(g->version);
+        const uint32_t type = c.get<uint32_t>();
+        GgufValue v;
+        if (!c.ok || !gguf_read_value(c, g->version, type, v, 0)) {
+            const bool trunc = !c.ok;
+            gguf_release(g);
+            return fail(B200_ERR_INVALID_ARGUMENT, trunc ? "GGUF metadata truncated (key '" + key + "')"
+                                                         : "invalid GGUF metadata value type " + std::to_string(type) + " (key '" + key + "')");
+        }
+        g->kv[key] = std::move(v);
+    }
+    g->tensors.reserve((size_t)n_tensors);
+    for (uint64_t i = 0; i < n_tensors; i++) {
+        GgufTensorInfo t;
+        t.name = c.str(g->version);
+        const uint32_t nd = c.get<uint32_t>();
+        if (!c.ok || nd < 1 || nd > 4) {
+            gguf_release(g);
+            return fail(B200_ERR_INVALID_ARGUMENT, "GGUF tensor info truncated or with a bad rank (tensor " + std::to_string(i) + ")");
+        }
+        t.n_dims = (int)nd;
+        for (uint32_t k = 0; k < nd; k++) t.ne[k] = c.len(g->version);
+        t.type = c.get<uint32_t>();
+        t.offset = c.get<uint64_t>();
+        if (!c.ok) {
+            gguf_release(g);
+            return fail(B200_ERR_INVALID_ARGUMENT, "GGUF tensor infos truncated");
+        }
+        const int be = type_block_elems((int)t.type), bb = type_block_bytes((int)t.type);
+        if (be) {
+            uint64_t numel = 1;
+            for (int k = 0; k < t.n_dims; k++) numel *= t.ne[k];
+            t.nbytes = (size_t)(numel / be * bb);   // TensorInfo::data_size (types.rs:45-50)
+        }
+        g->tensors.push_back(std::move(t));
+    }
+    {   // general.alignment: Uint32 or Uint64, default 32 (reader.rs:84-96)
+        auto it = g->kv.find("general.alignment");
+        if (it != g->kv.end() && (it->second.type == GV_U32 || it->second.type == GV_U64) && it->second.u > 0) g->alignment = it->second.u;
+    }
+    g->data_offset = ((uint64_t)c.pos + g->alignment - 1) / g->alignment * g->alignment;
+    {
+        auto it = g->kv.find("general.architecture");
+        if (it != g->kv.end() && it->second.type == GV_STRING) g->arch = it->second.s;
+    }
+    *out = g;
+    return B200_OK;
+}
+
+extern "C" void b200_gguf_close(b200_gguf* g) { gguf_release(g); }
+
+extern "C" int b200_gguf_info(b200_gguf* g, uint32_t* version, uint64_t* n_tensors, uint64_t* n_metadata, uint64_t* alignment,
+                              uint64_t* data_offset, uint64_t* file_bytes) {
+    if (!g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_gguf_info: null file");
+    if (version) *version = g->version;
+    if (n_tensors) *n_tensors = g->tensors.size();
+    if (n_metadata) *n_metadata = g->kv.size();
+    if (alignment) *alignment = g->alignment;
+    if (data_offset) *data_offset = g->data_offset;
+    if (file_bytes) *file_bytes = g->size;
+    return B200_OK;
+}
+
+extern "C" int b200_gguf_architecture(b200_gguf* g, char* out, size_t cap) {
+    if (!g || !out || cap == 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_gguf_architecture: bad argument");
+    if (g->arch.empty()) return fail(B200_ERR_INVALID_ARGUMENT, "missing metadata general.architecture");
+    snprintf(out, cap, "%s", g->arch.c_str());
+    return B200_OK;
+}
+
+// (name, type, ne, n_dims, pointer into the mapping, bytes) of tensor i; *data is NULL (and *nbytes 0) for a type the engine does not
+// implement.  Fails if the tensor's bytes lie outside the file (GgufFile::tensor_data returns None, mod.rs:34-42).
+extern "C" int b200_gguf_tensor_info(b200_gguf* g, uint64_t i, const char** name, uint32_t* ggml_type, uint64_t* ne4, int* n_dims,
+                                     const void** data, size_t* nbytes) {
+    if (!g || i >= g->tensors.size()) return fail(B200_ERR_INVALID_ARGUMENT, "b200_gguf_tensor_info: bad argument");
+    const GgufTensorInfo& t = g->tensors[(size_t)i];
+    if (name) *name = t.name.c_str();
+    if (ggml_type) *ggml_type = t.type;
+    if (ne4) for (int k = 0; k < 4; k++) ne4[k] = t.ne[k];
+    if (n_dims) *n_dims = t.n_dims;
+    if (nbytes) *nbytes = t.nbytes;
+    if (data) {
+        *data = nullptr;
+        if (t.nbytes) {
+            const uint64_t start = g->data_offset + t.offset;
+            if (start > g->size || t.nbytes > g->size - start)
+                return fail(B200_ERR_INVALID_ARGUMENT, t.name + ": tensor data lies outside the file (truncated GGUF?)");
+            *data = g->map + start;
+        }
+    }
+    return B200_OK;
+}
+
+// ModelLoader::parse_config (src/model/loader.rs:62-300), the keys GpuOnlyInference needs, same defaults and fallbacks.
+extern "C" int b200_gguf_model_desc(b200_gguf* g, int max_seq_len, int max_batch, b200_model_desc* out) {
+    if (!g || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_gguf_model_desc: null argument");
+    if (g->arch.empty()) return fail(B200_ERR_INVALID_ARGUMENT, "missing metadata general.architecture");
+    const std::string& a = g->arch;
+    // gemma (GELU), phi / gptneox (LayerNorm, fused QKV) ... share tensor names with llama but not its arithmetic: refuse them
+    if (a != "llama" && a != "mistral" && a != "mixtral" && a != "qwen2" && a != "qwen2moe")
+        return fail(B200_ERR_UNSUPPORTED, "unsupported architecture '" + a + "': cuda-b200 implements llama, mistral, mixtral, qwen2, qwen2moe (RMSNorm + SwiGLU + RoPE)");
+    auto need_u32 = [&](const char* key, uint32_t& v) { return gguf_get_u32(g, a + "." + key, v); };
+    b200_model_desc d{};
+    uint32_t u = 0;
+    if (!need_u32("embedding_length", u)) return fail(B200_ERR_INVALID_ARGUMENT, "missing metadata " + a + ".embedding_length");
+    d.hidden = (int32_t)u;
+    if (!need_u32("block_count", u)) return fail(B200_ERR_INVALID_ARGUMENT, "missing metadata " + a + ".block_count");
+    d.n_layers = (int32_t)u;
+    if (!need_u32("attention.head_count", u) || u == 0) return fail(B200_ERR_INVALID_ARGUMENT, "missing metadata " + a + ".attention.head_count");
+    d.n_heads = (int32_t)u;
+    d.n_kv_heads = need_u32("attention.head_count_kv", u) ? (int32_t)u : d.n_heads;
+    d.head_dim = need_u32("attention.key_length", u) ? (int32_t)u : d.hidden / d.n_heads;
+    d.ffn = need_u32("feed_forward_length", u) ? (int32_t)u : d.hidden * 4 * 2 / 3;
+    const int file_ctx = need_u32("context_length", u) ? (int)u : 2048;
+    d.max_seq_len = max_seq_len > 0 ? std::min(max_seq_len, file_ctx) : file_ctx;
+    float f = 0.0f;
+    d.norm_eps = gguf_get_f32(g, a + ".attention.layer_norm_rms_epsilon", f) ? f : gguf_get_f32(g, a + ".attention.layer_norm_epsilon", f) ? f : 1e-5f;
+    d.rope_base = gguf_get_f32(g, a + ".rope.freq_base", f) ? f : 10000.0f;
+    d.rope_scale = gguf_get_f32(g, a + ".rope.scale_linear", f) ? f : 1.0f;
+    d.rope_neox = (a == "qwen2" || a == "qwen2moe") ? 1 : 0;   // loader.rs:145-162
+    d.n_experts = need_u32("expert_count", u) ? (int32_t)u : 0;
+    d.n_experts_used = need_u32("expert_used_count", u) ? (int32_t)u : 0;
+    d.expert_ffn = need_u32("expert_feed_forward_length", u) ? (int32_t)u : 0;
+    if (need_u32("rope.dimension_count", u) && (int32_t)u != d.head_dim)
+        return fail(B200_ERR_UNSUPPORTED, "partial RoPE (rope.dimension_count " + std::to_string(u) + " != head_dim " + std::to_string(d.head_dim) + ") is not implemented");
+    // vocab: {arch}.vocab_size, tokenizer.ggml.vocab_size, the token array's length, the embedding's rows, 32000 (loader.rs:77-98)
+    const GgufTensorInfo* emb = gguf_find_tensor(g, "token_embd.weight");
+    if (need_u32("vocab_size", u) || gguf_get_u32(g, "tokenizer.ggml.vocab_size", u)) d.vocab = (int32_t)u;
+    else {
+        auto it = g->kv.find("tokenizer.ggml.tokens");
+        if (it != g->kv.end() && it->second.type == GV_ARRAY) d.vocab = (int32_t)it->second.arr_len;
+        else if (emb && emb->n_dims == 2) d.vocab = (int32_t)emb->ne[1];
+        else d.vocab = 32000;
+    }
+    d.tied_output = gguf_find_tensor(g, "output.weight") ? 0 : 1;   // loader.rs:349-355
+    if (d.n_experts > 0 && d.expert_ffn == 0) {
+        const GgufTensorInfo* ge = gguf_find_tensor(g, "blk.0.ffn_gate_exps.weight");
+        if (ge && ge->n_dims == 3) d.expert_ffn = (int32_t)ge->ne[1];
+    }
+    d.max_batch = std::max(1, max_batch);
+    *out = d;
+    return B200_OK;
+}
+
+static cudaError_t stage_begin(b200_ctx* c) {
+    b200_ctx::LoadStage& s = c->stage;
+    cudaError_t e;
+    s.chunk = (size_t)std::max(1, env_int("B200_LOAD_CHUNK_MB", 32)) << 20;
+    if (env_int("B200_LOAD_CHUNK_KB", 0) > 0) s.chunk = (size_t)env_int("B200_LOAD_CHUNK_KB", 0) << 10;   // (tests: many chunks per tensor)
+    // measured on the B200 box (16 host cores, Llama-3-8B Q4_K_M, 4.9 GB from the page cache): 1 thread 5.8 GB/s, 4: 9-14, 8: 15.8
+    s.threads = std::max(1, env_int("B200_LOAD_THREADS", (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()))));
+    s.next = 0;
+    s.bytes = 0;
+    if ((e = cudaStreamCreate(&s.st)) != cudaSuccess) return e;   // blocking stream: ordered with the legacy-stream memsets
+    for (int b = 0; b < 2; b++) {
+        if ((e = cudaHostAlloc((void**)&s.pin[b], s.chunk, cudaHostAllocDefault)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&s.ev[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    s.on = true;
+    return cudaSuccess;
+}
+static cudaError_t stage_end(b200_ctx* c) {
+    b200_ctx::LoadStage& s = c->stage;
+    s.on = false;
+    cudaError_t e = s.st ? cudaStreamSynchronize(s.st) : cudaSuccess;
+    for (int b = 0; b < 2; b++) {
+        if (s.ev[b]) cudaEventDestroy(s.ev[b]);
+        if (s.pin[b]) cudaFreeHost(s.pin[b]);
+        s.ev[b] = nullptr;
+        s.pin[b] = nullptr;
+    }
+    if (s.st) cudaStreamDestroy(s.st);
+    s.st = nullptr;
+    return e;
+}
+
+// Every tensor of the file that the engine has a slot for goes to HBM (this rank's shard under tensor / expert parallelism);
+// tensors it does not use (rope_freqs.weight, tokenizer tables ...) are skipped and counted.  B200_LOAD_STAGED=0 falls back to
+// cudaMemcpy straight from the mapping (pageable: the driver stages it internally, one thread) for comparison.
+extern "C" int b200_ctx_load_gguf(b200_ctx* c, b200_gguf* g, b200_load_stats* stats) {
+    if (!c || !g) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_load_gguf: null argument");
+    if (c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_load_gguf: context already finalized");
+    CU(cudaSetDevice(c->par.device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool staged = env_int("B200_LOAD_STAGED", 1) != 0;
+    if (staged) {
+        cudaError_t e = stage_begin(c);
+        if (e != cudaSuccess) {
+            stage_end(c);
+            return fail(B200_ERR_ALLOCATION_FAILED, std::string("b200_ctx_load_gguf: staging buffers: ") + cudaGetErrorString(e));
+        }
+    }
+    if (!c->arena && env_int("B200_LOAD_ARENA", 1)) {   // one zeroed allocation for all the tensors (upper bound: full tensors + padding)
+        const size_t P = (size_t)std::max(1, c->par.world_size);
+        size_t total = 0;
+        for (const GgufTensorInfo& t : g->tensors) {
+            if (!slot_for_name(c, t.name) || !t.nbytes) continue;
+            size_t b = t.nbytes;   // this rank's bytes of the tensor, as b200_ctx_upload_tensor will cut it
+            if (P > 1 && c->ep) {
+                if (t.name.find("_exps.weight") != std::string::npos) b = t.nbytes / P;
+            } else if (P > 1) {
+                const int kind = tp_shard_kind(t.name.c_str());
+                const size_t row = (size_t)(t.ne[0] / type_block_elems((int)t.type) * type_block_bytes((int)t.type));
+                if (kind == 1) b = t.nbytes / P;
+                else if (kind == 2 && row) b = ((row / P + 15) & ~(size_t)15) * (t.nbytes / row);   // 16-byte row pitch
+            }
+            total += (b + 256 + 255) & ~(size_t)255;
+        }
+        if (total && cudaMalloc((void**)&c->arena, total) == cudaSuccess) {
+            c->arena_size = total;
+            c->arena_off = 0;
+            CU(cudaMemset(c->arena, 0, total));
+        } else {
+            cudaGetLastError();
+            c->arena = nullptr;   // (falls back to one allocation per tensor)
+        }
+    }
+    uint32_t loaded = 0, skipped = 0;
+    uint64_t bytes = 0;
+    int rc = B200_OK;
+    for (uint64_t i = 0; i < g->tensors.size() && rc == B200_OK; i++) {
+        const GgufTensorInfo& t = g->tensors[(size_t)i];
+        if (!slot_for_name(c, t.name)) { skipped++; continue; }
+        const void* data = nullptr;
+        size_t nbytes = 0;
+        if ((rc = b200_gguf_tensor_info(g, i, nullptr, nullptr, nullptr, nullptr, &data, &nbytes))) break;
+        if (!data) { rc = fail(B200_ERR_UNSUPPORTED_DTYPE, t.name + ": unsupported ggml type " + std::to_string(t.type)); break; }
+        if (t.n_dims > 3) { rc = fail(B200_ERR_SHAPE_MISMATCH, t.name + ": 1..3 dims expected"); break; }
+        rc = b200_ctx_upload_tensor(c, t.name.c_str(), t.type, t.ne, t.n_dims, data, nbytes);
+        loaded++;
+        bytes += nbytes;
+    }
+    const uint64_t staged_bytes = c->stage.bytes;
+    if (staged) {
+        cudaError_t e = stage_end(c);
+        if (rc == B200_OK && e != cudaSuccess) rc = fail(B200_ERR_OPERATION_FAILED, std::string("b200_ctx_load_gguf: ") + cudaGetErrorString(e));
+    } else {
+        cudaDeviceSynchronize();
+    }
+    if (stats) {
+        stats->file_bytes = g->size;
+        stats->tensor_bytes = bytes;
+        stats->device_bytes = staged ? staged_bytes : bytes;
+        stats->tensors_loaded = loaded;
+        stats->tensors_skipped = skipped;
+        stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return rc;
+}
+
+// GpuOnlyInference::from_model for a file path: open + describe + create + load + finalize in one call.
+extern "C" int b200_ctx_create_from_gguf(const char* path, const b200_parallel_desc* par, int max_seq_len, int max_batch, int kv_format,
+                                         b200_ctx** out, b200_load_stats* stats) {
+    if (!path || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_create_from_gguf: null argument");
+    *out = nullptr;
+    b200_gguf* g = nullptr;
+    int rc = b200_gguf_open(path, &g);
+    if (rc) return rc;
+    b200_model_desc d{};
+    b200_ctx* c = nullptr;
+    if ((rc = b200_gguf_model_desc(g, max_seq_len, max_batch, &d)) == B200_OK && (rc = b200_ctx_create(&d, par, &c)) == B200_OK) {
+        if (kv_format != 0) rc = b200_ctx_set_kv_format(c, kv_format);
+        if (rc == B200_OK) rc = b200_ctx_load_gguf(c, g, stats);
+        if (rc == B200_OK) rc = b200_ctx_finalize(c);
+    }
+    const std::string msg = g_err;   // (destroy / close must not lose the message)
+    b200_gguf_close(g);
+    if (rc != B200_OK) {
+        if (c) b200_ctx_destroy(c);
+        g_err = msg;
+        return rc;
+    }
+    *out = c;
+    return B200_OK;
+}
+
+extern "C" int b200_group_load_gguf(b200_group* g, b200_gguf* file, b200_load_stats* stats) {
+    if (!g || !file) return fail(B200_ERR_INVALID_ARGUMENT, "b200_group_load_gguf: null argument");
+    return group_run(g, [=](int r) { return b200_ctx_load_gguf(g->ctx[r], file, r == 0 ? stats : nullptr); });
+}
+
+// ------------------------------------------------------------------ batched decode with the pick on the device + continuous batching
+static bool batch_gemm_eligible(b200_ctx* c, int n) {
+    if (n < c->batch_gemm_min || !prefill_gemm_ok(c)) return false;
+    const DevTensor& head = c->output.present() ? c->output : c->token_embd;
+    UmmaParams hp{};
+    hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = c->d.vocab; hp.K = c->d.hidden; hp.T = 1;
+    hp.x = reinterpret_cast<const __half*>(c->xa); hp.ldx = c->d.hidden;
+    return umma_eligible(hp) && n <= std::min(prefill_chunk(), c->d.max_seq_len);
+}
+
+// b200_decode_batch with the greedy pick (last maximum wins, src/main.rs:1816-1821) on the device: n token ids come back instead
+// of n x vocab logits (16 MB per step at batch 32 on Llama-3).  Same two paths as b200_decode_batch.
+extern "C" int b200_decode_batch_greedy(b200_ctx* c, const int* seqs, const uint32_t* tokens, int n, uint32_t* next_out) {
+    if (!c || !seqs || !tokens || !next_out || n <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch_greedy: bad argument");
+    if (c->par.world_size > 1) return fail(B200_ERR_UNSUPPORTED, "b200_decode_batch_greedy: not available under tensor parallelism");
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+            if (seqs[i] == seqs[j]) return fail(B200_ERR_INVALID_ARGUMENT, "b200_decode_batch_greedy: duplicate sequence slot");
+    int rc;
+    for (int i = 0; i < n; i++) {
+        if ((rc = check_slot(c, seqs[i], "b200_decode_batch_greedy"))) return rc;
+        if ((rc = check_token(c, seqs[i], tokens[i], "b200_decode_batch_greedy"))) return rc;
+        if ((rc = flush_pending(c, seqs[i]))) return rc;
+    }
+    if (batch_gemm_eligible(c, n)) {
+        CU(cudaSetDevice(c->par.device));
+        if (c->pf_argmax_rows < n) {
+            cudaFree(c->pf_argmax);
+            c->pf_argmax = nullptr;
+            CU_ALLOC(cudaMalloc((void**)&c->pf_argmax, (size_t)n * sizeof(int)));
+            c->pf_argmax_rows = n;
+        }
+        if ((rc = prefill_gemm(c, seqs[0], tokens, n, false, seqs))) return rc;
+        argmax_rows_kernel<<<n, 1024, 0, c->stream>>>(c->pf_logits, c->d.vocab, c->pf_argmax);
+        c->launches++;
+        CU(cudaMemcpyAsync(next_out, c->pf_argmax, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        WATCHDOG_FETCH(c);
+        CU(cudaStreamSynchronize(c->stream));
+        if ((rc = watchdog_check(c, "b200_decode_batch_greedy"))) return rc;
+        for (int i = 0; i < n; i++) c->slots[seqs[i]].host_pos++;
+        return B200_OK;
+    }
+    for (int i = 0; i < n; i++)
+        if ((rc = b200_decode_greedy(c, seqs[i], tokens[i], 1, next_out + i, nullptr))) return rc;
+    return B200_OK;
+}
+
+// Continuous batching: the peer of BatchedEngine's background loop (src/engine_batched.rs:199-411) below the tokenizer and the
+// channels.  submit = BatchedEngine::submit (:167-192, "queue full" past max_queue_depth) + the loop's drain step (:217-239: active
+// while there is room, else pending); step = one iteration of the loop: step_sequence's rules for every active sequence (:366-411:
+// finished if its last token is EOS or generated >= max_tokens, the whole prompt on the first step, then one token per step; EOS
+// ends the sequence without a Token event; Done carries MaxTokens iff generated >= max_tokens) and then the LIFO promotion of
+// pending requests (:291-304, Vec::pop).  The reference steps the sequences one by one through Model::forward; here every
+// sequence owns a KV slot of the context, the prompts go through b200_prefill and ALL decoding sequences share one pass over the
+// weights (b200_decode_batch_greedy).  Sampling is the greedy rule on the device.
+struct BatchSeq {
+    uint64_t id;
+    std::vector<uint32_t> tokens;
+    int prompt_len, generated, max_tokens, slot;
+    bool started;
+};
+struct BatchReq {
+    uint64_t id;
+    std::vector<uint32_t> tokens;
+    int max_tokens;
+};
+struct b200_batch {
+    b200_ctx* c = nullptr;
+    b200_batch_config cfg{};
+    std::vector<BatchSeq> active;
+    std::vector<BatchReq> pending;
+    std::vector<int> free_slots;
+    std::vector<b200_batch_event> events;   // not yet handed to the caller
+    uint64_t next_id = 1;
+    int queue_count = 0;                    // active + pending, as BatchedEngine::queue_count
+    uint64_t steps = 0, batched_rows = 0;
+    std::string last_error;                 // message of the last Error event
+};
+
+static void batch_event(b200_batch* b, uint64_t id, int kind, uint32_t token, int reason, int prompt_tokens, int completion_tokens) {
+    b200_batch_event e{};
+    e.request_id = id; e.kind = kind; e.token = token; e.reason = reason; e.prompt_tokens = prompt_tokens; e.completion_tokens = completion_tokens;
+    b->events.push_back(e);
+}
+// create_active_sequence (engine_batched.rs:322-356)
+static void batch_activate(b200_batch* b, BatchReq&& r) {
+    if (r.tokens.empty()) {   // "empty prompt"
+        batch_event(b, r.id, B200_BATCH_ERROR, 0, B200_FINISH_ERROR, 0, 0);
+        b->last_error = "empty prompt";
+        b->queue_count = std::max(0, b->queue_count - 1);
+        return;
+    }
+    const int max_seq = std::min(b->cfg.max_seq_len, b->c->d.max_seq_len);
+    const size_t keep = std::min(r.tokens.size(), (size_t)std::max(0, max_seq - 1));
+    BatchSeq s;
+    s.id = r.id;
+    s.tokens.assign(r.tokens.begin(), r.tokens.begin() + keep);
+    s.prompt_len = (int)keep;
+    s.generated = 0;
+    s.max_tokens = r.max_tokens;
+    s.slot = b->free_slots.back();
+    s.started = false;
+    b->free_slots.pop_back();
+    b->active.push_back(std::move(s));
+}
+
+extern "C" int b200_batch_create(b200_ctx* c, const b200_batch_config* cfg, b200_batch** out) {
+    if (!c || !out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_create: null argument");
+    if (!c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_create: context not finalized");
+    if (c->par.world_size > 1) return fail(B200_ERR_UNSUPPORTED, "b200_batch_create: not available under tensor / expert parallelism");
+    b200_batch* b = new b200_batch();
+    b->c = c;
+    b->cfg.max_batch_size = 8; b->cfg.max_seq_len = 4096; b->cfg.max_queue_depth = 64; b->cfg.eos_token_id = 2;   // BatchedEngineConfig::default (:32-40)
+    if (cfg) b->cfg = *cfg;
+    if (b->cfg.max_batch_size < 1 || b->cfg.max_batch_size > c->d.max_batch) {
+        const int want = b->cfg.max_batch_size;
+        delete b;
+        return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_create: max_batch_size " + std::to_string(want) + " needs a context with as many sequence slots (max_batch = " +
+                                                   std::to_string(c->d.max_batch) + ")");
+    }
+    if (b->cfg.max_seq_len < 2 || b->cfg.max_queue_depth < 1) {
+        delete b;
+        return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_create: bad max_seq_len / max_queue_depth");
+    }
+    for (int s = b->cfg.max_batch_size - 1; s >= 0; s--) b->free_slots.push_back(s);
+    *out = b;
+    return B200_OK;
+}
+extern "C" void b200_batch_destroy(b200_batch* b) { delete b; }
+
+extern "C" int b200_batch_submit(b200_batch* b, const uint32_t* tokens, int n, int max_tokens, uint64_t* request_id) {
+    if (!b || (n > 0 && !tokens) || n < 0 || max_tokens < 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_submit: bad argument");
+    if (b->queue_count >= b->cfg.max_queue_depth) return fail(B200_ERR_OPERATION_FAILED, "queue full");
+    for (int i = 0; i < n; i++)
+        if (tokens[i] >= (uint32_t)b->c->d.vocab) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_submit: token id exceeds vocab size");
+    b->queue_count++;
+    BatchReq r;
+    r.id = b->next_id++;
+    r.tokens.assign(tokens, tokens + n);
+    r.max_tokens = max_tokens;
+    if (request_id) *request_id = r.id;
+    if ((int)b->active.size() < b->cfg.max_batch_size) batch_activate(b, std::move(r));
+    else b->pending.push_back(std::move(r));
+    return B200_OK;
+}
+
+static uint32_t host_argmax_last(const float* v, int n) {
+    int bi = 0;
+    float best = v[0];
+    for (int i = 1; i < n; i++)
+        if (v[i] >= best) { best = v[i]; bi = i; }
+    return (uint32_t)bi;
+}
+
+extern "C" int b200_batch_step(b200_batch* b, b200_batch_event* out, int cap, int* n_out) {
+    if (!b || (cap > 0 && !out) || cap < 0 || !n_out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_step: bad argument");
+    b200_ctx* c = b->c;
+    // step_sequence for every active sequence: who is finished, who prefills, who decodes
+    const size_t n_act = b->active.size();
+    std::vector<int> action(n_act, 0);   // 0 = finished before stepping, 1 = prompt, 2 = one token, 3 = error
+    std::vector<uint32_t> next(n_act, 0);
+    std::vector<std::string> err(n_act);
+    std::vector<int> dec_idx, dec_slots;
+    std::vector<uint32_t> dec_tokens;
+    for (size_t i = 0; i < n_act; i++) {
+        BatchSeq& s = b->active[i];
+        if (!s.tokens.empty() && s.tokens.back() == b->cfg.eos_token_id) continue;   // :373-377
+        if (s.generated >= s.max_tokens) continue;                                    // :379-381
+        if (!s.started) { action[i] = 1; continue; }
+        if (c->slots[s.slot].host_pos + 1 > (uint64_t)c->d.max_seq_len) { action[i] = 3; err[i] = "context length exceeded"; continue; }
+        action[i] = 2;
+        dec_idx.push_back((int)i);
+        dec_slots.push_back(s.slot);
+        dec_tokens.push_back(s.tokens.back());
+    }
+    if (!dec_idx.empty()) {   // every decoding sequence in ONE pass over the weights
+        std::vector<uint32_t> picked(dec_idx.size());
+        const int rc = b200_decode_batch_greedy(c, dec_slots.data(), dec_tokens.data(), (int)dec_idx.size(), picked.data());
+        for (size_t k = 0; k < dec_idx.size(); k++) {
+            if (rc) { action[dec_idx[k]] = 3; err[dec_idx[k]] = g_err; }
+            else next[dec_idx[k]] = picked[k];
+        }
+        b->batched_rows += dec_idx.size();
+    }
+    std::vector<float> logits;
+    for (size_t i = 0; i < n_act; i++) {   // prompts: ctx.position == 0 -> the whole prompt in one forward (:383-389)
+        if (action[i] != 1) continue;
+        BatchSeq& s = b->active[i];
+        logits.resize((size_t)c->d.vocab);
+        int rc = b200_reset(c, s.slot);
+        if (!rc) rc = b200_prefill(c, s.slot, s.tokens.data(), (int)s.tokens.size(), logits.data());
+        if (rc) { action[i] = 3; err[i] = g_err; continue; }
+        next[i] = host_argmax_last(logits.data(), c->d.vocab);
+        s.started = true;
+    }
+    b->steps++;
+    // results in the order of the active list, removals as Vec::remove (:241-289)
+    std::vector<BatchSeq> keep;
+    keep.reserve(n_act);
+    for (size_t i = 0; i < n_act; i++) {
+        BatchSeq& s = b->active[i];
+        bool done = action[i] == 0;
+        if (action[i] == 3) {
+            batch_event(b, s.id, B200_BATCH_ERROR, 0, B200_FINISH_ERROR, s.prompt_len, s.generated);
+            b->last_error = err[i];
+            b->free_slots.push_back(s.slot);
+            b->queue_count = std::max(0, b->queue_count - 1);
+            continue;
+        }
+        if (action[i] == 1 || action[i] == 2) {
+            s.tokens.push_back(next[i]);
+            s.generated++;
+            if (next[i] == b->cfg.eos_token_id) done = true;   // :397-399: EOS ends the sequence, no Token event for it
+            else batch_event(b, s.id, B200_BATCH_TOKEN, next[i], 0, s.prompt_len, s.generated);
+        }
+        if (done) {
+            batch_event(b, s.id, B200_BATCH_DONE, 0, s.generated >= s.max_tokens ? B200_FINISH_MAX_TOKENS : B200_FINISH_STOP, s.prompt_len, s.generated);
+            b->free_slots.push_back(s.slot);
+            b->queue_count = std::max(0, b->queue_count - 1);
+            continue;
+        }
+        keep.push_back(std::move(s));
+    }
+    b->active.swap(keep);
+    while ((int)b->active.size() < b->cfg.max_batch_size && !b->pending.empty()) {   // :291-304 (pending.pop(): newest first)
+        BatchReq r = std::move(b->pending.back());
+        b->pending.pop_back();
+        batch_activate(b, std::move(r));
+    }
+    const int n = std::min<int>(cap, (int)b->events.size());
+    for (int i = 0; i < n; i++) out[i] = b->events[i];
+    b->events.erase(b->events.begin(), b->events.begin() + n);
+    *n_out = n;
+    return B200_OK;
+}
+
+extern "C" int b200_batch_counts(b200_batch* b, int* active, int* pending, int* undelivered_events, uint64_t* steps, uint64_t* decode_rows) {
+    if (!b) return fail(B200_ERR_INVALID_ARGUMENT, "b200_batch_counts: null batch");
+    if (active) *active = (int)b->active.size();
+    if (pending) *pending = (int)b->pending.size();
+    if (undelivered_events) *undelivered_events = (int)b->events.size();
+    if (steps) *steps = b->steps;
+    if (decode_rows) *decode_rows = b->batched_rows;
+    return B200_OK;
+}
+extern "C" const char* b200_batch_last_error(b200_batch* b) { return b ? b->last_error.c_str() : ""; }

@@ -112,122 +112,177 @@ struct AttnQ8Params {
     float scale;
 };
 
-// One warp per (kv head, split): the G query heads of the group share every K / V row read; four positions per step;
-// block-wise online softmax (as attn_decode_item).  grid (n_splits, n_kv), 32 threads.
-template <int VEC, int GMAX>
-__global__ void __launch_bounds__(32) attn_q8_split_kernel(const AttnQ8Params p) {
-    constexpr int HD = 32 * VEC, UB = 4;
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x, split = blockIdx.x, kh = blockIdx.y, G = p.G;
-    const int kv_len = *p.pos + 1;
-    const int chunk = (kv_len + p.n_splits - 1) / p.n_splits;
-    const int p_begin = split * chunk, p_end = min(kv_len, p_begin + chunk);
-    float q[GMAX][VEC], acc[GMAX][VEC], m[GMAX], l[GMAX];
+// 16 int8 values (one 16-byte load) -> 16 floats without I2F (quarter rate): x ^ 0x80 is the unsigned byte x + 128, PRMT drops it
+// into the mantissa of 2^23 (0x4B000000 | u = 2^23 + u exactly), one FADD removes 2^23 + 128.
+__device__ __forceinline__ void kv_q8_unpack16(const int4 raw, float (&f)[16]) {
+    const uint32_t w[4] = {(uint32_t)raw.x ^ 0x80808080u, (uint32_t)raw.y ^ 0x80808080u, (uint32_t)raw.z ^ 0x80808080u, (uint32_t)raw.w ^ 0x80808080u};
 #pragma unroll
-    for (int g = 0; g < GMAX; g++) {
-        m[g] = -INFINITY;
-        l[g] = 0.0f;
-#pragma unroll
-        for (int v = 0; v < VEC; v++) {
-            acc[g][v] = 0.0f;
-            q[g][v] = g < G ? p.q[(size_t)(kh * G + g) * HD + lane * VEC + v] : 0.0f;
-        }
-    }
-    const signed char* kb = p.k8 + (size_t)kh * p.max_seq * HD + lane * VEC;
-    const signed char* vb = p.v8 + (size_t)kh * p.max_seq * HD + lane * VEC;
-    const float* ksc = p.k_scale + (size_t)kh * p.max_seq;
-    const float* vsc = p.v_scale + (size_t)kh * p.max_seq;
-    for (int pos = p_begin; pos < p_end; pos += UB) {
-        float kr[UB][VEC], vr[UB][VEC];
-#pragma unroll
-        for (int u = 0; u < UB; u++) {
-            const int pc = min(pos + u, p_end - 1);   // clamped: stays in range, masked below
-            const float ks = ksc[pc], vs = vsc[pc];
-            if constexpr (VEC == 4) {
-                const char4 a = *reinterpret_cast<const char4*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const char4*>(vb + (size_t)pc * HD);
-                kr[u][0] = __fmul_rn((float)a.x, ks); kr[u][1] = __fmul_rn((float)a.y, ks); kr[u][2] = __fmul_rn((float)a.z, ks); kr[u][3] = __fmul_rn((float)a.w, ks);
-                vr[u][0] = __fmul_rn((float)b.x, vs); vr[u][1] = __fmul_rn((float)b.y, vs); vr[u][2] = __fmul_rn((float)b.z, vs); vr[u][3] = __fmul_rn((float)b.w, vs);
-            } else {
-                const char2 a = *reinterpret_cast<const char2*>(kb + (size_t)pc * HD), b = *reinterpret_cast<const char2*>(vb + (size_t)pc * HD);
-                kr[u][0] = __fmul_rn((float)a.x, ks); kr[u][1] = __fmul_rn((float)a.y, ks);
-                vr[u][0] = __fmul_rn((float)b.x, vs); vr[u][1] = __fmul_rn((float)b.y, vs);
-            }
-        }
-        float s[UB][GMAX];
-#pragma unroll
-        for (int u = 0; u < UB; u++)
-#pragma unroll
-            for (int g = 0; g < GMAX; g++) {
-                float d = 0.0f;
-#pragma unroll
-                for (int v = 0; v < VEC; v++) d = fmaf(q[g][v], kr[u][v], d);
-                s[u][g] = d;
-            }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int u = 0; u < UB; u++)
-#pragma unroll
-                for (int g = 0; g < GMAX; g++) s[u][g] += __shfl_xor_sync(0xffffffffu, s[u][g], o);
-#pragma unroll
-        for (int g = 0; g < GMAX; g++) {
-            if (g < G) {
-                float mb = -INFINITY;
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    s[u][g] = (pos + u < p_end) ? s[u][g] * p.scale : -INFINITY;
-                    mb = fmaxf(mb, s[u][g]);
-                }
-                const float mn = fmaxf(m[g], mb);
-                const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
-                float w[UB], ws = 0.0f;
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    w[u] = (s[u][g] == -INFINITY) ? 0.0f : expf(s[u][g] - mn);
-                    ws += w[u];
-                }
-                l[g] = l[g] * corr + ws;
-#pragma unroll
-                for (int v = 0; v < VEC; v++) {
-                    float a = acc[g][v] * corr;
-#pragma unroll
-                    for (int u = 0; u < UB; u++) a = fmaf(w[u], vr[u][v], a);
-                    acc[g][v] = a;
-                }
-                m[g] = mn;
-            }
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < GMAX; g++) {
-        if (g < G) {
-            float* dst = p.part + (((size_t)kh * p.n_splits + split) * G + g) * (HD + 2);
-#pragma unroll
-            for (int v = 0; v < VEC; v++) dst[lane * VEC + v] = acc[g][v];
-            if (lane == 0) { dst[HD] = m[g]; dst[HD + 1] = l[g]; }
-        }
+    for (int i = 0; i < 4; i++) {
+        f[4 * i + 0] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7650)) - 8388736.0f;
+        f[4 * i + 1] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7651)) - 8388736.0f;
+        f[4 * i + 2] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7652)) - 8388736.0f;
+        f[4 * i + 3] = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7653)) - 8388736.0f;
     }
 }
 
-// out[head][:] = sum_s acc_s e^(m_s - m) / sum_s l_s e^(m_s - m), splits in order.  grid n_heads, hd threads.
+constexpr int kAttnQ8Warps = 4;
+constexpr int kAttnQ8Unroll = 4;
+
+// One CTA of 4 warps per (kv head, split).  A lane owns 16 consecutive dims of a row (one 16-byte load of K, one of V), so a warp
+// reads 32 / (HD / 16) whole rows per instruction and a score costs log2(HD / 16) shuffles per head instead of 5 per position;
+// every (warp, row group) is an independent online-softmax stream over every STRIDE-th position of the split (no communication
+// inside the loop, kAttnQ8Unroll positions of loads in flight per stream), merged at the end: across the row groups by shuffles,
+// across the warps through shared memory.  HG <= 4 query heads per warp: a group of 8 heads is two head groups on two warp pairs
+// (both read the same rows; the second read hits L1 / L2).  The row scale is applied once per score (K) and folded into the
+// softmax weight (V).  grid (n_splits, n_kv), 128 threads.
+template <int HD, int HG>
+__global__ void __launch_bounds__(kAttnQ8Warps * 32, 2) attn_q8_split_kernel(const AttnQ8Params p) {
+    constexpr int LPR = HD / 16, RPW = 32 / LPR, U = kAttnQ8Unroll;
+    __shared__ float sm[kAttnQ8Warps][HG][HD + 2];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, split = blockIdx.x, kh = blockIdx.y, G = p.G;
+    const int NHG = (G + HG - 1) / HG, WPG = kAttnQ8Warps / NHG;   // head groups (1 or 2), warps per head group
+    const int hgp = warp % NHG, wsub = warp / NHG, sub = lane % LPR, rg = lane / LPR;
+    const int kv_len = *p.pos + 1;
+    const int chunk = (kv_len + p.n_splits - 1) / p.n_splits;
+    const int p_begin = split * chunk, p_end = min(kv_len, p_begin + chunk);
+    const int stride = WPG * RPW;
+    float q[HG][16], acc[HG][16], m[HG], l[HG];
+#pragma unroll
+    for (int g = 0; g < HG; g++) {
+        const int head = hgp * HG + g;
+        m[g] = -INFINITY;
+        l[g] = 0.0f;
+#pragma unroll
+        for (int v = 0; v < 16; v += 4) {
+            const float4 t = head < G ? *reinterpret_cast<const float4*>(p.q + (size_t)(kh * G + head) * HD + sub * 16 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[g][v] = t.x; q[g][v + 1] = t.y; q[g][v + 2] = t.z; q[g][v + 3] = t.w;
+            acc[g][v] = acc[g][v + 1] = acc[g][v + 2] = acc[g][v + 3] = 0.0f;
+        }
+    }
+    const signed char* kb = p.k8 + (size_t)kh * p.max_seq * HD + sub * 16;
+    const signed char* vb = p.v8 + (size_t)kh * p.max_seq * HD + sub * 16;
+    const float* ksc = p.k_scale + (size_t)kh * p.max_seq;
+    const float* vsc = p.v_scale + (size_t)kh * p.max_seq;
+    if (p_begin < p_end) {
+        for (int base = p_begin + wsub * RPW; base < p_end; base += U * stride) {   // warp-uniform trip count (shuffles inside)
+            const int pos0 = base + rg;
+            int4 kr[U], vr[U];
+            float ks[U], vs[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {   // every load of the step first (clamped: stays in range, masked below)
+                const int pc = min(pos0 + u * stride, p_end - 1);
+                kr[u] = *reinterpret_cast<const int4*>(kb + (size_t)pc * HD);
+                vr[u] = *reinterpret_cast<const int4*>(vb + (size_t)pc * HD);
+                ks[u] = ksc[pc];
+                vs[u] = vsc[pc];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool valid = pos0 + u * stride < p_end;
+                float f[16], s[HG];
+                kv_q8_unpack16(kr[u], f);
+#pragma unroll
+                for (int g = 0; g < HG; g++) {
+                    float d = 0.0f;
+#pragma unroll
+                    for (int v = 0; v < 16; v++) d = fmaf(q[g][v], f[v], d);
+                    s[g] = d;
+                }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+                    for (int g = 0; g < HG; g++) s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+                kv_q8_unpack16(vr[u], f);
+#pragma unroll
+                for (int g = 0; g < HG; g++) {
+                    const float sg = valid ? s[g] * ks[u] * p.scale : -INFINITY;
+                    const float mn = fmaxf(m[g], sg);
+                    const float corr = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn);
+                    const float w = valid ? expf(sg - mn) : 0.0f;
+                    const float wv = w * vs[u];
+                    l[g] = l[g] * corr + w;
+#pragma unroll
+                    for (int v = 0; v < 16; v++) acc[g][v] = fmaf(wv, f[v], acc[g][v] * corr);
+                    m[g] = mn;
+                }
+            }
+        }
+    }
+    // merge the RPW row-group streams of the warp (lanes with the same dims), then the WPG warps of the head group
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+        for (int g = 0; g < HG; g++) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m[g], o), l2 = __shfl_xor_sync(0xffffffffu, l[g], o);
+            const float mn = fmaxf(m[g], m2);
+            const float ca = (m[g] == -INFINITY) ? 0.0f : expf(m[g] - mn), cb = (m2 == -INFINITY) ? 0.0f : expf(m2 - mn);
+            l[g] = l[g] * ca + l2 * cb;
+#pragma unroll
+            for (int v = 0; v < 16; v++) acc[g][v] = acc[g][v] * ca + __shfl_xor_sync(0xffffffffu, acc[g][v], o) * cb;
+            m[g] = mn;
+        }
+    }
+    if (rg == 0) {
+#pragma unroll
+        for (int g = 0; g < HG; g++) {
+#pragma unroll
+            for (int v = 0; v < 16; v++) sm[warp][g][sub * 16 + v] = acc[g][v];
+            if (sub == 0) { sm[warp][g][HD] = m[g]; sm[warp][g][HD + 1] = l[g]; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * (HD + 1); i += blockDim.x) {   // element d < HD of head `head`, or (d == HD) its (m, l) pair
+        const int head = i / (HD + 1), d = i - head * (HD + 1);
+        const int hg2 = head / HG, g = head - hg2 * HG;
+        float mm = -INFINITY;
+        for (int w = 0; w < WPG; w++) mm = fmaxf(mm, sm[w * NHG + hg2][g][HD]);
+        float a = 0.0f, ll = 0.0f;
+        for (int w = 0; w < WPG; w++) {
+            const float* src = sm[w * NHG + hg2][g];
+            if (src[HD] == -INFINITY) continue;
+            const float c = expf(src[HD] - mm);
+            ll += src[HD + 1] * c;
+            a += src[d < HD ? d : 0] * c;
+        }
+        float* dst = p.part + (((size_t)kh * p.n_splits + split) * G + head) * (HD + 2);
+        if (d < HD) dst[d] = a;
+        else { dst[HD] = mm; dst[HD + 1] = ll; }
+    }
+}
+
+// out[head][:] = sum_s acc_s e^(m_s - m) / sum_s l_s e^(m_s - m), splits in order.  grid n_heads, hd threads.  The (m, l) pairs of
+// the splits are fetched by one thread each and the coefficients shared, so the loop over splits has no dependent load in it.
+constexpr int kAttnQ8MaxSplits = 128;
 __global__ void attn_q8_merge_kernel(const AttnQ8Params p, int hd) {
+    __shared__ float sc[kAttnQ8MaxSplits], sm_m[kAttnQ8MaxSplits], sm_l[kAttnQ8MaxSplits];
+    __shared__ float s_m, s_l;
     pdl_launch_dependents();
     pdl_wait();
     const int head = blockIdx.x, kh = head / p.G, g = head - kh * p.G, d = threadIdx.x;
     const float* base = p.part + (((size_t)kh * p.n_splits) * p.G + g) * (hd + 2);
     const size_t stride = (size_t)p.G * (hd + 2);
-    float m = -INFINITY;
-    for (int s = 0; s < p.n_splits; s++) m = fmaxf(m, base[s * stride + hd]);
-    float l = 0.0f, a = 0.0f;
-    for (int s = 0; s < p.n_splits; s++) {
-        const float ms = base[s * stride + hd];
-        if (ms == -INFINITY) continue;   // empty split
-        const float c = expf(ms - m);
-        l += base[s * stride + hd + 1] * c;
-        a += base[s * stride + d] * c;
+    for (int s = d; s < p.n_splits; s += blockDim.x) { sm_m[s] = base[s * stride + hd]; sm_l[s] = base[s * stride + hd + 1]; }
+    __syncthreads();
+    if (d == 0) {
+        float m = -INFINITY;
+        for (int s = 0; s < p.n_splits; s++) m = fmaxf(m, sm_m[s]);
+        s_m = m;
     }
-    p.out[(size_t)head * hd + d] = a / l;
+    __syncthreads();
+    for (int s = d; s < p.n_splits; s += blockDim.x) sc[s] = (sm_m[s] == -INFINITY) ? 0.0f : expf(sm_m[s] - s_m);
+    __syncthreads();
+    if (d == 0) {
+        float l = 0.0f;
+        for (int s = 0; s < p.n_splits; s++) l += sc[s] * sm_l[s];
+        s_l = l;
+    }
+    float a = 0.0f;
+#pragma unroll 8
+    for (int s = 0; s < p.n_splits; s++) a = fmaf(base[s * stride + d], sc[s], a);
+    __syncthreads();
+    p.out[(size_t)head * hd + d] = a / s_l;
 }
 
 }  // namespace b200

@@ -78,6 +78,39 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
     }
 }
 
+// The same pick for every row of a [rows][n] logits matrix (batched decode): one CTA per row, out[row] = LAST maximal index.
+__global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int n, int* __restrict__ out) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    const float* row = logits + (size_t)blockIdx.x * n;
+    float best = -INFINITY;
+    int bi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = row[i];
+        if (v >= best || bi < 0) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        best = threadIdx.x < nw ? s_v[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < nw ? s_i[threadIdx.x] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi > bi))) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) out[blockIdx.x] = bi;
+    }
+}
+
 // MoeRouter::route (src/model/moe.rs:128-198) with normalize=false: logits = W_r h (f32),
 // stable descending top-k (ties -> lowest expert index), softmax over the k selected.
 // One CTA; warp e computes logit e.  h is the (already RMS-normalised) FFN input.
