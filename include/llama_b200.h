@@ -189,6 +189,16 @@ B200_API int b200_prefill(b200_ctx* ctx, int seq, const uint32_t* tokens, int n,
 /* One token for each of n DISTINCT sequence slots;
  * logits_out is n x vocab. */
 B200_API int b200_decode_batch(b200_ctx* ctx, const int* seqs, const uint32_t* tokens, int n, float* logits_out);
+/* Greedy continuation behind b200_forward (opt-in, after finalize; one GPU, megakernel paths).  When on, b200_forward also picks
+ * argmax (last maximum wins, src/main.rs:1816-1821) on the device and launches the NEXT token on that pick before it returns.  If
+ * the next b200_forward of the sequence passes exactly that token -- what every greedy caller does, e.g. the reference's bench
+ * loop and a Sampler at temperature 0 -- its logits are already on their way and the host's turnaround (D2H, argmax, call
+ * overhead) overlaps the next token instead of idling the GPU; any other token, or any other entry point on the sequence, waits
+ * for the token in flight, discards it (the device position goes back; its KV rows lie beyond the position) and proceeds as
+ * usual.  Results are identical either way.  b200_position never counts a token in flight. */
+B200_API int b200_ctx_set_speculation(b200_ctx* ctx, int on);
+B200_API int b200_ctx_speculation_stats(b200_ctx* ctx, int* enabled, uint64_t* hits, uint64_t* misses);
+
 /* b200_decode_batch with the greedy pick (last maximum wins, src/main.rs:1816-1821) made on the device: next_out receives n token
  * ids instead of n x vocab logits. */
 B200_API int b200_decode_batch_greedy(b200_ctx* ctx, const int* seqs, const uint32_t* tokens, int n, uint32_t* next_out);
@@ -250,6 +260,8 @@ B200_API int b200_debug_mega_phase(b200_ctx* ctx, int phase, unsigned long long*
 /* Watchdog words of the tensor-pipe / megakernel paths: out8[0] = 0 when no bounded wait ever gave up, else
  * (code, which wait, CTA, sequence number); clears them. */
 B200_API int b200_debug_err(b200_ctx* ctx, int* out8);
+/* Lab: take the first `pos` positions of the slot's KV cache as valid as they are (attention at depth without a prompt). */
+B200_API int b200_debug_set_position(b200_ctx* ctx, int seq, uint64_t pos);
 /* Decode path chosen by b200_ctx_finalize: 0 = CUDA graph of per-op kernels, 1 = per-token megakernel,
  * 2 = streamed megakernel (TMA producer warp + mbarrier ring, csrc/stream.cuh). */
 B200_API int b200_ctx_path(b200_ctx* ctx, int* out);

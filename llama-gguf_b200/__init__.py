@@ -122,6 +122,9 @@ def lib():
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_ctx_destroy.restype = None
     u32p, i32p, szp = C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_size_t)
+    L.b200_ctx_set_speculation.argtypes = [vp, C.c_int]
+    L.b200_ctx_speculation_stats.argtypes = [vp, i32p, u64p, u64p]
+    L.b200_debug_set_position.argtypes = [vp, C.c_int, C.c_uint64]
     L.b200_decode_batch_greedy.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
     L.b200_batch_create.argtypes = [vp, C.POINTER(BatchConfig), C.POINTER(vp)]
     L.b200_batch_destroy.argtypes = [vp]
@@ -722,6 +725,19 @@ class GpuOnlyInference:
         _check(lib().b200_decode_batch(self._h, seqs.ctypes.data_as(C.POINTER(C.c_int)),
                                        toks.ctypes.data_as(C.POINTER(C.c_uint32)), seqs.size, _fp(logits)))
         return logits
+
+    def set_speculation(self, on=True):
+        """Greedy continuation behind forward() (b200_ctx_set_speculation): the device picks argmax and starts the next token
+        before forward() returns; a caller that feeds that token back finds its logits already on the way."""
+        _check(lib().b200_ctx_set_speculation(self._h, 1 if on else 0))
+
+    def speculation_stats(self):
+        en, h, m = C.c_int(), C.c_uint64(), C.c_uint64()
+        _check(lib().b200_ctx_speculation_stats(self._h, C.byref(en), C.byref(h), C.byref(m)))
+        return dict(enabled=bool(en.value), hits=h.value, misses=m.value)
+
+    def debug_set_position(self, pos, seq=0):
+        _check(lib().b200_debug_set_position(self._h, seq, int(pos)))
 
     def decode_batch_greedy(self, seqs, tokens):
         """b200_decode_batch_greedy: the next token of every sequence, picked on the device (last maximum wins)."""

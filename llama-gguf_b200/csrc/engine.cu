@@ -109,6 +109,8 @@ struct Slot {
     signed char* kv8 = nullptr;   // int8 KV format (kv_int8.cuh): [L][2][n_kv][max_seq][hd] bytes ...
     float* kv_scale = nullptr;    // ... and [L][2][n_kv][max_seq] scales; kv stays null
     uint64_t host_pos = 0;
+    bool spec = false;            // greedy continuation (b200_ctx_set_speculation): the NEXT token is already in flight ...
+    int spec_buf = 0;             // ... its logits land in h_spec_logits[spec_buf], the token it consumed in h_spec_pick[spec_buf]
     cudaGraphExec_t graph[MODE_COUNT] = {nullptr, nullptr, nullptr};
     uint64_t graph_launches[MODE_COUNT] = {0, 0, 0};
     MegaPhase* d_phases = nullptr;  // per-token megakernel program of this slot (mega.cuh)
@@ -163,6 +165,14 @@ struct b200_ctx {
     // zeroed once, tensors carved out at 256-byte boundaries with the 256 zero bytes behind each that the kernels' tail reads expect
     uint8_t* arena = nullptr;
     size_t arena_size = 0, arena_off = 0;
+    // Greedy continuation behind b200_forward (opt-in): after the logits of token t the device picks argmax (last maximum wins) and
+    // starts token t + 1 at once; if the caller's next token is that pick -- every greedy caller -- its logits are already on the way
+    // and the host's turnaround (D2H, argmax, call overhead) overlaps the next token instead of idling the GPU.
+    bool speculate = false;
+    float* h_spec_logits[2] = {nullptr, nullptr};
+    int* h_spec_pick = nullptr;   // pinned [2]
+    cudaEvent_t spec_ev[2] = {nullptr, nullptr};
+    uint64_t spec_hits = 0, spec_misses = 0;
     int kv_format = 0;            // 0 = f32 (model/mod.rs:83-108), 1 = int8 (model/kv_quantized.rs Int8): B200_KV_FORMAT / b200_ctx_set_kv_format
     float* attn_q8_part = nullptr;
     int attn_q8_splits = 0;
@@ -776,6 +786,11 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (c->h_logits) cudaFreeHost(c->h_logits);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_token) cudaFreeHost(c->h_token);
+    for (int b = 0; b < 2; b++) {
+        if (c->h_spec_logits[b]) cudaFreeHost(c->h_spec_logits[b]);
+        if (c->spec_ev[b]) cudaEventDestroy(c->spec_ev[b]);
+    }
+    if (c->h_spec_pick) cudaFreeHost(c->h_spec_pick);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1878,11 +1893,24 @@ static int run_token(b200_ctx* c, int slot_i, Mode mode) {
     return B200_OK;
 }
 
+// A speculative token that nobody will ask for: wait for it, then put the device position back to the last accepted token (the KV
+// rows it wrote lie beyond the position and are overwritten by the next real token).
+static int spec_drain(b200_ctx* c, int seq) {
+    Slot& sl = c->slots[seq];
+    if (!sl.spec) return B200_OK;
+    sl.spec = false;
+    c->spec_misses++;
+    CU(cudaSetDevice(c->par.device));
+    CU(cudaStreamSynchronize(c->stream));
+    const int pos = (int)sl.host_pos;
+    CU(cudaMemcpy(&sl.d_state->pos_next, &pos, sizeof(int), cudaMemcpyHostToDevice));
+    return B200_OK;
+}
 static int check_slot(b200_ctx* c, int seq, const char* fn) {
     if (!c) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": null ctx");
     if (!c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": context not finalized");
     if (seq < 0 || seq >= (int)c->slots.size()) return fail(B200_ERR_INVALID_ARGUMENT, std::string(fn) + ": bad sequence slot");
-    return B200_OK;
+    return spec_drain(c, seq);   // (every entry point but b200_forward's hit path and b200_position starts from a settled slot)
 }
 static int check_token(b200_ctx* c, int seq, uint32_t token, const char* fn) {
     if (token >= (uint32_t)c->d.vocab)
@@ -1945,9 +1973,40 @@ extern "C" int b200_ctx_kv_format(b200_ctx* c, int* out) {
     return B200_OK;
 }
 
+// argmax of the logits just produced -> st->token, its value to the host, the next token launched on it, its logits to h_spec_logits[buf]
+static int spec_enqueue(b200_ctx* c, int seq, int buf) {
+    Slot& sl = c->slots[seq];
+    if (!c->speculate || !c->mega_ok || c->par.world_size > 1 || c->use_taps || sl.host_pos + 2 > (uint64_t)c->d.max_seq_len) return B200_OK;
+    argmax_kernel<<<1, 1024, 0, c->stream>>>((const float*)c->logits, c->d.vocab, sl.d_state, sl.d_generated, 0);
+    CU(cudaMemcpyAsync(&c->h_spec_pick[buf], &sl.d_state->token, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int rc;
+    if ((rc = mega_launch(c, seq, MEGA_LOGITS, 1))) return rc;
+    CU(cudaMemcpyAsync(c->h_spec_logits[buf], c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
+    WATCHDOG_FETCH(c);
+    CU(cudaEventRecord(c->spec_ev[buf], c->stream));
+    c->launches++;
+    sl.spec = true;
+    sl.spec_buf = buf;
+    return B200_OK;
+}
+
 extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_out) {
     int rc;
-    if ((rc = check_slot(c, seq, "b200_forward"))) return rc;
+    if (c && c->finalized && seq >= 0 && seq < (int)c->slots.size() && c->slots[seq].spec && logits_out) {
+        Slot& sl = c->slots[seq];
+        const int buf = sl.spec_buf;
+        CU(cudaSetDevice(c->par.device));
+        CU(cudaEventSynchronize(c->spec_ev[buf]));
+        if ((uint32_t)c->h_spec_pick[buf] == token && !c->h_err[0]) {   // hit: the token in flight IS this call's token
+            sl.spec = false;
+            sl.host_pos++;
+            c->spec_hits++;
+            if ((rc = spec_enqueue(c, seq, buf ^ 1))) return rc;        // keep the device busy while the host copies and picks
+            memcpy(logits_out, c->h_spec_logits[buf], (size_t)c->vocab_l * 4);
+            return B200_OK;
+        }
+    }
+    if ((rc = check_slot(c, seq, "b200_forward"))) return rc;               // (drains a speculation that missed)
     if (!logits_out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_forward: null logits_out");
     if ((rc = flush_pending(c, seq))) return rc;
     if ((rc = check_token(c, seq, token, "b200_forward"))) return rc;
@@ -1955,6 +2014,19 @@ extern "C" int b200_forward(b200_ctx* c, int seq, uint32_t token, float* logits_
     Slot& sl = c->slots[seq];
     if ((rc = set_token(c, sl, token))) return rc;
     if ((rc = run_token(c, seq, MODE_LOGITS))) return rc;
+    if (c->speculate && c->mega_ok && c->par.world_size == 1 && !c->use_taps) {
+        for (int o = 0; o < (int)c->slots.size(); o++)      // the staging buffers are the context's: one sequence runs ahead at a time
+            if (o != seq && (rc = spec_drain(c, o))) return rc;
+        CU(cudaMemcpyAsync(c->h_spec_logits[0], c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
+        WATCHDOG_FETCH(c);
+        CU(cudaEventRecord(c->spec_ev[0], c->stream));
+        sl.host_pos++;                                                       // (spec_enqueue looks at the position after this token)
+        if ((rc = spec_enqueue(c, seq, 1))) { sl.host_pos--; return rc; }
+        CU(cudaEventSynchronize(c->spec_ev[0]));
+        if ((rc = watchdog_check(c, "b200_forward"))) { sl.host_pos--; return rc; }
+        memcpy(logits_out, c->h_spec_logits[0], (size_t)c->vocab_l * 4);
+        return B200_OK;
+    }
     // tensor parallel: this rank's slice [rank * vocab/P, (rank+1) * vocab/P) of the logits (the caller gathers)
     CU(cudaMemcpyAsync(c->h_logits, c->logits, (size_t)c->vocab_l * 4, cudaMemcpyDeviceToHost, c->stream));
     WATCHDOG_FETCH(c);
@@ -2063,9 +2135,8 @@ extern "C" int b200_reset(b200_ctx* c, int seq) {
 }
 
 extern "C" int b200_position(b200_ctx* c, int seq, uint64_t* out) {
-    int rc;
-    if ((rc = check_slot(c, seq, "b200_position"))) return rc;
-    if (!out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_position: null out");
+    if (!c || !c->finalized || seq < 0 || seq >= (int)c->slots.size()) return fail(B200_ERR_INVALID_ARGUMENT, "b200_position: bad argument");
+    if (!out) return fail(B200_ERR_INVALID_ARGUMENT, "b200_position: null out");   // (host-side count of accepted tokens: a token in flight does not count)
     *out = c->slots[seq].host_pos + c->slots[seq].pending.size();   // queued prefill tokens count (GpuInference::position)
     return B200_OK;
 }
@@ -3393,3 +3464,44 @@ extern "C" int b200_batch_counts(b200_batch* b, int* active, int* pending, int* 
     return B200_OK;
 }
 extern "C" const char* b200_batch_last_error(b200_batch* b) { return b ? b->last_error.c_str() : ""; }
+
+
+// ------------------------------------------------------------------ greedy continuation + lab positioning
+extern "C" int b200_ctx_set_speculation(b200_ctx* c, int on) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_set_speculation: null ctx");
+    if (!c->finalized) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_set_speculation: finalize the context first");
+    for (int s = 0; s < (int)c->slots.size(); s++) {
+        const int rc = spec_drain(c, s);
+        if (rc) return rc;
+    }
+    if (on && !c->h_spec_pick) {
+        CU(cudaSetDevice(c->par.device));
+        for (int b = 0; b < 2; b++) {
+            CU_ALLOC(cudaHostAlloc((void**)&c->h_spec_logits[b], (size_t)c->vocab_l * 4, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&c->spec_ev[b], cudaEventDisableTiming));
+        }
+        CU_ALLOC(cudaHostAlloc((void**)&c->h_spec_pick, 2 * sizeof(int), cudaHostAllocDefault));
+    }
+    c->speculate = on != 0;
+    return B200_OK;
+}
+extern "C" int b200_ctx_speculation_stats(b200_ctx* c, int* enabled, uint64_t* hits, uint64_t* misses) {
+    if (!c) return fail(B200_ERR_INVALID_ARGUMENT, "b200_ctx_speculation_stats: null ctx");
+    if (enabled) *enabled = (c->speculate && c->mega_ok && c->par.world_size == 1 && !c->use_taps) ? 1 : 0;
+    if (hits) *hits = c->spec_hits;
+    if (misses) *misses = c->spec_misses;
+    return B200_OK;
+}
+// Lab: declare the first `pos` positions of the slot's KV cache valid as they are (timing attention at depth without a prompt).
+extern "C" int b200_debug_set_position(b200_ctx* c, int seq, uint64_t pos) {
+    int rc;
+    if ((rc = check_slot(c, seq, "b200_debug_set_position"))) return rc;
+    if (pos >= (uint64_t)c->d.max_seq_len) return fail(B200_ERR_INVALID_ARGUMENT, "b200_debug_set_position: beyond the context");
+    if ((rc = flush_pending(c, seq))) return rc;
+    CU(cudaSetDevice(c->par.device));
+    CU(cudaStreamSynchronize(c->stream));
+    const int p = (int)pos;
+    CU(cudaMemcpy(&c->slots[seq].d_state->pos_next, &p, sizeof(int), cudaMemcpyHostToDevice));
+    c->slots[seq].host_pos = pos;
+    return B200_OK;
+}
