@@ -394,8 +394,39 @@ def main():
                                       "weight_stream_GBps": ach_b, "frac": ach_b / peaks["hbm_gbs"],
                                       "what": f"b200_decode_batch, {nb} sequences, host tokens in / host logits out every step "
                                               "(wall clock): one pass over the weights per step (tcgen05 dequant-GEMM path)"}
+            # the same pass with the greedy pick made on the device (what the continuous-batching engine calls): n ids back, not n x vocab logits
+            for _ in range(args.warmup):
+                btoks = gpu.decode_batch_greedy(seqs, btoks)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            for _ in range(nsteps_b):
+                btoks = gpu.decode_batch_greedy(seqs, btoks)
+            torch.cuda.synchronize()
+            sg = time.perf_counter() - tb
+            ach_g = wbytes / (sg / nsteps_b) / 1e9
+            extras["decode_batch_greedy"] = {"batch": nb, "value": nb * nsteps_b / sg, "unit": UNIT, "ms_per_step": sg / nsteps_b * 1e3,
+                                             "weight_stream_GBps": ach_g, "frac": ach_g / peaks["hbm_gbs"],
+                                             "what": f"b200_decode_batch_greedy, {nb} sequences, host tokens in / host token ids out every step "
+                                                     "(wall clock): the same GEMM pass, argmax of every row on the device"}
+            # continuous batching end to end (b200_batch_*): 2 x nb requests of 16-token prompts, 32 new tokens each, nb slots
+            eng = B.BatchedEngine(gpu, max_batch_size=nb, max_seq_len=args.ctx, max_queue_depth=4 * nb, eos_token_id=desc["vocab"] - 1)
+            for r in range(2 * nb):
+                eng.submit([((i + r) * 7919 + 1) % (desc["vocab"] - 1) for i in range(16)], 32)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            ev = eng.run()
+            torch.cuda.synchronize()
+            se = time.perf_counter() - tb
+            ntok = sum(1 for e in ev if e[0] == "token")
+            cnt = eng.counts()
+            eng.close()
+            extras["batched_engine"] = {"requests": 2 * nb, "slots": nb, "generated_tokens": ntok, "seconds": se, "value": ntok / se, "unit": UNIT,
+                                        "steps": cnt["steps"], "decode_rows": cnt["decode_rows"],
+                                        "what": "b200_batch_submit / b200_batch_step until every request is done: prompts through b200_prefill, all "
+                                                "running sequences of a step in one b200_decode_batch_greedy pass (wall clock, prompts included)"}
         except Exception as e:
-            extras["decode_batch"] = {"error": str(e)}
+            extras.setdefault("decode_batch", {"error": str(e)})
+            extras["batch_error"] = str(e)
 
     # ---- prefill: the whole prompt through the batch entry point (tcgen05 dequant-GEMM, csrc/gemm_umma.cuh) ----
     prefill = None

@@ -45,19 +45,15 @@ __device__ __forceinline__ float kv_q8_row(const float (&x)[VEC], signed char (&
 }
 
 // One warp per head unit: n_heads query heads (rotated in place), n_kv key heads (rotated, quantised, stored), n_kv value heads
-// (quantised, stored).  Rotation arithmetic as rope_kv_kernel (ops.rs:1216-1337).  HD = 32 * VEC.
+// (quantised, stored).  Rotation arithmetic as rope_kv_kernel (ops.rs:1216-1337).  HD = 32 * VEC.  `q`, `k`, `v` are the rows of ONE
+// token, `pos` its position.
 template <int VEC>
-__global__ void rope_kv_q8_kernel(const RopeKvQ8Params p) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31, unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void rope_kv_q8_unit(const RopeKvQ8Params& p, float* q, const float* k, const float* v, int pos, int unit, int lane) {
     const int hd = 32 * VEC, half = hd >> 1;
-    if (unit >= p.n_heads + 2 * p.n_kv) return;
-    const int pos = *p.pos;
     const float position = (float)pos / p.rope_scale;
     if (unit < p.n_heads + p.n_kv) {
         const bool is_q = unit < p.n_heads;
-        const float* src = is_q ? p.q + (size_t)unit * hd : p.k + (size_t)(unit - p.n_heads) * hd;
+        const float* src = is_q ? q + (size_t)unit * hd : k + (size_t)(unit - p.n_heads) * hd;
         float r[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; i++) {
@@ -75,7 +71,7 @@ __global__ void rope_kv_q8_kernel(const RopeKvQ8Params p) {
         __syncwarp();   // every lane has read its operands before anybody overwrites q in place
         if (is_q) {
 #pragma unroll
-            for (int i = 0; i < VEC; i++) p.q[(size_t)unit * hd + lane * VEC + i] = r[i];
+            for (int i = 0; i < VEC; i++) q[(size_t)unit * hd + lane * VEC + i] = r[i];
         } else {
             const int kh = unit - p.n_heads;
             signed char qv[VEC];
@@ -89,13 +85,68 @@ __global__ void rope_kv_q8_kernel(const RopeKvQ8Params p) {
         const int kh = unit - p.n_heads - p.n_kv;
         float r[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; i++) r[i] = p.v[(size_t)kh * hd + lane * VEC + i];
+        for (int i = 0; i < VEC; i++) r[i] = v[(size_t)kh * hd + lane * VEC + i];
         signed char qv[VEC];
         const float scale = kv_q8_row<VEC>(r, qv);
         signed char* dst = p.v8 + ((size_t)kh * p.max_seq + pos) * hd + lane * VEC;
 #pragma unroll
         for (int i = 0; i < VEC; i++) dst[i] = qv[i];
         if (lane == 0) p.v_scale[(size_t)kh * p.max_seq + pos] = scale;
+    }
+}
+
+template <int VEC>
+__global__ void rope_kv_q8_kernel(const RopeKvQ8Params p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= p.n_heads + 2 * p.n_kv) return;
+    rope_kv_q8_unit<VEC>(p, p.q, p.k, p.v, *p.pos, unit, lane);
+}
+
+// The same for the T rows of a prompt chunk (tensor-core prefill): row t = [q | k | v] of the token at position pos0 + t, `ld`
+// floats apart (p.q = the first row; p.k / p.v / p.pos unused).  grid (ceil(units / 4), T), 128 threads.
+template <int VEC>
+__global__ void prefill_rope_kv_q8_kernel(const RopeKvQ8Params p, int ld, int pos0) {
+    const int lane = threadIdx.x & 31, unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, t = blockIdx.y;
+    if (unit >= p.n_heads + 2 * p.n_kv) return;
+    const int hd = 32 * VEC;
+    float* q = p.q + (size_t)t * ld;
+    const float* k = q + (size_t)p.n_heads * hd;
+    const float* v = k + (size_t)p.n_kv * hd;
+    rope_kv_q8_unit<VEC>(p, q, k, v, pos0 + t, unit, lane);
+}
+
+// fp16 hi / lo pairs of one layer's DEQUANTISED cache rows 0 .. kv_end-1 for the tensor-core prefill attention: the int8 peer of
+// prefill_kv16_kernel (attn_umma.cuh), same output layout (K16[kv][pos][hd], Vt16[kv][hd][pos], lo halves after the hi halves).
+// The attention of the chunk then sees q * scale for every position, its own included -- what attention over a
+// QuantizedKVCache sees (kv_quantized.rs:230-310).  grid (kv_pad / 64, n_kv), 256 threads.
+template <int HD>
+__global__ void __launch_bounds__(256) prefill_kv16_q8_kernel(const signed char* __restrict__ k8, const signed char* __restrict__ v8,
+                                                              const float* __restrict__ k_scale, const float* __restrict__ v_scale, int max_seq,
+                                                              int kv_end, int P, __half* __restrict__ k16, __half* __restrict__ vt16) {
+    __shared__ __half tile[64][HD + 2], tile_lo[64][HD + 2];
+    const int kh = blockIdx.y, n_kv = gridDim.y, p0 = blockIdx.x * 64;
+    const signed char* ks = k8 + (size_t)kh * max_seq * HD;
+    const signed char* vs = v8 + (size_t)kh * max_seq * HD;
+    const float* ksc = k_scale + (size_t)kh * max_seq;
+    const float* vsc = v_scale + (size_t)kh * max_seq;
+    for (int i = threadIdx.x; i < 64 * HD; i += 256) {
+        const int pr = i / HD, d = i - pr * HD, pos = p0 + pr;
+        const bool ok = pos < kv_end;
+        const float k = ok ? fminf(fmaxf(__fmul_rn((float)ks[(size_t)pos * HD + d], ksc[pos]), -65504.0f), 65504.0f) : 0.0f;
+        const float v = ok ? fminf(fmaxf(__fmul_rn((float)vs[(size_t)pos * HD + d], vsc[pos]), -65504.0f), 65504.0f) : 0.0f;
+        const __half khi = __float2half_rn(k), vhi = __float2half_rn(v);
+        k16[((size_t)kh * P + pos) * HD + d] = khi;
+        k16[((size_t)(n_kv + kh) * P + pos) * HD + d] = __float2half_rn(k - __half2float(khi));
+        tile[pr][d] = vhi;
+        tile_lo[pr][d] = __float2half_rn(v - __half2float(vhi));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * HD; i += 256) {
+        const int d = i >> 6, pr = i & 63;
+        vt16[((size_t)kh * HD + d) * P + p0 + pr] = tile[pr][d];
+        vt16[((size_t)(n_kv + kh) * HD + d) * P + p0 + pr] = tile_lo[pr][d];
     }
 }
 

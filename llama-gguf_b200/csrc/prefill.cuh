@@ -48,7 +48,8 @@ __global__ void prefill_rope_kv_kernel(const PrefillRopeParams p) {
     float* row = p.qkv + (size_t)t * p.ld;
     const float* kraw = row + (size_t)p.n_heads * p.hd;
     const float* vraw = kraw + (size_t)p.n_kv * p.hd;
-    for (int i = threadIdx.x; i < n_pairs + n_v; i += blockDim.x) {
+    // gridDim.y CTAs share a token's items (each item is independent: same arithmetic whoever computes it)
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n_pairs + n_v; i += blockDim.x * gridDim.y) {
         if (i < n_pairs) {
             const int head = i / half, pi = i - head * half;
             const float theta = position * p.freq[pi];
@@ -195,12 +196,43 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
 
 // RMSNorm of T rows, output rounded to fp16 for the tensor-core GEMM that consumes it (same f32 arithmetic as
 // rms_norm_rows_kernel: ss = sum x^2, inv = 1/sqrt(ss/n + eps), (x*inv)*w; simd.rs:847-899)
+// Rows of up to 256 * kRmsMaxV elements are held in registers: all loads of a thread are issued before the first is used (a row is
+// 16 dependent-latency trips otherwise: 15 us per launch at 32 rows), the sums run in the SAME order as before (bit-identical).
+constexpr int kRmsMaxV = 32;
 __global__ void __launch_bounds__(256) prefill_rms_norm_kernel(const float* x, const float* w, float eps, __half* out, int n) {
     __shared__ float red[8];
     const float* xr = x + (size_t)blockIdx.x * n;
     __half* orow = out + (size_t)blockIdx.x * n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float ss = 0.0f;
+    if (n <= 256 * kRmsMaxV) {
+        float v[kRmsMaxV], wv[kRmsMaxV];
+#pragma unroll
+        for (int k = 0; k < kRmsMaxV; k++) {
+            const int i = threadIdx.x + 256 * k;
+            v[k] = i < n ? xr[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kRmsMaxV; k++) {
+            const int i = threadIdx.x + 256 * k;
+            wv[k] = i < n ? w[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kRmsMaxV; k++)
+            if (threadIdx.x + 256 * k < n) ss = fmaf(v[k], v[k], ss);
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float tot = 0.0f;
+        for (int k = 0; k < 8; k++) tot += red[k];
+        const float inv = 1.0f / sqrtf(tot / (float)n + eps);
+#pragma unroll
+        for (int k = 0; k < kRmsMaxV; k++) {
+            const int i = threadIdx.x + 256 * k;
+            if (i < n) orow[i] = f2h_sat(__fmul_rn(__fmul_rn(v[k], inv), wv[k]));
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
     ss = warp_sum(ss);
     if (lane == 0) red[warp] = ss;
