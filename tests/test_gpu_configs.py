@@ -163,3 +163,41 @@ def test_prefill_queue_reaches_the_gemm_prefill_through_prefill_token(b200, orac
     gpu.reset()                                                              # a reset drops the queue
     assert gpu.position() == 0
     gpu.close()
+
+
+def test_llama3_8b_shape_int8_kv_from_a_gguf_file_and_the_batched_engine(b200, oracle, tmp_path):
+    """The rows added last at Llama-3-8B shapes, 2 layers, full 128 256-row head: the model is written to a
+    GGUF file, loaded by the library's own reader (b200_ctx_create_from_gguf) with the INT8 KV cache, decoded against the oracle's
+    int8-cache model; then an f32 context of the same file runs four requests through the continuous-batching engine against the
+    reference loop's restatement (exact path: < 8 rows)."""
+    from llama_gguf_b200 import gguf_io
+    from test_gpu_batched_engine import ReferenceLoop
+
+    arch, desc, tensors = synth.synth_model("llama-3-8b", "Q4_K_M", 64, n_layers=2, max_batch=4)
+    path = os.path.join(tmp_path, "llama3-8b-2l.gguf")
+    gguf_io.write_gguf(path, arch, desc, tensors)
+    gpu = b200.GpuOnlyInference.from_gguf(path, max_seq_len=64, max_batch=4, kv_format="int8")
+    assert gpu.kv_format() == "int8" and gpu.load_stats["tensors_loaded"] == len(tensors)
+    ref = oracle.OracleModel(desc, tensors, kv_format="int8")
+    prompt = synth.prompt_tokens(20, desc["vocab"])
+    want = ref.forward(prompt)
+    assert rel_err(gpu.prefill(prompt), want) < TOL
+    tok = oracle.argmax_last(want)
+    for _ in range(6):
+        want = ref.forward([tok])
+        got = gpu.forward(tok)
+        assert rel_err(got, want) < TOL and oracle.argmax_last(got) == oracle.argmax_last(want)
+        tok = oracle.argmax_last(want)
+    gpu.close()
+    gpu = b200.GpuOnlyInference.from_gguf(path, max_seq_len=64, max_batch=4)
+    assert gpu.path() == "stream2"
+    eng = b200.BatchedEngine(gpu, max_batch_size=3, max_seq_len=64, max_queue_depth=8, eos_token_id=desc["vocab"] - 1)
+    loop = ReferenceLoop(oracle, desc, tensors, 3, 64, 8, desc["vocab"] - 1)
+    rng = np.random.default_rng(2)
+    for _ in range(4):
+        toks = [int(t) for t in rng.integers(0, desc["vocab"], size=int(rng.integers(2, 9)))]
+        mt = int(rng.integers(2, 5))
+        assert eng.submit(toks, mt) == loop.submit(toks, mt)
+    assert eng.run() == loop.run()
+    eng.close()
+    gpu.close()
