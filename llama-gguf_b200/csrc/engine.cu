@@ -1774,7 +1774,8 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         p.bias = (bias && bias->present()) ? bias->f32() : nullptr;
         p.accumulate = acc; p.err = c->mma_err;
         umma_set_tmap(c, p);
-        umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
+        if (gemm2_enabled() && gemm_encode_fn() && umma2_eligible(p) && env_int("B200_GEMM2_SPLIT_PLAN", 1)) umma2_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
+        else umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
         if (p.k_split && (p.n_rows + kUmmaM - 1) / kUmmaM <= 8192 && env_int("B200_GEMM2_FUSED_REDUCE", 0)) p.tile_cnt = c->pf_tile_cnt;
         return gemm_dispatch(p, c->n_sm, st, &c->launches);
     };

@@ -422,6 +422,31 @@ inline void umma_plan_split(UmmaParams& p, float* scratch, size_t scratch_floats
     p.k_split = ks;
     p.part = scratch;
 }
+// Split-K plan for the PERSISTENT kernel (gemm_umma2.cuh: one CTA per SM walks the items): what counts is the longest chain of
+// K steps one CTA executes, rounds(items / n_sm) x steps per item, plus the reduce kernel and the partial-tile traffic a split
+// costs (taken as 8 steps).  Llama-3-8B at 32 rows: q / o (32 tiles x 64 steps) -> 8 ranges (2 rounds x 8 steps), k / v -> 8,
+// down (32 x 224) -> 8, but gate / up (112 tiles x 64 steps) -> NO split: 3 ranges (what the rule above picks) make 336 items =
+// 3 rounds x 24 steps, longer than the 64 steps of the unsplit tiles, and add a reduce launch each.
+inline void umma2_plan_split(UmmaParams& p, float* scratch, size_t scratch_floats, int n_sm) {
+    p.k_split = 0;
+    p.part = nullptr;
+    if (!scratch || p.T > 64) return;
+    const int tn = p.T <= 32 ? 32 : 64;
+    const long long tiles = (long long)((p.n_rows + kUmmaM - 1) / kUmmaM) * ((p.T + tn - 1) / tn);
+    const int blocks = p.K / 256;
+    long long best_cost = ((tiles + n_sm - 1) / n_sm) * (long long)blocks * 4;
+    int best = 1;
+    for (int sN = 2; sN <= 8 && sN <= blocks / 2; sN++) {
+        if ((size_t)sN * p.T * p.n_rows > scratch_floats) break;
+        const int kb = (blocks + sN - 1) / sN;               // blocks per range
+        const int n_z = (blocks + kb - 1) / kb;              // ranges actually used
+        const long long cost = ((tiles * n_z + n_sm - 1) / n_sm) * (long long)kb * 4 + 8;
+        if (cost < best_cost) { best_cost = cost; best = sN; }
+    }
+    if (best <= 1) return;
+    p.k_split = ((blocks + best - 1) / best) * 256;
+    p.part = scratch;
+}
 inline cudaError_t umma_launch(const UmmaParams& p, cudaStream_t st) {
     if (p.T <= 32) return umma_launch_tn<32>(p, st);
     if (p.T <= 64) return umma_launch_tn<64>(p, st);
