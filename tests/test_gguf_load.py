@@ -274,7 +274,11 @@ def test_group_from_gguf(b200, oracle, tmp_path, n_devices):
     """Single-process group (tensor parallel over n devices): every rank stages its own shard out of the one mapping."""
     if b200.device_count() < n_devices:
         pytest.skip(f"needs {n_devices} GPUs")
-    path, arch, desc, tensors = _write(tmp_path, "llama-stream-tiny", "Q4_K_M", ctx=64)
+    from llama_gguf_b200 import gguf_io
+
+    arch, desc, tensors = synth.synth_model("llama-stream-tiny", "Q4_K_M", 64, vocab=1024)   # (vocab / world_size: a multiple of 16)
+    path = os.path.join(tmp_path, "llama-stream-tiny-v1024.gguf")
+    gguf_io.write_gguf(path, arch, desc, tensors)
     toks = synth.prompt_tokens(5, desc["vocab"])
     grp = b200.GroupInference.from_gguf(path, n_devices=n_devices, max_seq_len=64)
     if n_devices > 1:
