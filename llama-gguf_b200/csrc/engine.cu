@@ -232,6 +232,11 @@ struct b200_ctx {
     bool pf_tmaps_built = false;
     size_t pf_split_floats = 0;
     int pf_logits_rows = 0;
+    // batched decode: the launches of a step are the same for a given row count (positions, cache bases and slot states are read from
+    // device arrays) -> captured once per row count into a CUDA graph and replayed (B200_BATCH_GRAPH=0: eager launches)
+    struct BatchGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; bool warm = false; };
+    std::vector<BatchGraph> batch_graphs;
+    bool batch_graph = true;
     int* pf_argmax = nullptr;        // batched decode with the pick on the device: [rows]
     int pf_argmax_rows = 0;
     int batch_gemm_min = 8;    // measured crossover on Llama-3-8B: a GEMM pass costs ~12 ms up to 32 rows, a sequence alone 2 ms
@@ -341,6 +346,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->prefill_gemm_min = std::max(1, env_int("B200_PREFILL_GEMM_MIN", 32));
     c->prefill_queue = env_int("B200_PREFILL_QUEUE", 0) != 0;
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
+    c->batch_graph = env_int("B200_BATCH_GRAPH", 1) != 0;
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -774,6 +780,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaFree(c->pf_rows);
     cudaFree(c->pf_logits);
     cudaFree(c->pf_argmax);
+    for (auto& bg : c->batch_graphs)
+        if (bg.exec) cudaGraphExecDestroy(bg.exec);
     cudaFree(c->pf_split);
     cudaFree(c->pf_tmaps);
     cudaFree(c->pf_tile_cnt);
@@ -1756,6 +1764,41 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             c->pf_logits = nullptr;
             CU_ALLOC(cudaMalloc((void**)&c->pf_logits, (size_t)n * d.vocab * sizeof(float)));
             c->pf_logits_rows = n;
+            for (auto& bg : c->batch_graphs) {   // (the captured head GEMMs write the old buffer)
+                if (bg.exec) cudaGraphExecDestroy(bg.exec);
+                bg = b200_ctx::BatchGraph();
+            }
+        }
+    }
+    // CUDA graph of the step (rows mode): replay if this row count has one, capture on its second step (the first runs eagerly:
+    // function attributes and lazy allocations happen there), and run the capture's graph to do the step itself
+    struct CaptureGuard {
+        cudaStream_t st;
+        bool on = false;
+        ~CaptureGuard() {
+            if (!on) return;
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(st, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+    } capg{c->stream};
+    const bool use_graph = rows && c->batch_graph && !c->use_taps;
+    const uint64_t launches0 = c->launches;
+    if (use_graph) {
+        if ((int)c->batch_graphs.size() <= n) c->batch_graphs.resize((size_t)n + 1);
+        CU(cudaMemcpyAsync(c->pf_tok, tokens, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));   // the caller's buffer: not part of the graph
+        b200_ctx::BatchGraph& bg = c->batch_graphs[n];
+        if (bg.exec) {
+            CU(cudaGraphLaunch(bg.exec, c->stream));
+            c->launches += bg.launches;
+            return B200_OK;
+        }
+        if (bg.warm) {
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            capg.on = true;
+        } else {
+            bg.warm = true;
         }
     }
     float* X = c->pf_buf;                               // [T][H] residual stream (f32)
@@ -1784,7 +1827,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         const int T = std::min(cap, n - done);
         const int pos0 = (int)sl.host_pos + done;
         last_T = T;
-        CU(cudaMemcpyAsync(c->pf_tok, tokens + done, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!use_graph) CU(cudaMemcpyAsync(c->pf_tok, tokens + done, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
         prefill_embed_kernel<<<T, 256, 0, st>>>(c->token_embd.type, c->token_embd.d, c->token_embd.row_bytes, H, c->pf_tok, d.vocab, X);
         for (int l = 0; l < d.n_layers; l++) {
             Layer& L = c->layers[l];
@@ -1865,6 +1908,24 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         umma_set_tmap(c, hp);
         CU(gemm_dispatch(hp, c->n_sm, st));
         c->launches += 3;
+        if (capg.on) {
+            capg.on = false;
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ex = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess || !ex) {   // not capturable here: eager launches from now on (nothing has run yet: do the step)
+                cudaGetLastError();
+                c->batch_graph = false;
+                c->launches = launches0;
+                return prefill_gemm(c, seq, tokens, n, want_logits, seqs);
+            }
+            b200_ctx::BatchGraph& bg = c->batch_graphs[n];
+            bg.exec = ex;
+            bg.launches = c->launches - launches0;
+            CU(cudaGraphLaunch(ex, st));
+        }
         return B200_OK;
     }
     prefill_advance_kernel<<<1, 32, 0, st>>>(sl.d_state, n);
