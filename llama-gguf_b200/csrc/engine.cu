@@ -237,6 +237,7 @@ struct b200_ctx {
     struct BatchGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; bool warm = false; };
     std::vector<BatchGraph> batch_graphs;
     bool batch_graph = true;
+    bool batch_pdl = true;            // ... with programmatic dependent launches between its kernels (B200_BATCH_PDL=0: plain edges)
     int* pf_argmax = nullptr;        // batched decode with the pick on the device: [rows]
     int pf_argmax_rows = 0;
     int batch_gemm_min = 8;    // measured crossover on Llama-3-8B: a GEMM pass costs ~12 ms up to 32 rows, a sequence alone 2 ms
@@ -347,6 +348,7 @@ extern "C" int b200_ctx_create(const b200_model_desc* desc, const b200_parallel_
     c->prefill_queue = env_int("B200_PREFILL_QUEUE", 0) != 0;
     c->batch_gemm_min = std::max(2, env_int("B200_BATCH_GEMM_MIN", 8));
     c->batch_graph = env_int("B200_BATCH_GRAPH", 1) != 0;
+    c->batch_pdl = env_int("B200_BATCH_PDL", 1) != 0;
     c->mma_warps = std::max(4, std::min(kMmaMaxWarps, env_int("B200_MMA_WARPS", 16)));
     c->mma_stages = std::max(2, std::min(kMmaMaxStages, env_int("B200_MMA_STAGES", 3)));
     c->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -1682,6 +1684,20 @@ static void umma_set_tmap(b200_ctx* c, UmmaParams& p) {
     p.raw_bytes = 256 / type_block_elems(p.type) * type_block_bytes(p.type);
 }
 
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute when `pdl` (the kernel must call pdl_wait()
+// before it touches anything: every kernel of the batched-decode pass does)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_on(cudaStream_t st, bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl ? at : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // `prompt`: the caller is b200_prefill (consecutive positions of one sequence).  With the int8 KV cache only that case takes the GEMM
 // path, and only with the tensor-core attention (its fp16 K / V^T tiles are built from the dequantised rows, kv_int8.cuh).
 static bool prefill_gemm_ok(const b200_ctx* c, bool prompt = false) {
@@ -1810,12 +1826,13 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
     __half* Hh = ATh + (size_t)cap * A;                 // [T][I] silu(gate) * up, fp16
     const size_t kv_layer = (size_t)2 * nkv * d.max_seq_len * hd;
     cudaStream_t st = c->stream;
+    const bool pdl = rows && c->batch_pdl;   // batched decode: programmatic dependent launches along the whole chain
     auto gemm = [&](const DevTensor& w, int K, const __half* x, int ldx, int T, float* y, int ldy, const DevTensor* bias, int acc) -> cudaError_t {
         UmmaParams p{};
         p.w = w.d; p.row_bytes = w.row_bytes; p.type = w.type; p.n_rows = (int)w.ne[1]; p.K = K;
         p.x = x; p.ldx = ldx; p.T = T; p.y = y; p.ldy = ldy;
         p.bias = (bias && bias->present()) ? bias->f32() : nullptr;
-        p.accumulate = acc; p.err = c->mma_err;
+        p.accumulate = acc; p.err = c->mma_err; p.pdl = pdl ? 1 : 0;
         umma_set_tmap(c, p);
         if (gemm2_enabled() && gemm_encode_fn() && umma2_eligible(p) && env_int("B200_GEMM2_SPLIT_PLAN", 1)) umma2_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
         else umma_plan_split(p, c->pf_split, c->pf_split_floats, c->n_sm);
@@ -1828,12 +1845,12 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         const int pos0 = (int)sl.host_pos + done;
         last_T = T;
         if (!use_graph) CU(cudaMemcpyAsync(c->pf_tok, tokens + done, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
-        prefill_embed_kernel<<<T, 256, 0, st>>>(c->token_embd.type, c->token_embd.d, c->token_embd.row_bytes, H, c->pf_tok, d.vocab, X);
+        CU(launch_on(st, pdl, prefill_embed_kernel, dim3(T), dim3(256), 0, c->token_embd.type, (const uint8_t*)c->token_embd.d, c->token_embd.row_bytes, H, (const int*)c->pf_tok, d.vocab, X));
         for (int l = 0; l < d.n_layers; l++) {
             Layer& L = c->layers[l];
             float* kc = sl.kv + (size_t)l * kv_layer;
             float* vc = kc + kv_layer / 2;
-            prefill_rms_norm_kernel<<<T, 256, 0, st>>>(X, L.attn_norm.f32(), d.norm_eps, XNh, H);
+            CU(launch_on(st, pdl, prefill_rms_norm_kernel, dim3(T), dim3(256), 0, (const float*)X, L.attn_norm.f32(), d.norm_eps, XNh, H));
             CU(gemm(L.wq, H, XNh, H, T, Q, QKV, &L.bq, 0));
             CU(gemm(L.wk, H, XNh, H, T, Q + A, QKV, &L.bk, 0));
             CU(gemm(L.wv, H, XNh, H, T, Q + A + nkv * hd, QKV, &L.bv, 0));
@@ -1854,7 +1871,7 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
                 if (hd == 128) prefill_rope_kv_q8_kernel<4><<<rgrid, 128, 0, st>>>(qp, QKV, pos0);
                 else prefill_rope_kv_q8_kernel<2><<<rgrid, 128, 0, st>>>(qp, QKV, pos0);
             } else {
-                prefill_rope_kv_kernel<<<dim3(T, T <= 64 ? 4 : 1), 256, 0, st>>>(rp);   // few rows (batched decode): 4 CTAs per token
+                CU(launch_on(st, pdl, prefill_rope_kv_kernel, dim3(T, T <= 64 ? 4 : 1), dim3(256), 0, rp));   // few rows (batched decode): 4 CTAs per token
             }
             PrefillAttnParams ap{};
             ap.qkv = Q; ap.ld = QKV; ap.k_cache = kc; ap.v_cache = vc; ap.out = ATh; ap.ldo = A; ap.pos0 = pos0; ap.T = T;
@@ -1880,18 +1897,16 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
                 const int ablocks = (int)(((long long)T * nkv * 32 + 127) / 128);
                 const int Gq = nh / nkv;
                 if (hd == 128) {
-                    if (Gq <= 4) prefill_attn_kernel<128, 4><<<ablocks, 128, 0, st>>>(ap);
-                    else prefill_attn_kernel<128, 8><<<ablocks, 128, 0, st>>>(ap);
+                    CU(launch_on(st, pdl, Gq <= 4 ? prefill_attn_kernel<128, 4> : prefill_attn_kernel<128, 8>, dim3(ablocks), dim3(128), 0, ap));
                 } else {
-                    if (Gq <= 4) prefill_attn_kernel<64, 4><<<ablocks, 128, 0, st>>>(ap);
-                    else prefill_attn_kernel<64, 8><<<ablocks, 128, 0, st>>>(ap);
+                    CU(launch_on(st, pdl, Gq <= 4 ? prefill_attn_kernel<64, 4> : prefill_attn_kernel<64, 8>, dim3(ablocks), dim3(128), 0, ap));
                 }
             }
             CU(gemm(L.wo, A, ATh, A, T, X, H, nullptr, 1));                       // X += Wo attn
-            prefill_rms_norm_kernel<<<T, 256, 0, st>>>(X, L.ffn_norm.f32(), d.norm_eps, XNh, H);
+            CU(launch_on(st, pdl, prefill_rms_norm_kernel, dim3(T), dim3(256), 0, (const float*)X, L.ffn_norm.f32(), d.norm_eps, XNh, H));
             CU(gemm(L.gate, H, XNh, H, T, G, I, nullptr, 0));
             CU(gemm(L.up, H, XNh, H, T, U, I, nullptr, 0));
-            prefill_swiglu_kernel<<<std::min(148 * 8, (int)(((long long)T * I + 255) / 256)), 256, 0, st>>>(G, U, Hh, (long long)T * I);
+            CU(launch_on(st, pdl, prefill_swiglu_kernel, dim3(std::min(148 * 8, (int)(((long long)T * I + 255) / 256))), dim3(256), 0, (const float*)G, (const float*)U, Hh, (long long)T * I));
             CU(gemm(L.down, I, Hh, I, T, X, H, nullptr, 1));                      // X += Wd act
             c->launches += 5;
         }
@@ -1899,12 +1914,12 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
         CU(cudaGetLastError());
     }
     if (rows) {   // every row's slot advances by one; final RMSNorm + vocab head of ALL rows through the GEMM
-        prefill_advance_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_st, n);
+        CU(launch_on(st, pdl, prefill_advance_rows_kernel, dim3((n + 127) / 128), dim3(128), 0, (SeqState* const*)d_st, n));
         const DevTensor& head = c->output.present() ? c->output : c->token_embd;
-        prefill_rms_norm_kernel<<<n, 256, 0, st>>>(X, c->output_norm.f32(), d.norm_eps, XNh, H);
+        CU(launch_on(st, pdl, prefill_rms_norm_kernel, dim3(n), dim3(256), 0, (const float*)X, c->output_norm.f32(), d.norm_eps, XNh, H));
         UmmaParams hp{};
         hp.w = head.d; hp.row_bytes = head.row_bytes; hp.type = head.type; hp.n_rows = d.vocab; hp.K = H;
-        hp.x = XNh; hp.ldx = H; hp.T = n; hp.y = c->pf_logits; hp.ldy = d.vocab; hp.err = c->mma_err;
+        hp.x = XNh; hp.ldx = H; hp.T = n; hp.y = c->pf_logits; hp.ldy = d.vocab; hp.err = c->mma_err; hp.pdl = pdl ? 1 : 0;
         umma_set_tmap(c, hp);
         CU(gemm_dispatch(hp, c->n_sm, st));
         c->launches += 3;
@@ -1915,9 +1930,10 @@ static int prefill_gemm(b200_ctx* c, int seq, const uint32_t* tokens, int n, boo
             cudaError_t e = cudaStreamEndCapture(st, &g);
             if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
             if (g) cudaGraphDestroy(g);
-            if (e != cudaSuccess || !ex) {   // not capturable here: eager launches from now on (nothing has run yet: do the step)
+            if (e != cudaSuccess || !ex) {   // not capturable here: first without programmatic edges, then eager launches (nothing has run yet: do the step)
                 cudaGetLastError();
-                c->batch_graph = false;
+                if (c->batch_pdl) c->batch_pdl = false;
+                else c->batch_graph = false;
                 c->launches = launches0;
                 return prefill_gemm(c, seq, tokens, n, want_logits, seqs);
             }

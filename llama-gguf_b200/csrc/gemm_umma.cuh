@@ -200,6 +200,8 @@ struct UmmaParams {
     const void* tmap;
     int raw_pitch;       // bytes between the rows of a raw tile
     int raw_bytes;       // bytes of 256 elements of one row (144 / 176 / 210 / 272)
+    int pdl;             // host: launch with programmatic stream serialization (the persistent kernel and its reduce kernel wait
+                         // with griddepcontrol.wait after their prologue; batched decode, engine.cu)
 };
 
 template <int TN>
@@ -364,6 +366,8 @@ __global__ void __launch_bounds__(128) dequant_gemm_umma_kernel(const UmmaParams
 
 // Y[t][j] (+)= sum_z part[z][t][j] + bias[j]   (split-K epilogue, z in fixed order)
 __global__ void umma_reduce_kernel(const UmmaParams p, int splits) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n = (long long)p.T * p.n_rows;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i / p.n_rows), j = (int)(i - (long long)t * p.n_rows);

@@ -178,6 +178,7 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
     uint8_t* sB = base + pl.off_b;
     uint8_t* sR = base + pl.off_raw;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();   // (programmatic launch: the next kernel's CTAs may be scheduled; they wait for this grid to finish)
     const uint32_t bA_full = umma_smem_u32(bars.a_full), bA_empty = umma_smem_u32(bars.a_empty);
     const uint32_t bB_full = umma_smem_u32(bars.b_full), bB_empty = umma_smem_u32(bars.b_empty);
     const uint32_t bR_full = umma_smem_u32(bars.r_full), bR_empty = umma_smem_u32(bars.r_empty);
@@ -205,6 +206,7 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_wait();                // barriers, TMEM and the smem carve-out are set up; nothing of the predecessor has been touched yet
     const uint32_t tmem = s_tmem;
     const int n_items = pl.n_mt * pl.n_z * pl.n_nt;
     const uint32_t SA = (uint32_t)pl.sa, SB = (uint32_t)pl.sb, SR = (uint32_t)pl.sr;
@@ -506,6 +508,23 @@ inline cudaError_t umma2_launch_tn(const CUtensorMap& xmap, const UmmaParams& p,
     }
     const int n_items = pl.n_mt * pl.n_z * pl.n_nt;
     const int grid = std::min(n_items, n_sm);
+    if (p.pdl) {   // programmatic stream serialization for both launches (batched decode: ~580 dependent kernels per step)
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kU2FirstDeqWarp + 4 * NG) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, dequant_gemm_umma2_kernel<TN, NG>, xmap, p, pl);
+        if (e != cudaSuccess) return e;
+        if (pl.n_z > 1 && !p.tile_cnt) {
+            const long long n = (long long)p.T * p.n_rows;
+            cfg.gridDim = dim3((unsigned)std::min<long long>((n + 255) / 256, 148 * 8)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+            e = cudaLaunchKernelEx(&cfg, umma_reduce_kernel, p, pl.n_z);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaGetLastError();
+    }
     dequant_gemm_umma2_kernel<TN, NG><<<grid, (kU2FirstDeqWarp + 4 * NG) * 32, smem, st>>>(xmap, p, pl);
     if (pl.n_z > 1 && !p.tile_cnt) {
         const long long n = (long long)p.T * p.n_rows;

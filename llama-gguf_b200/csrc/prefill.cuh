@@ -13,6 +13,8 @@ namespace b200 {
 // X[t][:] = dequantised row tokens[t] of the embedding table (bit-exact)
 __global__ void prefill_embed_kernel(int type, const uint8_t* __restrict__ table, long long row_bytes, int hidden, const int* __restrict__ tokens,
                                      int vocab, float* __restrict__ X) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x;
     const int token = min(max(tokens[t], 0), vocab - 1);
     const int be = type_block_elems(type), bb = type_block_bytes(type);
@@ -39,6 +41,8 @@ struct PrefillRopeParams {
 };
 // one CTA per token: Backend::rope for the token's position pos0 + t, k rows -> cache, v rows -> cache
 __global__ void prefill_rope_kv_kernel(const PrefillRopeParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x, pos = p.row_pos ? p.row_pos[t] : p.pos0 + t;
     float* const k_cache = p.row_pos ? p.row_kv[t] + p.k_off : p.k_cache;
     float* const v_cache = p.row_pos ? p.row_kv[t] + p.v_off : p.v_cache;
@@ -94,6 +98,8 @@ struct PrefillAttnParams {
 // Causal: token t attends cache positions 0 .. pos0 + t.
 template <int HD, int GMAX>
 __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int VEC = HD / 32, UB = 4;
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -200,6 +206,8 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnPara
 // 16 dependent-latency trips otherwise: 15 us per launch at 32 rows), the sums run in the SAME order as before (bit-identical).
 constexpr int kRmsMaxV = 32;
 __global__ void __launch_bounds__(256) prefill_rms_norm_kernel(const float* x, const float* w, float eps, __half* out, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[8];
     const float* xr = x + (size_t)blockIdx.x * n;
     __half* orow = out + (size_t)blockIdx.x * n;
@@ -245,6 +253,8 @@ __global__ void __launch_bounds__(256) prefill_rms_norm_kernel(const float* x, c
 
 // g[i] = silu(g[i]) * u[i]  (silu rounded to f32 first, then the product: simd.rs:598-649)
 __global__ void prefill_swiglu_kernel(const float* __restrict__ g, const float* __restrict__ u, __half* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x = g[i];
         out[i] = f2h_sat((x / (1.0f + expf(-x))) * u[i]);
@@ -261,6 +271,8 @@ __global__ void prefill_advance_kernel(SeqState* st, int T) {
 
 // batched decode: every row's slot advances by one token
 __global__ void prefill_advance_rows_kernel(SeqState* const* st, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         SeqState* s = st[i];
