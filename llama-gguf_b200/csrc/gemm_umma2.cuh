@@ -206,7 +206,10 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    pdl_wait();                // barriers, TMEM and the smem carve-out are set up; nothing of the predecessor has been touched yet
+    // Programmatic launch: the weights never depend on the predecessor, so only the roles that touch ITS data wait for it
+    // (griddepcontrol.wait): the producer before its first activation load -- the raw weight tiles of the first item are already
+    // on their way by then -- and the epilogue warps before they read or write Y.  The dequant warps and the MMA thread only see
+    // shared memory and TMEM.
     const uint32_t tmem = s_tmem;
     const int n_items = pl.n_mt * pl.n_z * pl.n_nt;
     const uint32_t SA = (uint32_t)pl.sa, SB = (uint32_t)pl.sb, SR = (uint32_t)pl.sr;
@@ -229,19 +232,31 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
         if (lane == 0) {
             asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(p.tmap) : "memory");
             U2Ring rr{0u, 0u}, rb{0u, 0u};
+            auto raw_load = [&](int m, int blk) {
+                u2_wait(bR_empty + 8u * rr.i, rr.ph ^ 1u, alive, p.err, 11, waited);
+                if (pl.dbg & 2) {
+                    u2_mbar_arrive(bR_full + 8u * rr.i);
+                } else {
+                    u2_expect_tx(bR_full + 8u * rr.i, (uint32_t)(p.raw_pitch * kUmmaM));
+                    u2_tma_2d(umma_smem_u32(sR) + rr.i * (uint32_t)pl.raw_stage, p.tmap, ((blk * p.raw_bytes) & ~15) >> 2, m * kUmmaM, bR_full + 8u * rr.i);
+                }
+                rr.next(SR);
+            };
+            int pre = 0;   // raw blocks of the first item requested before the dependency wait (the raw ring is empty: no wait inside)
+            if ((int)blockIdx.x < n_items) {
+                int m, n, kb, nblk;
+                item_decode(blockIdx.x, m, n, kb, nblk);
+                pre = min(nblk, (int)SR);
+                for (int b = 0; b < pre; b++) raw_load(m, (kb >> 8) + b);
+            }
+            pdl_wait();
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int m, n, kb, nblk;
                 item_decode(item, m, n, kb, nblk);
                 for (int b = 0; b < nblk; b++) {
                     const int blk = (kb >> 8) + b;
-                    u2_wait(bR_empty + 8u * rr.i, rr.ph ^ 1u, alive, p.err, 11, waited);
-                    if (pl.dbg & 2) {
-                        u2_mbar_arrive(bR_full + 8u * rr.i);
-                    } else {
-                        u2_expect_tx(bR_full + 8u * rr.i, (uint32_t)(p.raw_pitch * kUmmaM));
-                        u2_tma_2d(umma_smem_u32(sR) + rr.i * (uint32_t)pl.raw_stage, p.tmap, ((blk * p.raw_bytes) & ~15) >> 2, m * kUmmaM, bR_full + 8u * rr.i);
-                    }
-                    rr.next(SR);
+                    if (pre > 0) pre--;
+                    else raw_load(m, blk);
 #pragma unroll 1
                     for (int s = 0; s < (kBBlock ? 1 : 4); s++) {
                         u2_wait(bB_empty + 8u * rb.i, rb.ph ^ 1u, alive, p.err, 12, waited);
@@ -359,6 +374,7 @@ dequant_gemm_umma2_kernel(const __grid_constant__ CUtensorMap xmap, const UmmaPa
     } else {
         role = 5;
         // ---- epilogue warps: warp w owns TMEM lanes 32w..32w+31 = weight rows, 32 token columns per load ----
+        pdl_wait();
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
             int m, n, kb, nblk;
