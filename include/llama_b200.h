@@ -260,6 +260,8 @@ B200_API int b200_debug_mega_phase(b200_ctx* ctx, int phase, unsigned long long*
 /* Watchdog words of the tensor-pipe / megakernel paths: out8[0] = 0 when no bounded wait ever gave up, else
  * (code, which wait, CTA, sequence number); clears them. */
 B200_API int b200_debug_err(b200_ctx* ctx, int* out8);
+/* Host logic of the dequant-GEMM's split-K planners (no device needed): K range per split, 0 = unsplit. */
+B200_API int b200_debug_plan_split(int n_rows, int K, int T, int n_sm, int persistent, int* k_split_out);
 /* Lab: take the first `pos` positions of the slot's KV cache as valid as they are (attention at depth without a prompt). */
 B200_API int b200_debug_set_position(b200_ctx* ctx, int seq, uint64_t pos);
 /* Decode path chosen by b200_ctx_finalize: 0 = CUDA graph of per-op kernels, 1 = per-token megakernel,

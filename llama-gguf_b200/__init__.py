@@ -125,6 +125,7 @@ def lib():
     L.b200_ctx_set_speculation.argtypes = [vp, C.c_int]
     L.b200_ctx_speculation_stats.argtypes = [vp, i32p, u64p, u64p]
     L.b200_debug_set_position.argtypes = [vp, C.c_int, C.c_uint64]
+    L.b200_debug_plan_split.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.b200_decode_batch_greedy.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
     L.b200_batch_create.argtypes = [vp, C.POINTER(BatchConfig), C.POINTER(vp)]
     L.b200_batch_destroy.argtypes = [vp]
@@ -435,6 +436,13 @@ class CudaB200Backend:
 
 # ----------------------------------------------------------------- GpuInference
 DESC_KEYS = [f[0] for f in ModelDesc._fields_]
+
+
+def plan_split(n_rows, K, T, n_sm=148, persistent=True):
+    """K range per split the dequant-GEMM would use (0 = unsplit): host logic, no device needed."""
+    v = C.c_int(0)
+    _check(lib().b200_debug_plan_split(int(n_rows), int(K), int(T), int(n_sm), 1 if persistent else 0, C.byref(v)))
+    return v.value
 
 
 class BatchedEngine:

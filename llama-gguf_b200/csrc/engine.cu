@@ -3639,3 +3639,16 @@ extern "C" int b200_debug_set_position(b200_ctx* c, int seq, uint64_t pos) {
     c->slots[seq].host_pos = pos;
     return B200_OK;
 }
+
+// Host logic of the split-K planners, callable without a device (tests): K range per split (0 = unsplit) for an n_rows x K matrix at
+// T token rows on n_sm SMs; persistent = the cost model of gemm_umma2.cuh's kernel, else round 1's rule.
+extern "C" int b200_debug_plan_split(int n_rows, int K, int T, int n_sm, int persistent, int* k_split_out) {
+    if (!k_split_out || n_rows <= 0 || K <= 0 || K % 256 || T <= 0 || n_sm <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "b200_debug_plan_split: bad argument");
+    UmmaParams p{};
+    p.n_rows = n_rows; p.K = K; p.T = T;
+    float dummy = 0.0f;
+    if (persistent) umma2_plan_split(p, &dummy, (size_t)1 << 40, n_sm);
+    else umma_plan_split(p, &dummy, (size_t)1 << 40, n_sm);
+    *k_split_out = p.k_split;
+    return B200_OK;
+}

@@ -428,8 +428,8 @@ inline void umma_plan_split(UmmaParams& p, float* scratch, size_t scratch_floats
 }
 // Split-K plan for the PERSISTENT kernel (gemm_umma2.cuh: one CTA per SM walks the items): what counts is the longest chain of
 // K steps one CTA executes, rounds(items / n_sm) x steps per item, plus the reduce kernel and the partial-tile traffic a split
-// costs (taken as 8 steps).  Llama-3-8B at 32 rows: q / o (32 tiles x 64 steps) -> 8 ranges (2 rounds x 8 steps), k / v -> 8,
-// down (32 x 224) -> 8, but gate / up (112 tiles x 64 steps) -> NO split: 3 ranges (what the rule above picks) make 336 items =
+// costs (taken as 8 steps).  Llama-3-8B at 32 rows on 148 SMs: q / o (32 tiles x 64 steps) -> 4 ranges (one round of 16 steps),
+// k / v (8 tiles) -> 8, down (32 x 224) -> 4 (one round of 56), but gate / up (112 tiles x 64 steps) -> NO split: 3 ranges (what the rule above picks) make 336 items =
 // 3 rounds x 24 steps, longer than the 64 steps of the unsplit tiles, and add a reduce launch each.
 inline void umma2_plan_split(UmmaParams& p, float* scratch, size_t scratch_floats, int n_sm) {
     p.k_split = 0;
