@@ -3077,7 +3077,13 @@ extern "C" int b200_gguf_open(const char* path, b200_gguf** out) {
         const int be = type_block_elems((int)t.type), bb = type_block_bytes((int)t.type);
         if (be) {
             uint64_t numel = 1;
-            for (int k = 0; k < t.n_dims; k++) numel *= t.ne[k];
+            bool overflow = false;
+            for (int k = 0; k < t.n_dims; k++) overflow |= __builtin_mul_overflow(numel, t.ne[k], &numel);
+            if (overflow || numel / be > ((uint64_t)1 << 50)) {   // (the byte size below must not wrap; real bounds: b200_gguf_tensor_info)
+                const std::string nm = t.name;
+                gguf_release(g);
+                return fail(B200_ERR_INVALID_ARGUMENT, nm + ": tensor shape overflows (corrupt GGUF?)");
+            }
             t.nbytes = (size_t)(numel / be * bb);   // TensorInfo::data_size (types.rs:45-50)
         }
         g->tensors.push_back(std::move(t));
@@ -3131,7 +3137,7 @@ extern "C" int b200_gguf_tensor_info(b200_gguf* g, uint64_t i, const char** name
         *data = nullptr;
         if (t.nbytes) {
             const uint64_t start = g->data_offset + t.offset;
-            if (start > g->size || t.nbytes > g->size - start)
+            if (t.offset > g->size || start > g->size || t.nbytes > g->size - start)
                 return fail(B200_ERR_INVALID_ARGUMENT, t.name + ": tensor data lies outside the file (truncated GGUF?)");
             *data = g->map + start;
         }

@@ -196,6 +196,39 @@ def test_truncated_files(b200, tmp_path):
                 f.tensor(i, with_data=True)
 
 
+def test_corrupt_shapes_and_offsets_are_refused(b200, tmp_path):
+    """Dimensions whose product overflows 64 bits, a shape larger than the file, an offset beyond it: errors, never a wild pointer."""
+    a = np.arange(64, dtype=np.float32)
+    kvs = [("general.architecture", 8, "llama")]
+    blob, data_offset = _pack_gguf(3, kvs, [("output_norm.weight", [64], a)])
+    # tensor info layout (v3): name (8 + 18) | n_dims u32 | ne[0] u64 | type u32 | offset u64 -- patch ne[0] / the offset in place
+    info_at = blob.index(b"output_norm.weight") + len("output_norm.weight")
+    def patched(ne0=None, offset=None):
+        b = bytearray(blob)
+        if ne0 is not None:
+            b[info_at + 4: info_at + 12] = struct.pack("<Q", ne0)
+        if offset is not None:
+            b[info_at + 16: info_at + 24] = struct.pack("<Q", offset)
+        return bytes(b)
+    p = os.path.join(tmp_path, "huge_dim.gguf")
+    open(p, "wb").write(patched(ne0=2 ** 63))
+    with pytest.raises(b200.InvalidArgument, match="overflows"):
+        b200.GgufFile(p)
+    p = os.path.join(tmp_path, "big_dim.gguf")          # 4 GB of f32 in a 1 KB file: parses, but has no data
+    open(p, "wb").write(patched(ne0=10 ** 9))
+    with b200.GgufFile(p) as f:
+        assert f.tensor(0)[3] == 4 * 10 ** 9
+        with pytest.raises(b200.InvalidArgument, match="outside the file"):
+            f.tensor(0, with_data=True)
+    for name, off in (("far_offset.gguf", 2 ** 40), ("wrap_offset.gguf", 2 ** 64 - data_offset)):
+        p = os.path.join(tmp_path, name)
+        open(p, "wb").write(patched(offset=off))
+        with b200.GgufFile(p) as f:
+            assert f.tensor(0)[3] == 256
+            with pytest.raises(b200.InvalidArgument, match="outside the file"):
+                f.tensor(0, with_data=True)
+
+
 # ------------------------------------------------------------------ GPU: the load itself
 @pytest.mark.gpu
 @pytest.mark.parametrize("preset,mix", FAMILIES)
