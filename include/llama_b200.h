@@ -107,7 +107,8 @@ B200_API void b200_ctx_destroy(b200_ctx* ctx);
  * b200_ctx_finalize (or with B200_KV_FORMAT=int8 in the environment): 0 = F32 (the KVCache of src/model/mod.rs:83-108, default),
  * 1 = Int8 -- QuantizedKVCache::write_kv / read_k_range semantics (kv_quantized.rs:143-216, 230-270, 366-392): one symmetric
  * scale = max|x| / 127 per (kv head, position) row, q = round(x / scale), attention over q * scale.  A quarter of the KV bytes; the
- * context then decodes on the per-op (graph) path and prefills token by token.  The FP8 formats are not built (UNSUPPORTED). */
+ * context then decodes on the per-op (graph) path and prefills token by token (B200_KV_INT8_GEMM=1: prompts of >= 32 tokens through
+ * the tensor-core pass, outside the 1e-3 parity bound -- DESIGN 3.8).  The FP8 formats are not built (UNSUPPORTED). */
 B200_API int b200_ctx_set_kv_format(b200_ctx* ctx, int format);
 B200_API int b200_ctx_kv_format(b200_ctx* ctx, int* out);
 
