@@ -687,7 +687,10 @@ __device__ __forceinline__ void attn2_phase(const AttnParams& p, int kv_len, flo
     const float* kb = p.k_cache + kv_row(p, kh, 0, HD) + lane * VEC;
     const float* vb = p.v_cache + kv_row(p, kh, 0, HD) + lane * VEC;
     const size_t pstride = p.kv_pos_stride ? (size_t)p.kv_pos_stride : (size_t)HD;
-    constexpr int UB = GMAX <= 4 ? 2 : 1;   // positions per batch: 128 registers per thread
+#ifndef B200_ATTN2_UB
+#define B200_ATTN2_UB 2
+#endif
+    constexpr int UB = GMAX <= 4 ? B200_ATTN2_UB : 1;   // positions per batch (two batches in flight per warp); lab: -DB200_ATTN2_UB=4
     constexpr int STEP = NW * UB;
     auto load = [&](int pos0, float (&kr)[UB][VEC], float (&vr)[UB][VEC]) {
 #pragma unroll
