@@ -238,6 +238,8 @@ struct b200_ctx {
     std::vector<BatchGraph> batch_graphs;
     bool batch_graph = true;
     bool batch_pdl = true;            // ... with programmatic dependent launches between its kernels (B200_BATCH_PDL=0: plain edges)
+    float* h_batch_logits = nullptr; // pinned staging of b200_decode_batch's n x vocab logits
+    size_t h_batch_logits_bytes = 0;
     int* pf_argmax = nullptr;        // batched decode with the pick on the device: [rows]
     int pf_argmax_rows = 0;
     int batch_gemm_min = 8;    // measured crossover on Llama-3-8B: a GEMM pass costs ~12 ms up to 32 rows, a sequence alone 2 ms
@@ -803,6 +805,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         if (c->spec_ev[b]) cudaEventDestroy(c->spec_ev[b]);
     }
     if (c->h_spec_pick) cudaFreeHost(c->h_spec_pick);
+    if (c->h_batch_logits) cudaFreeHost(c->h_batch_logits);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -2221,7 +2224,23 @@ extern "C" int b200_decode_batch(b200_ctx* c, const int* seqs, const uint32_t* t
             WATCHDOG_FETCH(c);
             CU(cudaStreamSynchronize(c->stream));
             if ((rc = watchdog_check(c, "b200_decode_batch"))) return rc;
-            CU(cudaMemcpy(logits_out, c->pf_logits, (size_t)n * c->d.vocab * sizeof(float), cudaMemcpyDeviceToHost));
+            {   // n x vocab logits (16.4 MB at batch 32 on Llama-3) to the caller's pageable buffer: DMA into a pinned buffer, rows copied
+                // out by a few host threads (a pageable cudaMemcpy stages the same bytes through the driver on one thread)
+                const size_t bytes = (size_t)n * c->d.vocab * sizeof(float);
+                if (c->h_batch_logits_bytes < bytes) {
+                    if (c->h_batch_logits) cudaFreeHost(c->h_batch_logits);
+                    c->h_batch_logits = nullptr;
+                    c->h_batch_logits_bytes = 0;
+                    if (cudaHostAlloc((void**)&c->h_batch_logits, bytes, cudaHostAllocDefault) == cudaSuccess) c->h_batch_logits_bytes = bytes;
+                    else cudaGetLastError();
+                }
+                if (c->h_batch_logits) {
+                    CU(cudaMemcpy(c->h_batch_logits, c->pf_logits, bytes, cudaMemcpyDeviceToHost));
+                    gguf_parallel_copy((uint8_t*)logits_out, (const uint8_t*)c->h_batch_logits, bytes, 4);
+                } else {
+                    CU(cudaMemcpy(logits_out, c->pf_logits, bytes, cudaMemcpyDeviceToHost));
+                }
+            }
             for (int i = 0; i < n; i++) c->slots[seqs[i]].host_pos++;
             return B200_OK;
         }
