@@ -422,7 +422,10 @@ static cudaError_t tensor_alloc(b200_ctx* c, DevTensor* t, size_t bytes, bool ze
 // legacy-stream memsets of the allocation are ordered with the copies.
 static cudaError_t h2d(b200_ctx* c, void* dst, const void* src, size_t n) {
     b200_ctx::LoadStage& s = c->stage;
-    if (!s.on) return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+    if (!s.on) {
+        s.bytes += n;   // (b200_load_stats.device_bytes of an unstaged load)
+        return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+    }
     cudaError_t e;
     for (size_t off = 0; off < n; off += s.chunk) {
         const size_t len = std::min(s.chunk, n - off);
@@ -439,7 +442,10 @@ static cudaError_t h2d(b200_ctx* c, void* dst, const void* src, size_t n) {
 // rows of `width` bytes, `spitch` apart on the host, `dpitch` apart on the device (row-parallel shards: a K range of every row)
 static cudaError_t h2d_2d(b200_ctx* c, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
     b200_ctx::LoadStage& s = c->stage;
-    if (!s.on) return cudaMemcpy2D(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice);
+    if (!s.on) {
+        s.bytes += width * rows;
+        return cudaMemcpy2D(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice);
+    }
     cudaError_t e;
     const size_t rpc = std::max<size_t>(1, s.chunk / width);
     if (width > s.chunk) return cudaErrorInvalidValue;
@@ -3256,6 +3262,7 @@ extern "C" int b200_ctx_load_gguf(b200_ctx* c, b200_gguf* g, b200_load_stats* st
     CU(cudaSetDevice(c->par.device));
     const auto t0 = std::chrono::steady_clock::now();
     const bool staged = env_int("B200_LOAD_STAGED", 1) != 0;
+    c->stage.bytes = 0;
     if (staged) {
         cudaError_t e = stage_begin(c);
         if (e != cudaSuccess) {
@@ -3313,7 +3320,7 @@ extern "C" int b200_ctx_load_gguf(b200_ctx* c, b200_gguf* g, b200_load_stats* st
     if (stats) {
         stats->file_bytes = g->size;
         stats->tensor_bytes = bytes;
-        stats->device_bytes = staged ? staged_bytes : bytes;
+        stats->device_bytes = staged_bytes;
         stats->tensors_loaded = loaded;
         stats->tensors_skipped = skipped;
         stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
