@@ -176,6 +176,44 @@ def test_description_errors_and_strict_getters(b200, tmp_path):
         assert f.model_desc()["rope_neox"] == 1                   # loader.rs:145-162
 
 
+def test_parse_config_fallbacks(b200, tmp_path):
+    """The fallback chains of ModelLoader::parse_config (loader.rs:77-137, 163-175, 349-355), one file per branch."""
+    def desc_of(kvs, tensors, name):
+        blob, _ = _pack_gguf(3, [("general.architecture", 8, "llama")] + kvs, tensors)
+        p = os.path.join(tmp_path, name)
+        open(p, "wb").write(blob)
+        with b200.GgufFile(p) as f:
+            return f.model_desc()
+
+    core = [("llama.embedding_length", 4, 128), ("llama.block_count", 4, 1), ("llama.attention.head_count", 4, 4)]
+    norm = ("output_norm.weight", [128], np.zeros(128))
+    emb = ("token_embd.weight", [128, 77], np.zeros(128 * 77))
+    # vocab: {arch}.vocab_size wins, then tokenizer.ggml.vocab_size, then the embedding's rows, then 32000
+    assert desc_of(core + [("llama.vocab_size", 4, 500), ("tokenizer.ggml.vocab_size", 4, 400)], [norm, emb], "v1.gguf")["vocab"] == 500
+    assert desc_of(core + [("tokenizer.ggml.vocab_size", 4, 400)], [norm, emb], "v2.gguf")["vocab"] == 400
+    assert desc_of(core, [norm, emb], "v3.gguf")["vocab"] == 77
+    assert desc_of(core, [norm], "v4.gguf")["vocab"] == 32000
+    # eps: layer_norm_rms_epsilon, else layer_norm_epsilon, else 1e-5
+    assert desc_of(core + [("llama.attention.layer_norm_epsilon", 6, 3e-6)], [norm], "e1.gguf")["norm_eps"] == pytest.approx(3e-6)
+    assert desc_of(core + [("llama.attention.layer_norm_rms_epsilon", 6, 2e-6), ("llama.attention.layer_norm_epsilon", 6, 3e-6)], [norm],
+                   "e2.gguf")["norm_eps"] == pytest.approx(2e-6)
+    # heads / head_dim / ffn / context / rope
+    d = desc_of(core + [("llama.attention.head_count_kv", 4, 2), ("llama.attention.key_length", 4, 64), ("llama.feed_forward_length", 4, 300),
+                        ("llama.context_length", 4, 4096), ("llama.rope.scale_linear", 6, 4.0), ("llama.rope.freq_base", 6, 1e6),
+                        ("llama.rope.dimension_count", 4, 64)], [norm], "h.gguf")
+    assert (d["n_kv_heads"], d["head_dim"], d["ffn"], d["max_seq_len"], d["rope_scale"], d["rope_base"]) == (2, 64, 300, 4096, 4.0, 1e6)
+    # MoE: counts from the metadata, the expert width from the metadata or from blk.0.ffn_gate_exps.weight ([in, out, experts])
+    exps = ("blk.0.ffn_gate_exps.weight", [128, 96, 8], np.zeros(128 * 96 * 8))
+    d = desc_of(core + [("llama.expert_count", 4, 8), ("llama.expert_used_count", 4, 2)], [norm, exps], "m1.gguf")
+    assert (d["n_experts"], d["n_experts_used"], d["expert_ffn"]) == (8, 2, 96)
+    d = desc_of(core + [("llama.expert_count", 4, 8), ("llama.expert_used_count", 4, 2), ("llama.expert_feed_forward_length", 4, 80)],
+                [norm, exps], "m2.gguf")
+    assert d["expert_ffn"] == 80
+    # tied head iff there is no output.weight
+    assert desc_of(core, [norm, emb], "t1.gguf")["tied_output"] == 1
+    assert desc_of(core, [norm, emb, ("output.weight", [128, 77], np.zeros(128 * 77))], "t2.gguf")["tied_output"] == 0
+
+
 def test_truncated_files(b200, tmp_path):
     path, arch, desc, tensors = _write(tmp_path, "tinyllama-tiny", "Q8_0")
     blob = open(path, "rb").read()
