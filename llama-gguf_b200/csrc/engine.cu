@@ -1635,10 +1635,11 @@ static Umma2EncodeFn gemm_encode_fn() {
 static bool gemm2_enabled() { static int v = env_int("B200_GEMM2", 1); return v != 0; }
 static cudaError_t gemm_dispatch(UmmaParams& p, int n_sm, cudaStream_t st, uint64_t* launches = nullptr) {
     if (gemm2_enabled() && gemm_encode_fn() && umma2_eligible(p)) {
-        // dequant groups: 2 for wide token tiles (a third changes nothing at T = 2048: 927 vs 944 TFLOP/s), 3 for the narrow tiles of
-        // batched decode (batch 32: 8.94 -> 8.70 ms per step); B200_GEMM2_GROUPS forces one value everywhere
+        // dequant groups: 2 for wide token tiles (a third changes nothing at T = 2048: 927 vs 944 TFLOP/s), 4 for the narrow tiles of
+        // batched decode (batch 32: 2 groups 8.94, 3 groups 8.70 ms per step; with the graph and programmatic launches 3 groups 6.84,
+        // 4 groups 6.61 -- 704 threads at 80 registers, 182 bytes of spills); B200_GEMM2_GROUPS forces one value (wide tiles: <= 3)
         static int ng_env = env_int("B200_GEMM2_GROUPS", 0);
-        const int ng = ng_env ? std::max(2, std::min(3, ng_env)) : (umma2_tn(p.T) <= 64 ? 3 : 2);
+        const int ng = ng_env ? std::max(2, std::min(umma2_tn(p.T) <= 64 ? 4 : 3, ng_env)) : (umma2_tn(p.T) <= 64 ? 4 : 2);
         if (launches) *launches += (p.k_split && !p.tile_cnt) ? 2 : 1;
         return umma2_launch(gemm_encode_fn(), p, n_sm, 227 * 1024 - 2048, st, ng);
     }

@@ -593,7 +593,11 @@ inline cudaError_t umma2_launch(Umma2EncodeFn encode, const UmmaParams& p, int n
     if (!umma2_plan(p, smem_limit, pl, smem) || !umma2_encode_xmap(encode, &xmap, p, pl.x3d)) return cudaErrorInvalidValue;
     if (dbg & 16) pl.x3d = 0, umma2_encode_xmap_2d_only(encode, &xmap, p);
     const int tn = umma2_tn(p.T);
-    if (ng == 3) {
+    if (ng == 4 && tn <= 64 && pl.sa >= 4) {   // narrow token tiles only (the A ring must hold one stage per group)
+        if (tn == 32) return umma2_launch_tn<32, 4>(xmap, p, pl, smem, n_sm, st);
+        return umma2_launch_tn<64, 4>(xmap, p, pl, smem, n_sm, st);
+    }
+    if (ng >= 3) {
         if (tn == 32) return umma2_launch_tn<32, 3>(xmap, p, pl, smem, n_sm, st);
         if (tn == 64) return umma2_launch_tn<64, 3>(xmap, p, pl, smem, n_sm, st);
         if (tn == 128) return umma2_launch_tn<128, 3>(xmap, p, pl, smem, n_sm, st);
